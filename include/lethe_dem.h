@@ -1,0 +1,232 @@
+/* lethe_dem.h — C ABI of the B200-native DEM time-step engine.
+ *
+ * This is the drop-in boundary for the `lethe-particles` hot path of
+ * chaos-polymtl/lethe (reference citations are relative to /root/reference):
+ *
+ *   reference interface                                   replaced by
+ *   ----------------------------------------------------  ---------------------------
+ *   DEMSolver ctor + setup_parameters / factories          lethe_dem_create
+ *     (source/dem/dem.cc:32-58,60-138,196-281;
+ *      set_particle_particle_contact_force_model.cc:12-103;
+ *      set_particle_wall_contact_force_model.cc:12-…)
+ *   ParticleHandler insertion result (id, x, props[9])     lethe_dem_set_particles /
+ *     (source/dem/insertion.cc:60-121,                       lethe_dem_add_particles
+ *      include/core/dem_properties.h:54-76)
+ *   BoundaryCellsInformation::build                        lethe_dem_set_walls /
+ *     (find_boundary_cells_information.cc:26-94,130-219)     lethe_dem_set_floating_walls
+ *   DEM boundary conditions (rotational / translational)   lethe_dem_set_boundary_motion
+ *     (particle_wall_contact_force.cc:602-610,
+ *      particle_wall_contact_force.h:199-246)
+ *   one iteration of the `while (simulation_control->      lethe_dem_step
+ *     integrate())` loop: execute_contact_detection_and_
+ *     search + compute_contact_forces + integrate
+ *     (source/dem/dem.cc:1115-1183,598-717)
+ *   DEMSolver::synchronize_velocities (dem.cc:719-745)     lethe_dem_synchronize_velocities
+ *   DEMActionManager::particle_insertion_step /            lethe_dem_force_contact_search
+ *     restart_simulation (dem_action_manager.h:191-232)
+ *   report_statistics reductions (dem.cc:902-971)          lethe_dem_get_stats
+ *   print_xyz / VTU snapshot (dem.cc:760-770)              lethe_dem_get_particles
+ *
+ * All arithmetic is IEEE FP64; indices are 32-bit. Every function returns 0 on
+ * success and a negative code on error; lethe_dem_last_error() gives the text.
+ * There is no CPU fallback: creating a context without a CUDA device fails.
+ *
+ * The oracle (oracle/dem_oracle.cpp, test infrastructure only) exports the same
+ * functions with the prefix `oracle_dem_` and the same structs, so that parity
+ * tests drive both through identical calls.
+ */
+#ifndef LETHE_DEM_H
+#define LETHE_DEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LETHE_DEM_MAX_TYPES 5            /* parameters_lagrangian.h:325 */
+#define LETHE_DEM_MAX_FLOATING_WALLS 9   /* parameters_lagrangian.cc:1405-1575 */
+#define LETHE_DEM_MAX_BOUNDARY_MOTIONS 16
+#define LETHE_DEM_N_PROPERTIES 9         /* dem_properties.h:54-76 */
+#define LETHE_DEM_FLOATING_WALL_BOUNDARY_ID 100 /* particle_wall_fine_search.cc:150 */
+
+/* Parameters::Lagrangian::ParticleParticleContactForceModel
+ * (include/core/parameters_lagrangian.h:33-86) */
+enum lethe_pp_model {
+  LETHE_PP_LINEAR = 0,
+  LETHE_PP_HERTZ_MINDLIN_LIMIT_FORCE = 1,
+  LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP = 2,
+  LETHE_PP_HERTZ = 3,
+  LETHE_PP_HERTZ_JKR = 4,
+  LETHE_PP_DMT = 5
+};
+/* ParticleWallContactForceModel */
+enum lethe_pw_model {
+  LETHE_PW_LINEAR = 0,
+  LETHE_PW_NONLINEAR = 1,
+  LETHE_PW_JKR = 2,
+  LETHE_PW_DMT = 3
+};
+/* RollingResistanceMethod */
+enum lethe_rolling_model {
+  LETHE_ROLLING_NONE = 0,
+  LETHE_ROLLING_CONSTANT = 1,
+  LETHE_ROLLING_VISCOUS = 2,
+  LETHE_ROLLING_EPSD = 3
+};
+enum lethe_integrator { LETHE_INTEGRATOR_VELOCITY_VERLET = 0 };
+enum lethe_detection { LETHE_DETECTION_DYNAMIC = 0, LETHE_DETECTION_CONSTANT = 1 };
+/* Order in which the reference's FE mesh enumerates its active cells; it only
+ * fixes which particle of a pair is "particle one" (history sign) and the
+ * summation order of the oracle. 0: lexicographic (subdivided_hyper_rectangle),
+ * 1: hierarchical z-order (hyper_cube + refine_global). */
+enum lethe_cell_order { LETHE_CELL_ORDER_LEXICOGRAPHIC = 0, LETHE_CELL_ORDER_MORTON = 1 };
+
+typedef struct lethe_dem_config {
+  /* model selectors (`subsection model parameters`, parameters_lagrangian.cc:918-1337) */
+  int32_t pp_model;
+  int32_t pw_model;
+  int32_t rolling_model;
+  int32_t integrator;
+  int32_t detection;                   /* contact detection method */
+  int32_t contact_detection_frequency; /* `frequency` */
+  int32_t cell_order;                  /* enum lethe_cell_order */
+  int32_t store_forces;                /* debug tap: keep last-step F/T for lethe_dem_get_forces */
+  double dt;                           /* `time step` */
+  double g[3];                         /* `g` */
+  double neighborhood_threshold;       /* `neighborhood threshold` (1.3) */
+  double d_max;                        /* maximum_particle_diameter (dem.cc:149-159) */
+  /* min(minimal_cell_diameter - d_max/2, coeff*(thr-1)*d_max/2), dem.cc:289-294;
+   * computed by the host because it contains the FE mesh's minimal cell diameter. */
+  double smallest_contact_search_criterion;
+  double dmt_cut_off_threshold;        /* `dmt cut-off threshold` */
+  double f_coefficient_epsd;           /* `f coefficient` */
+  /* Test hook mirroring the reference's unit tests, which force MOI = 1
+   * (tests/dem/full_contact_functions.h:135-141). <= 0: MOI = 0.1 m d^2 (dem.cc:1004-1011). */
+  double moi_override;
+  /* `subsection lagrangian physical properties` raw tables; effective pair
+   * tables are derived with the reference formulas
+   * (particle_particle_contact_force.h:1639-1746, particle_wall_contact_force.cc:588-694) */
+  int32_t n_types;
+  /* `subsection restart / set restart`: a restarted run resumes with regular
+   * integrate() steps instead of integrate_start (dem.cc:1162-1171). */
+  int32_t restart;
+  double young[LETHE_DEM_MAX_TYPES];
+  double poisson[LETHE_DEM_MAX_TYPES];
+  double restitution[LETHE_DEM_MAX_TYPES];
+  double friction[LETHE_DEM_MAX_TYPES];
+  double rolling_friction[LETHE_DEM_MAX_TYPES];
+  double rolling_viscous_damping[LETHE_DEM_MAX_TYPES];
+  double surface_energy[LETHE_DEM_MAX_TYPES];
+  double hamaker[LETHE_DEM_MAX_TYPES];
+  double young_wall, poisson_wall, restitution_wall, friction_wall;
+  double rolling_friction_wall, rolling_viscous_damping_wall;
+  double surface_energy_wall, hamaker_wall;
+  /* The reference's FE mesh when it is a uniform hex grid (hyper_cube /
+   * subdivided_hyper_rectangle): particles are binned into these cells and
+   * candidates are particles in vertex-sharing cells (find_cell_neighbors.cc:10-104). */
+  double grid_lo[3];
+  double cell_size[3];
+  int32_t grid_n[3];
+  int32_t periodic[3];                 /* periodic direction flags (DEM boundary conditions) */
+  /* slab decomposition (multi-GPU): this context owns grid cells
+   * [slab_lo, slab_hi) along slab_axis; -1/0/0 = whole grid. */
+  int32_t slab_axis;
+  int32_t slab_lo;
+  int32_t slab_hi;
+  int32_t pad1;
+} lethe_dem_config;
+
+/* One row of boundary_cells_info_struct (include/dem/boundary_cells_info_struct.h:20-38):
+ * a boundary face of grid cell `cell` (lexicographic index ix + nx*(iy + ny*iz)),
+ * treated as an infinite plane through `point` with inward unit `normal`. */
+typedef struct lethe_wall_face {
+  int32_t cell;
+  uint32_t boundary_id;
+  uint32_t global_face_id;
+  uint32_t pad;
+  double normal[3];
+  double point[3];
+} lethe_wall_face;
+
+/* min / max / sum over particles, as printed by report_statistics (dem.cc:902-971) */
+typedef struct lethe_dem_stats {
+  uint64_t n_particles;
+  uint64_t n_rebuilds;          /* contact_build_number */
+  uint64_t n_steps;
+  uint64_t n_pair_entries;      /* unordered pairs in the contact list */
+  uint64_t n_wall_entries;
+  uint64_t n_pairs_touching;    /* pairs with overlap > threshold at the last step (store_forces) */
+  double v_min, v_max, v_sum;          /* |v| */
+  double omega_min, omega_max, omega_sum;
+  double ke_trans_min, ke_trans_max, ke_trans_sum;
+  double ke_rot_min, ke_rot_max, ke_rot_sum;
+} lethe_dem_stats;
+
+typedef struct lethe_dem_ctx lethe_dem_ctx;
+
+/* --- lifetime --- */
+int lethe_dem_create(const lethe_dem_config *config, int device, lethe_dem_ctx **out);
+void lethe_dem_destroy(lethe_dem_ctx *ctx);
+const char *lethe_dem_last_error(const lethe_dem_ctx *ctx);
+/* Text of the error of the last failed lethe_dem_create (no ctx exists then). */
+const char *lethe_dem_create_error(void);
+
+/* --- state in / out (host buffers; rows laid out exactly as PropertiesIndex) --- */
+int lethe_dem_set_particles(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id,
+                            const double *x3, const double *props9);
+int lethe_dem_add_particles(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id,
+                            const double *x3, const double *props9);
+int lethe_dem_n_particles(lethe_dem_ctx *ctx, uint64_t *n);
+/* Fills up to n_max rows sorted by particle id; *n_out = number written. */
+int lethe_dem_get_particles(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out,
+                            uint32_t *id, double *x3, double *props9);
+int lethe_dem_set_walls(lethe_dem_ctx *ctx, uint64_t n_faces, const lethe_wall_face *faces);
+int lethe_dem_set_floating_walls(lethe_dem_ctx *ctx, int32_t n, const double *point3,
+                                 const double *normal3, const double *t_start,
+                                 const double *t_end);
+int lethe_dem_set_boundary_motion(lethe_dem_ctx *ctx, uint32_t boundary_id,
+                                  const double translational_velocity[3],
+                                  double rotational_speed, const double rotational_vector[3],
+                                  const double point_on_rotation_axis[3]);
+
+/* --- the hot path --- */
+int lethe_dem_step(lethe_dem_ctx *ctx, uint64_t n_steps);
+int lethe_dem_synchronize_velocities(lethe_dem_ctx *ctx);
+int lethe_dem_force_contact_search(lethe_dem_ctx *ctx, int clear_tangential_displacement);
+/* Reference-facing per-step call with HOST buffers (what a patched DEMSolver
+ * that keeps ParticleHandler on the host would call every iteration): uploads
+ * x/props for the n particles (same ids as resident), runs n_steps, downloads
+ * the updated rows into the same buffers. Contact history stays resident. */
+int lethe_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
+                        const uint32_t *id, double *x3, double *props9);
+
+/* --- debug taps / statistics --- */
+/* Unordered pairs (i_id < j_id) of the contact list with the tangential
+ * displacement oriented i -> j. */
+int lethe_dem_get_pairs(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *i_id,
+                        uint32_t *j_id, double *tangential3);
+int lethe_dem_get_wall_contacts(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out,
+                                uint32_t *particle_id, uint32_t *face_id, double *tangential3);
+/* Force / torque applied to each particle in the last step (requires
+ * config.store_forces); rows sorted by particle id. */
+int lethe_dem_get_forces(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id,
+                         double *force3, double *torque3);
+int lethe_dem_get_stats(lethe_dem_ctx *ctx, lethe_dem_stats *stats);
+/* Device time (ms, CUDA events on the engine's stream) spent in the fused step
+ * kernel and in list rebuilds since the last call with reset != 0. */
+int lethe_dem_get_timers(lethe_dem_ctx *ctx, int reset, double *step_kernel_ms,
+                         uint64_t *step_kernel_launches, double *rebuild_ms,
+                         uint64_t *rebuild_launches);
+int lethe_dem_enable_timers(lethe_dem_ctx *ctx, int enable);
+
+/* --- multi-GPU (one ctx per GPU per process; slab decomposition) --- */
+#define LETHE_DEM_NCCL_ID_BYTES 128
+int lethe_dem_nccl_unique_id(uint8_t id[LETHE_DEM_NCCL_ID_BYTES]);
+int lethe_dem_comm_init(lethe_dem_ctx *ctx, int rank, int world_size,
+                        const uint8_t id[LETHE_DEM_NCCL_ID_BYTES]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LETHE_DEM_H */

@@ -1,0 +1,202 @@
+"""Host-side mirror of the reference's `DEMSolver` for the hot path
+(source/dem/dem.cc:1064-1267): parameter set-up, wall table, insertion, the time
+loop and the `test` output.  Everything per-step is delegated to the C ABI
+(`lethe_dem_step`); this module only decides *when* to call it, exactly like
+`DEMSolver::solve` around `execute_contact_detection_and_search` /
+`compute_contact_forces` / `integrate`.
+
+The insertion and output paths are host code in the reference too (north star:
+"Host code remains C++ (… the insertion and output paths)"); they are restated
+here in Python only so that the reference's application tests can be replayed.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import abi
+from .prm import DEMParameters, Mesh
+
+# boundary ids of a colorized hyper_cube / hyper_rectangle: 2*axis + side
+_FACE_NORMALS = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+
+
+def box_wall_faces(mesh: Mesh, outlet_boundaries=(), periodic=(0, 0, 0)):
+    """Rows of BoundaryCellsInformation::find_boundary_cells_information
+    (source/dem/find_boundary_cells_information.cc:130-219) for a uniform box
+    mesh: one row per (boundary cell, boundary face) that is neither an outlet
+    nor periodic; inward normal, face centre as point."""
+    nx, ny, nz = mesh.n
+    h = mesh.cell_size
+    faces = []
+    n = (nx, ny, nz)
+    fid = 0
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                idx = (i, j, k)
+                cell = i + nx * (j + ny * k)
+                for axis in range(3):
+                    for side in (0, 1):
+                        if idx[axis] != (0 if side == 0 else n[axis] - 1):
+                            continue
+                        face_no = 2 * axis + side
+                        bid = face_no if mesh.colorize else 0
+                        unique = cell * 6 + face_no
+                        if periodic[axis] or bid in outlet_boundaries:
+                            continue
+                        f = abi.WallFace()
+                        f.cell = cell
+                        f.boundary_id = bid
+                        f.global_face_id = unique
+                        nrm = _FACE_NORMALS[face_no]
+                        f.normal[:] = [float(v) for v in nrm]
+                        centre = [mesh.lo[d] + (idx[d] + 0.5) * h[d] for d in range(3)]
+                        centre[axis] = mesh.lo[axis] if side == 0 else mesh.hi[axis]
+                        f.point[:] = centre
+                        faces.append(f)
+                        fid += 1
+    return faces
+
+
+_libc = None
+
+
+def _glibc_rand_container(n: int, maximum_range: float, seed: int):
+    """create_random_number_container (include/core/utilities.h:1061-1073): one
+    srand(seed*(i+1)) + rand() per element — glibc's generator."""
+    global _libc
+    if _libc is None:
+        _libc = ctypes.CDLL("libc.so.6")
+        _libc.rand.restype = ctypes.c_int
+        _libc.srand.argtypes = [ctypes.c_uint]
+    RAND_MAX = 2147483647
+    out = np.empty(n)
+    for i in range(n):
+        _libc.srand(ctypes.c_uint((seed * (i + 1)) & 0xFFFFFFFF))
+        out[i] = (float(_libc.rand()) / float(RAND_MAX)) * maximum_range
+    return out
+
+
+def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particle_type: int = 0):
+    """InsertionVolume::insert / find_insertion_location
+    (source/dem/insertion_volume.cc:43-206) + assign_particle_properties
+    (source/dem/insertion.cc:60-121) on one rank, uniform size distribution."""
+    ins = p.insertion
+    d_max = p.d_max
+    t = p.particle_types[particle_type]
+    if t.size_distribution_type != "uniform":
+        raise abi.DEMError("volume_insertion replay supports the uniform size distribution only")
+    n_dir = [0, 0, 0]
+    for axis in ins.direction_sequence:
+        n_dir[axis] = int((ins.box_point_2[axis] - ins.box_point_1[axis]) / (ins.distance_threshold * d_max))
+    n_sites = n_dir[0] * n_dir[1] * n_dir[2]
+    n_insert = min(n_insert, n_sites)
+    rnd = _glibc_rand_container(n_sites, ins.maximum_offset, ins.seed)
+    a0, a1, a2 = ins.direction_sequence
+    x = np.empty((n_insert, 3))
+    for k in range(n_insert):
+        r1, r2 = rnd[k], rnd[n_sites - k - 1]
+        i0 = k % n_dir[a0]
+        i1 = (k % (n_dir[a0] * n_dir[a1])) // n_dir[a0]
+        i2 = k // (n_dir[a0] * n_dir[a1])
+        x[k, a0] = ins.box_point_1[a0] + ((i0 + 0.5) * ins.distance_threshold - r1) * d_max
+        x[k, a1] = ins.box_point_1[a1] + ((i1 + 0.5) * ins.distance_threshold - r2) * d_max
+        x[k, a2] = ins.box_point_1[a2] + ((i2 + 0.5) * ins.distance_threshold - r1) * d_max
+    props = np.zeros((n_insert, abi.N_PROPERTIES))
+    d = abs(t.diameter)
+    h = d * 0.5
+    props[:, 0] = particle_type
+    props[:, 1] = d
+    props[:, 2] = t.density * 4.0 / 3.0 * math.pi * (h * h * h)
+    props[:, 3:6] = ins.initial_velocity
+    props[:, 6:9] = ins.initial_omega
+    ids = np.arange(first_id, first_id + n_insert, dtype=np.uint32)
+    return ids, x, props
+
+
+class DEMSolver:
+    """`DEMSolver<3, DEMProperties>` with the hot path behind the C ABI."""
+
+    def __init__(self, parameters: DEMParameters, engine_factory=None, device: int = 0, store_forces=False, moi_override=0.0):
+        self.parameters = parameters
+        self.config = parameters.to_config(store_forces=store_forces, moi_override=moi_override)
+        factory = engine_factory or (lambda cfg: abi.load_engine(cfg, device))
+        self.engine = factory(self.config)
+        self.iteration_number = 0
+        self.current_time = 0.0
+        self._remaining = [t.number for t in parameters.particle_types]
+        self._current_type = 0
+        self._next_id = 0
+        self._setup_boundaries()
+
+    # DEMSolver::setup_functions_and_pointers / boundary_cell_object.build
+    def _setup_boundaries(self):
+        p = self.parameters
+        if p.mesh.expand_particle_wall_contact_search:
+            raise abi.DEMError("`expand particle-wall contact search` is not on the B200 path (box meshes do not need it)")
+        self.engine.set_walls(box_wall_faces(p.mesh, p.outlet_boundaries, p.periodic))
+        if p.floating_walls:
+            pts, nrm, t0, t1 = zip(*p.floating_walls)
+            self.engine.set_floating_walls(pts, nrm, t0, t1)
+        for bc in p.boundary_conditions:
+            if bc.type == "rotational":
+                self.engine.set_boundary_motion(bc.boundary_id, (0, 0, 0), bc.rotational_speed, bc.rotational_vector, bc.point_on_rotational_vector)
+            elif bc.type == "translational":
+                self.engine.set_boundary_motion(bc.boundary_id, bc.translational_velocity, 0.0, (0, 0, 0), (0, 0, 0))
+
+    # DEMSolver::insert_particles (dem.cc:484-506)
+    def _insertion_due(self) -> bool:
+        ins = self.parameters.insertion
+        if ins.frequency == 0:
+            return False
+        return (self.iteration_number % ins.frequency) == 1 or self.iteration_number == 1
+
+    def _insert(self):
+        p = self.parameters
+        if self._remaining[self._current_type] == 0 and self._current_type != len(p.particle_types) - 1:
+            self._current_type += 1
+        remaining = self._remaining[self._current_type]
+        if remaining == 0:
+            return
+        n = min(p.insertion.inserted_this_step, remaining)
+        ids, x, props = volume_insertion(p, n, self._next_id, self._current_type)
+        self.engine.add_particles(ids, x, props)
+        self._next_id += len(ids)
+        self._remaining[self._current_type] -= len(ids)
+
+    def _is_at_end(self) -> bool:
+        # SimulationControlTransient::is_at_end (simulation_control.cc:371-378)
+        p = self.parameters
+        margin = max(1e-6 * p.time_step, 1e-12 * p.time_end)
+        return self.current_time >= (p.time_end - margin)
+
+    def solve(self, max_steps=None):
+        """The `while (simulation_control->integrate())` loop + closing half step."""
+        pending = 0
+        steps = 0
+        while not self._is_at_end() and (max_steps is None or steps < max_steps):
+            self.iteration_number += 1
+            self.current_time += self.parameters.time_step
+            steps += 1
+            if self._insertion_due() and any(self._remaining):
+                # the insertion belongs to this iteration: flush earlier ones first
+                if pending:
+                    self.engine.step(pending)
+                    pending = 0
+                self._insert()
+            pending += 1
+        if pending:
+            self.engine.step(pending)
+        self.engine.synchronize_velocities()
+        return self.engine.get_particles()
+
+    def test_output(self) -> str:
+        """finish_simulation with `subsection test / enable = true` (dem.cc:760-770)."""
+        ids, x, props = self.engine.get_particles()
+        lines = ["id, type, dp, x, y, z "]
+        for i in range(len(ids)):
+            lines.append(f"{ids[i]} {int(props[i, 0])} {props[i, 1]:.5f} {x[i, 0]:.4f} {x[i, 1]:.4f} {x[i, 2]:.4f}")
+        return "\n".join(lines)

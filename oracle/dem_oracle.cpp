@@ -1,0 +1,2061 @@
+// dem_oracle.cpp — CPU restatement of lethe-particles' DEM time step.
+//
+// TEST INFRASTRUCTURE ONLY. This file is the parity oracle for the CUDA engine
+// in lethe_b200/csrc. Nothing in the product path may include, link or call it;
+// only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs use it.
+//
+// It restates, on plain arrays and without deal.II, the algorithm of the
+// reference (citations relative to /root/reference). Parity is PINNED: the
+// restatement reproduces the reference's own golden outputs
+// (tests/dem/*.output, applications_tests/lethe-particles/packing_in_box*.output),
+// see tests/test_oracle_golden.py and tests/golden/.
+//
+// Arithmetic rules that matter for the last bits:
+//  * deal.II Tensor<1,3> / scalar multiplies by the reciprocal (inv = 1/s);
+//  * dot products and squared norms are summed in component order;
+//  * no FMA contraction (compile with -ffp-contract=off);
+//  * the reference's constants are kept verbatim (0.66665, 1.8257, 1.3333, 9.8696).
+//
+// Container semantics: the reference keeps candidates and adjacency lists in
+// ankerl::unordered_dense maps (insertion-ordered, erase = move last element into
+// the hole). DenseRows below mimics that so that iteration order, and hence the
+// floating-point summation order, is reference-like.
+
+#include "../include/lethe_dem.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace
+{
+  struct V3
+  {
+    double v[3];
+    double &operator[](int i) { return v[i]; }
+    const double &operator[](int i) const { return v[i]; }
+  };
+  inline V3 mk(double a, double b, double c) { return V3{{a, b, c}}; }
+  inline V3 operator+(const V3 &a, const V3 &b) { return mk(a[0] + b[0], a[1] + b[1], a[2] + b[2]); }
+  inline V3 operator-(const V3 &a, const V3 &b) { return mk(a[0] - b[0], a[1] - b[1], a[2] - b[2]); }
+  inline V3 operator-(const V3 &a) { return mk(-a[0], -a[1], -a[2]); }
+  inline V3 operator*(double s, const V3 &a) { return mk(s * a[0], s * a[1], s * a[2]); }
+  inline V3 operator*(const V3 &a, double s) { return mk(a[0] * s, a[1] * s, a[2] * s); }
+  // deal.II Tensor::operator/= for floating point: multiply by the reciprocal.
+  inline V3 operator/(const V3 &a, double s)
+  {
+    const double inv = 1.0 / s;
+    return mk(a[0] * inv, a[1] * inv, a[2] * inv);
+  }
+  inline double dot(const V3 &a, const V3 &b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+  inline double norm_square(const V3 &a) { return (a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]; }
+  inline double norm(const V3 &a) { return std::sqrt(norm_square(a)); }
+  inline V3 cross(const V3 &a, const V3 &b)
+  {
+    return mk(a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]);
+  }
+  inline double distance_square(const V3 &a, const V3 &b)
+  {
+    double sum = 0.0;
+    for (int i = 0; i < 3; ++i)
+      {
+        const double diff = a[i] - b[i];
+        sum += diff * diff;
+      }
+    return sum;
+  }
+  inline double sq(double x) { return x * x; }
+  inline double cube(double x) { return x * x * x; } // Utilities::fixed_power<3>: x * x^2 == x*x*x? see note
+
+  // include/core/auxiliary_math_functions.h:17-22
+  inline double harmonic_mean(double a, double b) { return (2 * a * b / (a + b + DBL_MIN)); }
+
+  enum Prop { P_TYPE = 0, P_DP = 1, P_MASS = 2, P_VX = 3, P_VY = 4, P_VZ = 5, P_WX = 6, P_WY = 7, P_WZ = 8 };
+
+  struct Particle
+  {
+    uint32_t id;
+    V3 x;
+    double p[9];
+    int cell; // lexicographic grid cell the particle is registered in (last sort)
+  };
+
+  struct PPInfo
+  {
+    uint32_t two;
+    V3 tangential_displacement;
+    V3 rolling_resistance_spring_torque;
+    V3 periodic_offset;
+  };
+  struct PPRow
+  {
+    uint32_t one;
+    std::vector<PPInfo> second;
+  };
+  struct PWInfo
+  {
+    uint32_t face; // global_face_id or floating wall id
+    V3 normal;
+    V3 point;
+    uint32_t boundary_id;
+    V3 tangential_displacement;
+    V3 rolling_resistance_spring_torque;
+  };
+  struct PWRow
+  {
+    uint32_t one;
+    std::vector<PWInfo> second;
+  };
+  struct CandRow
+  {
+    uint32_t one;
+    std::vector<uint32_t> c;
+  };
+  struct WCand
+  {
+    uint32_t face;
+    V3 normal;
+    V3 point;
+    uint32_t boundary_id;
+  };
+  struct WCandRow
+  {
+    uint32_t one;
+    std::vector<WCand> c;
+  };
+
+  // Insertion-ordered map id -> row with ankerl-style erase.
+  template <class Row> struct DenseRows
+  {
+    std::vector<Row> rows;
+    std::vector<int> pos; // id -> index in rows, -1 if absent
+    void clear()
+    {
+      for (auto &r : rows)
+        pos[r.one] = -1;
+      rows.clear();
+    }
+    void ensure(uint32_t id)
+    {
+      if (pos.size() <= id)
+        pos.resize(size_t(id) + 1, -1);
+    }
+    Row *find(uint32_t id)
+    {
+      if (id >= pos.size() || pos[id] < 0)
+        return nullptr;
+      return &rows[pos[id]];
+    }
+    Row &get_or_create(uint32_t id)
+    {
+      ensure(id);
+      if (pos[id] < 0)
+        {
+          pos[id] = int(rows.size());
+          rows.emplace_back();
+          rows.back().one = id;
+        }
+      return rows[pos[id]];
+    }
+    // erase row index r; the last row moves into the hole (ankerl do_erase)
+    void erase_at(size_t r)
+    {
+      pos[rows[r].one] = -1;
+      if (r + 1 != rows.size())
+        {
+          rows[r] = std::move(rows.back());
+          pos[rows[r].one] = int(r);
+        }
+      rows.pop_back();
+    }
+  };
+  template <class T> inline void swap_erase(std::vector<T> &v, size_t k)
+  {
+    if (k + 1 != v.size())
+      v[k] = std::move(v.back());
+    v.pop_back();
+  }
+
+  struct BoundaryMotion
+  {
+    uint32_t boundary_id;
+    V3 translational_velocity;
+    double rotational_speed;
+    V3 rotational_vector;
+    V3 point_on_axis;
+  };
+
+  struct Oracle
+  {
+    lethe_dem_config cfg;
+    std::string error;
+
+    // grid
+    int nx, ny, nz, n_cells;
+    std::vector<int> cell_of_rank; // active-cell order -> lexicographic index
+    std::vector<int> rank_of_cell;
+    std::vector<std::vector<int>> cells_local_neighbor_list;          // [cell, n0, n1, ...] lexicographic ids
+    std::vector<std::vector<int>> cells_local_periodic_neighbor_list; // [main, pn0, ...]
+    std::vector<V3> combined_periodic_offsets;
+    bool periodic_enabled;
+
+    // particles
+    std::vector<Particle> parts;               // iteration (= local index) order
+    std::vector<std::vector<int>> cell_parts;  // per lexicographic cell: local indices in order
+    std::vector<int> slot_of_id;               // particle_container
+    std::vector<V3> force, torque;
+    std::vector<double> displacement, MOI;
+    std::vector<V3> last_force, last_torque;
+
+    // contact containers
+    DenseRows<CandRow> local_candidates, periodic_candidates;
+    DenseRows<PPRow> local_adjacent, periodic_adjacent;
+    DenseRows<WCandRow> wall_candidates, fwall_candidates;
+    DenseRows<PWRow> wall_in_contact, fwall_in_contact;
+
+    // walls
+    std::vector<lethe_wall_face> faces;
+    std::vector<std::vector<int>> cell_faces; // per cell: indices into faces (in table order)
+    int n_floating;
+    V3 fw_point[LETHE_DEM_MAX_FLOATING_WALLS], fw_normal[LETHE_DEM_MAX_FLOATING_WALLS];
+    double fw_t0[LETHE_DEM_MAX_FLOATING_WALLS], fw_t1[LETHE_DEM_MAX_FLOATING_WALLS];
+    std::vector<std::vector<int>> fw_cells; // per floating wall: boundary cells (rank order)
+    std::vector<BoundaryMotion> motions;
+
+    // effective properties
+    int n_types;
+    std::vector<double> eY, eG, eRest, eMu, eRollVisc, eRollFric, eGamma, eHamaker, beta;
+    std::vector<double> wY, wG, wRest, wMu, wRollVisc, wRollFric, wGamma, wHamaker, wbeta;
+    double neighborhood_threshold_squared;
+    double pp_force_threshold, pw_force_threshold;
+
+    // time / triggers (DEMActionManager, dem_action_manager.h:395-412)
+    uint64_t iteration_number;
+    double current_time;
+    bool contact_search_trigger;
+    bool clear_tangential_displacement_trigger;
+    uint64_t contact_build_number;
+    uint64_t n_touching_last;
+  };
+
+  // ---------------------------------------------------------------- grid ----
+  inline int lin(const Oracle &o, int i, int j, int k) { return i + o.nx * (j + o.ny * k); }
+
+  void build_cell_order(Oracle &o)
+  {
+    o.cell_of_rank.clear();
+    o.rank_of_cell.assign(o.n_cells, -1);
+    if (o.cfg.cell_order == LETHE_CELL_ORDER_MORTON)
+      {
+        // hyper_cube + refine_global: children of a hex are visited x-fastest,
+        // recursively, i.e. Morton order with x the lowest bit.
+        int nmax = std::max(o.nx, std::max(o.ny, o.nz));
+        int bits = 0;
+        while ((1 << bits) < nmax)
+          ++bits;
+        const uint64_t total = uint64_t(1) << (3 * bits);
+        for (uint64_t m = 0; m < total; ++m)
+          {
+            int i = 0, j = 0, k = 0;
+            for (int b = 0; b < bits; ++b)
+              {
+                i |= int((m >> (3 * b)) & 1) << b;
+                j |= int((m >> (3 * b + 1)) & 1) << b;
+                k |= int((m >> (3 * b + 2)) & 1) << b;
+              }
+            if (i < o.nx && j < o.ny && k < o.nz)
+              o.cell_of_rank.push_back(lin(o, i, j, k));
+          }
+      }
+    else
+      {
+        for (int c = 0; c < o.n_cells; ++c)
+          o.cell_of_rank.push_back(c);
+      }
+    for (int r = 0; r < o.n_cells; ++r)
+      o.rank_of_cell[o.cell_of_rank[r]] = r;
+  }
+
+  // cells touching lattice vertex (vi,vj,vk), sorted by active-cell rank
+  // (GridTools::vertex_to_cell_map gives a std::set of cell iterators)
+  void cells_at_vertex(const Oracle &o, int vi, int vj, int vk, std::vector<int> &out)
+  {
+    out.clear();
+    for (int dk = -1; dk <= 0; ++dk)
+      for (int dj = -1; dj <= 0; ++dj)
+        for (int di = -1; di <= 0; ++di)
+          {
+            int i = vi + di, j = vj + dj, k = vk + dk;
+            if (i < 0 || j < 0 || k < 0 || i >= o.nx || j >= o.ny || k >= o.nz)
+              continue;
+            out.push_back(lin(o, i, j, k));
+          }
+    std::sort(out.begin(), out.end(), [&](int a, int b) { return o.rank_of_cell[a] < o.rank_of_cell[b]; });
+  }
+
+  // find_cell_neighbors<dim,false> (source/dem/find_cell_neighbors.cc:10-104), one rank
+  void find_cell_neighbors(Oracle &o)
+  {
+    o.cells_local_neighbor_list.clear();
+    std::vector<char> total_cell_list(o.n_cells, 0);
+    std::vector<int> vcells;
+    for (int r = 0; r < o.n_cells; ++r)
+      {
+        const int cell = o.cell_of_rank[r];
+        const int ci = cell % o.nx, cj = (cell / o.nx) % o.ny, ck = cell / (o.nx * o.ny);
+        std::vector<int> local_neighbor_vector;
+        local_neighbor_vector.push_back(cell);
+        total_cell_list[cell] = 1;
+        for (int vertex = 0; vertex < 8; ++vertex) // deal.II hex vertex v = i + 2j + 4k
+          {
+            cells_at_vertex(o, ci + (vertex & 1), cj + ((vertex >> 1) & 1), ck + ((vertex >> 2) & 1), vcells);
+            for (int neighbor : vcells)
+              {
+                if (total_cell_list[neighbor])
+                  continue;
+                if (std::find(local_neighbor_vector.begin(), local_neighbor_vector.end(), neighbor) !=
+                    local_neighbor_vector.end())
+                  continue;
+                local_neighbor_vector.push_back(neighbor);
+              }
+          }
+        o.cells_local_neighbor_list.push_back(local_neighbor_vector);
+      }
+  }
+
+  // find_cell_periodic_neighbors (find_cell_neighbors.cc:104-275) + get_periodic_neighbor_list
+  // (:337-378), one rank. Main cells are the cells with a face on periodic boundary 0
+  // (the low face of each periodic direction); they are visited in active-cell order.
+  void find_cell_periodic_neighbors(Oracle &o)
+  {
+    o.cells_local_periodic_neighbor_list.clear();
+    if (!o.periodic_enabled)
+      return;
+    const int n[3] = {o.nx, o.ny, o.nz};
+    std::vector<char> total_cell_list(o.n_cells, 0);
+    std::vector<int> vcells;
+    for (int r = 0; r < o.n_cells; ++r)
+      {
+        const int cell = o.cell_of_rank[r];
+        const int c[3] = {cell % o.nx, (cell / o.nx) % o.ny, cell / (o.nx * o.ny)};
+        bool on_pb0 = false;
+        for (int d = 0; d < 3; ++d)
+          if (o.cfg.periodic[d] && c[d] == 0)
+            on_pb0 = true;
+        if (!on_pb0)
+          continue;
+        std::vector<int> vec;
+        vec.push_back(cell);
+        total_cell_list[cell] = 1;
+        std::vector<int> periodic_neighbor_list;
+        for (int vertex = 0; vertex < 8; ++vertex)
+          {
+            const int v[3] = {c[0] + (vertex & 1), c[1] + ((vertex >> 1) & 1), c[2] + ((vertex >> 2) & 1)};
+            // coinciding vertices: every combination of periodic images, ascending vertex id
+            std::vector<int> alt[3];
+            for (int d = 0; d < 3; ++d)
+              {
+                alt[d].push_back(v[d]);
+                if (o.cfg.periodic[d] && (v[d] == 0 || v[d] == n[d]))
+                  alt[d].push_back(v[d] == 0 ? n[d] : 0);
+                std::sort(alt[d].begin(), alt[d].end());
+              }
+            if (alt[0].size() * alt[1].size() * alt[2].size() == 1)
+              continue;
+            for (int wk : alt[2])
+              for (int wj : alt[1])
+                for (int wi : alt[0])
+                  {
+                    if (wi == v[0] && wj == v[1] && wk == v[2])
+                      continue;
+                    cells_at_vertex(o, wi, wj, wk, vcells);
+                    for (int nb : vcells)
+                      periodic_neighbor_list.push_back(nb);
+                  }
+          }
+        for (int nb : periodic_neighbor_list)
+          {
+            if (total_cell_list[nb])
+              continue;
+            if (std::find(vec.begin(), vec.end(), nb) != vec.end())
+              continue;
+            vec.push_back(nb);
+          }
+        o.cells_local_periodic_neighbor_list.push_back(vec);
+      }
+  }
+
+  // PeriodicBoundariesManipulator::compute_combined_periodic_offsets
+  // (periodic_boundaries_manipulator.cc:229-263); offsets point from pb0 to pb1.
+  void compute_combined_periodic_offsets(Oracle &o)
+  {
+    o.combined_periodic_offsets.clear();
+    const int n[3] = {o.nx, o.ny, o.nz};
+    for (int d = 0; d < 3; ++d)
+      {
+        if (!o.cfg.periodic[d])
+          continue;
+        V3 offset = mk(0, 0, 0);
+        // point_on_periodic_face[d] - point_on_face[d] = hi - lo
+        offset[d] = (o.cfg.grid_lo[d] + n[d] * o.cfg.cell_size[d]) - o.cfg.grid_lo[d];
+        size_t current_size = o.combined_periodic_offsets.size();
+        if (current_size == 0)
+          {
+            o.combined_periodic_offsets.push_back(offset);
+            o.combined_periodic_offsets.push_back(-offset);
+          }
+        else
+          {
+            o.combined_periodic_offsets.push_back(offset);
+            o.combined_periodic_offsets.push_back(-offset);
+            for (size_t i = 0; i < current_size; ++i)
+              {
+                o.combined_periodic_offsets.push_back(o.combined_periodic_offsets[i] + offset);
+                o.combined_periodic_offsets.push_back(o.combined_periodic_offsets[i] - offset);
+              }
+          }
+      }
+  }
+
+  // --------------------------------------------------- effective properties --
+  // ParticleParticleContactForce::set_effective_properties (…contact_force.h:1639-1746)
+  // ParticleWallContactForce::set_effective_properties (…wall_contact_force.cc:588-694)
+  void set_effective_properties(Oracle &o)
+  {
+    const lethe_dem_config &c = o.cfg;
+    const int n = c.n_types;
+    o.n_types = n;
+    for (auto *v : {&o.eY, &o.eG, &o.eRest, &o.eMu, &o.eRollVisc, &o.eRollFric, &o.eGamma, &o.eHamaker, &o.beta})
+      v->assign(size_t(n) * n, 0.0);
+    for (auto *v : {&o.wY, &o.wG, &o.wRest, &o.wMu, &o.wRollVisc, &o.wRollFric, &o.wGamma, &o.wHamaker, &o.wbeta})
+      v->assign(size_t(n), 0.0);
+    for (int i = 0; i < n; ++i)
+      {
+        const double Yi = c.young[i], nui = c.poisson[i];
+        for (int j = 0; j < n; ++j)
+          {
+            const int k = i * n + j;
+            const double Yj = c.young[j], nuj = c.poisson[j];
+            o.eY[k] = (Yi * Yj) / ((Yj * (1.0 - nui * nui)) + (Yi * (1.0 - nuj * nuj)) + DBL_MIN);
+            o.eG[k] = (Yi * Yj) / (2.0 * ((Yj * (2.0 - nui) * (1.0 + nui)) + (Yi * (2.0 - nuj) * (1.0 + nuj))) + DBL_MIN);
+            o.eRest[k] = harmonic_mean(c.restitution[i], c.restitution[j]);
+            o.eMu[k] = harmonic_mean(c.friction[i], c.friction[j]);
+            o.eRollVisc[k] = harmonic_mean(c.rolling_viscous_damping[i], c.rolling_viscous_damping[j]);
+            o.eRollFric[k] = harmonic_mean(c.rolling_friction[i], c.rolling_friction[j]);
+            o.eGamma[k] = c.surface_energy[i] + c.surface_energy[j] -
+                          std::pow(std::sqrt(c.surface_energy[i]) - std::sqrt(c.surface_energy[j]), 2);
+            o.eHamaker[k] = 0.5 * (c.hamaker[i] + c.hamaker[j]);
+            const double lg = std::log(o.eRest[k]);
+            o.beta[k] = lg / std::sqrt(lg * lg + 9.8696);
+          }
+        const double Yw = c.young_wall, nuw = c.poisson_wall;
+        o.wY[i] = (Yi * Yw) / (Yw * (1. - nui * nui) + Yi * (1. - nuw * nuw) + DBL_MIN);
+        o.wG[i] = (Yi * Yw) / ((2. * Yw * (2. - nui) * (1. + nui)) + (2. * Yi * (2. - nuw) * (1. + nuw)) + DBL_MIN);
+        o.wRest[i] = harmonic_mean(c.restitution[i], c.restitution_wall);
+        o.wMu[i] = harmonic_mean(c.friction[i], c.friction_wall);
+        o.wRollFric[i] = harmonic_mean(c.rolling_friction[i], c.rolling_friction_wall);
+        o.wRollVisc[i] = harmonic_mean(c.rolling_viscous_damping[i], c.rolling_viscous_damping_wall);
+        o.wGamma[i] = c.surface_energy[i] + c.surface_energy_wall -
+                      std::pow(std::sqrt(c.surface_energy[i]) - std::sqrt(c.surface_energy_wall), 2);
+        o.wHamaker[i] = 0.5 * (c.hamaker[i] + c.hamaker_wall);
+        const double lg = std::log(o.wRest[i]);
+        o.wbeta[i] = lg / std::sqrt((lg * lg) + 9.8696);
+      }
+    // get_force_calculation_threshold_distance (…contact_force.h:504-529, wall .h equivalent)
+    o.pp_force_threshold = 0.;
+    if (c.pp_model == LETHE_PP_DMT)
+      {
+        const double maxA = *std::max_element(o.eHamaker.begin(), o.eHamaker.end());
+        const double minG = *std::min_element(o.eGamma.begin(), o.eGamma.end());
+        o.pp_force_threshold = -std::sqrt(maxA / (12. * M_PI * minG * c.dmt_cut_off_threshold));
+      }
+    o.pw_force_threshold = 0.;
+    if (c.pw_model == LETHE_PW_DMT)
+      {
+        const double maxA = *std::max_element(o.wHamaker.begin(), o.wHamaker.end());
+        const double minG = *std::min_element(o.wGamma.begin(), o.wGamma.end());
+        o.pw_force_threshold = -std::sqrt(maxA / (12. * M_PI * minG * c.dmt_cut_off_threshold));
+      }
+    // dem.cc:156-159
+    o.neighborhood_threshold_squared = std::pow(c.neighborhood_threshold * c.d_max, 2);
+  }
+
+  // -------------------------------------------------------------- sorting ----
+  inline int cell_of_point(const Oracle &o, const V3 &x)
+  {
+    int idx[3];
+    const int n[3] = {o.nx, o.ny, o.nz};
+    for (int d = 0; d < 3; ++d)
+      {
+        const double r = (x[d] - o.cfg.grid_lo[d]) / o.cfg.cell_size[d];
+        const double f = std::floor(r);
+        if (!(f >= 0.0) || !(f < double(n[d])))
+          return -1; // left the triangulation: deal.II drops the particle
+        idx[d] = int(f);
+      }
+    return lin(o, idx[0], idx[1], idx[2]);
+  }
+
+  // PeriodicBoundariesManipulator::execute_particles_displacement + check_and_move_particles
+  // (periodic_boundaries_manipulator.cc:145-224,266-338): particles registered in a cell on
+  // a periodic face that are on or beyond that face are translated by +-offset.
+  void execute_particles_displacement(Oracle &o)
+  {
+    if (!o.periodic_enabled)
+      return;
+    const int n[3] = {o.nx, o.ny, o.nz};
+    for (auto &p : o.parts)
+      {
+        if (p.cell < 0)
+          continue;
+        const int c[3] = {p.cell % o.nx, (p.cell / o.nx) % o.ny, p.cell / (o.nx * o.ny)};
+        for (int d = 0; d < 3; ++d)
+          {
+            if (!o.cfg.periodic[d])
+              continue;
+            const double lo = o.cfg.grid_lo[d];
+            const double hi = o.cfg.grid_lo[d] + n[d] * o.cfg.cell_size[d];
+            const double offset = hi - lo;
+            if (c[d] == 0)
+              {
+                // pb0 cell: outward normal -e_d, point on face lo
+                const double distance_with_face = (p.x[d] - lo) * -1.0;
+                if (distance_with_face >= 0.0)
+                  p.x[d] += offset;
+              }
+            if (c[d] == n[d] - 1)
+              {
+                const double distance_with_face = (p.x[d] - hi) * 1.0;
+                if (distance_with_face >= 0.0)
+                  p.x[d] += -offset;
+              }
+          }
+      }
+  }
+
+  // DEMSolver::sort_particles_into_subdomains_and_cells (dem.cc:982-1016)
+  void sort_particles_into_subdomains_and_cells(Oracle &o)
+  {
+    std::vector<std::vector<int>> new_cells(o.n_cells);
+    std::vector<char> lost(o.parts.size(), 0);
+    // visit in the current iteration order (cell by cell)
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      {
+        const int c = cell_of_point(o, o.parts[s].x);
+        if (c < 0)
+          lost[s] = 1;
+        else
+          new_cells[c].push_back(int(s));
+      }
+    std::vector<Particle> np;
+    np.reserve(o.parts.size());
+    o.cell_parts.assign(o.n_cells, std::vector<int>());
+    for (int r = 0; r < o.n_cells; ++r)
+      {
+        const int c = o.cell_of_rank[r];
+        for (int s : new_cells[c])
+          {
+            o.cell_parts[c].push_back(int(np.size()));
+            np.push_back(o.parts[s]);
+            np.back().cell = c;
+          }
+      }
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      if (lost[s] && o.parts[s].id < o.slot_of_id.size())
+        o.slot_of_id[o.parts[s].id] = -1;
+    o.parts.swap(np);
+    const size_t n = o.parts.size();
+    o.force.assign(n, mk(0, 0, 0));
+    o.torque.assign(n, mk(0, 0, 0));
+    o.MOI.resize(n);
+    for (size_t s = 0; s < n; ++s)
+      {
+        const double *p = o.parts[s].p;
+        o.MOI[s] = o.cfg.moi_override > 0 ? o.cfg.moi_override : 0.1 * p[P_MASS] * p[P_DP] * p[P_DP];
+      }
+    o.displacement.assign(n, 0.);
+  }
+
+  // update_particle_container (update_local_particle_containers.cc:11-38)
+  void update_particle_container(Oracle &o)
+  {
+    std::fill(o.slot_of_id.begin(), o.slot_of_id.end(), -1);
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      {
+        const uint32_t id = o.parts[s].id;
+        if (o.slot_of_id.size() <= id)
+          o.slot_of_id.resize(size_t(id) + 1, -1);
+        o.slot_of_id[id] = int(s);
+      }
+  }
+  inline int slot(const Oracle &o, uint32_t id) { return id < o.slot_of_id.size() ? o.slot_of_id[id] : -1; }
+
+  // ---------------------------------------------------------- broad search ---
+  // store_candidates (particle_particle_broad_search.cc:735-766)
+  inline void store_candidates(Oracle &o, DenseRows<CandRow> &cand, uint32_t main_id, const std::vector<int> &cellp,
+                               size_t begin)
+  {
+    CandRow &row = cand.get_or_create(main_id);
+    for (size_t k = begin; k < cellp.size(); ++k)
+      row.c.push_back(o.parts[cellp[k]].id);
+  }
+
+  // find_particle_particle_contact_pairs (particle_particle_broad_search.cc:9-132), local part
+  void find_particle_particle_contact_pairs(Oracle &o)
+  {
+    o.local_candidates.clear();
+    for (const auto &list : o.cells_local_neighbor_list)
+      {
+        const std::vector<int> &main = o.cell_parts[list[0]];
+        if (main.empty())
+          continue;
+        for (size_t a = 0; a < main.size(); ++a)
+          store_candidates(o, o.local_candidates, o.parts[main[a]].id, main, a + 1);
+        for (size_t nb = 1; nb < list.size(); ++nb)
+          {
+            const std::vector<int> &other = o.cell_parts[list[nb]];
+            for (size_t a = 0; a < main.size(); ++a)
+              store_candidates(o, o.local_candidates, o.parts[main[a]].id, other, 0);
+          }
+      }
+  }
+  // find_particle_particle_periodic_contact_pairs (…broad_search.cc:316-380), local part
+  void find_particle_particle_periodic_contact_pairs(Oracle &o)
+  {
+    o.periodic_candidates.clear();
+    for (const auto &list : o.cells_local_periodic_neighbor_list)
+      {
+        const std::vector<int> &main = o.cell_parts[list[0]];
+        if (main.empty())
+          continue;
+        for (size_t nb = 1; nb < list.size(); ++nb)
+          {
+            const std::vector<int> &other = o.cell_parts[list[nb]];
+            for (size_t a = 0; a < main.size(); ++a)
+              store_candidates(o, o.periodic_candidates, o.parts[main[a]].id, other, 0);
+          }
+      }
+  }
+
+  // find_particle_wall_contact_pairs + store_candidates
+  // (particle_wall_broad_search.cc:8-56, particle_wall_broad_search.h:212-246).
+  // boundary_cells_information is a std::map keyed by global_face_id -> ascending face id.
+  void find_particle_wall_contact_pairs(Oracle &o, const std::vector<int> &faces_by_id)
+  {
+    o.wall_candidates.clear();
+    for (int f : faces_by_id)
+      {
+        const lethe_wall_face &face = o.faces[f];
+        if (face.cell < 0 || face.cell >= o.n_cells)
+          continue;
+        for (int s : o.cell_parts[face.cell])
+          {
+            WCandRow &row = o.wall_candidates.get_or_create(o.parts[s].id);
+            bool exists = false;
+            for (auto &w : row.c)
+              if (w.face == face.global_face_id)
+                exists = true;
+            if (!exists)
+              row.c.push_back(WCand{face.global_face_id, mk(face.normal[0], face.normal[1], face.normal[2]),
+                                    mk(face.point[0], face.point[1], face.point[2]), face.boundary_id});
+          }
+      }
+  }
+
+  // find_particle_floating_wall_contact_pairs (particle_wall_broad_search.cc:58-125)
+  void find_particle_floating_wall_contact_pairs(Oracle &o, double simulation_time)
+  {
+    o.fwall_candidates.clear();
+    for (int w = 0; w < o.n_floating; ++w)
+      {
+        if (!(simulation_time >= o.fw_t0[w] && simulation_time <= o.fw_t1[w]))
+          continue;
+        for (int cell : o.fw_cells[w])
+          for (int s : o.cell_parts[cell])
+            {
+              WCandRow &row = o.fwall_candidates.get_or_create(o.parts[s].id);
+              bool exists = false;
+              for (auto &c : row.c)
+                if (c.face == uint32_t(w))
+                  exists = true;
+              if (!exists)
+                row.c.push_back(WCand{uint32_t(w), mk(0, 0, 0), mk(0, 0, 0), LETHE_DEM_FLOATING_WALL_BOUNDARY_ID});
+            }
+      }
+  }
+
+  // BoundaryCellsInformation::find_boundary_cells_for_floating_walls
+  // (find_boundary_cells_information.cc:653-703)
+  void find_boundary_cells_for_floating_walls(Oracle &o, double maximum_cell_diameter)
+  {
+    o.fw_cells.assign(o.n_floating, std::vector<int>());
+    for (int w = 0; w < o.n_floating; ++w)
+      for (int r = 0; r < o.n_cells; ++r)
+        {
+          const int cell = o.cell_of_rank[r];
+          const int c[3] = {cell % o.nx, (cell / o.nx) % o.ny, cell / (o.nx * o.ny)};
+          bool in = false;
+          for (int vertex = 0; vertex < 8 && !in; ++vertex)
+            {
+              V3 vx;
+              vx[0] = o.cfg.grid_lo[0] + (c[0] + (vertex & 1)) * o.cfg.cell_size[0];
+              vx[1] = o.cfg.grid_lo[1] + (c[1] + ((vertex >> 1) & 1)) * o.cfg.cell_size[1];
+              vx[2] = o.cfg.grid_lo[2] + (c[2] + ((vertex >> 2) & 1)) * o.cfg.cell_size[2];
+              const V3 connecting_vector = vx - o.fw_point[w];
+              const double vertex_wall_distance = dot(connecting_vector, o.fw_normal[w]);
+              if (std::fabs(vertex_wall_distance) < maximum_cell_diameter)
+                in = true;
+            }
+          if (in)
+            o.fw_cells[w].push_back(cell);
+        }
+  }
+
+  // ---------------------------------------- update_fine_search_candidates ----
+  // (update_fine_search_candidates.cc:9-212), local particle-particle flavour
+  void update_fine_search_candidates_pp(DenseRows<PPRow> &pairs_in_contact, DenseRows<CandRow> &contact_candidates)
+  {
+    for (size_t r = 0; r < pairs_in_contact.rows.size();)
+      {
+        PPRow &row = pairs_in_contact.rows[r];
+        const uint32_t particle_id = row.one;
+        CandRow *cand = contact_candidates.find(particle_id);
+        for (size_t k = 0; k < row.second.size();)
+          {
+            const uint32_t object_id = row.second[k].two;
+            if (cand)
+              {
+                auto it = std::find(cand->c.begin(), cand->c.end(), object_id);
+                if (it != cand->c.end())
+                  {
+                    cand->c.erase(it);
+                    ++k;
+                    continue;
+                  }
+              }
+            CandRow *cand2 = contact_candidates.find(object_id);
+            if (cand2)
+              {
+                auto it = std::find(cand2->c.begin(), cand2->c.end(), particle_id);
+                if (it != cand2->c.end())
+                  {
+                    cand2->c.erase(it);
+                    ++k;
+                    continue;
+                  }
+              }
+            swap_erase(row.second, k);
+          }
+        if (!row.second.empty())
+          ++r;
+        else
+          pairs_in_contact.erase_at(r);
+      }
+  }
+  // particle-wall / floating-wall flavour (:163-197)
+  void update_fine_search_candidates_pw(DenseRows<PWRow> &pairs_in_contact, DenseRows<WCandRow> &contact_candidates)
+  {
+    for (size_t r = 0; r < pairs_in_contact.rows.size();)
+      {
+        PWRow &row = pairs_in_contact.rows[r];
+        WCandRow *cand = contact_candidates.find(row.one);
+        for (size_t k = 0; k < row.second.size();)
+          {
+            const uint32_t object_id = row.second[k].face;
+            if (cand)
+              {
+                size_t q = 0;
+                for (; q < cand->c.size(); ++q)
+                  if (cand->c[q].face == object_id)
+                    break;
+                if (q < cand->c.size())
+                  {
+                    swap_erase(cand->c, q);
+                    ++k;
+                    continue;
+                  }
+              }
+            swap_erase(row.second, k);
+          }
+        if (!row.second.empty())
+          ++r;
+        else
+          pairs_in_contact.erase_at(r);
+      }
+  }
+
+  // update_contact_container_iterators (update_local_particle_containers.cc:40-200)
+  void update_contact_container_iterators_pp(Oracle &o, DenseRows<PPRow> &pairs)
+  {
+    for (size_t r = 0; r < pairs.rows.size();)
+      {
+        PPRow &row = pairs.rows[r];
+        if (slot(o, row.one) < 0)
+          {
+            pairs.erase_at(r);
+            continue;
+          }
+        for (size_t k = 0; k < row.second.size();)
+          {
+            if (slot(o, row.second[k].two) < 0)
+              {
+                swap_erase(row.second, k);
+                continue;
+              }
+            if (o.clear_tangential_displacement_trigger)
+              {
+                row.second[k].tangential_displacement = mk(0, 0, 0);
+                row.second[k].rolling_resistance_spring_torque = mk(0, 0, 0);
+              }
+            ++k;
+          }
+        ++r;
+      }
+  }
+  void update_contact_container_iterators_pw(Oracle &o, DenseRows<PWRow> &pairs)
+  {
+    for (size_t r = 0; r < pairs.rows.size();)
+      {
+        if (slot(o, pairs.rows[r].one) < 0)
+          {
+            pairs.erase_at(r);
+            continue;
+          }
+        ++r;
+      }
+  }
+
+  // ----------------------------------------------------------- fine search ---
+  // particle_particle_fine_search (particle_particle_fine_search.cc:19-232)
+  void particle_particle_fine_search(Oracle &o, DenseRows<PPRow> &adjacent, DenseRows<CandRow> &candidates,
+                                     bool periodic)
+  {
+    const double neighborhood_threshold = o.neighborhood_threshold_squared;
+    for (auto &row : adjacent.rows)
+      {
+        if (row.second.empty())
+          continue;
+        const V3 one = o.parts[slot(o, row.one)].x;
+        for (size_t k = 0; k < row.second.size();)
+          {
+            const V3 two = o.parts[slot(o, row.second[k].two)].x;
+            if (!periodic)
+              {
+                const double square_distance = distance_square(one, two);
+                if (square_distance > neighborhood_threshold)
+                  swap_erase(row.second, k);
+                else
+                  ++k;
+              }
+            else
+              {
+                double min_square_distance = DBL_MAX;
+                V3 nearest = mk(0, 0, 0);
+                for (const V3 &t : o.combined_periodic_offsets)
+                  {
+                    const double d2 = distance_square(one, two + t);
+                    if (d2 < min_square_distance)
+                      {
+                        min_square_distance = d2;
+                        nearest = t;
+                      }
+                  }
+                if (min_square_distance > neighborhood_threshold)
+                  swap_erase(row.second, k);
+                else
+                  {
+                    row.second[k].periodic_offset = nearest;
+                    ++k;
+                  }
+              }
+          }
+      }
+    for (auto &crow : candidates.rows)
+      {
+        if (crow.c.empty())
+          continue;
+        const V3 one = o.parts[slot(o, crow.one)].x;
+        for (uint32_t two_id : crow.c)
+          {
+            const V3 two = o.parts[slot(o, two_id)].x;
+            V3 offset = mk(0, 0, 0);
+            bool add;
+            if (!periodic)
+              add = distance_square(one, two) < neighborhood_threshold;
+            else
+              {
+                double min_square_distance = DBL_MAX;
+                for (const V3 &t : o.combined_periodic_offsets)
+                  {
+                    const double d2 = distance_square(one, two + t);
+                    if (d2 < min_square_distance)
+                      {
+                        min_square_distance = d2;
+                        offset = t;
+                      }
+                  }
+                add = min_square_distance < neighborhood_threshold;
+              }
+            if (add)
+              {
+                PPRow &row = adjacent.get_or_create(crow.one);
+                bool exists = false;
+                for (auto &e : row.second)
+                  if (e.two == two_id)
+                    exists = true;
+                if (!exists)
+                  row.second.push_back(PPInfo{two_id, mk(0, 0, 0), mk(0, 0, 0), offset});
+              }
+          }
+      }
+  }
+
+  // particle_wall_fine_search (particle_wall_fine_search.cc:18-70)
+  void particle_wall_fine_search(Oracle &o)
+  {
+    for (auto &crow : o.wall_candidates.rows)
+      for (auto &c : crow.c)
+        {
+          PWRow &row = o.wall_in_contact.get_or_create(crow.one);
+          bool exists = false;
+          for (auto &e : row.second)
+            if (e.face == c.face)
+              exists = true;
+          if (!exists)
+            row.second.push_back(PWInfo{c.face, c.normal, c.point, c.boundary_id, mk(0, 0, 0), mk(0, 0, 0)});
+        }
+  }
+  // particle_floating_wall_fine_search (particle_wall_fine_search.cc:72-166)
+  void particle_floating_wall_fine_search(Oracle &o, double simulation_time)
+  {
+    for (auto &crow : o.fwall_candidates.rows)
+      for (auto &c : crow.c)
+        {
+          const int w = int(c.face);
+          if (!(simulation_time >= o.fw_t0[w] && simulation_time <= o.fw_t1[w]))
+            continue;
+          V3 normal_vector = o.fw_normal[w];
+          const V3 connecting_vector = o.parts[slot(o, crow.one)].x - o.fw_point[w];
+          const double ip = dot(connecting_vector, normal_vector);
+          if (ip < 0)
+            normal_vector = -1 * normal_vector;
+          PWRow &row = o.fwall_in_contact.get_or_create(crow.one);
+          bool exists = false;
+          for (auto &e : row.second)
+            if (e.face == c.face)
+              exists = true;
+          if (!exists)
+            row.second.push_back(PWInfo{c.face, normal_vector, o.fw_point[w], LETHE_DEM_FLOATING_WALL_BOUNDARY_ID,
+                                        mk(0, 0, 0), mk(0, 0, 0)});
+        }
+  }
+
+  // ------------------------------------------------- rolling resistance (pp) --
+  // rolling_resistance_torque_models.h:12-250, dispatch …contact_force.h:643-698
+  V3 pp_rolling_resistance(const Oracle &o, double effective_r, const double *p1, const double *p2,
+                           double rolling_friction_coeff, double rolling_viscous_damping_coeff, double dt,
+                           double normal_spring_constant, double normal_force_norm, const V3 &n, V3 &cumulative)
+  {
+    switch (o.cfg.rolling_model)
+      {
+        case LETHE_ROLLING_NONE:
+          return mk(0, 0, 0);
+        case LETHE_ROLLING_CONSTANT:
+          {
+            const V3 w1 = mk(p1[P_WX], p1[P_WY], p1[P_WZ]), w2 = mk(p2[P_WX], p2[P_WY], p2[P_WZ]);
+            const V3 omega_ij = w1 - w2;
+            const V3 dir = omega_ij / (norm(omega_ij) + DBL_MIN);
+            return (-rolling_friction_coeff * effective_r * normal_force_norm) * dir;
+          }
+        case LETHE_ROLLING_VISCOUS:
+          {
+            const V3 w1 = mk(p1[P_WX], p1[P_WY], p1[P_WZ]), w2 = mk(p2[P_WX], p2[P_WY], p2[P_WZ]);
+            const V3 omega_ij = w1 - w2;
+            const V3 dir = omega_ij / (norm(omega_ij) + DBL_MIN);
+            const V3 v_omega = cross(w1, (p1[P_DP] * 0.5) * n) - cross(w2, (p2[P_DP] * 0.5) * (-n));
+            return (-rolling_friction_coeff * effective_r * normal_force_norm * norm(v_omega)) * dir;
+          }
+        default: // EPSD
+          {
+            const double mu_r_times_R_e = rolling_friction_coeff * effective_r;
+            V3 omega_ij;
+            for (int d = 0; d < 3; ++d)
+              omega_ij[d] = p1[P_WX + d] - p2[P_WX + d];
+            const V3 omega_perp = omega_ij - dot(omega_ij, n) * n;
+            const V3 delta_theta = dt * omega_perp;
+            const double K_r = 2.25 * normal_spring_constant * sq(mu_r_times_R_e);
+            cumulative = cumulative - K_r * delta_theta;
+            const double M_r_max = mu_r_times_R_e * normal_force_norm;
+            const double spring_norm = norm(cumulative);
+            const double I_i = 1.4 * p1[P_MASS] * sq(0.5 * p1[P_DP]);
+            const double I_j = 1.4 * p2[P_MASS] * sq(0.5 * p2[P_DP]);
+            const double I_e = I_i * I_j / (I_i + I_j);
+            const double C_r = rolling_viscous_damping_coeff * 2. * std::sqrt(I_e * K_r);
+            if (spring_norm > M_r_max)
+              {
+                cumulative = cumulative * (M_r_max / spring_norm);
+                return cumulative - (o.cfg.f_coefficient_epsd * C_r) * omega_perp;
+              }
+            return cumulative - C_r * omega_perp;
+          }
+      }
+  }
+
+  struct PPOut
+  {
+    V3 normal_force, tangential_force, t1, t2, rolling;
+  };
+
+  // Ferrari solution of the JKR contact-patch quartic (…contact_force.h:1356-1372).
+  inline double jkr_contact_radius(double R, double overlap, double gamma, double Y, bool clamp_root1)
+  {
+    const double c0 = sq(R * overlap);
+    const double c1 = -2. * sq(R) * M_PI * gamma / Y;
+    const double c2 = -2. * overlap * R;
+    const double P = -sq(c2) / 12. - c0;
+    const double Q = -cube(c2) / 108. + c0 * c2 / 3. - sq(c1) * 0.125;
+    double root1 = clamp_root1 ? std::max(0., (0.25 * sq(Q)) + (cube(P) / 27.)) : 0.25 * sq(Q) + cube(P) / 27.;
+    const double U = std::cbrt(-0.5 * Q + std::sqrt(root1));
+    const double s = -c2 * (5. / 6.) + U - P / (3. * U);
+    const double w = std::sqrt(std::max(1e-16, c2 + 2. * s));
+    const double lambda = 0.5 * c1 / w;
+    const double root2 = std::max(1e-16, w * w - 4. * (c2 + s + lambda));
+    return 0.5 * (w + std::sqrt(root2));
+  }
+
+  // calculate_contact for all particle-particle models (…contact_force.h:723-1544).
+  // `out` is NOT reset here: the reference keeps these tensors across the pairs of
+  // one row (…contact_force.h:1847-1853), which matters for the DMT non-contact branch.
+  void pp_calculate_contact(const Oracle &o, int model, PPInfo &info, const V3 &vt, double vn, const V3 &n,
+                            double overlap, double dt, const double *p1, const double *p2, PPOut &out)
+  {
+    const double d1 = p1[P_DP], d2 = p2[P_DP];
+    const double effective_radius = (d1 * d2) / (2 * (d1 + d2));
+    const double effective_mass = (p1[P_MASS] * p2[P_MASS]) / (p1[P_MASS] + p2[P_MASS]);
+    const unsigned int t1 = static_cast<unsigned int>(p1[P_TYPE]);
+    const unsigned int t2 = static_cast<unsigned int>(p2[P_TYPE]);
+    const unsigned int k = t1 * o.n_types + t2;
+    const double Y = o.eY[k], G = o.eG[k], beta = o.beta[k], mu = o.eMu[k];
+    const double roll_visc = o.eRollVisc[k], roll_fric = o.eRollFric[k];
+
+    if (model == LETHE_PP_DMT)
+      {
+        // calculate_DMT_contact (:1465-1544)
+        constexpr double M_2PI = 2. * M_PI;
+        const double gamma = o.eGamma[k], A = o.eHamaker[k];
+        const double F_po = M_2PI * effective_radius * gamma;
+        const double delta_0 = -std::sqrt(A * effective_radius / (6. * F_po));
+        double cohesive_term;
+        if (overlap > 0.)
+          {
+            cohesive_term = -F_po;
+            pp_calculate_contact(o, LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP, info, vt, vn, n, overlap, dt, p1, p2, out);
+          }
+        else if (overlap > delta_0)
+          {
+            cohesive_term = -F_po;
+            info.tangential_displacement = mk(0, 0, 0);
+            info.rolling_resistance_spring_torque = mk(0, 0, 0);
+          }
+        else
+          {
+            cohesive_term = -A * effective_radius / (6. * sq(overlap));
+            info.tangential_displacement = mk(0, 0, 0);
+            info.rolling_resistance_spring_torque = mk(0, 0, 0);
+          }
+        out.normal_force = out.normal_force + cohesive_term * n;
+        return;
+      }
+
+    if (model == LETHE_PP_LINEAR)
+      {
+        // calculate_linear_contact (:723-852)
+        constexpr double characteristic_velocity = 1.0;
+        const double kn = 1.0667 * std::sqrt(effective_radius) * Y *
+                          std::pow((0.9375 * effective_mass * characteristic_velocity * characteristic_velocity /
+                                    (std::sqrt(effective_radius) * Y)),
+                                   0.2);
+        const double kt = kn * 0.4;
+        const double etan = -2 * beta * std::sqrt(effective_mass * kn);
+        const double etat = etan * 0.6324555320336759;
+        const double normal_force_value = kn * overlap + etan * vn;
+        out.normal_force = normal_force_value * n;
+        const V3 damping_tangential_force = etat * vt;
+        out.tangential_force = (kt * info.tangential_displacement) + damping_tangential_force;
+        const double coulomb_threshold = mu * normal_force_value;
+        if (norm(out.tangential_force) > coulomb_threshold)
+          {
+            const V3 limited = coulomb_threshold * (out.tangential_force / (norm(out.tangential_force) + DBL_MIN));
+            info.tangential_displacement = (limited - damping_tangential_force) / (kt + DBL_MIN);
+            out.tangential_force = (kt * info.tangential_displacement) + damping_tangential_force;
+          }
+        out.t1 = cross(n, out.tangential_force * d1 * 0.5);
+        out.t2 = out.t1 * d2 / d1;
+        // note the swapped coefficient order in the reference (:841-851)
+        out.rolling = pp_rolling_resistance(o, effective_radius, p1, p2, roll_visc, roll_fric, dt, kn,
+                                            norm(out.normal_force), n, info.rolling_resistance_spring_torque);
+        return;
+      }
+
+    const double radius_times_overlap_sqrt = std::sqrt(effective_radius * overlap);
+    const double model_parameter_sn = 2.0 * Y * radius_times_overlap_sqrt;
+    const double model_parameter_st = 8.0 * G * radius_times_overlap_sqrt;
+
+    if (model == LETHE_PP_HERTZ_JKR)
+      {
+        // calculate_hertz_JKR_contact (:1304-1441)
+        const double gamma = o.eGamma[k];
+        const double a = jkr_contact_radius(effective_radius, overlap, gamma, Y, false);
+        const double etan = -1.8257 * beta * std::sqrt(model_parameter_sn * effective_mass);
+        const double kt = 8.0 * radius_times_overlap_sqrt * G;
+        const double etat = etan * std::sqrt(model_parameter_st / model_parameter_sn);
+        const double normal_force_coefficient =
+          4. * cube(a) / (3. * effective_radius) * Y - std::sqrt(8. * M_PI * gamma * Y * cube(a));
+        out.normal_force = (normal_force_coefficient + etan * vn) * n;
+        out.tangential_force = kt * info.tangential_displacement + etat * vt;
+        const double two_pull_off_force = 3. * M_PI * gamma * effective_radius;
+        const double modified_coulomb_threshold = (normal_force_coefficient + two_pull_off_force) * mu;
+        if (norm(out.tangential_force) > modified_coulomb_threshold)
+          out.tangential_force =
+            modified_coulomb_threshold * (out.tangential_force / (norm(out.tangential_force) + DBL_MIN));
+        out.t1 = cross(n, out.tangential_force * d1 * 0.5);
+        out.t2 = out.t1 * d2 / d1;
+        const double kn = 0.66665 * model_parameter_sn;
+        out.rolling = pp_rolling_resistance(o, effective_radius, p1, p2, roll_fric, roll_visc, dt, kn,
+                                            norm(out.normal_force), n, info.rolling_resistance_spring_torque);
+        return;
+      }
+
+    // hertz_mindlin_limit_overlap (:879-1010), limit_force (:1036-1151), hertz (:1176-1280)
+    const double kn = 0.66665 * model_parameter_sn;
+    const double etan = -1.8257 * beta * std::sqrt(model_parameter_sn * effective_mass);
+    const double kt = 8.0 * G * radius_times_overlap_sqrt;
+    const double normal_force_value = kn * overlap + etan * vn;
+    out.normal_force = normal_force_value * n;
+    const double coulomb_threshold_base = mu; // multiplied below, kept as in the reference
+    if (model == LETHE_PP_HERTZ)
+      {
+        out.tangential_force = kt * info.tangential_displacement;
+        const double coulomb_threshold = coulomb_threshold_base * normal_force_value;
+        if (norm(out.tangential_force) > coulomb_threshold)
+          out.tangential_force = coulomb_threshold * (out.tangential_force / (norm(out.tangential_force) + DBL_MIN));
+      }
+    else
+      {
+        const double etat = etan * std::sqrt(model_parameter_st / model_parameter_sn);
+        const V3 damping_tangential_force = etat * vt;
+        out.tangential_force = (kt * info.tangential_displacement) + damping_tangential_force;
+        const double coulomb_threshold = coulomb_threshold_base * normal_force_value;
+        if (norm(out.tangential_force) > coulomb_threshold)
+          {
+            if (model == LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP)
+              {
+                const V3 limited =
+                  coulomb_threshold * (out.tangential_force / (norm(out.tangential_force) + DBL_MIN));
+                info.tangential_displacement = (limited - damping_tangential_force) / (kt + DBL_MIN);
+                out.tangential_force = (kt * info.tangential_displacement) + damping_tangential_force;
+              }
+            else
+              out.tangential_force =
+                coulomb_threshold * (out.tangential_force / (norm(out.tangential_force) + DBL_MIN));
+          }
+      }
+    out.t1 = cross(n, out.tangential_force * d1 * 0.5);
+    out.t2 = out.t1 * d2 / d1;
+    out.rolling = pp_rolling_resistance(o, effective_radius, p1, p2, roll_fric, roll_visc, dt, kn,
+                                        norm(out.normal_force), n, info.rolling_resistance_spring_torque);
+  }
+
+  // update_contact_information (…contact_force.h:223-298)
+  inline void pp_update_contact_information(PPInfo &info, V3 &vt, double &vn, V3 &n, const double *p1,
+                                            const double *p2, const V3 &x1, const V3 &x2, double dt)
+  {
+    const V3 contact_vector = x2 - x1;
+    n = contact_vector / norm(contact_vector);
+    V3 vrel = mk(p1[P_VX] - p2[P_VX], p1[P_VY] - p2[P_VY], p1[P_VZ] - p2[P_VZ]);
+    const V3 w1 = mk(p1[P_WX], p1[P_WY], p1[P_WZ]), w2 = mk(p2[P_WX], p2[P_WY], p2[P_WZ]);
+    vrel = vrel + cross(0.5 * (p1[P_DP] * w1 + p2[P_DP] * w2), n);
+    vn = dot(vrel, n);
+    vt = vrel - (vn * n);
+    info.tangential_displacement = info.tangential_displacement + vt * dt;
+    info.tangential_displacement =
+      info.tangential_displacement - dot(info.tangential_displacement, n) * n;
+  }
+
+  // execute_contact_calculation<local / local_periodic> (…contact_force.h:1838-2063)
+  void pp_execute_contact_calculation(Oracle &o, PPRow &row, bool periodic, double dt)
+  {
+    if (row.second.empty())
+      return;
+    PPOut out;
+    out.normal_force = out.tangential_force = out.t1 = out.t2 = out.rolling = mk(0, 0, 0);
+    V3 n = mk(0, 0, 0), vt = mk(0, 0, 0);
+    double vn = 0;
+    const int s1 = slot(o, row.one);
+    const double *p1 = o.parts[s1].p;
+    const V3 x1 = o.parts[s1].x;
+    for (auto &info : row.second)
+      {
+        const int s2 = slot(o, info.two);
+        const double *p2 = o.parts[s2].p;
+        const V3 x2 = periodic ? (o.parts[s2].x + info.periodic_offset) : o.parts[s2].x;
+        const double normal_overlap = 0.5 * (p1[P_DP] + p2[P_DP]) - std::sqrt(distance_square(x1, x2));
+        if (normal_overlap > o.pp_force_threshold)
+          {
+            pp_update_contact_information(info, vt, vn, n, p1, p2, x1, x2, dt);
+            pp_calculate_contact(o, o.cfg.pp_model, info, vt, vn, n, normal_overlap, dt, p1, p2, out);
+            // apply_force_and_torque_on_local_particles (:548-570)
+            const V3 total_force = out.normal_force + out.tangential_force;
+            o.force[s1] = o.force[s1] - total_force;
+            o.force[s2] = o.force[s2] + total_force;
+            o.torque[s1] = o.torque[s1] + (-out.t1 + out.rolling);
+            o.torque[s2] = o.torque[s2] + (-out.t2 - out.rolling);
+            ++o.n_touching_last;
+          }
+        else
+          {
+            info.tangential_displacement = mk(0, 0, 0);
+            info.rolling_resistance_spring_torque = mk(0, 0, 0);
+          }
+      }
+  }
+
+  // ------------------------------------------------------------ wall force ---
+  const BoundaryMotion *find_motion(const Oracle &o, uint32_t boundary_id)
+  {
+    for (auto &m : o.motions)
+      if (m.boundary_id == boundary_id)
+        return &m;
+    return nullptr;
+  }
+
+  // particle_wall_rolling_resistance_torque.h:12-226
+  V3 pw_rolling_resistance(const Oracle &o, double R, const double *p, double rolling_friction_coeff,
+                           double rolling_viscous_damping_coeff, double dt, double normal_spring_constant,
+                           double normal_force_norm, const V3 &n, V3 &cumulative)
+  {
+    const V3 w = mk(p[P_WX], p[P_WY], p[P_WZ]);
+    switch (o.cfg.rolling_model)
+      {
+        case LETHE_ROLLING_NONE:
+          return mk(0, 0, 0);
+        case LETHE_ROLLING_CONSTANT:
+          {
+            const double omega_value = norm(w);
+            const V3 dir = w / (omega_value + DBL_MIN);
+            return (-rolling_friction_coeff * R * normal_force_norm) * dir;
+          }
+        case LETHE_ROLLING_VISCOUS:
+          {
+            const double omega_value = norm(w);
+            const V3 dir = w / (omega_value + DBL_MIN);
+            const V3 v_omega = cross(w, R * n);
+            return (-rolling_friction_coeff * R * normal_force_norm * norm(v_omega)) * dir;
+          }
+        default:
+          {
+            const double mu_r_times_R = rolling_friction_coeff * R;
+            const V3 omega_perp = w - dot(w, n) * n;
+            const V3 delta_theta = dt * omega_perp;
+            const double K_r = 2.25 * normal_spring_constant * sq(mu_r_times_R);
+            cumulative = cumulative - K_r * delta_theta;
+            const double M_r_max = mu_r_times_R * normal_force_norm;
+            const double spring_norm = norm(cumulative);
+            const double I_e = 1.4 * p[P_MASS] * sq(R);
+            const double C_r = rolling_viscous_damping_coeff * 2. * std::sqrt(I_e * K_r);
+            if (spring_norm > M_r_max)
+              {
+                cumulative = cumulative * (M_r_max / spring_norm);
+                return cumulative - (o.cfg.f_coefficient_epsd * C_r) * omega_perp;
+              }
+            return cumulative - C_r * omega_perp;
+          }
+      }
+  }
+
+  struct PWOut
+  {
+    V3 normal_force, tangential_force, tangential_torque, rolling;
+  };
+
+  // calculate_contact for particle-wall models (particle_wall_contact_force.h:610-1082)
+  void pw_calculate_contact(const Oracle &o, int model, PWInfo &info, const V3 &vt, double vn, double overlap,
+                            double dt, const double *p, PWOut &out)
+  {
+    const V3 normal_vector = -info.normal;
+    const unsigned int type = static_cast<unsigned int>(p[P_TYPE]);
+    const double Y = o.wY[type], G = o.wG[type], beta = o.wbeta[type], mu = o.wMu[type];
+    const double roll_visc = o.wRollVisc[type], roll_fric = o.wRollFric[type];
+
+    if (model == LETHE_PW_DMT)
+      {
+        constexpr double M_2PI = 2. * M_PI;
+        const double R = 0.5 * p[P_DP];
+        const double gamma = o.wGamma[type], A = o.wHamaker[type];
+        const double F_po = M_2PI * R * gamma;
+        const double delta_0 = -std::sqrt(A * R / (6. * F_po));
+        double cohesive_term;
+        if (overlap > 0.)
+          {
+            cohesive_term = -F_po;
+            pw_calculate_contact(o, LETHE_PW_NONLINEAR, info, vt, vn, overlap, dt, p, out);
+          }
+        else if (overlap > delta_0)
+          {
+            cohesive_term = -F_po;
+            info.tangential_displacement = mk(0, 0, 0);
+            info.rolling_resistance_spring_torque = mk(0, 0, 0);
+          }
+        else
+          {
+            cohesive_term = -A * R / (6. * sq(overlap));
+            info.tangential_displacement = mk(0, 0, 0);
+            info.rolling_resistance_spring_torque = mk(0, 0, 0);
+          }
+        out.normal_force = out.normal_force + cohesive_term * normal_vector;
+        return;
+      }
+    if (model == LETHE_PW_LINEAR)
+      {
+        const double R = p[P_DP] * 0.5;
+        const double rp_sqrt = std::sqrt(R);
+        const double kn = 1.0667 * rp_sqrt * Y * std::pow((0.9375 * p[P_MASS] * 1.0 * 1.0 / (rp_sqrt * Y)), 0.2);
+        const double etan = 2 * beta * std::sqrt(p[P_MASS] * kn);
+        const double kt = -kn * 0.4;
+        const double etat = etan * 0.6324555320336759;
+        out.normal_force = (kn * overlap + etan * vn) * normal_vector;
+        out.tangential_force = (kt * info.tangential_displacement + etat * vt);
+        const double coulomb_threshold = mu * norm(out.normal_force);
+        if (norm(out.tangential_force) > coulomb_threshold)
+          {
+            out.tangential_force = coulomb_threshold * (out.tangential_force / norm(out.tangential_force));
+            info.tangential_displacement = out.tangential_force / (kt + DBL_MIN);
+          }
+        out.tangential_torque = cross((R * normal_vector), -out.tangential_force);
+        out.rolling = pw_rolling_resistance(o, R, p, roll_fric, roll_visc, dt, kn, norm(out.normal_force),
+                                            info.normal, info.rolling_resistance_spring_torque);
+        return;
+      }
+    if (model == LETHE_PW_JKR)
+      {
+        const double R = 0.5 * p[P_DP];
+        const double gamma = o.wGamma[type];
+        const double radius_times_overlap_sqrt = std::sqrt(R * overlap);
+        const double sn = 2.0 * Y * radius_times_overlap_sqrt;
+        const double st = 8.0 * G * radius_times_overlap_sqrt;
+        const double a = jkr_contact_radius(R, overlap, gamma, Y, true);
+        const double etan = 1.8257 * beta * std::sqrt(sn * p[P_MASS]);
+        const double kt = -8.0 * G * radius_times_overlap_sqrt;
+        const double etat = etan * std::sqrt(st / (sn + DBL_MIN));
+        const double normal_force_norm =
+          4. * Y * cube(a) / (3. * R) - std::sqrt(8. * M_PI * gamma * Y * cube(a)) + etan * vn;
+        out.normal_force = normal_force_norm * normal_vector;
+        const V3 damping_tangential_force = etat * vt;
+        out.tangential_force = kt * info.tangential_displacement + damping_tangential_force;
+        const double modified_coulomb_threshold = (normal_force_norm + 3. * M_PI * gamma * R) * mu;
+        const double tangential_force_norm = norm(out.tangential_force);
+        if (tangential_force_norm > modified_coulomb_threshold)
+          {
+            info.tangential_displacement =
+              (modified_coulomb_threshold * (out.tangential_force / (tangential_force_norm + DBL_MIN)) -
+               damping_tangential_force) /
+              (kt + DBL_MIN);
+            out.tangential_force = (kt * info.tangential_displacement) + damping_tangential_force;
+          }
+        out.tangential_torque = cross((R * normal_vector), -out.tangential_force);
+        const double kn = 0.66665 * sn;
+        out.rolling = pw_rolling_resistance(o, R, p, roll_fric, roll_visc, dt, kn, norm(out.normal_force),
+                                            info.normal, info.rolling_resistance_spring_torque);
+        return;
+      }
+    // nonlinear (:723-833)
+    const double R = p[P_DP] * 0.5;
+    const double radius_times_overlap_sqrt = std::sqrt(R * overlap);
+    const double sn = 2.0 * Y * radius_times_overlap_sqrt;
+    const double st = 8.0 * G * radius_times_overlap_sqrt;
+    const double kn = 1.3333 * Y * radius_times_overlap_sqrt;
+    const double etan = 1.8257 * beta * std::sqrt(sn * p[P_MASS]);
+    const double kt = -8.0 * G * radius_times_overlap_sqrt + DBL_MIN;
+    const double etat = etan * std::sqrt(st / sn);
+    out.normal_force = (kn * overlap + etan * vn) * normal_vector;
+    const V3 damping_tangential_force = etat * vt;
+    out.tangential_force = kt * info.tangential_displacement + damping_tangential_force;
+    const double coulomb_threshold = mu * norm(out.normal_force);
+    const double tangential_force_norm = norm(out.tangential_force);
+    if (tangential_force_norm > coulomb_threshold)
+      {
+        info.tangential_displacement =
+          (coulomb_threshold * (out.tangential_force / (tangential_force_norm + DBL_MIN)) -
+           damping_tangential_force) /
+          (kt + DBL_MIN);
+        out.tangential_force = (kt * info.tangential_displacement) + damping_tangential_force;
+      }
+    out.tangential_torque = cross((R * normal_vector), -out.tangential_force);
+    out.rolling = pw_rolling_resistance(o, R, p, roll_fric, roll_visc, dt, kn, norm(out.normal_force), info.normal,
+                                        info.rolling_resistance_spring_torque);
+  }
+
+  // calculate_particle_wall_contact (particle_wall_contact_force.cc:45-142) with
+  // update_contact_information (particle_wall_contact_force.h:166-264)
+  void calculate_particle_wall_contact(Oracle &o, DenseRows<PWRow> &pairs, double dt)
+  {
+    for (auto &row : pairs.rows)
+      for (auto &info : row.second)
+        {
+          const int s = slot(o, row.one);
+          const double *p = o.parts[s].p;
+          const V3 x = o.parts[s].x;
+          const V3 point_to_particle_vector = x - info.point;
+          // find_projection (:~335)
+          const V3 projected_vector =
+            ((dot(point_to_particle_vector, info.normal)) / (norm_square(info.normal))) * info.normal;
+          const double normal_overlap = ((p[P_DP]) * 0.5) - (norm(projected_vector));
+          if (normal_overlap > o.pw_force_threshold)
+            {
+              const V3 normal_vector = -info.normal;
+              const V3 particle_velocity = mk(p[P_VX], p[P_VY], p[P_VZ]);
+              const V3 particle_angular_velocity = mk(p[P_WX], p[P_WY], p[P_WZ]);
+              const V3 contact_point = x + (0.5 * p[P_DP]) * normal_vector;
+              const BoundaryMotion *m = find_motion(o, info.boundary_id);
+              const V3 bt = m ? m->translational_velocity : mk(0, 0, 0);
+              const double bs = m ? m->rotational_speed : 0.;
+              const V3 br = m ? m->rotational_vector : mk(0, 0, 0);
+              const V3 bp = m ? m->point_on_axis : mk(0, 0, 0);
+              V3 vector_to_rotating_axis = contact_point - bp;
+              vector_to_rotating_axis = vector_to_rotating_axis - (dot(vector_to_rotating_axis, br)) * br;
+              const V3 vrel = bt - particle_velocity +
+                              cross(((-0.5 * p[P_DP]) * particle_angular_velocity), normal_vector) +
+                              cross(bs * br, vector_to_rotating_axis);
+              const double vn = dot(vrel, normal_vector);
+              const V3 vt = vrel - (vn * normal_vector);
+              info.tangential_displacement = info.tangential_displacement + vt * dt;
+
+              PWOut out;
+              out.normal_force = out.tangential_force = out.tangential_torque = out.rolling = mk(0, 0, 0);
+              pw_calculate_contact(o, o.cfg.pw_model, info, vt, vn, normal_overlap, dt, p, out);
+              // apply_force_and_torque (:506-522)
+              const V3 total_force = out.normal_force + out.tangential_force;
+              o.force[s] = o.force[s] - total_force;
+              o.torque[s] = o.torque[s] + (out.tangential_torque + out.rolling);
+            }
+          else
+            {
+              info.tangential_displacement = mk(0, 0, 0);
+              info.rolling_resistance_spring_torque = mk(0, 0, 0);
+            }
+        }
+  }
+
+  // ------------------------------------------------------------ integrator ---
+  // VelocityVerletIntegrator (velocity_verlet_integrator.cc:14-66,70-115,214-290)
+  void integrate_start(Oracle &o)
+  {
+    const double dt = o.cfg.dt;
+    const V3 g = mk(o.cfg.g[0], o.cfg.g[1], o.cfg.g[2]);
+    const V3 half_dt_g = 0.5 * g * dt;
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      {
+        double *p = o.parts[s].p;
+        const double half_dt_mass_inverse = 0.5 * dt / p[P_MASS];
+        const double half_dt_MOI_inverse = 0.5 * dt / o.MOI[s];
+        for (int d = 0; d < 3; ++d)
+          {
+            p[P_VX + d] += half_dt_g[d] + o.force[s][d] * half_dt_mass_inverse;
+            p[P_WX + d] += o.torque[s][d] * half_dt_MOI_inverse;
+          }
+        for (int d = 0; d < 3; ++d)
+          o.parts[s].x[d] += p[P_VX + d] * dt;
+        o.force[s] = mk(0, 0, 0);
+        o.torque[s] = mk(0, 0, 0);
+      }
+  }
+  void integrate_end(Oracle &o)
+  {
+    const double dt = o.cfg.dt;
+    const V3 g = mk(o.cfg.g[0], o.cfg.g[1], o.cfg.g[2]);
+    const V3 half_dt_g = 0.5 * g * dt;
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      {
+        double *p = o.parts[s].p;
+        const double half_dt_mass_inverse = 0.5 * dt / p[P_MASS];
+        const double half_dt_MOI_inverse = 0.5 * dt / o.MOI[s];
+        for (int d = 0; d < 3; ++d)
+          p[P_VX + d] += half_dt_g[d] + o.force[s][d] * half_dt_mass_inverse;
+        for (int d = 0; d < 3; ++d)
+          p[P_WX + d] += o.torque[s][d] * half_dt_MOI_inverse;
+        o.force[s] = mk(0, 0, 0);
+        o.torque[s] = mk(0, 0, 0);
+      }
+  }
+  void integrate(Oracle &o)
+  {
+    const double dt = o.cfg.dt;
+    const V3 g = mk(o.cfg.g[0], o.cfg.g[1], o.cfg.g[2]);
+    const V3 dt_g = g * dt;
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      {
+        double *p = o.parts[s].p;
+        const double dt_mass_inverse = dt / p[P_MASS];
+        const double dt_MOI_inverse = dt / o.MOI[s];
+        for (int d = 0; d < 3; ++d)
+          p[P_VX + d] += dt_g[d] + o.force[s][d] * dt_mass_inverse;
+        for (int d = 0; d < 3; ++d)
+          o.parts[s].x[d] += p[P_VX + d] * dt;
+        for (int d = 0; d < 3; ++d)
+          p[P_WX + d] += o.torque[s][d] * dt_MOI_inverse;
+        o.force[s] = mk(0, 0, 0);
+        o.torque[s] = mk(0, 0, 0);
+      }
+  }
+
+  // ------------------------------------------------------------ time step ----
+  // find_particle_contact_detection_step (find_contact_detection_step.cc:9-59) with
+  // check_contact_search_iteration_{dynamic,constant} (dem.cc:459-482)
+  void contact_detection_iteration_check(Oracle &o)
+  {
+    const uint64_t freq = uint64_t(std::max(1, o.cfg.contact_detection_frequency));
+    if (o.cfg.detection == LETHE_DETECTION_CONSTANT)
+      {
+        if ((o.iteration_number % freq) == 0)
+          o.contact_search_trigger = true;
+        return;
+      }
+    const bool parallel_update = (o.iteration_number % freq) == 0;
+    if (o.contact_search_trigger)
+      return;
+    double max_displacement = 0.;
+    const double dt = o.cfg.dt;
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      {
+        const double *p = o.parts[s].p;
+        o.displacement[s] += dt * std::sqrt(p[P_VX] * p[P_VX] + p[P_VY] * p[P_VY] + p[P_VZ] * p[P_VZ]);
+        max_displacement = std::max(max_displacement, o.displacement[s]);
+      }
+    const bool contact_detection_step = max_displacement > o.cfg.smallest_contact_search_criterion;
+    if (parallel_update && contact_detection_step)
+      o.contact_search_trigger = true;
+  }
+
+  // DEMSolver::execute_contact_detection_and_search (dem.cc:598-688)
+  void execute_contact_detection_and_search(Oracle &o)
+  {
+    contact_detection_iteration_check(o);
+    if (!o.contact_search_trigger)
+      return;
+    execute_particles_displacement(o);
+    sort_particles_into_subdomains_and_cells(o);
+
+    find_particle_particle_contact_pairs(o);
+    if (o.periodic_enabled)
+      find_particle_particle_periodic_contact_pairs(o);
+    std::vector<int> faces_by_id(o.faces.size());
+    for (size_t f = 0; f < o.faces.size(); ++f)
+      faces_by_id[f] = int(f);
+    std::stable_sort(faces_by_id.begin(), faces_by_id.end(),
+                     [&](int a, int b) { return o.faces[a].global_face_id < o.faces[b].global_face_id; });
+    find_particle_wall_contact_pairs(o, faces_by_id);
+    if (o.n_floating > 0)
+      find_particle_floating_wall_contact_pairs(o, o.current_time);
+
+    // DEMContactManager::update_contacts (dem_contact_manager.cc:52-144)
+    update_fine_search_candidates_pp(o.local_adjacent, o.local_candidates);
+    if (o.periodic_enabled)
+      update_fine_search_candidates_pp(o.periodic_adjacent, o.periodic_candidates);
+    update_fine_search_candidates_pw(o.wall_in_contact, o.wall_candidates);
+    update_fine_search_candidates_pw(o.fwall_in_contact, o.fwall_candidates);
+
+    // update_local_particles_in_cells (dem_contact_manager.cc:148-236)
+    update_particle_container(o);
+    update_contact_container_iterators_pp(o, o.local_adjacent);
+    if (o.periodic_enabled)
+      update_contact_container_iterators_pp(o, o.periodic_adjacent);
+    update_contact_container_iterators_pw(o, o.wall_in_contact);
+    update_contact_container_iterators_pw(o, o.fwall_in_contact);
+
+    particle_particle_fine_search(o, o.local_adjacent, o.local_candidates, false);
+    if (o.periodic_enabled)
+      particle_particle_fine_search(o, o.periodic_adjacent, o.periodic_candidates, true);
+    particle_wall_fine_search(o);
+    if (o.n_floating > 0)
+      particle_floating_wall_fine_search(o, o.current_time);
+    ++o.contact_build_number;
+  }
+
+  // DEMSolver::compute_contact_forces (dem.cc:690-717)
+  void compute_contact_forces(Oracle &o)
+  {
+    o.n_touching_last = 0;
+    const double dt = o.cfg.dt;
+    for (auto &row : o.local_adjacent.rows)
+      pp_execute_contact_calculation(o, row, false, dt);
+    if (o.periodic_enabled)
+      for (auto &row : o.periodic_adjacent.rows)
+        pp_execute_contact_calculation(o, row, true, dt);
+    calculate_particle_wall_contact(o, o.wall_in_contact, dt);
+    if (o.n_floating > 0)
+      calculate_particle_wall_contact(o, o.fwall_in_contact, dt);
+    if (o.cfg.store_forces)
+      {
+        o.last_force = o.force;
+        o.last_torque = o.torque;
+      }
+  }
+
+  void reset_triggers(Oracle &o)
+  {
+    o.contact_search_trigger = false;
+    o.clear_tangential_displacement_trigger = false;
+  }
+
+  void one_step(Oracle &o)
+  {
+    // SimulationControlTransient::integrate (simulation_control.cc:330-352)
+    o.iteration_number++;
+    o.current_time += o.cfg.dt;
+    execute_contact_detection_and_search(o);
+    compute_contact_forces(o);
+    if (o.iteration_number <= 1 && !o.cfg.restart)
+      integrate_start(o);
+    else
+      integrate(o);
+    reset_triggers(o);
+  }
+
+  int fail(Oracle *o, const char *msg)
+  {
+    if (o)
+      o->error = msg;
+    return -1;
+  }
+  std::string g_create_error;
+} // namespace
+
+// ------------------------------------------------------------------ C API ---
+extern "C" {
+
+struct lethe_dem_ctx; // the oracle reuses the opaque handle type of lethe_dem.h
+
+int oracle_dem_create(const lethe_dem_config *config, int /*device*/, lethe_dem_ctx **out)
+{
+  if (!config || !out)
+    {
+      g_create_error = "null argument";
+      return -1;
+    }
+  if (config->n_types < 1 || config->n_types > LETHE_DEM_MAX_TYPES)
+    {
+      g_create_error = "n_types out of range";
+      return -1;
+    }
+  if (config->grid_n[0] < 1 || config->grid_n[1] < 1 || config->grid_n[2] < 1)
+    {
+      g_create_error = "grid_n must be positive";
+      return -1;
+    }
+  if (config->integrator != LETHE_INTEGRATOR_VELOCITY_VERLET)
+    {
+      g_create_error = "only velocity_verlet is supported";
+      return -1;
+    }
+  Oracle *o = new Oracle();
+  o->cfg = *config;
+  o->nx = config->grid_n[0];
+  o->ny = config->grid_n[1];
+  o->nz = config->grid_n[2];
+  o->n_cells = o->nx * o->ny * o->nz;
+  o->periodic_enabled = config->periodic[0] || config->periodic[1] || config->periodic[2];
+  o->n_floating = 0;
+  o->iteration_number = 0;
+  o->current_time = 0.;
+  o->contact_search_trigger = true;
+  o->clear_tangential_displacement_trigger = false;
+  o->contact_build_number = 0;
+  o->n_touching_last = 0;
+  build_cell_order(*o);
+  find_cell_neighbors(*o);
+  find_cell_periodic_neighbors(*o);
+  compute_combined_periodic_offsets(*o);
+  set_effective_properties(*o);
+  o->cell_parts.assign(o->n_cells, std::vector<int>());
+  o->cell_faces.assign(o->n_cells, std::vector<int>());
+  *out = reinterpret_cast<lethe_dem_ctx *>(o);
+  return 0;
+}
+
+void oracle_dem_destroy(lethe_dem_ctx *ctx) { delete reinterpret_cast<Oracle *>(ctx); }
+const char *oracle_dem_last_error(const lethe_dem_ctx *ctx) { return reinterpret_cast<const Oracle *>(ctx)->error.c_str(); }
+const char *oracle_dem_create_error(void) { return g_create_error.c_str(); }
+
+int oracle_dem_add_particles(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *x3, const double *props9)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  for (uint64_t i = 0; i < n; ++i)
+    {
+      Particle p;
+      p.id = id[i];
+      p.x = mk(x3[3 * i], x3[3 * i + 1], x3[3 * i + 2]);
+      std::memcpy(p.p, props9 + 9 * i, 9 * sizeof(double));
+      p.cell = cell_of_point(*o, p.x);
+      o->parts.push_back(p);
+      o->force.push_back(mk(0, 0, 0));
+      o->torque.push_back(mk(0, 0, 0));
+      o->displacement.push_back(0.);
+      o->MOI.push_back(0.1 * p.p[P_MASS] * p.p[P_DP] * p.p[P_DP]);
+    }
+  // DEMActionManager::particle_insertion_step (dem_action_manager.h:226-230)
+  o->contact_search_trigger = true;
+  return 0;
+}
+
+int oracle_dem_set_particles(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *x3, const double *props9)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  o->parts.clear();
+  o->force.clear();
+  o->torque.clear();
+  o->displacement.clear();
+  o->MOI.clear();
+  o->local_adjacent.clear();
+  o->periodic_adjacent.clear();
+  o->wall_in_contact.clear();
+  o->fwall_in_contact.clear();
+  o->local_candidates.clear();
+  o->periodic_candidates.clear();
+  o->wall_candidates.clear();
+  o->fwall_candidates.clear();
+  return oracle_dem_add_particles(ctx, n, id, x3, props9);
+}
+
+int oracle_dem_n_particles(lethe_dem_ctx *ctx, uint64_t *n)
+{
+  *n = reinterpret_cast<Oracle *>(ctx)->parts.size();
+  return 0;
+}
+
+int oracle_dem_get_particles(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *x3, double *props9)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  std::vector<int> order(o->parts.size());
+  for (size_t s = 0; s < order.size(); ++s)
+    order[s] = int(s);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return o->parts[a].id < o->parts[b].id; });
+  uint64_t n = std::min<uint64_t>(n_max, order.size());
+  for (uint64_t i = 0; i < n; ++i)
+    {
+      const Particle &p = o->parts[order[i]];
+      id[i] = p.id;
+      for (int d = 0; d < 3; ++d)
+        x3[3 * i + d] = p.x[d];
+      std::memcpy(props9 + 9 * i, p.p, 9 * sizeof(double));
+    }
+  *n_out = n;
+  return 0;
+}
+
+int oracle_dem_set_walls(lethe_dem_ctx *ctx, uint64_t n_faces, const lethe_wall_face *faces)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  o->faces.assign(faces, faces + n_faces);
+  o->contact_search_trigger = true;
+  return 0;
+}
+
+int oracle_dem_set_floating_walls(lethe_dem_ctx *ctx, int32_t n, const double *point3, const double *normal3,
+                                  const double *t_start, const double *t_end)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  if (n < 0 || n > LETHE_DEM_MAX_FLOATING_WALLS)
+    return fail(o, "too many floating walls");
+  o->n_floating = n;
+  for (int w = 0; w < n; ++w)
+    {
+      o->fw_point[w] = mk(point3[3 * w], point3[3 * w + 1], point3[3 * w + 2]);
+      o->fw_normal[w] = mk(normal3[3 * w], normal3[3 * w + 1], normal3[3 * w + 2]);
+      o->fw_t0[w] = t_start[w];
+      o->fw_t1[w] = t_end[w];
+    }
+  // GridTools::maximal_cell_diameter of the uniform grid (dem.cc:1106-1112 -> build)
+  const double *h = o->cfg.cell_size;
+  const double maximum_cell_diameter = std::sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]);
+  find_boundary_cells_for_floating_walls(*o, maximum_cell_diameter);
+  o->contact_search_trigger = true;
+  return 0;
+}
+
+int oracle_dem_set_boundary_motion(lethe_dem_ctx *ctx, uint32_t boundary_id, const double tv[3], double speed,
+                                   const double axis[3], const double point[3])
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  BoundaryMotion m;
+  m.boundary_id = boundary_id;
+  m.translational_velocity = mk(tv[0], tv[1], tv[2]);
+  m.rotational_speed = speed;
+  m.rotational_vector = mk(axis[0], axis[1], axis[2]);
+  m.point_on_axis = mk(point[0], point[1], point[2]);
+  for (auto &e : o->motions)
+    if (e.boundary_id == boundary_id)
+      {
+        e = m;
+        return 0;
+      }
+  o->motions.push_back(m);
+  return 0;
+}
+
+int oracle_dem_step(lethe_dem_ctx *ctx, uint64_t n_steps)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  for (uint64_t s = 0; s < n_steps; ++s)
+    one_step(*o);
+  return 0;
+}
+
+// DEMSolver::synchronize_velocities (dem.cc:719-745)
+int oracle_dem_synchronize_velocities(lethe_dem_ctx *ctx)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  execute_contact_detection_and_search(*o);
+  compute_contact_forces(*o);
+  integrate_end(*o);
+  reset_triggers(*o);
+  return 0;
+}
+
+int oracle_dem_force_contact_search(lethe_dem_ctx *ctx, int clear_tangential_displacement)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  o->contact_search_trigger = true;
+  if (clear_tangential_displacement)
+    o->clear_tangential_displacement_trigger = true;
+  return 0;
+}
+
+int oracle_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n, const uint32_t *id, double *x3, double *props9)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  for (uint64_t i = 0; i < n; ++i)
+    {
+      const int s = slot(*o, id[i]);
+      if (s < 0)
+        continue;
+      o->parts[s].x = mk(x3[3 * i], x3[3 * i + 1], x3[3 * i + 2]);
+      std::memcpy(o->parts[s].p, props9 + 9 * i, 9 * sizeof(double));
+    }
+  oracle_dem_step(ctx, n_steps);
+  for (uint64_t i = 0; i < n; ++i)
+    {
+      const int s = slot(*o, id[i]);
+      if (s < 0)
+        continue;
+      for (int d = 0; d < 3; ++d)
+        x3[3 * i + d] = o->parts[s].x[d];
+      std::memcpy(props9 + 9 * i, o->parts[s].p, 9 * sizeof(double));
+    }
+  return 0;
+}
+
+// Unordered pairs (i<j by id), tangential displacement oriented i -> j.
+int oracle_dem_get_pairs(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *i_id, uint32_t *j_id,
+                         double *tangential3)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  struct E
+  {
+    uint32_t i, j;
+    V3 t;
+  };
+  std::vector<E> all;
+  for (DenseRows<PPRow> *adj : {&o->local_adjacent, &o->periodic_adjacent})
+    for (auto &row : adj->rows)
+      for (auto &e : row.second)
+        {
+          if (row.one < e.two)
+            all.push_back(E{row.one, e.two, e.tangential_displacement});
+          else
+            all.push_back(E{e.two, row.one, -e.tangential_displacement});
+        }
+  std::sort(all.begin(), all.end(), [](const E &a, const E &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
+  *n_out = all.size();
+  const uint64_t n = std::min<uint64_t>(n_max, all.size());
+  for (uint64_t k = 0; k < n; ++k)
+    {
+      i_id[k] = all[k].i;
+      j_id[k] = all[k].j;
+      if (tangential3)
+        for (int d = 0; d < 3; ++d)
+          tangential3[3 * k + d] = all[k].t[d];
+    }
+  return 0;
+}
+
+int oracle_dem_get_wall_contacts(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *particle_id,
+                                 uint32_t *face_id, double *tangential3)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  struct E
+  {
+    uint32_t p, f;
+    V3 t;
+  };
+  std::vector<E> all;
+  for (auto &row : o->wall_in_contact.rows)
+    for (auto &e : row.second)
+      all.push_back(E{row.one, e.face, e.tangential_displacement});
+  for (auto &row : o->fwall_in_contact.rows)
+    for (auto &e : row.second)
+      all.push_back(E{row.one, e.face | 0x80000000u, e.tangential_displacement});
+  std::sort(all.begin(), all.end(), [](const E &a, const E &b) { return a.p != b.p ? a.p < b.p : a.f < b.f; });
+  *n_out = all.size();
+  const uint64_t n = std::min<uint64_t>(n_max, all.size());
+  for (uint64_t k = 0; k < n; ++k)
+    {
+      particle_id[k] = all[k].p;
+      face_id[k] = all[k].f;
+      if (tangential3)
+        for (int d = 0; d < 3; ++d)
+          tangential3[3 * k + d] = all[k].t[d];
+    }
+  return 0;
+}
+
+int oracle_dem_get_forces(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *force3, double *torque3)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  if (!o->cfg.store_forces)
+    return fail(o, "store_forces not enabled");
+  std::vector<int> order(o->parts.size());
+  for (size_t s = 0; s < order.size(); ++s)
+    order[s] = int(s);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return o->parts[a].id < o->parts[b].id; });
+  const uint64_t n = std::min<uint64_t>(n_max, order.size());
+  for (uint64_t i = 0; i < n; ++i)
+    {
+      const int s = order[i];
+      id[i] = o->parts[s].id;
+      for (int d = 0; d < 3; ++d)
+        {
+          force3[3 * i + d] = size_t(s) < o->last_force.size() ? o->last_force[s][d] : 0.;
+          torque3[3 * i + d] = size_t(s) < o->last_torque.size() ? o->last_torque[s][d] : 0.;
+        }
+    }
+  *n_out = n;
+  return 0;
+}
+
+int oracle_dem_get_stats(lethe_dem_ctx *ctx, lethe_dem_stats *st)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  std::memset(st, 0, sizeof(*st));
+  st->n_particles = o->parts.size();
+  st->n_rebuilds = o->contact_build_number;
+  st->n_steps = o->iteration_number;
+  for (DenseRows<PPRow> *adj : {&o->local_adjacent, &o->periodic_adjacent})
+    for (auto &row : adj->rows)
+      st->n_pair_entries += row.second.size();
+  for (DenseRows<PWRow> *adj : {&o->wall_in_contact, &o->fwall_in_contact})
+    for (auto &row : adj->rows)
+      st->n_wall_entries += row.second.size();
+  st->n_pairs_touching = o->n_touching_last;
+  st->v_min = st->omega_min = st->ke_trans_min = st->ke_rot_min = DBL_MAX;
+  for (size_t s = 0; s < o->parts.size(); ++s)
+    {
+      const double *p = o->parts[s].p;
+      const double v2 = p[P_VX] * p[P_VX] + p[P_VY] * p[P_VY] + p[P_VZ] * p[P_VZ];
+      const double w2 = p[P_WX] * p[P_WX] + p[P_WY] * p[P_WY] + p[P_WZ] * p[P_WZ];
+      const double v = std::sqrt(v2), w = std::sqrt(w2);
+      const double ket = 0.5 * p[P_MASS] * v2;
+      const double ker = 0.5 * (0.1 * p[P_MASS] * p[P_DP] * p[P_DP]) * w2;
+      st->v_min = std::min(st->v_min, v);
+      st->v_max = std::max(st->v_max, v);
+      st->v_sum += v;
+      st->omega_min = std::min(st->omega_min, w);
+      st->omega_max = std::max(st->omega_max, w);
+      st->omega_sum += w;
+      st->ke_trans_min = std::min(st->ke_trans_min, ket);
+      st->ke_trans_max = std::max(st->ke_trans_max, ket);
+      st->ke_trans_sum += ket;
+      st->ke_rot_min = std::min(st->ke_rot_min, ker);
+      st->ke_rot_max = std::max(st->ke_rot_max, ker);
+      st->ke_rot_sum += ker;
+    }
+  if (o->parts.empty())
+    st->v_min = st->omega_min = st->ke_trans_min = st->ke_rot_min = 0;
+  return 0;
+}
+
+// ---- single-contact taps used by the golden-vector tests (no grid needed) ----
+// One particle-particle contact evaluation exactly as execute_contact_calculation
+// does for one pair: returns force on particle one/two and torques; updates history.
+int oracle_dem_pair_force(lethe_dem_ctx *ctx, const double *x1, const double *p1, const double *x2, const double *p2,
+                          double *tangential3, double *rolling3, double *force_one3, double *torque_one3,
+                          double *force_two3, double *torque_two3, double *overlap)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  PPInfo info;
+  info.two = 1;
+  info.tangential_displacement = mk(tangential3[0], tangential3[1], tangential3[2]);
+  info.rolling_resistance_spring_torque = mk(rolling3[0], rolling3[1], rolling3[2]);
+  info.periodic_offset = mk(0, 0, 0);
+  const V3 a = mk(x1[0], x1[1], x1[2]), b = mk(x2[0], x2[1], x2[2]);
+  const double normal_overlap = 0.5 * (p1[P_DP] + p2[P_DP]) - std::sqrt(distance_square(a, b));
+  *overlap = normal_overlap;
+  V3 f1 = mk(0, 0, 0), f2 = mk(0, 0, 0), t1 = mk(0, 0, 0), t2 = mk(0, 0, 0);
+  if (normal_overlap > o->pp_force_threshold)
+    {
+      PPOut out;
+      out.normal_force = out.tangential_force = out.t1 = out.t2 = out.rolling = mk(0, 0, 0);
+      V3 n, vt;
+      double vn;
+      pp_update_contact_information(info, vt, vn, n, p1, p2, a, b, o->cfg.dt);
+      pp_calculate_contact(*o, o->cfg.pp_model, info, vt, vn, n, normal_overlap, o->cfg.dt, p1, p2, out);
+      const V3 total = out.normal_force + out.tangential_force;
+      f1 = f1 - total;
+      f2 = f2 + total;
+      t1 = t1 + (-out.t1 + out.rolling);
+      t2 = t2 + (-out.t2 - out.rolling);
+    }
+  else
+    {
+      info.tangential_displacement = mk(0, 0, 0);
+      info.rolling_resistance_spring_torque = mk(0, 0, 0);
+    }
+  for (int d = 0; d < 3; ++d)
+    {
+      tangential3[d] = info.tangential_displacement[d];
+      rolling3[d] = info.rolling_resistance_spring_torque[d];
+      force_one3[d] = f1[d];
+      force_two3[d] = f2[d];
+      torque_one3[d] = t1[d];
+      torque_two3[d] = t2[d];
+    }
+  return 0;
+}
+
+// Integrator taps for the free-flight golden (tests/dem/integration_velocity_verlet.cc):
+// apply a constant external force / torque and an explicit MOI to every particle.
+int oracle_dem_integrate_external(lethe_dem_ctx *ctx, int phase, const double *force3, const double *torque3, double moi)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  for (size_t s = 0; s < o->parts.size(); ++s)
+    {
+      o->force[s] = mk(force3[0], force3[1], force3[2]);
+      o->torque[s] = mk(torque3[0], torque3[1], torque3[2]);
+      if (moi > 0)
+        o->MOI[s] = moi;
+    }
+  if (phase == 0)
+    integrate_start(*o);
+  else if (phase == 1)
+    integrate(*o);
+  else
+    integrate_end(*o);
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,99 @@
+"""Shared helpers for the parity tests: parameter sets of the reference's unit
+tests and synthetic packings fed identically to the oracle and the CUDA engine."""
+import json
+import math
+import os
+
+import numpy as np
+
+from lethe_b200 import abi
+from lethe_b200.prm import DEMParameters, Mesh, ParticleType
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name="unit_goldens.json"):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def sig6(x):
+    """Round to deallog's 6 significant digits."""
+    return float(f"{x:.6g}")
+
+
+def assert_sig6(value, gold, what=""):
+    # deallog prints 6 significant digits; allow one unit in the last printed digit
+    if gold == 0.0:
+        assert abs(value) < 5e-7, (what, value, gold)
+        return
+    tol = 10 ** (math.floor(math.log10(abs(gold))) - 5) * 1.0
+    assert abs(value - gold) <= tol, (what, value, gold)
+
+
+def unit_test_parameters(pp_model="hertz_mindlin_limit_overlap", pw_model="nonlinear", rolling="constant", dt=1e-5, d=0.005,
+                         young=5e7, restitution=0.5, friction=0.5, rolling_friction=0.1, rolling_viscous=0.5, g=(0, 0, 0),
+                         wall_rolling_viscous=0.1):
+    """set_default_dem_parameters + the overrides of tests/dem/*.cc: hyper_cube(-1,1) refined twice."""
+    p = DEMParameters()
+    p.time_step = dt
+    p.pp_model, p.pw_model, p.rolling_model = pp_model, pw_model, rolling
+    p.g = g
+    t = ParticleType(diameter=d, young=young, poisson=0.3, restitution=restitution, friction=friction,
+                     rolling_friction=rolling_friction, rolling_viscous_damping=rolling_viscous, surface_energy=0.0, hamaker=0.0,
+                     density=2500)
+    p.particle_types = [t]
+    p.young_wall, p.poisson_wall, p.restitution_wall, p.friction_wall = young, 0.3, restitution, friction
+    p.rolling_friction_wall, p.rolling_viscous_damping_wall = rolling_friction, wall_rolling_viscous
+    p.mesh = Mesh((-1.0,) * 3, (1.0,) * 3, (4, 4, 4), True, "morton")
+    return p
+
+
+def props_row(ptype, d, mass, v=(0, 0, 0), w=(0, 0, 0)):
+    return [ptype, d, mass, *v, *w]
+
+
+def random_packing(n_side, d=0.005, spacing=1.02, jitter=0.05, seed=19, poly=0.0, vel=0.05, density=1000.0, nz=None, n_types=1):
+    """Jittered lattice of ~n_side^3 spheres with overlaps and random velocities:
+    a dense synthetic state that exercises touching + near pairs immediately."""
+    rng = np.random.default_rng(seed)
+    nz = nz or n_side
+    ii, jj, kk = np.meshgrid(np.arange(n_side), np.arange(n_side), np.arange(nz), indexing="ij")
+    x = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], axis=1).astype(np.float64)
+    x = (x + 0.5) * (d * spacing) + rng.uniform(-jitter, jitter, x.shape) * d
+    n = len(x)
+    diam = d * (1.0 - poly * rng.uniform(0, 1, n))
+    props = np.zeros((n, 9))
+    props[:, 0] = rng.integers(0, n_types, n)
+    props[:, 1] = diam
+    props[:, 2] = density * 4.0 / 3.0 * math.pi * (diam * 0.5) ** 3
+    props[:, 3:6] = rng.normal(0, vel, (n, 3))
+    props[:, 6:9] = rng.normal(0, vel / d * 0.2, (n, 3))
+    ids = rng.permutation(n).astype(np.uint32)
+    extent = np.array([n_side, n_side, nz]) * d * spacing
+    return ids, x, props, extent
+
+
+def packing_parameters(extent, d=0.005, cell=None, pp_model="hertz_mindlin_limit_overlap", pw_model="nonlinear", rolling="none",
+                       dt=1e-5, g=(0, 0, -9.81), n_types=1, periodic=(0, 0, 0), surface_energy=0.0, hamaker=4e-19, young=1e6,
+                       cell_order="lexicographic"):
+    p = DEMParameters()
+    p.time_step = dt
+    p.pp_model, p.pw_model, p.rolling_model = pp_model, pw_model, rolling
+    p.g = g
+    p.dynamic_contact_search_factor = 0.9
+    p.particle_types = []
+    for t in range(n_types):
+        p.particle_types.append(ParticleType(diameter=d, young=young * (1 + t), poisson=0.3 - 0.05 * t, restitution=0.3 + 0.2 * t,
+                                             friction=0.1 + 0.2 * t, rolling_friction=0.1 + 0.05 * t, rolling_viscous_damping=0.1 + 0.1 * t,
+                                             surface_energy=surface_energy, hamaker=hamaker))
+    p.young_wall, p.restitution_wall, p.friction_wall = young, 0.3, 0.1
+    p.surface_energy_wall, p.hamaker_wall = surface_energy, hamaker
+    cell = cell or 2 * d
+    n = tuple(max(3, int(math.ceil(e / cell))) for e in extent)
+    p.mesh = Mesh((0.0, 0.0, 0.0), tuple(n[i] * cell for i in range(3)), n, True, cell_order)
+    from lethe_b200.prm import BoundaryCondition
+    for ax in range(3):
+        if periodic[ax]:
+            p.boundary_conditions.append(BoundaryCondition(type="periodic", periodic_id_0=2 * ax, periodic_id_1=2 * ax + 1, periodic_direction=ax))
+    return p
