@@ -218,7 +218,15 @@ int lethe_dem_get_stats(lethe_dem_ctx *ctx, lethe_dem_stats *stats);
 int lethe_dem_get_timers(lethe_dem_ctx *ctx, int reset, double *step_kernel_ms,
                          uint64_t *step_kernel_launches, double *rebuild_ms,
                          uint64_t *rebuild_launches);
-int lethe_dem_enable_timers(lethe_dem_ctx *ctx, int enable);
+/* flags: bit 0 = CUDA-event timers, bit 1 = count touching pairs in the step kernel
+ * (lethe_dem_stats.n_pairs_touching; one warp-aggregated atomic per warp). */
+int lethe_dem_enable_timers(lethe_dem_ctx *ctx, int flags);
+/* Region timing on the engine's own stream: record event `which` (0 = start, 1 = stop);
+ * lethe_dem_event_elapsed synchronises and returns the device time between them. */
+int lethe_dem_event_record(lethe_dem_ctx *ctx, int which);
+int lethe_dem_event_elapsed(lethe_dem_ctx *ctx, double *ms);
+/* Number of kernels this library has launched in the calling process so far. */
+int lethe_dem_kernel_launches(lethe_dem_ctx *ctx, uint64_t *n_launches);
 
 /* --- multi-GPU (one ctx per GPU per process; slab decomposition) --- */
 #define LETHE_DEM_NCCL_ID_BYTES 128

@@ -148,6 +148,9 @@ ABI_SYMBOLS = [
     "get_stats",
     "get_timers",
     "enable_timers",
+    "kernel_launches",
+    "event_record",
+    "event_elapsed",
     "nccl_unique_id",
     "comm_init",
 ]
@@ -320,8 +323,21 @@ class Engine:
         self._call("get_stats", C.byref(st))
         return st
 
-    def enable_timers(self, enable=True):
-        self._call("enable_timers", C.c_int(int(enable)))
+    def enable_timers(self, timers=True, count_touching=False):
+        self._call("enable_timers", C.c_int(int(bool(timers)) | (int(bool(count_touching)) << 1)))
+
+    def event_record(self, which: int):
+        self._call("event_record", C.c_int(which))
+
+    def event_elapsed_ms(self) -> float:
+        ms = C.c_double()
+        self._call("event_elapsed", C.byref(ms))
+        return ms.value
+
+    def kernel_launches(self) -> int:
+        n = C.c_uint64()
+        self._call("kernel_launches", C.byref(n))
+        return n.value
 
     def get_timers(self, reset=True):
         a, b = C.c_double(), C.c_double()

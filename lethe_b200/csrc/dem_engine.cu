@@ -1,0 +1,1318 @@
+// dem_engine.cu — host side of the B200 DEM engine: context, buffers, the per-step
+// control flow of DEMSolver::solve and the C ABI of include/lethe_dem.h.
+//
+// Control flow mirrored (source/dem/dem.cc): one lethe_dem_step iteration ==
+//   simulation_control->integrate()            (iteration_number++, time += dt)
+//   execute_contact_detection_and_search()     (:598-688)  -> rebuild() when triggered
+//   compute_contact_forces() + integrate()     (:690-717,1143-1181) -> ONE fused kernel
+//   action_manager->reset_triggers()           (:1246)
+// No CPU fallback exists: without a CUDA device lethe_dem_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dem_kernels.cuh"
+#include "dem_multi.cuh"
+
+using namespace dem;
+
+#define CU_TRY(call)                                                                                       \
+  do                                                                                                       \
+    {                                                                                                      \
+      cudaError_t err__ = (call);                                                                          \
+      if (err__ != cudaSuccess)                                                                            \
+        {                                                                                                  \
+          char buf__[512];                                                                                 \
+          snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+          throw std::runtime_error(buf__);                                                                 \
+        }                                                                                                  \
+    }                                                                                                      \
+  while (0)
+
+namespace
+{
+  template <class T> struct DevBuf
+  {
+    T *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+      if (p)
+        cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+    // grow to hold n elements; keep_n > 0 preserves the first keep_n elements
+    void ensure(size_t n, size_t keep_n = 0, cudaStream_t s = 0, double growth = 1.25)
+    {
+      if (n <= cap)
+        return;
+      size_t ncap = std::max<size_t>(n, size_t(double(cap) * growth) + 16);
+      T *np = nullptr;
+      CU_TRY(cudaMalloc(&np, ncap * sizeof(T)));
+      if (keep_n && p)
+        {
+          CU_TRY(cudaMemcpyAsync(np, p, std::min(keep_n, cap) * sizeof(T), cudaMemcpyDeviceToDevice, s));
+          CU_TRY(cudaStreamSynchronize(s));
+        }
+      if (p)
+        cudaFree(p);
+      p = np;
+      cap = ncap;
+    }
+  };
+
+  struct StateBufs
+  {
+    DevBuf<double4> pos, vel, omg;
+    DevBuf<uint32_t> id;
+    DevBuf<int32_t> cell_reg;
+    StateView view() { return StateView{pos.p, vel.p, omg.p}; }
+    void ensure(size_t n, size_t keep, cudaStream_t s)
+    {
+      pos.ensure(n, keep, s);
+      vel.ensure(n, keep, s);
+      omg.ensure(n, keep, s);
+      id.ensure(n, keep, s);
+      cell_reg.ensure(n, keep, s);
+    }
+  };
+
+  struct ListBufs
+  {
+    DevBuf<uint32_t> row_start, col;
+    DevBuf<double> hist, roll;
+    DevBuf<uint8_t> img;
+    uint32_t n_rows = 0;
+    uint64_t n_entries = 0;
+    ListView view() { return ListView{row_start.p, col.p, hist.p, roll.p, img.p}; }
+  };
+  struct WallListBufs
+  {
+    DevBuf<uint32_t> row_start, entry;
+    DevBuf<double> hist, roll;
+    uint32_t n_rows = 0;
+    uint64_t n_entries = 0;
+    WallListView view() { return WallListView{row_start.p, entry.p, hist.p, roll.p}; }
+  };
+
+  std::string g_create_error;
+} // namespace
+
+struct lethe_dem_ctx
+{
+  lethe_dem_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+
+  GridDesc grid;
+  MaterialTables mt;
+  double thr2 = 0;
+
+  // state: generation `cur` is current; the step kernel writes cur^1. ids / registered cells
+  // only change at a rebuild and follow their own generation `cur_ids`.
+  StateBufs st[2];
+  int cur = 0;
+  DevBuf<double> disp;
+  uint32_t n_owned = 0; // particles owned (integrated) by this context
+  uint32_t n_ghost = 0; // ghost copies stored behind the owned ones
+  DevBuf<uint32_t> slot_of_id;
+  uint32_t slot_map_size = 0;
+
+  // lists (double-buffered across rebuilds: the old one is the history source)
+  ListBufs lists[2];
+  WallListBufs wlists[2];
+  int cur_list = 0;
+
+  // grid tables
+  DevBuf<int32_t> cell_rank, cell_of_rank;
+  DevBuf<uint32_t> cell_count, cell_start;
+  DevBuf<uint32_t> key, slot, perm, old_of_new, counts, scan_tmp;
+
+  // walls
+  std::vector<lethe_wall_face> faces_host; // sorted by cell
+  DevBuf<uint32_t> cell_face_start;
+  DevBuf<double> face_normal, face_point;
+  DevBuf<uint32_t> face_boundary;
+  DevBuf<int32_t> face_motion;
+  uint32_t n_faces = 0;
+  std::vector<uint32_t> face_gid_host;
+  struct Motion
+  {
+    uint32_t boundary_id;
+    BoundaryMotionDev m;
+  };
+  std::vector<Motion> motions_host;
+  DevBuf<BoundaryMotionDev> motions;
+  FloatingWallsDev fw_host;
+  DevBuf<FloatingWallsDev> fw_dev;
+  DevBuf<uint32_t> cell_fw_mask;
+  bool walls_dirty = true;
+
+  // triggers / time (DEMActionManager + SimulationControl)
+  uint64_t iteration_number = 0;
+  double current_time = 0;
+  bool contact_search_trigger = true;
+  bool clear_history_trigger = false;
+  uint64_t n_rebuilds = 0;
+  int *h_flag = nullptr; // mapped pinned: written by the step kernel
+  int *d_flag = nullptr;
+
+  // debug taps
+  DevBuf<double> force_out, torque_out;
+  DevBuf<unsigned long long> touching;
+
+  // staging for host rows
+  DevBuf<uint32_t> stage_ids;
+  DevBuf<double> stage_x, stage_p;
+  DevBuf<StatsPartial> stats_partials;
+
+  // timers
+  bool timers_enabled = false;
+  bool count_touching = false;
+  cudaEvent_t region_ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> event_pool;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_step, pending_rebuild;
+  double step_ms = 0, rebuild_ms = 0;
+  uint64_t step_launches = 0, rebuild_launches = 0;
+
+  dem::MultiGpu multi;
+};
+
+namespace
+{
+  using Ctx = lethe_dem_ctx;
+
+  inline double harmonic_mean(double a, double b) { return (2 * a * b / (a + b + DBL_MIN)); }
+
+  // set_effective_properties (particle_particle_contact_force.h:1639-1746,
+  // particle_wall_contact_force.cc:588-694), evaluated on the host with glibc
+  void build_material_tables(const lethe_dem_config &c, MaterialTables &mt)
+  {
+    std::memset(&mt, 0, sizeof(mt));
+    const int n = c.n_types;
+    mt.n_types = n;
+    for (int i = 0; i < n; ++i)
+      {
+        const double Yi = c.young[i], nui = c.poisson[i];
+        for (int j = 0; j < n; ++j)
+          {
+            const int k = i * n + j;
+            const double Yj = c.young[j], nuj = c.poisson[j];
+            mt.Y[k] = (Yi * Yj) / ((Yj * (1.0 - nui * nui)) + (Yi * (1.0 - nuj * nuj)) + DBL_MIN);
+            mt.G[k] = (Yi * Yj) / (2.0 * ((Yj * (2.0 - nui) * (1.0 + nui)) + (Yi * (2.0 - nuj) * (1.0 + nuj))) + DBL_MIN);
+            const double rest = harmonic_mean(c.restitution[i], c.restitution[j]);
+            mt.mu[k] = harmonic_mean(c.friction[i], c.friction[j]);
+            mt.roll_visc[k] = harmonic_mean(c.rolling_viscous_damping[i], c.rolling_viscous_damping[j]);
+            mt.roll_fric[k] = harmonic_mean(c.rolling_friction[i], c.rolling_friction[j]);
+            mt.gamma[k] = c.surface_energy[i] + c.surface_energy[j] -
+                          std::pow(std::sqrt(c.surface_energy[i]) - std::sqrt(c.surface_energy[j]), 2);
+            mt.hamaker[k] = 0.5 * (c.hamaker[i] + c.hamaker[j]);
+            const double lg = std::log(rest);
+            mt.beta[k] = lg / std::sqrt(lg * lg + 9.8696);
+          }
+        const double Yw = c.young_wall, nuw = c.poisson_wall;
+        mt.wY[i] = (Yi * Yw) / (Yw * (1. - nui * nui) + Yi * (1. - nuw * nuw) + DBL_MIN);
+        mt.wG[i] = (Yi * Yw) / ((2. * Yw * (2. - nui) * (1. + nui)) + (2. * Yi * (2. - nuw) * (1. + nuw)) + DBL_MIN);
+        const double rest = harmonic_mean(c.restitution[i], c.restitution_wall);
+        mt.wmu[i] = harmonic_mean(c.friction[i], c.friction_wall);
+        mt.wroll_fric[i] = harmonic_mean(c.rolling_friction[i], c.rolling_friction_wall);
+        mt.wroll_visc[i] = harmonic_mean(c.rolling_viscous_damping[i], c.rolling_viscous_damping_wall);
+        mt.wgamma[i] = c.surface_energy[i] + c.surface_energy_wall -
+                       std::pow(std::sqrt(c.surface_energy[i]) - std::sqrt(c.surface_energy_wall), 2);
+        mt.whamaker[i] = 0.5 * (c.hamaker[i] + c.hamaker_wall);
+        const double lg = std::log(rest);
+        mt.wbeta[i] = lg / std::sqrt((lg * lg) + 9.8696);
+      }
+    // get_force_calculation_threshold_distance (…force.h:504-529)
+    mt.pp_force_threshold = 0.;
+    if (c.pp_model == LETHE_PP_DMT)
+      {
+        const double maxA = *std::max_element(mt.hamaker, mt.hamaker + n * n);
+        const double minG = *std::min_element(mt.gamma, mt.gamma + n * n);
+        mt.pp_force_threshold = -std::sqrt(maxA / (12. * M_PI * minG * c.dmt_cut_off_threshold));
+      }
+    mt.pw_force_threshold = 0.;
+    if (c.pw_model == LETHE_PW_DMT)
+      {
+        const double maxA = *std::max_element(mt.whamaker, mt.whamaker + n);
+        const double minG = *std::min_element(mt.wgamma, mt.wgamma + n);
+        mt.pw_force_threshold = -std::sqrt(maxA / (12. * M_PI * minG * c.dmt_cut_off_threshold));
+      }
+    mt.f_coefficient_epsd = c.f_coefficient_epsd;
+  }
+
+  // Morton (z-order) rank of every grid cell: the sort key of the particles.
+  void build_cell_curve(const GridDesc &g, std::vector<int32_t> &rank_of_cell, std::vector<int32_t> &cell_of_rank)
+  {
+    const int nmax = std::max(g.n[0], std::max(g.n[1], g.n[2]));
+    int bits = 0;
+    while ((1 << bits) < nmax)
+      ++bits;
+    std::vector<std::pair<uint64_t, int32_t>> codes;
+    codes.reserve(g.n_cells);
+    for (int k = 0; k < g.n[2]; ++k)
+      for (int j = 0; j < g.n[1]; ++j)
+        for (int i = 0; i < g.n[0]; ++i)
+          {
+            uint64_t m = 0;
+            for (int b = 0; b < bits; ++b)
+              {
+                m |= uint64_t((i >> b) & 1) << (3 * b);
+                m |= uint64_t((j >> b) & 1) << (3 * b + 1);
+                m |= uint64_t((k >> b) & 1) << (3 * b + 2);
+              }
+            codes.emplace_back(m, i + g.n[0] * (j + g.n[1] * k));
+          }
+    std::sort(codes.begin(), codes.end());
+    rank_of_cell.assign(g.n_cells, 0);
+    cell_of_rank.assign(g.n_cells, 0);
+    for (int r = 0; r < g.n_cells; ++r)
+      {
+        cell_of_rank[r] = codes[r].second;
+        rank_of_cell[codes[r].second] = r;
+      }
+  }
+
+  cudaEvent_t get_event(Ctx *c)
+  {
+    if (!c->event_pool.empty())
+      {
+        cudaEvent_t e = c->event_pool.back();
+        c->event_pool.pop_back();
+        return e;
+      }
+    cudaEvent_t e;
+    CU_TRY(cudaEventCreate(&e));
+    return e;
+  }
+  void resolve_timers(Ctx *c)
+  {
+    if (c->pending_step.empty() && c->pending_rebuild.empty())
+      return;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    for (auto &pr : c->pending_step)
+      {
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        c->step_ms += ms;
+        c->event_pool.push_back(pr.first);
+        c->event_pool.push_back(pr.second);
+      }
+    for (auto &pr : c->pending_rebuild)
+      {
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        c->rebuild_ms += ms;
+        c->event_pool.push_back(pr.first);
+        c->event_pool.push_back(pr.second);
+      }
+    c->pending_step.clear();
+    c->pending_rebuild.clear();
+  }
+
+  void upload_walls(Ctx *c)
+  {
+    if (!c->walls_dirty)
+      return;
+    const int n_cells = c->grid.n_cells;
+    // face table sorted by cell (stable: keeps the host's order inside a cell)
+    std::vector<lethe_wall_face> f = c->faces_host;
+    std::stable_sort(f.begin(), f.end(), [](const lethe_wall_face &a, const lethe_wall_face &b) { return a.cell < b.cell; });
+    c->n_faces = uint32_t(f.size());
+    std::vector<uint32_t> start(size_t(n_cells) + 1, 0);
+    for (auto &face : f)
+      start[size_t(face.cell) + 1]++;
+    for (int k = 0; k < n_cells; ++k)
+      start[k + 1] += start[k];
+    std::vector<double> nrm(3 * f.size() + 3), pt(3 * f.size() + 3);
+    std::vector<uint32_t> bid(f.size() + 1);
+    std::vector<int32_t> mot(f.size() + 1, -1);
+    c->face_gid_host.assign(f.size(), 0);
+    for (size_t k = 0; k < f.size(); ++k)
+      {
+        for (int d = 0; d < 3; ++d)
+          {
+            nrm[3 * k + d] = f[k].normal[d];
+            pt[3 * k + d] = f[k].point[d];
+          }
+        bid[k] = f[k].boundary_id;
+        c->face_gid_host[k] = f[k].global_face_id;
+        for (size_t m = 0; m < c->motions_host.size(); ++m)
+          if (c->motions_host[m].boundary_id == f[k].boundary_id)
+            mot[k] = int32_t(m);
+      }
+    c->cell_face_start.ensure(start.size());
+    c->face_normal.ensure(nrm.size());
+    c->face_point.ensure(pt.size());
+    c->face_boundary.ensure(bid.size());
+    c->face_motion.ensure(mot.size());
+    CU_TRY(cudaMemcpyAsync(c->cell_face_start.p, start.data(), start.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->face_normal.p, nrm.data(), nrm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->face_point.p, pt.data(), pt.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->face_boundary.p, bid.data(), bid.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->face_motion.p, mot.data(), mot.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    std::vector<BoundaryMotionDev> md(std::max<size_t>(1, c->motions_host.size()));
+    for (size_t m = 0; m < c->motions_host.size(); ++m)
+      md[m] = c->motions_host[m].m;
+    c->motions.ensure(md.size());
+    CU_TRY(cudaMemcpyAsync(c->motions.p, md.data(), md.size() * sizeof(BoundaryMotionDev), cudaMemcpyHostToDevice, c->stream));
+    // floating walls: boundary cells = cells with a vertex closer than the maximal cell
+    // diameter to the plane (find_boundary_cells_information.cc:653-703)
+    c->fw_dev.ensure(1);
+    CU_TRY(cudaMemcpyAsync(c->fw_dev.p, &c->fw_host, sizeof(FloatingWallsDev), cudaMemcpyHostToDevice, c->stream));
+    if (c->fw_host.n > 0)
+      {
+        std::vector<uint32_t> mask(n_cells, 0);
+        const GridDesc &g = c->grid;
+        const double maxd = std::sqrt(g.h[0] * g.h[0] + g.h[1] * g.h[1] + g.h[2] * g.h[2]);
+        for (int w = 0; w < c->fw_host.n; ++w)
+          for (int cell = 0; cell < n_cells; ++cell)
+            {
+              const int ci[3] = {cell % g.n[0], (cell / g.n[0]) % g.n[1], cell / (g.n[0] * g.n[1])};
+              for (int v = 0; v < 8; ++v)
+                {
+                  const double vx[3] = {g.lo[0] + (ci[0] + (v & 1)) * g.h[0], g.lo[1] + (ci[1] + ((v >> 1) & 1)) * g.h[1],
+                                        g.lo[2] + (ci[2] + ((v >> 2) & 1)) * g.h[2]};
+                  const double cv[3] = {vx[0] - c->fw_host.point[w][0], vx[1] - c->fw_host.point[w][1],
+                                        vx[2] - c->fw_host.point[w][2]};
+                  const double dist =
+                    (cv[0] * c->fw_host.normal[w][0] + cv[1] * c->fw_host.normal[w][1]) + cv[2] * c->fw_host.normal[w][2];
+                  if (std::fabs(dist) < maxd)
+                    {
+                      mask[cell] |= 1u << w;
+                      break;
+                    }
+                }
+            }
+        c->cell_fw_mask.ensure(mask.size());
+        CU_TRY(cudaMemcpyAsync(c->cell_fw_mask.p, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->walls_dirty = false;
+  }
+
+  FaceTable face_table(Ctx *c)
+  {
+    return FaceTable{c->cell_face_start.p, c->face_normal.p, c->face_point.p, c->face_boundary.p, c->face_motion.p, c->n_faces};
+  }
+
+  uint32_t read_u32(Ctx *c, const uint32_t *dptr)
+  {
+    uint32_t v = 0;
+    CU_TRY(cudaMemcpyAsync(&v, dptr, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return v;
+  }
+
+  // ------------------------------------------------------------ rebuild ----
+  void rebuild(Ctx *c)
+  {
+    cudaStream_t s = c->stream;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (c->timers_enabled)
+      {
+        ev0 = get_event(c);
+        ev1 = get_event(c);
+        CU_TRY(cudaEventRecord(ev0, s));
+      }
+    upload_walls(c);
+    const int n_cells = c->grid.n_cells;
+    const bool use_roll = c->cfg.rolling_model == LETHE_ROLLING_EPSD;
+    const bool use_img = c->grid.periodic[0] || c->grid.periodic[1] || c->grid.periodic[2];
+
+    // multi-GPU: drop last rebuild's ghosts; they are re-exchanged below
+    uint32_t n = c->n_owned;
+    StateBufs &src = c->st[c->cur];
+    StateBufs &dst = c->st[c->cur ^ 1];
+
+    // 1. bin + periodic wrap
+    c->key.ensure(n + 1);
+    c->slot.ensure(n + 1);
+    c->perm.ensure(n + 1);
+    c->cell_count.ensure(size_t(n_cells) + 8);
+    c->cell_start.ensure(size_t(n_cells) + 8);
+    c->scan_tmp.ensure(scan_tmp_elems(std::max<size_t>(size_t(n_cells) + 8, size_t(n) + 8)));
+    CU_TRY(cudaMemsetAsync(c->cell_count.p, 0, (size_t(n_cells) + 8) * 4, s));
+    BinParams bp{src.pos.p, src.cell_reg.p, c->grid, c->cell_rank.p, c->cell_count.p, c->key.p, c->slot.p, n};
+    launch_bin(bp, s);
+    // buckets: [0,n_cells) cells in curve order, n_cells = left the domain (+ migration buckets)
+    const size_t n_buckets = size_t(n_cells) + 3;
+    exclusive_scan_u32(c->cell_count.p, c->cell_start.p, n_buckets + 1, c->scan_tmp.p, s);
+    launch_scatter_perm(c->key.p, c->slot.p, c->cell_start.p, c->perm.p, n, s);
+    launch_sort_cells(c->cell_start.p, uint32_t(n_buckets), c->perm.p, src.id.p, s);
+    const uint32_t n_new = read_u32(c, c->cell_start.p + n_cells); // particles still inside the domain
+
+    // 2. permute the state into cell order
+    dst.ensure(std::max<size_t>(n_new, 1), 0, s);
+    c->old_of_new.ensure(std::max<size_t>(n_new, 1));
+    c->disp.ensure(std::max<size_t>(n_new, 1), 0, s);
+    if (c->slot_map_size)
+      launch_fill_u32(c->slot_of_id.p, 0xffffffffu, c->slot_map_size, s);
+    GatherParams gp{src.view(), dst.view(), src.id.p,       dst.id.p,       c->perm.p, c->key.p,
+                    c->cell_of_rank.p, dst.cell_reg.p,      c->old_of_new.p, c->disp.p, c->slot_of_id.p, n_new};
+    launch_gather(gp, s);
+    c->cur ^= 1;
+    c->n_owned = n_new;
+    c->n_ghost = 0;
+    StateBufs &stn = c->st[c->cur];
+    // the other generation must be able to hold the step kernel's output
+    c->st[c->cur ^ 1].ensure(std::max<size_t>(n_new, 1), 0, s);
+
+    // 3. particle-particle list
+    ListBufs &oldl = c->lists[c->cur_list];
+    ListBufs &newl = c->lists[c->cur_list ^ 1];
+    c->counts.ensure(size_t(n_new) + 2);
+    newl.row_start.ensure(size_t(n_new) + 2);
+    NeighborParams np;
+    np.st = stn.view();
+    np.cell_reg = stn.cell_reg.p;
+    np.cell_rank = c->cell_rank.p;
+    np.cell_start = c->cell_start.p;
+    np.grid = c->grid;
+    np.thr2 = c->thr2;
+    np.n_rows = n_new;
+    np.n_total = n_new;
+    np.old_list = oldl.view();
+    np.old_of_new = c->old_of_new.p;
+    np.n_old_rows = oldl.n_rows;
+    np.clear_history = c->clear_history_trigger ? 1 : 0;
+    np.new_list = newl.view();
+    np.counts = c->counts.p;
+    np.use_roll = use_roll;
+    np.use_img = use_img;
+    launch_count_neighbors(np, s);
+    exclusive_scan_u32(c->counts.p, newl.row_start.p, size_t(n_new) + 1, c->scan_tmp.p, s);
+    const uint32_t n_entries = n_new ? read_u32(c, newl.row_start.p + n_new) : 0;
+    newl.col.ensure(std::max<size_t>(n_entries, 1));
+    newl.hist.ensure(std::max<size_t>(3 * size_t(n_entries), 1));
+    if (use_roll)
+      newl.roll.ensure(std::max<size_t>(3 * size_t(n_entries), 1));
+    if (use_img)
+      newl.img.ensure(std::max<size_t>(n_entries, 1));
+    np.new_list = newl.view();
+    launch_fill_neighbors(np, s);
+    newl.n_rows = n_new;
+    newl.n_entries = n_entries;
+
+    // 4. particle-wall list
+    WallListBufs &oldw = c->wlists[c->cur_list];
+    WallListBufs &neww = c->wlists[c->cur_list ^ 1];
+    neww.row_start.ensure(size_t(n_new) + 2);
+    WallBuildParams wp;
+    wp.st = stn.view();
+    wp.cell_reg = stn.cell_reg.p;
+    wp.grid = c->grid;
+    wp.faces = face_table(c);
+    wp.floating = c->fw_host.n > 0 ? c->fw_dev.p : nullptr;
+    wp.cell_fw_mask = c->fw_host.n > 0 ? c->cell_fw_mask.p : nullptr;
+    wp.time = c->current_time;
+    wp.n_rows = n_new;
+    wp.old_list = oldw.view();
+    wp.old_of_new = c->old_of_new.p;
+    wp.n_old_rows = oldw.n_rows;
+    wp.clear_history = c->clear_history_trigger ? 1 : 0;
+    wp.new_list = neww.view();
+    wp.counts = c->counts.p;
+    wp.use_roll = use_roll;
+    launch_count_walls(wp, s);
+    exclusive_scan_u32(c->counts.p, neww.row_start.p, size_t(n_new) + 1, c->scan_tmp.p, s);
+    const uint32_t n_wall = n_new ? read_u32(c, neww.row_start.p + n_new) : 0;
+    neww.entry.ensure(std::max<size_t>(n_wall, 1));
+    neww.hist.ensure(std::max<size_t>(3 * size_t(n_wall), 1));
+    if (use_roll)
+      neww.roll.ensure(std::max<size_t>(3 * size_t(n_wall), 1));
+    wp.new_list = neww.view();
+    launch_fill_walls(wp, s);
+    neww.n_rows = n_new;
+    neww.n_entries = n_wall;
+
+    c->cur_list ^= 1;
+    *c->h_flag = 0; // stream is idle w.r.t. the flag: last reader/writer synchronised above
+    ++c->n_rebuilds;
+    if (c->timers_enabled)
+      {
+        CU_TRY(cudaEventRecord(ev1, s));
+        c->pending_rebuild.emplace_back(ev0, ev1);
+        ++c->rebuild_launches;
+      }
+  }
+
+  void launch_step_kernel(Ctx *c, int phase)
+  {
+    cudaStream_t s = c->stream;
+    StepParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.in = c->st[c->cur].view();
+    P.out = c->st[c->cur ^ 1].view();
+    P.list = c->lists[c->cur_list].view();
+    P.walls = c->wlists[c->cur_list].view();
+    P.id = c->st[c->cur].id.p;
+    P.disp = c->disp.p;
+    P.rebuild_flag = c->d_flag;
+    if (c->cfg.store_forces || c->count_touching)
+      {
+        c->touching.ensure(1);
+        CU_TRY(cudaMemsetAsync(c->touching.p, 0, sizeof(unsigned long long), s));
+        P.touching_counter = c->touching.p;
+      }
+    if (c->cfg.store_forces)
+      {
+        c->force_out.ensure(std::max<size_t>(3 * size_t(c->n_owned), 1));
+        c->torque_out.ensure(std::max<size_t>(3 * size_t(c->n_owned), 1));
+        P.force_out = c->force_out.p;
+        P.torque_out = c->torque_out.p;
+      }
+    P.faces = face_table(c);
+    P.motions = c->motions.p;
+    P.floating = c->fw_dev.p;
+    P.n_owned = c->n_owned;
+    P.phase = phase;
+    P.pw_model = c->cfg.pw_model;
+    P.rolling_model = c->cfg.rolling_model;
+    P.periodic_any = c->grid.periodic[0] || c->grid.periodic[1] || c->grid.periodic[2];
+    P.dt = c->cfg.dt;
+    for (int d = 0; d < 3; ++d)
+      {
+        P.g[d] = c->cfg.g[d];
+        P.L[d] = c->grid.L[d];
+      }
+    P.criterion = c->cfg.smallest_contact_search_criterion;
+    P.moi_override = c->cfg.moi_override;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (c->timers_enabled)
+      {
+        ev0 = get_event(c);
+        ev1 = get_event(c);
+        CU_TRY(cudaEventRecord(ev0, s));
+      }
+    launch_step(c->cfg.pp_model, c->cfg.rolling_model, P, c->mt, s);
+    if (c->timers_enabled)
+      {
+        CU_TRY(cudaEventRecord(ev1, s));
+        c->pending_step.emplace_back(ev0, ev1);
+        ++c->step_launches;
+        if (c->pending_step.size() > 4096)
+          resolve_timers(c);
+      }
+    CU_TRY(cudaGetLastError());
+    // ids / registered cells do not change in a step: both generations share them logically;
+    // keep the other generation's copies in sync lazily (they are only read at rebuilds).
+    c->cur ^= 1;
+  }
+
+  // ids and cell_reg live per generation; after a step the "current" generation flips, so
+  // mirror them once per rebuild into both generations.
+  void mirror_ids(Ctx *c)
+  {
+    StateBufs &a = c->st[c->cur], &b = c->st[c->cur ^ 1];
+    const size_t n = c->n_owned;
+    if (!n)
+      return;
+    b.id.ensure(n);
+    b.cell_reg.ensure(n);
+    CU_TRY(cudaMemcpyAsync(b.id.p, a.id.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(b.cell_reg.p, a.cell_reg.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+  }
+
+  // execute_contact_detection_and_search (dem.cc:598-688) + check functions (dem.cc:459-482)
+  void contact_detection_and_search(Ctx *c)
+  {
+    bool search = c->contact_search_trigger;
+    const uint64_t freq = uint64_t(std::max(1, c->cfg.contact_detection_frequency));
+    if (c->cfg.detection == LETHE_DETECTION_CONSTANT)
+      {
+        if ((c->iteration_number % freq) == 0)
+          search = true;
+      }
+    else if (!search && (c->iteration_number % freq) == 0)
+      {
+        // max displacement > criterion, evaluated by the previous step kernel
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (*c->h_flag)
+          search = true;
+      }
+    if (search)
+      {
+        if (c->multi.enabled())
+          c->multi.rebuild_with_exchange(c);
+        else
+          {
+            rebuild(c);
+            mirror_ids(c);
+          }
+      }
+    else if (c->multi.enabled())
+      c->multi.refresh_ghosts(c);
+  }
+
+  void one_step(Ctx *c)
+  {
+    c->iteration_number++;
+    c->current_time += c->cfg.dt;
+    contact_detection_and_search(c);
+    const int phase = (c->iteration_number <= 1 && !c->cfg.restart) ? PHASE_START : PHASE_REGULAR;
+    launch_step_kernel(c, phase);
+    c->contact_search_trigger = false;
+    c->clear_history_trigger = false;
+  }
+
+  template <class F> int guarded(Ctx *c, F &&f)
+  {
+    try
+      {
+        CU_TRY(cudaSetDevice(c->device));
+        f();
+        return 0;
+      }
+    catch (const std::exception &e)
+      {
+        c->error = e.what();
+        return -1;
+      }
+  }
+
+  void append_particles(Ctx *c, uint64_t n, const uint32_t *id, const double *x3, const double *props9)
+  {
+    if (n == 0)
+      return;
+    cudaStream_t s = c->stream;
+    const size_t base = c->n_owned;
+    const size_t total = base + n;
+    if (total >= 0x7fffffffull)
+      throw std::runtime_error("too many particles for 31-bit indices");
+    c->st[c->cur].ensure(total, base, s);
+    c->st[c->cur ^ 1].ensure(total, 0, s);
+    c->disp.ensure(total, base, s);
+    c->stage_ids.ensure(n);
+    c->stage_x.ensure(3 * n);
+    c->stage_p.ensure(9 * n);
+    CU_TRY(cudaMemcpyAsync(c->stage_ids.p, id, n * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(c->stage_x.p, x3, 3 * n * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(c->stage_p.p, props9, 9 * n * 8, cudaMemcpyHostToDevice, s));
+    launch_unpack_host_rows(c->stage_ids.p, c->stage_x.p, c->stage_p.p, uint32_t(n), c->st[c->cur].view(), c->st[c->cur].id.p,
+                            c->st[c->cur].cell_reg.p, c->disp.p, uint32_t(base), s);
+    uint32_t max_id = 0;
+    for (uint64_t k = 0; k < n; ++k)
+      max_id = std::max(max_id, id[k]);
+    if (size_t(max_id) + 1 > c->slot_map_size)
+      {
+        const size_t old = c->slot_map_size;
+        c->slot_of_id.ensure(size_t(max_id) + 1, old, s, 1.5);
+        launch_fill_u32(c->slot_of_id.p + old, 0xffffffffu, size_t(max_id) + 1 - old, s);
+        c->slot_map_size = uint32_t(size_t(max_id) + 1);
+      }
+    CU_TRY(cudaStreamSynchronize(s));
+    c->n_owned = uint32_t(total);
+    c->n_ghost = 0;
+    // DEMActionManager::particle_insertion_step
+    c->contact_search_trigger = true;
+  }
+
+  struct HostRows
+  {
+    std::vector<uint32_t> id;
+    std::vector<double> x, p;
+  };
+  void download_rows(Ctx *c, HostRows &h)
+  {
+    const size_t n = c->n_owned;
+    h.id.resize(n);
+    h.x.resize(3 * n);
+    h.p.resize(9 * n);
+    if (!n)
+      return;
+    cudaStream_t s = c->stream;
+    c->stage_ids.ensure(n);
+    c->stage_x.ensure(3 * n);
+    c->stage_p.ensure(9 * n);
+    launch_pack_all_rows(c->st[c->cur].view(), c->st[c->cur].id.p, uint32_t(n), c->stage_ids.p, c->stage_x.p, c->stage_p.p, s);
+    CU_TRY(cudaMemcpyAsync(h.id.data(), c->stage_ids.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(h.x.data(), c->stage_x.p, 3 * n * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(h.p.data(), c->stage_p.p, 9 * n * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+  }
+} // namespace
+
+// hooks used by dem_multi.cu
+namespace dem
+{
+  void engine_rebuild_local(lethe_dem_ctx *c)
+  {
+    rebuild(c);
+    mirror_ids(c);
+  }
+} // namespace dem
+
+// =================================================================== C ABI ===
+extern "C" {
+
+const char *lethe_dem_create_error(void) { return g_create_error.c_str(); }
+
+int lethe_dem_create(const lethe_dem_config *config, int device, lethe_dem_ctx **out)
+{
+  if (!config || !out)
+    {
+      g_create_error = "null argument";
+      return -1;
+    }
+  auto bad = [&](const char *m) {
+    g_create_error = m;
+    return -1;
+  };
+  if (config->n_types < 1 || config->n_types > LETHE_DEM_MAX_TYPES)
+    return bad("n_types out of range (1..5)");
+  if (config->grid_n[0] < 1 || config->grid_n[1] < 1 || config->grid_n[2] < 1)
+    return bad("grid_n must be positive");
+  if (config->integrator != LETHE_INTEGRATOR_VELOCITY_VERLET)
+    return bad("only the velocity_verlet integrator is on the B200 path");
+  if (config->pp_model < 0 || config->pp_model > LETHE_PP_DMT || config->pw_model < 0 || config->pw_model > LETHE_PW_DMT ||
+      config->rolling_model < 0 || config->rolling_model > LETHE_ROLLING_EPSD)
+    return bad("invalid contact model selector");
+  if (!(config->dt > 0))
+    return bad("dt must be positive");
+  for (int d = 0; d < 3; ++d)
+    if (config->periodic[d] && config->grid_n[d] < 3)
+      return bad("a periodic direction needs at least 3 grid cells");
+  if (double(config->grid_n[0]) * config->grid_n[1] * config->grid_n[2] > 2.0e9)
+    return bad("grid too large");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    {
+      g_create_error = std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e);
+      return -2;
+    }
+  if (device < 0 || device >= n_dev)
+    return bad("device index out of range");
+  lethe_dem_ctx *c = nullptr;
+  try
+    {
+      CU_TRY(cudaSetDevice(device));
+      c = new lethe_dem_ctx();
+      c->cfg = *config;
+      c->device = device;
+      CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      GridDesc &g = c->grid;
+      for (int d = 0; d < 3; ++d)
+        {
+          g.lo[d] = config->grid_lo[d];
+          g.h[d] = config->cell_size[d];
+          g.n[d] = config->grid_n[d];
+          g.periodic[d] = config->periodic[d];
+          g.L[d] = (config->grid_lo[d] + config->grid_n[d] * config->cell_size[d]) - config->grid_lo[d];
+        }
+      g.n_cells = g.n[0] * g.n[1] * g.n[2];
+      g.slab_axis = config->slab_axis;
+      g.slab_lo = config->slab_lo;
+      g.slab_hi = config->slab_hi;
+      build_material_tables(*config, c->mt);
+      c->thr2 = std::pow(config->neighborhood_threshold * config->d_max, 2); // dem.cc:156-159
+      std::vector<int32_t> rank, inv;
+      build_cell_curve(g, rank, inv);
+      c->cell_rank.ensure(rank.size());
+      c->cell_of_rank.ensure(inv.size());
+      CU_TRY(cudaMemcpy(c->cell_rank.p, rank.data(), rank.size() * 4, cudaMemcpyHostToDevice));
+      CU_TRY(cudaMemcpy(c->cell_of_rank.p, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+      CU_TRY(cudaHostAlloc(&c->h_flag, sizeof(int), cudaHostAllocMapped));
+      *c->h_flag = 0;
+      CU_TRY(cudaHostGetDevicePointer(&c->d_flag, c->h_flag, 0));
+      std::memset(&c->fw_host, 0, sizeof(c->fw_host));
+      // empty lists so that a step with zero particles is well defined
+      for (int k = 0; k < 2; ++k)
+        {
+          c->lists[k].row_start.ensure(2);
+          c->wlists[k].row_start.ensure(2);
+          CU_TRY(cudaMemset(c->lists[k].row_start.p, 0, 8));
+          CU_TRY(cudaMemset(c->wlists[k].row_start.p, 0, 8));
+        }
+      c->walls_dirty = true;
+    }
+  catch (const std::exception &ex)
+    {
+      g_create_error = ex.what();
+      delete c;
+      return -3;
+    }
+  *out = c;
+  return 0;
+}
+
+void lethe_dem_destroy(lethe_dem_ctx *c)
+{
+  if (!c)
+    return;
+  cudaSetDevice(c->device);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
+  c->multi.shutdown();
+  for (auto &pr : c->pending_step)
+    {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+  for (auto &pr : c->pending_rebuild)
+    {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+  for (auto ev : c->event_pool)
+    cudaEventDestroy(ev);
+  for (auto ev : c->region_ev)
+    if (ev)
+      cudaEventDestroy(ev);
+  if (c->h_flag)
+    cudaFreeHost(c->h_flag);
+  if (c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *lethe_dem_last_error(const lethe_dem_ctx *c) { return c ? c->error.c_str() : "null context"; }
+
+int lethe_dem_set_particles(lethe_dem_ctx *c, uint64_t n, const uint32_t *id, const double *x3, const double *props9)
+{
+  return guarded(c, [&] {
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->n_owned = 0;
+    c->n_ghost = 0;
+    for (int k = 0; k < 2; ++k)
+      {
+        c->lists[k].n_rows = 0;
+        c->lists[k].n_entries = 0;
+        c->wlists[k].n_rows = 0;
+        c->wlists[k].n_entries = 0;
+      }
+    if (c->slot_map_size)
+      launch_fill_u32(c->slot_of_id.p, 0xffffffffu, c->slot_map_size, c->stream);
+    append_particles(c, n, id, x3, props9);
+    c->contact_search_trigger = true;
+  });
+}
+
+int lethe_dem_add_particles(lethe_dem_ctx *c, uint64_t n, const uint32_t *id, const double *x3, const double *props9)
+{
+  return guarded(c, [&] { append_particles(c, n, id, x3, props9); });
+}
+
+int lethe_dem_n_particles(lethe_dem_ctx *c, uint64_t *n)
+{
+  *n = c->n_owned;
+  return 0;
+}
+
+int lethe_dem_get_particles(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *x3, double *props9)
+{
+  return guarded(c, [&] {
+    HostRows h;
+    download_rows(c, h);
+    const size_t n = h.id.size();
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h.id[a] < h.id[b]; });
+    const uint64_t m = std::min<uint64_t>(n_max, n);
+    for (uint64_t k = 0; k < m; ++k)
+      {
+        const uint32_t q = order[k];
+        id[k] = h.id[q];
+        std::memcpy(x3 + 3 * k, h.x.data() + 3 * size_t(q), 24);
+        std::memcpy(props9 + 9 * k, h.p.data() + 9 * size_t(q), 72);
+      }
+    *n_out = m;
+  });
+}
+
+int lethe_dem_set_walls(lethe_dem_ctx *c, uint64_t n_faces, const lethe_wall_face *faces)
+{
+  return guarded(c, [&] {
+    for (uint64_t k = 0; k < n_faces; ++k)
+      if (faces[k].cell < 0 || faces[k].cell >= c->grid.n_cells)
+        throw std::runtime_error("wall face refers to a cell outside the grid");
+    if (n_faces > WALL_INDEX_MASK)
+      throw std::runtime_error("too many wall faces");
+    c->faces_host.assign(faces, faces + n_faces);
+    c->walls_dirty = true;
+    c->contact_search_trigger = true;
+    // face indices change: wall history cannot be matched any more
+    for (int k = 0; k < 2; ++k)
+      c->wlists[k].n_rows = 0;
+  });
+}
+
+int lethe_dem_set_floating_walls(lethe_dem_ctx *c, int32_t n, const double *point3, const double *normal3, const double *t_start,
+                                 const double *t_end)
+{
+  return guarded(c, [&] {
+    if (n < 0 || n > LETHE_DEM_MAX_FLOATING_WALLS)
+      throw std::runtime_error("at most 9 floating walls");
+    c->fw_host.n = n;
+    for (int w = 0; w < n; ++w)
+      {
+        for (int d = 0; d < 3; ++d)
+          {
+            c->fw_host.point[w][d] = point3[3 * w + d];
+            c->fw_host.normal[w][d] = normal3[3 * w + d];
+          }
+        c->fw_host.t0[w] = t_start[w];
+        c->fw_host.t1[w] = t_end[w];
+      }
+    c->walls_dirty = true;
+    c->contact_search_trigger = true;
+  });
+}
+
+int lethe_dem_set_boundary_motion(lethe_dem_ctx *c, uint32_t boundary_id, const double tv[3], double speed, const double axis[3],
+                                  const double point[3])
+{
+  return guarded(c, [&] {
+    lethe_dem_ctx::Motion m;
+    m.boundary_id = boundary_id;
+    for (int d = 0; d < 3; ++d)
+      {
+        m.m.translational_velocity[d] = tv[d];
+        m.m.rotational_vector[d] = axis[d];
+        m.m.point_on_axis[d] = point[d];
+      }
+    m.m.rotational_speed = speed;
+    bool found = false;
+    for (auto &e : c->motions_host)
+      if (e.boundary_id == boundary_id)
+        {
+          e = m;
+          found = true;
+        }
+    if (!found)
+      {
+        if (c->motions_host.size() >= LETHE_DEM_MAX_BOUNDARY_MOTIONS)
+          throw std::runtime_error("too many boundary motions");
+        c->motions_host.push_back(m);
+      }
+    c->walls_dirty = true;
+  });
+}
+
+int lethe_dem_step(lethe_dem_ctx *c, uint64_t n_steps)
+{
+  return guarded(c, [&] {
+    for (uint64_t s = 0; s < n_steps; ++s)
+      one_step(c);
+  });
+}
+
+// DEMSolver::synchronize_velocities (dem.cc:719-745)
+int lethe_dem_synchronize_velocities(lethe_dem_ctx *c)
+{
+  return guarded(c, [&] {
+    contact_detection_and_search(c);
+    launch_step_kernel(c, PHASE_END);
+    c->contact_search_trigger = false;
+    c->clear_history_trigger = false;
+  });
+}
+
+int lethe_dem_force_contact_search(lethe_dem_ctx *c, int clear_tangential_displacement)
+{
+  c->contact_search_trigger = true;
+  if (clear_tangential_displacement)
+    c->clear_history_trigger = true;
+  return 0;
+}
+
+int lethe_dem_step_host(lethe_dem_ctx *c, uint64_t n_steps, uint64_t n, const uint32_t *id, double *x3, double *props9)
+{
+  return guarded(c, [&] {
+    cudaStream_t s = c->stream;
+    if (n)
+      {
+        c->stage_ids.ensure(n);
+        c->stage_x.ensure(3 * n);
+        c->stage_p.ensure(9 * n);
+        CU_TRY(cudaMemcpyAsync(c->stage_ids.p, id, n * 4, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(c->stage_x.p, x3, 3 * n * 8, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(c->stage_p.p, props9, 9 * n * 8, cudaMemcpyHostToDevice, s));
+        launch_update_from_host_rows(c->stage_ids.p, c->stage_x.p, c->stage_p.p, uint32_t(n), c->slot_of_id.p, c->slot_map_size,
+                                     c->st[c->cur].view(), s);
+      }
+    for (uint64_t k = 0; k < n_steps; ++k)
+      one_step(c);
+    if (n)
+      {
+        launch_pack_host_rows(c->stage_ids.p, uint32_t(n), c->slot_of_id.p, c->slot_map_size, c->st[c->cur].view(), c->stage_x.p,
+                              c->stage_p.p, s);
+        CU_TRY(cudaMemcpyAsync(x3, c->stage_x.p, 3 * n * 8, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(props9, c->stage_p.p, 9 * n * 8, cudaMemcpyDeviceToHost, s));
+      }
+    CU_TRY(cudaStreamSynchronize(s));
+  });
+}
+
+int lethe_dem_get_pairs(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *i_id, uint32_t *j_id, double *tangential3)
+{
+  return guarded(c, [&] {
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    ListBufs &l = c->lists[c->cur_list];
+    const size_t n = l.n_rows, E = l.n_entries;
+    const size_t n_all = size_t(c->n_owned) + c->n_ghost;
+    std::vector<uint32_t> rs(n + 1, 0), col(E), ids(n_all);
+    std::vector<double> hist(3 * E);
+    if (n)
+      {
+        CU_TRY(cudaMemcpy(rs.data(), l.row_start.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(ids.data(), c->st[c->cur].id.p, n_all * 4, cudaMemcpyDeviceToHost));
+      }
+    if (E)
+      {
+        CU_TRY(cudaMemcpy(col.data(), l.col.p, E * 4, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(hist.data(), l.hist.p, 3 * E * 8, cudaMemcpyDeviceToHost));
+      }
+    struct P
+    {
+      uint32_t i, j;
+      double t[3];
+    };
+    std::vector<P> pairs;
+    pairs.reserve(E / 2 + 1);
+    for (size_t q = 0; q < n; ++q)
+      for (uint32_t e = rs[q]; e < rs[q + 1]; ++e)
+        {
+          const uint32_t r = col[e] & COL_INDEX_MASK;
+          const uint32_t a = ids[q], b = ids[r];
+          // each unordered pair is listed from both rows; report the copy of the lower id
+          // (ghost partners have no row here, so always report those)
+          if (a < b || (r >= n && a > b))
+            {
+              P p;
+              const bool has = (col[e] & COL_HIST_BIT) != 0;
+              const double sgn = a < b ? 1.0 : -1.0;
+              p.i = std::min(a, b);
+              p.j = std::max(a, b);
+              for (int d = 0; d < 3; ++d)
+                p.t[d] = has ? sgn * hist[3 * size_t(e) + d] : 0.0;
+              pairs.push_back(p);
+            }
+        }
+    std::sort(pairs.begin(), pairs.end(), [](const P &a, const P &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
+    *n_out = pairs.size();
+    const uint64_t m = std::min<uint64_t>(n_max, pairs.size());
+    for (uint64_t k = 0; k < m; ++k)
+      {
+        i_id[k] = pairs[k].i;
+        j_id[k] = pairs[k].j;
+        if (tangential3)
+          for (int d = 0; d < 3; ++d)
+            tangential3[3 * k + d] = pairs[k].t[d];
+      }
+  });
+}
+
+int lethe_dem_get_wall_contacts(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *particle_id, uint32_t *face_id,
+                                double *tangential3)
+{
+  return guarded(c, [&] {
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    WallListBufs &l = c->wlists[c->cur_list];
+    const size_t n = l.n_rows, W = l.n_entries;
+    std::vector<uint32_t> rs(n + 1, 0), ent(W), ids(n);
+    std::vector<double> hist(3 * W);
+    if (n)
+      {
+        CU_TRY(cudaMemcpy(rs.data(), l.row_start.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(ids.data(), c->st[c->cur].id.p, n * 4, cudaMemcpyDeviceToHost));
+      }
+    if (W)
+      {
+        CU_TRY(cudaMemcpy(ent.data(), l.entry.p, W * 4, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(hist.data(), l.hist.p, 3 * W * 8, cudaMemcpyDeviceToHost));
+      }
+    struct P
+    {
+      uint32_t p, f;
+      double t[3];
+    };
+    std::vector<P> all;
+    for (size_t q = 0; q < n; ++q)
+      for (uint32_t e = rs[q]; e < rs[q + 1]; ++e)
+        {
+          P p;
+          p.p = ids[q];
+          const uint32_t idx = ent[e] & WALL_INDEX_MASK;
+          p.f = (ent[e] & WALL_FLOATING_BIT) ? (idx | 0x80000000u) : c->face_gid_host[idx];
+          for (int d = 0; d < 3; ++d)
+            p.t[d] = (ent[e] & WALL_HIST_BIT) ? hist[3 * size_t(e) + d] : 0.0;
+          all.push_back(p);
+        }
+    std::sort(all.begin(), all.end(), [](const P &a, const P &b) { return a.p != b.p ? a.p < b.p : a.f < b.f; });
+    *n_out = all.size();
+    const uint64_t m = std::min<uint64_t>(n_max, all.size());
+    for (uint64_t k = 0; k < m; ++k)
+      {
+        particle_id[k] = all[k].p;
+        face_id[k] = all[k].f;
+        if (tangential3)
+          for (int d = 0; d < 3; ++d)
+            tangential3[3 * k + d] = all[k].t[d];
+      }
+  });
+}
+
+int lethe_dem_get_forces(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *force3, double *torque3)
+{
+  return guarded(c, [&] {
+    if (!c->cfg.store_forces)
+      throw std::runtime_error("store_forces not enabled in the config");
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    const size_t n = c->n_owned;
+    std::vector<uint32_t> ids(n);
+    std::vector<double> f(3 * n), t(3 * n);
+    if (n && c->force_out.p)
+      {
+        CU_TRY(cudaMemcpy(ids.data(), c->st[c->cur].id.p, n * 4, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(f.data(), c->force_out.p, 3 * n * 8, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(t.data(), c->torque_out.p, 3 * n * 8, cudaMemcpyDeviceToHost));
+      }
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b]; });
+    const uint64_t m = std::min<uint64_t>(n_max, n);
+    for (uint64_t k = 0; k < m; ++k)
+      {
+        const uint32_t q = order[k];
+        id[k] = ids[q];
+        for (int d = 0; d < 3; ++d)
+          {
+            force3[3 * k + d] = f[3 * size_t(q) + d];
+            torque3[3 * k + d] = t[3 * size_t(q) + d];
+          }
+      }
+    *n_out = m;
+  });
+}
+
+int lethe_dem_get_stats(lethe_dem_ctx *c, lethe_dem_stats *st)
+{
+  return guarded(c, [&] {
+    std::memset(st, 0, sizeof(*st));
+    st->n_particles = c->n_owned;
+    st->n_rebuilds = c->n_rebuilds;
+    st->n_steps = c->iteration_number;
+    st->n_pair_entries = c->lists[c->cur_list].n_entries / 2;
+    st->n_wall_entries = c->wlists[c->cur_list].n_entries;
+    if (c->multi.enabled())
+      st->n_pair_entries = c->lists[c->cur_list].n_entries; // full-list entries (owned rows), not halved
+    if ((c->cfg.store_forces || c->count_touching) && c->touching.p)
+      {
+        unsigned long long t = 0;
+        CU_TRY(cudaMemcpyAsync(&t, c->touching.p, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        st->n_pairs_touching = t / 2;
+      }
+    const uint32_t n = c->n_owned;
+    if (!n)
+      return;
+    const uint32_t nb = std::min<uint32_t>((n + STATS_BLOCK - 1) / STATS_BLOCK, 148 * 8);
+    c->stats_partials.ensure(nb);
+    launch_stats(c->st[c->cur].view(), n, c->cfg.moi_override, c->stats_partials.p, nb, c->stream);
+    std::vector<StatsPartial> h(nb);
+    CU_TRY(cudaMemcpyAsync(h.data(), c->stats_partials.p, nb * sizeof(StatsPartial), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    StatsPartial a = h[0];
+    for (uint32_t b = 1; b < nb; ++b)
+      {
+        a.vmin = std::min(a.vmin, h[b].vmin);
+        a.vmax = std::max(a.vmax, h[b].vmax);
+        a.vsum += h[b].vsum;
+        a.wmin = std::min(a.wmin, h[b].wmin);
+        a.wmax = std::max(a.wmax, h[b].wmax);
+        a.wsum += h[b].wsum;
+        a.ktmin = std::min(a.ktmin, h[b].ktmin);
+        a.ktmax = std::max(a.ktmax, h[b].ktmax);
+        a.ktsum += h[b].ktsum;
+        a.krmin = std::min(a.krmin, h[b].krmin);
+        a.krmax = std::max(a.krmax, h[b].krmax);
+        a.krsum += h[b].krsum;
+      }
+    st->v_min = a.vmin;
+    st->v_max = a.vmax;
+    st->v_sum = a.vsum;
+    st->omega_min = a.wmin;
+    st->omega_max = a.wmax;
+    st->omega_sum = a.wsum;
+    st->ke_trans_min = a.ktmin;
+    st->ke_trans_max = a.ktmax;
+    st->ke_trans_sum = a.ktsum;
+    st->ke_rot_min = a.krmin;
+    st->ke_rot_max = a.krmax;
+    st->ke_rot_sum = a.krsum;
+  });
+}
+
+int lethe_dem_enable_timers(lethe_dem_ctx *c, int flags)
+{
+  return guarded(c, [&] {
+    resolve_timers(c);
+    c->timers_enabled = (flags & 1) != 0;
+    c->count_touching = (flags & 2) != 0;
+  });
+}
+
+int lethe_dem_event_record(lethe_dem_ctx *c, int which)
+{
+  return guarded(c, [&] {
+    if (which < 0 || which > 1)
+      throw std::runtime_error("event index must be 0 or 1");
+    if (!c->region_ev[which])
+      CU_TRY(cudaEventCreate(&c->region_ev[which]));
+    CU_TRY(cudaEventRecord(c->region_ev[which], c->stream));
+  });
+}
+
+int lethe_dem_event_elapsed(lethe_dem_ctx *c, double *ms)
+{
+  return guarded(c, [&] {
+    if (!c->region_ev[0] || !c->region_ev[1])
+      throw std::runtime_error("record both events first");
+    CU_TRY(cudaEventSynchronize(c->region_ev[1]));
+    float f = 0;
+    CU_TRY(cudaEventElapsedTime(&f, c->region_ev[0], c->region_ev[1]));
+    *ms = f;
+  });
+}
+
+int lethe_dem_kernel_launches(lethe_dem_ctx *, uint64_t *n_launches)
+{
+  *n_launches = dem::launch_count();
+  return 0;
+}
+
+int lethe_dem_get_timers(lethe_dem_ctx *c, int reset, double *step_kernel_ms, uint64_t *step_kernel_launches, double *rebuild_ms,
+                         uint64_t *rebuild_launches)
+{
+  return guarded(c, [&] {
+    resolve_timers(c);
+    *step_kernel_ms = c->step_ms;
+    *step_kernel_launches = c->step_launches;
+    *rebuild_ms = c->rebuild_ms;
+    *rebuild_launches = c->rebuild_launches;
+    if (reset)
+      {
+        c->step_ms = c->rebuild_ms = 0;
+        c->step_launches = c->rebuild_launches = 0;
+      }
+  });
+}
+
+int lethe_dem_nccl_unique_id(uint8_t id[LETHE_DEM_NCCL_ID_BYTES]) { return dem::MultiGpu::unique_id(id); }
+
+int lethe_dem_comm_init(lethe_dem_ctx *c, int rank, int world_size, const uint8_t id[LETHE_DEM_NCCL_ID_BYTES])
+{
+  return guarded(c, [&] { c->multi.init(c, rank, world_size, id); });
+}
+
+} // extern "C"

@@ -1,0 +1,713 @@
+// dem_kernels.cu — contact-list rebuild: cell binning along a Morton curve, counting sort,
+// neighbour (fine) search with tangential-history carry-over, wall candidate lists, scans.
+//
+// Reference path replaced (the `if (check_contact_search())` branch of
+// DEMSolver::execute_contact_detection_and_search, source/dem/dem.cc:631-683):
+//   periodic wrap              periodic_boundaries_manipulator.cc:145-224,266-338
+//   sort into cells            ParticleHandler::sort_particles_into_subdomains_and_cells (dem.cc:982-1016)
+//   pp broad search            particle_particle_broad_search.cc:9-132,316-380,735-766
+//   history reconciliation     update_fine_search_candidates.cc:9-212, update_local_particle_containers.cc:40-200
+//   pp fine search             particle_particle_fine_search.cc:19-232
+//   pw broad + fine search     particle_wall_broad_search.cc:8-125, particle_wall_fine_search.cc:18-166
+//
+// The reference's pair list after a rebuild is, as a set of unordered pairs,
+//   { (i,j) in vertex-sharing cells : d2 < thr2 }  U  { old pairs still in vertex-sharing cells : d2 == thr2 }
+// and a pair keeps its history iff it was in the list before (in the same container:
+// non-periodic vs periodic). That is what k_count/k_fill_neighbors build directly.
+#include <algorithm>
+#include <atomic>
+
+#include "dem_kernels.cuh"
+
+namespace dem
+{
+  namespace
+  {
+    constexpr int SCAN_THREADS = 256;
+    constexpr int SCAN_ITEMS = 8;
+    constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+    __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v)
+    {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+        {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+          if ((threadIdx.x & 31) >= o)
+            v += t;
+        }
+      return v;
+    }
+
+    // tile-local exclusive scan (warp shuffles + one shared-memory hop), tile totals to sums[]
+    __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t *in, uint32_t *out, size_t n, size_t n_valid,
+                                                                 uint32_t *sums)
+    {
+      __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+      const size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
+      uint32_t v[SCAN_ITEMS];
+      uint32_t local = 0;
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k)
+        {
+          const size_t idx = base + k;
+          v[k] = (idx < n_valid) ? in[idx] : 0u;
+          local += v[k];
+        }
+      const uint32_t incl = warp_inclusive_scan(local);
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      if (lane == 31)
+        warp_tot[warp] = incl;
+      __syncthreads();
+      if (warp == 0)
+        {
+          uint32_t t = (lane < SCAN_THREADS / 32) ? warp_tot[lane] : 0u;
+          t = warp_inclusive_scan(t);
+          if (lane < SCAN_THREADS / 32)
+            warp_tot[lane] = t;
+        }
+      __syncthreads();
+      uint32_t run = (incl - local) + (warp > 0 ? warp_tot[warp - 1] : 0u);
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k)
+        {
+          const size_t idx = base + k;
+          if (idx < n)
+            out[idx] = run;
+          run += v[k];
+        }
+      if (threadIdx.x == SCAN_THREADS - 1)
+        sums[blockIdx.x] = warp_tot[SCAN_THREADS / 32 - 1];
+    }
+
+    __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *out, size_t n, const uint32_t *sums_scanned)
+    {
+      const uint32_t add = sums_scanned[blockIdx.x];
+      const size_t base = size_t(blockIdx.x) * SCAN_TILE;
+      for (int k = threadIdx.x; k < SCAN_TILE; k += SCAN_THREADS)
+        {
+          const size_t idx = base + k;
+          if (idx < n)
+            out[idx] += add;
+        }
+    }
+
+    __device__ __forceinline__ int cell_of_point(const GridDesc &g, double x, double y, double z)
+    {
+      const double p[3] = {x, y, z};
+      int idx[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        {
+          const double r = (p[d] - g.lo[d]) / g.h[d];
+          const double f = floor(r);
+          if (!(f >= 0.0) || !(f < double(g.n[d])))
+            return -1;
+          idx[d] = int(f);
+        }
+      return idx[0] + g.n[0] * (idx[1] + g.n[1] * idx[2]);
+    }
+
+    __global__ void __launch_bounds__(256) k_bin(const __grid_constant__ BinParams P)
+    {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      if (p >= P.n)
+        return;
+      double4 x = P.pos[p];
+      const GridDesc &g = P.grid;
+      const int creg = P.cell_reg[p];
+      if ((g.periodic[0] | g.periodic[1] | g.periodic[2]) && creg >= 0)
+        {
+          // check_and_move_particles: only particles registered in a cell on a periodic face
+          const int c[3] = {creg % g.n[0], (creg / g.n[0]) % g.n[1], creg / (g.n[0] * g.n[1])};
+          double xv[3] = {x.x, x.y, x.z};
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            {
+              if (!g.periodic[d])
+                continue;
+              const double lo = g.lo[d];
+              const double hi = g.lo[d] + g.n[d] * g.h[d];
+              if (c[d] == 0)
+                {
+                  const double distance_with_face = (xv[d] - lo) * -1.0;
+                  if (distance_with_face >= 0.0)
+                    xv[d] += g.L[d];
+                }
+              if (c[d] == g.n[d] - 1)
+                {
+                  const double distance_with_face = (xv[d] - hi) * 1.0;
+                  if (distance_with_face >= 0.0)
+                    xv[d] += -g.L[d];
+                }
+            }
+          x.x = xv[0];
+          x.y = xv[1];
+          x.z = xv[2];
+          P.pos[p] = x;
+        }
+      const int lin = cell_of_point(g, x.x, x.y, x.z);
+      uint32_t bucket;
+      if (lin < 0)
+        bucket = uint32_t(g.n_cells); // left the triangulation: dropped
+      else
+        bucket = uint32_t(P.cell_rank[lin]);
+      P.key[p] = bucket;
+      P.slot[p] = atomicAdd(&P.cell_count[bucket], 1u);
+    }
+
+    __global__ void __launch_bounds__(256) k_scatter_perm(const uint32_t *key, const uint32_t *slot, const uint32_t *cell_start,
+                                                          uint32_t *perm, uint32_t n)
+    {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      if (p >= n)
+        return;
+      perm[cell_start[key[p]] + slot[p]] = p;
+    }
+
+    // Deterministic in-cell order: sort each cell's slice of perm by particle id (the atomic
+    // slot order is not reproducible). Cells hold a handful of particles: insertion sort.
+    __global__ void __launch_bounds__(256) k_sort_cells(const uint32_t *cell_start, uint32_t n_buckets, uint32_t *perm,
+                                                        const uint32_t *id)
+    {
+      const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+      if (c >= n_buckets)
+        return;
+      const uint32_t s = cell_start[c], e = cell_start[c + 1];
+      for (uint32_t a = s + 1; a < e; ++a)
+        {
+          const uint32_t pa = perm[a];
+          const uint32_t ida = id[pa];
+          uint32_t b = a;
+          while (b > s && id[perm[b - 1]] > ida)
+            {
+              perm[b] = perm[b - 1];
+              --b;
+            }
+          perm[b] = pa;
+        }
+    }
+
+    __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherParams P)
+    {
+      const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q >= P.n_new)
+        return;
+      const uint32_t o = P.perm[q];
+      P.out.pos[q] = P.in.pos[o];
+      P.out.vel[q] = P.in.vel[o];
+      P.out.omg[q] = P.in.omg[o];
+      const uint32_t pid = P.id_in[o];
+      P.id_out[q] = pid;
+      P.cell_reg_out[q] = P.cell_of_rank[P.key[o]];
+      P.old_of_new[q] = o;
+      P.disp[q] = 0.0;
+      P.slot_of_id[pid] = q;
+    }
+
+    // ---- neighbour search ----
+    struct NbVisitor
+    {
+      uint32_t count;
+    };
+
+    // Visits every (neighbour r, image code) of particle q that belongs in the contact list.
+    template <class F> __device__ __forceinline__ void for_each_neighbor(const NeighborParams &P, uint32_t q, F &&f)
+    {
+      const GridDesc &g = P.grid;
+      const double4 pq = P.st.pos[q];
+      const vec3 xq = v3(pq.x, pq.y, pq.z);
+      const int lin = P.cell_reg[q];
+      const int ci = lin % g.n[0], cj = (lin / g.n[0]) % g.n[1], ck = lin / (g.n[0] * g.n[1]);
+      const uint32_t old_q = P.old_of_new ? P.old_of_new[q] : 0xffffffffu;
+      for (int dz = -1; dz <= 1; ++dz)
+        {
+          // s = image shift (in units of L) that brings the neighbour cell next to mine:
+          // my cell on the low face, neighbour wrapped to the high face -> s = -1.
+          int nk = ck + dz, sz = 0;
+          if (nk < 0 || nk >= g.n[2])
+            {
+              if (!g.periodic[2])
+                continue;
+              sz = nk < 0 ? -1 : 1;
+              nk -= sz * g.n[2];
+            }
+          for (int dy = -1; dy <= 1; ++dy)
+            {
+              int nj = cj + dy, sy = 0;
+              if (nj < 0 || nj >= g.n[1])
+                {
+                  if (!g.periodic[1])
+                    continue;
+                  sy = nj < 0 ? -1 : 1;
+                  nj -= sy * g.n[1];
+                }
+              for (int dx = -1; dx <= 1; ++dx)
+                {
+                  int ni = ci + dx, sx = 0;
+                  if (ni < 0 || ni >= g.n[0])
+                    {
+                      if (!g.periodic[0])
+                        continue;
+                      sx = ni < 0 ? -1 : 1;
+                      ni -= sx * g.n[0];
+                    }
+                  const uint32_t img = (sx | sy | sz) ? uint32_t(1 + (sx + 1) + 3 * (sy + 1) + 9 * (sz + 1)) : 0u;
+                  const int nlin = ni + g.n[0] * (nj + g.n[1] * nk);
+                  const uint32_t rank = uint32_t(P.cell_rank[nlin]);
+                  const uint32_t s = P.cell_start[rank], e = P.cell_start[rank + 1];
+                  for (uint32_t r = s; r < e; ++r)
+                    {
+                      if (r == q)
+                        continue;
+                      const double4 pr = P.st.pos[r];
+                      const vec3 xr = v3(pr.x, pr.y, pr.z);
+                      double d2;
+                      if (img)
+                        {
+                          const vec3 shift = v3(sx * g.L[0], sy * g.L[1], sz * g.L[2]);
+                          const int first = sx != 0 ? sx : (sy != 0 ? sy : sz);
+                          // canonical orientation (see decode_image in dem_step.cu)
+                          if (first < 0)
+                            d2 = dist2(xq, xr + shift);
+                          else
+                            d2 = dist2(xr, xq + (-shift));
+                        }
+                      else
+                        d2 = dist2(xq, xr);
+                      bool in = d2 < P.thr2;
+                      if (!in && d2 == P.thr2 && old_q != 0xffffffffu && old_q < P.n_old_rows)
+                        {
+                          // pairs sitting exactly on the threshold are neither inserted (<) nor
+                          // erased (>): they survive iff they were already listed.
+                          const uint32_t old_r = P.old_of_new[r];
+                          for (uint32_t eo = P.old_list.row_start[old_q]; eo < P.old_list.row_start[old_q + 1]; ++eo)
+                            if ((P.old_list.col[eo] & COL_INDEX_MASK) == old_r &&
+                                ((P.use_img ? P.old_list.img[eo] != 0 : false) == (img != 0)))
+                              in = true;
+                        }
+                      if (in)
+                        f(r, img);
+                    }
+                }
+            }
+        }
+    }
+
+    __global__ void __launch_bounds__(128) k_count_neighbors(const __grid_constant__ NeighborParams P)
+    {
+      const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q >= P.n_rows)
+        return;
+      uint32_t count = 0;
+      for_each_neighbor(P, q, [&](uint32_t, uint32_t) { ++count; });
+      P.counts[q] = count;
+    }
+
+    __global__ void __launch_bounds__(128) k_fill_neighbors(const __grid_constant__ NeighborParams P)
+    {
+      const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q >= P.n_rows)
+        return;
+      uint32_t e = P.new_list.row_start[q];
+      const uint32_t old_q = P.old_of_new ? P.old_of_new[q] : 0xffffffffu;
+      const bool have_old = !P.clear_history && old_q != 0xffffffffu && old_q < P.n_old_rows;
+      uint32_t o0 = 0, o1 = 0;
+      if (have_old)
+        {
+          o0 = P.old_list.row_start[old_q];
+          o1 = P.old_list.row_start[old_q + 1];
+        }
+      for_each_neighbor(P, q, [&](uint32_t r, uint32_t img) {
+        uint32_t word = r;
+        if (have_old)
+          {
+            const uint32_t old_r = P.old_of_new[r];
+            for (uint32_t eo = o0; eo < o1; ++eo)
+              {
+                const uint32_t oc = P.old_list.col[eo];
+                if ((oc & COL_INDEX_MASK) != old_r)
+                  continue;
+                // history only survives inside the same container (periodic vs not)
+                const bool old_periodic = P.use_img ? (P.old_list.img[eo] != 0) : false;
+                if (old_periodic != (img != 0))
+                  continue;
+                if (oc & COL_HIST_BIT)
+                  {
+                    word |= COL_HIST_BIT;
+                    for (int d = 0; d < 3; ++d)
+                      P.new_list.hist[3 * size_t(e) + d] = P.old_list.hist[3 * size_t(eo) + d];
+                    if (P.use_roll)
+                      for (int d = 0; d < 3; ++d)
+                        P.new_list.roll[3 * size_t(e) + d] = P.old_list.roll[3 * size_t(eo) + d];
+                  }
+                break;
+              }
+          }
+        P.new_list.col[e] = word;
+        if (P.use_img)
+          P.new_list.img[e] = uint8_t(img);
+        ++e;
+      });
+    }
+
+    // ---- wall candidates ----
+    template <class F> __device__ __forceinline__ void for_each_wall(const WallBuildParams &P, uint32_t q, F &&f)
+    {
+      const int lin = P.cell_reg[q];
+      if (P.faces.n_faces)
+        for (uint32_t k = P.faces.cell_face_start[lin]; k < P.faces.cell_face_start[lin + 1]; ++k)
+          f(k);
+      if (P.floating && P.cell_fw_mask)
+        {
+          const uint32_t mask = P.cell_fw_mask[lin];
+          if (mask)
+            for (int w = 0; w < P.floating->n; ++w)
+              if ((mask >> w) & 1u)
+                if (P.time >= P.floating->t0[w] && P.time <= P.floating->t1[w])
+                  f(WALL_FLOATING_BIT | uint32_t(w));
+        }
+    }
+
+    __global__ void __launch_bounds__(256) k_count_walls(const __grid_constant__ WallBuildParams P)
+    {
+      const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q >= P.n_rows)
+        return;
+      uint32_t count = 0;
+      for_each_wall(P, q, [&](uint32_t) { ++count; });
+      P.counts[q] = count;
+    }
+
+    __global__ void __launch_bounds__(256) k_fill_walls(const __grid_constant__ WallBuildParams P)
+    {
+      const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q >= P.n_rows)
+        return;
+      uint32_t e = P.new_list.row_start[q];
+      const uint32_t old_q = P.old_of_new ? P.old_of_new[q] : 0xffffffffu;
+      const bool have_old = old_q != 0xffffffffu && old_q < P.n_old_rows;
+      uint32_t o0 = 0, o1 = 0;
+      if (have_old)
+        {
+          o0 = P.old_list.row_start[old_q];
+          o1 = P.old_list.row_start[old_q + 1];
+        }
+      const double4 pq = P.st.pos[q];
+      for_each_wall(P, q, [&](uint32_t key) {
+        uint32_t word = key;
+        bool found = false;
+        for (uint32_t eo = o0; eo < o1 && !found; ++eo)
+          {
+            const uint32_t oe = P.old_list.entry[eo];
+            if ((oe & (WALL_FLOATING_BIT | WALL_INDEX_MASK)) != key)
+              continue;
+            found = true;
+            // the (particle, face) pair stayed a candidate: the contact_info survives as is,
+            // including a floating wall's side (update_fine_search_candidates.cc:163-197)
+            word |= (oe & WALL_FLIPPED_BIT);
+            if ((oe & WALL_HIST_BIT) && !P.clear_history)
+              {
+                word |= WALL_HIST_BIT;
+                for (int d = 0; d < 3; ++d)
+                  P.new_list.hist[3 * size_t(e) + d] = P.old_list.hist[3 * size_t(eo) + d];
+                if (P.use_roll)
+                  for (int d = 0; d < 3; ++d)
+                    P.new_list.roll[3 * size_t(e) + d] = P.old_list.roll[3 * size_t(eo) + d];
+              }
+          }
+        if (!found && (key & WALL_FLOATING_BIT))
+          {
+            // particle_floating_wall_fine_search (particle_wall_fine_search.cc:122-140): normal
+            // flipped to the particle's side when the entry is created
+            const uint32_t w = key & WALL_INDEX_MASK;
+            const vec3 connecting_vector =
+              v3(pq.x, pq.y, pq.z) - v3(P.floating->point[w][0], P.floating->point[w][1], P.floating->point[w][2]);
+            const double ip =
+              dot(connecting_vector, v3(P.floating->normal[w][0], P.floating->normal[w][1], P.floating->normal[w][2]));
+            if (ip < 0)
+              word |= WALL_FLIPPED_BIT;
+          }
+        P.new_list.entry[e] = word;
+        ++e;
+      });
+    }
+
+    // ---- statistics ----
+    __device__ __forceinline__ double warp_min(double v)
+    {
+      for (int o = 16; o > 0; o >>= 1)
+        v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+      return v;
+    }
+    __device__ __forceinline__ double warp_max(double v)
+    {
+      for (int o = 16; o > 0; o >>= 1)
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+      return v;
+    }
+    __device__ __forceinline__ double warp_sum(double v)
+    {
+      for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+      return v;
+    }
+
+    __global__ void __launch_bounds__(STATS_BLOCK) k_stats(StateView st, uint32_t n, double moi_override, StatsPartial *partials)
+    {
+      __shared__ double sm[12][STATS_BLOCK / 32];
+      double vals[12] = {DBL_MAX, 0, 0, DBL_MAX, 0, 0, DBL_MAX, 0, 0, DBL_MAX, 0, 0};
+      for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+        {
+          const double4 x = st.pos[p], v = st.vel[p], w = st.omg[p];
+          const double v2 = v.x * v.x + v.y * v.y + v.z * v.z;
+          const double w2 = w.x * w.x + w.y * w.y + w.z * w.z;
+          const double moi = moi_override > 0 ? moi_override : 0.1 * v.w * x.w * x.w;
+          const double q[4] = {sqrt(v2), sqrt(w2), 0.5 * v.w * v2, 0.5 * moi * w2};
+          for (int k = 0; k < 4; ++k)
+            {
+              vals[3 * k] = fmin(vals[3 * k], q[k]);
+              vals[3 * k + 1] = fmax(vals[3 * k + 1], q[k]);
+              vals[3 * k + 2] += q[k];
+            }
+        }
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      for (int k = 0; k < 12; ++k)
+        {
+          const double r = (k % 3 == 0) ? warp_min(vals[k]) : (k % 3 == 1 ? warp_max(vals[k]) : warp_sum(vals[k]));
+          if (lane == 0)
+            sm[k][warp] = r;
+        }
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          double out[12];
+          for (int k = 0; k < 12; ++k)
+            {
+              double r = sm[k][0];
+              for (int w = 1; w < STATS_BLOCK / 32; ++w)
+                r = (k % 3 == 0) ? fmin(r, sm[k][w]) : (k % 3 == 1 ? fmax(r, sm[k][w]) : r + sm[k][w]);
+              out[k] = r;
+            }
+          StatsPartial sp = {out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7], out[8], out[9], out[10], out[11]};
+          partials[blockIdx.x] = sp;
+        }
+    }
+
+    // ---- host rows <-> device SoA ----
+    __global__ void __launch_bounds__(256) k_unpack_host_rows(const uint32_t *ids, const double *x3, const double *props9,
+                                                              uint32_t n, StateView st, uint32_t *id_out, int32_t *cell_reg,
+                                                              double *disp, uint32_t base)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const double *p = props9 + 9 * size_t(k);
+      const uint32_t q = base + k;
+      st.pos[q] = make_double4(x3[3 * size_t(k)], x3[3 * size_t(k) + 1], x3[3 * size_t(k) + 2], p[1]);
+      st.vel[q] = make_double4(p[3], p[4], p[5], p[2]);
+      st.omg[q] = make_double4(p[6], p[7], p[8], p[0]);
+      id_out[q] = ids[k];
+      cell_reg[q] = -1; // not registered in any cell yet (no periodic wrap before the first sort)
+      disp[q] = 0.0;
+    }
+
+    __global__ void __launch_bounds__(256) k_update_from_host_rows(const uint32_t *ids, const double *x3, const double *props9,
+                                                                   uint32_t n, const uint32_t *slot_of_id, uint32_t map_size,
+                                                                   StateView st)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t pid = ids[k];
+      if (pid >= map_size)
+        return;
+      const uint32_t q = slot_of_id[pid];
+      if (q == 0xffffffffu)
+        return;
+      const double *p = props9 + 9 * size_t(k);
+      st.pos[q] = make_double4(x3[3 * size_t(k)], x3[3 * size_t(k) + 1], x3[3 * size_t(k) + 2], p[1]);
+      st.vel[q] = make_double4(p[3], p[4], p[5], p[2]);
+      st.omg[q] = make_double4(p[6], p[7], p[8], p[0]);
+    }
+
+    __device__ __forceinline__ void write_row(double4 x, double4 v, double4 w, double *x3, double *props9, size_t k)
+    {
+      x3[3 * k] = x.x;
+      x3[3 * k + 1] = x.y;
+      x3[3 * k + 2] = x.z;
+      double *p = props9 + 9 * k;
+      p[0] = w.w;
+      p[1] = x.w;
+      p[2] = v.w;
+      p[3] = v.x;
+      p[4] = v.y;
+      p[5] = v.z;
+      p[6] = w.x;
+      p[7] = w.y;
+      p[8] = w.z;
+    }
+
+    __global__ void __launch_bounds__(256) k_pack_host_rows(const uint32_t *ids, uint32_t n, const uint32_t *slot_of_id,
+                                                            uint32_t map_size, StateView st, double *x3, double *props9)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t pid = ids[k];
+      if (pid >= map_size)
+        return;
+      const uint32_t q = slot_of_id[pid];
+      if (q == 0xffffffffu)
+        return;
+      write_row(st.pos[q], st.vel[q], st.omg[q], x3, props9, k);
+    }
+
+    __global__ void __launch_bounds__(256) k_pack_all_rows(StateView st, const uint32_t *id, uint32_t n, uint32_t *ids_out,
+                                                           double *x3, double *props9)
+    {
+      const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q >= n)
+        return;
+      ids_out[q] = id[q];
+      write_row(st.pos[q], st.vel[q], st.omg[q], x3, props9, q);
+    }
+
+    __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *p, uint32_t v, size_t n)
+    {
+      for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        p[i] = v;
+    }
+
+    inline unsigned blocks_for(size_t n, unsigned bs) { return unsigned((n + bs - 1) / bs); }
+  } // namespace
+
+  static std::atomic<unsigned long long> g_launches{0};
+  void count_launch(unsigned n) { g_launches += n; }
+  unsigned long long launch_count() { return g_launches.load(); }
+
+  size_t scan_tmp_elems(size_t n)
+  {
+    size_t total = 0;
+    size_t m = n;
+    while (m > 1)
+      {
+        m = (m + SCAN_TILE - 1) / SCAN_TILE;
+        total += 2 * (m + 1);
+        if (m == 1)
+          break;
+      }
+    return total + 8;
+  }
+
+  static void scan_rec(const uint32_t *in, uint32_t *out, size_t n, size_t n_valid, uint32_t *tmp, cudaStream_t s)
+  {
+    const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t *sums = tmp;
+    uint32_t *sums_scanned = tmp + (tiles + 1);
+    k_scan_tiles<<<unsigned(tiles), SCAN_THREADS, 0, s>>>(in, out, n, n_valid, sums);
+    count_launch();
+    if (tiles > 1)
+      {
+        scan_rec(sums, sums_scanned, tiles, tiles, tmp + 2 * (tiles + 1), s);
+        k_scan_add<<<unsigned(tiles), SCAN_THREADS, 0, s>>>(out, n, sums_scanned);
+        count_launch();
+      }
+  }
+
+  void exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n_plus_1, uint32_t *tmp, cudaStream_t s)
+  {
+    if (n_plus_1 == 0)
+      return;
+    scan_rec(in, out, n_plus_1, n_plus_1 - 1, tmp, s);
+  }
+
+  void launch_bin(const BinParams &p, cudaStream_t s)
+  {
+    if (p.n)
+      k_bin<<<blocks_for(p.n, 256), 256, 0, s>>>(p);
+      count_launch();
+  }
+  void launch_scatter_perm(const uint32_t *key, const uint32_t *slot, const uint32_t *cell_start, uint32_t *perm, uint32_t n,
+                           cudaStream_t s)
+  {
+    if (n)
+      k_scatter_perm<<<blocks_for(n, 256), 256, 0, s>>>(key, slot, cell_start, perm, n);
+      count_launch();
+  }
+  void launch_sort_cells(const uint32_t *cell_start, uint32_t n_buckets, uint32_t *perm, const uint32_t *id, cudaStream_t s)
+  {
+    if (n_buckets)
+      k_sort_cells<<<blocks_for(n_buckets, 256), 256, 0, s>>>(cell_start, n_buckets, perm, id);
+      count_launch();
+  }
+  void launch_gather(const GatherParams &p, cudaStream_t s)
+  {
+    if (p.n_new)
+      k_gather<<<blocks_for(p.n_new, 256), 256, 0, s>>>(p);
+      count_launch();
+  }
+  void launch_count_neighbors(const NeighborParams &p, cudaStream_t s)
+  {
+    if (p.n_rows)
+      k_count_neighbors<<<blocks_for(p.n_rows, 128), 128, 0, s>>>(p);
+      count_launch();
+  }
+  void launch_fill_neighbors(const NeighborParams &p, cudaStream_t s)
+  {
+    if (p.n_rows)
+      k_fill_neighbors<<<blocks_for(p.n_rows, 128), 128, 0, s>>>(p);
+      count_launch();
+  }
+  void launch_count_walls(const WallBuildParams &p, cudaStream_t s)
+  {
+    if (p.n_rows)
+      k_count_walls<<<blocks_for(p.n_rows, 256), 256, 0, s>>>(p);
+      count_launch();
+  }
+  void launch_fill_walls(const WallBuildParams &p, cudaStream_t s)
+  {
+    if (p.n_rows)
+      k_fill_walls<<<blocks_for(p.n_rows, 256), 256, 0, s>>>(p);
+      count_launch();
+  }
+  void launch_stats(StateView st, uint32_t n, double moi_override, StatsPartial *partials, uint32_t n_blocks, cudaStream_t s)
+  {
+    k_stats<<<n_blocks, STATS_BLOCK, 0, s>>>(st, n, moi_override, partials);
+    count_launch();
+  }
+  void launch_unpack_host_rows(const uint32_t *ids, const double *x3, const double *props9, uint32_t n, StateView st,
+                               uint32_t *id_out, int32_t *cell_reg, double *disp, uint32_t base, cudaStream_t s)
+  {
+    if (n)
+      k_unpack_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, x3, props9, n, st, id_out, cell_reg, disp, base);
+      count_launch();
+  }
+  void launch_update_from_host_rows(const uint32_t *ids, const double *x3, const double *props9, uint32_t n,
+                                    const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, cudaStream_t s)
+  {
+    if (n)
+      k_update_from_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, x3, props9, n, slot_of_id, slot_map_size, st);
+      count_launch();
+  }
+  void launch_pack_host_rows(const uint32_t *ids, uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st,
+                             double *x3, double *props9, cudaStream_t s)
+  {
+    if (n)
+      k_pack_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, n, slot_of_id, slot_map_size, st, x3, props9);
+      count_launch();
+  }
+  void launch_pack_all_rows(StateView st, const uint32_t *id, uint32_t n, uint32_t *ids_out, double *x3, double *props9,
+                            cudaStream_t s)
+  {
+    if (n)
+      k_pack_all_rows<<<blocks_for(n, 256), 256, 0, s>>>(st, id, n, ids_out, x3, props9);
+      count_launch();
+  }
+  void launch_fill_u32(uint32_t *p, uint32_t v, size_t n, cudaStream_t s)
+  {
+    if (n)
+      k_fill_u32<<<unsigned(std::min<size_t>((n + 255) / 256, 148 * 16)), 256, 0, s>>>(p, v, n);
+      count_launch();
+  }
+} // namespace dem

@@ -1,0 +1,235 @@
+// dem_kernels.cuh — device data layout and kernel launch interface of the DEM engine.
+//
+// HBM layout (all arrays struct-of-arrays over the particle index p in cell-sorted
+// order; cells are ordered along a Morton curve so that the 27-cell neighbourhood
+// of a particle is a handful of short contiguous runs that stay L2-resident):
+//
+//   pos[p] = (x, y, z, d)         double4, 32 B = one sector per neighbour gather
+//   vel[p] = (vx, vy, vz, mass)   double4
+//   omg[p] = (wx, wy, wz, type)   double4  (type stored as double, like PropertiesIndex::type)
+//   id[p], cell[p]                u32 / i32 (cell = grid cell at the last sort)
+//   disp[p]                       f64, sum of dt*|v| since the last rebuild
+//
+//   row_start[p], col[e]          CSR contact list, FULL (each unordered pair appears in the
+//                                 row of both particles); col bit 31 = "history is non-zero"
+//   hist[e][3], roll[e][3]        tangential displacement / EPSD spring torque of entry e in the
+//                                 orientation row-particle -> col-particle. Both rows keep their own
+//                                 copy; the arithmetic is exactly antisymmetric so the copies stay
+//                                 bit-wise negatives of each other.
+//   img[e]                        periodic image code of the neighbour (0 = none), periodic runs only
+//
+// pos/vel/omg are double-buffered: the fused step kernel reads generation g and writes g^1,
+// so no thread ever sees a half-updated neighbour and one launch does forces + integration.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "dem_physics.cuh"
+
+namespace dem
+{
+  constexpr uint32_t COL_HIST_BIT = 0x80000000u;
+  constexpr uint32_t COL_INDEX_MASK = 0x7fffffffu;
+
+  // wall entry word: bit31 floating wall, bit30 normal flipped (floating), bit29 history non-zero
+  constexpr uint32_t WALL_FLOATING_BIT = 0x80000000u;
+  constexpr uint32_t WALL_FLIPPED_BIT = 0x40000000u;
+  constexpr uint32_t WALL_HIST_BIT = 0x20000000u;
+  constexpr uint32_t WALL_INDEX_MASK = 0x1fffffffu;
+
+  struct GridDesc
+  {
+    double lo[3];
+    double h[3];
+    double L[3]; // (lo + n*h) - lo, the periodic offset of each direction
+    int n[3];
+    int periodic[3];
+    int n_cells;
+    int slab_axis, slab_lo, slab_hi; // owned cell range along slab_axis (-1: everything)
+  };
+
+  struct FaceTable
+  {
+    // sorted by cell; cell_face_start has n_cells+1 entries
+    const uint32_t *cell_face_start;
+    const double *normal; // [n_faces][3]
+    const double *point;  // [n_faces][3]
+    const uint32_t *boundary_id;
+    const int32_t *motion; // index into motions or -1
+    uint32_t n_faces;
+  };
+
+  struct BoundaryMotionDev
+  {
+    double translational_velocity[3];
+    double rotational_speed;
+    double rotational_vector[3];
+    double point_on_axis[3];
+  };
+
+  struct FloatingWallsDev
+  {
+    int n;
+    double point[LETHE_DEM_MAX_FLOATING_WALLS][3];
+    double normal[LETHE_DEM_MAX_FLOATING_WALLS][3];
+    double t0[LETHE_DEM_MAX_FLOATING_WALLS], t1[LETHE_DEM_MAX_FLOATING_WALLS];
+  };
+
+  struct StateView
+  {
+    double4 *pos, *vel, *omg;
+  };
+
+  struct ListView
+  {
+    uint32_t *row_start;
+    uint32_t *col;
+    double *hist; // [E][3]
+    double *roll; // [E][3] (EPSD only, else nullptr)
+    uint8_t *img; // periodic only, else nullptr
+  };
+
+  struct WallListView
+  {
+    uint32_t *row_start;
+    uint32_t *entry;
+    double *hist; // [W][3]
+    double *roll; // [W][3]
+  };
+
+  enum StepPhase
+  {
+    PHASE_START = 0,   // integrate_start: half kick + full drift
+    PHASE_REGULAR = 1, // integrate
+    PHASE_END = 2      // integrate_end: half kick, no drift
+  };
+
+  struct StepParams
+  {
+    StateView in, out;
+    ListView list;
+    WallListView walls;
+    const uint32_t *id;
+    double *disp;
+    int *rebuild_flag;
+    unsigned long long *touching_counter; // debug (store_forces)
+    double *force_out, *torque_out;       // debug taps [N][3] or nullptr
+    FaceTable faces;
+    const BoundaryMotionDev *motions;
+    const FloatingWallsDev *floating;
+    uint32_t n_owned; // particles integrated by this rank
+    int phase;
+    int pw_model;
+    int rolling_model;
+    int periodic_any;
+    double dt;
+    double g[3];
+    double criterion;
+    double moi_override;
+    double L[3];
+  };
+
+  void launch_step(int pp_model, int rolling_model, const StepParams &p, const MaterialTables &mt, cudaStream_t stream);
+
+  // ---- rebuild ----
+  struct BinParams
+  {
+    double4 *pos; // wrapped in place
+    const int32_t *cell_reg;
+    GridDesc grid;
+    const int32_t *cell_rank; // lexicographic -> curve rank
+    uint32_t *cell_count;     // [n_cells + 4], zeroed
+    uint32_t *key, *slot;
+    uint32_t n;
+  };
+  void launch_bin(const BinParams &p, cudaStream_t s);
+  void launch_scatter_perm(const uint32_t *key, const uint32_t *slot, const uint32_t *cell_start, uint32_t *perm, uint32_t n,
+                           cudaStream_t s);
+  void launch_sort_cells(const uint32_t *cell_start, uint32_t n_buckets, uint32_t *perm, const uint32_t *id, cudaStream_t s);
+  struct GatherParams
+  {
+    StateView in, out;
+    const uint32_t *id_in;
+    uint32_t *id_out;
+    const uint32_t *perm;
+    const uint32_t *key; // old index -> bucket (curve rank)
+    const int32_t *cell_of_rank;
+    int32_t *cell_reg_out;
+    uint32_t *old_of_new;
+    double *disp;
+    uint32_t *slot_of_id;
+    uint32_t n_new;
+  };
+  void launch_gather(const GatherParams &p, cudaStream_t s);
+
+  struct NeighborParams
+  {
+    StateView st;
+    const int32_t *cell_reg;
+    const int32_t *cell_rank;
+    const uint32_t *cell_start; // by curve rank, n_cells+1
+    GridDesc grid;
+    double thr2;
+    uint32_t n_rows;  // rows built (owned particles)
+    uint32_t n_total; // owned + ghost particles present in the cell lists
+    // old list (history source)
+    ListView old_list;
+    const uint32_t *old_of_new; // new index -> old index or 0xffffffff
+    uint32_t n_old_rows;
+    int clear_history;
+    // new list
+    ListView new_list;
+    uint32_t *counts; // [n_rows+1]
+    int use_roll, use_img;
+  };
+  void launch_count_neighbors(const NeighborParams &p, cudaStream_t s);
+  void launch_fill_neighbors(const NeighborParams &p, cudaStream_t s);
+
+  struct WallBuildParams
+  {
+    StateView st;
+    const int32_t *cell_reg;
+    GridDesc grid;
+    FaceTable faces;
+    const FloatingWallsDev *floating;
+    const uint32_t *cell_fw_mask; // per cell bit mask of floating walls whose boundary cells include it
+    double time;
+    uint32_t n_rows;
+    WallListView old_list;
+    const uint32_t *old_of_new;
+    uint32_t n_old_rows;
+    int clear_history;
+    WallListView new_list;
+    uint32_t *counts;
+    int use_roll;
+  };
+  void launch_count_walls(const WallBuildParams &p, cudaStream_t s);
+  void launch_fill_walls(const WallBuildParams &p, cudaStream_t s);
+
+  // exclusive scan of n+1 u32 values (in[n] is ignored and treated as 0); out[n] = total.
+  // tmp must hold scan_tmp_elems(n+1) u32.
+  size_t scan_tmp_elems(size_t n);
+  void exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n_plus_1, uint32_t *tmp, cudaStream_t s);
+
+  // ---- misc ----
+  struct StatsPartial
+  {
+    double vmin, vmax, vsum, wmin, wmax, wsum, ktmin, ktmax, ktsum, krmin, krmax, krsum;
+  };
+  void launch_stats(StateView st, uint32_t n, double moi_override, StatsPartial *partials, uint32_t n_blocks, cudaStream_t s);
+  constexpr uint32_t STATS_BLOCK = 256;
+
+  // host-facing AoS <-> device SoA
+  void launch_unpack_host_rows(const uint32_t *ids, const double *x3, const double *props9, uint32_t n, StateView st,
+                               uint32_t *id_out, int32_t *cell_reg, double *disp, uint32_t base, cudaStream_t s);
+  void launch_update_from_host_rows(const uint32_t *ids, const double *x3, const double *props9, uint32_t n,
+                                    const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, cudaStream_t s);
+  void launch_pack_host_rows(const uint32_t *ids, uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st,
+                             double *x3, double *props9, cudaStream_t s);
+  void launch_pack_all_rows(StateView st, const uint32_t *id, uint32_t n, uint32_t *ids_out, double *x3, double *props9,
+                            cudaStream_t s);
+  void launch_fill_u32(uint32_t *p, uint32_t v, size_t n, cudaStream_t s);
+  // process-wide count of kernel launches issued by this library
+  void count_launch(unsigned n = 1);
+  unsigned long long launch_count();
+} // namespace dem

@@ -1,0 +1,380 @@
+// dem_step.cu — the fused DEM step kernel: particle-particle forces over the contact
+// list (with in-place tangential-history update), particle-wall forces, velocity-Verlet
+// integration and the displacement trigger, ONE launch per time step.
+//
+// One thread owns one particle i and walks row i of the FULL contact list, so the force
+// and torque on i are reduced in registers in list order (a per-particle segment
+// reduction: no atomics, deterministic) and the integrator runs in the same thread right
+// after. Neighbours are read from state generation g, results go to g^1.
+//
+// Reference path replaced (one iteration of source/dem/dem.cc:1134-1183):
+//   calculate_particle_particle_contact / execute_contact_calculation
+//     (particle_particle_contact_force.cc:38-100, …force.h:1838-2063)
+//   calculate_particle_wall_contact (particle_wall_contact_force.cc:45-142, .h:166-264)
+//   VelocityVerletIntegrator::integrate{,_start,_end} (velocity_verlet_integrator.cc:14-115,214-290)
+//   displacement accumulation of find_particle_contact_detection_step
+//     (find_contact_detection_step.cc:29-47) for the NEXT step's check.
+#include "dem_kernels.cuh"
+
+namespace dem
+{
+  namespace
+  {
+    __device__ __forceinline__ ParticleView make_view(double4 p, double4 v, double4 w)
+    {
+      ParticleView r;
+      r.x = v3(p.x, p.y, p.z);
+      r.d = p.w;
+      r.v = v3(v.x, v.y, v.z);
+      r.m = v.w;
+      r.w = v3(w.x, w.y, w.z);
+      r.type = static_cast<int>(static_cast<unsigned int>(w.w));
+      return r;
+    }
+
+    // img = 1 + (sx+1) + 3*(sy+1) + 9*(sz+1) for a neighbour seen through the periodic
+    // image shifted by (sx*Lx, sy*Ly, sz*Lz); 0 = no image.
+    __device__ __forceinline__ void decode_image(uint32_t img, const double *L, vec3 &shift, bool &i_am_two)
+    {
+      const int c = int(img) - 1;
+      const int sx = c % 3 - 1, sy = (c / 3) % 3 - 1, sz = c / 9 - 1;
+      shift = v3(sx * L[0], sy * L[1], sz * L[2]);
+      // canonical orientation of a periodic pair = the reference's: particle one sits in the
+      // cell on periodic boundary 0 (low side), particle two is translated by -L
+      // (find_cell_neighbors.cc:147-170, particle_particle_fine_search.cc:193-228).
+      const int first = sx != 0 ? sx : (sy != 0 ? sy : sz);
+      i_am_two = first > 0;
+    }
+
+    template <int MODEL, int ROLLING, bool PERIODIC>
+    __global__ void __launch_bounds__(128) k_step(const __grid_constant__ StepParams P, const __grid_constant__ MaterialTables mt)
+    {
+      const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= P.n_owned)
+        return;
+      const double4 pi = P.in.pos[i], vi = P.in.vel[i], wi = P.in.omg[i];
+      const ParticleView me = make_view(pi, vi, wi);
+      vec3 F = v3(0, 0, 0), T = v3(0, 0, 0);
+      const double dt = P.dt;
+      unsigned int touching = 0;
+
+      // ---------------- particle-particle contacts ----------------
+      const uint32_t e0 = P.list.row_start[i], e1 = P.list.row_start[i + 1];
+      for (uint32_t e = e0; e < e1; ++e)
+        {
+          const uint32_t c = P.list.col[e];
+          const uint32_t j = c & COL_INDEX_MASK;
+          const double4 pj = P.in.pos[j];
+          bool i_am_two = false;
+          vec3 shift = v3(0, 0, 0);
+          uint32_t img = 0;
+          if constexpr (PERIODIC)
+            {
+              img = P.list.img[e];
+              if (img)
+                decode_image(img, P.L, shift, i_am_two);
+            }
+          // positions of canonical particle one / two
+          vec3 x1, x2;
+          double dsum;
+          if (PERIODIC && img)
+            {
+              if (!i_am_two)
+                {
+                  x1 = me.x;
+                  x2 = v3(pj.x, pj.y, pj.z) + shift;
+                  dsum = me.d + pj.w;
+                }
+              else
+                {
+                  x1 = v3(pj.x, pj.y, pj.z);
+                  x2 = me.x + (-shift);
+                  dsum = pj.w + me.d;
+                }
+            }
+          else
+            {
+              x1 = me.x;
+              x2 = v3(pj.x, pj.y, pj.z);
+              dsum = me.d + pj.w;
+            }
+          const double distance = sqrt(dist2(x1, x2));
+          const double normal_overlap = 0.5 * dsum - distance;
+          if (normal_overlap > mt.pp_force_threshold)
+            {
+              const ParticleView other = make_view(pj, P.in.vel[j], P.in.omg[j]);
+              vec3 h = v3(0, 0, 0), rs = v3(0, 0, 0);
+              if (c & COL_HIST_BIT)
+                {
+                  const double *hp = P.list.hist + 3 * size_t(e);
+                  h = v3(hp[0], hp[1], hp[2]);
+                  if constexpr (ROLLING == LETHE_ROLLING_EPSD)
+                    {
+                      const double *rp = P.list.roll + 3 * size_t(e);
+                      rs = v3(rp[0], rp[1], rp[2]);
+                    }
+                }
+              PairResult r;
+              r.normal_force = r.tangential_force = r.torque_one = r.torque_two = r.rolling = v3(0, 0, 0);
+              vec3 n, vt;
+              double vn;
+              if (PERIODIC && i_am_two)
+                {
+                  // evaluate the pair in its canonical orientation (one = neighbour) so that both
+                  // owners of the pair run bit-identical arithmetic; my copy of the history is the
+                  // negative of the canonical one.
+                  ParticleView one = other, two = me;
+                  one.x = x1;
+                  h = -h;
+                  rs = -rs;
+                  pp_update_contact_information(h, vt, vn, n, one, two, x2, dt);
+                  pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, two, r);
+                  // apply_force_and_torque_on_local_particles, particle two (…force.h:565-569)
+                  const vec3 total_force = r.normal_force + r.tangential_force;
+                  F = F + total_force;
+                  T = T + (-r.torque_two - r.rolling);
+                  h = -h;
+                  rs = -rs;
+                }
+              else
+                {
+                  ParticleView one = me;
+                  one.x = x1;
+                  pp_update_contact_information(h, vt, vn, n, one, other, x2, dt);
+                  pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, other, r);
+                  // particle one (…force.h:561-567)
+                  const vec3 total_force = r.normal_force + r.tangential_force;
+                  F = F - total_force;
+                  T = T + (-r.torque_one + r.rolling);
+                }
+              double *hp = P.list.hist + 3 * size_t(e);
+              hp[0] = h.x;
+              hp[1] = h.y;
+              hp[2] = h.z;
+              if constexpr (ROLLING == LETHE_ROLLING_EPSD)
+                {
+                  double *rp = P.list.roll + 3 * size_t(e);
+                  rp[0] = rs.x;
+                  rp[1] = rs.y;
+                  rp[2] = rs.z;
+                }
+              if (!(c & COL_HIST_BIT))
+                P.list.col[e] = c | COL_HIST_BIT;
+              ++touching;
+            }
+          else if (c & COL_HIST_BIT)
+            {
+              // contact_info.tangential_displacement.clear() (…force.h:2057-2063): dropping the
+              // flag is the clear; the 24 B are not touched.
+              P.list.col[e] = j;
+            }
+        }
+
+      // ---------------- particle-wall contacts ----------------
+      const uint32_t w0 = P.walls.row_start[i], w1 = P.walls.row_start[i + 1];
+      for (uint32_t w = w0; w < w1; ++w)
+        {
+          const uint32_t we = P.walls.entry[w];
+          const uint32_t idx = we & WALL_INDEX_MASK;
+          vec3 wall_normal, point;
+          int motion = -1;
+          if (we & WALL_FLOATING_BIT)
+            {
+              wall_normal = v3(P.floating->normal[idx][0], P.floating->normal[idx][1], P.floating->normal[idx][2]);
+              if (we & WALL_FLIPPED_BIT)
+                wall_normal = -1 * wall_normal;
+              point = v3(P.floating->point[idx][0], P.floating->point[idx][1], P.floating->point[idx][2]);
+            }
+          else
+            {
+              const double *np = P.faces.normal + 3 * size_t(idx), *pp = P.faces.point + 3 * size_t(idx);
+              wall_normal = v3(np[0], np[1], np[2]);
+              point = v3(pp[0], pp[1], pp[2]);
+              motion = P.faces.motion[idx];
+            }
+          // particle_wall_contact_force.cc:72-88
+          const vec3 point_to_particle_vector = me.x - point;
+          const vec3 projected_vector = ((dot(point_to_particle_vector, wall_normal)) / (norm2(wall_normal))) * wall_normal;
+          const double normal_overlap = ((me.d) * 0.5) - (norm(projected_vector));
+          if (normal_overlap > mt.pw_force_threshold)
+            {
+              vec3 h = v3(0, 0, 0), rs = v3(0, 0, 0);
+              if (we & WALL_HIST_BIT)
+                {
+                  const double *hp = P.walls.hist + 3 * size_t(w);
+                  h = v3(hp[0], hp[1], hp[2]);
+                  if (P.rolling_model == LETHE_ROLLING_EPSD)
+                    {
+                      const double *rp = P.walls.roll + 3 * size_t(w);
+                      rs = v3(rp[0], rp[1], rp[2]);
+                    }
+                }
+              // update_contact_information (particle_wall_contact_force.h:166-264)
+              const vec3 normal_vector = -wall_normal;
+              const vec3 contact_point = me.x + (0.5 * me.d) * normal_vector;
+              vec3 bt = v3(0, 0, 0), br = v3(0, 0, 0), bp = v3(0, 0, 0);
+              double bs = 0.;
+              if (motion >= 0)
+                {
+                  const BoundaryMotionDev &m = P.motions[motion];
+                  bt = v3(m.translational_velocity[0], m.translational_velocity[1], m.translational_velocity[2]);
+                  bs = m.rotational_speed;
+                  br = v3(m.rotational_vector[0], m.rotational_vector[1], m.rotational_vector[2]);
+                  bp = v3(m.point_on_axis[0], m.point_on_axis[1], m.point_on_axis[2]);
+                }
+              vec3 vector_to_rotating_axis = contact_point - bp;
+              vector_to_rotating_axis = vector_to_rotating_axis - (dot(vector_to_rotating_axis, br)) * br;
+              const vec3 vrel =
+                bt - me.v + cross(((-0.5 * me.d) * me.w), normal_vector) + cross(bs * br, vector_to_rotating_axis);
+              const double vn = dot(vrel, normal_vector);
+              const vec3 vt = vrel - (vn * normal_vector);
+              h = h + vt * dt;
+              WallResult r;
+              r.normal_force = r.tangential_force = r.tangential_torque = r.rolling = v3(0, 0, 0);
+              pw_calculate_contact(P.pw_model, P.rolling_model, mt, wall_normal, h, rs, vt, vn, normal_overlap, dt, me, r);
+              // apply_force_and_torque (particle_wall_contact_force.h:506-522)
+              const vec3 total_force = r.normal_force + r.tangential_force;
+              F = F - total_force;
+              T = T + (r.tangential_torque + r.rolling);
+              double *hp = P.walls.hist + 3 * size_t(w);
+              hp[0] = h.x;
+              hp[1] = h.y;
+              hp[2] = h.z;
+              if (P.rolling_model == LETHE_ROLLING_EPSD)
+                {
+                  double *rp = P.walls.roll + 3 * size_t(w);
+                  rp[0] = rs.x;
+                  rp[1] = rs.y;
+                  rp[2] = rs.z;
+                }
+              if (!(we & WALL_HIST_BIT))
+                P.walls.entry[w] = we | WALL_HIST_BIT;
+            }
+          else if (we & WALL_HIST_BIT)
+            P.walls.entry[w] = we & ~WALL_HIST_BIT;
+        }
+
+      if (P.touching_counter && touching)
+        atomicAdd(P.touching_counter, (unsigned long long)touching);
+      if (P.force_out)
+        {
+          P.force_out[3 * size_t(i) + 0] = F.x;
+          P.force_out[3 * size_t(i) + 1] = F.y;
+          P.force_out[3 * size_t(i) + 2] = F.z;
+          P.torque_out[3 * size_t(i) + 0] = T.x;
+          P.torque_out[3 * size_t(i) + 1] = T.y;
+          P.torque_out[3 * size_t(i) + 2] = T.z;
+        }
+
+      // ---------------- velocity-Verlet ----------------
+      const double MOI = P.moi_override > 0 ? P.moi_override : 0.1 * me.m * me.d * me.d; // dem.cc:1004-1011
+      vec3 v = me.v, x = me.x, om = me.w;
+      const vec3 g = v3(P.g[0], P.g[1], P.g[2]);
+      if (P.phase == PHASE_REGULAR)
+        {
+          const vec3 dt_g = g * dt;
+          const double dt_mass_inverse = dt / me.m;
+          const double dt_MOI_inverse = dt / MOI;
+          v.x = v.x + (dt_g.x + F.x * dt_mass_inverse);
+          v.y = v.y + (dt_g.y + F.y * dt_mass_inverse);
+          v.z = v.z + (dt_g.z + F.z * dt_mass_inverse);
+          x.x = x.x + v.x * dt;
+          x.y = x.y + v.y * dt;
+          x.z = x.z + v.z * dt;
+          om.x = om.x + T.x * dt_MOI_inverse;
+          om.y = om.y + T.y * dt_MOI_inverse;
+          om.z = om.z + T.z * dt_MOI_inverse;
+        }
+      else
+        {
+          const vec3 half_dt_g = 0.5 * g * dt;
+          const double half_dt_mass_inverse = 0.5 * dt / me.m;
+          const double half_dt_MOI_inverse = 0.5 * dt / MOI;
+          v.x = v.x + (half_dt_g.x + F.x * half_dt_mass_inverse);
+          v.y = v.y + (half_dt_g.y + F.y * half_dt_mass_inverse);
+          v.z = v.z + (half_dt_g.z + F.z * half_dt_mass_inverse);
+          om.x = om.x + T.x * half_dt_MOI_inverse;
+          om.y = om.y + T.y * half_dt_MOI_inverse;
+          om.z = om.z + T.z * half_dt_MOI_inverse;
+          if (P.phase == PHASE_START)
+            {
+              x.x = x.x + v.x * dt;
+              x.y = x.y + v.y * dt;
+              x.z = x.z + v.z * dt;
+            }
+        }
+      P.out.pos[i] = make_double4(x.x, x.y, x.z, pi.w);
+      P.out.vel[i] = make_double4(v.x, v.y, v.z, vi.w);
+      P.out.omg[i] = make_double4(om.x, om.y, om.z, wi.w);
+
+      // displacement for the next step's contact-detection check
+      if (P.phase != PHASE_END)
+        {
+          const double dsp = P.disp[i] + dt * sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+          P.disp[i] = dsp;
+          if (dsp > P.criterion)
+            *P.rebuild_flag = 1;
+        }
+    }
+
+    template <int MODEL, int ROLLING>
+    void launch_mr(const StepParams &p, const MaterialTables &mt, cudaStream_t stream)
+    {
+      if (p.n_owned == 0)
+        return;
+      const dim3 block(128), grid((p.n_owned + 127) / 128);
+      if (p.periodic_any)
+        k_step<MODEL, ROLLING, true><<<grid, block, 0, stream>>>(p, mt);
+      else
+        k_step<MODEL, ROLLING, false><<<grid, block, 0, stream>>>(p, mt);
+      count_launch();
+    }
+
+    template <int MODEL>
+    void launch_m(int rolling, const StepParams &p, const MaterialTables &mt, cudaStream_t stream)
+    {
+      switch (rolling)
+        {
+          case LETHE_ROLLING_NONE:
+            launch_mr<MODEL, LETHE_ROLLING_NONE>(p, mt, stream);
+            break;
+          case LETHE_ROLLING_CONSTANT:
+            launch_mr<MODEL, LETHE_ROLLING_CONSTANT>(p, mt, stream);
+            break;
+          case LETHE_ROLLING_VISCOUS:
+            launch_mr<MODEL, LETHE_ROLLING_VISCOUS>(p, mt, stream);
+            break;
+          default:
+            launch_mr<MODEL, LETHE_ROLLING_EPSD>(p, mt, stream);
+            break;
+        }
+    }
+  } // namespace
+
+  // Runtime -> template dispatch, the same pattern as set_particle_particle_contact_force_model
+  // / set_rolling_resistance_model (set_particle_particle_contact_force_model.cc:12-103).
+  void launch_step(int pp_model, int rolling_model, const StepParams &p, const MaterialTables &mt, cudaStream_t stream)
+  {
+    switch (pp_model)
+      {
+        case LETHE_PP_LINEAR:
+          launch_m<LETHE_PP_LINEAR>(rolling_model, p, mt, stream);
+          break;
+        case LETHE_PP_HERTZ_MINDLIN_LIMIT_FORCE:
+          launch_m<LETHE_PP_HERTZ_MINDLIN_LIMIT_FORCE>(rolling_model, p, mt, stream);
+          break;
+        case LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP:
+          launch_m<LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP>(rolling_model, p, mt, stream);
+          break;
+        case LETHE_PP_HERTZ:
+          launch_m<LETHE_PP_HERTZ>(rolling_model, p, mt, stream);
+          break;
+        case LETHE_PP_HERTZ_JKR:
+          launch_m<LETHE_PP_HERTZ_JKR>(rolling_model, p, mt, stream);
+          break;
+        default:
+          launch_m<LETHE_PP_DMT>(rolling_model, p, mt, stream);
+          break;
+      }
+  }
+} // namespace dem

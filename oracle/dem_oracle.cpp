@@ -242,6 +242,8 @@ namespace
     bool clear_tangential_displacement_trigger;
     uint64_t contact_build_number;
     uint64_t n_touching_last;
+    // reference defect switch, see pp_execute_contact_calculation
+    bool dmt_stale_scratch = true;
   };
 
   // ---------------------------------------------------------------- grid ----
@@ -1208,6 +1210,14 @@ namespace
         const double normal_overlap = 0.5 * (p1[P_DP] + p2[P_DP]) - std::sqrt(distance_square(x1, x2));
         if (normal_overlap > o.pp_force_threshold)
           {
+            // The reference declares the scratch tensors once per row (…force.h:1847-1853). Every
+            // model overwrites them except the DMT non-contact branches (:1514-1532), which ADD the
+            // cohesive term to whatever the previous pair of the row left behind and then apply the
+            // stale tangential force / torques too. dmt_stale_scratch = true reproduces that;
+            // false gives the evident intent (zero scratch per pair), which is what the CUDA
+            // engine implements because the artefact depends on hash-map iteration order.
+            if (!o.dmt_stale_scratch)
+              out.normal_force = out.tangential_force = out.t1 = out.t2 = out.rolling = mk(0, 0, 0);
             pp_update_contact_information(info, vt, vn, n, p1, p2, x1, x2, dt);
             pp_calculate_contact(o, o.cfg.pp_model, info, vt, vn, n, normal_overlap, dt, p1, p2, out);
             // apply_force_and_torque_on_local_particles (:548-570)
@@ -1987,6 +1997,30 @@ int oracle_dem_get_stats(lethe_dem_ctx *ctx, lethe_dem_stats *st)
   if (o->parts.empty())
     st->v_min = st->omega_min = st->ke_trans_min = st->ke_rot_min = 0;
   return 0;
+}
+
+int oracle_dem_enable_timers(lethe_dem_ctx *, int) { return 0; }
+int oracle_dem_event_record(lethe_dem_ctx *, int) { return 0; }
+int oracle_dem_event_elapsed(lethe_dem_ctx *, double *ms) { *ms = 0; return 0; }
+int oracle_dem_nccl_unique_id(uint8_t *) { return -1; }
+int oracle_dem_comm_init(lethe_dem_ctx *, int, int, const uint8_t *) { return -1; }
+int oracle_dem_kernel_launches(lethe_dem_ctx *, uint64_t *n) { *n = 0; return 0; }
+int oracle_dem_get_timers(lethe_dem_ctx *, int, double *a, uint64_t *na, double *b, uint64_t *nb)
+{
+  *a = *b = 0;
+  *na = *nb = 0;
+  return 0;
+}
+
+int oracle_dem_set_option(lethe_dem_ctx *ctx, const char *name, int value)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  if (std::string(name) == "dmt_stale_scratch")
+    {
+      o->dmt_stale_scratch = value != 0;
+      return 0;
+    }
+  return fail(o, "unknown option");
 }
 
 // ---- single-contact taps used by the golden-vector tests (no grid needed) ----

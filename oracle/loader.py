@@ -62,3 +62,11 @@ def integrate_external(engine, phase, force, torque, moi):
     fn.restype = ctypes.c_int
     rc = fn(engine._ctx, ctypes.c_int(phase), f.ctypes.data_as(P), t.ctypes.data_as(P), ctypes.c_double(moi))
     assert rc == 0
+
+
+def set_option(engine, name, value):
+    """oracle_dem_set_option: test-only switches of the oracle (e.g. dmt_stale_scratch)."""
+    fn = library().oracle_dem_set_option
+    fn.restype = ctypes.c_int
+    rc = fn(engine._ctx, name.encode(), ctypes.c_int(int(value)))
+    assert rc == 0, name

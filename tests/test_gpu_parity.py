@@ -1,0 +1,338 @@
+"""Parity of the CUDA engine (through the C ABI) against the CPU oracle and the
+reference's golden vectors.  All tests here need a B200 (`-m gpu`).
+
+Bars (BASELINE.json north_star): contact pair sets bit-exact; per-step forces,
+torques and positions within 1e-12 relative in FP64 over short horizons."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from lethe_b200 import abi
+from lethe_b200.prm import load_prm
+from lethe_b200.solver import DEMSolver, box_wall_faces
+from oracle import loader
+from tests.util import GOLDEN, assert_sig6, golden, packing_parameters, props_row, random_packing, unit_test_parameters
+
+pytestmark = pytest.mark.gpu
+
+FORCE_RTOL = 1e-12  # relative to the largest force magnitude acting in the system at that step
+
+
+def both(params, store_forces=True, moi_override=0.0):
+    cfg = params.to_config(store_forces=store_forces, moi_override=moi_override)
+    return abi.load_engine(cfg), loader.oracle_engine(cfg)
+
+
+def setup_pair(params, ids, x, props, walls=True, **kw):
+    g, o = both(params, **kw)
+    for e in (g, o):
+        if walls:
+            e.set_walls(box_wall_faces(params.mesh, params.outlet_boundaries, params.periodic))
+        e.set_particles(ids, x, props)
+    return g, o
+
+
+def compare_step(g, o, step, check_pairs=True, pos_rtol=1e-12, force_rtol=None):
+    force_rtol = FORCE_RTOL if force_rtol is None else force_rtol
+    ig, fg, tg = g.get_forces()
+    io, fo, to = o.get_forces()
+    assert np.array_equal(ig, io)
+    fscale = max(np.abs(fo).max(), 1e-300)
+    tscale = max(np.abs(to).max(), 1e-300)
+    assert np.abs(fg - fo).max() <= force_rtol * fscale, (step, np.abs(fg - fo).max() / fscale)
+    assert np.abs(tg - to).max() <= force_rtol * tscale, (step, np.abs(tg - to).max() / tscale)
+    idg, xg, pg = g.get_particles()
+    ido, xo, po = o.get_particles()
+    assert np.array_equal(idg, ido)
+    assert np.abs(xg - xo).max() <= pos_rtol * max(np.abs(xo).max(), 1e-300), (step, np.abs(xg - xo).max())
+    vscale = max(np.abs(po[:, 3:6]).max(), 1e-300)
+    assert np.abs(pg[:, 3:6] - po[:, 3:6]).max() <= 10 * pos_rtol * vscale, step
+    if check_pairs:
+        pi, pj, pt = g.get_pairs()
+        qi, qj, qt = o.get_pairs()
+        assert np.array_equal(pi, qi) and np.array_equal(pj, qj), (step, len(pi), len(qi))
+        hscale = max(np.abs(qt).max(), 1e-300)
+        assert np.abs(pt - qt).max() <= 100 * force_rtol * hscale, (step, np.abs(pt - qt).max() / hscale)
+
+
+def lockstep(g, o, n_resync, n_free, force_rtol=FORCE_RTOL, free_rtol=1e-8, extra=None):
+    """Phase 1 (n_resync steps): before every step the GPU is given the oracle's exact
+    particle state (contact history stays the GPU's own), so each step is a single-step
+    parity check at the north-star tolerance. The overlap r1+r2-|dx| is ~1e-3 d, i.e. one
+    ulp of a position is already ~1e-12 of a force, so free-running trajectories cannot
+    hold 1e-12 beyond a few steps.
+    Phase 2 (n_free steps): both run freely; documented looser bound."""
+    for step in range(n_resync):
+        ids, x, props = o.get_particles()
+        x, props = np.ascontiguousarray(x), np.ascontiguousarray(props)
+        g.step_host(0, ids, x, props)
+        g.step(1)
+        o.step(1)
+        compare_step(g, o, step, force_rtol=force_rtol)
+        if extra:
+            extra(step)
+    for step in range(n_free):
+        g.step(1)
+        o.step(1)
+        compare_step(g, o, n_resync + step, force_rtol=free_rtol, pos_rtol=free_rtol)
+        if extra:
+            extra(n_resync + step)
+
+
+def test_library_loads_and_rejects_bad_config():
+    lib = abi.load_library()
+    for sym in abi.ABI_SYMBOLS:
+        assert hasattr(lib, "lethe_dem_" + sym)
+    p = unit_test_parameters()
+    cfg = p.to_config()
+    cfg.n_types = 9
+    with pytest.raises(abi.DEMError):
+        abi.load_engine(cfg)
+
+
+def test_pp_force_kat_on_gpu():
+    # tests/dem/particle_particle_contact_force_nonlinear.cc -> -0.258955 N on particle 0
+    p = unit_test_parameters()
+    cfg = p.to_config(store_forces=True, moi_override=1.0)
+    e = abi.load_engine(cfg)
+    e.set_particles([0, 1], [[0.4, 0, 0], [0.40499, 0, 0]], [props_row(0, 0.005, 1, (0.01, 0, 0)), props_row(0, 0.005, 1)])
+    e.step(1)
+    _, f, _ = e.get_forces()
+    g = golden()["pp_force_nonlinear"]
+    for d in range(3):
+        assert_sig6(f[0, d], g[d])
+        assert f[1, d] == -f[0, d]  # the two owners of a pair compute exactly opposite forces
+    assert abs(f[0, 0] - (-0.2589545634)) < 1e-9
+
+
+@pytest.mark.parametrize("model,key", [("nonlinear", "pw_force_nonlinear"), ("linear", "pw_force_linear")])
+def test_pw_force_kat_on_gpu(model, key):
+    p = unit_test_parameters(pw_model=model, g=(0, 0, -9.81))
+    e = abi.load_engine(p.to_config(store_forces=True, moi_override=1.0))
+    e.set_walls(box_wall_faces(p.mesh))
+    e.set_particles([0], [[-0.998, 0, 0]], [props_row(0, 0.005, 1, (0.01, 0, 0))])
+    e.step(1)
+    _, f, _ = e.get_forces()
+    assert_sig6(f[0, 0], golden()[key])
+
+
+@pytest.mark.parametrize("model", ["linear", "hertz_mindlin_limit_overlap"])
+def test_full_contact_series_on_gpu(model):
+    # the 242-sample collision golden, including the tensile tail where the reference
+    # turns rounding residue into mu*|Fn|: requires bit-faithful arithmetic
+    p = unit_test_parameters(pp_model=model)
+    p.restart = True
+    p.contact_detection_method, p.contact_detection_frequency = "constant", 1
+    g, o = both(p, moi_override=1.0)
+    for e in (g, o):
+        e.set_particles([0, 1], [[0.4, 0, 0], [0.405, 0, 0]], [props_row(0, 0.005, 1, (0.01, 0, 0)), props_row(0, 0.005, 1)])
+    series = golden()["full_contact"][model]
+    by_iter = {int(round(s["time"] / 1e-5)): s for s in series}
+    n_bitexact = 0
+    for it in range(max(by_iter) + 1):
+        g.step(1)
+        o.step(1)
+        _, fg, tg = g.get_forces()
+        _, fo, to = o.get_forces()
+        if model != "linear":  # linear uses pow(): CUDA and glibc may differ in the last ulp
+            assert np.array_equal(fg, fo), (it, fg, fo)
+            n_bitexact += 1
+        if it in by_iter:
+            for d in range(3):
+                assert_sig6(fg[0, d], by_iter[it]["force"][d], f"{model} it={it}")
+                assert_sig6(tg[0, d], by_iter[it]["torque"][d], f"{model} it={it}")
+    _, xg, pg = g.get_particles()
+    _, xo, po = o.get_particles()
+    if model != "linear":
+        assert np.array_equal(xg, xo) and np.array_equal(pg, po)
+
+
+def test_normal_force_series_on_gpu():
+    p = unit_test_parameters(pw_model="nonlinear", dt=1e-6, d=0.001, young=2e11, restitution=0.5, friction=0.3, rolling_viscous=0.1)
+    p.restart = True
+    e = abi.load_engine(p.to_config(store_forces=True, moi_override=1.0))
+    e.set_walls(box_wall_faces(p.mesh))
+    e.set_particles([0], [[-0.999, 0, 0]], [props_row(0, 0.001, 1, (-1.0, 0, 0))])
+    gold = golden()["normal_force"]
+    out = []
+    time = 0.0
+    while time < 0.00115:
+        _, x, _ = e.get_particles()
+        distance = 1 + x[0, 0] - 0.001 / 2.0
+        e.step(1)
+        if not distance > 0.0:
+            _, f, _ = e.get_forces()
+            out.append(f[0, 0])
+        time += 1e-6
+    assert len(out) == len(gold)
+    for a, b in zip(out, gold):
+        assert_sig6(a, b)
+
+
+def test_velocity_verlet_free_fall_on_gpu():
+    # integrate_start + n x integrate + integrate_end against the analytic solution
+    # (tests/dem/integration_velocity_verlet.cc pattern, gravity only)
+    p = unit_test_parameters(dt=1e-3, g=(0, 0, -9.81))
+    g, o = both(p)
+    for e in (g, o):
+        e.set_particles([0], [[0, 0, 0.5]], [props_row(0, 0.005, 1.0, (0.3, 0, 0))])
+        e.step(5)
+        e.synchronize_velocities()
+    _, xg, pg = g.get_particles()
+    _, xo, po = o.get_particles()
+    assert np.array_equal(xg, xo) and np.array_equal(pg, po)
+    t = 5e-3
+    assert abs(xg[0, 2] - (0.5 - 0.5 * 9.81 * t * t)) < 1e-15
+    assert abs(pg[0, 5] - (-9.81 * t)) < 1e-15
+    assert abs(xg[0, 0] - 0.3 * t) < 1e-15
+
+
+CASES = [
+    # pp model, pw model, rolling, polydispersity, n_types
+    ("hertz_mindlin_limit_overlap", "nonlinear", "none", 0.0, 1),
+    ("hertz_mindlin_limit_overlap", "nonlinear", "constant", 0.3, 2),
+    ("hertz_mindlin_limit_overlap", "nonlinear", "viscous", 0.2, 1),
+    ("hertz_mindlin_limit_overlap", "nonlinear", "epsd", 0.2, 2),
+    ("hertz_mindlin_limit_force", "nonlinear", "constant", 0.2, 1),
+    ("hertz", "nonlinear", "constant", 0.2, 1),
+    ("linear", "linear", "constant", 0.2, 2),
+    ("hertz_JKR", "JKR", "constant", 0.2, 1),
+    ("DMT", "DMT", "constant", 0.2, 1),
+]
+
+
+@pytest.mark.parametrize("pp,pw,rolling,poly,n_types", CASES)
+def test_packing_parity_stepwise(pp, pw, rolling, poly, n_types):
+    """~1700 overlapping spheres in a box with walls, gravity, random velocities: every step
+    the pair set must be identical and forces/torques/positions within 1e-12 relative."""
+    d = 0.005
+    ids, x, props, extent = random_packing(12, d=d, spacing=0.98, jitter=0.08, poly=poly, n_types=n_types, seed=7)
+    cohesive = pp in ("hertz_JKR", "DMT")
+    params = packing_parameters(extent, d=d, pp_model=pp, pw_model=pw, rolling=rolling, n_types=n_types,
+                                surface_energy=0.05 if cohesive else 0.0, hamaker=1e-19 if cohesive else 4e-19,
+                                young=1e6)
+    g, o = setup_pair(params, ids, x, props)
+    if pp == "DMT":
+        loader.set_option(o, "dmt_stale_scratch", 0)  # see DESIGN.md "known reference defect"
+    # cbrt / pow differ by an ulp between CUDA and glibc for the JKR and linear models
+    loose = pp in ("hertz_JKR", "linear") or pw in ("JKR", "linear")
+    lockstep(g, o, 30, 20, force_rtol=1e-10 if loose else FORCE_RTOL)
+    sg, so = g.get_stats(), o.get_stats()
+    assert sg.n_rebuilds == so.n_rebuilds and sg.n_rebuilds >= 2
+    assert sg.n_pair_entries == so.n_pair_entries
+    assert sg.n_wall_entries == so.n_wall_entries
+    assert sg.n_pairs_touching == so.n_pairs_touching
+
+
+def test_periodic_parity_stepwise():
+    d = 0.005
+    ids, x, props, extent = random_packing(10, d=d, spacing=1.0, jitter=0.08, poly=0.1, seed=3, vel=0.3)
+    params = packing_parameters(extent, d=d, cell=0.01, rolling="constant", periodic=(1, 1, 1), g=(0, 0, 0))
+    # fill the periodic box exactly: the lattice pitch equals the box so images touch
+    g, o = setup_pair(params, ids, x, props)
+    lockstep(g, o, 40, 20)
+    assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 2
+    # particles crossed periodic faces and were wrapped identically
+    _, xg, _ = g.get_particles()
+    assert xg.min() >= 0.0 - 0.01 and xg.max() <= params.mesh.hi[0] + 0.01
+
+
+def test_floating_wall_and_moving_boundary_parity():
+    d = 0.005
+    ids, x, props, extent = random_packing(8, d=d, spacing=1.05, jitter=0.05, seed=11)
+    params = packing_parameters(extent, d=d, rolling="constant")
+    params.floating_walls = [((0, 0, 0.4 * extent[2]), (0, 0, 1), 0.0, 2e-4)]
+    from lethe_b200.prm import BoundaryCondition
+
+    params.boundary_conditions.append(BoundaryCondition(type="translational", boundary_id=4, translational_velocity=(0.05, 0.0, 0.0)))
+    params.boundary_conditions.append(BoundaryCondition(type="rotational", boundary_id=0, rotational_speed=2.0, rotational_vector=(1.0, 0, 0), point_on_rotational_vector=(0, 0.02, 0.02)))
+    cfg = params.to_config(store_forces=True)
+    g, o = abi.load_engine(cfg), loader.oracle_engine(cfg)
+    for e in (g, o):
+        e.set_walls(box_wall_faces(params.mesh))
+        pts, nrm, t0, t1 = zip(*params.floating_walls)
+        e.set_floating_walls(pts, nrm, t0, t1)
+        e.set_boundary_motion(4, (0.05, 0, 0), 0.0, (0, 0, 0), (0, 0, 0))
+        e.set_boundary_motion(0, (0, 0, 0), 2.0, (1.0, 0, 0), (0, 0.02, 0.02))
+        e.set_particles(ids, x, props)
+    def walls_equal(step):
+        wg, wo = g.get_wall_contacts(), o.get_wall_contacts()
+        assert np.array_equal(wg[0], wo[0]) and np.array_equal(wg[1], wo[1]), step
+
+    lockstep(g, o, 30, 10, extra=walls_equal)
+
+
+def test_insertion_outlet_and_lost_particles():
+    # particles added mid-run trigger a search; particles leaving through an open (outlet)
+    # boundary are dropped at the next rebuild, like sort_particles_into_subdomains_and_cells
+    d = 0.005
+    ids, x, props, extent = random_packing(6, d=d, spacing=1.2, jitter=0.05, seed=5)
+    params = packing_parameters(extent, d=d)
+    from lethe_b200.prm import BoundaryCondition
+
+    params.boundary_conditions.append(BoundaryCondition(type="outlet", boundary_id=4))
+    g, o = setup_pair(params, ids, x, props)
+    for e in (g, o):
+        e.step(30)
+    ids2 = np.arange(1000, 1040, dtype=np.uint32)
+    x2 = x[:40] + np.array([0, 0, extent[2] * 0.4])
+    for e in (g, o):
+        e.add_particles(ids2, x2, props[:40])
+        e.step(1500)
+    ig, xg, pg = g.get_particles()
+    io, xo, po = o.get_particles()
+    assert np.array_equal(ig, io)
+    assert len(ig) < len(ids) + 40  # some fell out through the outlet
+    assert np.abs(xg - xo).max() < 1e-7  # 1.5k chaotic steps: loose
+
+
+def test_packing_in_box_application_on_gpu():
+    p = load_prm(os.path.join(GOLDEN, "packing_in_box.prm"))
+    s = DEMSolver(p)
+    ids, x, props = s.solve()
+    rows = golden("packing_in_box.mpirun1.json")["rows"]
+    gold = np.array([r[3:6] for r in rows])
+    assert [r[0] for r in rows] == list(ids)
+    err = np.abs(x - gold).max(axis=1)
+    assert np.mean(err <= 1.01e-4) > 0.9 and err.max() < 0.2 * 0.005, (np.mean(err <= 1.01e-4), err.max())
+
+
+def test_step_host_roundtrip_matches_resident():
+    d = 0.005
+    ids, x, props, extent = random_packing(8, d=d, spacing=0.99, seed=2)
+    params = packing_parameters(extent, d=d)
+    a, _ = setup_pair(params, ids, x, props)
+    b, _ = setup_pair(params, ids, x, props)
+    a.step(20)
+    hx, hp = x.copy(), props.copy()
+    for _ in range(20):
+        b.step_host(1, ids, hx, hp)
+    ia, xa, pa = a.get_particles()
+    order = np.argsort(ids)
+    assert np.array_equal(xa, hx[order]) and np.array_equal(pa, hp[order])
+
+
+def test_properties_at_scale():
+    """Size-independent properties on a 64^3 packing (262k spheres): run-to-run bitwise
+    determinism, exact action-reaction (sum of pair forces == 0 up to summation rounding)
+    and the stats reductions."""
+    d = 0.005
+    ids, x, props, extent = random_packing(64, d=d, spacing=0.99, jitter=0.06, seed=1)
+    params = packing_parameters(extent, d=d, g=(0, 0, 0), periodic=(1, 1, 1), cell=extent[0] / 32)
+    out = []
+    for _ in range(2):
+        cfg = params.to_config(store_forces=True)
+        e = abi.load_engine(cfg)
+        e.set_particles(ids, x, props)
+        e.step(25)
+        out.append((e.get_particles(), e.get_forces(), e.get_stats()))
+    (p0, f0, s0), (p1, f1, s1) = out
+    assert np.array_equal(p0[1], p1[1]) and np.array_equal(p0[2], p1[2])
+    assert np.array_equal(f0[1], f1[1])
+    f = f0[1]
+    assert np.abs(f.sum(axis=0)).max() <= 1e-9 * np.abs(f).sum()
+    assert s0.n_particles == len(ids) and s0.n_pair_entries > 3 * len(ids)
+    v = np.sqrt((p0[2][:, 3:6] ** 2).sum(axis=1))
+    assert abs(s0.v_max - v.max()) <= 1e-15 * v.max() and abs(s0.v_sum - v.sum()) <= 1e-10 * v.sum()

@@ -76,12 +76,12 @@ def random_packing(n_side, d=0.005, spacing=1.02, jitter=0.05, seed=19, poly=0.0
 
 def packing_parameters(extent, d=0.005, cell=None, pp_model="hertz_mindlin_limit_overlap", pw_model="nonlinear", rolling="none",
                        dt=1e-5, g=(0, 0, -9.81), n_types=1, periodic=(0, 0, 0), surface_energy=0.0, hamaker=4e-19, young=1e6,
-                       cell_order="lexicographic"):
+                       cell_order="lexicographic", search_factor=0.05):
     p = DEMParameters()
     p.time_step = dt
     p.pp_model, p.pw_model, p.rolling_model = pp_model, pw_model, rolling
     p.g = g
-    p.dynamic_contact_search_factor = 0.9
+    p.dynamic_contact_search_factor = search_factor  # small: several list rebuilds within a short test
     p.particle_types = []
     for t in range(n_types):
         p.particle_types.append(ParticleType(diameter=d, young=young * (1 + t), poisson=0.3 - 0.05 * t, restitution=0.3 + 0.2 * t,
