@@ -52,12 +52,12 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -69,10 +69,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
@@ -170,11 +170,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-particles", type=int, default=40_000)
     ap.add_argument("--cpu-steps", type=int, default=300)
-    ap.add_argument("--cpu-settle", type=int, default=300)
+    ap.add_argument("--cpu-settle", type=int, default=-1, help="settling steps of the CPU sample (-1: same as --settle)")
     ap.add_argument("--cpu-substeps", type=int, default=100)
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.cpu_settle < 0:
+        args.cpu_settle = args.settle
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -188,7 +190,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from lethe_b200 import abi, multi
+    from lethe_b200 import abi
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the DEM engine has no CPU fallback")
@@ -199,6 +201,8 @@ def main():
     w = make_workload(args, rank, world)
     cfg_params = w.params
     if world > 1:
+        from lethe_b200 import multi
+
         engine, n_local = multi.create_slab_engine(w, rank, world, local_rank, dist)
     else:
         engine = abi.load_engine(cfg_params.to_config(), local_rank)
