@@ -1,0 +1,194 @@
+// dem_context.cuh — the engine context (all device buffers of one GPU) shared by
+// dem_engine.cu (control flow + C ABI) and dem_multi.cu (slab exchange).
+#pragma once
+
+#include <algorithm>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dem_kernels.cuh"
+#include "dem_multi.cuh"
+
+#define CU_TRY(call)                                                                                       \
+  do                                                                                                       \
+    {                                                                                                      \
+      cudaError_t err__ = (call);                                                                          \
+      if (err__ != cudaSuccess)                                                                            \
+        {                                                                                                  \
+          char buf__[512];                                                                                 \
+          snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+          throw std::runtime_error(buf__);                                                                 \
+        }                                                                                                  \
+    }                                                                                                      \
+  while (0)
+
+namespace dem
+{
+  template <class T> struct DevBuf
+  {
+    T *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+      if (p)
+        cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+    // grow to hold n elements; keep_n > 0 preserves the first keep_n elements
+    void ensure(size_t n, size_t keep_n = 0, cudaStream_t s = 0, double growth = 1.25)
+    {
+      if (n <= cap)
+        return;
+      size_t ncap = std::max<size_t>(n, size_t(double(cap) * growth) + 16);
+      T *np = nullptr;
+      CU_TRY(cudaMalloc(&np, ncap * sizeof(T)));
+      if (keep_n && p)
+        {
+          CU_TRY(cudaMemcpyAsync(np, p, std::min(keep_n, cap) * sizeof(T), cudaMemcpyDeviceToDevice, s));
+          CU_TRY(cudaStreamSynchronize(s));
+        }
+      if (p)
+        cudaFree(p);
+      p = np;
+      cap = ncap;
+    }
+  };
+
+  struct StateBufs
+  {
+    DevBuf<double4> pos, vel, omg;
+    DevBuf<uint32_t> id;
+    DevBuf<int32_t> cell_reg;
+    dem::StateView view() { return dem::StateView{pos.p, vel.p, omg.p}; }
+    void ensure(size_t n, size_t keep, cudaStream_t s)
+    {
+      pos.ensure(n, keep, s);
+      vel.ensure(n, keep, s);
+      omg.ensure(n, keep, s);
+      id.ensure(n, keep, s);
+      cell_reg.ensure(n, keep, s);
+    }
+  };
+
+  struct ListBufs
+  {
+    DevBuf<uint32_t> row_start, col;
+    DevBuf<double> hist, roll;
+    DevBuf<uint8_t> img;
+    uint32_t n_rows = 0;
+    uint64_t n_entries = 0;
+    dem::ListView view() { return dem::ListView{row_start.p, col.p, hist.p, roll.p, img.p}; }
+  };
+  struct WallListBufs
+  {
+    DevBuf<uint32_t> row_start, entry;
+    DevBuf<double> hist, roll;
+    uint32_t n_rows = 0;
+    uint64_t n_entries = 0;
+    dem::WallListView view() { return dem::WallListView{row_start.p, entry.p, hist.p, roll.p}; }
+  };
+
+} // namespace dem
+
+using dem::DevBuf;
+using dem::ListBufs;
+using dem::StateBufs;
+using dem::WallListBufs;
+
+struct lethe_dem_ctx
+{
+  using GridDesc = dem::GridDesc;
+  using MaterialTables = dem::MaterialTables;
+  using BoundaryMotionDev = dem::BoundaryMotionDev;
+  using FloatingWallsDev = dem::FloatingWallsDev;
+  using StatsPartial = dem::StatsPartial;
+  lethe_dem_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+
+  GridDesc grid;
+  MaterialTables mt;
+  double thr2 = 0;
+
+  // state: generation `cur` is current; the step kernel writes cur^1. ids / registered cells
+  // only change at a rebuild and follow their own generation `cur_ids`.
+  StateBufs st[2];
+  int cur = 0;
+  DevBuf<double> disp;
+  uint32_t n_owned = 0; // particles owned (integrated) by this context
+  uint32_t n_ghost = 0; // ghost copies stored behind the owned ones
+  // id -> particle slot map of the current list generation; the previous generation's map is
+  // kept as the history source of ghost copies (multi-GPU)
+  DevBuf<uint32_t> slot_of_id, slot_of_id_old;
+  uint32_t slot_map_size = 0, slot_map_size_old = 0;
+  uint32_t old_n_owned = 0;
+  // ghost runs (multi-GPU): [start,end) per curve rank for the copies received from the lower /
+  // upper neighbour rank
+  DevBuf<uint32_t> ghost_start[2], ghost_end[2];
+  uint32_t n_ghost_run[2] = {0, 0};
+
+  // lists (double-buffered across rebuilds: the old one is the history source)
+  ListBufs lists[2];
+  WallListBufs wlists[2];
+  int cur_list = 0;
+
+  // grid tables
+  DevBuf<int32_t> cell_rank, cell_of_rank;
+  DevBuf<uint32_t> cell_count, cell_start;
+  DevBuf<uint32_t> key, slot, perm, old_of_new, counts, scan_tmp;
+
+  // walls
+  std::vector<lethe_wall_face> faces_host; // sorted by cell
+  DevBuf<uint32_t> cell_face_start;
+  DevBuf<double> face_normal, face_point;
+  DevBuf<uint32_t> face_boundary;
+  DevBuf<int32_t> face_motion;
+  uint32_t n_faces = 0;
+  std::vector<uint32_t> face_gid_host;
+  struct Motion
+  {
+    uint32_t boundary_id;
+    BoundaryMotionDev m;
+  };
+  std::vector<Motion> motions_host;
+  DevBuf<BoundaryMotionDev> motions;
+  FloatingWallsDev fw_host;
+  DevBuf<FloatingWallsDev> fw_dev;
+  DevBuf<uint32_t> cell_fw_mask;
+  bool walls_dirty = true;
+
+  // triggers / time (DEMActionManager + SimulationControl)
+  uint64_t iteration_number = 0;
+  double current_time = 0;
+  bool contact_search_trigger = true;
+  bool clear_history_trigger = false;
+  uint64_t n_rebuilds = 0;
+  int *h_flag = nullptr; // mapped pinned: written by the step kernel
+  int *d_flag = nullptr;
+
+  // debug taps
+  DevBuf<double> force_out, torque_out;
+  DevBuf<unsigned long long> touching;
+
+  // staging for host rows
+  DevBuf<uint32_t> stage_ids;
+  DevBuf<double> stage_x, stage_p;
+  DevBuf<StatsPartial> stats_partials;
+
+  // timers
+  bool timers_enabled = false;
+  bool count_touching = false;
+  cudaEvent_t region_ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> event_pool;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_step, pending_rebuild;
+  double step_ms = 0, rebuild_ms = 0;
+  uint64_t step_launches = 0, rebuild_launches = 0;
+
+  dem::MultiGpu multi;
+};
+

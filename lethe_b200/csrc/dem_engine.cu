@@ -16,175 +16,14 @@
 #include <string>
 #include <vector>
 
-#include "dem_kernels.cuh"
-#include "dem_multi.cuh"
+#include "dem_context.cuh"
 
 using namespace dem;
 
-#define CU_TRY(call)                                                                                       \
-  do                                                                                                       \
-    {                                                                                                      \
-      cudaError_t err__ = (call);                                                                          \
-      if (err__ != cudaSuccess)                                                                            \
-        {                                                                                                  \
-          char buf__[512];                                                                                 \
-          snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
-          throw std::runtime_error(buf__);                                                                 \
-        }                                                                                                  \
-    }                                                                                                      \
-  while (0)
-
 namespace
 {
-  template <class T> struct DevBuf
-  {
-    T *p = nullptr;
-    size_t cap = 0;
-    ~DevBuf() { release(); }
-    void release()
-    {
-      if (p)
-        cudaFree(p);
-      p = nullptr;
-      cap = 0;
-    }
-    // grow to hold n elements; keep_n > 0 preserves the first keep_n elements
-    void ensure(size_t n, size_t keep_n = 0, cudaStream_t s = 0, double growth = 1.25)
-    {
-      if (n <= cap)
-        return;
-      size_t ncap = std::max<size_t>(n, size_t(double(cap) * growth) + 16);
-      T *np = nullptr;
-      CU_TRY(cudaMalloc(&np, ncap * sizeof(T)));
-      if (keep_n && p)
-        {
-          CU_TRY(cudaMemcpyAsync(np, p, std::min(keep_n, cap) * sizeof(T), cudaMemcpyDeviceToDevice, s));
-          CU_TRY(cudaStreamSynchronize(s));
-        }
-      if (p)
-        cudaFree(p);
-      p = np;
-      cap = ncap;
-    }
-  };
-
-  struct StateBufs
-  {
-    DevBuf<double4> pos, vel, omg;
-    DevBuf<uint32_t> id;
-    DevBuf<int32_t> cell_reg;
-    StateView view() { return StateView{pos.p, vel.p, omg.p}; }
-    void ensure(size_t n, size_t keep, cudaStream_t s)
-    {
-      pos.ensure(n, keep, s);
-      vel.ensure(n, keep, s);
-      omg.ensure(n, keep, s);
-      id.ensure(n, keep, s);
-      cell_reg.ensure(n, keep, s);
-    }
-  };
-
-  struct ListBufs
-  {
-    DevBuf<uint32_t> row_start, col;
-    DevBuf<double> hist, roll;
-    DevBuf<uint8_t> img;
-    uint32_t n_rows = 0;
-    uint64_t n_entries = 0;
-    ListView view() { return ListView{row_start.p, col.p, hist.p, roll.p, img.p}; }
-  };
-  struct WallListBufs
-  {
-    DevBuf<uint32_t> row_start, entry;
-    DevBuf<double> hist, roll;
-    uint32_t n_rows = 0;
-    uint64_t n_entries = 0;
-    WallListView view() { return WallListView{row_start.p, entry.p, hist.p, roll.p}; }
-  };
-
   std::string g_create_error;
-} // namespace
-
-struct lethe_dem_ctx
-{
-  lethe_dem_config cfg;
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::string error;
-
-  GridDesc grid;
-  MaterialTables mt;
-  double thr2 = 0;
-
-  // state: generation `cur` is current; the step kernel writes cur^1. ids / registered cells
-  // only change at a rebuild and follow their own generation `cur_ids`.
-  StateBufs st[2];
-  int cur = 0;
-  DevBuf<double> disp;
-  uint32_t n_owned = 0; // particles owned (integrated) by this context
-  uint32_t n_ghost = 0; // ghost copies stored behind the owned ones
-  DevBuf<uint32_t> slot_of_id;
-  uint32_t slot_map_size = 0;
-
-  // lists (double-buffered across rebuilds: the old one is the history source)
-  ListBufs lists[2];
-  WallListBufs wlists[2];
-  int cur_list = 0;
-
-  // grid tables
-  DevBuf<int32_t> cell_rank, cell_of_rank;
-  DevBuf<uint32_t> cell_count, cell_start;
-  DevBuf<uint32_t> key, slot, perm, old_of_new, counts, scan_tmp;
-
-  // walls
-  std::vector<lethe_wall_face> faces_host; // sorted by cell
-  DevBuf<uint32_t> cell_face_start;
-  DevBuf<double> face_normal, face_point;
-  DevBuf<uint32_t> face_boundary;
-  DevBuf<int32_t> face_motion;
-  uint32_t n_faces = 0;
-  std::vector<uint32_t> face_gid_host;
-  struct Motion
-  {
-    uint32_t boundary_id;
-    BoundaryMotionDev m;
-  };
-  std::vector<Motion> motions_host;
-  DevBuf<BoundaryMotionDev> motions;
-  FloatingWallsDev fw_host;
-  DevBuf<FloatingWallsDev> fw_dev;
-  DevBuf<uint32_t> cell_fw_mask;
-  bool walls_dirty = true;
-
-  // triggers / time (DEMActionManager + SimulationControl)
-  uint64_t iteration_number = 0;
-  double current_time = 0;
-  bool contact_search_trigger = true;
-  bool clear_history_trigger = false;
-  uint64_t n_rebuilds = 0;
-  int *h_flag = nullptr; // mapped pinned: written by the step kernel
-  int *d_flag = nullptr;
-
-  // debug taps
-  DevBuf<double> force_out, torque_out;
-  DevBuf<unsigned long long> touching;
-
-  // staging for host rows
-  DevBuf<uint32_t> stage_ids;
-  DevBuf<double> stage_x, stage_p;
-  DevBuf<StatsPartial> stats_partials;
-
-  // timers
-  bool timers_enabled = false;
-  bool count_touching = false;
-  cudaEvent_t region_ev[2] = {nullptr, nullptr};
-  std::vector<cudaEvent_t> event_pool;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_step, pending_rebuild;
-  double step_ms = 0, rebuild_ms = 0;
-  uint64_t step_launches = 0, rebuild_launches = 0;
-
-  dem::MultiGpu multi;
-};
+}
 
 namespace
 {
@@ -413,27 +252,15 @@ namespace
   }
 
   // ------------------------------------------------------------ rebuild ----
-  void rebuild(Ctx *c)
+  // Phase 1: periodic wrap, binning, counting sort along the Morton curve, permutation of the
+  // owned particles into cell order (drops particles that left the domain or migrated away).
+  void rebuild_sort(Ctx *c)
   {
     cudaStream_t s = c->stream;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (c->timers_enabled)
-      {
-        ev0 = get_event(c);
-        ev1 = get_event(c);
-        CU_TRY(cudaEventRecord(ev0, s));
-      }
-    upload_walls(c);
     const int n_cells = c->grid.n_cells;
-    const bool use_roll = c->cfg.rolling_model == LETHE_ROLLING_EPSD;
-    const bool use_img = c->grid.periodic[0] || c->grid.periodic[1] || c->grid.periodic[2];
-
-    // multi-GPU: drop last rebuild's ghosts; they are re-exchanged below
     uint32_t n = c->n_owned;
     StateBufs &src = c->st[c->cur];
     StateBufs &dst = c->st[c->cur ^ 1];
-
-    // 1. bin + periodic wrap
     c->key.ensure(n + 1);
     c->slot.ensure(n + 1);
     c->perm.ensure(n + 1);
@@ -443,33 +270,48 @@ namespace
     CU_TRY(cudaMemsetAsync(c->cell_count.p, 0, (size_t(n_cells) + 8) * 4, s));
     BinParams bp{src.pos.p, src.cell_reg.p, c->grid, c->cell_rank.p, c->cell_count.p, c->key.p, c->slot.p, n};
     launch_bin(bp, s);
-    // buckets: [0,n_cells) cells in curve order, n_cells = left the domain (+ migration buckets)
+    // buckets: [0,n_cells) cells in curve order, n_cells = left the domain / migrated
     const size_t n_buckets = size_t(n_cells) + 3;
     exclusive_scan_u32(c->cell_count.p, c->cell_start.p, n_buckets + 1, c->scan_tmp.p, s);
     launch_scatter_perm(c->key.p, c->slot.p, c->cell_start.p, c->perm.p, n, s);
     launch_sort_cells(c->cell_start.p, uint32_t(n_buckets), c->perm.p, src.id.p, s);
     const uint32_t n_new = read_u32(c, c->cell_start.p + n_cells); // particles still inside the domain
 
-    // 2. permute the state into cell order
     dst.ensure(std::max<size_t>(n_new, 1), 0, s);
     c->old_of_new.ensure(std::max<size_t>(n_new, 1));
     c->disp.ensure(std::max<size_t>(n_new, 1), 0, s);
+    // the id map of the outgoing list generation becomes the "old" one
+    std::swap(c->slot_of_id.p, c->slot_of_id_old.p);
+    std::swap(c->slot_of_id.cap, c->slot_of_id_old.cap);
+    c->slot_map_size_old = c->slot_map_size;
+    c->slot_of_id.ensure(std::max<size_t>(c->slot_map_size, 1));
     if (c->slot_map_size)
       launch_fill_u32(c->slot_of_id.p, 0xffffffffu, c->slot_map_size, s);
     GatherParams gp{src.view(), dst.view(), src.id.p,       dst.id.p,       c->perm.p, c->key.p,
                     c->cell_of_rank.p, dst.cell_reg.p,      c->old_of_new.p, c->disp.p, c->slot_of_id.p, n_new};
     launch_gather(gp, s);
     c->cur ^= 1;
+    c->old_n_owned = c->lists[c->cur_list].n_rows;
     c->n_owned = n_new;
     c->n_ghost = 0;
-    StateBufs &stn = c->st[c->cur];
+    c->n_ghost_run[0] = c->n_ghost_run[1] = 0;
     // the other generation must be able to hold the step kernel's output
     c->st[c->cur ^ 1].ensure(std::max<size_t>(n_new, 1), 0, s);
+  }
 
-    // 3. particle-particle list
+  // Phase 2: contact lists (particle-particle with history carry-over, particle-wall).
+  void rebuild_lists(Ctx *c)
+  {
+    cudaStream_t s = c->stream;
+    const bool use_roll = c->cfg.rolling_model == LETHE_ROLLING_EPSD;
+    const bool use_img = c->grid.periodic[0] || c->grid.periodic[1] || c->grid.periodic[2];
+    const uint32_t n_new = c->n_owned;
+    StateBufs &stn = c->st[c->cur];
+
     ListBufs &oldl = c->lists[c->cur_list];
     ListBufs &newl = c->lists[c->cur_list ^ 1];
     c->counts.ensure(size_t(n_new) + 2);
+    c->scan_tmp.ensure(scan_tmp_elems(size_t(n_new) + 8));
     newl.row_start.ensure(size_t(n_new) + 2);
     NeighborParams np;
     np.st = stn.view();
@@ -479,7 +321,13 @@ namespace
     np.grid = c->grid;
     np.thr2 = c->thr2;
     np.n_rows = n_new;
-    np.n_total = n_new;
+    np.n_total = n_new + c->n_ghost;
+    for (int k = 0; k < 2; ++k)
+      {
+        np.ghost_start[k] = c->n_ghost_run[k] ? c->ghost_start[k].p : nullptr;
+        np.ghost_end[k] = c->n_ghost_run[k] ? c->ghost_end[k].p : nullptr;
+      }
+    np.old_n_owned = c->old_n_owned;
     np.old_list = oldl.view();
     np.old_of_new = c->old_of_new.p;
     np.n_old_rows = oldl.n_rows;
@@ -502,7 +350,6 @@ namespace
     newl.n_rows = n_new;
     newl.n_entries = n_entries;
 
-    // 4. particle-wall list
     WallListBufs &oldw = c->wlists[c->cur_list];
     WallListBufs &neww = c->wlists[c->cur_list ^ 1];
     neww.row_start.ensure(size_t(n_new) + 2);
@@ -535,11 +382,26 @@ namespace
     neww.n_entries = n_wall;
 
     c->cur_list ^= 1;
-    *c->h_flag = 0; // stream is idle w.r.t. the flag: last reader/writer synchronised above
+    CU_TRY(cudaStreamSynchronize(s));
+    *c->h_flag = 0; // no kernel in flight can touch the flag here
     ++c->n_rebuilds;
+  }
+
+  void rebuild(Ctx *c)
+  {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (c->timers_enabled)
       {
-        CU_TRY(cudaEventRecord(ev1, s));
+        ev0 = get_event(c);
+        ev1 = get_event(c);
+        CU_TRY(cudaEventRecord(ev0, c->stream));
+      }
+    upload_walls(c);
+    rebuild_sort(c);
+    rebuild_lists(c);
+    if (c->timers_enabled)
+      {
+        CU_TRY(cudaEventRecord(ev1, c->stream));
         c->pending_rebuild.emplace_back(ev0, ev1);
         ++c->rebuild_launches;
       }
@@ -613,7 +475,7 @@ namespace
   void mirror_ids(Ctx *c)
   {
     StateBufs &a = c->st[c->cur], &b = c->st[c->cur ^ 1];
-    const size_t n = c->n_owned;
+    const size_t n = size_t(c->n_owned) + c->n_ghost;
     if (!n)
       return;
     b.id.ensure(n);
@@ -635,10 +497,17 @@ namespace
     else if (!search && (c->iteration_number % freq) == 0)
       {
         // max displacement > criterion, evaluated by the previous step kernel
-        CU_TRY(cudaStreamSynchronize(c->stream));
-        if (*c->h_flag)
-          search = true;
+        if (c->multi.enabled())
+          search = c->multi.any_rank_flag(c); // MPI logical_or (find_contact_detection_step.cc:53-58)
+        else
+          {
+            CU_TRY(cudaStreamSynchronize(c->stream));
+            if (*c->h_flag)
+              search = true;
+          }
       }
+    if (c->multi.enabled())
+      search = c->multi.agree(c, search); // logical_or over ranks; insertion on one rank triggers all
     if (search)
       {
         if (c->multi.enabled())
@@ -749,6 +618,11 @@ namespace dem
     rebuild(c);
     mirror_ids(c);
   }
+  void engine_upload_walls(lethe_dem_ctx *c) { upload_walls(c); }
+  void engine_rebuild_sort(lethe_dem_ctx *c) { rebuild_sort(c); }
+  void engine_rebuild_lists(lethe_dem_ctx *c) { rebuild_lists(c); }
+  void engine_mirror_ids(lethe_dem_ctx *c) { mirror_ids(c); }
+  cudaEvent_t engine_get_event(lethe_dem_ctx *c) { return get_event(c); }
 } // namespace dem
 
 // =================================================================== C ABI ===

@@ -146,7 +146,7 @@ namespace dem
           x.z = xv[2];
           P.pos[p] = x;
         }
-      const int lin = cell_of_point(g, x.x, x.y, x.z);
+      const int lin = creg == -2 ? -1 : cell_of_point(g, x.x, x.y, x.z); // -2: migrated to a neighbour rank
       uint32_t bucket;
       if (lin < 0)
         bucket = uint32_t(g.n_cells); // left the triangulation: dropped
@@ -255,39 +255,55 @@ namespace dem
                   const uint32_t img = (sx | sy | sz) ? uint32_t(1 + (sx + 1) + 3 * (sy + 1) + 9 * (sz + 1)) : 0u;
                   const int nlin = ni + g.n[0] * (nj + g.n[1] * nk);
                   const uint32_t rank = uint32_t(P.cell_rank[nlin]);
-                  const uint32_t s = P.cell_start[rank], e = P.cell_start[rank + 1];
-                  for (uint32_t r = s; r < e; ++r)
+                  // owned particles of the cell, then the ghost copies of either neighbour rank
+                  for (int range = 0; range < 3; ++range)
                     {
-                      if (r == q)
-                        continue;
-                      const double4 pr = P.st.pos[r];
-                      const vec3 xr = v3(pr.x, pr.y, pr.z);
-                      double d2;
-                      if (img)
+                      uint32_t s, e;
+                      if (range == 0)
                         {
-                          const vec3 shift = v3(sx * g.L[0], sy * g.L[1], sz * g.L[2]);
-                          const int first = sx != 0 ? sx : (sy != 0 ? sy : sz);
-                          // canonical orientation (see decode_image in dem_step.cu)
-                          if (first < 0)
-                            d2 = dist2(xq, xr + shift);
-                          else
-                            d2 = dist2(xr, xq + (-shift));
+                          s = P.cell_start[rank];
+                          e = P.cell_start[rank + 1];
                         }
                       else
-                        d2 = dist2(xq, xr);
-                      bool in = d2 < P.thr2;
-                      if (!in && d2 == P.thr2 && old_q != 0xffffffffu && old_q < P.n_old_rows)
                         {
-                          // pairs sitting exactly on the threshold are neither inserted (<) nor
-                          // erased (>): they survive iff they were already listed.
-                          const uint32_t old_r = P.old_of_new[r];
-                          for (uint32_t eo = P.old_list.row_start[old_q]; eo < P.old_list.row_start[old_q + 1]; ++eo)
-                            if ((P.old_list.col[eo] & COL_INDEX_MASK) == old_r &&
-                                ((P.use_img ? P.old_list.img[eo] != 0 : false) == (img != 0)))
-                              in = true;
+                          if (!P.ghost_start[range - 1])
+                            continue;
+                          s = P.ghost_start[range - 1][rank];
+                          e = P.ghost_end[range - 1][rank];
                         }
-                      if (in)
-                        f(r, img);
+                  for (uint32_t r = s; r < e; ++r)
+                        {
+                          if (r == q)
+                            continue;
+                          const double4 pr = P.st.pos[r];
+                          const vec3 xr = v3(pr.x, pr.y, pr.z);
+                          double d2;
+                          if (img)
+                            {
+                              const vec3 shift = v3(sx * g.L[0], sy * g.L[1], sz * g.L[2]);
+                              const int first = sx != 0 ? sx : (sy != 0 ? sy : sz);
+                              // canonical orientation (see decode_image in dem_step.cu)
+                              if (first < 0)
+                                d2 = dist2(xq, xr + shift);
+                              else
+                                d2 = dist2(xr, xq + (-shift));
+                            }
+                          else
+                            d2 = dist2(xq, xr);
+                          bool in = d2 < P.thr2;
+                          if (!in && d2 == P.thr2 && old_q != 0xffffffffu && old_q < P.n_old_rows)
+                            {
+                              // pairs sitting exactly on the threshold are neither inserted (<) nor
+                              // erased (>): they survive iff they were already listed.
+                              const uint32_t old_r = P.old_of_new[r];
+                              for (uint32_t eo = P.old_list.row_start[old_q]; eo < P.old_list.row_start[old_q + 1]; ++eo)
+                                if ((P.old_list.col[eo] & COL_INDEX_MASK) == old_r &&
+                                    ((P.use_img ? P.old_list.img[eo] != 0 : false) == (img != 0)))
+                                  in = true;
+                            }
+                          if (in)
+                            f(r, img);
+                        }
                     }
                 }
             }
@@ -323,7 +339,11 @@ namespace dem
         if (have_old)
           {
             const uint32_t old_r = P.old_of_new[r];
-            for (uint32_t eo = o0; eo < o1; ++eo)
+            // a pair only keeps its history inside the same container: local-local vs local-ghost
+            // (the reference starts from zero when a partner changes ownership,
+            // update_fine_search_candidates.cc:136-152)
+            const bool same_class = old_r != 0xffffffffu && ((old_r < P.old_n_owned) == (r < P.n_rows));
+            for (uint32_t eo = o0; eo < o1 && same_class; ++eo)
               {
                 const uint32_t oc = P.old_list.col[eo];
                 if ((oc & COL_INDEX_MASK) != old_r)
@@ -573,6 +593,181 @@ namespace dem
       write_row(st.pos[q], st.vel[q], st.omg[q], x3, props9, q);
     }
 
+    // ---- multi-GPU helpers ----
+    __global__ void __launch_bounds__(256) k_classify(const __grid_constant__ ClassifyParams P)
+    {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      if (p >= P.n)
+        return;
+      const GridDesc &g = P.grid;
+      double4 x = P.pos[p];
+      const int creg = P.cell_reg[p];
+      if ((g.periodic[0] | g.periodic[1] | g.periodic[2]) && creg >= 0)
+        {
+          // same periodic displacement as k_bin (idempotent: the wrapped particle is then inside)
+          const int c[3] = {creg % g.n[0], (creg / g.n[0]) % g.n[1], creg / (g.n[0] * g.n[1])};
+          double xv[3] = {x.x, x.y, x.z};
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            {
+              if (!g.periodic[d])
+                continue;
+              const double lo = g.lo[d];
+              const double hi = g.lo[d] + g.n[d] * g.h[d];
+              if (c[d] == 0 && (xv[d] - lo) * -1.0 >= 0.0)
+                xv[d] += g.L[d];
+              if (c[d] == g.n[d] - 1 && (xv[d] - hi) * 1.0 >= 0.0)
+                xv[d] += -g.L[d];
+            }
+          x.x = xv[0];
+          x.y = xv[1];
+          x.z = xv[2];
+          P.pos[p] = x;
+          P.cell_reg[p] = -1; // wrapped already: k_bin must not wrap it a second time
+        }
+      const int lin = cell_of_point(g, x.x, x.y, x.z);
+      if (lin < 0)
+        return; // left the domain: the sort drops it
+      const int a = g.slab_axis;
+      const int ca = a == 0 ? lin % g.n[0] : (a == 1 ? (lin / g.n[0]) % g.n[1] : lin / (g.n[0] * g.n[1]));
+      if (ca >= g.slab_lo && ca < g.slab_hi)
+        return;
+      const int na = g.n[a];
+      int dir;
+      if (ca == g.slab_lo - 1 || (g.periodic[a] && ca == (g.slab_lo - 1 + na) % na))
+        dir = 0;
+      else if (ca == g.slab_hi || (g.periodic[a] && ca == g.slab_hi % na))
+        dir = 1;
+      else
+        {
+          atomicAdd(&P.send_count[2], 1u); // moved further than the neighbouring slab: not supported
+          P.cell_reg[p] = -2;
+          return;
+        }
+      const uint32_t k = atomicAdd(&P.send_count[dir], 1u);
+      if (k < P.send_cap)
+        {
+          MigrateRecord r;
+          r.pos = x;
+          r.vel = P.vel[p];
+          r.omg = P.omg[p];
+          P.send_rec[dir][k] = r;
+          P.send_id[dir][k] = P.id[p];
+        }
+      P.cell_reg[p] = -2;
+    }
+
+    __global__ void __launch_bounds__(256) k_append_records(const MigrateRecord *rec, const uint32_t *ids, uint32_t n, StateView st,
+                                                            uint32_t *id_out, int32_t *cell_reg, double *disp, uint32_t base)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t q = base + k;
+      st.pos[q] = rec[k].pos;
+      st.vel[q] = rec[k].vel;
+      st.omg[q] = rec[k].omg;
+      id_out[q] = ids[k];
+      cell_reg[q] = -1;
+      disp[q] = 0.0;
+    }
+
+    __global__ void __launch_bounds__(256) k_flag_layer(const int32_t *cell_reg, GridDesc g, int layer_cell, uint32_t n, uint32_t *flags)
+    {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      if (p > n)
+        return;
+      if (p == n)
+        {
+          flags[p] = 0;
+          return;
+        }
+      const int lin = cell_reg[p];
+      const int a = g.slab_axis;
+      const int ca = a == 0 ? lin % g.n[0] : (a == 1 ? (lin / g.n[0]) % g.n[1] : lin / (g.n[0] * g.n[1]));
+      flags[p] = ca == layer_cell ? 1u : 0u;
+    }
+
+    __global__ void __launch_bounds__(256) k_compact_indices(const uint32_t *flags, const uint32_t *offsets, uint32_t n, uint32_t *out)
+    {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      if (p < n && flags[p])
+        out[offsets[p]] = p;
+    }
+
+    __global__ void __launch_bounds__(256) k_gather_state(StateView st, const uint32_t *idx, uint32_t n, double4 *pos, double4 *vel,
+                                                          double4 *omg)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t p = idx[k];
+      pos[k] = st.pos[p];
+      vel[k] = st.vel[p];
+      omg[k] = st.omg[p];
+    }
+
+    __global__ void __launch_bounds__(256) k_gather_ids(const uint32_t *id, const uint32_t *idx, uint32_t n, uint32_t *out)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k < n)
+        out[k] = id[idx[k]];
+    }
+
+    __global__ void __launch_bounds__(256) k_ghost_run(const __grid_constant__ GhostRunParams P)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= P.n)
+        return;
+      const double4 x = P.pos[k];
+      const int lin = cell_of_point(P.grid, x.x, x.y, x.z);
+      const uint32_t q = P.base + k;
+      P.cell_reg[q] = lin;
+      // the run arrives sorted by (curve rank, id): cell boundaries are where the rank changes
+      const uint32_t rank = lin >= 0 ? uint32_t(P.cell_rank[lin]) : 0xffffffffu;
+      uint32_t prev = 0xffffffffu, next = 0xffffffffu;
+      if (k > 0)
+        {
+          const double4 xp = P.pos[k - 1];
+          const int lp = cell_of_point(P.grid, xp.x, xp.y, xp.z);
+          prev = lp >= 0 ? uint32_t(P.cell_rank[lp]) : 0xffffffffu;
+        }
+      if (k + 1 < P.n)
+        {
+          const double4 xn = P.pos[k + 1];
+          const int ln = cell_of_point(P.grid, xn.x, xn.y, xn.z);
+          next = ln >= 0 ? uint32_t(P.cell_rank[ln]) : 0xffffffffu;
+        }
+      if (rank != 0xffffffffu)
+        {
+          if (k == 0 || prev != rank)
+            P.start[rank] = q;
+          if (k + 1 == P.n || next != rank)
+            P.end[rank] = q + 1;
+        }
+      // history source: the ghost's slot in the previous list generation (ghost -> ghost only)
+      uint32_t old = 0xffffffffu;
+      const uint32_t pid = P.id[q];
+      if (P.old_slot_of_id && pid < P.old_map_size)
+        {
+          const uint32_t o = P.old_slot_of_id[pid];
+          if (o != 0xffffffffu && o >= P.old_n_owned)
+            old = o;
+        }
+      P.old_of_new[q] = old;
+    }
+
+    __global__ void __launch_bounds__(256) k_register_ids(const uint32_t *id, uint32_t base, uint32_t n, uint32_t *slot_of_id,
+                                                          uint32_t map_size)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t pid = id[base + k];
+      if (pid < map_size)
+        slot_of_id[pid] = base + k;
+    }
+
     __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *p, uint32_t v, size_t n)
     {
       for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
@@ -703,6 +898,69 @@ namespace dem
     if (n)
       k_pack_all_rows<<<blocks_for(n, 256), 256, 0, s>>>(st, id, n, ids_out, x3, props9);
       count_launch();
+  }
+  void launch_classify(const ClassifyParams &p, cudaStream_t s)
+  {
+    if (p.n)
+      {
+        k_classify<<<blocks_for(p.n, 256), 256, 0, s>>>(p);
+        count_launch();
+      }
+  }
+  void launch_append_records(const MigrateRecord *rec, const uint32_t *ids, uint32_t n, StateView st, uint32_t *id_out,
+                             int32_t *cell_reg, double *disp, uint32_t base, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_append_records<<<blocks_for(n, 256), 256, 0, s>>>(rec, ids, n, st, id_out, cell_reg, disp, base);
+        count_launch();
+      }
+  }
+  void launch_flag_layer(const int32_t *cell_reg, GridDesc grid, int layer_cell, uint32_t n, uint32_t *flags, cudaStream_t s)
+  {
+    k_flag_layer<<<blocks_for(size_t(n) + 1, 256), 256, 0, s>>>(cell_reg, grid, layer_cell, n, flags);
+    count_launch();
+  }
+  void launch_compact_indices(const uint32_t *flags, const uint32_t *offsets, uint32_t n, uint32_t *out, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_compact_indices<<<blocks_for(n, 256), 256, 0, s>>>(flags, offsets, n, out);
+        count_launch();
+      }
+  }
+  void launch_gather_state(StateView st, const uint32_t *idx, uint32_t n, double4 *pos, double4 *vel, double4 *omg,
+                           cudaStream_t s)
+  {
+    if (n)
+      {
+        k_gather_state<<<blocks_for(n, 256), 256, 0, s>>>(st, idx, n, pos, vel, omg);
+        count_launch();
+      }
+  }
+  void launch_gather_ids(const uint32_t *id, const uint32_t *idx, uint32_t n, uint32_t *out, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_gather_ids<<<blocks_for(n, 256), 256, 0, s>>>(id, idx, n, out);
+        count_launch();
+      }
+  }
+  void launch_ghost_run(const GhostRunParams &p, cudaStream_t s)
+  {
+    if (p.n)
+      {
+        k_ghost_run<<<blocks_for(p.n, 256), 256, 0, s>>>(p);
+        count_launch();
+      }
+  }
+  void launch_register_ids(const uint32_t *id, uint32_t base, uint32_t n, uint32_t *slot_of_id, uint32_t map_size, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_register_ids<<<blocks_for(n, 256), 256, 0, s>>>(id, base, n, slot_of_id, map_size);
+        count_launch();
+      }
   }
   void launch_fill_u32(uint32_t *p, uint32_t v, size_t n, cudaStream_t s)
   {

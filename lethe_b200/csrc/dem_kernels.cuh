@@ -162,6 +162,54 @@ namespace dem
   };
   void launch_gather(const GatherParams &p, cudaStream_t s);
 
+  // ---- multi-GPU helpers (dem_multi.cu drives them) ----
+  struct MigrateRecord
+  {
+    double4 pos, vel, omg;
+  };
+  // classify owned particles against the slab [slab_lo, slab_hi) along grid.slab_axis after the
+  // periodic wrap; movers are appended to send buffers (dir 0 = lower neighbour, 1 = upper) and
+  // marked cell_reg = -2 so that the following sort drops them.
+  struct ClassifyParams
+  {
+    double4 *pos;
+    const double4 *vel, *omg;
+    const uint32_t *id;
+    int32_t *cell_reg;
+    GridDesc grid;
+    uint32_t n;
+    MigrateRecord *send_rec[2];
+    uint32_t *send_id[2];
+    uint32_t *send_count; // [2] + [2] = far movers (error)
+    uint32_t send_cap;
+  };
+  void launch_classify(const ClassifyParams &p, cudaStream_t s);
+  void launch_append_records(const MigrateRecord *rec, const uint32_t *ids, uint32_t n, StateView st, uint32_t *id_out,
+                             int32_t *cell_reg, double *disp, uint32_t base, cudaStream_t s);
+  // flag owned particles (sorted) lying in the slab's boundary cell layer `layer` along the axis
+  void launch_flag_layer(const int32_t *cell_reg, GridDesc grid, int layer_cell, uint32_t n, uint32_t *flags, cudaStream_t s);
+  void launch_compact_indices(const uint32_t *flags, const uint32_t *offsets, uint32_t n, uint32_t *out, cudaStream_t s);
+  void launch_gather_state(StateView st, const uint32_t *idx, uint32_t n, double4 *pos, double4 *vel, double4 *omg,
+                           cudaStream_t s);
+  void launch_gather_ids(const uint32_t *id, const uint32_t *idx, uint32_t n, uint32_t *out, cudaStream_t s);
+  // ghost run bookkeeping: cell of each ghost, [start,end) per curve rank, old index via id map
+  struct GhostRunParams
+  {
+    const double4 *pos; // ghost positions (run)
+    GridDesc grid;
+    const int32_t *cell_rank;
+    uint32_t base; // index of the first ghost of the run in the particle arrays
+    uint32_t n;
+    int32_t *cell_reg;          // [base + g]
+    uint32_t *start, *end;      // by curve rank, zero-initialised
+    const uint32_t *id;         // [base + g]
+    const uint32_t *old_slot_of_id;
+    uint32_t old_map_size, old_n_owned;
+    uint32_t *old_of_new;       // [base + g]
+  };
+  void launch_ghost_run(const GhostRunParams &p, cudaStream_t s);
+  void launch_register_ids(const uint32_t *id, uint32_t base, uint32_t n, uint32_t *slot_of_id, uint32_t map_size, cudaStream_t s);
+
   struct NeighborParams
   {
     StateView st;
@@ -172,6 +220,11 @@ namespace dem
     double thr2;
     uint32_t n_rows;  // rows built (owned particles)
     uint32_t n_total; // owned + ghost particles present in the cell lists
+    // ghost copies (multi-GPU): up to two runs, each sorted by curve rank, stored behind the
+    // owned particles; per-rank [start,end) tables or nullptr
+    const uint32_t *ghost_start[2];
+    const uint32_t *ghost_end[2];
+    uint32_t old_n_owned; // ownership split of the old list's particle indices
     // old list (history source)
     ListView old_list;
     const uint32_t *old_of_new; // new index -> old index or 0xffffffff

@@ -1,11 +1,431 @@
-// dem_multi.cu — placeholder until the slab exchange lands.
-#include <stdexcept>
-#include "dem_multi.cuh"
+// dem_multi.cu — slab decomposition over the GPUs of one node: one context per GPU per
+// process, NCCL point-to-point between neighbouring slabs.
+//
+// Reference behaviour mirrored (MPI through deal.II):
+//   every step      particle_handler.update_ghost_particles()                 (dem.cc:686)
+//                   + logical_or of the contact-detection flag                (find_contact_detection_step.cc:53-58)
+//   rebuild steps   sort_particles_into_subdomains_and_cells() (migration)
+//                   + exchange_ghost_particles(true)                           (dem.cc:986-989)
+// Cross-slab pairs are evaluated on both ranks and applied to the owned particle only, each
+// rank keeping its own copy of the pair history (…contact_force.h:2022-2033); the history of a
+// pair restarts from zero when one of its particles changes owner
+// (update_fine_search_candidates.cc:136-152).
+//
+// Layout: ghost copies live behind the owned particles in the same SoA arrays, as two runs
+// (from the lower / upper neighbour), each already sorted by (Morton cell rank, id) because
+// the sender's particles are. The per-step refresh therefore needs no unpack kernel: the
+// three state arrays are received straight into place.
+//
+// NCCL is loaded with dlopen so that single-GPU use has no dependency on it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "dem_context.cuh"
+
 namespace dem
 {
-  int MultiGpu::unique_id(uint8_t *) { return -1; }
-  void MultiGpu::init(lethe_dem_ctx *, int, int, const uint8_t *) { throw std::runtime_error("multi-GPU exchange not built"); }
-  void MultiGpu::shutdown() {}
-  void MultiGpu::rebuild_with_exchange(lethe_dem_ctx *) {}
-  void MultiGpu::refresh_ghosts(lethe_dem_ctx *) {}
+  namespace
+  {
+    struct NcclApi
+    {
+      void *handle = nullptr;
+      ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+      ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+      ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+      ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+      ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+      ncclResult_t (*GroupStart)() = nullptr;
+      ncclResult_t (*GroupEnd)() = nullptr;
+      ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+      const char *(*GetErrorString)(ncclResult_t) = nullptr;
+      bool load()
+      {
+        if (handle)
+          return true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"})
+          {
+            handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (handle)
+              break;
+          }
+        if (!handle)
+          return false;
+#define LOAD(sym) *(void **)(&sym) = dlsym(handle, "nccl" #sym)
+        LOAD(GetUniqueId);
+        LOAD(CommInitRank);
+        LOAD(CommDestroy);
+        LOAD(Send);
+        LOAD(Recv);
+        LOAD(GroupStart);
+        LOAD(GroupEnd);
+        LOAD(AllReduce);
+        LOAD(GetErrorString);
+#undef LOAD
+        return GetUniqueId && CommInitRank && Send && Recv && GroupStart && GroupEnd && AllReduce;
+      }
+    };
+    NcclApi g_nccl;
+
+    inline void nccl_check(ncclResult_t r, const char *what)
+    {
+      if (r != ncclSuccess)
+        throw std::runtime_error(std::string(what) + " failed: " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"));
+    }
+#define NCCL_TRY(call) nccl_check((call), #call)
+  } // namespace
+
+  struct MultiGpuImpl
+  {
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int peer[2] = {-1, -1}; // lower / upper neighbour rank or -1
+    // migration buffers
+    DevBuf<MigrateRecord> send_rec[2], recv_rec[2];
+    DevBuf<uint32_t> send_id[2], recv_id[2];
+    DevBuf<uint32_t> counters; // [4] device
+    DevBuf<uint32_t> xcount;   // [4] device: counts exchanged with the peers
+    // halo: indices of my boundary-layer particles per direction + packed send buffers
+    DevBuf<uint32_t> flags, offsets, send_idx[2], send_ids[2];
+    DevBuf<double4> send_pos[2], send_vel[2], send_omg[2];
+    uint32_t n_send[2] = {0, 0};
+    DevBuf<int> flag_dev; // [2]
+    int *flag_host = nullptr;
+  };
+
+  int MultiGpu::unique_id(uint8_t *id128)
+  {
+    if (!g_nccl.load())
+      return -1;
+    static_assert(sizeof(ncclUniqueId) == LETHE_DEM_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess)
+      return -2;
+    std::memcpy(id128, &id, sizeof(id));
+    return 0;
+  }
+
+  void MultiGpu::init(lethe_dem_ctx *c, int rank, int world, const uint8_t *id128)
+  {
+    if (!g_nccl.load())
+      throw std::runtime_error("libnccl.so.2 not found: multi-GPU needs NCCL");
+    if (c->grid.slab_axis < 0 || c->grid.slab_axis > 2)
+      throw std::runtime_error("config.slab_axis must be 0..2 for a multi-GPU context");
+    if (c->grid.slab_hi - c->grid.slab_lo < 2)
+      throw std::runtime_error("every slab needs at least 2 cell layers");
+    if (impl)
+      throw std::runtime_error("communicator already initialised");
+    MultiGpuImpl *m = new MultiGpuImpl();
+    m->rank = rank;
+    m->world = world;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    NCCL_TRY(g_nccl.CommInitRank(&m->comm, world, id, rank));
+    const bool periodic = c->grid.periodic[c->grid.slab_axis] != 0;
+    m->peer[0] = rank > 0 ? rank - 1 : (periodic && world > 1 ? world - 1 : -1);
+    m->peer[1] = rank < world - 1 ? rank + 1 : (periodic && world > 1 ? 0 : -1);
+    m->counters.ensure(8);
+    m->xcount.ensure(8);
+    m->flag_dev.ensure(2);
+    CU_TRY(cudaHostAlloc(&m->flag_host, 2 * sizeof(int), cudaHostAllocDefault));
+    impl = m;
+    c->contact_search_trigger = true;
+  }
+
+  void MultiGpu::shutdown()
+  {
+    if (!impl)
+      return;
+    if (impl->comm && g_nccl.CommDestroy)
+      g_nccl.CommDestroy(impl->comm);
+    if (impl->flag_host)
+      cudaFreeHost(impl->flag_host);
+    delete impl;
+    impl = nullptr;
+  }
+
+  bool MultiGpu::agree(lethe_dem_ctx *c, bool local)
+  {
+    MultiGpuImpl *m = impl;
+    cudaStream_t s = c->stream;
+    m->flag_host[0] = local ? 1 : 0;
+    CU_TRY(cudaMemcpyAsync(m->flag_dev.p, m->flag_host, sizeof(int), cudaMemcpyHostToDevice, s));
+    NCCL_TRY(g_nccl.AllReduce(m->flag_dev.p, m->flag_dev.p, 1, ncclInt32, ncclMax, m->comm, s));
+    CU_TRY(cudaMemcpyAsync(m->flag_host, m->flag_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return m->flag_host[0] != 0;
+  }
+
+  bool MultiGpu::any_rank_flag(lethe_dem_ctx *c)
+  {
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return *c->h_flag != 0; // agree() is applied by the caller to the combined decision
+  }
+
+  namespace
+  {
+    // exchange `n_send[d]` -> `n_recv[d]` (one u32 per direction) with the neighbours
+    void exchange_counts(lethe_dem_ctx *c, MultiGpuImpl *m, const uint32_t n_send[2], uint32_t n_recv[2])
+    {
+      cudaStream_t s = c->stream;
+      uint32_t h[4] = {n_send[0], n_send[1], 0, 0};
+      CU_TRY(cudaMemcpyAsync(m->xcount.p, h, 16, cudaMemcpyHostToDevice, s));
+      // phase A: count of what goes up, received from below; phase B: the other way round
+      // (see for_each_direction_pair for why the order matters when both peers are one rank)
+      NCCL_TRY(g_nccl.GroupStart());
+      if (m->peer[1] >= 0)
+        NCCL_TRY(g_nccl.Send(m->xcount.p + 1, 1, ncclUint32, m->peer[1], m->comm, s));
+      if (m->peer[0] >= 0)
+        NCCL_TRY(g_nccl.Recv(m->xcount.p + 2, 1, ncclUint32, m->peer[0], m->comm, s));
+      if (m->peer[0] >= 0)
+        NCCL_TRY(g_nccl.Send(m->xcount.p + 0, 1, ncclUint32, m->peer[0], m->comm, s));
+      if (m->peer[1] >= 0)
+        NCCL_TRY(g_nccl.Recv(m->xcount.p + 3, 1, ncclUint32, m->peer[1], m->comm, s));
+      NCCL_TRY(g_nccl.GroupEnd());
+      CU_TRY(cudaMemcpyAsync(h, m->xcount.p, 16, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      n_recv[0] = m->peer[0] >= 0 ? h[2] : 0;
+      n_recv[1] = m->peer[1] >= 0 ? h[3] : 0;
+    }
+
+    // With world == 2 and a periodic axis both neighbours are the same rank: NCCL matches the
+    // two send/recv pairs between the same peers in issue order, so rank 0 must post its
+    // (dir 0, dir 1) operations in the opposite order of rank 1's. Directions are therefore
+    // always issued as "send up / recv from below" first, then "send down / recv from above".
+    template <class F> void for_each_direction_pair(MultiGpuImpl *m, F &&f)
+    {
+      // phase A: send towards upper (dir 1), receive from lower (dir 0)
+      f(1, 0);
+      // phase B: send towards lower (dir 0), receive from upper (dir 1)
+      f(0, 1);
+      (void)m;
+    }
+  } // namespace
+
+  void MultiGpu::rebuild_with_exchange(lethe_dem_ctx *c)
+  {
+    MultiGpuImpl *m = impl;
+    cudaStream_t s = c->stream;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (c->timers_enabled)
+      {
+        CU_TRY(cudaEventCreate(&ev0));
+        CU_TRY(cudaEventCreate(&ev1));
+        CU_TRY(cudaEventRecord(ev0, s));
+      }
+    engine_upload_walls(c);
+
+    // ---- 0. the id -> slot maps must cover every id of the job (ghosts, immigrants) ----
+    {
+      uint32_t want = c->slot_map_size;
+      CU_TRY(cudaMemcpyAsync(m->xcount.p, &want, 4, cudaMemcpyHostToDevice, s));
+      NCCL_TRY(g_nccl.AllReduce(m->xcount.p, m->xcount.p, 1, ncclUint32, ncclMax, m->comm, s));
+      CU_TRY(cudaMemcpyAsync(&want, m->xcount.p, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      if (want > c->slot_map_size)
+        {
+          const size_t old = c->slot_map_size;
+          c->slot_of_id.ensure(want, old, s, 1.0);
+          launch_fill_u32(c->slot_of_id.p + old, 0xffffffffu, size_t(want) - old, s);
+          c->slot_map_size = want;
+        }
+    }
+
+    // ---- 1. migration of the particles that left the slab ----
+    const uint32_t n0 = c->n_owned;
+    const uint32_t cap = std::max<uint32_t>(1024u, n0 / 8 + 1024u);
+    for (int d = 0; d < 2; ++d)
+      {
+        m->send_rec[d].ensure(cap);
+        m->send_id[d].ensure(cap);
+      }
+    CU_TRY(cudaMemsetAsync(m->counters.p, 0, 32, s));
+    StateBufs &st = c->st[c->cur];
+    ClassifyParams cp;
+    cp.pos = st.pos.p;
+    cp.vel = st.vel.p;
+    cp.omg = st.omg.p;
+    cp.id = st.id.p;
+    cp.cell_reg = st.cell_reg.p;
+    cp.grid = c->grid;
+    cp.n = n0;
+    for (int d = 0; d < 2; ++d)
+      {
+        cp.send_rec[d] = m->send_rec[d].p;
+        cp.send_id[d] = m->send_id[d].p;
+      }
+    cp.send_count = m->counters.p;
+    cp.send_cap = cap;
+    launch_classify(cp, s);
+    uint32_t hc[4] = {0, 0, 0, 0};
+    CU_TRY(cudaMemcpyAsync(hc, m->counters.p, 16, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (hc[0] > cap || hc[1] > cap)
+      throw std::runtime_error("migration buffer overflow: more than 1/8 of the slab left in one rebuild");
+    if (hc[2])
+      fprintf(stderr, "[lethe_dem] rank %d: %u particles jumped over a whole slab and were dropped\n", m->rank, hc[2]);
+    uint32_t n_send[2] = {m->peer[0] >= 0 ? hc[0] : 0, m->peer[1] >= 0 ? hc[1] : 0};
+    uint32_t n_recv[2] = {0, 0};
+    exchange_counts(c, m, n_send, n_recv);
+    for (int d = 0; d < 2; ++d)
+      {
+        m->recv_rec[d].ensure(std::max<uint32_t>(n_recv[d], 1));
+        m->recv_id[d].ensure(std::max<uint32_t>(n_recv[d], 1));
+      }
+    NCCL_TRY(g_nccl.GroupStart());
+    for_each_direction_pair(m, [&](int ds, int dr) {
+      if (m->peer[ds] >= 0 && n_send[ds])
+        {
+          NCCL_TRY(g_nccl.Send(m->send_rec[ds].p, size_t(n_send[ds]) * sizeof(MigrateRecord), ncclUint8, m->peer[ds], m->comm, s));
+          NCCL_TRY(g_nccl.Send(m->send_id[ds].p, n_send[ds], ncclUint32, m->peer[ds], m->comm, s));
+        }
+      if (m->peer[dr] >= 0 && n_recv[dr])
+        {
+          NCCL_TRY(g_nccl.Recv(m->recv_rec[dr].p, size_t(n_recv[dr]) * sizeof(MigrateRecord), ncclUint8, m->peer[dr], m->comm, s));
+          NCCL_TRY(g_nccl.Recv(m->recv_id[dr].p, n_recv[dr], ncclUint32, m->peer[dr], m->comm, s));
+        }
+    });
+    NCCL_TRY(g_nccl.GroupEnd());
+    const uint32_t n_in = n_recv[0] + n_recv[1];
+    if (n_in)
+      {
+        const size_t total = size_t(n0) + n_in;
+        c->st[c->cur].ensure(total, n0, s);
+        c->st[c->cur ^ 1].ensure(total, 0, s);
+        c->disp.ensure(total, n0, s);
+        uint32_t base = n0;
+        for (int d = 0; d < 2; ++d)
+          if (n_recv[d])
+            {
+              launch_append_records(m->recv_rec[d].p, m->recv_id[d].p, n_recv[d], c->st[c->cur].view(), c->st[c->cur].id.p,
+                                    c->st[c->cur].cell_reg.p, c->disp.p, base, s);
+              base += n_recv[d];
+            }
+        c->n_owned = uint32_t(total);
+      }
+
+    // ---- 2. local sort (drops the particles sent away) ----
+    engine_rebuild_sort(c);
+
+    // ---- 3. ghost exchange: my boundary cell layers -> neighbours ----
+    const uint32_t n = c->n_owned;
+    StateBufs &sn = c->st[c->cur];
+    m->flags.ensure(size_t(n) + 2);
+    m->offsets.ensure(size_t(n) + 2);
+    c->scan_tmp.ensure(scan_tmp_elems(size_t(n) + 8));
+    const int layer[2] = {c->grid.slab_lo, c->grid.slab_hi - 1};
+    for (int d = 0; d < 2; ++d)
+      {
+        m->n_send[d] = 0;
+        if (m->peer[d] < 0)
+          continue;
+        launch_flag_layer(sn.cell_reg.p, c->grid, layer[d], n, m->flags.p, s);
+        exclusive_scan_u32(m->flags.p, m->offsets.p, size_t(n) + 1, c->scan_tmp.p, s);
+        uint32_t cnt = 0;
+        CU_TRY(cudaMemcpyAsync(&cnt, m->offsets.p + n, 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        m->n_send[d] = cnt;
+        m->send_idx[d].ensure(std::max<uint32_t>(cnt, 1));
+        m->send_ids[d].ensure(std::max<uint32_t>(cnt, 1));
+        m->send_pos[d].ensure(std::max<uint32_t>(cnt, 1));
+        m->send_vel[d].ensure(std::max<uint32_t>(cnt, 1));
+        m->send_omg[d].ensure(std::max<uint32_t>(cnt, 1));
+        launch_compact_indices(m->flags.p, m->offsets.p, n, m->send_idx[d].p, s);
+        launch_gather_ids(sn.id.p, m->send_idx[d].p, cnt, m->send_ids[d].p, s);
+      }
+    uint32_t g_recv[2] = {0, 0};
+    exchange_counts(c, m, m->n_send, g_recv);
+    c->n_ghost_run[0] = g_recv[0];
+    c->n_ghost_run[1] = g_recv[1];
+    c->n_ghost = g_recv[0] + g_recv[1];
+    const size_t total = size_t(n) + c->n_ghost;
+    c->st[c->cur].ensure(total, n, s);
+    c->st[c->cur ^ 1].ensure(total, n, s);
+    c->old_of_new.ensure(std::max<size_t>(total, 1), n, s);
+    // ids of the ghosts
+    NCCL_TRY(g_nccl.GroupStart());
+    for_each_direction_pair(m, [&](int ds, int dr) {
+      if (m->peer[ds] >= 0 && m->n_send[ds])
+        NCCL_TRY(g_nccl.Send(m->send_ids[ds].p, m->n_send[ds], ncclUint32, m->peer[ds], m->comm, s));
+      if (m->peer[dr] >= 0 && g_recv[dr])
+        NCCL_TRY(g_nccl.Recv(c->st[c->cur].id.p + n + (dr == 1 ? g_recv[0] : 0), g_recv[dr], ncclUint32, m->peer[dr], m->comm, s));
+    });
+    NCCL_TRY(g_nccl.GroupEnd());
+    refresh_ghosts(c); // positions / velocities of the new ghost set
+
+    // ---- 4. ghost cell tables + history source ----
+    const size_t n_cells = size_t(c->grid.n_cells);
+    StateBufs &sg = c->st[c->cur];
+    // ghost ids must be addressable in the id map
+    for (int d = 0; d < 2; ++d)
+      {
+        if (!g_recv[d])
+          continue;
+        c->ghost_start[d].ensure(n_cells + 1);
+        c->ghost_end[d].ensure(n_cells + 1);
+        CU_TRY(cudaMemsetAsync(c->ghost_start[d].p, 0, (n_cells + 1) * 4, s));
+        CU_TRY(cudaMemsetAsync(c->ghost_end[d].p, 0, (n_cells + 1) * 4, s));
+        GhostRunParams gp;
+        const uint32_t base = n + (d == 1 ? g_recv[0] : 0);
+        gp.pos = sg.pos.p + base;
+        gp.grid = c->grid;
+        gp.cell_rank = c->cell_rank.p;
+        gp.base = base;
+        gp.n = g_recv[d];
+        gp.cell_reg = sg.cell_reg.p;
+        gp.start = c->ghost_start[d].p;
+        gp.end = c->ghost_end[d].p;
+        gp.id = sg.id.p;
+        gp.old_slot_of_id = c->slot_map_size_old ? c->slot_of_id_old.p : nullptr;
+        gp.old_map_size = c->slot_map_size_old;
+        gp.old_n_owned = c->old_n_owned;
+        gp.old_of_new = c->old_of_new.p;
+        launch_ghost_run(gp, s);
+      }
+    if (c->n_ghost)
+      launch_register_ids(sg.id.p, n, c->n_ghost, c->slot_of_id.p, c->slot_map_size, s);
+
+    // ---- 5. lists ----
+    engine_rebuild_lists(c);
+    engine_mirror_ids(c);
+    if (c->timers_enabled)
+      {
+        CU_TRY(cudaEventRecord(ev1, s));
+        c->pending_rebuild.emplace_back(ev0, ev1);
+        ++c->rebuild_launches;
+      }
+  }
+
+  // update_ghost_particles: my boundary particles' state goes straight into the neighbours'
+  // ghost runs (three arrays, no unpack kernel on the receiving side).
+  void MultiGpu::refresh_ghosts(lethe_dem_ctx *c)
+  {
+    MultiGpuImpl *m = impl;
+    cudaStream_t s = c->stream;
+    StateBufs &st = c->st[c->cur];
+    const uint32_t n = c->n_owned;
+    for (int d = 0; d < 2; ++d)
+      if (m->peer[d] >= 0 && m->n_send[d])
+        launch_gather_state(st.view(), m->send_idx[d].p, m->n_send[d], m->send_pos[d].p, m->send_vel[d].p, m->send_omg[d].p, s);
+    NCCL_TRY(g_nccl.GroupStart());
+    for_each_direction_pair(m, [&](int ds, int dr) {
+      if (m->peer[ds] >= 0 && m->n_send[ds])
+        {
+          const size_t cnt = size_t(m->n_send[ds]) * 4;
+          NCCL_TRY(g_nccl.Send(m->send_pos[ds].p, cnt, ncclDouble, m->peer[ds], m->comm, s));
+          NCCL_TRY(g_nccl.Send(m->send_vel[ds].p, cnt, ncclDouble, m->peer[ds], m->comm, s));
+          NCCL_TRY(g_nccl.Send(m->send_omg[ds].p, cnt, ncclDouble, m->peer[ds], m->comm, s));
+        }
+      if (m->peer[dr] >= 0 && c->n_ghost_run[dr])
+        {
+          const size_t base = size_t(n) + (dr == 1 ? c->n_ghost_run[0] : 0);
+          const size_t cnt = size_t(c->n_ghost_run[dr]) * 4;
+          NCCL_TRY(g_nccl.Recv(st.pos.p + base, cnt, ncclDouble, m->peer[dr], m->comm, s));
+          NCCL_TRY(g_nccl.Recv(st.vel.p + base, cnt, ncclDouble, m->peer[dr], m->comm, s));
+          NCCL_TRY(g_nccl.Recv(st.omg.p + base, cnt, ncclDouble, m->peer[dr], m->comm, s));
+        }
+    });
+    NCCL_TRY(g_nccl.GroupEnd());
+  }
 } // namespace dem

@@ -18,6 +18,14 @@ namespace dem
     void rebuild_with_exchange(lethe_dem_ctx *c);
     // non-rebuild step: refresh the state of the ghost copies (update_ghost_particles)
     void refresh_ghosts(lethe_dem_ctx *c);
+    // logical_or over ranks of the displacement flag written by the last step kernel
+    bool any_rank_flag(lethe_dem_ctx *c);
+    // logical_or over ranks of a host-side decision
+    bool agree(lethe_dem_ctx *c, bool local);
   };
   void engine_rebuild_local(lethe_dem_ctx *c);
+  void engine_upload_walls(lethe_dem_ctx *c);
+  void engine_rebuild_sort(lethe_dem_ctx *c);
+  void engine_rebuild_lists(lethe_dem_ctx *c);
+  void engine_mirror_ids(lethe_dem_ctx *c);
 } // namespace dem

@@ -1,0 +1,75 @@
+"""Host-side logic of the slab decomposition (no GPU): partition properties and a
+world_size-2 gloo run of the ownership / bootstrap plumbing."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from lethe_b200 import multi, workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_bounds_cover_axis():
+    for n, w in [(16, 2), (17, 4), (650, 8), (16, 8)]:
+        b = multi.slab_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[r][1] == b[r + 1][0] for r in range(w - 1))
+        assert all(hi - lo >= 2 for lo, hi in b)
+    with pytest.raises(Exception):
+        multi.slab_bounds(7, 4)
+
+
+def test_balanced_bounds_and_ownership_partition():
+    w = workloads.drum(n_target=20000, radius=0.03)
+    mesh = w.params.mesh
+    ca = np.floor((w.x[:, 0] - mesh.lo[0]) / mesh.cell_size[0]).astype(np.int64)
+    for world in (2, 3, 8):
+        b = multi.balanced_slab_bounds(ca, mesh.n[0], world)
+        masks = [multi.owner_mask(w.x, mesh, 0, lo, hi) for lo, hi in b]
+        total = np.sum(masks, axis=0)
+        assert np.all(total == 1)  # every particle has exactly one owner
+        counts = [int(m.sum()) for m in masks]
+        assert max(counts) < 1.3 * w.n / world
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_gloo_world2_ownership_and_id_broadcast(tmp_path):
+    script = tmp_path / "w2.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch.distributed as dist
+        from lethe_b200 import multi, workloads
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        w = workloads.periodic_box(cells=(8, 4, 4))
+        mesh = w.params.mesh
+        lo, hi = multi.slab_bounds(mesh.n[0], world)[rank]
+        mask = multi.owner_mask(w.x, mesh, 0, lo, hi)
+        obj = [os.urandom(128) if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)   # the NCCL unique id travels the same way
+        counts = [None] * world
+        dist.all_gather_object(counts, (int(mask.sum()), obj[0][:8].hex(), lo, hi))
+        if rank == 0:
+            assert sum(c[0] for c in counts) == w.n, counts
+            assert counts[0][1] == counts[1][1]
+            assert counts[0][3] == counts[1][2]
+            print("GLOO_OK")
+        dist.destroy_process_group()
+    """))
+    port = _free_port()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
+    assert "GLOO_OK" in out.stdout, out.stdout + out.stderr
