@@ -78,10 +78,10 @@ namespace dem
   {
     DevBuf<uint32_t> row_start, col;
     DevBuf<double> hist, roll;
-    DevBuf<uint8_t> img;
+    DevBuf<uint8_t> img, rowl;
     uint32_t n_rows = 0;
     uint64_t n_entries = 0;
-    dem::ListView view() { return dem::ListView{row_start.p, col.p, hist.p, roll.p, img.p}; }
+    dem::ListView view() { return dem::ListView{row_start.p, col.p, hist.p, roll.p, img.p, rowl.p}; }
   };
   struct WallListBufs
   {

@@ -341,6 +341,7 @@ namespace
     const uint32_t n_entries = n_new ? read_u32(c, newl.row_start.p + n_new) : 0;
     newl.col.ensure(std::max<size_t>(n_entries, 1));
     newl.hist.ensure(std::max<size_t>(3 * size_t(n_entries), 1));
+    newl.rowl.ensure(std::max<size_t>(n_entries, 1));
     if (use_roll)
       newl.roll.ensure(std::max<size_t>(3 * size_t(n_entries), 1));
     if (use_img)

@@ -365,6 +365,7 @@ namespace dem
               }
           }
         P.new_list.col[e] = word;
+        P.new_list.rowl[e] = uint8_t(q & 31u);
         if (P.use_img)
           P.new_list.img[e] = uint8_t(img);
         ++e;

@@ -17,6 +17,8 @@
 //                                 copy; the arithmetic is exactly antisymmetric so the copies stay
 //                                 bit-wise negatives of each other.
 //   img[e]                        periodic image code of the neighbour (0 = none), periodic runs only
+//   rowl[e]                       row(e) mod 32: lets the step kernel sweep the entries of 32 rows as one
+//                                 flat, coalesced range without searching row_start
 //
 // pos/vel/omg are double-buffered: the fused step kernel reads generation g and writes g^1,
 // so no thread ever sees a half-updated neighbour and one launch does forces + integration.
@@ -87,6 +89,7 @@ namespace dem
     double *hist; // [E][3]
     double *roll; // [E][3] (EPSD only, else nullptr)
     uint8_t *img; // periodic only, else nullptr
+    uint8_t *rowl; // [E] row of the entry modulo 32 (= lane of the step kernel's warp that owns it)
   };
 
   struct WallListView

@@ -142,10 +142,13 @@ namespace dem
   // update_contact_information (…contact_force.h:223-298)
   __device__ __forceinline__ void pp_update_contact_information(vec3 &tangential_displacement, vec3 &vt, double &vn, vec3 &n,
                                                                 const ParticleView &p1, const ParticleView &p2, vec3 x2,
-                                                                double dt)
+                                                                double distance, double dt)
   {
+    // `distance` = sqrt(dist2(p1.x, x2)) from the caller is bit-identical to norm(x2 - p1.x):
+    // the component differences are exact negatives, their squares and the component-ordered
+    // sum are the same, so the second square root is not taken.
     const vec3 contact_vector = x2 - p1.x;
-    n = contact_vector / norm(contact_vector);
+    n = contact_vector / distance;
     vec3 vrel = p1.v - p2.v;
     vrel = vrel + cross(0.5 * (p1.d * p1.w + p2.d * p2.w), n);
     vn = dot(vrel, n);

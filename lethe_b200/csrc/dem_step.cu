@@ -2,10 +2,20 @@
 // list (with in-place tangential-history update), particle-wall forces, velocity-Verlet
 // integration and the displacement trigger, ONE launch per time step.
 //
-// One thread owns one particle i and walks row i of the FULL contact list, so the force
-// and torque on i are reduced in registers in list order (a per-particle segment
-// reduction: no atomics, deterministic) and the integrator runs in the same thread right
-// after. Neighbours are read from state generation g, results go to g^1.
+// Work decomposition (v2, warp-cooperative):
+//   * a warp owns 32 consecutive particles (= 32 consecutive rows of the FULL contact list,
+//     a contiguous range [E0,E1) of list entries);
+//   * phase A, entry-parallel: the 32 lanes sweep [E0,E1) 32 entries at a time with coalesced
+//     loads of col[], test "in contact?" with a sqrt-free two-sided bound (exact fall-back in
+//     the 1e-12 band around the threshold) and append the touching entries, by ballot +
+//     prefix popcount, to a small circular queue in shared memory;
+//   * phase B, whenever >= 32 touching entries are queued: one touching pair per lane, all 32
+//     lanes converged on the full Hertz-Mindlin evaluation (no lane idles on a non-touching
+//     entry); the per-pair force/torque lands in shared memory and the owner lanes add their
+//     pairs up in list order — a per-particle segment reduction, no atomics, deterministic
+//     and bit-identical to the serial row walk;
+//   * walls, integrator and the displacement trigger run per owner lane afterwards.
+// Neighbours are read from state generation g, results go to g^1.
 //
 // Reference path replaced (one iteration of source/dem/dem.cc:1134-1183):
 //   calculate_particle_particle_contact / execute_contact_calculation
@@ -20,6 +30,12 @@ namespace dem
 {
   namespace
   {
+    constexpr int STEP_WARPS = 4; // warps per block
+    constexpr int QUEUE = 512;    // touching entries a warp can queue before it has to drain (>= 32 * SWEEP)
+    constexpr int RES_SLOTS = 64;  // evaluated pairs buffered per warp before the owners add them up (2 rounds)
+    constexpr int SWEEP = 4;      // 32-entry blocks of the list swept per phase-A iteration (loads in flight)
+    constexpr int STEP_MIN_BLOCKS = 4; // resident blocks per SM the register allocation is held to
+
     __device__ __forceinline__ ParticleView make_view(double4 p, double4 v, double4 w)
     {
       ParticleView r;
@@ -46,129 +62,316 @@ namespace dem
       i_am_two = first > 0;
     }
 
-    template <int MODEL, int ROLLING, bool PERIODIC>
-    __global__ void __launch_bounds__(128) k_step(const __grid_constant__ StepParams P, const __grid_constant__ MaterialTables mt)
+    // Canonical positions of particle one / two of the pair (row particle, neighbour).
+    template <bool PERIODIC>
+    __device__ __forceinline__ void pair_positions(const StepParams &P, uint32_t e, const double4 &pme, const double4 &pj, vec3 &x1,
+                                                   vec3 &x2, double &dsum, bool &i_am_two)
     {
-      const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-      if (i >= P.n_owned)
-        return;
-      const double4 pi = P.in.pos[i], vi = P.in.vel[i], wi = P.in.omg[i];
-      const ParticleView me = make_view(pi, vi, wi);
-      vec3 F = v3(0, 0, 0), T = v3(0, 0, 0);
-      const double dt = P.dt;
-      unsigned int touching = 0;
-
-      // ---------------- particle-particle contacts ----------------
-      const uint32_t e0 = P.list.row_start[i], e1 = P.list.row_start[i + 1];
-      for (uint32_t e = e0; e < e1; ++e)
+      i_am_two = false;
+      if constexpr (PERIODIC)
         {
-          const uint32_t c = P.list.col[e];
-          const uint32_t j = c & COL_INDEX_MASK;
-          const double4 pj = P.in.pos[j];
-          bool i_am_two = false;
-          vec3 shift = v3(0, 0, 0);
-          uint32_t img = 0;
-          if constexpr (PERIODIC)
+          const uint32_t img = P.list.img[e];
+          if (img)
             {
-              img = P.list.img[e];
-              if (img)
-                decode_image(img, P.L, shift, i_am_two);
-            }
-          // positions of canonical particle one / two
-          vec3 x1, x2;
-          double dsum;
-          if (PERIODIC && img)
-            {
+              vec3 shift;
+              decode_image(img, P.L, shift, i_am_two);
               if (!i_am_two)
                 {
-                  x1 = me.x;
+                  x1 = v3(pme.x, pme.y, pme.z);
                   x2 = v3(pj.x, pj.y, pj.z) + shift;
-                  dsum = me.d + pj.w;
+                  dsum = pme.w + pj.w;
                 }
               else
                 {
                   x1 = v3(pj.x, pj.y, pj.z);
-                  x2 = me.x + (-shift);
-                  dsum = pj.w + me.d;
+                  x2 = v3(pme.x, pme.y, pme.z) + (-shift);
+                  dsum = pj.w + pme.w;
                 }
-            }
-          else
-            {
-              x1 = me.x;
-              x2 = v3(pj.x, pj.y, pj.z);
-              dsum = me.d + pj.w;
-            }
-          const double distance = sqrt(dist2(x1, x2));
-          const double normal_overlap = 0.5 * dsum - distance;
-          if (normal_overlap > mt.pp_force_threshold)
-            {
-              const ParticleView other = make_view(pj, P.in.vel[j], P.in.omg[j]);
-              vec3 h = v3(0, 0, 0), rs = v3(0, 0, 0);
-              if (c & COL_HIST_BIT)
-                {
-                  const double *hp = P.list.hist + 3 * size_t(e);
-                  h = v3(hp[0], hp[1], hp[2]);
-                  if constexpr (ROLLING == LETHE_ROLLING_EPSD)
-                    {
-                      const double *rp = P.list.roll + 3 * size_t(e);
-                      rs = v3(rp[0], rp[1], rp[2]);
-                    }
-                }
-              PairResult r;
-              r.normal_force = r.tangential_force = r.torque_one = r.torque_two = r.rolling = v3(0, 0, 0);
-              vec3 n, vt;
-              double vn;
-              if (PERIODIC && i_am_two)
-                {
-                  // evaluate the pair in its canonical orientation (one = neighbour) so that both
-                  // owners of the pair run bit-identical arithmetic; my copy of the history is the
-                  // negative of the canonical one.
-                  ParticleView one = other, two = me;
-                  one.x = x1;
-                  h = -h;
-                  rs = -rs;
-                  pp_update_contact_information(h, vt, vn, n, one, two, x2, dt);
-                  pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, two, r);
-                  // apply_force_and_torque_on_local_particles, particle two (…force.h:565-569)
-                  const vec3 total_force = r.normal_force + r.tangential_force;
-                  F = F + total_force;
-                  T = T + (-r.torque_two - r.rolling);
-                  h = -h;
-                  rs = -rs;
-                }
-              else
-                {
-                  ParticleView one = me;
-                  one.x = x1;
-                  pp_update_contact_information(h, vt, vn, n, one, other, x2, dt);
-                  pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, other, r);
-                  // particle one (…force.h:561-567)
-                  const vec3 total_force = r.normal_force + r.tangential_force;
-                  F = F - total_force;
-                  T = T + (-r.torque_one + r.rolling);
-                }
-              double *hp = P.list.hist + 3 * size_t(e);
-              hp[0] = h.x;
-              hp[1] = h.y;
-              hp[2] = h.z;
-              if constexpr (ROLLING == LETHE_ROLLING_EPSD)
-                {
-                  double *rp = P.list.roll + 3 * size_t(e);
-                  rp[0] = rs.x;
-                  rp[1] = rs.y;
-                  rp[2] = rs.z;
-                }
-              if (!(c & COL_HIST_BIT))
-                P.list.col[e] = c | COL_HIST_BIT;
-              ++touching;
-            }
-          else if (c & COL_HIST_BIT)
-            {
-              // contact_info.tangential_displacement.clear() (…force.h:2057-2063): dropping the
-              // flag is the clear; the 24 B are not touched.
-              P.list.col[e] = j;
+              return;
             }
         }
+      x1 = v3(pme.x, pme.y, pme.z);
+      x2 = v3(pj.x, pj.y, pj.z);
+      dsum = pme.w + pj.w;
+    }
+
+    struct __align__(16) WarpScratch
+    {
+      double4 pos[32], vel[32], omg[32]; // state of the warp's own 32 particles
+      double2 res[RES_SLOTS][3];         // per evaluated pair: force (3) and torque (3) on the row particle
+      uint32_t q_e[QUEUE];               // queued touching entries: list position,
+      uint32_t q_c[QUEUE];               //   col word (neighbour index | history bit),
+      uint8_t q_owner[QUEUE];            //   row (lane) that owns it
+      uint8_t res_owner[RES_SLOTS];      // row that owns res[k] (non-decreasing in k)
+    };
+
+    __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+    template <int MODEL, int ROLLING, bool PERIODIC>
+    __global__ void __launch_bounds__(32 * STEP_WARPS, STEP_MIN_BLOCKS) k_step(const __grid_constant__ StepParams P, const __grid_constant__ MaterialTables mt)
+    {
+      __shared__ WarpScratch scratch[STEP_WARPS];
+      const uint32_t lane = threadIdx.x & 31u;
+      WarpScratch &S = scratch[threadIdx.x >> 5];
+      const uint32_t warp_base = (blockIdx.x * STEP_WARPS + (threadIdx.x >> 5)) * 32u;
+      if (warp_base >= P.n_owned)
+        return; // whole warp
+      const uint32_t n_rows = min(32u, P.n_owned - warp_base);
+      const uint32_t i = warp_base + lane;
+      const bool valid = lane < n_rows;
+      const double dt = P.dt;
+
+      // ---------------- stage the warp's own rows ----------------
+      const uint32_t E0 = P.list.row_start[warp_base], E1 = P.list.row_start[warp_base + n_rows];
+      if (valid)
+        {
+          S.pos[lane] = P.in.pos[i];
+          S.vel[lane] = P.in.vel[i];
+          S.omg[lane] = P.in.omg[i];
+        }
+      __syncwarp();
+
+      vec3 F = v3(0, 0, 0), T = v3(0, 0, 0);
+      unsigned int touching_count = 0;
+      uint32_t q_n = 0, n_res = 0; // warp-uniform
+
+      // Operands of a queued pair, pulled towards L1 one round before the pair is evaluated.
+      auto prefetch_item = [&](uint32_t slot) {
+        const uint32_t c = S.q_c[slot];
+        const uint32_t j = c & COL_INDEX_MASK;
+        prefetch_l1(&P.in.pos[j]);
+        prefetch_l1(&P.in.vel[j]);
+        prefetch_l1(&P.in.omg[j]);
+        if (c & COL_HIST_BIT)
+          {
+            const double *hp = P.list.hist + 3 * size_t(S.q_e[slot]);
+            prefetch_l1(hp);
+            prefetch_l1(hp + 2);
+            if constexpr (ROLLING == LETHE_ROLLING_EPSD)
+              {
+                const double *rp = P.list.roll + 3 * size_t(S.q_e[slot]);
+                prefetch_l1(rp);
+                prefetch_l1(rp + 2);
+              }
+          }
+      };
+
+      // phase B: evaluate the queued pairs [first, first + cnt), cnt <= 32, one per lane
+      auto process_round = [&](uint32_t first, uint32_t cnt) {
+        if (first + 32 + lane < q_n)
+          prefetch_item(first + 32 + lane);
+        if (lane < cnt)
+          {
+            const uint32_t slot = first + lane;
+            const uint32_t e = S.q_e[slot];
+            const uint32_t owner = S.q_owner[slot];
+            const uint32_t c = S.q_c[slot];
+            const uint32_t j = c & COL_INDEX_MASK;
+            const double4 pme = S.pos[owner];
+            const double4 pj = P.in.pos[j];
+            const ParticleView me = make_view(pme, S.vel[owner], S.omg[owner]);
+            const ParticleView other = make_view(pj, P.in.vel[j], P.in.omg[j]);
+            vec3 x1, x2;
+            double dsum;
+            bool i_am_two;
+            pair_positions<PERIODIC>(P, e, pme, pj, x1, x2, dsum, i_am_two);
+            const double distance = sqrt(dist2(x1, x2));
+            const double normal_overlap = 0.5 * dsum - distance;
+            vec3 h = v3(0, 0, 0), rs = v3(0, 0, 0);
+            double *hp = P.list.hist + 3 * size_t(e);
+            if (c & COL_HIST_BIT)
+              {
+                h = v3(hp[0], hp[1], hp[2]);
+                if constexpr (ROLLING == LETHE_ROLLING_EPSD)
+                  {
+                    const double *rp = P.list.roll + 3 * size_t(e);
+                    rs = v3(rp[0], rp[1], rp[2]);
+                  }
+              }
+            PairResult r;
+            r.normal_force = r.tangential_force = r.torque_one = r.torque_two = r.rolling = v3(0, 0, 0);
+            vec3 n, vt;
+            double vn;
+            vec3 fc, tc; // what the row particle receives: F -= fc, T += tc
+            if (PERIODIC && i_am_two)
+              {
+                // evaluate the pair in its canonical orientation (one = neighbour) so that both
+                // owners of the pair run bit-identical arithmetic; my copy of the history is the
+                // negative of the canonical one.
+                ParticleView one = other, two = me;
+                one.x = x1;
+                h = -h;
+                rs = -rs;
+                pp_update_contact_information(h, vt, vn, n, one, two, x2, distance, dt);
+                pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, two, r);
+                // apply_force_and_torque_on_local_particles, particle two (…force.h:565-569)
+                fc = -(r.normal_force + r.tangential_force);
+                tc = -r.torque_two - r.rolling;
+                h = -h;
+                rs = -rs;
+              }
+            else
+              {
+                ParticleView one = me;
+                one.x = x1;
+                pp_update_contact_information(h, vt, vn, n, one, other, x2, distance, dt);
+                pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, other, r);
+                // particle one (…force.h:561-567)
+                fc = r.normal_force + r.tangential_force;
+                tc = -r.torque_one + r.rolling;
+              }
+            hp[0] = h.x;
+            hp[1] = h.y;
+            hp[2] = h.z;
+            if constexpr (ROLLING == LETHE_ROLLING_EPSD)
+              {
+                double *rp = P.list.roll + 3 * size_t(e);
+                rp[0] = rs.x;
+                rp[1] = rs.y;
+                rp[2] = rs.z;
+              }
+            if (!(c & COL_HIST_BIT))
+              P.list.col[e] = c | COL_HIST_BIT;
+            S.res[n_res + lane][0] = make_double2(fc.x, fc.y);
+            S.res[n_res + lane][1] = make_double2(fc.z, tc.x);
+            S.res[n_res + lane][2] = make_double2(tc.y, tc.z);
+            S.res_owner[n_res + lane] = uint8_t(owner);
+          }
+        n_res += cnt;
+        __syncwarp();
+      };
+
+      // Owner lanes add up the buffered pair results. Queue order = list order, so res_owner is
+      // non-decreasing and every owner's pairs are one run [lo, hi) of the buffer, added in list
+      // order: the same sequence of additions as a serial walk of the row.
+      auto flush_results = [&]() {
+        uint32_t a0 = 0, a1 = n_res, b0 = 0, b1 = n_res;
+        while (a0 < a1 || b0 < b1)
+          {
+            if (a0 < a1)
+              {
+                const uint32_t mid = (a0 + a1) >> 1;
+                if (S.res_owner[mid] < lane)
+                  a0 = mid + 1;
+                else
+                  a1 = mid;
+              }
+            if (b0 < b1)
+              {
+                const uint32_t mid = (b0 + b1) >> 1;
+                if (S.res_owner[mid] <= lane)
+                  b0 = mid + 1;
+                else
+                  b1 = mid;
+              }
+          }
+        for (uint32_t k = a0; k < b0; ++k)
+          {
+            const double2 a = S.res[k][0], b = S.res[k][1], cc = S.res[k][2];
+            F = F - v3(a.x, a.y, b.x);
+            T = T + v3(b.y, cc.x, cc.y);
+          }
+        touching_count += b0 - a0;
+        n_res = 0;
+        __syncwarp();
+      };
+
+      // The warp alternates between (A) sweeping its list entries, which only queues the
+      // touching ones, until the range is exhausted (or, for very dense rows, the queue is
+      // full), and (B) draining the queue in rounds of 32 pairs. Keeping the two apart keeps
+      // the sweep a tight streaming loop with many loads in flight, and lets every round
+      // prefetch the operands of the next one.
+      uint32_t eb = E0;
+      while (eb < E1)
+        {
+          // ---------------- phase A ----------------
+          uint32_t c_nx[SWEEP], ow_nx[SWEEP];
+#pragma unroll
+          for (int u = 0; u < SWEEP; ++u)
+            {
+              const uint32_t e = eb + 32u * u + lane;
+              c_nx[u] = e < E1 ? P.list.col[e] : 0u;
+              ow_nx[u] = e < E1 ? P.list.rowl[e] : 0u;
+            }
+          while (eb < E1 && q_n + 32u * SWEEP <= QUEUE)
+            {
+              uint32_t c[SWEEP], ow[SWEEP];
+              double4 pj[SWEEP];
+#pragma unroll
+              for (int u = 0; u < SWEEP; ++u)
+                {
+                  c[u] = c_nx[u];
+                  ow[u] = ow_nx[u];
+                  const uint32_t e = eb + 32u * u + lane;
+                  if (e < E1)
+                    pj[u] = P.in.pos[c[u] & COL_INDEX_MASK];
+                }
+#pragma unroll
+              for (int u = 0; u < SWEEP; ++u)
+                {
+                  const uint32_t e = eb + 32u * (SWEEP + u) + lane;
+                  c_nx[u] = e < E1 ? P.list.col[e] : 0u;
+                  ow_nx[u] = e < E1 ? P.list.rowl[e] : 0u;
+                }
+#pragma unroll
+              for (int u = 0; u < SWEEP; ++u)
+                {
+                  const uint32_t e = eb + 32u * u + lane;
+                  bool touching = false;
+                  if (e < E1)
+                    {
+                      const double4 pme = S.pos[ow[u]];
+                      vec3 x1, x2;
+                      double dsum;
+                      bool i_am_two;
+                      pair_positions<PERIODIC>(P, e, pme, pj[u], x1, x2, dsum, i_am_two);
+                      const double d2 = dist2(x1, x2);
+                      // in contact  <=>  0.5*dsum - sqrt(d2) > threshold (…force.h:1868-1876). Decide
+                      // without the square root when d2 is clearly on one side of (0.5*dsum - thr)^2.
+                      const double hgap = 0.5 * dsum - mt.pp_force_threshold;
+                      const double hh = hgap * hgap;
+                      if (d2 < hh * (1.0 - 1e-12))
+                        touching = true;
+                      else if (d2 > hh * (1.0 + 1e-12))
+                        touching = false;
+                      else
+                        touching = (0.5 * dsum - sqrt(d2)) > mt.pp_force_threshold;
+                      // contact_info.tangential_displacement.clear() (…force.h:2057-2063): dropping
+                      // the flag is the clear; the 24 B are not touched.
+                      if (!touching && (c[u] & COL_HIST_BIT))
+                        P.list.col[e] = c[u] & COL_INDEX_MASK;
+                    }
+                  const uint32_t m = __ballot_sync(0xffffffffu, touching);
+                  if (touching)
+                    {
+                      const uint32_t slot = q_n + __popc(m & ((1u << lane) - 1u));
+                      S.q_e[slot] = e;
+                      S.q_c[slot] = c[u];
+                      S.q_owner[slot] = uint8_t(ow[u]);
+                    }
+                  q_n += __popc(m);
+                }
+              eb += 32u * SWEEP;
+            }
+          __syncwarp();
+          // ---------------- phase B ----------------
+          if (lane < q_n)
+            prefetch_item(lane);
+          for (uint32_t first = 0; first < q_n; first += 32)
+            {
+              process_round(first, min(32u, q_n - first));
+              if (n_res > RES_SLOTS - 32)
+                flush_results();
+            }
+          if (n_res)
+            flush_results();
+          q_n = 0;
+        }
+
+      if (!valid)
+        return;
+      const double4 pi = S.pos[lane], vi = S.vel[lane], wi = S.omg[lane];
+      const ParticleView me = make_view(pi, vi, wi);
 
       // ---------------- particle-wall contacts ----------------
       const uint32_t w0 = P.walls.row_start[i], w1 = P.walls.row_start[i + 1];
@@ -254,8 +457,8 @@ namespace dem
             P.walls.entry[w] = we & ~WALL_HIST_BIT;
         }
 
-      if (P.touching_counter && touching)
-        atomicAdd(P.touching_counter, (unsigned long long)touching);
+      if (P.touching_counter && touching_count)
+        atomicAdd(P.touching_counter, (unsigned long long)touching_count);
       if (P.force_out)
         {
           P.force_out[3 * size_t(i) + 0] = F.x;
@@ -322,7 +525,8 @@ namespace dem
     {
       if (p.n_owned == 0)
         return;
-      const dim3 block(128), grid((p.n_owned + 127) / 128);
+      constexpr uint32_t per_block = 32 * STEP_WARPS;
+      const dim3 block(per_block), grid((p.n_owned + per_block - 1) / per_block);
       if (p.periodic_any)
         k_step<MODEL, ROLLING, true><<<grid, block, 0, stream>>>(p, mt);
       else
