@@ -350,7 +350,8 @@ class Engine:
         self._call("comm_init", C.c_int(rank), C.c_int(world_size), buf)
 
 
-CUDA_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "liblethe_dem_b200.so")
+# LETHE_DEM_B200_LIB selects another build of the same CUDA library (kernel tuning experiments)
+CUDA_LIB = os.environ.get("LETHE_DEM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "liblethe_dem_b200.so")
 
 
 def load_library(path: str = CUDA_LIB) -> C.CDLL:

@@ -2,19 +2,23 @@
 // list (with in-place tangential-history update), particle-wall forces, velocity-Verlet
 // integration and the displacement trigger, ONE launch per time step.
 //
-// Work decomposition (v2, warp-cooperative):
+// Work decomposition (warp-cooperative):
 //   * a warp owns 32 consecutive particles (= 32 consecutive rows of the FULL contact list,
 //     a contiguous range [E0,E1) of list entries);
-//   * phase A, entry-parallel: the 32 lanes sweep [E0,E1) 32 entries at a time with coalesced
-//     loads of col[], test "in contact?" with a sqrt-free two-sided bound (exact fall-back in
-//     the 1e-12 band around the threshold) and append the touching entries, by ballot +
-//     prefix popcount, to a small circular queue in shared memory;
-//   * phase B, whenever >= 32 touching entries are queued: one touching pair per lane, all 32
-//     lanes converged on the full Hertz-Mindlin evaluation (no lane idles on a non-touching
-//     entry); the per-pair force/torque lands in shared memory and the owner lanes add their
-//     pairs up in list order — a per-particle segment reduction, no atomics, deterministic
-//     and bit-identical to the serial row walk;
+//   * phase A, entry-parallel: the 32 lanes sweep [E0,E1) SWEEP x 32 entries at a time with
+//     coalesced loads of col[]/rowl[] (software-pipelined one iteration ahead) and SWEEP
+//     position gathers in flight per lane, test "in contact?" with a sqrt-free two-sided bound
+//     (exact fall-back in the 1e-12 band around the threshold) and append the touching
+//     entries, by ballot + prefix popcount, to a queue in shared memory;
+//   * phase B, once the range is swept: rounds of 32 queued pairs, one per lane, all lanes
+//     converged on the full contact model (no lane idles on a non-touching entry); the
+//     per-pair force/torque lands in shared memory and every two rounds the owner lanes add
+//     their pairs up in list order — a per-particle segment reduction, no atomics,
+//     deterministic, the same sequence of additions as a serial walk of the row;
 //   * walls, integrator and the displacement trigger run per owner lane afterwards.
+// Measured dead ends (profiles/): prefetch.global.L1/L2 of the round operands,
+// cp.async staging of the next round, deeper sweep pipelines — the kernel is bound by the
+// issue latency of dependent FP64 chains at 16 warps/SM, not by exposed memory latency.
 // Neighbours are read from state generation g, results go to g^1.
 //
 // Reference path replaced (one iteration of source/dem/dem.cc:1134-1183):
@@ -33,8 +37,14 @@ namespace dem
     constexpr int STEP_WARPS = 4; // warps per block
     constexpr int QUEUE = 512;    // touching entries a warp can queue before it has to drain (>= 32 * SWEEP)
     constexpr int RES_SLOTS = 64;  // evaluated pairs buffered per warp before the owners add them up (2 rounds)
-    constexpr int SWEEP = 4;      // 32-entry blocks of the list swept per phase-A iteration (loads in flight)
-    constexpr int STEP_MIN_BLOCKS = 4; // resident blocks per SM the register allocation is held to
+#ifndef DEM_SWEEP
+#define DEM_SWEEP 4
+#endif
+#ifndef DEM_MIN_BLOCKS
+#define DEM_MIN_BLOCKS 4
+#endif
+    constexpr int SWEEP = DEM_SWEEP;      // 32-entry blocks of the list swept per phase-A iteration (loads in flight)
+    constexpr int STEP_MIN_BLOCKS = DEM_MIN_BLOCKS; // resident blocks per SM the register allocation is held to
 
     __device__ __forceinline__ ParticleView make_view(double4 p, double4 v, double4 w)
     {
@@ -103,9 +113,8 @@ namespace dem
       uint32_t q_c[QUEUE];               //   col word (neighbour index | history bit),
       uint8_t q_owner[QUEUE];            //   row (lane) that owns it
       uint8_t res_owner[RES_SLOTS];      // row that owns res[k] (non-decreasing in k)
+      uint8_t seg[32];                   // per owner: first buffer position of its run at the current flush
     };
-
-    __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
     template <int MODEL, int ROLLING, bool PERIODIC>
     __global__ void __launch_bounds__(32 * STEP_WARPS, STEP_MIN_BLOCKS) k_step(const __grid_constant__ StepParams P, const __grid_constant__ MaterialTables mt)
@@ -135,31 +144,8 @@ namespace dem
       unsigned int touching_count = 0;
       uint32_t q_n = 0, n_res = 0; // warp-uniform
 
-      // Operands of a queued pair, pulled towards L1 one round before the pair is evaluated.
-      auto prefetch_item = [&](uint32_t slot) {
-        const uint32_t c = S.q_c[slot];
-        const uint32_t j = c & COL_INDEX_MASK;
-        prefetch_l1(&P.in.pos[j]);
-        prefetch_l1(&P.in.vel[j]);
-        prefetch_l1(&P.in.omg[j]);
-        if (c & COL_HIST_BIT)
-          {
-            const double *hp = P.list.hist + 3 * size_t(S.q_e[slot]);
-            prefetch_l1(hp);
-            prefetch_l1(hp + 2);
-            if constexpr (ROLLING == LETHE_ROLLING_EPSD)
-              {
-                const double *rp = P.list.roll + 3 * size_t(S.q_e[slot]);
-                prefetch_l1(rp);
-                prefetch_l1(rp + 2);
-              }
-          }
-      };
-
       // phase B: evaluate the queued pairs [first, first + cnt), cnt <= 32, one per lane
       auto process_round = [&](uint32_t first, uint32_t cnt) {
-        if (first + 32 + lane < q_n)
-          prefetch_item(first + 32 + lane);
         if (lane < cnt)
           {
             const uint32_t slot = first + lane;
@@ -242,36 +228,40 @@ namespace dem
       };
 
       // Owner lanes add up the buffered pair results. Queue order = list order, so res_owner is
-      // non-decreasing and every owner's pairs are one run [lo, hi) of the buffer, added in list
-      // order: the same sequence of additions as a serial walk of the row.
+      // non-decreasing and every owner's pairs are one run of the buffer, added in list order:
+      // the same sequence of additions as a serial walk of the row.
       auto flush_results = [&]() {
-        uint32_t a0 = 0, a1 = n_res, b0 = 0, b1 = n_res;
-        while (a0 < a1 || b0 < b1)
+        static_assert(RES_SLOTS == 64, "the run search below looks at two buffer positions per lane");
+        // lanes inspect buffer positions lane and lane + 32; the first lane of every run (head)
+        // publishes the run's start for its owner, the ballots give every run's end
+        const uint32_t o0 = lane < n_res ? S.res_owner[lane] : 0xffu;
+        const uint32_t o1 = lane + 32 < n_res ? S.res_owner[lane + 32] : 0xffu;
+        const uint32_t p0 = __shfl_up_sync(0xffffffffu, o0, 1);
+        const uint32_t p1 = __shfl_up_sync(0xffffffffu, o1, 1);
+        const uint32_t last0 = __shfl_sync(0xffffffffu, o0, 31);
+        const bool head0 = lane < n_res && (lane == 0 || p0 != o0);
+        const bool head1 = lane + 32 < n_res && ((lane == 0 ? last0 : p1) != o1);
+        const uint64_t heads = (uint64_t(__ballot_sync(0xffffffffu, head1)) << 32) | __ballot_sync(0xffffffffu, head0);
+        const uint32_t present =
+          __reduce_or_sync(0xffffffffu, (lane < n_res ? (1u << o0) : 0u) | (lane + 32 < n_res ? (1u << o1) : 0u));
+        if (head0)
+          S.seg[o0] = uint8_t(lane);
+        if (head1)
+          S.seg[o1] = uint8_t(32 + lane);
+        __syncwarp();
+        if ((present >> lane) & 1u)
           {
-            if (a0 < a1)
+            const uint32_t s0 = S.seg[lane];
+            const uint64_t above = s0 >= 63 ? 0ull : (heads & (~0ull << (s0 + 1)));
+            const uint32_t end = above ? uint32_t(__ffsll((long long)above) - 1) : n_res;
+            for (uint32_t k = s0; k < end; ++k)
               {
-                const uint32_t mid = (a0 + a1) >> 1;
-                if (S.res_owner[mid] < lane)
-                  a0 = mid + 1;
-                else
-                  a1 = mid;
+                const double2 a = S.res[k][0], b = S.res[k][1], cc = S.res[k][2];
+                F = F - v3(a.x, a.y, b.x);
+                T = T + v3(b.y, cc.x, cc.y);
               }
-            if (b0 < b1)
-              {
-                const uint32_t mid = (b0 + b1) >> 1;
-                if (S.res_owner[mid] <= lane)
-                  b0 = mid + 1;
-                else
-                  b1 = mid;
-              }
+            touching_count += end - s0;
           }
-        for (uint32_t k = a0; k < b0; ++k)
-          {
-            const double2 a = S.res[k][0], b = S.res[k][1], cc = S.res[k][2];
-            F = F - v3(a.x, a.y, b.x);
-            T = T + v3(b.y, cc.x, cc.y);
-          }
-        touching_count += b0 - a0;
         n_res = 0;
         __syncwarp();
       };
@@ -279,8 +269,8 @@ namespace dem
       // The warp alternates between (A) sweeping its list entries, which only queues the
       // touching ones, until the range is exhausted (or, for very dense rows, the queue is
       // full), and (B) draining the queue in rounds of 32 pairs. Keeping the two apart keeps
-      // the sweep a tight streaming loop with many loads in flight, and lets every round
-      // prefetch the operands of the next one.
+      // the sweep a tight streaming loop with many loads in flight and the (large) pair
+      // evaluation a single instance in the instruction stream.
       uint32_t eb = E0;
       while (eb < E1)
         {
@@ -355,8 +345,6 @@ namespace dem
             }
           __syncwarp();
           // ---------------- phase B ----------------
-          if (lane < q_n)
-            prefetch_item(lane);
           for (uint32_t first = 0; first < q_n; first += 32)
             {
               process_round(first, min(32u, q_n - first));

@@ -1,0 +1,244 @@
+// dem_solver.cc — see dem_solver.h.
+#include "dem_solver.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+namespace lethe_b200
+{
+  std::vector<lethe_wall_face> box_wall_faces(const Mesh &mesh, const std::vector<unsigned> &outlets, const std::array<int, 3> &periodic)
+  {
+    static const double normals[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+    const Vec3 h = mesh.cell_size();
+    std::vector<lethe_wall_face> faces;
+    for (int k = 0; k < mesh.n[2]; ++k)
+      for (int j = 0; j < mesh.n[1]; ++j)
+        for (int i = 0; i < mesh.n[0]; ++i)
+          {
+            const int idx[3] = {i, j, k};
+            const int cell = i + mesh.n[0] * (j + mesh.n[1] * k);
+            for (int axis = 0; axis < 3; ++axis)
+              for (int side = 0; side < 2; ++side)
+                {
+                  if (idx[axis] != (side == 0 ? 0 : mesh.n[axis] - 1))
+                    continue;
+                  const int face_no = 2 * axis + side;
+                  // colorized hyper_cube / hyper_rectangle: boundary id = 2*axis + side
+                  const unsigned bid = mesh.colorize ? unsigned(face_no) : 0u;
+                  if (periodic[axis] || std::find(outlets.begin(), outlets.end(), bid) != outlets.end())
+                    continue;
+                  lethe_wall_face f{};
+                  f.cell = cell;
+                  f.boundary_id = bid;
+                  f.global_face_id = uint32_t(cell * 6 + face_no);
+                  for (int d = 0; d < 3; ++d)
+                    {
+                      f.normal[d] = normals[face_no][d];
+                      f.point[d] = mesh.lo[d] + (idx[d] + 0.5) * h[d];
+                    }
+                  f.point[axis] = side == 0 ? mesh.lo[axis] : mesh.hi[axis];
+                  faces.push_back(f);
+                }
+          }
+    return faces;
+  }
+
+  ParticleRows volume_insertion(const DEMParameters &p, long n_insert, uint32_t first_id, int particle_type)
+  {
+    const InsertionInfo &ins = p.insertion;
+    const ParticleType &t = p.particle_types.at(particle_type);
+    if (t.size_distribution_type != "uniform")
+      throw std::runtime_error("volume insertion on the host supports the uniform size distribution only");
+    const double d_max = p.maximum_particle_diameter();
+    long n_dir[3] = {0, 0, 0};
+    for (int axis : ins.direction_sequence)
+      n_dir[axis] = long((ins.box_point_2[axis] - ins.box_point_1[axis]) / (ins.distance_threshold * d_max));
+    const long n_sites = n_dir[0] * n_dir[1] * n_dir[2];
+    n_insert = std::min(n_insert, n_sites);
+    // one srand(seed * (i + 1)) + rand() per site
+    std::vector<double> rnd(n_sites);
+    for (long i = 0; i < n_sites; ++i)
+      {
+        srand(unsigned(ins.prn_seed * (i + 1)));
+        rnd[i] = (double(rand()) / double(RAND_MAX)) * ins.maximum_offset;
+      }
+    const int a0 = ins.direction_sequence[0], a1 = ins.direction_sequence[1], a2 = ins.direction_sequence[2];
+    ParticleRows rows;
+    rows.id.resize(n_insert);
+    rows.x.resize(3 * n_insert);
+    rows.props.assign(size_t(LETHE_DEM_N_PROPERTIES) * n_insert, 0.0);
+    const double d = std::fabs(t.average_diameter), half = d * 0.5;
+    for (long k = 0; k < n_insert; ++k)
+      {
+        const double r1 = rnd[k], r2 = rnd[n_sites - k - 1];
+        const long i0 = k % n_dir[a0], i1 = (k % (n_dir[a0] * n_dir[a1])) / n_dir[a0], i2 = k / (n_dir[a0] * n_dir[a1]);
+        rows.x[3 * k + a0] = ins.box_point_1[a0] + ((i0 + 0.5) * ins.distance_threshold - r1) * d_max;
+        rows.x[3 * k + a1] = ins.box_point_1[a1] + ((i1 + 0.5) * ins.distance_threshold - r2) * d_max;
+        rows.x[3 * k + a2] = ins.box_point_1[a2] + ((i2 + 0.5) * ins.distance_threshold - r1) * d_max;
+        double *pr = &rows.props[size_t(LETHE_DEM_N_PROPERTIES) * k];
+        pr[0] = particle_type;
+        pr[1] = d;
+        pr[2] = t.density * 4.0 / 3.0 * M_PI * (half * half * half);
+        for (int c = 0; c < 3; ++c)
+          {
+            pr[3 + c] = ins.initial_velocity[c];
+            pr[6 + c] = ins.initial_omega[c];
+          }
+        rows.id[k] = first_id + uint32_t(k);
+      }
+    return rows;
+  }
+
+  DEMSolverB200::DEMSolverB200(const DEMParameters &prm, int device, std::ostream &log)
+    : parameters(prm)
+    , pcout(log)
+  {
+    const lethe_dem_config config = parameters.to_config();
+    engine = std::make_unique<DEMEngine>(config, device);
+    for (const auto &t : parameters.particle_types)
+      remaining_particles.push_back(t.number_of_particles);
+    setup_boundaries();
+  }
+
+  void DEMSolverB200::setup_boundaries()
+  {
+    if (parameters.mesh.expand_particle_wall_contact_search)
+      throw std::runtime_error("`expand particle-wall contact search` is not on the B200 path (box meshes do not need it)");
+    engine->set_walls(box_wall_faces(parameters.mesh, parameters.outlet_boundaries(), parameters.periodic_directions()));
+    if (!parameters.floating_walls.empty())
+      {
+        std::vector<double> pts, nrm, t0, t1;
+        for (const auto &w : parameters.floating_walls)
+          {
+            pts.insert(pts.end(), w.point.begin(), w.point.end());
+            nrm.insert(nrm.end(), w.normal.begin(), w.normal.end());
+            t0.push_back(w.time_start);
+            t1.push_back(w.time_end);
+          }
+        engine->set_floating_walls(pts, nrm, t0, t1);
+      }
+    const double zero[3] = {0, 0, 0};
+    for (const auto &bc : parameters.boundary_conditions)
+      {
+        if (bc.type == "rotational")
+          engine->set_boundary_motion(bc.boundary_id, zero, bc.rotational_speed, bc.rotational_vector.data(),
+                                      bc.point_on_rotational_vector.data());
+        else if (bc.type == "translational")
+          engine->set_boundary_motion(bc.boundary_id, bc.translational_velocity.data(), 0.0, zero, zero);
+      }
+  }
+
+  bool DEMSolverB200::insertion_due() const
+  {
+    const long f = parameters.insertion.frequency;
+    if (f == 0)
+      return false;
+    return (iteration_number % f) == 1 || iteration_number == 1;
+  }
+
+  void DEMSolverB200::insert_particles()
+  {
+    const int last = int(parameters.particle_types.size()) - 1;
+    if (remaining_particles[current_inserting_type] == 0 && current_inserting_type != last)
+      ++current_inserting_type;
+    const long remaining = remaining_particles[current_inserting_type];
+    if (remaining == 0)
+      return;
+    const long n = std::min(parameters.insertion.inserted_this_step, remaining);
+    const ParticleRows rows = volume_insertion(parameters, n, next_id, current_inserting_type);
+    engine->add_particles(rows); // triggers the contact search (DEMActionManager::particle_insertion_step)
+    next_id += uint32_t(rows.size());
+    remaining_particles[current_inserting_type] -= long(rows.size());
+  }
+
+  bool DEMSolverB200::is_at_end() const
+  {
+    // simulation_control.cc:371-378
+    const double margin = std::max(1e-6 * parameters.time_step, 1e-12 * parameters.time_end);
+    return current_time >= (parameters.time_end - margin);
+  }
+
+  void DEMSolverB200::print_progression()
+  {
+    std::stringstream ss;
+    ss << "Transient iteration: " << std::setw(8) << std::left << iteration_number << " Time: " << std::setw(8) << std::left
+       << current_time << " Time step: " << std::setw(8) << std::left << parameters.time_step;
+    const std::string line(ss.str().size() + 1, '*');
+    pcout << '\n' << line << '\n' << ss.str() << '\n' << line << '\n';
+  }
+
+  void DEMSolverB200::report_statistics()
+  {
+    const lethe_dem_stats s = engine->stats();
+    const double built = double(s.n_rebuilds) - list_total;
+    list_max = std::max(built, list_max);
+    list_min = std::min(built, list_min);
+    list_total += built;
+    const double list_avg = list_total / double(std::max<unsigned long>(iteration_number, 1)) * double(parameters.log_frequency);
+    const double n = double(std::max<uint64_t>(s.n_particles, 1));
+    auto row = [&](const char *name, double mn, double mx, double avg, double tot) {
+      pcout << "| " << std::setw(30) << std::left << name << "| " << std::scientific << std::setprecision(6) << mn << " | " << mx
+            << " | " << avg << " | " << tot << " |\n";
+    };
+    pcout << "| " << std::setw(30) << std::left << "Variable"
+          << "| Min          | Max          | Average      | Total        |\n";
+    row("Contact list generation", list_min, list_max, list_avg, list_total);
+    row("Velocity magnitude", s.v_min, s.v_max, s.v_sum / n, s.v_sum);
+    row("Angular velocity magnitude", s.omega_min, s.omega_max, s.omega_sum / n, s.omega_sum);
+    row("Translational kinetic energy", s.ke_trans_min, s.ke_trans_max, s.ke_trans_sum / n, s.ke_trans_sum);
+    row("Rotational kinetic energy", s.ke_rot_min, s.ke_rot_max, s.ke_rot_sum / n, s.ke_rot_sum);
+    pcout << std::defaultfloat;
+  }
+
+  void DEMSolverB200::solve()
+  {
+    // Steps between two host-visible events (insertion, log line) are handed to the engine
+    // in one call: the C ABI runs them back to back without returning to the host.
+    uint64_t pending = 0;
+    auto flush = [&] {
+      if (pending)
+        engine->step(pending);
+      pending = 0;
+    };
+    while (!is_at_end())
+      {
+        ++iteration_number;
+        current_time += parameters.time_step;
+        if (is_verbose_iteration())
+          {
+            flush();
+            print_progression();
+            report_statistics();
+          }
+        bool any_left = false;
+        for (long r : remaining_particles)
+          any_left = any_left || r > 0;
+        if (insertion_due() && any_left)
+          {
+            flush(); // the insertion belongs to this iteration: run the earlier ones first
+            insert_particles();
+          }
+        ++pending;
+      }
+    flush();
+    // closing half kick of the velocity-Verlet scheme (dem.cc:1249-1259)
+    engine->synchronize_velocities();
+  }
+
+  void DEMSolverB200::print_xyz(std::ostream &out)
+  {
+    const ParticleRows r = engine->get_particles(); // sorted by id
+    out << "id, type, dp, x, y, z \n";
+    for (size_t k = 0; k < r.size(); ++k)
+      {
+        const double *p = &r.props[size_t(LETHE_DEM_N_PROPERTIES) * k];
+        out << r.id[k] << " " << int(p[0]) << " " << std::fixed << std::setprecision(5) << p[1] << " " << std::setprecision(4)
+            << r.x[3 * k] << " " << r.x[3 * k + 1] << " " << r.x[3 * k + 2] << "\n";
+      }
+    out << std::defaultfloat;
+  }
+} // namespace lethe_b200

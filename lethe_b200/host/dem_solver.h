@@ -1,0 +1,60 @@
+// dem_solver.h — host-side mirror of `DEMSolver<3, DEM::DEMProperties::PropertiesIndex>`
+// (include/dem/dem.h, source/dem/dem.cc) with the per-step work behind the C ABI.
+//
+// What stays on the host is what the reference keeps on the host too: parameter set-up,
+// the wall table (BoundaryCellsInformation for box meshes), insertion, the time loop's
+// bookkeeping (when to insert, log, stop) and the `test` output. One iteration of
+// `while (simulation_control->integrate())` — contact detection + search, pp/pw forces,
+// integration, trigger reset (dem.cc:1115-1246) — is `DEMEngine::step`.
+#pragma once
+
+#include <iosfwd>
+#include <memory>
+
+#include "dem_engine.h"
+#include "dem_parameters.h"
+
+namespace lethe_b200
+{
+  // BoundaryCellsInformation::find_boundary_cells_information for a uniform box mesh
+  // (find_boundary_cells_information.cc:130-219): one row per (boundary cell, boundary face)
+  // that is neither an outlet nor periodic; inward normal, face centre as the point.
+  std::vector<lethe_wall_face> box_wall_faces(const Mesh &mesh, const std::vector<unsigned> &outlet_boundaries,
+                                              const std::array<int, 3> &periodic);
+
+  // InsertionVolume::insert + assign_particle_properties on one rank, uniform diameters
+  // (insertion_volume.cc:43-206, insertion.cc:60-121); jitter from glibc rand() exactly as
+  // create_random_number_container does (include/core/utilities.h:1061-1073).
+  ParticleRows volume_insertion(const DEMParameters &p, long n_insert, uint32_t first_id, int particle_type);
+
+  class DEMSolverB200
+  {
+  public:
+    DEMSolverB200(const DEMParameters &parameters, int device, std::ostream &log);
+    // DEMSolver::solve (dem.cc:1064-1267)
+    void solve();
+    // finish_simulation with `subsection test / set enable = true`: print_xyz (dem.cc:760-770)
+    void print_xyz(std::ostream &out);
+    DEMEngine &get_engine() { return *engine; }
+
+  private:
+    void setup_boundaries();     // setup_functions_and_pointers + boundary_cell_object.build
+    bool insertion_due() const;  // insert_particles (dem.cc:484-506)
+    void insert_particles();
+    bool is_at_end() const;      // SimulationControlTransient::is_at_end
+    bool is_verbose_iteration() const { return (iteration_number % parameters.log_frequency) == 0; }
+    void print_progression();    // SimulationControlTransientDEM::print_progression
+    void report_statistics();    // dem.cc:902-971
+
+    DEMParameters parameters;
+    std::unique_ptr<DEMEngine> engine;
+    std::ostream &pcout;
+    unsigned long iteration_number = 0;
+    double current_time = 0;
+    std::vector<long> remaining_particles; // per type
+    int current_inserting_type = 0;
+    uint32_t next_id = 0;
+    // contact_list statistics of report_statistics
+    double list_min = 1e300, list_max = 0, list_total = 0;
+  };
+} // namespace lethe_b200

@@ -1,0 +1,95 @@
+"""The C++ host side (lethe_b200/host): `.prm` reader, DEMSolver mirror, lethe-particles-b200.
+
+CPU part: the product binary's --dump-config must agree with the Python mirror's
+to_config() for the reference's own parameter file, and the same host sources, compiled
+here against the CPU oracle's identically-shaped ABI (test-only binary under tests/_build),
+must reproduce applications_tests/lethe-particles/packing_in_box.mpirun=1.output.
+GPU part: the product binary itself against the same golden."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from lethe_b200.prm import load_prm
+from lethe_b200.solver import box_wall_faces
+from oracle import loader
+from tests.util import GOLDEN, golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "lethe_b200", "host")
+PRM = os.path.join(GOLDEN, "packing_in_box.prm")
+
+
+def product_binary():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "lethe_b200", "csrc"), "-s", "-j8"])
+    subprocess.check_call(["make", "-C", HOST, "-s"])
+    return os.path.join(HOST, "lethe-particles-b200")
+
+
+def parse_xyz(text):
+    rows = []
+    for line in text.splitlines():
+        parts = line.split()
+        if len(parts) == 6 and parts[0].isdigit():
+            rows.append([int(parts[0]), int(parts[1])] + [float(v) for v in parts[2:]])
+    return rows
+
+
+def check_against_golden(rows):
+    gold = golden("packing_in_box.mpirun1.json")["rows"]
+    assert len(rows) == len(gold) == 200
+    assert [r[0] for r in rows] == [g[0] for g in gold]
+    err = np.abs(np.array([r[3:6] for r in rows]) - np.array([g[3:6] for g in gold])).max(axis=1)
+    assert np.mean(err <= 1.01e-4) > 0.9 and err.max() < 0.2 * 0.005, (np.mean(err <= 1.01e-4), err.max())
+
+
+def test_dump_config_matches_python_mirror():
+    exe = product_binary()
+    out = subprocess.run([exe, PRM, "--dump-config"], capture_output=True, text=True, check=True).stdout
+    c = json.loads(out)
+    p = load_prm(PRM)
+    ref = p.to_config()
+    for key in ("pp_model", "pw_model", "rolling_model", "detection", "contact_detection_frequency", "cell_order", "n_types", "restart"):
+        assert c[key] == getattr(ref, key), key
+    for key in ("dt", "neighborhood_threshold", "d_max", "smallest_contact_search_criterion", "dmt_cut_off_threshold",
+                "f_coefficient_epsd", "young_wall", "friction_wall"):
+        assert c[key] == getattr(ref, key), key
+    for key in ("g", "grid_lo", "cell_size", "grid_n", "periodic"):
+        assert list(c[key]) == list(getattr(ref, key)), key
+    assert c["young"][0] == ref.young[0] and c["friction"][0] == ref.friction[0]
+    assert c["n_wall_faces"] == len(box_wall_faces(p.mesh, p.outlet_boundaries, p.periodic))
+
+
+def test_product_binary_fails_loudly_without_gpu_or_runs():
+    """No CPU fallback: without a CUDA device the binary exits 1 with the reference's banner."""
+    exe = product_binary()
+    r = subprocess.run([exe, PRM, "--quiet"], capture_output=True, text=True)
+    if r.returncode != 0:
+        assert r.returncode == 1 and "no CUDA device" in r.stderr and "Aborting!" in r.stderr
+    else:
+        check_against_golden(parse_xyz(r.stdout))
+
+
+def test_host_sources_against_oracle_reproduce_reference_golden(tmp_path):
+    loader.build()
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "lethe-particles-oracle")
+    srcs = [os.path.join(HOST, f) for f in ("dem_parameters.cc", "dem_solver.cc", "lethe_particles_b200.cc")]
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DLETHE_DEM_ABI_PREFIX=oracle_dem_", "-o", exe, *srcs, "-L" + odir,
+                           "-ldem_oracle", "-Wl,-rpath," + odir])
+    r = subprocess.run([exe, PRM, "--quiet"], capture_output=True, text=True, check=True)
+    check_against_golden(parse_xyz(r.stdout))
+
+
+@pytest.mark.gpu
+def test_product_binary_reproduces_reference_golden_on_gpu():
+    exe = product_binary()
+    r = subprocess.run([exe, PRM, "--quiet"], capture_output=True, text=True, check=True)
+    check_against_golden(parse_xyz(r.stdout))
+    # and the log path (progression banner + statistics table) runs
+    r2 = subprocess.run([exe, PRM], capture_output=True, text=True, check=True)
+    assert "Transient iteration:" in r2.stdout and "Contact list generation" in r2.stdout
