@@ -86,10 +86,17 @@ def test_host_sources_against_oracle_reproduce_reference_golden(tmp_path):
 
 
 @pytest.mark.gpu
-def test_product_binary_reproduces_reference_golden_on_gpu():
+def test_product_binary_reproduces_reference_golden_on_gpu(tmp_path):
     exe = product_binary()
     r = subprocess.run([exe, PRM, "--quiet"], capture_output=True, text=True, check=True)
     check_against_golden(parse_xyz(r.stdout))
-    # and the log path (progression banner + statistics table) runs
-    r2 = subprocess.run([exe, PRM], capture_output=True, text=True, check=True)
+    # and the log path (progression banner + statistics table) runs: the golden case logs every
+    # 1e6 iterations (never, in 1e4 steps), so use a copy that logs every 2500
+    with open(PRM) as f:
+        text = f.read().replace("set log frequency    = 1000000", "set log frequency    = 2500")
+    assert "= 2500" in text
+    prm2 = tmp_path / "packing_in_box_log.prm"
+    prm2.write_text(text)
+    r2 = subprocess.run([exe, str(prm2)], capture_output=True, text=True, check=True)
     assert "Transient iteration:" in r2.stdout and "Contact list generation" in r2.stdout
+    check_against_golden(parse_xyz(r2.stdout[r2.stdout.index("id, type"):]))
