@@ -30,6 +30,9 @@ namespace dem
   {
     T *p = nullptr;
     size_t cap = 0;
+    // when set, outgrown allocations are parked here instead of freed (a peer GPU may still have
+    // them mapped through CUDA IPC; the owner of the list frees them once that cannot be)
+    std::vector<void *> *retire = nullptr;
     ~DevBuf() { release(); }
     void release()
     {
@@ -52,7 +55,12 @@ namespace dem
           CU_TRY(cudaStreamSynchronize(s));
         }
       if (p)
-        cudaFree(p);
+        {
+          if (retire)
+            retire->push_back(p);
+          else
+            cudaFree(p);
+        }
       p = np;
       cap = ncap;
     }
@@ -168,8 +176,17 @@ struct lethe_dem_ctx
   bool contact_search_trigger = true;
   bool clear_history_trigger = false;
   uint64_t n_rebuilds = 0;
-  int *h_flag = nullptr; // mapped pinned: written by the step kernel
-  int *d_flag = nullptr;
+  // contact-detection trigger (StepParams::flag_*): the tag of the step that asked for a new
+  // list, 0 = nobody. `h_flag` is mapped pinned memory (device alias `d_flag`) the host polls,
+  // `flag_dev[0]` the device copy the next (speculative) launch checks, `flag_dev[1]` the
+  // job-wide agreed flag of a multi-GPU run.
+  volatile uint32_t *h_flag = nullptr;
+  uint32_t *d_flag = nullptr;
+  DevBuf<uint32_t> flag_dev;
+  // pipelined stepping: step k+1 is queued before the host has seen step k's flag
+  bool pipeline = true;
+  cudaEvent_t step_done[2] = {nullptr, nullptr};
+  uint64_t n_void_launches = 0;
 
   // debug taps
   DevBuf<double> force_out, torque_out;

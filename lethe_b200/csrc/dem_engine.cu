@@ -383,6 +383,7 @@ namespace
     neww.n_entries = n_wall;
 
     c->cur_list ^= 1;
+    CU_TRY(cudaMemsetAsync(c->flag_dev.p, 0, 4 * sizeof(uint32_t), s));
     CU_TRY(cudaStreamSynchronize(s));
     *c->h_flag = 0; // no kernel in flight can touch the flag here
     ++c->n_rebuilds;
@@ -408,7 +409,10 @@ namespace
       }
   }
 
-  void launch_step_kernel(Ctx *c, int phase)
+  // non-zero tag of a step: what its kernel leaves in the trigger flag
+  inline uint32_t step_tag(uint64_t iteration) { return uint32_t(iteration % 0x7fffffffull) + 1u; }
+
+  void launch_step_kernel(Ctx *c, int phase, bool speculative = false)
   {
     cudaStream_t s = c->stream;
     StepParams P;
@@ -419,7 +423,16 @@ namespace
     P.walls = c->wlists[c->cur_list].view();
     P.id = c->st[c->cur].id.p;
     P.disp = c->disp.p;
-    P.rebuild_flag = c->d_flag;
+    P.flag_local = c->flag_dev.p;
+    P.flag_host = c->d_flag;
+    P.flag_check = c->flag_dev.p;
+    P.flag_tag = step_tag(c->iteration_number);
+    P.spec_check = speculative ? 1 : 0;
+    if (c->multi.enabled())
+      {
+        c->multi.fill_halo(c, c->cur ^ 1, P.halo);
+        P.flag_check = c->multi.agreed_flag_dev(c); // the job-wide agreement, never this step's own tag
+      }
     if (c->cfg.store_forces || c->count_touching)
       {
         c->touching.ensure(1);
@@ -466,6 +479,7 @@ namespace
           resolve_timers(c);
       }
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(c->step_done[c->iteration_number & 1], s));
     // ids / registered cells do not change in a step: both generations share them logically;
     // keep the other generation's copies in sync lazily (they are only read at rebuilds).
     c->cur ^= 1;
@@ -523,13 +537,88 @@ namespace
       c->multi.refresh_ghosts(c);
   }
 
+  void drop_last_step_timer(Ctx *c);
+
+  // Pipelined form of "check the flag, then step" for the common case (one GPU, dynamic
+  // detection, nothing forced): the step kernel is queued SPECULATIVELY behind the previous
+  // one, then the host waits for the previous kernel only and reads its flag. If that flag asks
+  // for a new list, the queued launch has found the same flag on the device and has returned
+  // without touching anything; the host takes the state flip back, rebuilds and launches the
+  // step for real. The GPU therefore always has the next kernel queued and never waits for the
+  // host's flag read; the sequence of kernels that DO something is exactly the unpipelined one.
+  bool step_speculatively(Ctx *c, int phase)
+  {
+    if (!c->pipeline || c->multi.enabled() || c->contact_search_trigger || c->cfg.detection != LETHE_DETECTION_DYNAMIC)
+      return false;
+    const uint64_t freq = uint64_t(std::max(1, c->cfg.contact_detection_frequency));
+    if ((c->iteration_number % freq) != 0 || phase != PHASE_REGULAR)
+      return false;
+    launch_step_kernel(c, phase, true);
+    CU_TRY(cudaEventSynchronize(c->step_done[(c->iteration_number - 1) & 1])); // previous step's kernel
+    const uint32_t seen = *c->h_flag;
+    if (seen == 0u || seen == step_tag(c->iteration_number))
+      return true; // nothing asked for a new list before this step: the launch is the step
+    // void launch: undo its bookkeeping, rebuild, run the step
+    c->cur ^= 1;
+    ++c->n_void_launches;
+    drop_last_step_timer(c);
+    rebuild(c);
+    mirror_ids(c);
+    launch_step_kernel(c, phase, false);
+    return true;
+  }
+
+  void drop_last_step_timer(Ctx *c)
+  {
+    if (c->timers_enabled && !c->pending_step.empty())
+      {
+        c->event_pool.push_back(c->pending_step.back().first);
+        c->event_pool.push_back(c->pending_step.back().second);
+        c->pending_step.pop_back();
+        --c->step_launches;
+      }
+  }
+
+  // Multi-GPU step with the fused halo (MultiGpu::fused): the ghost copies this step reads were
+  // stored by the neighbours' previous step kernels, so the only collective of a step is the
+  // 4-byte agreement "does anybody need a new list" — find_contact_detection_step.cc:53-58's
+  // logical_or — which is also the barrier that orders those peer stores. It is queued on the
+  // stream, the step kernel is queued speculatively behind it (void if the agreement is
+  // non-zero), and the host reads the agreement while the kernel already runs.
+  void step_fused_multi(Ctx *c, int phase)
+  {
+    const uint64_t freq = uint64_t(std::max(1, c->cfg.contact_detection_frequency));
+    const bool on_check_iteration = (c->iteration_number % freq) == 0;
+    const bool forced = c->contact_search_trigger || (c->cfg.detection == LETHE_DETECTION_CONSTANT && on_check_iteration);
+    const bool consult = c->cfg.detection == LETHE_DETECTION_DYNAMIC && on_check_iteration;
+    c->multi.post_agree(c, forced ? 0x80000000u : 0u, consult);
+    const bool launched = !forced; // a rank that knows the answer does not speculate
+    if (launched)
+      launch_step_kernel(c, phase, true);
+    if (c->multi.wait_agree(c) == 0u)
+      return;
+    if (launched)
+      {
+        c->cur ^= 1; // the launch was void on every rank
+        ++c->n_void_launches;
+        drop_last_step_timer(c);
+      }
+    c->multi.rebuild_with_exchange(c);
+    launch_step_kernel(c, phase, false);
+  }
+
   void one_step(Ctx *c)
   {
     c->iteration_number++;
     c->current_time += c->cfg.dt;
-    contact_detection_and_search(c);
     const int phase = (c->iteration_number <= 1 && !c->cfg.restart) ? PHASE_START : PHASE_REGULAR;
-    launch_step_kernel(c, phase);
+    if (c->multi.fused() && c->pipeline)
+      step_fused_multi(c, phase);
+    else if (!step_speculatively(c, phase))
+      {
+        contact_detection_and_search(c);
+        launch_step_kernel(c, phase);
+      }
     c->contact_search_trigger = false;
     c->clear_history_trigger = false;
   }
@@ -696,9 +785,20 @@ int lethe_dem_create(const lethe_dem_config *config, int device, lethe_dem_ctx *
       c->cell_of_rank.ensure(inv.size());
       CU_TRY(cudaMemcpy(c->cell_rank.p, rank.data(), rank.size() * 4, cudaMemcpyHostToDevice));
       CU_TRY(cudaMemcpy(c->cell_of_rank.p, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
-      CU_TRY(cudaHostAlloc(&c->h_flag, sizeof(int), cudaHostAllocMapped));
-      *c->h_flag = 0;
-      CU_TRY(cudaHostGetDevicePointer(&c->d_flag, c->h_flag, 0));
+      {
+        void *hf = nullptr, *df = nullptr;
+        CU_TRY(cudaHostAlloc(&hf, sizeof(uint32_t), cudaHostAllocMapped));
+        c->h_flag = static_cast<volatile uint32_t *>(hf);
+        *c->h_flag = 0;
+        CU_TRY(cudaHostGetDevicePointer(&df, hf, 0));
+        c->d_flag = static_cast<uint32_t *>(df);
+      }
+      c->flag_dev.ensure(4);
+      CU_TRY(cudaMemset(c->flag_dev.p, 0, 4 * sizeof(uint32_t)));
+      for (auto &ev : c->step_done)
+        CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      if (const char *e = getenv("LETHE_DEM_NO_PIPELINE"))
+        c->pipeline = !(e[0] == '1');
       std::memset(&c->fw_host, 0, sizeof(c->fw_host));
       // empty lists so that a step with zero particles is well defined
       for (int k = 0; k < 2; ++k)
@@ -743,8 +843,11 @@ void lethe_dem_destroy(lethe_dem_ctx *c)
   for (auto ev : c->region_ev)
     if (ev)
       cudaEventDestroy(ev);
+  for (auto ev : c->step_done)
+    if (ev)
+      cudaEventDestroy(ev);
   if (c->h_flag)
-    cudaFreeHost(c->h_flag);
+    cudaFreeHost(const_cast<uint32_t *>(c->h_flag));
   if (c->stream)
     cudaStreamDestroy(c->stream);
   delete c;

@@ -922,6 +922,35 @@ namespace dem
     k_flag_layer<<<blocks_for(size_t(n) + 1, 256), 256, 0, s>>>(cell_reg, grid, layer_cell, n, flags);
     count_launch();
   }
+  namespace
+  {
+    __global__ void __launch_bounds__(256) k_halo_warp_table(const uint32_t *flags, const uint32_t *offsets, uint32_t n,
+                                                             uint32_t *bits, uint32_t *prefix)
+    {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      const uint32_t b = __ballot_sync(0xffffffffu, p < n && flags[p] != 0u);
+      if ((threadIdx.x & 31u) == 0u && p < n)
+        {
+          bits[p >> 5] = b;
+          prefix[p >> 5] = offsets[p];
+        }
+    }
+    __global__ void k_prepare_flag(uint32_t *w, uint32_t host_bits, int consult) { w[2] = (consult ? w[0] : 0u) | host_bits; }
+  } // namespace
+  void launch_halo_warp_table(const uint32_t *flags, const uint32_t *offsets, uint32_t n, uint32_t *bits, uint32_t *prefix,
+                              cudaStream_t s)
+  {
+    if (n)
+      {
+        k_halo_warp_table<<<blocks_for(n, 256), 256, 0, s>>>(flags, offsets, n, bits, prefix);
+        count_launch();
+      }
+  }
+  void launch_prepare_flag(uint32_t *flag_words, uint32_t host_bits, int consult, cudaStream_t s)
+  {
+    k_prepare_flag<<<1, 1, 0, s>>>(flag_words, host_bits, consult);
+    count_launch();
+  }
   void launch_compact_indices(const uint32_t *flags, const uint32_t *offsets, uint32_t n, uint32_t *out, cudaStream_t s)
   {
     if (n)

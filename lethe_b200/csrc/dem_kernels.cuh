@@ -107,6 +107,19 @@ namespace dem
     PHASE_END = 2      // integrate_end: half kick, no drift
   };
 
+  // Fused halo push (multi-GPU): the step kernel stores the new state of the owned particles
+  // that lie in the slab's boundary cell layers straight into the ghost slots of the
+  // neighbouring GPU's OUT generation, through peer (NVLink) pointers — the per-step
+  // update_ghost_particles (dem.cc:686) without a separate pack / send / receive.
+  // Direction d: 0 = towards the lower neighbour, 1 = towards the upper one.
+  struct HaloPush
+  {
+    double4 *pos[2], *vel[2], *omg[2]; // peer arrays of the generation this step writes (nullptr: nothing to push)
+    const uint32_t *bits[2];           // per 32-row block: rows lying in the boundary layer
+    const uint32_t *prefix[2];         // per 32-row block: boundary rows before the block
+    uint32_t base[2];                  // first ghost slot of my run in the peer's arrays
+  };
+
   struct StepParams
   {
     StateView in, out;
@@ -114,7 +127,18 @@ namespace dem
     WallListView walls;
     const uint32_t *id;
     double *disp;
-    int *rebuild_flag;
+    // Contact-detection trigger (find_contact_detection_step.cc:29-58). A step whose largest
+    // accumulated displacement exceeds `criterion` writes its non-zero `flag_tag` to
+    // `flag_local` (device) and, when given, to `flag_host` (mapped pinned, single-GPU).
+    // A SPECULATIVE launch (`spec_check`) is queued before the host has seen the previous
+    // step's flag: it reads `flag_check` first and returns without touching anything when an
+    // earlier step (any tag but its own) already asked for a new list.
+    uint32_t *flag_local;
+    uint32_t *flag_host;
+    const uint32_t *flag_check;
+    uint32_t flag_tag;
+    int spec_check;
+    HaloPush halo;
     unsigned long long *touching_counter; // debug (store_forces)
     double *force_out, *torque_out;       // debug taps [N][3] or nullptr
     FaceTable faces;
@@ -192,6 +216,11 @@ namespace dem
   // flag owned particles (sorted) lying in the slab's boundary cell layer `layer` along the axis
   void launch_flag_layer(const int32_t *cell_reg, GridDesc grid, int layer_cell, uint32_t n, uint32_t *flags, cudaStream_t s);
   void launch_compact_indices(const uint32_t *flags, const uint32_t *offsets, uint32_t n, uint32_t *out, cudaStream_t s);
+  // per block of 32 rows: ballot of `flags` and the exclusive prefix at the block's first row (HaloPush tables)
+  void launch_halo_warp_table(const uint32_t *flags, const uint32_t *offsets, uint32_t n, uint32_t *bits, uint32_t *prefix,
+                              cudaStream_t s);
+  // word[2] = (consult ? word[0] : 0) | host_bits : the rank's contribution to the per-step agreement
+  void launch_prepare_flag(uint32_t *flag_words, uint32_t host_bits, int consult, cudaStream_t s);
   void launch_gather_state(StateView st, const uint32_t *idx, uint32_t n, double4 *pos, double4 *vel, double4 *omg,
                            cudaStream_t s);
   void launch_gather_ids(const uint32_t *id, const uint32_t *idx, uint32_t n, uint32_t *out, cudaStream_t s);

@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "dem_context.cuh"
@@ -92,7 +93,43 @@ namespace dem
     uint32_t n_send[2] = {0, 0};
     DevBuf<int> flag_dev; // [2]
     int *flag_host = nullptr;
+
+    // ---- fused halo over peer memory ----
+    bool want_fused = true;   // LETHE_DEM_HALO=nccl keeps the send/recv halo
+    bool fused_ready = false; // every rank mapped its neighbours' state arrays
+    struct Mapping
+    {
+      cudaIpcMemHandle_t handle;
+      void *base;
+      uint64_t epoch; // exchange at which the mapping was last referenced
+    };
+    std::vector<Mapping> mappings;
+    double4 *peer_arr[2][2][3] = {}; // [direction][peer generation][pos, vel, omg]
+    uint32_t peer_base[2] = {0, 0};
+    int gen_xor[2] = {0, 0}; // my generation index -> the peer's (both flip in lockstep)
+    DevBuf<uint32_t> halo_bits[2], halo_prefix[2];
+    DevBuf<uint8_t> info_dev;
+    uint64_t epoch = 0;
+    std::vector<void *> retired;                           // outgrown state arrays (DevBuf::retire)
+    std::vector<std::pair<void *, uint64_t>> graveyard;    // ... with the exchange they were retired at
+    uint32_t *agreed_host = nullptr;                       // pinned [2]
+    cudaEvent_t agreed_ev[2] = {nullptr, nullptr};
+    int agreed_slot = 0;
   };
+
+  namespace
+  {
+    // what a rank tells the neighbour that pushes into one of its ghost runs
+    struct HaloInfo
+    {
+      cudaIpcMemHandle_t handle[2][3];
+      uint64_t offset[2][3]; // of the array inside the exported allocation
+      uint32_t cur;          // current state generation of the sender
+      uint32_t base;         // first slot of the ghost run
+      uint32_t ok;
+      uint32_t pad;
+    };
+  } // namespace
 
   int MultiGpu::unique_id(uint8_t *id128)
   {
@@ -129,6 +166,25 @@ namespace dem
     m->xcount.ensure(8);
     m->flag_dev.ensure(2);
     CU_TRY(cudaHostAlloc(&m->flag_host, 2 * sizeof(int), cudaHostAllocDefault));
+    if (const char *e = getenv("LETHE_DEM_HALO"))
+      m->want_fused = std::strcmp(e, "nccl") != 0;
+    if (world < 2)
+      m->want_fused = false;
+    if (m->want_fused)
+      {
+        CU_TRY(cudaHostAlloc(&m->agreed_host, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+        m->agreed_host[0] = m->agreed_host[1] = 0;
+        for (auto &ev : m->agreed_ev)
+          CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        m->info_dev.ensure(4 * sizeof(HaloInfo));
+        // state arrays a neighbour may have mapped are never freed under its feet
+        for (int g = 0; g < 2; ++g)
+          {
+            c->st[g].pos.retire = &m->retired;
+            c->st[g].vel.retire = &m->retired;
+            c->st[g].omg.retire = &m->retired;
+          }
+      }
     impl = m;
     c->contact_search_trigger = true;
   }
@@ -141,6 +197,17 @@ namespace dem
       g_nccl.CommDestroy(impl->comm);
     if (impl->flag_host)
       cudaFreeHost(impl->flag_host);
+    if (impl->agreed_host)
+      cudaFreeHost(impl->agreed_host);
+    for (auto ev : impl->agreed_ev)
+      if (ev)
+        cudaEventDestroy(ev);
+    for (auto &mp : impl->mappings)
+      cudaIpcCloseMemHandle(mp.base);
+    for (void *q : impl->retired)
+      cudaFree(q);
+    for (auto &g : impl->graveyard)
+      cudaFree(g.first);
     delete impl;
     impl = nullptr;
   }
@@ -202,6 +269,205 @@ namespace dem
       (void)m;
     }
   } // namespace
+
+  namespace
+  {
+    typedef int (*cuMemGetAddressRange_t)(unsigned long long *, size_t *, unsigned long long);
+
+    // (allocation base, offset) of a device pointer: cudaMalloc may sub-allocate, and an IPC
+    // handle always names the whole allocation
+    bool allocation_base(const void *p, void **base, uint64_t *offset)
+    {
+      static cuMemGetAddressRange_t fn = nullptr;
+      static bool tried = false;
+      if (!tried)
+        {
+          tried = true;
+          void *f = nullptr;
+          cudaDriverEntryPointQueryResult q;
+          if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<cuMemGetAddressRange_t>(f);
+        }
+      if (!fn)
+        return false;
+      unsigned long long b = 0;
+      size_t sz = 0;
+      if (fn(&b, &sz, (unsigned long long)(uintptr_t)p) != 0)
+        return false;
+      *base = reinterpret_cast<void *>(uintptr_t(b));
+      *offset = uint64_t(uintptr_t(p)) - uint64_t(b);
+      return true;
+    }
+
+    void *map_peer_allocation(MultiGpuImpl *m, const cudaIpcMemHandle_t &h)
+    {
+      for (auto &mp : m->mappings)
+        if (std::memcmp(&mp.handle, &h, sizeof(h)) == 0)
+          {
+            mp.epoch = m->epoch;
+            return mp.base;
+          }
+      void *base = nullptr;
+      if (cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        {
+          cudaGetLastError();
+          return nullptr;
+        }
+      m->mappings.push_back({h, base, m->epoch});
+      return base;
+    }
+
+    // Every rebuild: tell the two neighbours where their pushes must land (IPC handles of my six
+    // state arrays, my generation, the first slot of the ghost run they fill) and map theirs.
+    void exchange_halo_info(lethe_dem_ctx *c, MultiGpuImpl *m, const uint32_t g_recv[2])
+    {
+      cudaStream_t s = c->stream;
+      ++m->epoch;
+      HaloInfo mine[2], theirs[2];
+      std::memset(mine, 0, sizeof(mine));
+      std::memset(theirs, 0, sizeof(theirs));
+      bool ok = true;
+      HaloInfo base_info;
+      std::memset(&base_info, 0, sizeof(base_info));
+      for (int g = 0; g < 2 && ok; ++g)
+        {
+          double4 *arr[3] = {c->st[g].pos.p, c->st[g].vel.p, c->st[g].omg.p};
+          for (int a = 0; a < 3 && ok; ++a)
+            {
+              void *b = nullptr;
+              ok = arr[a] && allocation_base(arr[a], &b, &base_info.offset[g][a]) &&
+                   cudaIpcGetMemHandle(&base_info.handle[g][a], b) == cudaSuccess;
+            }
+        }
+      if (!ok)
+        cudaGetLastError();
+      base_info.cur = uint32_t(c->cur);
+      base_info.ok = ok ? 1u : 0u;
+      // run 0 is filled by the lower neighbour, run 1 by the upper one
+      for (int r = 0; r < 2; ++r)
+        {
+          mine[r] = base_info;
+          mine[r].base = c->n_owned + (r == 1 ? g_recv[0] : 0u);
+        }
+      uint8_t *dev = m->info_dev.p;
+      CU_TRY(cudaMemcpyAsync(dev, mine, 2 * sizeof(HaloInfo), cudaMemcpyHostToDevice, s));
+      NCCL_TRY(g_nccl.GroupStart());
+      // phase A: my run-1 description goes up; from below comes the lower neighbour's run 1 (the
+      // one I fill when pushing in direction 0). Phase B: the mirror image.
+      if (m->peer[1] >= 0)
+        NCCL_TRY(g_nccl.Send(dev + 1 * sizeof(HaloInfo), sizeof(HaloInfo), ncclUint8, m->peer[1], m->comm, s));
+      if (m->peer[0] >= 0)
+        NCCL_TRY(g_nccl.Recv(dev + 2 * sizeof(HaloInfo), sizeof(HaloInfo), ncclUint8, m->peer[0], m->comm, s));
+      if (m->peer[0] >= 0)
+        NCCL_TRY(g_nccl.Send(dev + 0 * sizeof(HaloInfo), sizeof(HaloInfo), ncclUint8, m->peer[0], m->comm, s));
+      if (m->peer[1] >= 0)
+        NCCL_TRY(g_nccl.Recv(dev + 3 * sizeof(HaloInfo), sizeof(HaloInfo), ncclUint8, m->peer[1], m->comm, s));
+      NCCL_TRY(g_nccl.GroupEnd());
+      CU_TRY(cudaMemcpyAsync(theirs, dev + 2 * sizeof(HaloInfo), 2 * sizeof(HaloInfo), cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      for (int d = 0; d < 2; ++d)
+        {
+          for (int g = 0; g < 2; ++g)
+            for (int a = 0; a < 3; ++a)
+              m->peer_arr[d][g][a] = nullptr;
+          if (m->peer[d] < 0)
+            continue;
+          const HaloInfo &t = theirs[d];
+          if (!t.ok)
+            {
+              ok = false;
+              continue;
+            }
+          for (int g = 0; g < 2; ++g)
+            for (int a = 0; a < 3; ++a)
+              {
+                void *b = map_peer_allocation(m, t.handle[g][a]);
+                if (!b)
+                  ok = false;
+                else
+                  m->peer_arr[d][g][a] = reinterpret_cast<double4 *>(static_cast<uint8_t *>(b) + t.offset[g][a]);
+              }
+          m->peer_base[d] = t.base;
+          m->gen_xor[d] = int(t.cur ^ uint32_t(c->cur)) & 1;
+        }
+      // fused only if it works for every rank (the per-step protocol is collective)
+      uint32_t all_ok = ok ? 1u : 0u;
+      CU_TRY(cudaMemcpyAsync(m->xcount.p, &all_ok, 4, cudaMemcpyHostToDevice, s));
+      NCCL_TRY(g_nccl.AllReduce(m->xcount.p, m->xcount.p, 1, ncclUint32, ncclMin, m->comm, s));
+      CU_TRY(cudaMemcpyAsync(&all_ok, m->xcount.p, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      if (!all_ok && m->rank == 0 && !m->fused_ready && m->epoch == 1)
+        fprintf(stderr, "[lethe_dem] CUDA IPC mapping of the neighbours' state arrays failed: halo stays on NCCL send/recv\n");
+      m->fused_ready = all_ok != 0;
+      // mappings nobody referenced for two exchanges belong to arrays their owner has outgrown;
+      // outgrown arrays of mine that were retired two exchanges ago are mapped by nobody any more
+      for (size_t k = 0; k < m->mappings.size();)
+        if (m->mappings[k].epoch + 2 <= m->epoch)
+          {
+            cudaIpcCloseMemHandle(m->mappings[k].base);
+            m->mappings[k] = m->mappings.back();
+            m->mappings.pop_back();
+          }
+        else
+          ++k;
+      for (void *q : m->retired)
+        m->graveyard.emplace_back(q, m->epoch);
+      m->retired.clear();
+      for (size_t k = 0; k < m->graveyard.size();)
+        if (m->graveyard[k].second + 4 <= m->epoch)
+          {
+            cudaFree(m->graveyard[k].first);
+            m->graveyard[k] = m->graveyard.back();
+            m->graveyard.pop_back();
+          }
+        else
+          ++k;
+    }
+  } // namespace
+
+  bool MultiGpu::fused() const { return impl && impl->fused_ready; }
+
+  const uint32_t *MultiGpu::agreed_flag_dev(lethe_dem_ctx *c) const { return c->flag_dev.p + 1; }
+
+  void MultiGpu::post_agree(lethe_dem_ctx *c, uint32_t host_bits, bool consult)
+  {
+    MultiGpuImpl *m = impl;
+    cudaStream_t s = c->stream;
+    launch_prepare_flag(c->flag_dev.p, host_bits, consult ? 1 : 0, s);
+    NCCL_TRY(g_nccl.AllReduce(c->flag_dev.p + 2, c->flag_dev.p + 1, 1, ncclUint32, ncclMax, m->comm, s));
+    m->agreed_slot ^= 1;
+    CU_TRY(cudaMemcpyAsync(m->agreed_host + m->agreed_slot, c->flag_dev.p + 1, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaEventRecord(m->agreed_ev[m->agreed_slot], s));
+  }
+
+  uint32_t MultiGpu::wait_agree(lethe_dem_ctx *c)
+  {
+    MultiGpuImpl *m = impl;
+    (void)c;
+    CU_TRY(cudaEventSynchronize(m->agreed_ev[m->agreed_slot]));
+    return *reinterpret_cast<volatile uint32_t *>(m->agreed_host + m->agreed_slot);
+  }
+
+  void MultiGpu::fill_halo(lethe_dem_ctx *c, int out_gen, HaloPush &h) const
+  {
+    std::memset(&h, 0, sizeof(h));
+    const MultiGpuImpl *m = impl;
+    if (!m || !m->fused_ready)
+      return;
+    (void)c;
+    for (int d = 0; d < 2; ++d)
+      {
+        if (m->peer[d] < 0 || m->n_send[d] == 0)
+          continue;
+        const int pg = (out_gen ^ m->gen_xor[d]) & 1;
+        h.pos[d] = m->peer_arr[d][pg][0];
+        h.vel[d] = m->peer_arr[d][pg][1];
+        h.omg[d] = m->peer_arr[d][pg][2];
+        h.bits[d] = m->halo_bits[d].p;
+        h.prefix[d] = m->halo_prefix[d].p;
+        h.base[d] = m->peer_base[d];
+      }
+  }
 
   void MultiGpu::rebuild_with_exchange(lethe_dem_ctx *c)
   {
@@ -333,6 +599,12 @@ namespace dem
         m->send_omg[d].ensure(std::max<uint32_t>(cnt, 1));
         launch_compact_indices(m->flags.p, m->offsets.p, n, m->send_idx[d].p, s);
         launch_gather_ids(sn.id.p, m->send_idx[d].p, cnt, m->send_ids[d].p, s);
+        if (m->want_fused)
+          {
+            m->halo_bits[d].ensure(size_t(n) / 32 + 2);
+            m->halo_prefix[d].ensure(size_t(n) / 32 + 2);
+            launch_halo_warp_table(m->flags.p, m->offsets.p, n, m->halo_bits[d].p, m->halo_prefix[d].p, s);
+          }
       }
     uint32_t g_recv[2] = {0, 0};
     exchange_counts(c, m, m->n_send, g_recv);
@@ -352,6 +624,8 @@ namespace dem
         NCCL_TRY(g_nccl.Recv(c->st[c->cur].id.p + n + (dr == 1 ? g_recv[0] : 0), g_recv[dr], ncclUint32, m->peer[dr], m->comm, s));
     });
     NCCL_TRY(g_nccl.GroupEnd());
+    if (m->want_fused)
+      exchange_halo_info(c, m, g_recv); // after the last (re)allocation of the state arrays in this rebuild
     refresh_ghosts(c); // positions / velocities of the new ghost set
 
     // ---- 4. ghost cell tables + history source ----

@@ -2,6 +2,8 @@
 #pragma once
 #include <cstdint>
 
+#include "dem_kernels.cuh"
+
 struct lethe_dem_ctx;
 
 namespace dem
@@ -22,6 +24,20 @@ namespace dem
     bool any_rank_flag(lethe_dem_ctx *c);
     // logical_or over ranks of a host-side decision
     bool agree(lethe_dem_ctx *c, bool local);
+
+    // ---- fused halo (peer-memory) mode ----
+    // true once every rank has mapped its neighbours' state arrays (CUDA IPC over NVLink): the
+    // step kernel then pushes the boundary-layer state itself and the only per-step collective
+    // left is the 4-byte agreement below, which doubles as the barrier between steps.
+    bool fused() const;
+    // queue on the stream: contribution = (consult ? my displacement flag : 0) | host_bits,
+    // all-reduce(max) into the device word the speculative step kernel checks, copy to the host
+    void post_agree(lethe_dem_ctx *c, uint32_t host_bits, bool consult);
+    // wait for the agreement posted last and return it (0 = nobody asked for a new list)
+    uint32_t wait_agree(lethe_dem_ctx *c);
+    // peer pointers / tables of the halo push for a kernel that writes state generation `out_gen`
+    void fill_halo(lethe_dem_ctx *c, int out_gen, HaloPush &h) const;
+    const uint32_t *agreed_flag_dev(lethe_dem_ctx *c) const;
   };
   void engine_rebuild_local(lethe_dem_ctx *c);
   void engine_upload_walls(lethe_dem_ctx *c);

@@ -71,6 +71,14 @@ namespace dem
     int type;
   };
 
+  // R* = d d / (2 (d + d)) and m* = m m / (m + m) of the particle that owns the list row,
+  // computed once per particle per step: valid for every pair whose partner has bit-identical
+  // diameter and mass (all pairs of a monodisperse type), where it saves two IEEE divisions.
+  struct SelfPair
+  {
+    double effective_radius, effective_mass;
+  };
+
   struct PairResult
   {
     vec3 normal_force, tangential_force, torque_one, torque_two, rolling;
@@ -166,11 +174,22 @@ namespace dem
   template <int MODEL, int ROLLING>
   __device__ __forceinline__ void pp_calculate_contact(const MaterialTables &mt, vec3 &tangential_displacement,
                                                        vec3 &rolling_spring_torque, vec3 vt, double vn, vec3 n, double overlap,
-                                                       double dt, const ParticleView &p1, const ParticleView &p2, PairResult &r)
+                                                       double dt, const ParticleView &p1, const ParticleView &p2, PairResult &r,
+                                                       const SelfPair &self)
   {
     const double d1 = p1.d, d2 = p2.d;
-    const double effective_radius = (d1 * d2) / (2 * (d1 + d2));
-    const double effective_mass = (p1.m * p2.m) / (p1.m + p2.m);
+    double effective_radius, effective_mass;
+    if (d1 == d2 && p1.m == p2.m)
+      {
+        // same operands, same expression: bit-identical to the general branch
+        effective_radius = self.effective_radius;
+        effective_mass = self.effective_mass;
+      }
+    else
+      {
+        effective_radius = (d1 * d2) / (2 * (d1 + d2));
+        effective_mass = (p1.m * p2.m) / (p1.m + p2.m);
+      }
     const int k = p1.type * mt.n_types + p2.type;
     const double Y = mt.Y[k], G = mt.G[k], beta = mt.beta[k], mu = mt.mu[k];
     const double roll_visc = mt.roll_visc[k], roll_fric = mt.roll_fric[k];
@@ -186,7 +205,7 @@ namespace dem
           {
             cohesive_term = -F_po;
             pp_calculate_contact<LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP, ROLLING>(mt, tangential_displacement, rolling_spring_torque,
-                                                                                vt, vn, n, overlap, dt, p1, p2, r);
+                                                                                vt, vn, n, overlap, dt, p1, p2, r, self);
           }
         else if (overlap > delta_0)
           {

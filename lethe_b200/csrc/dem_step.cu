@@ -114,6 +114,10 @@ namespace dem
       uint8_t q_owner[QUEUE];            //   row (lane) that owns it
       uint8_t res_owner[RES_SLOTS];      // row that owns res[k] (non-decreasing in k)
       uint8_t seg[32];                   // per owner: first buffer position of its run at the current flush
+      double2 self[32];                  // per owner: R* and m* of a pair of two copies of itself (SelfPair)
+      double disp[32];                   // per owner: accumulated displacement, loaded with the state
+      uint32_t w0[32], w1[32];           // per owner: its range of the wall list
+      uint32_t halo[4];                  // HaloPush bits / prefix of this 32-row block, per direction
     };
 
     template <int MODEL, int ROLLING, bool PERIODIC>
@@ -125,19 +129,46 @@ namespace dem
       const uint32_t warp_base = (blockIdx.x * STEP_WARPS + (threadIdx.x >> 5)) * 32u;
       if (warp_base >= P.n_owned)
         return; // whole warp
+      // speculative launch: the flag of the steps before this one, read with everything else
+      // the prologue loads so that its latency is not exposed on its own
+      const uint32_t flag_seen = P.spec_check ? *reinterpret_cast<const volatile uint32_t *>(P.flag_check) : 0u;
       const uint32_t n_rows = min(32u, P.n_owned - warp_base);
       const uint32_t i = warp_base + lane;
       const bool valid = lane < n_rows;
       const double dt = P.dt;
 
       // ---------------- stage the warp's own rows ----------------
+      // every per-owner operand of the whole kernel is requested here, in one batch of
+      // independent loads: state, the displacement accumulator and the wall-list range
       const uint32_t E0 = P.list.row_start[warp_base], E1 = P.list.row_start[warp_base + n_rows];
+      double4 own_pos = make_double4(0, 0, 0, 1), own_vel = make_double4(0, 0, 0, 1), own_omg = make_double4(0, 0, 0, 0);
+      double own_disp = 0.;
+      uint32_t own_w0 = 0, own_w1 = 0;
       if (valid)
         {
-          S.pos[lane] = P.in.pos[i];
-          S.vel[lane] = P.in.vel[i];
-          S.omg[lane] = P.in.omg[i];
+          own_pos = P.in.pos[i];
+          own_vel = P.in.vel[i];
+          own_omg = P.in.omg[i];
+          own_disp = P.disp[i];
+          own_w0 = P.walls.row_start[i];
+          own_w1 = P.walls.row_start[i + 1];
         }
+      if (flag_seen != 0u && flag_seen != P.flag_tag)
+        return; // an earlier step asked for a new list: this launch is void (whole grid)
+      S.pos[lane] = own_pos;
+      S.vel[lane] = own_vel;
+      S.omg[lane] = own_omg;
+      S.disp[lane] = own_disp;
+      S.w0[lane] = own_w0;
+      S.w1[lane] = own_w1;
+      if (lane < 4)
+        {
+          const uint32_t d = lane & 1u;
+          S.halo[lane] = P.halo.pos[d] ? (lane < 2 ? P.halo.bits[d][warp_base >> 5] : P.halo.prefix[d][warp_base >> 5]) : 0u;
+        }
+      // R* and m* of a pair whose two particles have my diameter and mass (bit-identical to what
+      // pp_calculate_contact computes for such a pair, which is every pair of a monodisperse type)
+      S.self[lane] = make_double2((own_pos.w * own_pos.w) / (2 * (own_pos.w + own_pos.w)), (own_vel.w * own_vel.w) / (own_vel.w + own_vel.w));
       __syncwarp();
 
       vec3 F = v3(0, 0, 0), T = v3(0, 0, 0);
@@ -176,6 +207,8 @@ namespace dem
               }
             PairResult r;
             r.normal_force = r.tangential_force = r.torque_one = r.torque_two = r.rolling = v3(0, 0, 0);
+            const double2 self = S.self[owner];
+            const SelfPair sp{self.x, self.y};
             vec3 n, vt;
             double vn;
             vec3 fc, tc; // what the row particle receives: F -= fc, T += tc
@@ -189,7 +222,7 @@ namespace dem
                 h = -h;
                 rs = -rs;
                 pp_update_contact_information(h, vt, vn, n, one, two, x2, distance, dt);
-                pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, two, r);
+                pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, two, r, sp);
                 // apply_force_and_torque_on_local_particles, particle two (…force.h:565-569)
                 fc = -(r.normal_force + r.tangential_force);
                 tc = -r.torque_two - r.rolling;
@@ -201,7 +234,7 @@ namespace dem
                 ParticleView one = me;
                 one.x = x1;
                 pp_update_contact_information(h, vt, vn, n, one, other, x2, distance, dt);
-                pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, other, r);
+                pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, other, r, sp);
                 // particle one (…force.h:561-567)
                 fc = r.normal_force + r.tangential_force;
                 tc = -r.torque_one + r.rolling;
@@ -362,7 +395,7 @@ namespace dem
       const ParticleView me = make_view(pi, vi, wi);
 
       // ---------------- particle-wall contacts ----------------
-      const uint32_t w0 = P.walls.row_start[i], w1 = P.walls.row_start[i + 1];
+      const uint32_t w0 = S.w0[lane], w1 = S.w1[lane];
       for (uint32_t w = w0; w < w1; ++w)
         {
           const uint32_t we = P.walls.entry[w];
@@ -494,17 +527,36 @@ namespace dem
               x.z = x.z + v.z * dt;
             }
         }
-      P.out.pos[i] = make_double4(x.x, x.y, x.z, pi.w);
-      P.out.vel[i] = make_double4(v.x, v.y, v.z, vi.w);
-      P.out.omg[i] = make_double4(om.x, om.y, om.z, wi.w);
+      const double4 new_pos = make_double4(x.x, x.y, x.z, pi.w), new_vel = make_double4(v.x, v.y, v.z, vi.w),
+                    new_omg = make_double4(om.x, om.y, om.z, wi.w);
+      P.out.pos[i] = new_pos;
+      P.out.vel[i] = new_vel;
+      P.out.omg[i] = new_omg;
+      // fused halo push: boundary-layer rows also go to the neighbour GPU's ghost slots
+#pragma unroll
+      for (int d = 0; d < 2; ++d)
+        {
+          const uint32_t bits = S.halo[d];
+          if ((bits >> lane) & 1u)
+            {
+              const uint32_t k = P.halo.base[d] + S.halo[2 + d] + __popc(bits & ((1u << lane) - 1u));
+              P.halo.pos[d][k] = new_pos;
+              P.halo.vel[d][k] = new_vel;
+              P.halo.omg[d][k] = new_omg;
+            }
+        }
 
       // displacement for the next step's contact-detection check
       if (P.phase != PHASE_END)
         {
-          const double dsp = P.disp[i] + dt * sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+          const double dsp = S.disp[lane] + dt * sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
           P.disp[i] = dsp;
-          if (dsp > P.criterion)
-            *P.rebuild_flag = 1;
+          if (dsp > P.criterion && *reinterpret_cast<volatile uint32_t *>(P.flag_local) != P.flag_tag)
+            {
+              *reinterpret_cast<volatile uint32_t *>(P.flag_local) = P.flag_tag;
+              if (P.flag_host)
+                *reinterpret_cast<volatile uint32_t *>(P.flag_host) = P.flag_tag;
+            }
         }
     }
 

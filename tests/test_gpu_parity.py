@@ -336,3 +336,28 @@ def test_properties_at_scale():
     assert s0.n_particles == len(ids) and s0.n_pair_entries > 3 * len(ids)
     v = np.sqrt((p0[2][:, 3:6] ** 2).sum(axis=1))
     assert abs(s0.v_max - v.max()) <= 1e-15 * v.max() and abs(s0.v_sum - v.sum()) <= 1e-10 * v.sum()
+
+
+def test_pipelined_stepping_is_bitwise_identical(monkeypatch):
+    """The speculative (pipelined) launch protocol must execute exactly the kernel sequence of
+    the synchronous flag check: same rebuild steps, same bits, through several rebuilds."""
+    d = 0.005
+    ids, x, props, extent = random_packing(24, d=d, spacing=1.02, jitter=0.05, seed=5)
+    props[:, 3:6] = np.random.default_rng(3).normal(0, 0.3, (len(ids), 3))
+    params = packing_parameters(extent, d=d, rolling="constant")
+    params.dynamic_contact_search_factor = 0.2
+    out = []
+    for no_pipe in ("1", "0"):
+        monkeypatch.setenv("LETHE_DEM_NO_PIPELINE", no_pipe)
+        e = abi.load_engine(params.to_config(store_forces=True))
+        e.set_walls(box_wall_faces(params.mesh))
+        e.set_particles(ids, x, props)
+        e.step(150)
+        e.step(1)
+        e.step(149)
+        out.append((e.get_particles(), e.get_pairs(), e.get_forces(), e.get_stats().n_rebuilds))
+    (pa, qa, fa, ra), (pb, qb, fb, rb) = out
+    assert ra == rb and ra >= 4, (ra, rb)
+    assert np.array_equal(pa[1], pb[1]) and np.array_equal(pa[2], pb[2])
+    assert all(np.array_equal(u, v) for u, v in zip(qa, qb))
+    assert np.array_equal(fa[1], fb[1]) and np.array_equal(fa[2], fb[2])
