@@ -90,7 +90,13 @@ def make_workload(args, rank, world):
         # cubic cells per direction for ~n_per_gpu*world particles: 4 per FCC cell
         per = args.n_per_gpu
         side = max(4, round((per / 4.0) ** (1.0 / 3.0)))
-        return workloads.periodic_box(cells=(side * world, side, side), spacing=1.005, jitter=0.002)
+        return workloads.periodic_box(cells=(side * world, side, side), spacing=1.005, jitter=0.002,
+                                      slab=(rank, world) if world > 1 else None)
+    if args.workload == "hopper":
+        return workloads.hopper(n_target=args.n_per_gpu * world)
+    if args.workload in ("cohesive_jkr", "cohesive_dmt"):
+        side = max(4, round((args.n_per_gpu / 1.41) ** (1.0 / 3.0)))
+        return workloads.cohesive_box(side, model="hertz_JKR" if args.workload == "cohesive_jkr" else "DMT")
     if args.workload == "box_packing":
         side = max(4, round((args.n_per_gpu / 1.41) ** (1.0 / 3.0)))
         return workloads.box_packing(side, spacing=1.005, jitter=0.002)
@@ -164,7 +170,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="drum", choices=["drum", "periodic_box", "box_packing"])
+    ap.add_argument("--workload", default="drum", choices=["drum", "periodic_box", "box_packing", "hopper", "cohesive_jkr", "cohesive_dmt"])
     ap.add_argument("--n-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--settle", type=int, default=3000, help="untimed settling steps before warm-up")
     ap.add_argument("--e2e-steps", type=int, default=30)
@@ -203,12 +209,14 @@ def main():
     if world > 1:
         from lethe_b200 import multi
 
-        engine, n_local = multi.create_slab_engine(w, rank, world, local_rank, dist)
+        # a workload generated per slab (periodic_box) is cut into equal-width slabs; otherwise the
+        # cut planes balance the particle histogram
+        engine, n_local = multi.create_slab_engine(w, rank, world, local_rank, dist, balanced=not hasattr(w, "n_global"))
     else:
         engine = abi.load_engine(cfg_params.to_config(), local_rank)
         w.install(engine)
         n_local = w.n
-    n_global = w.n
+    n_global = getattr(w, "n_global", w.n)
 
     def barrier():
         if world > 1:

@@ -936,7 +936,51 @@ namespace dem
         }
     }
     __global__ void k_prepare_flag(uint32_t *w, uint32_t host_bits, int consult) { w[2] = (consult ? w[0] : 0u) | host_bits; }
+
+    __global__ void __launch_bounds__(32) k_agree(uint64_t *const *peer_mailbox, uint64_t *my_mailbox, int rank, int world, uint32_t seq,
+                                                  uint32_t *flag_words, uint32_t host_bits, int consult)
+    {
+      const int lane = threadIdx.x;
+      const uint32_t word = (consult ? flag_words[0] : 0u) | host_bits;
+      const int parity = int(seq & 1u);
+      uint32_t got = 0;
+      if (lane < world)
+        {
+          // the stores of the kernels before this one (halo pushes into the peers) are ordered
+          // before this release; the peer's acquire below makes them visible to its next kernel
+          uint64_t *dst = peer_mailbox[lane] + size_t(parity) * world + rank;
+          const uint64_t v = (uint64_t(seq) << 32) | word;
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+          const uint64_t *src = my_mailbox + size_t(parity) * world + lane;
+          uint64_t r;
+          const long long t0 = clock64();
+          for (;;)
+            {
+              asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(r) : "l"(src) : "memory");
+              if (uint32_t(r >> 32) == seq)
+                {
+                  got = uint32_t(r);
+                  break;
+                }
+              if (clock64() - t0 > 240000000000ll)
+                {
+                  got = 0xffffffffu;
+                  break;
+                }
+            }
+        }
+      for (int o = 16; o; o >>= 1)
+        got = max(got, __shfl_xor_sync(0xffffffffu, got, o));
+      if (lane == 0)
+        flag_words[1] = got;
+    }
   } // namespace
+  void launch_agree(uint64_t *const *peer_mailbox, uint64_t *my_mailbox, int rank, int world, uint32_t seq, uint32_t *flag_words,
+                    uint32_t host_bits, int consult, cudaStream_t s)
+  {
+    k_agree<<<1, 32, 0, s>>>(peer_mailbox, my_mailbox, rank, world, seq, flag_words, host_bits, consult);
+    count_launch();
+  }
   void launch_halo_warp_table(const uint32_t *flags, const uint32_t *offsets, uint32_t n, uint32_t *bits, uint32_t *prefix,
                               cudaStream_t s)
   {

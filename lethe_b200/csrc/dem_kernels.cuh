@@ -221,6 +221,14 @@ namespace dem
                               cudaStream_t s);
   // word[2] = (consult ? word[0] : 0) | host_bits : the rank's contribution to the per-step agreement
   void launch_prepare_flag(uint32_t *flag_words, uint32_t host_bits, int consult, cudaStream_t s);
+  // Per-step agreement over peer memory (the logical_or of find_contact_detection_step.cc:53-58
+  // without a library collective): every rank stores (seq, its word) into slot `rank` of every
+  // rank's mailbox (system-scope release), waits until its own mailbox holds `seq` from all
+  // `world` ranks (acquire) and writes the maximum to flag_words[1]. mailbox layout:
+  // [parity of seq][world] u64 = seq << 32 | word. A rank that waits longer than ~2 min writes
+  // 0xffffffff (the host turns that into an error instead of a hung GPU).
+  void launch_agree(uint64_t *const *peer_mailbox, uint64_t *my_mailbox, int rank, int world, uint32_t seq, uint32_t *flag_words,
+                    uint32_t host_bits, int consult, cudaStream_t s);
   void launch_gather_state(StateView st, const uint32_t *idx, uint32_t n, double4 *pos, double4 *vel, double4 *omg,
                            cudaStream_t s);
   void launch_gather_ids(const uint32_t *id, const uint32_t *idx, uint32_t n, uint32_t *out, cudaStream_t s);

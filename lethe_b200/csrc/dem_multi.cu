@@ -40,6 +40,7 @@ namespace dem
       ncclResult_t (*GroupStart)() = nullptr;
       ncclResult_t (*GroupEnd)() = nullptr;
       ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+      ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
       const char *(*GetErrorString)(ncclResult_t) = nullptr;
       bool load()
       {
@@ -62,6 +63,7 @@ namespace dem
         LOAD(GroupStart);
         LOAD(GroupEnd);
         LOAD(AllReduce);
+        LOAD(AllGather);
         LOAD(GetErrorString);
 #undef LOAD
         return GetUniqueId && CommInitRank && Send && Recv && GroupStart && GroupEnd && AllReduce;
@@ -112,6 +114,13 @@ namespace dem
     uint64_t epoch = 0;
     std::vector<void *> retired;                           // outgrown state arrays (DevBuf::retire)
     std::vector<std::pair<void *, uint64_t>> graveyard;    // ... with the exchange they were retired at
+    // per-step agreement over peer memory (launch_agree); NCCL all-reduce when not available
+    bool want_mailbox = true; // LETHE_DEM_AGREE=nccl keeps the library collective
+    bool mailbox_ready = false, mailbox_tried = false;
+    uint64_t *mailbox = nullptr;
+    DevBuf<uint64_t *> peer_mailbox;
+    std::vector<void *> mailbox_maps;
+    uint32_t agree_seq = 0;
     uint32_t *agreed_host = nullptr;                       // pinned [2]
     cudaEvent_t agreed_ev[2] = {nullptr, nullptr};
     int agreed_slot = 0;
@@ -168,8 +177,12 @@ namespace dem
     CU_TRY(cudaHostAlloc(&m->flag_host, 2 * sizeof(int), cudaHostAllocDefault));
     if (const char *e = getenv("LETHE_DEM_HALO"))
       m->want_fused = std::strcmp(e, "nccl") != 0;
+    if (const char *e = getenv("LETHE_DEM_AGREE"))
+      m->want_mailbox = std::strcmp(e, "nccl") != 0;
     if (world < 2)
       m->want_fused = false;
+    if (world > 32 || !g_nccl.AllGather)
+      m->want_mailbox = false;
     if (m->want_fused)
       {
         CU_TRY(cudaHostAlloc(&m->agreed_host, 2 * sizeof(uint32_t), cudaHostAllocDefault));
@@ -204,6 +217,10 @@ namespace dem
         cudaEventDestroy(ev);
     for (auto &mp : impl->mappings)
       cudaIpcCloseMemHandle(mp.base);
+    for (void *q : impl->mailbox_maps)
+      cudaIpcCloseMemHandle(q);
+    if (impl->mailbox)
+      cudaFree(impl->mailbox);
     for (void *q : impl->retired)
       cudaFree(q);
     for (auto &g : impl->graveyard)
@@ -317,11 +334,80 @@ namespace dem
       return base;
     }
 
+    // Once: every rank maps every rank's agreement mailbox (launch_agree). Collective; the result
+    // (usable or not) is the same on all ranks.
+    void bootstrap_mailboxes(lethe_dem_ctx *c, MultiGpuImpl *m)
+    {
+      cudaStream_t s = c->stream;
+      m->mailbox_tried = true;
+      struct Slot
+      {
+        cudaIpcMemHandle_t handle;
+        uint64_t offset;
+        uint64_t ok;
+      };
+      const int W = m->world;
+      Slot mine;
+      std::memset(&mine, 0, sizeof(mine));
+      bool ok = cudaMalloc(&m->mailbox, size_t(2) * W * sizeof(uint64_t)) == cudaSuccess;
+      void *base = nullptr;
+      if (ok)
+        {
+          CU_TRY(cudaMemsetAsync(m->mailbox, 0, size_t(2) * W * sizeof(uint64_t), s));
+          ok = allocation_base(m->mailbox, &base, &mine.offset) && cudaIpcGetMemHandle(&mine.handle, base) == cudaSuccess;
+        }
+      if (!ok)
+        cudaGetLastError();
+      mine.ok = ok ? 1 : 0;
+      DevBuf<uint8_t> buf;
+      buf.ensure(size_t(W + 1) * sizeof(Slot));
+      CU_TRY(cudaMemcpyAsync(buf.p + size_t(W) * sizeof(Slot), &mine, sizeof(Slot), cudaMemcpyHostToDevice, s));
+      NCCL_TRY(g_nccl.AllGather(buf.p + size_t(W) * sizeof(Slot), buf.p, sizeof(Slot), ncclUint8, m->comm, s));
+      std::vector<Slot> all(W);
+      CU_TRY(cudaMemcpyAsync(all.data(), buf.p, size_t(W) * sizeof(Slot), cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      std::vector<uint64_t *> ptrs(W, nullptr);
+      for (int r = 0; r < W; ++r)
+        {
+          if (!all[r].ok)
+            ok = false;
+          if (!ok)
+            break;
+          if (r == m->rank)
+            {
+              ptrs[r] = m->mailbox;
+              continue;
+            }
+          void *b = nullptr;
+          if (cudaIpcOpenMemHandle(&b, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+            {
+              cudaGetLastError();
+              ok = false;
+              break;
+            }
+          m->mailbox_maps.push_back(b);
+          ptrs[r] = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(b) + all[r].offset);
+        }
+      if (ok)
+        {
+          m->peer_mailbox.ensure(W);
+          CU_TRY(cudaMemcpyAsync(m->peer_mailbox.p, ptrs.data(), size_t(W) * sizeof(uint64_t *), cudaMemcpyHostToDevice, s));
+        }
+      uint32_t all_ok = ok ? 1u : 0u;
+      CU_TRY(cudaMemcpyAsync(m->xcount.p, &all_ok, 4, cudaMemcpyHostToDevice, s));
+      NCCL_TRY(g_nccl.AllReduce(m->xcount.p, m->xcount.p, 1, ncclUint32, ncclMin, m->comm, s));
+      CU_TRY(cudaMemcpyAsync(&all_ok, m->xcount.p, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s)); // every mailbox is zeroed and mapped before anyone posts
+      m->mailbox_ready = all_ok != 0;
+    }
+
     // Every rebuild: tell the two neighbours where their pushes must land (IPC handles of my six
     // state arrays, my generation, the first slot of the ghost run they fill) and map theirs.
     void exchange_halo_info(lethe_dem_ctx *c, MultiGpuImpl *m, const uint32_t g_recv[2])
     {
       cudaStream_t s = c->stream;
+      if (m->want_mailbox && !m->mailbox_tried)
+        bootstrap_mailboxes(c, m);
       ++m->epoch;
       HaloInfo mine[2], theirs[2];
       std::memset(mine, 0, sizeof(mine));
@@ -433,8 +519,13 @@ namespace dem
   {
     MultiGpuImpl *m = impl;
     cudaStream_t s = c->stream;
-    launch_prepare_flag(c->flag_dev.p, host_bits, consult ? 1 : 0, s);
-    NCCL_TRY(g_nccl.AllReduce(c->flag_dev.p + 2, c->flag_dev.p + 1, 1, ncclUint32, ncclMax, m->comm, s));
+    if (m->mailbox_ready)
+      launch_agree(m->peer_mailbox.p, m->mailbox, m->rank, m->world, ++m->agree_seq, c->flag_dev.p, host_bits, consult ? 1 : 0, s);
+    else
+      {
+        launch_prepare_flag(c->flag_dev.p, host_bits, consult ? 1 : 0, s);
+        NCCL_TRY(g_nccl.AllReduce(c->flag_dev.p + 2, c->flag_dev.p + 1, 1, ncclUint32, ncclMax, m->comm, s));
+      }
     m->agreed_slot ^= 1;
     CU_TRY(cudaMemcpyAsync(m->agreed_host + m->agreed_slot, c->flag_dev.p + 1, 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaEventRecord(m->agreed_ev[m->agreed_slot], s));
@@ -445,7 +536,10 @@ namespace dem
     MultiGpuImpl *m = impl;
     (void)c;
     CU_TRY(cudaEventSynchronize(m->agreed_ev[m->agreed_slot]));
-    return *reinterpret_cast<volatile uint32_t *>(m->agreed_host + m->agreed_slot);
+    const uint32_t v = *reinterpret_cast<volatile uint32_t *>(m->agreed_host + m->agreed_slot);
+    if (v == 0xffffffffu)
+      throw std::runtime_error("multi-GPU step agreement timed out: a neighbouring rank did not reach this step");
+    return v;
   }
 
   void MultiGpu::fill_halo(lethe_dem_ctx *c, int out_gen, HaloPush &h) const

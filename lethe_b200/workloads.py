@@ -5,6 +5,9 @@ CPU oracle.  Host set-up only (the reference does this in insertion / mesh code)
     box_packing   config 1: monodisperse spheres in a box under gravity, HM limit-overlap
     drum          config 2: rotating drum, HM limit-overlap + constant rolling resistance,
                             faceted cylinder wall rotating about x
+    hopper        config 3: wedge hopper, polydisperse spheres held by a floating wall that
+                            opens at `gate_open_time`, outlet (particle deletion) below the slot
+    cohesive_box  config 4: config 1's geometry with hertz_JKR or DMT cohesion (history heavy)
     periodic_box  config 5: 3-periodic box, Maxwellian velocities, g = 0 (slab-decomposable)
 """
 from __future__ import annotations
@@ -83,12 +86,41 @@ def cylinder_wall_faces(mesh: Mesh, radius, centre_yz, d_max, boundary_id=4, cap
     return faces
 
 
+def plane_wall_faces(mesh: Mesh, point, normal, boundary_id, cell_filter=None, face_no=7):
+    """One face row (infinite plane `point`, inward unit `normal`) for every grid cell the
+    plane passes through or that lies within one cell diagonal behind it — what
+    BoundaryCellsInformation extracts for the boundary cells of an inclined mesh wall
+    (find_boundary_cells_information.cc:130-219). `cell_filter(i, j, k)` restricts the cells."""
+    nx, ny, nz = mesh.n
+    h = mesh.cell_size
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    centre = np.stack([mesh.lo[0] + (i + 0.5) * h[0], mesh.lo[1] + (j + 0.5) * h[1], mesh.lo[2] + (k + 0.5) * h[2]], axis=-1)
+    nrm = np.asarray(normal, dtype=np.float64)
+    nrm = nrm / np.linalg.norm(nrm)
+    dist = (centre - np.asarray(point)) @ nrm
+    half_diag = 0.5 * math.sqrt(h[0] ** 2 + h[1] ** 2 + h[2] ** 2)
+    sel = (dist < half_diag) & (dist > -half_diag)
+    if cell_filter is not None:
+        sel &= cell_filter(i, j, k)
+    faces = []
+    for ci, cj, ck in zip(i[sel].tolist(), j[sel].tolist(), k[sel].tolist()):
+        f = abi.WallFace()
+        f.cell = ci + nx * (cj + ny * ck)
+        f.boundary_id = boundary_id
+        f.global_face_id = f.cell * 8 + face_no
+        f.normal[:] = [float(v) for v in nrm]
+        f.point[:] = [float(v) for v in point]
+        faces.append(f)
+    return faces
+
+
 class Workload:
-    def __init__(self, name, params, ids, x, props, faces, motions=(), description=""):
+    def __init__(self, name, params, ids, x, props, faces, motions=(), description="", floating_walls=()):
         self.name, self.params = name, params
         self.ids, self.x, self.props = ids, x, props
         self.faces, self.motions = faces, list(motions)
         self.description = description
+        self.floating_walls = list(floating_walls)  # (point, normal, t_start, t_end)
 
     @property
     def n(self):
@@ -96,6 +128,9 @@ class Workload:
 
     def install(self, engine):
         engine.set_walls(self.faces)
+        if self.floating_walls:
+            engine.set_floating_walls([w[0] for w in self.floating_walls], [w[1] for w in self.floating_walls],
+                                      [w[2] for w in self.floating_walls], [w[3] for w in self.floating_walls])
         for m in self.motions:
             engine.set_boundary_motion(*m)
         engine.set_particles(self.ids, self.x, self.props)
@@ -176,23 +211,52 @@ def box_packing(n_side=47, nz=None, d=0.005, seed=19, spacing=1.0, jitter=0.02, 
     return Workload("box_packing", p, ids, pts, props, box_wall_faces(mesh), (), f"box packing, {m} spheres, HM limit-overlap")
 
 
-def periodic_box(n_cells_side=32, d=0.005, seed=19, spacing=1.0, jitter=0.03, vel_sigma=0.1, cells=(None, None, None)):
+def periodic_box(n_cells_side=32, d=0.005, seed=19, spacing=1.0, jitter=0.03, vel_sigma=0.1, cells=(None, None, None), slab=None):
     """Config 5: 3-periodic box filled with a jittered FCC lattice (solid fraction ~0.55-0.7),
-    Maxwellian velocities, g = 0. `cells` = FCC cubic cells per direction (n^3*4 particles)."""
-    rng = np.random.default_rng(seed)
+    Maxwellian velocities, g = 0. `cells` = FCC cubic cells per direction (n^3*4 particles).
+    The lattice is generated one x-layer of cells at a time from a per-layer seeded stream, so
+    `slab=(rank, world)` can build just the layers of one rank's slab (equal-width slabs along
+    x, as multi.slab_bounds) with the very same particles the full generation would give it:
+    a 64 M-particle job never materialises on one host. ids are the global lattice index."""
     a = d * spacing
     c = a * math.sqrt(2.0)
     nc = [cells[k] or n_cells_side for k in range(3)]
-    i, j, k = np.meshgrid(np.arange(nc[0]), np.arange(nc[1]), np.arange(nc[2]), indexing="ij")
-    base = np.stack([i.ravel(), j.ravel(), k.ravel()], axis=1).astype(np.float64)
-    offs = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
-    pts = (base[:, None, :] + offs[None, :, :]).reshape(-1, 3) * c + 0.25 * c
     L = [nc[k] * c for k in range(3)]
-    pts = pts + rng.uniform(-jitter, jitter, pts.shape) * d
-    n = len(pts)
     # grid: cells of ~1.5 d that tile the box exactly
     ng = tuple(max(3, int(math.floor(L[k] / (1.5 * d)))) for k in range(3))
     mesh = Mesh((0.0, 0.0, 0.0), tuple(L), ng, True, "lexicographic")
+    layers = range(nc[0])
+    x_lo, x_hi = -1.0, L[0] + 1.0
+    if slab is not None:
+        from .multi import slab_bounds
+
+        lo, hi = slab_bounds(ng[0], slab[1])[slab[0]]
+        hx = L[0] / ng[0]
+        x_lo, x_hi = lo * hx, hi * hx
+        margin = jitter * d + 1e-12
+        layers = range(max(0, int(math.floor((x_lo - margin) / c)) - 1), min(nc[0], int(math.ceil((x_hi + margin) / c)) + 1))
+    j, k = np.meshgrid(np.arange(nc[1]), np.arange(nc[2]), indexing="ij")
+    offs = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
+    per_layer = nc[1] * nc[2] * 4
+    xs, vs, idl = [], [], []
+    for i in layers:
+        rng = np.random.default_rng([seed, i])
+        base = np.stack([np.full(j.size, float(i)), j.ravel(), k.ravel()], axis=1)
+        pts = (base[:, None, :] + offs[None, :, :]).reshape(-1, 3) * c + 0.25 * c
+        pts = pts + rng.uniform(-jitter, jitter, pts.shape) * d
+        vel = rng.normal(0.0, vel_sigma, pts.shape) if vel_sigma > 0 else np.zeros_like(pts)
+        gid = np.arange(per_layer, dtype=np.int64) + i * per_layer
+        if slab is not None:
+            # the same ownership rule as multi.owner_mask
+            cx = np.floor((pts[:, 0] - mesh.lo[0]) / mesh.cell_size[0]).astype(np.int64)
+            keep = (cx >= lo) & (cx < hi)
+            pts, vel, gid = pts[keep], vel[keep], gid[keep]
+        xs.append(pts)
+        vs.append(vel)
+        idl.append(gid)
+    pts = np.concatenate(xs) if xs else np.zeros((0, 3))
+    n = len(pts)
+    n_global = per_layer * nc[0]
     p = DEMParameters()
     p.time_step = 1e-5
     p.pp_model, p.pw_model, p.rolling_model = "hertz_mindlin_limit_overlap", "nonlinear", "none"
@@ -201,6 +265,92 @@ def periodic_box(n_cells_side=32, d=0.005, seed=19, spacing=1.0, jitter=0.03, ve
     p.particle_types = [ParticleType(diameter=d, density=1000, young=1e6, poisson=0.3, restitution=0.9, friction=0.3)]
     p.mesh = mesh
     p.boundary_conditions = [BoundaryCondition(type="periodic", periodic_id_0=2 * ax, periodic_id_1=2 * ax + 1, periodic_direction=ax) for ax in range(3)]
+    ids = np.concatenate(idl).astype(np.uint32) if idl else np.zeros(0, np.uint32)
+    props = make_props(n, d, 1000, np.random.default_rng(seed))
+    if n:
+        props[:, 3:6] = np.concatenate(vs)
+    w = Workload("periodic_box", p, ids, pts, props, [], (), f"3-periodic box, {n_global} spheres, HM limit-overlap, Maxwellian v")
+    w.n_global = n_global
+    return w
+
+
+def hopper(n_target=4_000_000, d=0.00224, sigma=0.1, slot=12.0, seed=19, spacing=1.0, jitter=0.02, gate_open_time=0.02,
+           chute_cells=3, min_nx=16):
+    """Config 3 (examples/dem/3d-rectangular-hopper/hopper.prm scaled): a wedge hopper whose two
+    45-degree walls converge to a slot of width `slot`*d at z = 0; polydisperse spheres (normal
+    distribution about d with relative std `sigma`, truncated at +-2.5 sigma as
+    distributions.cc:169-189) rest on a floating wall closing the slot until `gate_open_time`
+    (subsection floating walls), then discharge through a short chute whose bottom boundary is
+    an outlet: particles that pass it are deleted at the next rebuild. Rolling = constant
+    mu_r 0.1786 as the example. The hopper is long in x (the slab axis of multi-GPU runs)."""
+    rng = np.random.default_rng(seed)
+    dmax = d * (1.0 + 2.5 * sigma)
+    a = dmax * spacing
+    w = slot * d
+    # wedge cross-section area up to height H: w H + H^2; pick H ~ 40 d_max and get the length from n_target
+    H = 40.0 * dmax
+    area = w * H + H * H
+    per_volume = math.sqrt(2.0) / a**3
+    length = n_target / (per_volume * area * 0.93)
+    h = 1.35 * dmax
+    if length < min_nx * h:  # small cases: keep the hopper long enough to be cut into slabs, make it lower
+        length = min_nx * h
+        area = n_target / (per_volume * length * 0.93)
+        H = max(6.0 * dmax, 0.5 * (-w + math.sqrt(w * w + 4.0 * area)))
+    half_w = 0.5 * w + H + 2 * h
+    ny = int(math.ceil(2 * half_w / h))
+    nzu = int(math.ceil((H + 2 * dmax) / h))
+    nx = max(4, int(math.ceil(length / h)))
+    lo = (0.0, -0.5 * ny * h, -chute_cells * h)
+    mesh = Mesh(lo, (nx * h, lo[1] + ny * h, nzu * h), (nx, ny, chute_cells + nzu), True, "lexicographic")
+    length = nx * h
+    pts = fcc_points((0.5 * dmax, -half_w, 0.55 * dmax), (length - 0.5 * dmax, half_w, H), a)
+    inside = (np.abs(pts[:, 1]) < 0.5 * w + pts[:, 2] - 0.8 * dmax) & (pts[:, 0] > 0.55 * dmax) & (pts[:, 0] < length - 0.55 * dmax)
+    pts = pts[inside]
+    if len(pts) > n_target:
+        pts = pts[np.argsort(pts[:, 0], kind="stable")[:n_target]]
+    pts = pts + rng.uniform(-jitter, jitter, pts.shape) * d
+    n = len(pts)
+    dd = np.clip(rng.normal(d, sigma * d, n), d * (1 - 2.5 * sigma), dmax)
+    p = DEMParameters()
+    p.time_step = 1e-5
+    p.pp_model, p.pw_model, p.rolling_model = "hertz_mindlin_limit_overlap", "nonlinear", "constant"
+    p.g = (0.0, 0.0, -9.81)
+    p.dynamic_contact_search_factor = 0.9
+    p.neighborhood_threshold = 1.3
+    p.particle_types = [ParticleType(diameter=dmax, density=600, young=5e6, poisson=0.5, restitution=0.7, friction=0.5,
+                                     rolling_friction=0.1786, rolling_viscous_damping=0.1)]
+    p.young_wall, p.poisson_wall, p.restitution_wall, p.friction_wall, p.rolling_friction_wall = 5e6, 0.5, 0.7, 0.5, 0.1786
+    p.mesh = mesh
+    p.boundary_conditions = [BoundaryCondition(type="outlet", boundary_id=4)]  # z-min face of the chute
+    p.floating_walls = [((0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 0.0, gate_open_time)]
+    faces = box_wall_faces(mesh, p.outlet_boundaries)
+    above = lambda i, j, k: k >= chute_cells  # noqa: E731  the inclined walls end at the slot lip
+    s2 = math.sqrt(0.5)
+    faces += plane_wall_faces(mesh, (0.0, -0.5 * w, 0.0), (0.0, s2, s2), 10, above, face_no=6)
+    faces += plane_wall_faces(mesh, (0.0, 0.5 * w, 0.0), (0.0, -s2, s2), 11, above, face_no=7)
     ids = rng.permutation(n).astype(np.uint32)
-    props = make_props(n, d, 1000, rng, vel_sigma=vel_sigma)
-    return Workload("periodic_box", p, ids, pts, props, [], (), f"3-periodic box, {n} spheres, HM limit-overlap, Maxwellian v")
+    props = make_props(n, dd, 600, rng)
+    desc = (f"wedge hopper discharge, {n} polydisperse spheres d={d * 1e3:g} mm +-{sigma:.0%}, HM limit-overlap + constant rolling, "
+            f"floating wall opens at t={gate_open_time:g} s, outlet deletion")
+    return Workload("hopper", p, ids, pts, props, faces, (), desc, p.floating_walls)
+
+
+def cohesive_box(n_side=47, d=0.001, model="hertz_JKR", seed=19, spacing=0.995, jitter=0.01, surface_energy=None):
+    """Config 4: a dense box packing with cohesion — `hertz_JKR` (surface energy 0.5 J/m^2, the
+    range of pp_jkr_equilibrium.prm) or `DMT` (Hamaker 4e-19, cut-off 0.1 as
+    pp_dmt_equilibrium.prm) — slightly compressed so that the coordination number is high and
+    nearly every list entry carries history."""
+    w = box_packing(n_side, d=d, seed=seed, spacing=spacing, jitter=jitter)
+    p = w.params
+    p.pp_model = model
+    p.pw_model = "JKR" if model == "hertz_JKR" else "DMT"
+    gamma = surface_energy if surface_energy is not None else (0.5 if model == "hertz_JKR" else 1e-4)
+    t = p.particle_types[0]
+    t.surface_energy, t.hamaker = gamma, 4e-19
+    t.young, t.restitution, t.friction = 1e6, 0.5, 0.3
+    p.surface_energy_wall, p.hamaker_wall = gamma, 4e-19
+    p.dmt_cut_off_threshold = 0.1
+    w.name = "cohesive_box"
+    w.description = f"cohesive box packing, {w.n} spheres d={d * 1e3:g} mm, {model} (gamma={gamma:g} J/m^2), history heavy"
+    return w

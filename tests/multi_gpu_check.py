@@ -72,7 +72,7 @@ def run_case(name, w, checkpoints, rank, world, local_rank, tol=(1e-9, 1e-6)):
                   f"pairs={len(pairs)} same_pairs={same_pairs} slab-vs-oracle dx={ex:.2e} dF={ef:.2e} dT={et:.2e} | "
                   f"1gpu-vs-oracle dx={sx_err:.2e} dF={sf_err:.2e}", flush=True)
             if k == 0:  # the bar: short horizon (trajectories are chaotic, BASELINE north_star)
-                ok &= same_pairs and ex < tol[0] and ef < tol[1] and all(r == o.get_stats().n_rebuilds for r in rebuilds)
+                ok &= same_pairs and ex < tol[0] and ef < tol[1] and et < tol[1] and all(r == o.get_stats().n_rebuilds for r in rebuilds)
         done = steps
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
@@ -85,14 +85,24 @@ def main():
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ok = True
-    # non-periodic axis: a short drum (walls, rotating boundary, gravity)
+    # non-periodic axis: a short drum (walls, rotating boundary, gravity, constant rolling).
+    # The spheres get random initial angular velocities: constant rolling resistance acts along
+    # omega_ij / |omega_ij| (rolling_resistance_torque_models.h:64), which for spheres that all
+    # start at rest is the direction of a rounding-level vector — a noise amplifier in the
+    # reference too, and not what this check is about.
     w = workloads.drum(n_target=30000, radius=0.03, spacing=1.0, jitter=0.02)
+    w.props[:, 6:9] = np.random.default_rng(5).normal(0.0, 5.0, (w.n, 3))
     w.params.dynamic_contact_search_factor = 0.1
-    ok &= run_case("drum", w, (10, 20, 40, 80), rank, world, local_rank)
+    ok &= run_case("drum", w, (10, 40), rank, world, local_rank, tol=(1e-11, 1e-8))
     # periodic axis: particles migrate across slabs and wrap around
     w = workloads.periodic_box(cells=(12, 6, 6), spacing=1.0, jitter=0.03, vel_sigma=0.5)
     w.params.dynamic_contact_search_factor = 0.1
-    ok &= run_case("periodic", w, (30, 120), rank, world, local_rank)
+    ok &= run_case("periodic", w, (30, 120), rank, world, local_rank, tol=(1e-13, 1e-10))
+    # polydisperse hopper: floating wall that opens during the run, outlet deletion at rebuilds
+    w = workloads.hopper(n_target=20000, gate_open_time=0.0003)
+    w.props[:, 6:9] = np.random.default_rng(6).normal(0.0, 5.0, (w.n, 3))
+    w.params.dynamic_contact_search_factor = 0.1
+    ok &= run_case("hopper", w, (20, 60), rank, world, local_rank, tol=(1e-11, 1e-8))
     dist.destroy_process_group()
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)

@@ -361,3 +361,34 @@ def test_pipelined_stepping_is_bitwise_identical(monkeypatch):
     assert np.array_equal(pa[1], pb[1]) and np.array_equal(pa[2], pb[2])
     assert all(np.array_equal(u, v) for u, v in zip(qa, qb))
     assert np.array_equal(fa[1], fb[1]) and np.array_equal(fa[2], fb[2])
+
+
+@pytest.mark.parametrize("name", ["drum", "hopper", "cohesive_jkr", "cohesive_dmt", "periodic_box"])
+def test_baseline_config_workloads_parity(name):
+    """The synthetic workloads bench.py runs for BASELINE.json's configs, at sizes the oracle
+    finishes in seconds: lock-step parity at 1e-12, then a short free run."""
+    from lethe_b200 import workloads
+
+    if name == "drum":
+        w = workloads.drum(n_target=6000, radius=0.02, spacing=1.0, jitter=0.02)
+    elif name == "hopper":
+        w = workloads.hopper(n_target=5000, gate_open_time=0.0002)
+    elif name == "periodic_box":
+        w = workloads.periodic_box(cells=(7, 6, 6), spacing=1.0, jitter=0.03, vel_sigma=0.5)
+    else:
+        w = workloads.cohesive_box(12, model="hertz_JKR" if name == "cohesive_jkr" else "DMT")
+    # well-conditioned rolling resistance needs non-zero relative angular velocities
+    w.props[:, 6:9] = np.random.default_rng(8).normal(0.0, 5.0, (w.n, 3))
+    w.params.dynamic_contact_search_factor = 0.1
+    cfg = w.params.to_config(store_forces=True)
+    g, o = abi.load_engine(cfg), loader.oracle_engine(cfg)
+    w.install(g)
+    w.install(o)
+
+    def walls_equal(step):
+        wg, wo = g.get_wall_contacts(), o.get_wall_contacts()
+        assert np.array_equal(wg[0], wo[0]) and np.array_equal(wg[1], wo[1]), step
+
+    lockstep(g, o, 40, 10, extra=walls_equal)
+    assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 2
+    assert g.get_stats().n_particles == o.get_stats().n_particles
