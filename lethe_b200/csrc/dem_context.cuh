@@ -140,6 +140,13 @@ struct lethe_dem_ctx
   DevBuf<uint32_t> ghost_start[2], ghost_end[2];
   uint32_t n_ghost_run[2] = {0, 0};
 
+  // multi-GPU rebuild in progress: first input index of the particles that immigrated in it
+  // (0xffffffff: none) and the contact history that came with them (dem_multi.cu)
+  uint32_t first_immigrant = 0xffffffffu;
+  DevBuf<dem::HistRecord> pay;
+  DevBuf<uint32_t> pay_start;
+  uint32_t n_pay = 0;
+
   // lists (double-buffered across rebuilds: the old one is the history source)
   ListBufs lists[2];
   WallListBufs wlists[2];

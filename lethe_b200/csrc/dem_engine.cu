@@ -288,7 +288,9 @@ namespace
     if (c->slot_map_size)
       launch_fill_u32(c->slot_of_id.p, 0xffffffffu, c->slot_map_size, s);
     GatherParams gp{src.view(), dst.view(), src.id.p,       dst.id.p,       c->perm.p, c->key.p,
-                    c->cell_of_rank.p, dst.cell_reg.p,      c->old_of_new.p, c->disp.p, c->slot_of_id.p, n_new};
+                    c->cell_of_rank.p, dst.cell_reg.p,      c->old_of_new.p, c->disp.p, c->slot_of_id.p, n_new,
+                    c->first_immigrant, c->lists[c->cur_list].n_rows, c->slot_map_size_old ? c->slot_of_id_old.p : nullptr,
+                    c->slot_map_size_old};
     launch_gather(gp, s);
     c->cur ^= 1;
     c->old_n_owned = c->lists[c->cur_list].n_rows;
@@ -336,6 +338,8 @@ namespace
     np.counts = c->counts.p;
     np.use_roll = use_roll;
     np.use_img = use_img;
+    HistPayload pay{c->n_pay ? c->pay.p : nullptr, c->pay_start.p, c->n_pay, c->slot_map_size, stn.id.p};
+    np.pay = pay;
     launch_count_neighbors(np, s);
     exclusive_scan_u32(c->counts.p, newl.row_start.p, size_t(n_new) + 1, c->scan_tmp.p, s);
     const uint32_t n_entries = n_new ? read_u32(c, newl.row_start.p + n_new) : 0;
@@ -370,6 +374,7 @@ namespace
     wp.new_list = neww.view();
     wp.counts = c->counts.p;
     wp.use_roll = use_roll;
+    wp.pay = pay;
     launch_count_walls(wp, s);
     exclusive_scan_u32(c->counts.p, neww.row_start.p, size_t(n_new) + 1, c->scan_tmp.p, s);
     const uint32_t n_wall = n_new ? read_u32(c, neww.row_start.p + n_new) : 0;

@@ -200,7 +200,12 @@ namespace dem
       const uint32_t pid = P.id_in[o];
       P.id_out[q] = pid;
       P.cell_reg_out[q] = P.cell_of_rank[P.key[o]];
-      P.old_of_new[q] = o;
+      uint32_t old = o;
+      if (o >= P.first_immigrant)
+        old = (P.old_slot_of_id && pid < P.old_map_size) ? P.old_slot_of_id[pid] : 0xffffffffu;
+      else if (o >= P.n_listed)
+        old = 0xffffffffu; // inserted after the outgoing list was built: no history anywhere
+      P.old_of_new[q] = old;
       P.disp[q] = 0.0;
       P.slot_of_id[pid] = q;
     }
@@ -334,33 +339,75 @@ namespace dem
           o0 = P.old_list.row_start[old_q];
           o1 = P.old_list.row_start[old_q + 1];
         }
+      const uint32_t qid = P.pay.rec ? P.pay.id[q] : 0u;
       for_each_neighbor(P, q, [&](uint32_t r, uint32_t img) {
         uint32_t word = r;
-        if (have_old)
-          {
-            const uint32_t old_r = P.old_of_new[r];
-            // a pair only keeps its history inside the same container: local-local vs local-ghost
-            // (the reference starts from zero when a partner changes ownership,
-            // update_fine_search_candidates.cc:136-152)
-            const bool same_class = old_r != 0xffffffffu && ((old_r < P.old_n_owned) == (r < P.n_rows));
-            for (uint32_t eo = o0; eo < o1 && same_class; ++eo)
-              {
-                const uint32_t oc = P.old_list.col[eo];
-                if ((oc & COL_INDEX_MASK) != old_r)
-                  continue;
-                // history only survives inside the same container (periodic vs not)
-                const bool old_periodic = P.use_img ? (P.old_list.img[eo] != 0) : false;
-                if (old_periodic != (img != 0))
-                  continue;
-                if (oc & COL_HIST_BIT)
-                  {
-                    word |= COL_HIST_BIT;
+        const uint32_t old_r = (!P.clear_history && P.old_of_new) ? P.old_of_new[r] : 0xffffffffu;
+        bool found = false;
+        // The history of a pair follows the pair, whichever rank evaluates it (the reference
+        // restarts it from zero when a partner changes owner, update_fine_search_candidates.cc:
+        // 136-152; here an N-GPU run reproduces the single-domain one instead).
+        // (1) my own old row: the partner may have been owned or a ghost then
+        if (have_old && old_r != 0xffffffffu)
+          for (uint32_t eo = o0; eo < o1; ++eo)
+            {
+              const uint32_t oc = P.old_list.col[eo];
+              if ((oc & COL_INDEX_MASK) != old_r)
+                continue;
+              // history only survives inside the same container (periodic vs not)
+              const bool old_periodic = P.use_img ? (P.old_list.img[eo] != 0) : false;
+              if (old_periodic != (img != 0))
+                continue;
+              found = true;
+              if (oc & COL_HIST_BIT)
+                {
+                  word |= COL_HIST_BIT;
+                  for (int d = 0; d < 3; ++d)
+                    P.new_list.hist[3 * size_t(e) + d] = P.old_list.hist[3 * size_t(eo) + d];
+                  if (P.use_roll)
                     for (int d = 0; d < 3; ++d)
-                      P.new_list.hist[3 * size_t(e) + d] = P.old_list.hist[3 * size_t(eo) + d];
-                    if (P.use_roll)
-                      for (int d = 0; d < 3; ++d)
-                        P.new_list.roll[3 * size_t(e) + d] = P.old_list.roll[3 * size_t(eo) + d];
-                  }
+                      P.new_list.roll[3 * size_t(e) + d] = P.old_list.roll[3 * size_t(eo) + d];
+                }
+              break;
+            }
+        // (2) I immigrated and was a ghost here: the partner's old row holds this rank's copy of
+        // the pair, in the opposite orientation
+        if (!found && !have_old && !P.clear_history && old_q != 0xffffffffu && old_r != 0xffffffffu && old_r < P.n_old_rows)
+          for (uint32_t eo = P.old_list.row_start[old_r]; eo < P.old_list.row_start[old_r + 1]; ++eo)
+            {
+              const uint32_t oc = P.old_list.col[eo];
+              if ((oc & COL_INDEX_MASK) != old_q)
+                continue;
+              const bool old_periodic = P.use_img ? (P.old_list.img[eo] != 0) : false;
+              if (old_periodic != (img != 0))
+                continue;
+              found = true;
+              if (oc & COL_HIST_BIT)
+                {
+                  word |= COL_HIST_BIT;
+                  for (int d = 0; d < 3; ++d)
+                    P.new_list.hist[3 * size_t(e) + d] = -P.old_list.hist[3 * size_t(eo) + d];
+                  if (P.use_roll)
+                    for (int d = 0; d < 3; ++d)
+                      P.new_list.roll[3 * size_t(e) + d] = -P.old_list.roll[3 * size_t(eo) + d];
+                }
+              break;
+            }
+        // (3) I immigrated and the pair lived on the rank I came from: its history came with me
+        if (!found && !have_old && !P.clear_history && P.pay.rec && qid < P.pay.map_size)
+          {
+            const uint32_t rid = P.pay.id[r];
+            for (uint32_t k = P.pay.start[qid]; k < P.pay.n && P.pay.rec[k].qid == qid; ++k)
+              {
+                const HistRecord &rec = P.pay.rec[k];
+                if (rec.rid != rid || (rec.flags & HIST_REC_WALL) || ((rec.flags & HIST_REC_PERIODIC) != 0) != (img != 0))
+                  continue;
+                word |= COL_HIST_BIT;
+                for (int d = 0; d < 3; ++d)
+                  P.new_list.hist[3 * size_t(e) + d] = rec.h[d];
+                if (P.use_roll)
+                  for (int d = 0; d < 3; ++d)
+                    P.new_list.roll[3 * size_t(e) + d] = rec.roll[d];
                 break;
               }
           }
@@ -435,6 +482,25 @@ namespace dem
                 if (P.use_roll)
                   for (int d = 0; d < 3; ++d)
                     P.new_list.roll[3 * size_t(e) + d] = P.old_list.roll[3 * size_t(eo) + d];
+              }
+          }
+        if (!found && !have_old && !P.clear_history && P.pay.rec && P.pay.id[q] < P.pay.map_size)
+          {
+            // the (particle, face) contact_info of an immigrant came with it
+            const uint32_t qid = P.pay.id[q];
+            for (uint32_t k = P.pay.start[qid]; k < P.pay.n && P.pay.rec[k].qid == qid; ++k)
+              {
+                const HistRecord &rec = P.pay.rec[k];
+                if (!(rec.flags & HIST_REC_WALL) || rec.rid != key)
+                  continue;
+                found = true;
+                word |= WALL_HIST_BIT | ((rec.flags & HIST_REC_FLIPPED) ? WALL_FLIPPED_BIT : 0u);
+                for (int d = 0; d < 3; ++d)
+                  P.new_list.hist[3 * size_t(e) + d] = rec.h[d];
+                if (P.use_roll)
+                  for (int d = 0; d < 3; ++d)
+                    P.new_list.roll[3 * size_t(e) + d] = rec.roll[d];
+                break;
               }
           }
         if (!found && (key & WALL_FLOATING_BIT))
@@ -654,6 +720,7 @@ namespace dem
           r.omg = P.omg[p];
           P.send_rec[dir][k] = r;
           P.send_id[dir][k] = P.id[p];
+          P.send_slot[dir][k] = p;
         }
       P.cell_reg[p] = -2;
     }
@@ -746,15 +813,12 @@ namespace dem
           if (k + 1 == P.n || next != rank)
             P.end[rank] = q + 1;
         }
-      // history source: the ghost's slot in the previous list generation (ghost -> ghost only)
+      // history source: the particle's slot in the previous list generation, whether it was a
+      // ghost here already or an owned particle that has just emigrated
       uint32_t old = 0xffffffffu;
       const uint32_t pid = P.id[q];
       if (P.old_slot_of_id && pid < P.old_map_size)
-        {
-          const uint32_t o = P.old_slot_of_id[pid];
-          if (o != 0xffffffffu && o >= P.old_n_owned)
-            old = o;
-        }
+        old = P.old_slot_of_id[pid];
       P.old_of_new[q] = old;
     }
 
@@ -900,6 +964,98 @@ namespace dem
       k_pack_all_rows<<<blocks_for(n, 256), 256, 0, s>>>(st, id, n, ids_out, x3, props9);
       count_launch();
   }
+  namespace
+  {
+    template <bool PACK> __global__ void __launch_bounds__(128) k_hist_rows(const __grid_constant__ HistPackParams P)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= P.n)
+        return;
+      const uint32_t p = P.send_slot[k];
+      uint32_t n = 0;
+      const uint32_t base = PACK ? P.counts[k] : 0u;
+      const uint32_t qid = P.id[p];
+      if (p < P.n_rows)
+        for (uint32_t e = P.list.row_start[p]; e < P.list.row_start[p + 1]; ++e)
+          {
+            const uint32_t c = P.list.col[e];
+            if (!(c & COL_HIST_BIT))
+              continue;
+            if (PACK)
+              {
+                HistRecord r;
+                r.qid = qid;
+                r.rid = P.id[c & COL_INDEX_MASK];
+                r.flags = (P.use_img && P.list.img[e]) ? HIST_REC_PERIODIC : 0u;
+                r.pad = 0;
+                for (int d = 0; d < 3; ++d)
+                  {
+                    r.h[d] = P.list.hist[3 * size_t(e) + d];
+                    r.roll[d] = P.use_roll ? P.list.roll[3 * size_t(e) + d] : 0.0;
+                  }
+                P.out[base + n] = r;
+              }
+            ++n;
+          }
+      if (p < P.n_wall_rows)
+        for (uint32_t w = P.walls.row_start[p]; w < P.walls.row_start[p + 1]; ++w)
+          {
+            const uint32_t we = P.walls.entry[w];
+            if (!(we & WALL_HIST_BIT))
+              continue;
+            if (PACK)
+              {
+                HistRecord r;
+                r.qid = qid;
+                r.rid = we & (WALL_FLOATING_BIT | WALL_INDEX_MASK);
+                r.flags = HIST_REC_WALL | ((we & WALL_FLIPPED_BIT) ? HIST_REC_FLIPPED : 0u);
+                r.pad = 0;
+                for (int d = 0; d < 3; ++d)
+                  {
+                    r.h[d] = P.walls.hist[3 * size_t(w) + d];
+                    r.roll[d] = P.use_roll ? P.walls.roll[3 * size_t(w) + d] : 0.0;
+                  }
+                P.out[base + n] = r;
+              }
+            ++n;
+          }
+      if (!PACK)
+        P.counts[k] = n;
+    }
+    __global__ void __launch_bounds__(256) k_hist_index(const HistRecord *rec, uint32_t n, uint32_t *pay_start, uint32_t map_size)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t qid = rec[k].qid;
+      if ((k == 0 || rec[k - 1].qid != qid) && qid < map_size)
+        pay_start[qid] = k;
+    }
+  } // namespace
+  void launch_hist_count(const HistPackParams &p, cudaStream_t s)
+  {
+    if (p.n)
+      {
+        k_hist_rows<false><<<blocks_for(p.n, 128), 128, 0, s>>>(p);
+        count_launch();
+      }
+  }
+  void launch_hist_pack(const HistPackParams &p, cudaStream_t s)
+  {
+    if (p.n)
+      {
+        k_hist_rows<true><<<blocks_for(p.n, 128), 128, 0, s>>>(p);
+        count_launch();
+      }
+  }
+  void launch_hist_index(const HistRecord *rec, uint32_t n, uint32_t *pay_start, uint32_t map_size, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_hist_index<<<blocks_for(n, 256), 256, 0, s>>>(rec, n, pay_start, map_size);
+        count_launch();
+      }
+  }
   void launch_classify(const ClassifyParams &p, cudaStream_t s)
   {
     if (p.n)
@@ -938,7 +1094,7 @@ namespace dem
     __global__ void k_prepare_flag(uint32_t *w, uint32_t host_bits, int consult) { w[2] = (consult ? w[0] : 0u) | host_bits; }
 
     __global__ void __launch_bounds__(32) k_agree(uint64_t *const *peer_mailbox, uint64_t *my_mailbox, int rank, int world, uint32_t seq,
-                                                  uint32_t *flag_words, uint32_t host_bits, int consult)
+                                                  uint32_t *flag_words, uint32_t host_bits, int consult, uint32_t *host_out)
     {
       const int lane = threadIdx.x;
       const uint32_t word = (consult ? flag_words[0] : 0u) | host_bits;
@@ -972,13 +1128,16 @@ namespace dem
       for (int o = 16; o; o >>= 1)
         got = max(got, __shfl_xor_sync(0xffffffffu, got, o));
       if (lane == 0)
-        flag_words[1] = got;
+        {
+          flag_words[1] = got;
+          *reinterpret_cast<volatile uint32_t *>(host_out) = got;
+        }
     }
   } // namespace
   void launch_agree(uint64_t *const *peer_mailbox, uint64_t *my_mailbox, int rank, int world, uint32_t seq, uint32_t *flag_words,
-                    uint32_t host_bits, int consult, cudaStream_t s)
+                    uint32_t host_bits, int consult, uint32_t *host_out, cudaStream_t s)
   {
-    k_agree<<<1, 32, 0, s>>>(peer_mailbox, my_mailbox, rank, world, seq, flag_words, host_bits, consult);
+    k_agree<<<1, 32, 0, s>>>(peer_mailbox, my_mailbox, rank, world, seq, flag_words, host_bits, consult, host_out);
     count_launch();
   }
   void launch_halo_warp_table(const uint32_t *flags, const uint32_t *offsets, uint32_t n, uint32_t *bits, uint32_t *prefix,

@@ -186,6 +186,13 @@ namespace dem
     double *disp;
     uint32_t *slot_of_id;
     uint32_t n_new;
+    // multi-GPU: particles at input index >= first_immigrant arrived from a neighbouring rank in
+    // this rebuild; their "old" index is the ghost slot they had here (or none), looked up in
+    // the id map of the outgoing list generation
+    uint32_t first_immigrant; // 0xffffffff: none
+    uint32_t n_listed;        // rows of the outgoing list: input indices in [n_listed, first_immigrant) were inserted since
+    const uint32_t *old_slot_of_id;
+    uint32_t old_map_size;
   };
   void launch_gather(const GatherParams &p, cudaStream_t s);
 
@@ -193,6 +200,43 @@ namespace dem
   struct MigrateRecord
   {
     double4 pos, vel, omg;
+  };
+  // Contact history that travels with a migrating particle (SURVEY.md §8e "variable payload incl.
+  // history rows"): one record per touching entry of its particle-particle row and of its wall
+  // row, so that a pair keeps its tangential displacement whichever rank ends up evaluating it
+  // and an N-GPU run reproduces the single-domain one.
+  struct HistRecord
+  {
+    uint32_t qid;   // id of the migrating particle
+    uint32_t rid;   // partner id, or the wall key (WALL_FLOATING_BIT | index) of a wall record
+    uint32_t flags; // HIST_REC_*
+    uint32_t pad;
+    double h[3];    // tangential displacement in the orientation qid -> rid
+    double roll[3]; // EPSD rolling spring torque (zero otherwise)
+  };
+  constexpr uint32_t HIST_REC_PERIODIC = 1u, HIST_REC_WALL = 2u, HIST_REC_FLIPPED = 4u;
+  struct HistPackParams
+  {
+    const uint32_t *send_slot; // emigrants of one direction: slot in the (pre-sort) particle arrays
+    uint32_t n;
+    const uint32_t *id;        // [owned + ghost] ids of the pre-sort arrangement
+    ListView list;
+    WallListView walls;
+    uint32_t n_rows, n_wall_rows;
+    int use_roll, use_img;
+    uint32_t *counts;          // [n + 1] (count pass) / exclusive offsets (pack pass)
+    HistRecord *out;
+  };
+  void launch_hist_count(const HistPackParams &p, cudaStream_t s);
+  void launch_hist_pack(const HistPackParams &p, cudaStream_t s);
+  // pay_start[qid] = first record of qid (records of one particle are contiguous)
+  void launch_hist_index(const HistRecord *rec, uint32_t n, uint32_t *pay_start, uint32_t map_size, cudaStream_t s);
+  struct HistPayload
+  {
+    const HistRecord *rec; // nullptr: nothing arrived
+    const uint32_t *start; // by particle id, 0xffffffff = none
+    uint32_t n, map_size;
+    const uint32_t *id;    // ids of the new arrangement (owned + ghost)
   };
   // classify owned particles against the slab [slab_lo, slab_hi) along grid.slab_axis after the
   // periodic wrap; movers are appended to send buffers (dir 0 = lower neighbour, 1 = upper) and
@@ -207,6 +251,7 @@ namespace dem
     uint32_t n;
     MigrateRecord *send_rec[2];
     uint32_t *send_id[2];
+    uint32_t *send_slot[2];
     uint32_t *send_count; // [2] + [2] = far movers (error)
     uint32_t send_cap;
   };
@@ -224,11 +269,12 @@ namespace dem
   // Per-step agreement over peer memory (the logical_or of find_contact_detection_step.cc:53-58
   // without a library collective): every rank stores (seq, its word) into slot `rank` of every
   // rank's mailbox (system-scope release), waits until its own mailbox holds `seq` from all
-  // `world` ranks (acquire) and writes the maximum to flag_words[1]. mailbox layout:
+  // `world` ranks (acquire) and writes the maximum to flag_words[1] and to `host_out` (mapped
+  // pinned memory the host reads after the event behind this kernel: no copy engine in the step). mailbox layout:
   // [parity of seq][world] u64 = seq << 32 | word. A rank that waits longer than ~2 min writes
   // 0xffffffff (the host turns that into an error instead of a hung GPU).
   void launch_agree(uint64_t *const *peer_mailbox, uint64_t *my_mailbox, int rank, int world, uint32_t seq, uint32_t *flag_words,
-                    uint32_t host_bits, int consult, cudaStream_t s);
+                    uint32_t host_bits, int consult, uint32_t *host_out, cudaStream_t s);
   void launch_gather_state(StateView st, const uint32_t *idx, uint32_t n, double4 *pos, double4 *vel, double4 *omg,
                            cudaStream_t s);
   void launch_gather_ids(const uint32_t *id, const uint32_t *idx, uint32_t n, uint32_t *out, cudaStream_t s);
@@ -274,6 +320,7 @@ namespace dem
     ListView new_list;
     uint32_t *counts; // [n_rows+1]
     int use_roll, use_img;
+    HistPayload pay; // history that arrived with immigrants
   };
   void launch_count_neighbors(const NeighborParams &p, cudaStream_t s);
   void launch_fill_neighbors(const NeighborParams &p, cudaStream_t s);
@@ -295,6 +342,7 @@ namespace dem
     WallListView new_list;
     uint32_t *counts;
     int use_roll;
+    HistPayload pay;
   };
   void launch_count_walls(const WallBuildParams &p, cudaStream_t s);
   void launch_fill_walls(const WallBuildParams &p, cudaStream_t s);

@@ -86,7 +86,9 @@ namespace dem
     int peer[2] = {-1, -1}; // lower / upper neighbour rank or -1
     // migration buffers
     DevBuf<MigrateRecord> send_rec[2], recv_rec[2];
-    DevBuf<uint32_t> send_id[2], recv_id[2];
+    DevBuf<uint32_t> send_id[2], recv_id[2], send_slot[2];
+    DevBuf<HistRecord> send_hist[2]; // contact history of the emigrants (HistRecord)
+    DevBuf<uint32_t> hist_offsets[2];
     DevBuf<uint32_t> counters; // [4] device
     DevBuf<uint32_t> xcount;   // [4] device: counts exchanged with the peers
     // halo: indices of my boundary-layer particles per direction + packed send buffers
@@ -121,7 +123,8 @@ namespace dem
     DevBuf<uint64_t *> peer_mailbox;
     std::vector<void *> mailbox_maps;
     uint32_t agree_seq = 0;
-    uint32_t *agreed_host = nullptr;                       // pinned [2]
+    uint32_t *agreed_host = nullptr;                       // mapped pinned [2]
+    uint32_t *agreed_host_dev = nullptr;                   // its device alias
     cudaEvent_t agreed_ev[2] = {nullptr, nullptr};
     int agreed_slot = 0;
   };
@@ -185,8 +188,9 @@ namespace dem
       m->want_mailbox = false;
     if (m->want_fused)
       {
-        CU_TRY(cudaHostAlloc(&m->agreed_host, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+        CU_TRY(cudaHostAlloc(&m->agreed_host, 2 * sizeof(uint32_t), cudaHostAllocMapped));
         m->agreed_host[0] = m->agreed_host[1] = 0;
+        CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&m->agreed_host_dev), m->agreed_host, 0));
         for (auto &ev : m->agreed_ev)
           CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         m->info_dev.ensure(4 * sizeof(HaloInfo));
@@ -519,15 +523,16 @@ namespace dem
   {
     MultiGpuImpl *m = impl;
     cudaStream_t s = c->stream;
+    m->agreed_slot ^= 1;
     if (m->mailbox_ready)
-      launch_agree(m->peer_mailbox.p, m->mailbox, m->rank, m->world, ++m->agree_seq, c->flag_dev.p, host_bits, consult ? 1 : 0, s);
+      launch_agree(m->peer_mailbox.p, m->mailbox, m->rank, m->world, ++m->agree_seq, c->flag_dev.p, host_bits, consult ? 1 : 0,
+                   m->agreed_host_dev + m->agreed_slot, s);
     else
       {
         launch_prepare_flag(c->flag_dev.p, host_bits, consult ? 1 : 0, s);
         NCCL_TRY(g_nccl.AllReduce(c->flag_dev.p + 2, c->flag_dev.p + 1, 1, ncclUint32, ncclMax, m->comm, s));
+        CU_TRY(cudaMemcpyAsync(m->agreed_host + m->agreed_slot, c->flag_dev.p + 1, 4, cudaMemcpyDeviceToHost, s));
       }
-    m->agreed_slot ^= 1;
-    CU_TRY(cudaMemcpyAsync(m->agreed_host + m->agreed_slot, c->flag_dev.p + 1, 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaEventRecord(m->agreed_ev[m->agreed_slot], s));
   }
 
@@ -599,6 +604,7 @@ namespace dem
       {
         m->send_rec[d].ensure(cap);
         m->send_id[d].ensure(cap);
+        m->send_slot[d].ensure(cap);
       }
     CU_TRY(cudaMemsetAsync(m->counters.p, 0, 32, s));
     StateBufs &st = c->st[c->cur];
@@ -614,6 +620,7 @@ namespace dem
       {
         cp.send_rec[d] = m->send_rec[d].p;
         cp.send_id[d] = m->send_id[d].p;
+        cp.send_slot[d] = m->send_slot[d].p;
       }
     cp.send_count = m->counters.p;
     cp.send_cap = cap;
@@ -647,7 +654,58 @@ namespace dem
         }
     });
     NCCL_TRY(g_nccl.GroupEnd());
+
+    // ---- 1b. the contact history of the emigrants travels with them ----
+    {
+      const bool use_roll = c->cfg.rolling_model == LETHE_ROLLING_EPSD;
+      const bool use_img = c->grid.periodic[0] || c->grid.periodic[1] || c->grid.periodic[2];
+      ListBufs &l = c->lists[c->cur_list];
+      WallListBufs &wl = c->wlists[c->cur_list];
+      uint32_t h_send[2] = {0, 0}, h_recv[2] = {0, 0};
+      HistPackParams hp[2];
+      for (int d = 0; d < 2; ++d)
+        {
+          if (!n_send[d])
+            continue;
+          m->hist_offsets[d].ensure(size_t(n_send[d]) + 2);
+          c->scan_tmp.ensure(scan_tmp_elems(size_t(n_send[d]) + 8));
+          hp[d] = HistPackParams{m->send_slot[d].p, n_send[d], st.id.p, l.view(), wl.view(), l.n_rows, wl.n_rows,
+                                 use_roll ? 1 : 0, use_img ? 1 : 0, m->hist_offsets[d].p, nullptr};
+          launch_hist_count(hp[d], s);
+          exclusive_scan_u32(m->hist_offsets[d].p, m->hist_offsets[d].p, size_t(n_send[d]) + 1, c->scan_tmp.p, s);
+          CU_TRY(cudaMemcpyAsync(&h_send[d], m->hist_offsets[d].p + n_send[d], 4, cudaMemcpyDeviceToHost, s));
+        }
+      CU_TRY(cudaStreamSynchronize(s));
+      for (int d = 0; d < 2; ++d)
+        if (h_send[d])
+          {
+            m->send_hist[d].ensure(h_send[d]);
+            hp[d].out = m->send_hist[d].p;
+            launch_hist_pack(hp[d], s);
+          }
+      exchange_counts(c, m, h_send, h_recv);
+      c->n_pay = h_recv[0] + h_recv[1];
+      if (c->n_pay)
+        c->pay.ensure(c->n_pay);
+      NCCL_TRY(g_nccl.GroupStart());
+      for_each_direction_pair(m, [&](int ds, int dr) {
+        if (m->peer[ds] >= 0 && h_send[ds])
+          NCCL_TRY(g_nccl.Send(m->send_hist[ds].p, size_t(h_send[ds]) * sizeof(HistRecord), ncclUint8, m->peer[ds], m->comm, s));
+        if (m->peer[dr] >= 0 && h_recv[dr])
+          NCCL_TRY(g_nccl.Recv(c->pay.p + (dr == 1 ? h_recv[0] : 0), size_t(h_recv[dr]) * sizeof(HistRecord), ncclUint8, m->peer[dr],
+                               m->comm, s));
+      });
+      NCCL_TRY(g_nccl.GroupEnd());
+      if (c->n_pay)
+        {
+          c->pay_start.ensure(std::max<size_t>(c->slot_map_size, 1));
+          launch_fill_u32(c->pay_start.p, 0xffffffffu, c->slot_map_size, s);
+          launch_hist_index(c->pay.p, c->n_pay, c->pay_start.p, c->slot_map_size, s);
+        }
+    }
+
     const uint32_t n_in = n_recv[0] + n_recv[1];
+    c->first_immigrant = n0;
     if (n_in)
       {
         const size_t total = size_t(n0) + n_in;
@@ -667,6 +725,7 @@ namespace dem
 
     // ---- 2. local sort (drops the particles sent away) ----
     engine_rebuild_sort(c);
+    c->first_immigrant = 0xffffffffu;
 
     // ---- 3. ghost exchange: my boundary cell layers -> neighbours ----
     const uint32_t n = c->n_owned;
@@ -756,6 +815,7 @@ namespace dem
 
     // ---- 5. lists ----
     engine_rebuild_lists(c);
+    c->n_pay = 0;
     engine_mirror_ids(c);
     if (c->timers_enabled)
       {

@@ -40,7 +40,7 @@ def case(name, w, steps, rank, world, local_rank):
             bad = np.argsort(-np.maximum(err, terr))[:6]
             h = w.params.mesh.cell_size[0]
             cut = w.params.mesh.lo[0] + objs[0][4][2] * h
-            print(f"[{name}] steps={s} dx={np.abs(gx - ox).max() / np.abs(ox).max():.2e} dF={err.max():.2e} dT={terr.max():.2e} "
+            print(f"[{name}] rebuilds={eng.get_stats().n_rebuilds}/{o.get_stats().n_rebuilds} n={len(gid)}/{len(oid)} steps={s} dx={np.abs(gx - ox).max() / np.abs(ox).max():.2e} dF={err.max():.2e} dT={terr.max():.2e} "
                   f"n_bad(F>1e-9)={(err > 1e-9).sum()} n_bad(T>1e-9)={(terr > 1e-9).sum()} cut_x={cut:.5f} h={h:.5f}", flush=True)
             for b in bad:
                 r = np.hypot(ox[b, 1], ox[b, 2])
@@ -61,13 +61,9 @@ def main():
             setattr(w.params, k, v)
         return w
 
-    case("drum", drum(), (1, 2, 5), rank, world, local_rank)
-    case("drum-noroll", drum(rolling_model="none"), (1, 2, 5), rank, world, local_rank)
     w = drum()
-    w.motions = []
-    w.params.boundary_conditions = []
-    case("drum-static-wall", w, (1, 2, 5), rank, world, local_rank)
-    case("drum-g0", drum(g=(0.0, 0.0, 0.0)), (1, 2, 5), rank, world, local_rank)
+    w.props[:, 6:9] = np.random.default_rng(5).normal(0.0, 5.0, (w.n, 3))
+    case("drum-omega", w, (5, 6, 7, 8, 9, 10), rank, world, local_rank)
     dist.destroy_process_group()
 
 
