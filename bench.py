@@ -93,7 +93,7 @@ def make_workload(args, rank, world):
         return workloads.periodic_box(cells=(side * world, side, side), spacing=1.005, jitter=0.002,
                                       slab=(rank, world) if world > 1 else None)
     if args.workload == "hopper":
-        return workloads.hopper(n_target=args.n_per_gpu * world)
+        return workloads.hopper(n_target=args.n_per_gpu * world, gate_open_time=1e-5 * (args.settle + 100))
     if args.workload in ("cohesive_jkr", "cohesive_dmt"):
         side = max(4, round((args.n_per_gpu / 1.41) ** (1.0 / 3.0)))
         return workloads.cohesive_box(side, model="hertz_JKR" if args.workload == "cohesive_jkr" else "DMT")
@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="drum", choices=["drum", "periodic_box", "box_packing", "hopper", "cohesive_jkr", "cohesive_dmt"])
     ap.add_argument("--n-per-gpu", type=int, default=1_000_000)
-    ap.add_argument("--settle", type=int, default=3000, help="untimed settling steps before warm-up")
+    ap.add_argument("--settle", type=int, default=-1, help="untimed settling steps before warm-up (-1: per workload)")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-particles", type=int, default=40_000)
     ap.add_argument("--cpu-steps", type=int, default=300)
@@ -181,6 +181,9 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.settle < 0:
+        # enough for the bed to come to rest on its supports (loose lattices fall first)
+        args.settle = {"drum": 3000, "hopper": 20000, "box_packing": 20000, "periodic_box": 500}.get(args.workload, 3000)
     if args.cpu_settle < 0:
         args.cpu_settle = args.settle
 
@@ -201,6 +204,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the DEM engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of the one-JSON-line stdout
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

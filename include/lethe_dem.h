@@ -228,7 +228,17 @@ int lethe_dem_event_elapsed(lethe_dem_ctx *ctx, double *ms);
 /* Number of kernels this library has launched in the calling process so far. */
 int lethe_dem_kernel_launches(lethe_dem_ctx *ctx, uint64_t *n_launches);
 
-/* --- multi-GPU (one ctx per GPU per process; slab decomposition) --- */
+/* --- multi-GPU (one ctx per GPU per process; slab decomposition) ---
+ * Replaces particle_handler.update_ghost_particles (dem.cc:686),
+ * sort_particles_into_subdomains_and_cells + exchange_ghost_particles (dem.cc:986-989) and the
+ * Utilities::MPI::logical_or of find_contact_detection_step.cc:53-58. NCCL carries the rebuild-step
+ * exchanges (migration incl. contact history, ghost ids); the per-step ghost refresh is written by
+ * the step kernel into the neighbour GPU's memory (CUDA IPC over NVLink) and the per-step logical_or
+ * is a 4-byte peer-memory agreement. Every rank must be given the same wall / floating-wall /
+ * boundary-motion tables. Environment switches (read at lethe_dem_comm_init / lethe_dem_create):
+ *   LETHE_DEM_HALO=nccl      per-step ghost refresh over ncclSend/ncclRecv instead of peer stores
+ *   LETHE_DEM_AGREE=nccl     per-step agreement over ncclAllReduce instead of peer memory
+ *   LETHE_DEM_NO_PIPELINE=1  synchronous flag check before every step (no speculative launch) */
 #define LETHE_DEM_NCCL_ID_BYTES 128
 int lethe_dem_nccl_unique_id(uint8_t id[LETHE_DEM_NCCL_ID_BYTES]);
 int lethe_dem_comm_init(lethe_dem_ctx *ctx, int rank, int world_size,

@@ -384,11 +384,14 @@ def test_baseline_config_workloads_parity(name):
     g, o = abi.load_engine(cfg), loader.oracle_engine(cfg)
     w.install(g)
     w.install(o)
+    if name == "cohesive_dmt":
+        loader.set_option(o, "dmt_stale_scratch", 0)  # see DESIGN.md "known reference defect"
 
     def walls_equal(step):
         wg, wo = g.get_wall_contacts(), o.get_wall_contacts()
         assert np.array_equal(wg[0], wo[0]) and np.array_equal(wg[1], wo[1]), step
 
-    lockstep(g, o, 40, 10, extra=walls_equal)
+    # cbrt differs by an ulp between CUDA and glibc for the JKR model
+    lockstep(g, o, 40, 10, force_rtol=1e-10 if name == "cohesive_jkr" else FORCE_RTOL, extra=walls_equal)
     assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 2
     assert g.get_stats().n_particles == o.get_stats().n_particles
