@@ -16,9 +16,13 @@
 //     their pairs up in list order — a per-particle segment reduction, no atomics,
 //     deterministic, the same sequence of additions as a serial walk of the row;
 //   * walls, integrator and the displacement trigger run per owner lane afterwards.
-// Measured dead ends (profiles/): prefetch.global.L1/L2 of the round operands,
-// cp.async staging of the next round, deeper sweep pipelines — the kernel is bound by the
-// issue latency of dependent FP64 chains at 16 warps/SM, not by exposed memory latency.
+// Measured dead ends (profiles/): prefetching the round operands at the start
+// of the previous round, cp.async staging of the next round, deeper or shallower sweep
+// pipelines (SWEEP 2 / 8), 3 / 5 / 6 resident blocks per SM, a 256-slot queue, reading
+// neighbours that belong to the warp's own 32 rows from shared memory instead of through L1
+// (+6 %: divergence costs more than the gathers) — the kernel is bound by the issue latency
+// of dependent FP64 chains at 16 warps/SM. What did pay: prefetch.global.L2 of the round
+// operands as soon as the sweep finds a touching entry (-2 %).
 // Neighbours are read from state generation g, results go to g^1.
 //
 // Reference path replaced (one iteration of source/dem/dem.cc:1134-1183):
