@@ -230,6 +230,12 @@ def main():
 
     # ---- settle + warm-up (untimed) ----
     engine.step(args.settle)
+    # the contact lists are double-buffered across rebuilds: make sure both generations (and the
+    # migration / halo buffers) have been allocated before the clock starts. A forced rebuild is
+    # transparent to the physics (history is carried over).
+    for _ in range(2):
+        engine.force_contact_search()
+        engine.step(1)
     engine.step(max(3, args.warmup))
     barrier()
 

@@ -74,7 +74,9 @@ enum lethe_rolling_model {
   LETHE_ROLLING_VISCOUS = 2,
   LETHE_ROLLING_EPSD = 3
 };
-enum lethe_integrator { LETHE_INTEGRATOR_VELOCITY_VERLET = 0 };
+/* `integration method = velocity_verlet|explicit_euler` (parameters_lagrangian.cc:1049,1314;
+ * DEMSolver::set_integrator_type, dem.cc:260-279) */
+enum lethe_integrator { LETHE_INTEGRATOR_VELOCITY_VERLET = 0, LETHE_INTEGRATOR_EXPLICIT_EULER = 1 };
 enum lethe_detection { LETHE_DETECTION_DYNAMIC = 0, LETHE_DETECTION_CONSTANT = 1 };
 /* Order in which the reference's FE mesh enumerates its active cells; it only
  * fixes which particle of a pair is "particle one" (history sign) and the

@@ -456,6 +456,7 @@ namespace
     P.floating = c->fw_dev.p;
     P.n_owned = c->n_owned;
     P.phase = phase;
+    P.integrator = c->cfg.integrator;
     P.pw_model = c->cfg.pw_model;
     P.rolling_model = c->cfg.rolling_model;
     P.periodic_any = c->grid.periodic[0] || c->grid.periodic[1] || c->grid.periodic[2];
@@ -740,8 +741,8 @@ int lethe_dem_create(const lethe_dem_config *config, int device, lethe_dem_ctx *
     return bad("n_types out of range (1..5)");
   if (config->grid_n[0] < 1 || config->grid_n[1] < 1 || config->grid_n[2] < 1)
     return bad("grid_n must be positive");
-  if (config->integrator != LETHE_INTEGRATOR_VELOCITY_VERLET)
-    return bad("only the velocity_verlet integrator is on the B200 path");
+  if (config->integrator != LETHE_INTEGRATOR_VELOCITY_VERLET && config->integrator != LETHE_INTEGRATOR_EXPLICIT_EULER)
+    return bad("unknown integrator (velocity_verlet or explicit_euler)");
   if (config->pp_model < 0 || config->pp_model > LETHE_PP_DMT || config->pw_model < 0 || config->pw_model > LETHE_PW_DMT ||
       config->rolling_model < 0 || config->rolling_model > LETHE_ROLLING_EPSD)
     return bad("invalid contact model selector");

@@ -146,6 +146,7 @@ namespace dem
     const FloatingWallsDev *floating;
     uint32_t n_owned; // particles integrated by this rank
     int phase;
+    int integrator; // lethe_integrator
     int pw_model;
     int rolling_model;
     int periodic_any;

@@ -523,7 +523,26 @@ namespace dem
       const double MOI = P.moi_override > 0 ? P.moi_override : 0.1 * me.m * me.d * me.d; // dem.cc:1004-1011
       vec3 v = me.v, x = me.x, om = me.w;
       const vec3 g = v3(P.g[0], P.g[1], P.g[2]);
-      if (P.phase == PHASE_REGULAR)
+      if (P.integrator == LETHE_INTEGRATOR_EXPLICIT_EULER)
+        {
+          // ExplicitEulerIntegrator::integrate (explicit_euler_integrator.cc:69-130); the opening
+          // step is a regular step (:14-26), the closing one leaves the state untouched (:32-48)
+          if (P.phase != PHASE_END)
+            {
+              const double mass_inverse = 1 / me.m;
+              const double MOI_inverse = 1 / MOI;
+              v.x = v.x + dt * (g.x + (F.x) * mass_inverse);
+              v.y = v.y + dt * (g.y + (F.y) * mass_inverse);
+              v.z = v.z + dt * (g.z + (F.z) * mass_inverse);
+              x.x = x.x + dt * v.x;
+              x.y = x.y + dt * v.y;
+              x.z = x.z + dt * v.z;
+              om.x = om.x + dt * (T.x * MOI_inverse);
+              om.y = om.y + dt * (T.y * MOI_inverse);
+              om.z = om.z + dt * (T.z * MOI_inverse);
+            }
+        }
+      else if (P.phase == PHASE_REGULAR)
         {
           const vec3 dt_g = g * dt;
           const double dt_mass_inverse = dt / me.m;

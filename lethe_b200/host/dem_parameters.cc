@@ -258,8 +258,8 @@ namespace lethe_b200
 
   lethe_dem_config DEMParameters::to_config(bool store_forces) const
   {
-    if (integration_method != "velocity_verlet")
-      throw std::runtime_error("integration method `" + integration_method + "` is not on the B200 path (velocity_verlet only)");
+    if (integration_method != "velocity_verlet" && integration_method != "explicit_euler")
+      throw std::runtime_error("unknown integration method `" + integration_method + "` (velocity_verlet|explicit_euler)");
     if (solver_type != "dem")
       throw std::runtime_error("solver type dem_mp is out of scope");
     static const std::map<std::string, int> pp{{"linear", LETHE_PP_LINEAR},
@@ -280,7 +280,7 @@ namespace lethe_b200
     c.pp_model = lookup(pp, pp_model, "particle particle contact force method");
     c.pw_model = lookup(pw, pw_model, "particle wall contact force method");
     c.rolling_model = lookup(rolling, rolling_model, "rolling resistance torque method");
-    c.integrator = LETHE_INTEGRATOR_VELOCITY_VERLET;
+    c.integrator = integration_method == "explicit_euler" ? LETHE_INTEGRATOR_EXPLICIT_EULER : LETHE_INTEGRATOR_VELOCITY_VERLET;
     c.detection = lookup(detection, contact_detection_method, "contact detection method");
     c.contact_detection_frequency = int(contact_detection_frequency);
     c.cell_order = mesh.cell_order;

@@ -194,8 +194,8 @@ class DEMParameters:
         )
 
     def to_config(self, store_forces=False, moi_override=0.0, slab=None) -> abi.Config:
-        if self.integration_method != "velocity_verlet":
-            raise abi.DEMError(f"integration method {self.integration_method!r} is not on the B200 path (velocity_verlet only)")
+        if self.integration_method not in ("velocity_verlet", "explicit_euler"):
+            raise abi.DEMError(f"unknown integration method {self.integration_method!r} (velocity_verlet|explicit_euler)")
         if self.solver_type != "dem":
             raise abi.DEMError("solver type dem_mp is out of scope")
         for name, table, val in (
@@ -210,7 +210,7 @@ class DEMParameters:
         c.pp_model = abi.PP_MODELS[self.pp_model]
         c.pw_model = abi.PW_MODELS[self.pw_model]
         c.rolling_model = abi.ROLLING_MODELS[self.rolling_model]
-        c.integrator = 0
+        c.integrator = 1 if self.integration_method == "explicit_euler" else 0
         c.detection = abi.DETECTION[self.contact_detection_method]
         c.contact_detection_frequency = self.contact_detection_frequency
         c.cell_order = abi.CELL_ORDER[self.mesh.cell_order]

@@ -1463,9 +1463,41 @@ namespace
   }
 
   // ------------------------------------------------------------ integrator ---
+  // ExplicitEulerIntegrator::integrate (explicit_euler_integrator.cc:69-130); integrate_start is
+  // the same step (:14-26), integrate_end only zeroes force and torque (:32-48)
+  void integrate_euler(Oracle &o)
+  {
+    const double dt = o.cfg.dt;
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      {
+        double *p = o.parts[s].p;
+        const double mass_inverse = 1 / p[P_MASS];
+        const double MOI_inverse = 1 / o.MOI[s];
+        for (int d = 0; d < 3; ++d)
+          {
+            const double acceleration = o.cfg.g[d] + (o.force[s][d]) * mass_inverse;
+            p[P_VX + d] += dt * acceleration;
+            o.parts[s].x[d] += dt * p[P_VX + d];
+            p[P_WX + d] += dt * (o.torque[s][d] * MOI_inverse);
+          }
+        o.force[s] = mk(0, 0, 0);
+        o.torque[s] = mk(0, 0, 0);
+      }
+  }
+  void zero_force_torque(Oracle &o)
+  {
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      {
+        o.force[s] = mk(0, 0, 0);
+        o.torque[s] = mk(0, 0, 0);
+      }
+  }
+
   // VelocityVerletIntegrator (velocity_verlet_integrator.cc:14-66,70-115,214-290)
   void integrate_start(Oracle &o)
   {
+    if (o.cfg.integrator == LETHE_INTEGRATOR_EXPLICIT_EULER)
+      return integrate_euler(o);
     const double dt = o.cfg.dt;
     const V3 g = mk(o.cfg.g[0], o.cfg.g[1], o.cfg.g[2]);
     const V3 half_dt_g = 0.5 * g * dt;
@@ -1487,6 +1519,8 @@ namespace
   }
   void integrate_end(Oracle &o)
   {
+    if (o.cfg.integrator == LETHE_INTEGRATOR_EXPLICIT_EULER)
+      return zero_force_torque(o);
     const double dt = o.cfg.dt;
     const V3 g = mk(o.cfg.g[0], o.cfg.g[1], o.cfg.g[2]);
     const V3 half_dt_g = 0.5 * g * dt;
@@ -1505,6 +1539,8 @@ namespace
   }
   void integrate(Oracle &o)
   {
+    if (o.cfg.integrator == LETHE_INTEGRATOR_EXPLICIT_EULER)
+      return integrate_euler(o);
     const double dt = o.cfg.dt;
     const V3 g = mk(o.cfg.g[0], o.cfg.g[1], o.cfg.g[2]);
     const V3 dt_g = g * dt;
@@ -1668,9 +1704,9 @@ int oracle_dem_create(const lethe_dem_config *config, int /*device*/, lethe_dem_
       g_create_error = "grid_n must be positive";
       return -1;
     }
-  if (config->integrator != LETHE_INTEGRATOR_VELOCITY_VERLET)
+  if (config->integrator != LETHE_INTEGRATOR_VELOCITY_VERLET && config->integrator != LETHE_INTEGRATOR_EXPLICIT_EULER)
     {
-      g_create_error = "only velocity_verlet is supported";
+      g_create_error = "unknown integrator";
       return -1;
     }
   Oracle *o = new Oracle();

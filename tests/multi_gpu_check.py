@@ -95,11 +95,11 @@ def main():
     w.params.dynamic_contact_search_factor = 0.1
     ok &= run_case("drum", w, (10, 40), rank, world, local_rank, tol=(1e-11, 1e-8))
     # periodic axis: particles migrate across slabs and wrap around
-    w = workloads.periodic_box(cells=(12, 6, 6), spacing=1.0, jitter=0.03, vel_sigma=0.5)
+    w = workloads.periodic_box(cells=(max(12, 3 * world), 6, 6), spacing=1.0, jitter=0.03, vel_sigma=0.5)
     w.params.dynamic_contact_search_factor = 0.1
     ok &= run_case("periodic", w, (30, 120), rank, world, local_rank, tol=(1e-13, 1e-10))
     # polydisperse hopper: floating wall that opens during the run, outlet deletion at rebuilds
-    w = workloads.hopper(n_target=20000, gate_open_time=0.0003)
+    w = workloads.hopper(n_target=20000, gate_open_time=0.0003, min_nx=max(16, 3 * world))
     w.props[:, 6:9] = np.random.default_rng(6).normal(0.0, 5.0, (w.n, 3))
     w.params.dynamic_contact_search_factor = 0.1
     ok &= run_case("hopper", w, (20, 60), rank, world, local_rank, tol=(1e-11, 1e-8))

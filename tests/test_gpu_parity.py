@@ -226,6 +226,21 @@ def test_packing_parity_stepwise(pp, pw, rolling, poly, n_types):
     assert sg.n_pairs_touching == so.n_pairs_touching
 
 
+def test_explicit_euler_parity_stepwise():
+    """`integration method = explicit_euler` (explicit_euler_integrator.cc): same lock-step bar."""
+    d = 0.005
+    ids, x, props, extent = random_packing(10, d=d, spacing=0.98, jitter=0.08, poly=0.2, seed=9)
+    params = packing_parameters(extent, d=d, rolling="constant")
+    params.integration_method = "explicit_euler"
+    g, o = setup_pair(params, ids, x, props)
+    lockstep(g, o, 30, 10)
+    assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 2
+    g.synchronize_velocities()
+    o.synchronize_velocities()
+    (_, xg, pg), (_, xo, po) = g.get_particles(), o.get_particles()
+    assert np.abs(pg - po).max() <= 1e-8 * np.abs(po).max()
+
+
 def test_periodic_parity_stepwise():
     d = 0.005
     ids, x, props, extent = random_packing(10, d=d, spacing=1.0, jitter=0.08, poly=0.1, seed=3, vel=0.3)

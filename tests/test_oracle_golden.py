@@ -145,6 +145,48 @@ def test_velocity_verlet_free_flight(oracle_lib):
         assert_sig6(props[0, 6 + d], g["omega"][d], "omega")
 
 
+def test_explicit_euler_free_fall(oracle_lib):
+    # tests/dem/integration_euler.cc: one particle at rest, g = -9.81 z, dt = 1e-5, one `integrate`;
+    # golden integration_euler.output: z = -9.81000e-10
+    p = unit_test_parameters(dt=1e-5, g=(0, 0, -9.81))
+    p.integration_method = "explicit_euler"
+    e = loader.oracle_engine(p.to_config())
+    e.set_particles([0], [[0, 0, 0]], [props_row(1, 0.005, 1.0)])
+    loader.integrate_external(e, 1, [0.0, 0, 0], [0.0, 0, 0], 1.0)
+    _, x, props = e.get_particles()
+    assert_sig6(x[0, 2], -9.81000e-10, "z after one explicit Euler step")
+    assert x[0, 0] == 0 and x[0, 1] == 0
+    # the closing step leaves the state untouched (explicit_euler_integrator.cc:32-48)
+    loader.integrate_external(e, 2, [1.0, 0, 0], [0.0, 0, 0], 1.0)
+    _, x2, props2 = e.get_particles()
+    assert np.array_equal(x, x2) and np.array_equal(props, props2)
+
+
+def test_integration_schemes_order(oracle_lib):
+    # tests/dem/integration_schemes_accuracy.cc: a particle on a linear spring F = -k x; halving dt
+    # divides the end-position error by 2^order; golden: Euler 1.00529, Verlet 2.00189
+    # (the exact decimals depend on the test's spring set-up; the orders are what is pinned here)
+    def run(method, dt, t_end=0.05, k=50.0):
+        p = unit_test_parameters(dt=dt, g=(0, 0, 0))
+        p.integration_method = method
+        e = loader.oracle_engine(p.to_config())
+        e.set_particles([0], [[0.3, 0, 0]], [props_row(1, 0.005, 1.0)])
+        n = int(round(t_end / dt))
+        for it in range(n):
+            _, x, _ = e.get_particles()
+            f = [-k * x[0, 0], 0.0, 0.0]
+            loader.integrate_external(e, 0 if (it == 0) else 1, f, [0.0, 0, 0], 1.0)
+        _, x, _ = e.get_particles()
+        return x[0, 0]
+
+    import math as m
+    exact = 0.3 * m.cos(m.sqrt(50.0) * 0.05)
+    for method, order in (("explicit_euler", 1.0), ("velocity_verlet", 2.0)):
+        e1 = abs(run(method, 1e-4) - exact)
+        e2 = abs(run(method, 5e-5) - exact)
+        assert abs(m.log2(e1 / e2) - order) < 0.1, (method, e1, e2)
+
+
 def test_find_contact_pairs_and_fine_search(oracle_lib):
     # tests/dem/find_contact_pairs.cc: three particles, candidate pairs (0,1) and (1,2);
     # tests/dem/particle_particle_fine_search.cc: pair enters with zero tangential displacement
