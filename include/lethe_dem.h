@@ -191,6 +191,31 @@ int lethe_dem_set_boundary_motion(lethe_dem_ctx *ctx, uint32_t boundary_id,
                                   const double translational_velocity[3],
                                   double rotational_speed, const double rotational_vector[3],
                                   const double point_on_rotation_axis[3]);
+/* Solid surfaces (triangle meshes; `subsection solid objects / solid surfaces`, SerialSolid<2,3>,
+ * source/core/serial_solid.cc). Replaces DEMSolver::setup_solid_objects (dem.cc:164-191); the
+ * per-step motion (move_solid_triangulation, serial_solid.cc:333-410), the background-mesh
+ * mapping (map_solid_in_background_triangulation, :83-150, refreshed when a vertex has moved more
+ * than 3^-1/2 of the cell diameter, find_contact_detection_step.cc:139-161), the candidate search
+ * (particle_wall_broad_search.cc:129-215) and calculate_particle_solid_object_contact
+ * (particle_wall_contact_force.cc:153-580, incl. the face/edge/vertex double-contact elimination)
+ * then run inside lethe_dem_step. `triangles3` holds 3 vertex indices per triangle, in mesh
+ * element order. Velocities are the values of the reference's velocity functions for the
+ * coming steps; update them with lethe_dem_set_solid_motion when they depend on time. */
+int lethe_dem_add_solid_surface(lethe_dem_ctx *ctx, uint32_t n_vertices, const double *vertices3,
+                                uint32_t n_triangles, const uint32_t *triangles3,
+                                const double translational_velocity[3],
+                                const double angular_velocity[3],
+                                const double center_of_rotation[3], int32_t *solid_index);
+int lethe_dem_set_solid_motion(lethe_dem_ctx *ctx, int32_t solid_index,
+                               const double translational_velocity[3],
+                               const double angular_velocity[3]);
+/* current vertex positions of a solid (3 doubles per vertex) */
+int lethe_dem_get_solid_vertices(lethe_dem_ctx *ctx, int32_t solid_index, uint32_t n_max,
+                                 double *vertices3);
+/* debug tap: (particle id, solid, triangle) candidates in (id, solid, triangle) order + history */
+int lethe_dem_get_solid_contacts(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out,
+                                 uint32_t *particle_id, uint32_t *solid, uint32_t *triangle,
+                                 double *tangential3);
 
 /* --- the hot path --- */
 int lethe_dem_step(lethe_dem_ctx *ctx, uint64_t n_steps);

@@ -138,6 +138,10 @@ ABI_SYMBOLS = [
     "set_walls",
     "set_floating_walls",
     "set_boundary_motion",
+    "add_solid_surface",
+    "set_solid_motion",
+    "get_solid_vertices",
+    "get_solid_contacts",
     "step",
     "synchronize_velocities",
     "force_contact_search",
@@ -269,6 +273,36 @@ class Engine:
             _d3(*rotational_vector),
             _d3(*point_on_axis),
         )
+
+    def add_solid_surface(self, vertices, triangles, translational_velocity=(0, 0, 0), angular_velocity=(0, 0, 0), center_of_rotation=(0, 0, 0)) -> int:
+        """A triangle-mesh solid surface (SerialSolid<2,3>); returns its index."""
+        v = _f64(vertices).reshape(-1, 3)
+        t = _u32(triangles).reshape(-1, 3)
+        idx = C.c_int32(-1)
+        self._call("add_solid_surface", C.c_uint32(len(v)), _ptr(v, _p_f64), C.c_uint32(len(t)), _ptr(t, _p_u32),
+                   _d3(*translational_velocity), _d3(*angular_velocity), _d3(*center_of_rotation), C.byref(idx))
+        self._solid_sizes = getattr(self, "_solid_sizes", {})
+        self._solid_sizes[idx.value] = len(v)
+        return idx.value
+
+    def set_solid_motion(self, solid, translational_velocity=(0, 0, 0), angular_velocity=(0, 0, 0)):
+        self._call("set_solid_motion", C.c_int32(solid), _d3(*translational_velocity), _d3(*angular_velocity))
+
+    def get_solid_vertices(self, solid):
+        n = self._solid_sizes[solid]
+        out = np.empty((n, 3), np.float64)
+        self._call("get_solid_vertices", C.c_int32(solid), C.c_uint32(n), _ptr(out, _p_f64))
+        return out
+
+    def get_solid_contacts(self):
+        n = C.c_uint64()
+        self._call("get_solid_contacts", C.c_uint64(0), C.byref(n), None, None, None, None)
+        p = np.empty(n.value, np.uint32)
+        sd = np.empty(n.value, np.uint32)
+        tr = np.empty(n.value, np.uint32)
+        t = np.empty((n.value, 3), np.float64)
+        self._call("get_solid_contacts", C.c_uint64(n.value), C.byref(n), _ptr(p, _p_u32), _ptr(sd, _p_u32), _ptr(tr, _p_u32), _ptr(t, _p_f64))
+        return p, sd, tr, t
 
     # -- hot path --
     def step(self, n_steps=1):

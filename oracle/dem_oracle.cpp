@@ -25,6 +25,10 @@
 #include "../include/lethe_dem.h"
 
 #include <algorithm>
+#include <array>
+#include <map>
+#include <set>
+#include <tuple>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -191,6 +195,20 @@ namespace
     V3 point_on_axis;
   };
 
+  // SerialSolid<2,3> (source/core/serial_solid.cc) + the containers keyed by it
+  // (include/dem/data_containers.h:147-177)
+  struct Solid
+  {
+    std::vector<V3> vertices;
+    std::vector<std::array<uint32_t, 3>> tri;
+    std::vector<std::vector<uint32_t>> es_neighbors, vs_neighbors; // setup_containers (:617-682)
+    V3 translational_velocity, angular_velocity, center_of_rotation;
+    std::vector<V3> displacement_since_mapped;
+    std::vector<std::pair<int, uint32_t>> mesh_info;           // (background cell, triangle), mapping order
+    std::map<uint32_t, std::set<uint32_t>> candidates;         // triangle -> particle ids
+    std::map<uint32_t, std::map<uint32_t, PWInfo>> in_contact; // triangle -> particle id -> contact_info
+  };
+
   struct Oracle
   {
     lethe_dem_config cfg;
@@ -227,6 +245,10 @@ namespace
     double fw_t0[LETHE_DEM_MAX_FLOATING_WALLS], fw_t1[LETHE_DEM_MAX_FLOATING_WALLS];
     std::vector<std::vector<int>> fw_cells; // per floating wall: boundary cells (rank order)
     std::vector<BoundaryMotion> motions;
+
+    // solid surfaces
+    std::vector<Solid> solids;
+    bool solid_object_search_trigger = false;
 
     // effective properties
     int n_types;
@@ -1462,6 +1484,552 @@ namespace
         }
   }
 
+
+  // ------------------------------------------------------- solid surfaces ----
+  enum TriangleContact { TC_FACE = 0, TC_EDGE = 1, TC_VERTEX = 2, TC_NONE = 3 };
+
+  // Eberly's closest point on a triangle, as both LetheGridTools functions evaluate it
+  // (lethe_grid_tools.cc:1277-1434 and :1565-1697), quirks included (region 4: t = e / c).
+  inline void closest_point_parameters(double a, double b, double c, double d, double e, double det, double &s, double &t,
+                                       int &indicator)
+  {
+    s = b * e - c * d;
+    t = b * d - a * e;
+    if (s + t <= det)
+      {
+        if (s < 0)
+          {
+            if (t < 0)
+              {
+                indicator = TC_VERTEX; // region 4
+                if (d < 0)
+                  {
+                    t = 0;
+                    if (-d >= a)
+                      s = 1;
+                    else
+                      s = -d / a;
+                  }
+                else
+                  {
+                    s = 0;
+                    if (e >= 0)
+                      t = 0;
+                    else if (-e >= c)
+                      t = 1;
+                    else
+                      t = e / c;
+                  }
+              }
+            else
+              {
+                indicator = TC_EDGE; // region 3
+                s = 0;
+                if (e >= 0)
+                  t = 0;
+                else if (-e >= c)
+                  t = 1;
+                else
+                  t = -e / c;
+              }
+          }
+        else if (t < 0)
+          {
+            indicator = TC_EDGE; // region 5
+            t = 0;
+            if (d >= 0)
+              s = 0;
+            else if (-d >= a)
+              s = 1;
+            else
+              s = -d / a;
+          }
+        else
+          {
+            indicator = TC_FACE; // region 0
+            const double inv_det = 1. / det;
+            s *= inv_det;
+            t *= inv_det;
+          }
+      }
+    else
+      {
+        if (s < 0)
+          {
+            indicator = TC_VERTEX; // region 2
+            const double tmp0 = b + d;
+            const double tmp1 = c + e;
+            if (tmp1 > tmp0)
+              {
+                const double numer = tmp1 - tmp0;
+                const double denom = a - 2 * b + c;
+                if (numer >= denom)
+                  s = 1;
+                else
+                  s = numer / denom;
+                t = 1 - s;
+              }
+            else
+              {
+                s = 0;
+                if (tmp1 <= 0)
+                  t = 1;
+                else if (e >= 0)
+                  t = 0;
+                else
+                  t = -e / c;
+              }
+          }
+        else if (t < 0)
+          {
+            indicator = TC_VERTEX; // region 6
+            const double tmp0 = b + e;
+            const double tmp1 = a + d;
+            if (tmp1 > tmp0)
+              {
+                const double numer = tmp1 - tmp0;
+                const double denom = a - 2 * b + c;
+                if (numer >= denom)
+                  t = 1;
+                else
+                  t = numer / denom;
+                s = 1 - t;
+              }
+            else
+              {
+                t = 0;
+                if (tmp1 <= 0)
+                  s = 1;
+                else if (d >= 0)
+                  s = 0;
+                else
+                  s = -d / a;
+              }
+          }
+        else
+          {
+            indicator = TC_EDGE; // region 1
+            const double numer = (c + e) - (b + d);
+            if (numer <= 0)
+              s = 0;
+            else
+              {
+                const double denom = a - 2 * b + c;
+                if (numer >= denom)
+                  s = 1;
+                else
+                  s = numer / denom;
+              }
+            t = 1 - s;
+          }
+      }
+  }
+
+  // LetheGridTools::find_point_triangle_distance (lethe_grid_tools.cc:1536-1700), dim = 3
+  double find_point_triangle_distance(const V3 &p0, const V3 &p1, const V3 &p2, const V3 &point)
+  {
+    const V3 e_0 = p1 - p0, e_1 = p2 - p0;
+    const double a = norm_square(e_0), b = dot(e_0, e_1), c = norm_square(e_1);
+    const double det = a * c - b * b;
+    const V3 vector_to_plane = p0 - point;
+    const double d = dot(e_0, vector_to_plane), e = dot(e_1, vector_to_plane);
+    double s, t;
+    int ind;
+    closest_point_parameters(a, b, c, d, e, det, s, t, ind);
+    const V3 pt_in_triangle = p0 + s * e_0 + t * e_1;
+    return std::sqrt(distance_square(pt_in_triangle, point));
+  }
+
+  // LetheGridTools::find_particle_triangle_projection (lethe_grid_tools.cc:1226-1450)
+  bool find_particle_triangle_projection(const V3 &p0, const V3 &p1, const V3 &p2, const V3 &particle_position, double radius,
+                                         V3 &projection, V3 &unit_normal_out, int &indicator)
+  {
+    const V3 e_0 = p1 - p0, e_1 = p2 - p0;
+    V3 normal = cross(e_0, e_1);
+    const double norm_normal = norm(normal);
+    V3 unit_normal = normal / norm_normal;
+    const double a = norm_square(e_0), b = dot(e_0, e_1), c = norm_square(e_1);
+    const double det = a * c - b * b;
+    const V3 vector_to_plane = p0 - particle_position;
+    if (dot(vector_to_plane, unit_normal) > 0)
+      unit_normal = unit_normal * -1.0;
+    // (sic) a signed distance compared with a squared radius; it is never positive after the flip
+    const double distance_squared = dot(vector_to_plane, unit_normal);
+    if (distance_squared > (radius * radius))
+      {
+        indicator = TC_NONE;
+        return false;
+      }
+    const double d = dot(e_0, vector_to_plane), e = dot(e_1, vector_to_plane);
+    double s, t;
+    closest_point_parameters(a, b, c, d, e, det, s, t, indicator);
+    const V3 pt_in_triangle = p0 + s * e_0 + t * e_1;
+    if (indicator == TC_FACE)
+      unit_normal_out = unit_normal;
+    else
+      {
+        normal = particle_position - pt_in_triangle;
+        unit_normal_out = normal / norm(normal);
+      }
+    projection = pt_in_triangle;
+    return true;
+  }
+
+  // SerialSolid::setup_containers (serial_solid.cc:617-682)
+  void setup_solid_neighbors(Solid &sd)
+  {
+    const size_t nt = sd.tri.size();
+    std::vector<std::set<uint32_t>> vertices_cell_map(sd.vertices.size());
+    for (uint32_t t = 0; t < nt; ++t)
+      for (int v = 0; v < 3; ++v)
+        vertices_cell_map[sd.tri[t][v]].insert(t);
+    sd.es_neighbors.assign(nt, {});
+    sd.vs_neighbors.assign(nt, {});
+    for (uint32_t t = 0; t < nt; ++t)
+      {
+        std::set<uint32_t> around;
+        for (int v = 0; v < 3; ++v)
+          around.insert(vertices_cell_map[sd.tri[t][v]].begin(), vertices_cell_map[sd.tri[t][v]].end());
+        for (uint32_t n : around)
+          {
+            if (n == t)
+              continue;
+            unsigned int n_sharing_vertices = 0;
+            for (int v = 0; v < 3; ++v)
+              if (std::find(sd.tri[t].begin(), sd.tri[t].end(), sd.tri[n][v]) != sd.tri[t].end())
+                n_sharing_vertices++;
+            if (n_sharing_vertices == 1)
+              sd.vs_neighbors[t].push_back(n);
+            else
+              sd.es_neighbors[t].push_back(n);
+          }
+      }
+  }
+
+  // SerialSolid::map_solid_in_background_triangulation (serial_solid.cc:83-150)
+  void map_solid_in_background_triangulation(const Oracle &o, Solid &sd)
+  {
+    sd.mesh_info.clear();
+    const double *h = o.cfg.cell_size;
+    const double bg_cell_length = std::sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
+    for (int r = 0; r < o.n_cells; ++r)
+      {
+        const int cell = o.cell_of_rank[r];
+        const int ci = cell % o.nx, cj = (cell / o.nx) % o.ny, ck = cell / (o.nx * o.ny);
+        const V3 bg_cell_center = mk(o.cfg.grid_lo[0] + (ci + 0.5) * h[0], o.cfg.grid_lo[1] + (cj + 0.5) * h[1],
+                                     o.cfg.grid_lo[2] + (ck + 0.5) * h[2]);
+        for (uint32_t t = 0; t < sd.tri.size(); ++t)
+          {
+            const double distance = find_point_triangle_distance(sd.vertices[sd.tri[t][0]], sd.vertices[sd.tri[t][1]],
+                                                                 sd.vertices[sd.tri[t][2]], bg_cell_center);
+            if (distance < bg_cell_length)
+              sd.mesh_info.emplace_back(cell, t);
+          }
+      }
+    for (auto &dsp : sd.displacement_since_mapped)
+      dsp = mk(0, 0, 0);
+  }
+
+  // find_floating_mesh_mapping_step (find_contact_detection_step.cc:139-161); criterion dem.cc:296-308
+  void find_floating_mesh_mapping_step(Oracle &o)
+  {
+    if (o.solids.empty())
+      return;
+    const double *h = o.cfg.cell_size;
+    const double criterion = 0.57735026918962576451 * std::sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
+    bool floating_mesh_requires_map = false;
+    for (auto &sd : o.solids)
+      {
+        double displacement = 0.;
+        for (auto &dsp : sd.displacement_since_mapped)
+          for (int d = 0; d < 3; ++d)
+            displacement = std::max(displacement, std::fabs(dsp[d]));
+        floating_mesh_requires_map = floating_mesh_requires_map || displacement > criterion;
+      }
+    if (floating_mesh_requires_map)
+      {
+        o.solid_object_search_trigger = true;
+        o.contact_search_trigger = true;
+      }
+  }
+
+  // SerialSolid::move_solid_triangulation (serial_solid.cc:333-410)
+  void move_solid_objects(Oracle &o)
+  {
+    const double time_step = o.cfg.dt;
+    for (auto &sd : o.solids)
+      {
+        for (size_t v = 0; v < sd.vertices.size(); ++v)
+          {
+            const V3 distance_vector = sd.vertices[v] - sd.center_of_rotation;
+            V3 local_velocity = sd.translational_velocity;
+            local_velocity = local_velocity + cross(sd.angular_velocity, distance_vector);
+            const V3 vertex_displacement = time_step * local_velocity;
+            sd.vertices[v] = sd.vertices[v] + vertex_displacement;
+            sd.displacement_since_mapped[v] = sd.displacement_since_mapped[v] + vertex_displacement;
+          }
+        sd.center_of_rotation = sd.center_of_rotation + sd.translational_velocity * time_step;
+      }
+  }
+
+  // find_full_cell_neighbors (find_cell_neighbors.cc:293-333): the cell and its vertex-sharing cells
+  void full_cell_neighbors(const Oracle &o, int cell, std::vector<int> &out)
+  {
+    out.clear();
+    out.push_back(cell);
+    const int ci = cell % o.nx, cj = (cell / o.nx) % o.ny, ck = cell / (o.nx * o.ny);
+    for (int dk = -1; dk <= 1; ++dk)
+      for (int dj = -1; dj <= 1; ++dj)
+        for (int di = -1; di <= 1; ++di)
+          {
+            if (!di && !dj && !dk)
+              continue;
+            const int i = ci + di, j = cj + dj, k = ck + dk;
+            if (i < 0 || j < 0 || k < 0 || i >= o.nx || j >= o.ny || k >= o.nz)
+              continue;
+            out.push_back(lin(o, i, j, k));
+          }
+  }
+
+  // particle_solid_surfaces_contact_search (particle_wall_broad_search.cc:129-215)
+  void particle_solid_surfaces_contact_search(Oracle &o)
+  {
+    std::vector<int> cell_list;
+    for (auto &sd : o.solids)
+      {
+        sd.candidates.clear();
+        for (auto &bt : sd.mesh_info)
+          {
+            full_cell_neighbors(o, bt.first, cell_list);
+            for (int c : cell_list)
+              for (int s : o.cell_parts[c])
+                sd.candidates[bt.second].insert(o.parts[s].id);
+          }
+      }
+  }
+
+  // update_fine_search_candidates<particle_floating_mesh> (update_fine_search_candidates.cc:163-212)
+  // + particle_floating_mesh_fine_search (particle_wall_fine_search.cc:170-210)
+  void update_and_fine_search_solids(Oracle &o)
+  {
+    for (auto &sd : o.solids)
+      {
+        for (auto it = sd.in_contact.begin(); it != sd.in_contact.end();)
+          {
+            auto cand = sd.candidates.find(it->first);
+            for (auto pit = it->second.begin(); pit != it->second.end();)
+              {
+                if (cand != sd.candidates.end())
+                  {
+                    auto f = cand->second.find(pit->first);
+                    if (f != cand->second.end())
+                      {
+                        cand->second.erase(f);
+                        ++pit;
+                        continue;
+                      }
+                  }
+                pit = it->second.erase(pit);
+              }
+            if (it->second.empty())
+              it = sd.in_contact.erase(it);
+            else
+              ++it;
+          }
+        for (auto &c : sd.candidates)
+          for (uint32_t pid : c.second)
+            {
+              PWInfo info;
+              info.face = c.first;
+              info.normal = info.point = mk(0, 0, 0);
+              info.boundary_id = 0;
+              info.tangential_displacement = info.rolling_resistance_spring_torque = mk(0, 0, 0);
+              sd.in_contact[c.first].emplace(pid, info);
+            }
+      }
+  }
+
+  struct SolidContact
+  {
+    uint32_t triangle;
+    double normal_overlap;
+    int indicator;
+    PWInfo *info;
+  };
+
+  // ParticleWallContactForce::calculate_particle_solid_object_contact
+  // (particle_wall_contact_force.cc:153-580)
+  void calculate_particle_solid_object_contact(Oracle &o, double dt)
+  {
+    for (size_t solid_counter = 0; solid_counter < o.solids.size(); ++solid_counter)
+      {
+        Solid &sd = o.solids[solid_counter];
+        std::map<int, std::vector<SolidContact>> contact_record; // particle local index -> contacts in triangle order
+        for (auto &tp : sd.in_contact)
+          {
+            const uint32_t t = tp.first;
+            const V3 &p0 = sd.vertices[sd.tri[t][0]], &p1 = sd.vertices[sd.tri[t][1]], &p2 = sd.vertices[sd.tri[t][2]];
+            for (auto &pi : tp.second)
+              {
+                PWInfo &contact_info = pi.second;
+                const int s = slot(o, pi.first);
+                if (s < 0)
+                  continue;
+                const double *pp = o.parts[s].p;
+                V3 projection_point, normal_vector;
+                int contact_indicator;
+                if (!find_particle_triangle_projection(p0, p1, p2, o.parts[s].x, pp[P_DP] * 0.5, projection_point, normal_vector,
+                                                       contact_indicator))
+                  continue;
+                const double particle_triangle_distance = std::sqrt(distance_square(o.parts[s].x, projection_point));
+                const double normal_overlap = 0.5 * pp[P_DP] - particle_triangle_distance;
+                if (normal_overlap > o.pw_force_threshold)
+                  {
+                    contact_info.normal = normal_vector;
+                    contact_info.point = projection_point;
+                    contact_info.boundary_id = uint32_t(solid_counter);
+                    contact_record[s].push_back(SolidContact{t, normal_overlap, contact_indicator, &contact_info});
+                  }
+                else
+                  {
+                    contact_info.tangential_displacement = mk(0, 0, 0);
+                    contact_info.rolling_resistance_spring_torque = mk(0, 0, 0);
+                  }
+              }
+          }
+        auto clear_contact_info = [](PWInfo &ci) {
+          ci.tangential_displacement = mk(0, 0, 0);
+          ci.rolling_resistance_spring_torque = mk(0, 0, 0);
+        };
+        auto has = [](const std::vector<uint32_t> &v, uint32_t x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+        for (auto &rec : contact_record)
+          {
+            const int particle_index = rec.first;
+            std::vector<SolidContact> &R = rec.second;
+            // double-contact elimination between connected triangles (:262-468)
+            for (size_t c1 = 0; c1 < R.size();)
+              {
+                const uint32_t T1 = R[c1].triangle;
+                const int I1 = R[c1].indicator;
+                const auto &T1_es = sd.es_neighbors[T1];
+                const auto &T1_vs = sd.vs_neighbors[T1];
+                bool erase_contact_1 = false;
+                size_t c2 = c1 + 1;
+                while (c2 < R.size())
+                  {
+                    const uint32_t T2 = R[c2].triangle;
+                    const int I2 = R[c2].indicator;
+                    if (!has(T1_es, T2) && !has(T1_vs, T2))
+                      {
+                        ++c2;
+                        continue;
+                      }
+                    if (I1 == TC_FACE)
+                      {
+                        if (I2 == TC_FACE)
+                          {
+                            ++c2;
+                            continue;
+                          }
+                        if (I2 == TC_EDGE)
+                          {
+                            if (has(T1_vs, T2))
+                              {
+                                ++c2;
+                                continue;
+                              }
+                            clear_contact_info(*R[c2].info);
+                            R.erase(R.begin() + c2);
+                            continue;
+                          }
+                        clear_contact_info(*R[c2].info);
+                        R.erase(R.begin() + c2);
+                        continue;
+                      }
+                    if (I1 == TC_EDGE)
+                      {
+                        if (I2 == TC_FACE)
+                          {
+                            erase_contact_1 = true;
+                            break;
+                          }
+                        if (I2 == TC_EDGE)
+                          {
+                            if (has(T1_es, T2))
+                              {
+                                clear_contact_info(*R[c2].info);
+                                R.erase(R.begin() + c2);
+                                continue;
+                              }
+                            else
+                              {
+                                ++c2;
+                                continue;
+                              }
+                          }
+                      }
+                    if (I1 == TC_VERTEX)
+                      {
+                        if (I2 == TC_FACE)
+                          {
+                            erase_contact_1 = true;
+                            break;
+                          }
+                        if (I2 == TC_EDGE)
+                          {
+                            if (has(T1_vs, T2))
+                              {
+                                erase_contact_1 = true;
+                                break;
+                              }
+                            ++c2;
+                            continue;
+                          }
+                        if (I2 == TC_VERTEX)
+                          {
+                            clear_contact_info(*R[c2].info);
+                            R.erase(R.begin() + c2);
+                            continue;
+                          }
+                      }
+                    ++c2;
+                  }
+                if (erase_contact_1)
+                  {
+                    clear_contact_info(*R[c1].info);
+                    R.erase(R.begin() + c1);
+                    continue;
+                  }
+                ++c1;
+              }
+            const int s = particle_index;
+            const double *pp = o.parts[s].p;
+            for (auto &contact : R)
+              {
+                PWInfo &contact_info = *contact.info;
+                // update_particle_solid_object_contact_information (particle_wall_contact_force.h:283-331)
+                const V3 normal_vector = -contact_info.normal;
+                const V3 particle_velocity = mk(pp[P_VX], pp[P_VY], pp[P_VZ]);
+                const V3 particle_angular_velocity = mk(pp[P_WX], pp[P_WY], pp[P_WZ]);
+                const double center_of_rotation_particle_distance = std::sqrt(distance_square(sd.center_of_rotation, o.parts[s].x));
+                const V3 contact_relative_velocity =
+                  sd.translational_velocity - particle_velocity +
+                  cross((center_of_rotation_particle_distance * sd.angular_velocity - 0.5 * pp[P_DP] * particle_angular_velocity),
+                        normal_vector);
+                const double vn = dot(contact_relative_velocity, normal_vector);
+                const V3 vt = contact_relative_velocity - vn * normal_vector;
+                contact_info.tangential_displacement = contact_info.tangential_displacement + vt * dt;
+                PWOut out;
+                out.normal_force = out.tangential_force = out.tangential_torque = out.rolling = mk(0, 0, 0);
+                pw_calculate_contact(o, o.cfg.pw_model, contact_info, vt, vn, contact.normal_overlap, dt, pp, out);
+                const V3 total_force = out.normal_force + out.tangential_force;
+                o.force[s] = o.force[s] - total_force;
+                o.torque[s] = o.torque[s] + (out.tangential_torque + out.rolling);
+              }
+          }
+      }
+  }
+
   // ------------------------------------------------------------ integrator ---
   // ExplicitEulerIntegrator::integrate (explicit_euler_integrator.cc:69-130); integrate_start is
   // the same step (:14-26), integrate_end only zeroes force and torque (:32-48)
@@ -1592,6 +2160,11 @@ namespace
   void execute_contact_detection_and_search(Oracle &o)
   {
     contact_detection_iteration_check(o);
+    // solid objects: mapping onto the background mesh (dem.cc:605-628)
+    find_floating_mesh_mapping_step(o);
+    if (o.solid_object_search_trigger)
+      for (auto &sd : o.solids)
+        map_solid_in_background_triangulation(o, sd);
     if (!o.contact_search_trigger)
       return;
     execute_particles_displacement(o);
@@ -1608,6 +2181,8 @@ namespace
     find_particle_wall_contact_pairs(o, faces_by_id);
     if (o.n_floating > 0)
       find_particle_floating_wall_contact_pairs(o, o.current_time);
+    if (!o.solids.empty())
+      particle_solid_surfaces_contact_search(o);
 
     // DEMContactManager::update_contacts (dem_contact_manager.cc:52-144)
     update_fine_search_candidates_pp(o.local_adjacent, o.local_candidates);
@@ -1630,6 +2205,8 @@ namespace
     particle_wall_fine_search(o);
     if (o.n_floating > 0)
       particle_floating_wall_fine_search(o, o.current_time);
+    if (!o.solids.empty())
+      update_and_fine_search_solids(o);
     ++o.contact_build_number;
   }
 
@@ -1646,6 +2223,8 @@ namespace
     calculate_particle_wall_contact(o, o.wall_in_contact, dt);
     if (o.n_floating > 0)
       calculate_particle_wall_contact(o, o.fwall_in_contact, dt);
+    if (!o.solids.empty())
+      calculate_particle_solid_object_contact(o, dt);
     if (o.cfg.store_forces)
       {
         o.last_force = o.force;
@@ -1657,6 +2236,7 @@ namespace
   {
     o.contact_search_trigger = false;
     o.clear_tangential_displacement_trigger = false;
+    o.solid_object_search_trigger = false;
   }
 
   void one_step(Oracle &o)
@@ -1665,6 +2245,7 @@ namespace
     o.iteration_number++;
     o.current_time += o.cfg.dt;
     execute_contact_detection_and_search(o);
+    move_solid_objects(o); // dem.cc:1141-1142
     compute_contact_forces(o);
     if (o.iteration_number <= 1 && !o.cfg.restart)
       integrate_start(o);
@@ -1851,6 +2432,87 @@ int oracle_dem_set_boundary_motion(lethe_dem_ctx *ctx, uint32_t boundary_id, con
         return 0;
       }
   o->motions.push_back(m);
+  return 0;
+}
+
+int oracle_dem_add_solid_surface(lethe_dem_ctx *ctx, uint32_t n_vertices, const double *vertices3, uint32_t n_triangles,
+                                 const uint32_t *triangles3, const double tv[3], const double av[3], const double center[3],
+                                 int32_t *solid_index)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  Solid sd;
+  for (uint32_t v = 0; v < n_vertices; ++v)
+    sd.vertices.push_back(mk(vertices3[3 * v], vertices3[3 * v + 1], vertices3[3 * v + 2]));
+  for (uint32_t t = 0; t < n_triangles; ++t)
+    {
+      for (int k = 0; k < 3; ++k)
+        if (triangles3[3 * t + k] >= n_vertices)
+          return fail(o, "triangle refers to a vertex outside the solid");
+      sd.tri.push_back({triangles3[3 * t], triangles3[3 * t + 1], triangles3[3 * t + 2]});
+    }
+  sd.translational_velocity = mk(tv[0], tv[1], tv[2]);
+  sd.angular_velocity = mk(av[0], av[1], av[2]);
+  sd.center_of_rotation = mk(center[0], center[1], center[2]);
+  sd.displacement_since_mapped.assign(n_vertices, mk(0, 0, 0));
+  setup_solid_neighbors(sd);
+  o->solids.push_back(sd);
+  // DEMActionManager::set_solid_objects_enabled: the first search maps the solids
+  o->solid_object_search_trigger = true;
+  o->contact_search_trigger = true;
+  if (solid_index)
+    *solid_index = int32_t(o->solids.size()) - 1;
+  return 0;
+}
+
+int oracle_dem_set_solid_motion(lethe_dem_ctx *ctx, int32_t solid_index, const double tv[3], const double av[3])
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  if (solid_index < 0 || size_t(solid_index) >= o->solids.size())
+    return fail(o, "no such solid");
+  o->solids[solid_index].translational_velocity = mk(tv[0], tv[1], tv[2]);
+  o->solids[solid_index].angular_velocity = mk(av[0], av[1], av[2]);
+  return 0;
+}
+
+int oracle_dem_get_solid_vertices(lethe_dem_ctx *ctx, int32_t solid_index, uint32_t n_max, double *vertices3)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  if (solid_index < 0 || size_t(solid_index) >= o->solids.size())
+    return fail(o, "no such solid");
+  const Solid &sd = o->solids[solid_index];
+  for (uint32_t v = 0; v < std::min<size_t>(n_max, sd.vertices.size()); ++v)
+    for (int d = 0; d < 3; ++d)
+      vertices3[3 * v + d] = sd.vertices[v][d];
+  return 0;
+}
+
+int oracle_dem_get_solid_contacts(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *particle_id, uint32_t *solid,
+                                  uint32_t *triangle, double *tangential3)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  struct Row
+  {
+    uint32_t pid, solid, tri;
+    V3 h;
+  };
+  std::vector<Row> rows;
+  for (size_t sc = 0; sc < o->solids.size(); ++sc)
+    for (auto &tp : o->solids[sc].in_contact)
+      for (auto &pi : tp.second)
+        rows.push_back(Row{pi.first, uint32_t(sc), tp.first, pi.second.tangential_displacement});
+  std::sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
+    return std::tie(a.pid, a.solid, a.tri) < std::tie(b.pid, b.solid, b.tri);
+  });
+  const uint64_t n = std::min<uint64_t>(n_max, rows.size());
+  for (uint64_t k = 0; k < n; ++k)
+    {
+      particle_id[k] = rows[k].pid;
+      solid[k] = rows[k].solid;
+      triangle[k] = rows[k].tri;
+      for (int d = 0; d < 3; ++d)
+        tangential3[3 * k + d] = rows[k].h[d];
+    }
+  *n_out = rows.size();
   return 0;
 }
 

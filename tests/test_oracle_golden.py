@@ -251,3 +251,29 @@ def test_packing_in_box_application(oracle_lib):
     # printed digit and every particle to within a fraction of a diameter
     assert np.mean(err <= 1.01e-4) > 0.9, (np.mean(err <= 1.01e-4), err.max())
     assert err.max() < 0.2 * 0.005, err.max()
+
+
+@pytest.mark.parametrize("case", ["edge_vertex_contact", "CPES_double_edge_contact", "NPES_double_edge_contact",
+                                  "NPES_double_face_contact"])
+def test_particle_solid_surface_application_goldens(oracle_lib, case):
+    """applications_tests/lethe-particles/particle_solid_surface_*.prm: one sphere dropped on two
+    triangles; the logged velocity magnitude pins find_particle_triangle_projection, the
+    face/edge/vertex double-contact elimination and the solid-object contact force
+    (particle_wall_contact_force.cc:153-580). The statistics of iteration n are printed before the
+    step body, i.e. they show the state after n - 1 steps (dem.cc:1115-1120)."""
+    from lethe_b200.solver import box_wall_faces
+    from tests.util import solid_surface_case
+
+    c, params, x, props, vertices, triangles = solid_surface_case(case)
+    e = loader.oracle_engine(params.to_config())
+    e.set_walls(box_wall_faces(params.mesh))
+    e.add_solid_surface(vertices, triangles)
+    e.set_particles([0], x, props)
+    done = 0
+    for k, gold in enumerate(c["velocity_magnitude"], start=1):
+        target = k * c["log_frequency"] - 1
+        e.step(target - done)
+        done = target
+        _, _, p = e.get_particles()
+        v = float(np.sqrt((p[0, 3:6] ** 2).sum()))
+        assert abs(v - gold) <= 5.1e-5 * max(abs(gold), 1e-30) + 1e-12, (case, k, v, gold)  # 5 printed digits

@@ -97,3 +97,35 @@ def packing_parameters(extent, d=0.005, cell=None, pp_model="hertz_mindlin_limit
         if periodic[ax]:
             p.boundary_conditions.append(BoundaryCondition(type="periodic", periodic_id_0=2 * ax, periodic_id_1=2 * ax + 1, periodic_direction=ax))
     return p
+
+
+def solid_surface_case(name):
+    """Parameters, particle row and (rotated) solid mesh of one
+    applications_tests/lethe-particles/particle_solid_surface_<name> case
+    (tests/golden/solid_surface_goldens.json, made by make_solid_goldens.py)."""
+    with open(os.path.join(GOLDEN, "solid_surface_goldens.json")) as f:
+        c = json.load(f)[name]
+    p = DEMParameters()
+    p.time_step = c["dt"]
+    p.pp_model, p.pw_model, p.rolling_model = c["pp_model"], c["pw_model"], "constant"
+    p.g = tuple(c["g"])
+    p.neighborhood_threshold = c["neighborhood_threshold"]
+    p.dynamic_contact_search_factor = c["search_factor"]
+    p.particle_types = [ParticleType(diameter=c["diameter"], density=c["density"], young=c["young"], poisson=c["poisson"],
+                                     restitution=c["restitution"], friction=c["friction"])]
+    p.young_wall, p.poisson_wall = c["young_wall"], c["poisson_wall"]
+    p.restitution_wall, p.friction_wall = c["restitution_wall"], c["friction_wall"]
+    n = 2 ** c["refinement"]
+    p.mesh = Mesh((c["box"][0],) * 3, (c["box"][1],) * 3, (n, n, n), False, "morton")
+    d = c["diameter"]
+    mass = c["density"] * 4.0 / 3.0 * math.pi * (d * 0.5) ** 3
+    row = [0, d, mass, 0, 0, 0, 0, 0, 0]
+    # GridTools::rotate(axis, angle): Rodrigues' rotation matrix applied to every vertex
+    v = np.array(c["vertices"], dtype=np.float64)
+    a = np.array(c["rotation_axis"], dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    th = c["rotation_angle"]
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    R = math.cos(th) * np.eye(3) + math.sin(th) * K + (1 - math.cos(th)) * np.outer(a, a)
+    v = v @ R.T
+    return c, p, np.array([c["position"]]), np.array([row]), v, np.array(c["triangles"], dtype=np.uint32)
