@@ -10,6 +10,7 @@
 
 #include "dem_kernels.cuh"
 #include "dem_multi.cuh"
+#include "dem_solid.cuh"
 
 #define CU_TRY(call)                                                                                       \
   do                                                                                                       \
@@ -100,6 +101,14 @@ namespace dem
     dem::WallListView view() { return dem::WallListView{row_start.p, entry.p, hist.p, roll.p}; }
   };
 
+  struct SolidListBufs
+  {
+    DevBuf<uint32_t> row_start, entry;
+    DevBuf<double> hist, roll;
+    uint32_t n_rows = 0;
+    uint64_t n_entries = 0;
+    dem::SolidListView view() { return dem::SolidListView{row_start.p, entry.p, hist.p, roll.p}; }
+  };
 } // namespace dem
 
 using dem::DevBuf;
@@ -176,6 +185,24 @@ struct lethe_dem_ctx
   DevBuf<FloatingWallsDev> fw_dev;
   DevBuf<uint32_t> cell_fw_mask;
   bool walls_dirty = true;
+
+  // solid surfaces (dem_solid.cuh): topology and initial geometry on the host, current vertex
+  // positions / centres of rotation on the device
+  uint32_t n_solids = 0;
+  std::vector<double> solid_vertices_host;
+  std::vector<uint32_t> solid_tri_host, solid_tri_solid_host, solid_vertex_solid_host; // global vertex indices
+  std::vector<uint32_t> solid_vertex_start, solid_tri_start;                          // per solid offsets (+ end)
+  std::vector<dem::SolidMotionDev> solid_motion_host;
+  uint32_t n_solid_vertices_dev = 0; // vertices whose current position lives on the device
+  bool solids_dirty = false, solid_map_needed = false;
+  DevBuf<double> solid_vertices, solid_disp, solid_force, solid_torque;
+  DevBuf<uint32_t> solid_vertex_solid, solid_tri, solid_tri_solid, solid_es_start, solid_es_idx, solid_vs_start, solid_vs_idx;
+  DevBuf<dem::SolidMotionDev> solid_motion;
+  DevBuf<uint32_t> cell_tri_start, cell_tri, solid_active, solid_overflow;
+  dem::SolidListBufs slists[2];
+  uint32_t n_solid_active = 0;
+  volatile uint32_t *h_remap = nullptr; // mapped pinned: a solid vertex moved past the mapping criterion
+  uint32_t *d_remap = nullptr;
 
   // triggers / time (DEMActionManager + SimulationControl)
   uint64_t iteration_number = 0;

@@ -251,6 +251,161 @@ namespace
     return v;
   }
 
+
+  // ------------------------------------------------------ solid surfaces ----
+  SolidSetView solid_view(Ctx *c)
+  {
+    return SolidSetView{c->solid_vertices.p, c->solid_disp.p, c->solid_vertex_solid.p, c->solid_tri.p, c->solid_tri_solid.p,
+                        c->solid_es_start.p, c->solid_es_idx.p, c->solid_vs_start.p, c->solid_vs_idx.p, c->solid_motion.p,
+                        uint32_t(c->solid_vertex_solid_host.size()), uint32_t(c->solid_tri_solid_host.size()), c->n_solids};
+  }
+
+  // Uploads topology (and the geometry of solids added since the last upload; solids already on
+  // the device keep their current, moved vertices). SerialSolid::setup_containers
+  // (serial_solid.cc:617-682) gives the edge- / vertex-sharing neighbour tables.
+  void upload_solids(Ctx *c)
+  {
+    if (!c->solids_dirty)
+      return;
+    cudaStream_t s = c->stream;
+    const uint32_t nv = uint32_t(c->solid_vertex_solid_host.size()), nt = uint32_t(c->solid_tri_solid_host.size());
+    const uint32_t nv_old = c->n_solid_vertices_dev;
+    c->solid_vertices.ensure(3 * size_t(nv), 3 * size_t(nv_old), s);
+    c->solid_disp.ensure(3 * size_t(nv), 3 * size_t(nv_old), s);
+    if (nv > nv_old)
+      {
+        CU_TRY(cudaMemcpyAsync(c->solid_vertices.p + 3 * size_t(nv_old), c->solid_vertices_host.data() + 3 * size_t(nv_old),
+                               3 * size_t(nv - nv_old) * 8, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemsetAsync(c->solid_disp.p + 3 * size_t(nv_old), 0, 3 * size_t(nv - nv_old) * 8, s));
+      }
+    // motion records: new solids only (the centres of the old ones have moved on the device)
+    const uint32_t ns_old = nv_old ? c->solid_vertex_solid_host[nv_old - 1] + 1 : 0;
+    c->solid_motion.ensure(MAX_SOLIDS);
+    CU_TRY(cudaMemcpyAsync(c->solid_motion.p + ns_old, c->solid_motion_host.data() + ns_old,
+                           size_t(c->n_solids - ns_old) * sizeof(SolidMotionDev), cudaMemcpyHostToDevice, s));
+    // neighbour tables over the global triangle index
+    std::vector<std::vector<uint32_t>> cells_of_vertex(nv);
+    for (uint32_t t = 0; t < nt; ++t)
+      for (int k = 0; k < 3; ++k)
+        cells_of_vertex[c->solid_tri_host[3 * size_t(t) + k]].push_back(t);
+    std::vector<uint32_t> es_start(size_t(nt) + 1, 0), vs_start(size_t(nt) + 1, 0), es_idx, vs_idx;
+    for (uint32_t t = 0; t < nt; ++t)
+      {
+        std::vector<uint32_t> around;
+        for (int k = 0; k < 3; ++k)
+          {
+            const auto &l = cells_of_vertex[c->solid_tri_host[3 * size_t(t) + k]];
+            around.insert(around.end(), l.begin(), l.end());
+          }
+        std::sort(around.begin(), around.end());
+        around.erase(std::unique(around.begin(), around.end()), around.end());
+        for (uint32_t n : around)
+          {
+            if (n == t)
+              continue;
+            int sharing = 0;
+            for (int k = 0; k < 3; ++k)
+              for (int m = 0; m < 3; ++m)
+                if (c->solid_tri_host[3 * size_t(n) + k] == c->solid_tri_host[3 * size_t(t) + m])
+                  {
+                    ++sharing;
+                    break;
+                  }
+            (sharing == 1 ? vs_idx : es_idx).push_back(n);
+          }
+        es_start[size_t(t) + 1] = uint32_t(es_idx.size());
+        vs_start[size_t(t) + 1] = uint32_t(vs_idx.size());
+      }
+    auto up = [&](DevBuf<uint32_t> &d, const std::vector<uint32_t> &h) {
+      d.ensure(std::max<size_t>(h.size(), 1));
+      if (!h.empty())
+        CU_TRY(cudaMemcpyAsync(d.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
+    };
+    up(c->solid_vertex_solid, c->solid_vertex_solid_host);
+    up(c->solid_tri, c->solid_tri_host);
+    up(c->solid_tri_solid, c->solid_tri_solid_host);
+    up(c->solid_es_start, es_start);
+    up(c->solid_es_idx, es_idx);
+    up(c->solid_vs_start, vs_start);
+    up(c->solid_vs_idx, vs_idx);
+    c->solid_overflow.ensure(1);
+    CU_TRY(cudaMemsetAsync(c->solid_overflow.p, 0, 4, s));
+    CU_TRY(cudaStreamSynchronize(s)); // the host vectors above go out of scope
+    c->n_solid_vertices_dev = nv;
+    c->solids_dirty = false;
+  }
+
+  // Rebuild-time part: (re)map the solids onto the background grid when asked
+  // (find_floating_mesh_mapping_step / the first search), then every particle's candidate row.
+  void rebuild_solid_lists(Ctx *c)
+  {
+    if (!c->n_solids)
+      return;
+    cudaStream_t s = c->stream;
+    upload_solids(c);
+    const bool use_roll = c->cfg.rolling_model == LETHE_ROLLING_EPSD;
+    const uint32_t n_new = c->n_owned;
+    CU_TRY(cudaStreamSynchronize(s));
+    if (c->solid_map_needed || *c->h_remap)
+      {
+        const size_t nv = c->solid_vertex_solid_host.size();
+        std::vector<double> v(3 * nv);
+        CU_TRY(cudaMemcpyAsync(v.data(), c->solid_vertices.p, v.size() * 8, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        std::vector<uint32_t> start, tri;
+        map_solids_on_host(c->grid, v.data(), c->solid_tri_host.data(), uint32_t(c->solid_tri_solid_host.size()), start, tri);
+        c->cell_tri_start.ensure(start.size());
+        c->cell_tri.ensure(std::max<size_t>(tri.size(), 1));
+        CU_TRY(cudaMemcpyAsync(c->cell_tri_start.p, start.data(), start.size() * 4, cudaMemcpyHostToDevice, s));
+        if (!tri.empty())
+          CU_TRY(cudaMemcpyAsync(c->cell_tri.p, tri.data(), tri.size() * 4, cudaMemcpyHostToDevice, s));
+        // reset_displacement_monitoring
+        CU_TRY(cudaMemsetAsync(c->solid_disp.p, 0, 3 * nv * 8, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        *c->h_remap = 0;
+        c->solid_map_needed = false;
+      }
+    // cur_list has already been flipped by rebuild_lists: the old generation is cur_list ^ 1
+    SolidListBufs &olds = c->slists[c->cur_list ^ 1];
+    SolidListBufs &news = c->slists[c->cur_list];
+    c->counts.ensure(size_t(n_new) + 2);
+    c->scan_tmp.ensure(scan_tmp_elems(size_t(n_new) + 8));
+    news.row_start.ensure(size_t(n_new) + 2);
+    SolidBuildParams bp;
+    bp.cell_reg = c->st[c->cur].cell_reg.p;
+    bp.cell_tri_start = c->cell_tri_start.p;
+    bp.cell_tri = c->cell_tri.p;
+    bp.n_rows = n_new;
+    bp.old_list = olds.view();
+    bp.old_of_new = c->old_of_new.p;
+    bp.n_old_rows = olds.n_rows;
+    bp.clear_history = c->clear_history_trigger ? 1 : 0;
+    bp.new_list = news.view();
+    bp.counts = c->counts.p;
+    bp.use_roll = use_roll ? 1 : 0;
+    launch_count_solid_rows(bp, s);
+    exclusive_scan_u32(c->counts.p, news.row_start.p, size_t(n_new) + 1, c->scan_tmp.p, s);
+    const uint32_t n_entries = n_new ? read_u32(c, news.row_start.p + n_new) : 0;
+    news.entry.ensure(std::max<size_t>(n_entries, 1));
+    news.hist.ensure(std::max<size_t>(3 * size_t(n_entries), 1));
+    if (use_roll)
+      news.roll.ensure(std::max<size_t>(3 * size_t(n_entries), 1));
+    bp.new_list = news.view();
+    launch_fill_solid_rows(bp, s); // leaves counts[q] = row not empty
+    news.n_rows = n_new;
+    news.n_entries = n_entries;
+    // compact set of particles that have candidates
+    c->key.ensure(size_t(n_new) + 2);
+    exclusive_scan_u32(c->counts.p, c->key.p, size_t(n_new) + 1, c->scan_tmp.p, s);
+    c->n_solid_active = n_new ? read_u32(c, c->key.p + n_new) : 0;
+    c->solid_active.ensure(std::max<size_t>(c->n_solid_active, 1));
+    launch_compact_indices(c->counts.p, c->key.p, n_new, c->solid_active.p, s);
+    c->solid_force.ensure(std::max<size_t>(3 * size_t(n_new), 1));
+    c->solid_torque.ensure(std::max<size_t>(3 * size_t(n_new), 1));
+    CU_TRY(cudaMemsetAsync(c->solid_force.p, 0, 3 * size_t(n_new) * 8, s));
+    CU_TRY(cudaMemsetAsync(c->solid_torque.p, 0, 3 * size_t(n_new) * 8, s));
+  }
+
   // ------------------------------------------------------------ rebuild ----
   // Phase 1: periodic wrap, binning, counting sort along the Morton curve, permutation of the
   // owned particles into cell order (drops particles that left the domain or migrated away).
@@ -388,6 +543,7 @@ namespace
     neww.n_entries = n_wall;
 
     c->cur_list ^= 1;
+    rebuild_solid_lists(c);
     CU_TRY(cudaMemsetAsync(c->flag_dev.p, 0, 4 * sizeof(uint32_t), s));
     CU_TRY(cudaStreamSynchronize(s));
     *c->h_flag = 0; // no kernel in flight can touch the flag here
@@ -468,6 +624,44 @@ namespace
       }
     P.criterion = c->cfg.smallest_contact_search_criterion;
     P.moi_override = c->cfg.moi_override;
+    if (c->n_solids)
+      {
+        // dem.cc:1141-1147: move the solids (not in the closing half step, dem.cc:726-728), then
+        // the particle - solid surface contacts of this step
+        if (phase != PHASE_END)
+          {
+            SolidMoveParams mp;
+            mp.s = solid_view(c);
+            mp.dt = c->cfg.dt;
+            mp.criterion = 0.57735026918962576451 *
+                           std::sqrt((c->grid.h[0] * c->grid.h[0] + c->grid.h[1] * c->grid.h[1]) + c->grid.h[2] * c->grid.h[2]);
+            mp.flag_local = P.flag_local;
+            mp.flag_host = P.flag_host;
+            mp.remap_host = c->d_remap;
+            mp.flag_check = P.flag_check;
+            mp.flag_tag = P.flag_tag;
+            mp.spec_check = P.spec_check;
+            launch_move_solids(mp, s);
+          }
+        SolidContactParams sp;
+        sp.s = solid_view(c);
+        sp.list = c->slists[c->cur_list].view();
+        sp.active = c->solid_active.p;
+        sp.n_active = c->n_solid_active;
+        sp.in = P.in;
+        sp.force = c->solid_force.p;
+        sp.torque = c->solid_torque.p;
+        sp.overflow = c->solid_overflow.p;
+        sp.pw_model = c->cfg.pw_model;
+        sp.rolling_model = c->cfg.rolling_model;
+        sp.dt = c->cfg.dt;
+        sp.flag_check = P.flag_check;
+        sp.flag_tag = P.flag_tag;
+        sp.spec_check = P.spec_check;
+        launch_solid_contacts(sp, c->mt, s);
+        P.solid_force = c->solid_force.p;
+        P.solid_torque = c->solid_torque.p;
+      }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (c->timers_enabled)
       {
@@ -799,6 +993,14 @@ int lethe_dem_create(const lethe_dem_config *config, int device, lethe_dem_ctx *
         CU_TRY(cudaHostGetDevicePointer(&df, hf, 0));
         c->d_flag = static_cast<uint32_t *>(df);
       }
+      {
+        void *hf = nullptr, *df = nullptr;
+        CU_TRY(cudaHostAlloc(&hf, sizeof(uint32_t), cudaHostAllocMapped));
+        c->h_remap = static_cast<volatile uint32_t *>(hf);
+        *c->h_remap = 0;
+        CU_TRY(cudaHostGetDevicePointer(&df, hf, 0));
+        c->d_remap = static_cast<uint32_t *>(df);
+      }
       c->flag_dev.ensure(4);
       CU_TRY(cudaMemset(c->flag_dev.p, 0, 4 * sizeof(uint32_t)));
       for (auto &ev : c->step_done)
@@ -854,6 +1056,8 @@ void lethe_dem_destroy(lethe_dem_ctx *c)
       cudaEventDestroy(ev);
   if (c->h_flag)
     cudaFreeHost(const_cast<uint32_t *>(c->h_flag));
+  if (c->h_remap)
+    cudaFreeHost(const_cast<uint32_t *>(c->h_remap));
   if (c->stream)
     cudaStreamDestroy(c->stream);
   delete c;
@@ -873,6 +1077,8 @@ int lethe_dem_set_particles(lethe_dem_ctx *c, uint64_t n, const uint32_t *id, co
         c->lists[k].n_entries = 0;
         c->wlists[k].n_rows = 0;
         c->wlists[k].n_entries = 0;
+        c->slists[k].n_rows = 0;
+        c->slists[k].n_entries = 0;
       }
     if (c->slot_map_size)
       launch_fill_u32(c->slot_of_id.p, 0xffffffffu, c->slot_map_size, c->stream);
@@ -979,6 +1185,131 @@ int lethe_dem_set_boundary_motion(lethe_dem_ctx *c, uint32_t boundary_id, const 
         c->motions_host.push_back(m);
       }
     c->walls_dirty = true;
+  });
+}
+
+int lethe_dem_add_solid_surface(lethe_dem_ctx *c, uint32_t n_vertices, const double *vertices3, uint32_t n_triangles,
+                                const uint32_t *triangles3, const double tv[3], const double av[3], const double center[3],
+                                int32_t *solid_index)
+{
+  return guarded(c, [&] {
+    if (c->n_solids >= uint32_t(MAX_SOLIDS))
+      throw std::runtime_error("too many solid surfaces");
+    for (uint64_t k = 0; k < 3ull * n_triangles; ++k)
+      if (triangles3[k] >= n_vertices)
+        throw std::runtime_error("triangle refers to a vertex outside the solid");
+    const uint32_t v0 = uint32_t(c->solid_vertex_solid_host.size());
+    c->solid_vertices_host.resize(3 * size_t(v0));
+    c->solid_vertices_host.insert(c->solid_vertices_host.end(), vertices3, vertices3 + 3 * size_t(n_vertices));
+    c->solid_vertex_solid_host.insert(c->solid_vertex_solid_host.end(), n_vertices, c->n_solids);
+    for (uint64_t k = 0; k < 3ull * n_triangles; ++k)
+      c->solid_tri_host.push_back(v0 + triangles3[k]);
+    c->solid_tri_solid_host.insert(c->solid_tri_solid_host.end(), n_triangles, c->n_solids);
+    if (c->solid_vertex_start.empty())
+      {
+        c->solid_vertex_start.push_back(0);
+        c->solid_tri_start.push_back(0);
+      }
+    c->solid_vertex_start.push_back(uint32_t(c->solid_vertex_solid_host.size()));
+    c->solid_tri_start.push_back(uint32_t(c->solid_tri_solid_host.size()));
+    SolidMotionDev m;
+    for (int d = 0; d < 3; ++d)
+      {
+        m.translational_velocity[d] = tv[d];
+        m.angular_velocity[d] = av[d];
+        m.center_of_rotation[d] = center[d];
+      }
+    c->solid_motion_host.push_back(m);
+    if (solid_index)
+      *solid_index = int32_t(c->n_solids);
+    ++c->n_solids;
+    c->solids_dirty = true;
+    // DEMActionManager::set_solid_objects_enabled: the first search maps the solids
+    c->solid_map_needed = true;
+    c->contact_search_trigger = true;
+  });
+}
+
+int lethe_dem_set_solid_motion(lethe_dem_ctx *c, int32_t solid_index, const double tv[3], const double av[3])
+{
+  return guarded(c, [&] {
+    if (solid_index < 0 || uint32_t(solid_index) >= c->n_solids)
+      throw std::runtime_error("no such solid");
+    for (int d = 0; d < 3; ++d)
+      {
+        c->solid_motion_host[solid_index].translational_velocity[d] = tv[d];
+        c->solid_motion_host[solid_index].angular_velocity[d] = av[d];
+      }
+    const uint32_t n_on_device = c->n_solid_vertices_dev ? c->solid_vertex_solid_host[c->n_solid_vertices_dev - 1] + 1 : 0;
+    if (uint32_t(solid_index) < n_on_device)
+      {
+        // velocities only: the centre of rotation on the device has moved with the solid
+        SolidMotionDev *dst = c->solid_motion.p + solid_index;
+        CU_TRY(cudaMemcpyAsync(dst->translational_velocity, tv, 24, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(dst->angular_velocity, av, 24, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+      }
+  });
+}
+
+int lethe_dem_get_solid_vertices(lethe_dem_ctx *c, int32_t solid_index, uint32_t n_max, double *vertices3)
+{
+  return guarded(c, [&] {
+    if (solid_index < 0 || uint32_t(solid_index) >= c->n_solids)
+      throw std::runtime_error("no such solid");
+    upload_solids(c);
+    const uint32_t v0 = c->solid_vertex_start[solid_index], v1 = c->solid_vertex_start[solid_index + 1];
+    const uint32_t n = std::min(n_max, v1 - v0);
+    CU_TRY(cudaMemcpyAsync(vertices3, c->solid_vertices.p + 3 * size_t(v0), 3 * size_t(n) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int lethe_dem_get_solid_contacts(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *particle_id, uint32_t *solid,
+                                 uint32_t *triangle, double *tangential3)
+{
+  return guarded(c, [&] {
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    SolidListBufs &l = c->slists[c->cur_list];
+    const size_t n = c->n_solids ? l.n_rows : 0, E = c->n_solids ? l.n_entries : 0;
+    *n_out = E;
+    if (n_max < E || E == 0)
+      return;
+    std::vector<uint32_t> rs(n + 1), ent(E), ids(n);
+    std::vector<double> hist(3 * E);
+    CU_TRY(cudaMemcpy(rs.data(), l.row_start.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(ent.data(), l.entry.p, E * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(hist.data(), l.hist.p, 3 * E * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(ids.data(), c->st[c->cur].id.p, n * 4, cudaMemcpyDeviceToHost));
+    struct Row
+    {
+      uint32_t pid, solid, tri;
+      double h[3];
+    };
+    std::vector<Row> rows;
+    rows.reserve(E);
+    for (size_t q = 0; q < n; ++q)
+      for (uint32_t e = rs[q]; e < rs[q + 1]; ++e)
+        {
+          const uint32_t t = ent[e] & SOLID_INDEX_MASK;
+          const uint32_t sd = c->solid_tri_solid_host[t];
+          Row r{ids[q], sd, t - c->solid_tri_start[sd], {0, 0, 0}};
+          if (ent[e] & SOLID_HIST_BIT)
+            for (int d = 0; d < 3; ++d)
+              r.h[d] = hist[3 * size_t(e) + d];
+          rows.push_back(r);
+        }
+    std::sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
+      return a.pid != b.pid ? a.pid < b.pid : (a.solid != b.solid ? a.solid < b.solid : a.tri < b.tri);
+    });
+    for (size_t k = 0; k < rows.size(); ++k)
+      {
+        particle_id[k] = rows[k].pid;
+        solid[k] = rows[k].solid;
+        triangle[k] = rows[k].tri;
+        for (int d = 0; d < 3; ++d)
+          tangential3[3 * k + d] = rows[k].h[d];
+      }
   });
 }
 

@@ -141,6 +141,7 @@ namespace dem
     HaloPush halo;
     unsigned long long *touching_counter; // debug (store_forces)
     double *force_out, *torque_out;       // debug taps [N][3] or nullptr
+    const double *solid_force, *solid_torque; // [N][3] solid-surface contacts of this step (dem_solid.cuh) or nullptr
     FaceTable faces;
     const BoundaryMotionDev *motions;
     const FloatingWallsDev *floating;

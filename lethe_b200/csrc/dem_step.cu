@@ -507,6 +507,14 @@ namespace dem
             P.walls.entry[w] = we & ~WALL_HIST_BIT;
         }
 
+      // particle - solid surface contacts (calculate_particle_solid_object_contact, dem.cc:527-537),
+      // evaluated by k_solid_contacts just before this kernel
+      if (P.solid_force)
+        {
+          F = F + v3(P.solid_force[3 * size_t(i) + 0], P.solid_force[3 * size_t(i) + 1], P.solid_force[3 * size_t(i) + 2]);
+          T = T + v3(P.solid_torque[3 * size_t(i) + 0], P.solid_torque[3 * size_t(i) + 1], P.solid_torque[3 * size_t(i) + 2]);
+        }
+
       if (P.touching_counter && touching_count)
         atomicAdd(P.touching_counter, (unsigned long long)touching_count);
       if (P.force_out)

@@ -410,3 +410,69 @@ def test_baseline_config_workloads_parity(name):
     lockstep(g, o, 40, 10, force_rtol=1e-10 if name == "cohesive_jkr" else FORCE_RTOL, extra=walls_equal)
     assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 2
     assert g.get_stats().n_particles == o.get_stats().n_particles
+
+
+@pytest.mark.parametrize("case", ["edge_vertex_contact", "CPES_double_edge_contact", "NPES_double_edge_contact",
+                                  "NPES_double_face_contact"])
+def test_particle_solid_surface_goldens_on_gpu(case):
+    """The reference's particle_solid_surface_* application cases (one sphere on two triangles)
+    through the CUDA engine: same logged velocity magnitudes (5 printed digits) and agreement
+    with the oracle at 1e-9 over the whole run (up to 600 k steps, several bounces)."""
+    from tests.util import solid_surface_case
+
+    c, params, x, props, vertices, triangles = solid_surface_case(case)
+    cfg = params.to_config()
+    g, o = abi.load_engine(cfg), loader.oracle_engine(cfg)
+    for e in (g, o):
+        e.set_walls(box_wall_faces(params.mesh))
+        e.add_solid_surface(vertices, triangles)
+        e.set_particles([0], x, props)
+    done = 0
+    for k, gold in enumerate(c["velocity_magnitude"], start=1):
+        target = k * c["log_frequency"] - 1
+        g.step(target - done)
+        o.step(target - done)
+        done = target
+        (_, xg, pg), (_, xo, po) = g.get_particles(), o.get_particles()
+        v = float(np.sqrt((pg[0, 3:6] ** 2).sum()))
+        assert abs(v - gold) <= 5.1e-5 * abs(gold) + 1e-12, (case, k, v, gold)
+        assert np.abs(xg - xo).max() <= 1e-9 * max(np.abs(xo).max(), 1e-300), (case, k)
+        assert np.abs(pg - po).max() <= 1e-9 * np.abs(po).max(), (case, k)
+
+
+def test_moving_solid_surface_parity_stepwise():
+    """A packing raining on a tilted, translating and rotating triangle mesh (the set-up of
+    moving_solid_surface_hmlo.prm): candidate (particle, triangle) sets identical, forces and
+    positions at the lock-step bar, mapping refreshed several times as the solid moves."""
+    d = 0.005
+    ids, x, props, extent = random_packing(10, d=d, spacing=1.05, jitter=0.05, seed=13)
+    params = packing_parameters(extent, d=d, rolling="constant")
+    # an 6 x 6 grid of squares split into triangles, tilted, just under the packing's mid height
+    n = 6
+    L = extent[0] * 1.2
+    gx, gy = np.meshgrid(np.linspace(-0.1 * L, L, n + 1), np.linspace(-0.1 * L, L, n + 1), indexing="ij")
+    vertices = np.stack([gx.ravel(), gy.ravel(), 0.45 * extent[2] + 0.15 * gx.ravel()], axis=1)
+    tris = []
+    for i in range(n):
+        for j in range(n):
+            a, b, cc, dd = i * (n + 1) + j, (i + 1) * (n + 1) + j, (i + 1) * (n + 1) + j + 1, i * (n + 1) + j + 1
+            tris += [[a, b, cc], [a, cc, dd]]
+    cfg = params.to_config(store_forces=True)
+    g, o = abi.load_engine(cfg), loader.oracle_engine(cfg)
+    for e in (g, o):
+        e.set_walls(box_wall_faces(params.mesh))
+        e.add_solid_surface(vertices, tris, translational_velocity=(0.0, 0.0, 20.0), angular_velocity=(0.0, 3.0, 0.0),
+                            center_of_rotation=(0.5 * extent[0], 0.5 * extent[1], 0.5 * extent[2]))
+        e.set_particles(ids, x, props)
+
+    def solids_equal(step):
+        sg, so = g.get_solid_contacts(), o.get_solid_contacts()
+        assert all(np.array_equal(u, v) for u, v in zip(sg[:3], so[:3])), step
+        hs = max(np.abs(so[3]).max(), 1e-300) if len(so[3]) else 1.0
+        assert np.abs(sg[3] - so[3]).max() <= 1e-10 * hs if len(so[3]) else True, step
+        assert np.abs(g.get_solid_vertices(0) - o.get_solid_vertices(0)).max() == 0.0, step
+
+    lockstep(g, o, 60, 20, extra=solids_equal)
+    assert len(g.get_solid_contacts()[0]) > 50
+    assert (g.get_solid_contacts()[3] != 0).any()  # some contacts carry tangential history
+    assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 3
