@@ -107,8 +107,28 @@ class BoundaryCondition:
 
 
 @dataclass
+class SolidSurface:
+    """`subsection solid objects / solid surfaces / solid object N`
+    (source/core/parameters.cc, Parameters::RigidSolidObject; SerialSolid<2,3>)."""
+
+    mesh_file: str = ""
+    rotation_axis: tuple = (1.0, 0.0, 0.0)
+    rotation_angle: float = 0.0
+    translation: tuple = (0.0, 0.0, 0.0)
+    translational_velocity: tuple = (0.0, 0.0, 0.0)  # constant `Function expression`s only
+    angular_velocity: tuple = (0.0, 0.0, 0.0)
+    center_of_rotation: tuple = (0.0, 0.0, 0.0)
+
+
+@dataclass
 class Insertion:
     method: str = "volume"
+    list_x: tuple = ()
+    list_y: tuple = ()
+    list_z: tuple = ()
+    list_velocity: tuple = ()  # per particle (vx, vy, vz)
+    list_omega: tuple = ()
+    list_diameters: tuple = ()
     inserted_this_step: int = 0
     frequency: int = 1
     box_point_1: tuple = (0.0, 0.0, 0.0)
@@ -157,6 +177,7 @@ class DEMParameters:
     insertion: Insertion = field(default_factory=Insertion)
     boundary_conditions: list = field(default_factory=list)
     floating_walls: list = field(default_factory=list)  # (point, normal, t_start, t_end)
+    solid_surfaces: list = field(default_factory=list)  # SolidSurface
     restart: bool = False
     test_enabled: bool = False
 
@@ -374,7 +395,45 @@ def parameters_from_prm(text: str) -> DEMParameters:
         ins.initial_velocity = tuple(_floats(ii["initial velocity"]))
     if "initial angular velocity" in ii:
         ins.initial_omega = tuple(_floats(ii["initial angular velocity"]))
+    if ins.method == "list":
+        # insertion_list.cc: explicit positions / velocities / diameters
+        ins.list_x, ins.list_y, ins.list_z = (tuple(_floats(ii.get("list " + a, ""))) for a in "xyz")
+        n = len(ins.list_x)
+
+        def triple(prefix):
+            cols = [list(_floats(ii.get(f"list {prefix} {a}", ""))) for a in "xyz"]
+            cols = [c + [0.0] * (n - len(c)) for c in cols]
+            return tuple(zip(*cols)) if n else ()
+
+        ins.list_velocity, ins.list_omega = triple("velocity"), triple("omega")
+        ins.list_diameters = tuple(_floats(ii.get("list diameters", "")))
     p.insertion = ins
+
+    so = d.get("solid objects", {}).get("solid surfaces", {})
+    for i in range(int(so.get("number of solids", "0"))):
+        s = so.get(f"solid object {i}", {})
+        m = s.get("mesh", {})
+        if m.get("type", "gmsh") != "gmsh":
+            raise abi.DEMError("solid surfaces: only `mesh type = gmsh` files are read")
+
+        def constant_function(sub, default=(0.0, 0.0, 0.0)):
+            expr = s.get(sub, {}).get("Function expression")
+            if expr is None:
+                return default
+            try:
+                return tuple(float(v) for v in expr.split(";"))
+            except ValueError:
+                raise abi.DEMError(f"solid surfaces: `{sub}` must be constant (got {expr!r}); drive time-dependent motion "
+                                   "through Engine.set_solid_motion")
+
+        p.solid_surfaces.append(SolidSurface(
+            mesh_file=m.get("file name", ""),
+            rotation_axis=tuple(_floats(m.get("initial rotation axis", "1, 0, 0"))),
+            rotation_angle=float(m.get("initial rotation angle", "0")),
+            translation=tuple(_floats(m.get("initial translation", "0, 0, 0"))),
+            translational_velocity=constant_function("translational velocity"),
+            angular_velocity=constant_function("angular velocity"),
+            center_of_rotation=tuple(_floats(s.get("center of rotation", "0, 0, 0")))))
 
     bcs = d.get("DEM boundary conditions", {})
     for i in range(int(bcs.get("number of boundary conditions", "0"))):

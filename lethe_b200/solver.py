@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import numpy as np
 
@@ -117,11 +118,31 @@ def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particl
     return ids, x, props
 
 
+def list_insertion(p: DEMParameters, first_id: int = 0, particle_type: int = 0):
+    """InsertionList::insert (source/dem/insertion_list.cc): the listed positions, velocities and
+    diameters, all at the first insertion step."""
+    ins = p.insertion
+    n = len(ins.list_x)
+    t = p.particle_types[particle_type]
+    x = np.stack([np.asarray(ins.list_x), np.asarray(ins.list_y), np.asarray(ins.list_z)], axis=1).astype(np.float64)
+    d = np.asarray(ins.list_diameters if len(ins.list_diameters) == n else [t.diameter] * n, dtype=np.float64)
+    props = np.zeros((n, abi.N_PROPERTIES))
+    props[:, 0] = particle_type
+    props[:, 1] = d
+    props[:, 2] = t.density * 4.0 / 3.0 * math.pi * (d * 0.5) ** 3
+    if n:
+        props[:, 3:6] = np.asarray(ins.list_velocity)
+        props[:, 6:9] = np.asarray(ins.list_omega)
+    return np.arange(first_id, first_id + n, dtype=np.uint32), x, props
+
+
 class DEMSolver:
     """`DEMSolver<3, DEMProperties>` with the hot path behind the C ABI."""
 
-    def __init__(self, parameters: DEMParameters, engine_factory=None, device: int = 0, store_forces=False, moi_override=0.0):
+    def __init__(self, parameters: DEMParameters, engine_factory=None, device: int = 0, store_forces=False, moi_override=0.0,
+                 prm_directory="."):
         self.parameters = parameters
+        self.prm_directory = prm_directory  # mesh file names of the .prm are relative to it
         self.config = parameters.to_config(store_forces=store_forces, moi_override=moi_override)
         factory = engine_factory or (lambda cfg: abi.load_engine(cfg, device))
         self.engine = factory(self.config)
@@ -141,6 +162,20 @@ class DEMSolver:
         if p.floating_walls:
             pts, nrm, t0, t1 = zip(*p.floating_walls)
             self.engine.set_floating_walls(pts, nrm, t0, t1)
+        # DEMSolver::setup_solid_objects (dem.cc:164-191) + SerialSolid::setup_triangulation
+        # (serial_solid.cc:163-216: read, rotate, translate)
+        for so in p.solid_surfaces:
+            from .mesh_io import read_msh_triangles
+
+            path = so.mesh_file if os.path.isabs(so.mesh_file) else os.path.join(self.prm_directory, so.mesh_file)
+            vertices, triangles = read_msh_triangles(path)
+            a = np.asarray(so.rotation_axis, dtype=np.float64)
+            a = a / np.linalg.norm(a)
+            th = so.rotation_angle
+            K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+            rot = math.cos(th) * np.eye(3) + math.sin(th) * K + (1 - math.cos(th)) * np.outer(a, a)
+            vertices = vertices @ rot.T + np.asarray(so.translation)
+            self.engine.add_solid_surface(vertices, triangles, so.translational_velocity, so.angular_velocity, so.center_of_rotation)
         for bc in p.boundary_conditions:
             if bc.type == "rotational":
                 self.engine.set_boundary_motion(bc.boundary_id, (0, 0, 0), bc.rotational_speed, bc.rotational_vector, bc.point_on_rotational_vector)
@@ -161,8 +196,11 @@ class DEMSolver:
         remaining = self._remaining[self._current_type]
         if remaining == 0:
             return
-        n = min(p.insertion.inserted_this_step, remaining)
-        ids, x, props = volume_insertion(p, n, self._next_id, self._current_type)
+        if p.insertion.method == "list":
+            ids, x, props = list_insertion(p, self._next_id, self._current_type)
+        else:
+            n = min(p.insertion.inserted_this_step, remaining)
+            ids, x, props = volume_insertion(p, n, self._next_id, self._current_type)
         self.engine.add_particles(ids, x, props)
         self._next_id += len(ids)
         self._remaining[self._current_type] -= len(ids)

@@ -4,6 +4,7 @@ Each test replays the driver of a reference unit / application test through the
 oracle's C ABI and compares with the numbers the reference's ctest diffs against
 (tests/golden/*.json, extracted by tests/golden/make_golden.py)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -277,3 +278,23 @@ def test_particle_solid_surface_application_goldens(oracle_lib, case):
         _, _, p = e.get_particles()
         v = float(np.sqrt((p[0, 3:6] ** 2).sum()))
         assert abs(v - gold) <= 5.1e-5 * max(abs(gold), 1e-30) + 1e-12, (case, k, v, gold)  # 5 printed digits
+
+
+def test_solid_surface_prm_end_to_end(oracle_lib):
+    """The reference's own particle_solid_surface_NPES_double_edge_contact.prm (+ its gmsh file),
+    read by the .prm mirror — `subsection solid objects`, `insertion method = list` — and run
+    through DEMSolver: velocity magnitude after the first bounce as logged at iteration 380000
+    (the closing half kick of solve() changes it by g*dt/2, far below the printed digits)."""
+    import json
+
+    from tests.util import GOLDEN as GDIR
+
+    d = os.path.join(GDIR, "solid_surfaces")
+    params = load_prm(os.path.join(d, "particle_solid_surface_NPES_double_edge_contact.prm"))
+    assert params.insertion.method == "list" and len(params.solid_surfaces) == 1
+    solver = DEMSolver(params, engine_factory=loader.oracle_engine, prm_directory=d)
+    _, _, p = solver.solve(max_steps=379999)
+    with open(os.path.join(GDIR, "solid_surface_goldens.json")) as f:
+        gold = json.load(f)["NPES_double_edge_contact"]["velocity_magnitude"][37]
+    v = float(np.sqrt((p[0, 3:6] ** 2).sum()))
+    assert abs(v - gold) <= 1e-4 * gold, (v, gold)
