@@ -30,6 +30,9 @@ int LETHE_DEM_FN(get_particles)(lethe_dem_ctx *, uint64_t, uint64_t *, uint32_t 
 int LETHE_DEM_FN(set_walls)(lethe_dem_ctx *, uint64_t, const lethe_wall_face *);
 int LETHE_DEM_FN(set_floating_walls)(lethe_dem_ctx *, int32_t, const double *, const double *, const double *, const double *);
 int LETHE_DEM_FN(set_boundary_motion)(lethe_dem_ctx *, uint32_t, const double *, double, const double *, const double *);
+int LETHE_DEM_FN(add_solid_surface)(lethe_dem_ctx *, uint32_t, const double *, uint32_t, const uint32_t *, const double *, const double *,
+                                    const double *, int32_t *);
+int LETHE_DEM_FN(set_solid_motion)(lethe_dem_ctx *, int32_t, const double *, const double *);
 int LETHE_DEM_FN(step)(lethe_dem_ctx *, uint64_t);
 int LETHE_DEM_FN(synchronize_velocities)(lethe_dem_ctx *);
 int LETHE_DEM_FN(force_contact_search)(lethe_dem_ctx *, int);
@@ -97,6 +100,16 @@ namespace lethe_b200
     {
       check(LETHE_DEM_FN(set_boundary_motion)(ctx, boundary_id, v, speed, axis, point));
     }
+    // DEMSolver::setup_solid_objects (dem.cc:164-191): one SerialSolid<2,3> per call
+    int add_solid_surface(const std::vector<double> &vertices3, const std::vector<uint32_t> &triangles3, const double tv[3],
+                          const double av[3], const double center[3])
+    {
+      int32_t index = -1;
+      check(LETHE_DEM_FN(add_solid_surface)(ctx, uint32_t(vertices3.size() / 3), vertices3.data(), uint32_t(triangles3.size() / 3),
+                                            triangles3.data(), tv, av, center, &index));
+      return index;
+    }
+    void set_solid_motion(int solid, const double tv[3], const double av[3]) { check(LETHE_DEM_FN(set_solid_motion)(ctx, solid, tv, av)); }
     void step(uint64_t n_steps) { check(LETHE_DEM_FN(step)(ctx, n_steps)); }
     void synchronize_velocities() { check(LETHE_DEM_FN(synchronize_velocities)(ctx)); }
     void force_contact_search(bool clear_tangential_displacement)

@@ -76,7 +76,10 @@ namespace lethe_b200
     std::ifstream in(path);
     if (!in)
       throw std::runtime_error("cannot open parameter file " + path);
-    return from_prm(*parse_prm(in));
+    DEMParameters p = from_prm(*parse_prm(in));
+    const auto slash = path.find_last_of('/');
+    p.prm_directory = slash == std::string::npos ? "." : path.substr(0, slash);
+    return p;
   }
 
   DEMParameters DEMParameters::from_prm(const PrmSection &d)
@@ -177,6 +180,47 @@ namespace lethe_b200
       ins.initial_velocity = to_vec3(ii.get_list("initial velocity"), "initial velocity");
     if (ii.has("initial angular velocity"))
       ins.initial_omega = to_vec3(ii.get_list("initial angular velocity"), "initial angular velocity");
+
+    if (ins.method == "list")
+      {
+        ins.list_x = ii.get_list("list x");
+        ins.list_y = ii.get_list("list y");
+        ins.list_z = ii.get_list("list z");
+        ins.list_vx = ii.get_list("list velocity x");
+        ins.list_vy = ii.get_list("list velocity y");
+        ins.list_vz = ii.get_list("list velocity z");
+        ins.list_wx = ii.get_list("list omega x");
+        ins.list_wy = ii.get_list("list omega y");
+        ins.list_wz = ii.get_list("list omega z");
+        ins.list_diameters = ii.get_list("list diameters");
+      }
+
+    const PrmSection &so = d.sub("solid objects").sub("solid surfaces");
+    for (long i = 0; i < so.get_int("number of solids", 0); ++i)
+      {
+        const PrmSection &s = so.sub("solid object " + std::to_string(i));
+        const PrmSection &m = s.sub("mesh");
+        if (m.get("type", "gmsh") != "gmsh")
+          throw std::runtime_error("solid surfaces: only `mesh type = gmsh` files are read");
+        SolidSurface sd;
+        sd.mesh_file = m.get("file name", "");
+        if (m.has("initial rotation axis"))
+          sd.rotation_axis = to_vec3(m.get_list("initial rotation axis"), "initial rotation axis");
+        sd.rotation_angle = m.get_double("initial rotation angle", 0);
+        if (m.has("initial translation"))
+          sd.translation = to_vec3(m.get_list("initial translation"), "initial translation");
+        // constant `Function expression = a ; b ; c` only (time-dependent motion: lethe_dem_set_solid_motion)
+        auto constant_function = [&](const char *sub, Vec3 &out) {
+          const PrmSection &f = s.sub(sub);
+          if (f.has("Function expression"))
+            out = to_vec3(f.get_list("Function expression", ';'), sub);
+        };
+        constant_function("translational velocity", sd.translational_velocity);
+        constant_function("angular velocity", sd.angular_velocity);
+        if (s.has("center of rotation"))
+          sd.center_of_rotation = to_vec3(s.get_list("center of rotation"), "center of rotation");
+        p.solid_surfaces.push_back(sd);
+      }
 
     const PrmSection &bcs = d.sub("DEM boundary conditions");
     for (long i = 0; i < bcs.get_int("number of boundary conditions", 0); ++i)

@@ -66,10 +66,22 @@ namespace lethe_b200
     double time_start = 0, time_end = 0;
   };
 
-  // Parameters::Lagrangian::InsertionInfo (volume method)
+  // `subsection solid objects / solid surfaces / solid object N` (Parameters::RigidSolidObject,
+  // SerialSolid<2,3>): gmsh triangle surface, initial rotation / translation, constant velocities
+  struct SolidSurface
+  {
+    std::string mesh_file;
+    Vec3 rotation_axis{{1, 0, 0}};
+    double rotation_angle = 0;
+    Vec3 translation{{0, 0, 0}}, translational_velocity{{0, 0, 0}}, angular_velocity{{0, 0, 0}}, center_of_rotation{{0, 0, 0}};
+  };
+
+  // Parameters::Lagrangian::InsertionInfo (volume and list methods)
   struct InsertionInfo
   {
     std::string method = "volume";
+    // insertion_list.cc: explicit positions / velocities / diameters
+    std::vector<double> list_x, list_y, list_z, list_vx, list_vy, list_vz, list_wx, list_wy, list_wz, list_diameters;
     long inserted_this_step = 0;
     long frequency = 1;
     Vec3 box_point_1{{0, 0, 0}}, box_point_2{{1, 1, 1}};
@@ -106,6 +118,8 @@ namespace lethe_b200
     InsertionInfo insertion;
     std::vector<BoundaryCondition> boundary_conditions;
     std::vector<FloatingWall> floating_walls;
+    std::vector<SolidSurface> solid_surfaces;
+    std::string prm_directory = "."; // mesh file names are relative to the parameter file
     bool restart = false;
     bool test_enabled = false;
 

@@ -5,7 +5,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <iomanip>
+#include <array>
+#include <fstream>
 #include <iostream>
+#include <map>
 #include <sstream>
 
 namespace lethe_b200
@@ -121,6 +124,32 @@ namespace lethe_b200
           }
         engine->set_floating_walls(pts, nrm, t0, t1);
       }
+    // DEMSolver::setup_solid_objects (dem.cc:164-191); SerialSolid::setup_triangulation reads the
+    // mesh, rotates it (GridTools::rotate(axis, angle)) and translates it (serial_solid.cc:163-216)
+    for (const auto &so : parameters.solid_surfaces)
+      {
+        std::vector<double> v;
+        std::vector<uint32_t> t;
+        const std::string path = (!so.mesh_file.empty() && so.mesh_file[0] == '/') ? so.mesh_file : parameters.prm_directory + "/" + so.mesh_file;
+        read_msh_triangles(path, v, t);
+        Vec3 a = so.rotation_axis;
+        const double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        for (auto &c : a)
+          c /= an;
+        const double co = std::cos(so.rotation_angle), si = std::sin(so.rotation_angle);
+        const double K[3][3] = {{0, -a[2], a[1]}, {a[2], 0, -a[0]}, {-a[1], a[0], 0}};
+        double R[3][3];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c)
+            R[r][c] = co * (r == c ? 1.0 : 0.0) + si * K[r][c] + (1 - co) * a[r] * a[c];
+        for (size_t k = 0; k < v.size() / 3; ++k)
+          {
+            const double x[3] = {v[3 * k], v[3 * k + 1], v[3 * k + 2]};
+            for (int r = 0; r < 3; ++r)
+              v[3 * k + r] = (R[r][0] * x[0] + R[r][1] * x[1] + R[r][2] * x[2]) + so.translation[r];
+          }
+        engine->add_solid_surface(v, t, so.translational_velocity.data(), so.angular_velocity.data(), so.center_of_rotation.data());
+      }
     const double zero[3] = {0, 0, 0};
     for (const auto &bc : parameters.boundary_conditions)
       {
@@ -130,6 +159,118 @@ namespace lethe_b200
         else if (bc.type == "translational")
           engine->set_boundary_motion(bc.boundary_id, bc.translational_velocity.data(), 0.0, zero, zero);
       }
+  }
+
+  ParticleRows list_insertion(const DEMParameters &p, uint32_t first_id, int particle_type)
+  {
+    const InsertionInfo &ins = p.insertion;
+    const ParticleType &t = p.particle_types.at(particle_type);
+    const size_t n = ins.list_x.size();
+    auto at = [](const std::vector<double> &v, size_t k) { return k < v.size() ? v[k] : 0.0; };
+    ParticleRows rows;
+    for (size_t k = 0; k < n; ++k)
+      {
+        const double d = ins.list_diameters.size() == n ? ins.list_diameters[k] : t.average_diameter;
+        rows.id.push_back(first_id + uint32_t(k));
+        rows.x.insert(rows.x.end(), {ins.list_x[k], at(ins.list_y, k), at(ins.list_z, k)});
+        const double h = d * 0.5;
+        const double props[9] = {double(particle_type), d, t.density * 4.0 / 3.0 * M_PI * (h * h * h), at(ins.list_vx, k),
+                                 at(ins.list_vy, k),    at(ins.list_vz, k), at(ins.list_wx, k), at(ins.list_wy, k), at(ins.list_wz, k)};
+        rows.props.insert(rows.props.end(), props, props + 9);
+      }
+    return rows;
+  }
+
+  void read_msh_triangles(const std::string &path, std::vector<double> &vertices3, std::vector<uint32_t> &triangles3)
+  {
+    std::ifstream in(path);
+    if (!in)
+      throw std::runtime_error("cannot open solid surface mesh " + path);
+    std::map<std::string, std::vector<std::string>> sections;
+    std::string line, name;
+    while (std::getline(in, line))
+      {
+        line = PrmSection::trim(line);
+        if (line.empty())
+          continue;
+        if (line[0] == '$')
+          {
+            name = line.rfind("$End", 0) == 0 ? "" : line.substr(1);
+            continue;
+          }
+        if (!name.empty())
+          sections[name].push_back(line);
+      }
+    auto numbers = [](const std::string &s) {
+      std::vector<double> v;
+      std::istringstream is(s);
+      double x;
+      while (is >> x)
+        v.push_back(x);
+      return v;
+    };
+    if (!sections.count("MeshFormat") || !sections.count("Nodes") || !sections.count("Elements"))
+      throw std::runtime_error("not a gmsh ASCII file: " + path);
+    const double version = numbers(sections["MeshFormat"][0]).at(0);
+    std::map<long, std::array<double, 3>> nodes;
+    std::vector<std::array<long, 3>> tris;
+    const auto &nb = sections["Nodes"];
+    const auto &eb = sections["Elements"];
+    if (version >= 4.0)
+      {
+        size_t k = 1;
+        for (long b = 0, nblocks = long(numbers(nb[0]).at(0)); b < nblocks; ++b)
+          {
+            const long n_in_block = long(numbers(nb[k]).at(3));
+            for (long i = 0; i < n_in_block; ++i)
+              {
+                const auto xyz = numbers(nb[k + 1 + n_in_block + i]);
+                nodes[long(numbers(nb[k + 1 + i]).at(0))] = {{xyz.at(0), xyz.at(1), xyz.at(2)}};
+              }
+            k += 1 + 2 * size_t(n_in_block);
+          }
+        k = 1;
+        for (long b = 0, nblocks = long(numbers(eb[0]).at(0)); b < nblocks; ++b)
+          {
+            const auto head = numbers(eb[k]);
+            const long etype = long(head.at(2)), n_in_block = long(head.at(3));
+            for (long i = 0; i < n_in_block; ++i)
+              if (etype == 2)
+                {
+                  const auto e = numbers(eb[k + 1 + i]);
+                  tris.push_back({{long(e.at(1)), long(e.at(2)), long(e.at(3))}});
+                }
+            k += 1 + size_t(n_in_block);
+          }
+      }
+    else
+      {
+        for (long i = 0, n = long(numbers(nb[0]).at(0)); i < n; ++i)
+          {
+            const auto v = numbers(nb[1 + i]);
+            nodes[long(v.at(0))] = {{v.at(1), v.at(2), v.at(3)}};
+          }
+        for (long i = 0, n = long(numbers(eb[0]).at(0)); i < n; ++i)
+          {
+            const auto e = numbers(eb[1 + i]);
+            if (long(e.at(1)) == 2)
+              {
+                const size_t o = 3 + size_t(e.at(2));
+                tris.push_back({{long(e.at(o)), long(e.at(o + 1)), long(e.at(o + 2))}});
+              }
+          }
+      }
+    std::map<long, uint32_t> index;
+    vertices3.clear();
+    for (const auto &kv : nodes) // std::map: ascending node tag
+      {
+        index[kv.first] = uint32_t(index.size());
+        vertices3.insert(vertices3.end(), kv.second.begin(), kv.second.end());
+      }
+    triangles3.clear();
+    for (const auto &t : tris)
+      for (long v : t)
+        triangles3.push_back(index.at(v));
   }
 
   bool DEMSolverB200::insertion_due() const
@@ -149,7 +290,8 @@ namespace lethe_b200
     if (remaining == 0)
       return;
     const long n = std::min(parameters.insertion.inserted_this_step, remaining);
-    const ParticleRows rows = volume_insertion(parameters, n, next_id, current_inserting_type);
+    const ParticleRows rows = parameters.insertion.method == "list" ? list_insertion(parameters, next_id, current_inserting_type) :
+                                                                      volume_insertion(parameters, n, next_id, current_inserting_type);
     engine->add_particles(rows); // triggers the contact search (DEMActionManager::particle_insertion_step)
     next_id += uint32_t(rows.size());
     remaining_particles[current_inserting_type] -= long(rows.size());

@@ -26,6 +26,11 @@ namespace lethe_b200
   // (insertion_volume.cc:43-206, insertion.cc:60-121); jitter from glibc rand() exactly as
   // create_random_number_container does (include/core/utilities.h:1061-1073).
   ParticleRows volume_insertion(const DEMParameters &p, long n_insert, uint32_t first_id, int particle_type);
+  // InsertionList::insert (insertion_list.cc): the listed positions / velocities / diameters
+  ParticleRows list_insertion(const DEMParameters &p, uint32_t first_id, int particle_type);
+  // GridIn::read_msh for a triangle surface (gmsh 4.1 / 2.2 ASCII): vertices in node order,
+  // triangles in element order (SerialSolid::setup_triangulation, serial_solid.cc:163-175)
+  void read_msh_triangles(const std::string &path, std::vector<double> &vertices3, std::vector<uint32_t> &triangles3);
 
   class DEMSolverB200
   {

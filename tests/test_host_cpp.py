@@ -100,3 +100,27 @@ def test_product_binary_reproduces_reference_golden_on_gpu(tmp_path):
     r2 = subprocess.run([exe, str(prm2)], capture_output=True, text=True, check=True)
     assert "Transient iteration:" in r2.stdout and "Contact list generation" in r2.stdout
     check_against_golden(parse_xyz(r2.stdout[r2.stdout.index("id, type"):]))
+
+
+def test_host_sources_solid_surface_prm_against_oracle():
+    """The reference's particle_solid_surface_NPES_double_edge_contact.prm through the C++ host
+    (prm reader incl. `solid objects` and `insertion method = list`, gmsh reader, DEMSolver mirror,
+    statistics log) linked to the CPU oracle: the logged "Velocity magnitude" column equals the
+    reference's .output to its 5 printed digits at all 60 log lines."""
+    import re
+
+    loader.build()
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "lethe-particles-oracle")
+    srcs = [os.path.join(HOST, f) for f in ("dem_parameters.cc", "dem_solver.cc", "lethe_particles_b200.cc")]
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DLETHE_DEM_ABI_PREFIX=oracle_dem_", "-o", exe, *srcs, "-L" + odir,
+                           "-ldem_oracle", "-Wl,-rpath," + odir])
+    prm = os.path.join(GOLDEN, "solid_surfaces", "particle_solid_surface_NPES_double_edge_contact.prm")
+    r = subprocess.run([exe, prm], capture_output=True, text=True, check=True)
+    got = [float(m) for m in re.findall(r"Velocity magnitude\s*\|\s*\S+\s*\|\s*(\S+)", r.stdout)]
+    with open(os.path.join(GOLDEN, "solid_surface_goldens.json")) as f:
+        gold = json.load(f)["NPES_double_edge_contact"]["velocity_magnitude"]
+    assert len(got) == len(gold) == 60
+    assert all(abs(a - b) <= 1.01e-4 * abs(b) + 1e-12 for a, b in zip(got, gold)), list(zip(got, gold))[:5]
