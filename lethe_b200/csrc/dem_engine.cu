@@ -383,6 +383,11 @@ namespace
     bp.new_list = news.view();
     bp.counts = c->counts.p;
     bp.use_roll = use_roll ? 1 : 0;
+    bp.pay = HistPayload{c->n_pay ? c->pay.p : nullptr, c->pay_start.p, c->n_pay, c->slot_map_size, c->st[c->cur].id.p};
+    // a sphere touched more triangles than k_solid_contacts keeps for the elimination
+    if (read_u32(c, c->solid_overflow.p))
+      throw std::runtime_error("a particle touches more than 24 triangles of a solid surface at once: the mesh is too fine for "
+                               "the particle size (SOLID_MAX_CONTACTS)");
     launch_count_solid_rows(bp, s);
     exclusive_scan_u32(c->counts.p, news.row_start.p, size_t(n_new) + 1, c->scan_tmp.p, s);
     const uint32_t n_entries = n_new ? read_u32(c, news.row_start.p + n_new) : 0;

@@ -400,7 +400,7 @@ namespace dem
             for (uint32_t k = P.pay.start[qid]; k < P.pay.n && P.pay.rec[k].qid == qid; ++k)
               {
                 const HistRecord &rec = P.pay.rec[k];
-                if (rec.rid != rid || (rec.flags & HIST_REC_WALL) || ((rec.flags & HIST_REC_PERIODIC) != 0) != (img != 0))
+                if (rec.rid != rid || (rec.flags & (HIST_REC_WALL | HIST_REC_SOLID)) || ((rec.flags & HIST_REC_PERIODIC) != 0) != (img != 0))
                   continue;
                 word |= COL_HIST_BIT;
                 for (int d = 0; d < 3; ++d)
@@ -1014,6 +1014,28 @@ namespace dem
                   {
                     r.h[d] = P.walls.hist[3 * size_t(w) + d];
                     r.roll[d] = P.use_roll ? P.walls.roll[3 * size_t(w) + d] : 0.0;
+                  }
+                P.out[base + n] = r;
+              }
+            ++n;
+          }
+      if (P.solid_row_start && p < P.n_solid_rows)
+        for (uint32_t w = P.solid_row_start[p]; w < P.solid_row_start[p + 1]; ++w)
+          {
+            const uint32_t se = P.solid_entry[w];
+            if (!(se & 0x80000000u))
+              continue;
+            if (PACK)
+              {
+                HistRecord r;
+                r.qid = qid;
+                r.rid = se & 0x7fffffffu;
+                r.flags = HIST_REC_SOLID;
+                r.pad = 0;
+                for (int d = 0; d < 3; ++d)
+                  {
+                    r.h[d] = P.solid_hist[3 * size_t(w) + d];
+                    r.roll[d] = P.use_roll ? P.solid_roll[3 * size_t(w) + d] : 0.0;
                   }
                 P.out[base + n] = r;
               }

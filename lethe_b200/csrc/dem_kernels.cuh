@@ -216,7 +216,7 @@ namespace dem
     double h[3];    // tangential displacement in the orientation qid -> rid
     double roll[3]; // EPSD rolling spring torque (zero otherwise)
   };
-  constexpr uint32_t HIST_REC_PERIODIC = 1u, HIST_REC_WALL = 2u, HIST_REC_FLIPPED = 4u;
+  constexpr uint32_t HIST_REC_PERIODIC = 1u, HIST_REC_WALL = 2u, HIST_REC_FLIPPED = 4u, HIST_REC_SOLID = 8u;
   struct HistPackParams
   {
     const uint32_t *send_slot; // emigrants of one direction: slot in the (pre-sort) particle arrays
@@ -225,6 +225,11 @@ namespace dem
     ListView list;
     WallListView walls;
     uint32_t n_rows, n_wall_rows;
+    // solid-surface contact rows (dem_solid.cuh; nullptr when there are no solids): entry = global
+    // triangle index | bit 31 (history)
+    const uint32_t *solid_row_start, *solid_entry;
+    const double *solid_hist, *solid_roll;
+    uint32_t n_solid_rows;
     int use_roll, use_img;
     uint32_t *counts;          // [n + 1] (count pass) / exclusive offsets (pack pass)
     HistRecord *out;

@@ -669,7 +669,10 @@ namespace dem
             continue;
           m->hist_offsets[d].ensure(size_t(n_send[d]) + 2);
           c->scan_tmp.ensure(scan_tmp_elems(size_t(n_send[d]) + 8));
+          SolidListBufs &sl = c->slists[c->cur_list];
+          const bool solids = c->n_solids > 0 && sl.n_rows > 0;
           hp[d] = HistPackParams{m->send_slot[d].p, n_send[d], st.id.p, l.view(), wl.view(), l.n_rows, wl.n_rows,
+                                 solids ? sl.row_start.p : nullptr, sl.entry.p, sl.hist.p, sl.roll.p, solids ? sl.n_rows : 0u,
                                  use_roll ? 1 : 0, use_img ? 1 : 0, m->hist_offsets[d].p, nullptr};
           launch_hist_count(hp[d], s);
           exclusive_scan_u32(m->hist_offsets[d].p, m->hist_offsets[d].p, size_t(n_send[d]) + 1, c->scan_tmp.p, s);

@@ -257,6 +257,24 @@ namespace dem
                 for (int d = 0; d < 3; ++d)
                   P.new_list.roll[3 * size_t(e) + d] = P.old_list.roll[3 * size_t(eo) + d];
             }
+          else if (!have_old && !P.clear_history && P.pay.rec && P.pay.id[q] < P.pay.map_size)
+            {
+              // the contact_info of an immigrant came with it (HistRecord, HIST_REC_SOLID)
+              const uint32_t qid = P.pay.id[q];
+              for (uint32_t r = P.pay.start[qid]; r < P.pay.n && P.pay.rec[r].qid == qid; ++r)
+                {
+                  const HistRecord &rec = P.pay.rec[r];
+                  if (!(rec.flags & HIST_REC_SOLID) || rec.rid != t)
+                    continue;
+                  word |= SOLID_HIST_BIT;
+                  for (int d = 0; d < 3; ++d)
+                    P.new_list.hist[3 * size_t(e) + d] = rec.h[d];
+                  if (P.use_roll)
+                    for (int d = 0; d < 3; ++d)
+                      P.new_list.roll[3 * size_t(e) + d] = rec.roll[d];
+                  break;
+                }
+            }
           P.new_list.entry[e] = word;
         }
       P.counts[q] = e_end > P.new_list.row_start[q] ? 1u : 0u;

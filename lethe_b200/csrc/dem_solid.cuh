@@ -84,6 +84,7 @@ namespace dem
     SolidListView new_list;
     uint32_t *counts; // [n_rows + 1]; after the fill: 1 where the row is not empty
     int use_roll;
+    HistPayload pay; // history that arrived with particles that immigrated in this rebuild
   };
   void launch_count_solid_rows(const SolidBuildParams &p, cudaStream_t s);
   void launch_fill_solid_rows(const SolidBuildParams &p, cudaStream_t s);

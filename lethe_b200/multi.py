@@ -64,6 +64,11 @@ def create_slab_engine(workload, rank: int, world: int, device: int, dist=None, 
     engine.set_walls(workload.faces)
     for m in workload.motions:
         engine.set_boundary_motion(*m)
+    if getattr(workload, "floating_walls", None):
+        fw = workload.floating_walls
+        engine.set_floating_walls([w[0] for w in fw], [w[1] for w in fw], [w[2] for w in fw], [w[3] for w in fw])
+    for sd in getattr(workload, "solids", []):
+        engine.add_solid_surface(*sd)  # every rank holds every solid
     mask = owner_mask(workload.x, mesh, axis, lo, hi)
     engine.set_particles(workload.ids[mask], workload.x[mask], workload.props[mask])
     engine.slab = (axis, lo, hi)

@@ -121,6 +121,7 @@ class Workload:
         self.faces, self.motions = faces, list(motions)
         self.description = description
         self.floating_walls = list(floating_walls)  # (point, normal, t_start, t_end)
+        self.solids = []  # (vertices, triangles, translational velocity, angular velocity, centre of rotation)
 
     @property
     def n(self):
@@ -133,7 +134,22 @@ class Workload:
                                       [w[2] for w in self.floating_walls], [w[3] for w in self.floating_walls])
         for m in self.motions:
             engine.set_boundary_motion(*m)
+        for sd in self.solids:
+            engine.add_solid_surface(*sd)
         engine.set_particles(self.ids, self.x, self.props)
+
+
+def sheet_mesh(x0, x1, y0, y1, z_of_xy, n):
+    """An n x n grid of squares over [x0,x1] x [y0,y1], each split into two triangles, at height
+    z_of_xy(x, y): a stand-in for the gmsh surfaces of `subsection solid objects`."""
+    gx, gy = np.meshgrid(np.linspace(x0, x1, n + 1), np.linspace(y0, y1, n + 1), indexing="ij")
+    vertices = np.stack([gx.ravel(), gy.ravel(), z_of_xy(gx.ravel(), gy.ravel())], axis=1)
+    tris = []
+    for i in range(n):
+        for j in range(n):
+            a, b, c, d = i * (n + 1) + j, (i + 1) * (n + 1) + j, (i + 1) * (n + 1) + j + 1, i * (n + 1) + j + 1
+            tris += [[a, b, c], [a, c, d]]
+    return vertices, np.asarray(tris, dtype=np.uint32)
 
 
 def drum(n_target=1_000_000, d=0.003, radius=0.12, fill=0.45, seed=19, spacing=1.0, jitter=0.02):

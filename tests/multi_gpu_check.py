@@ -103,6 +103,17 @@ def main():
     w.props[:, 6:9] = np.random.default_rng(6).normal(0.0, 5.0, (w.n, 3))
     w.params.dynamic_contact_search_factor = 0.1
     ok &= run_case("hopper", w, (20, 60), rank, world, local_rank, tol=(1e-11, 1e-8))
+    # solid surface: a tilted sheet sweeping through a box packing along the slab axis, so that
+    # particles in contact with it (and with each other) change owner while they carry history
+    w = workloads.box_packing(n_side=max(16, 4 * world), nz=8, spacing=1.02, jitter=0.05)
+    w.props[:, 6:9] = np.random.default_rng(7).normal(0.0, 5.0, (w.n, 3))
+    w.props[:, 3] = 2.0  # the whole bed drifts along x: steady migration across the cuts
+    w.params.rolling_model = "constant"
+    w.params.dynamic_contact_search_factor = 0.1
+    hi = w.params.mesh.hi
+    v, t = workloads.sheet_mesh(-0.05 * hi[0], 1.05 * hi[0], -0.05 * hi[1], 1.05 * hi[1], lambda x, y: 0.3 * hi[2] + 0.2 * x, 8)
+    w.solids = [(v, t, (0.0, 0.0, 10.0), (0.0, 2.0, 0.0), (0.5 * hi[0], 0.5 * hi[1], 0.5 * hi[2]))]
+    ok &= run_case("solid", w, (20, 60), rank, world, local_rank, tol=(1e-11, 1e-8))
     dist.destroy_process_group()
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
