@@ -100,7 +100,12 @@ namespace dem
       for (int d = 0; d < 3; ++d)
         {
           const double r = (p[d] - g.lo[d]) / g.h[d];
-          const double f = floor(r);
+          double f = floor(r);
+          // a point exactly on a face shared by two cells belongs to the lower one (the
+          // reference's point location returns the first cell that contains the point; pinned by
+          // epsd_rolling_resistance_model.output)
+          if (r == f && f > 0.0)
+            f -= 1.0;
           if (!(f >= 0.0) || !(f < double(g.n[d])))
             return -1;
           idx[d] = int(f);

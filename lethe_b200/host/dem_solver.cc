@@ -359,10 +359,14 @@ namespace lethe_b200
         bool any_left = false;
         for (long r : remaining_particles)
           any_left = any_left || r > 0;
-        if (insertion_due() && any_left)
+        if (insertion_due())
           {
             flush(); // the insertion belongs to this iteration: run the earlier ones first
-            insert_particles();
+            if (any_left)
+              insert_particles();
+            // action_manager->particle_insertion_step() at every insertion iteration, whether or
+            // not particles are left to insert (dem.cc:494-500)
+            engine->force_contact_search(false);
           }
         ++pending;
       }

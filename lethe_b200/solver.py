@@ -219,12 +219,16 @@ class DEMSolver:
             self.iteration_number += 1
             self.current_time += self.parameters.time_step
             steps += 1
-            if self._insertion_due() and any(self._remaining):
+            if self._insertion_due():
                 # the insertion belongs to this iteration: flush earlier ones first
                 if pending:
                     self.engine.step(pending)
                     pending = 0
-                self._insert()
+                if any(self._remaining):
+                    self._insert()
+                # insert_particles calls action_manager->particle_insertion_step() at every insertion
+                # iteration, whether or not particles are left to insert (dem.cc:494-500)
+                self.engine.force_contact_search()
             pending += 1
         if pending:
             self.engine.step(pending)

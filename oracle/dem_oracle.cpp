@@ -518,7 +518,13 @@ namespace
     for (int d = 0; d < 3; ++d)
       {
         const double r = (x[d] - o.cfg.grid_lo[d]) / o.cfg.cell_size[d];
-        const double f = std::floor(r);
+        double f = std::floor(r);
+        // a point exactly on a face shared by two cells belongs to the lower one: the reference's
+        // point location returns the first (lowest-index) cell that contains the point. Pinned by
+        // epsd_rolling_resistance_model.output, whose resting spheres sit on cell corners and keep
+        // their wall-contact history only if they stay registered in the lower cell.
+        if (r == f && f > 0.0)
+          f -= 1.0;
         if (!(f >= 0.0) || !(f < double(n[d])))
           return -1; // left the triangulation: deal.II drops the particle
         idx[d] = int(f);

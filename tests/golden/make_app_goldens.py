@@ -1,0 +1,51 @@
+"""Copies the reference's lethe-particles application cases that run on a box mesh — parameter file
+(input data) plus the final `id, type, dp, x, y, z` table of the golden .output (numbers) — into
+tests/golden/apps/ (run where /root/reference is mounted).
+
+    python tests/golden/make_app_goldens.py
+"""
+import json
+import os
+import re
+import shutil
+
+REF = "/root/reference/applications_tests/lethe-particles"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "apps")
+CASES = {
+    "rolling_on_plane": "rolling_on_plane.output",
+    "velocity_verlet_free_fall": "velocity_verlet_free_fall.output",
+    "multiperiodic_collisions_3d": "multiperiodic_collisions_3d.output",
+    "multiperiodic_edge_contact_3d": "multiperiodic_edge_contact_3d.output",
+    "pp_jkr_equilibrium": "pp_jkr_equilibrium.output",
+    "pp_dmt_equilibrium": "pp_dmt_equilibrium.output",
+    "pw_jkr_equilibrium": "pw_jkr_equilibrium.output",
+    "pw_dmt_equilibrium": "pw_dmt_equilibrium.output",
+    "epsd_rolling_resistance_model": "epsd_rolling_resistance_model.output",
+    "sliding_in_box": "sliding_in_box.output",
+    "periodic_boundary_box": "periodic_boundary_box.output",
+    "moving_solid_surface_hmlo": "moving_solid_surface_hmlo.mpirun=1.output",
+    "moving_solid_surface_jkr": "moving_solid_surface_jkr.mpirun=1.output",
+    "moving_solid_surface_dmt": "moving_solid_surface_dmt.mpirun=1.output",
+}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    gold = {}
+    for case, output in CASES.items():
+        shutil.copy(f"{REF}/{case}.prm", f"{OUT}/{case}.prm")
+        rows = []
+        for line in open(f"{REF}/{output}"):
+            parts = line.split()
+            if len(parts) == 6 and parts[0].isdigit():
+                rows.append([int(parts[0]), int(parts[1])] + [float(v) for v in parts[2:]])
+        gold[case] = rows
+        print(case, len(rows), "rows")
+    # the moving_solid_surface cases name their mesh `../square.msh` relative to the run directory
+    shutil.copy(f"{REF}/moving_solid_surface_files/square.msh", os.path.join(os.path.dirname(OUT), "square.msh"))
+    with open(f"{OUT}/final_positions.json", "w") as f:
+        json.dump(gold, f)
+
+
+if __name__ == "__main__":
+    main()

@@ -476,3 +476,15 @@ def test_moving_solid_surface_parity_stepwise():
     assert len(g.get_solid_contacts()[0]) > 50
     assert (g.get_solid_contacts()[3] != 0).any()  # some contacts carry tangential history
     assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 3
+
+
+@pytest.mark.parametrize("case", ["rolling_on_plane", "multiperiodic_collisions_3d", "pp_jkr_equilibrium", "pp_dmt_equilibrium",
+                                  "pw_jkr_equilibrium", "pw_dmt_equilibrium", "epsd_rolling_resistance_model", "sliding_in_box",
+                                  "periodic_boundary_box", "moving_solid_surface_hmlo", "moving_solid_surface_jkr",
+                                  "moving_solid_surface_dmt"])
+def test_application_goldens_on_gpu(case):
+    """The reference's application tests (unmodified .prm files) through the CUDA engine: final
+    positions to the 4 printed decimals of the reference's .output."""
+    from tests.test_oracle_golden import run_application_case
+
+    run_application_case(case, lambda cfg: abi.load_engine(cfg))

@@ -298,3 +298,72 @@ def test_solid_surface_prm_end_to_end(oracle_lib):
         gold = json.load(f)["NPES_double_edge_contact"]["velocity_magnitude"][37]
     v = float(np.sqrt((p[0, 3:6] ** 2).sum()))
     assert abs(v - gold) <= 1e-4 * gold, (v, gold)
+
+
+APP_CASES = ["rolling_on_plane", "velocity_verlet_free_fall", "multiperiodic_collisions_3d", "multiperiodic_edge_contact_3d",
+             "pp_jkr_equilibrium", "pp_dmt_equilibrium", "pw_jkr_equilibrium", "pw_dmt_equilibrium", "epsd_rolling_resistance_model",
+             "sliding_in_box", "periodic_boundary_box", "moving_solid_surface_hmlo", "moving_solid_surface_jkr",
+             "moving_solid_surface_dmt"]
+
+
+def run_application_case(case, engine_factory):
+    d = os.path.join(GOLDEN, "apps")
+    params = load_prm(os.path.join(d, case + ".prm"))
+    solver = DEMSolver(params, engine_factory=engine_factory, prm_directory=d)
+    ids, x, props = solver.solve()
+    import json
+
+    with open(os.path.join(d, "final_positions.json")) as f:
+        rows = json.load(f)[case]
+    assert list(ids) == [r[0] for r in rows]
+    gold = np.array([r[3:6] for r in rows])
+    # the goldens print 4 decimals
+    assert np.abs(x - gold).max() <= 0.5e-4 + 1e-9, (case, np.abs(x - gold).max())
+    assert np.abs(props[:, 1] - np.array([r[2] for r in rows])).max() <= 0.5e-5 + 1e-12
+    return solver
+
+
+@pytest.mark.parametrize("case", APP_CASES)
+def test_application_goldens(oracle_lib, case):
+    """The reference's own lethe-particles application tests that run on box meshes, from their
+    unmodified .prm files through the .prm mirror + DEMSolver + oracle: final positions to the 4
+    printed decimals. Covers constant / viscous / EPSD rolling resistance, hertz_mindlin_limit_force,
+    JKR and DMT (particle-particle and particle-wall), periodic boundaries in 1 and 3 directions, list
+    and volume insertion, and moving solid surfaces with all three wall models."""
+    run_application_case(case, loader.oracle_engine)
+
+
+def test_epsd_application_log_statistics(oracle_lib):
+    """epsd_rolling_resistance_model.output also logs statistics every 5000 iterations: the number
+    of contact searches and the angular-velocity statistics through the multi-collision phase are
+    reproduced to the 5 printed digits (this is what pins the contact-search trigger at insertion
+    iterations and the lower-cell rule for points on cell faces)."""
+    from lethe_b200.solver import list_insertion
+
+    d = os.path.join(GOLDEN, "apps")
+    p = load_prm(os.path.join(d, "epsd_rolling_resistance_model.prm"))
+    e = loader.oracle_engine(p.to_config())
+    e.set_walls(box_wall_faces(p.mesh, p.outlet_boundaries, p.periodic))
+    e.add_particles(*list_insertion(p))
+    gold_searches = [3, 10, 22, 34, 42, 48, 54]
+    gold_omega = [(0.0, 6.2832, 4.7124), (0.0, 6.2832, 4.7124), (6.2832, 264.41, 88.006), (2.4912, 338.42, 159.38),
+                  (6.2832, 303.86, 123.10), (0.12798, 28.603, 13.803), (2.9838e-05, 6.2832, 2.2325)]
+    it = 0
+    for k in range(7):
+        target = (k + 1) * 5000 - 1
+        while it < target:
+            nxt = min(target, ((it // 10000) + 1) * 10000)  # stop before every insertion iteration (10001, 20001, ...)
+            e.step(nxt - it)
+            it = nxt
+            if it % 10000 == 0 and it < target:
+                e.force_contact_search()
+        _, _, props = e.get_particles()
+        w = np.sqrt((props[:, 6:9] ** 2).sum(axis=1))
+        assert e.get_stats().n_rebuilds == gold_searches[k], (k, e.get_stats().n_rebuilds)
+        for got, gold in zip((w.min(), w.max(), w.mean()), gold_omega[k]):
+            assert abs(got - gold) <= 2e-4 * abs(gold) + 1e-12, (k, got, gold)
+        if (it + 1) % 10000 == 0:
+            # iteration it + 2 == 10001 (mod 10000) is an insertion iteration
+            e.step(1)
+            it += 1
+            e.force_contact_search()
