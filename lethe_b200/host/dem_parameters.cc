@@ -195,6 +195,11 @@ namespace lethe_b200
         ins.list_diameters = ii.get_list("list diameters");
       }
 
+    if (ins.method == "file")
+      for (const auto &f : PrmSection::split(ii.get("list of input files", "particles.input"), ','))
+        if (!PrmSection::trim(f).empty())
+          ins.input_files.push_back(PrmSection::trim(f));
+
     const PrmSection &so = d.sub("solid objects").sub("solid surfaces");
     for (long i = 0; i < so.get_int("number of solids", 0); ++i)
       {

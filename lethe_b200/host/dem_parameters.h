@@ -82,6 +82,7 @@ namespace lethe_b200
     std::string method = "volume";
     // insertion_list.cc: explicit positions / velocities / diameters
     std::vector<double> list_x, list_y, list_z, list_vx, list_vy, list_vz, list_wx, list_wy, list_wz, list_diameters;
+    std::vector<std::string> input_files; // `insertion method = file`: `list of input files`
     long inserted_this_step = 0;
     long frequency = 1;
     Vec3 box_point_1{{0, 0, 0}}, box_point_2{{1, 1, 1}};

@@ -181,6 +181,41 @@ namespace lethe_b200
     return rows;
   }
 
+  ParticleRows file_insertion(const DEMParameters &p, const std::string &path, long n_max, uint32_t first_id, int particle_type)
+  {
+    std::ifstream in(path);
+    if (!in)
+      throw std::runtime_error("cannot open insertion file " + path);
+    std::string line;
+    std::getline(in, line);
+    std::vector<std::string> header;
+    for (const auto &h : PrmSection::split(line, ';'))
+      if (!PrmSection::trim(h).empty())
+        header.push_back(PrmSection::trim(h));
+    std::map<std::string, std::vector<double>> data;
+    while (std::getline(in, line))
+      {
+        const auto v = PrmSection::split_doubles(line, ';');
+        if (v.size() < header.size())
+          continue;
+        for (size_t k = 0; k < header.size(); ++k)
+          data[header[k]].push_back(v[k]);
+      }
+    const ParticleType &t = p.particle_types.at(particle_type);
+    const size_t n = std::min<size_t>(size_t(std::max(0l, n_max)), data["p_x"].size());
+    ParticleRows rows;
+    for (size_t k = 0; k < n; ++k)
+      {
+        const double d = data.at("diameters")[k], h = d * 0.5;
+        rows.id.push_back(first_id + uint32_t(k));
+        rows.x.insert(rows.x.end(), {data.at("p_x")[k], data.at("p_y")[k], data.at("p_z")[k]});
+        const double props[9] = {double(particle_type), d, t.density * 4.0 / 3.0 * M_PI * (h * h * h), data.at("v_x")[k], data.at("v_y")[k],
+                                 data.at("v_z")[k],     data.at("w_x")[k], data.at("w_y")[k], data.at("w_z")[k]};
+        rows.props.insert(rows.props.end(), props, props + 9);
+      }
+    return rows;
+  }
+
   void read_msh_triangles(const std::string &path, std::vector<double> &vertices3, std::vector<uint32_t> &triangles3)
   {
     std::ifstream in(path);
@@ -290,8 +325,19 @@ namespace lethe_b200
     if (remaining == 0)
       return;
     const long n = std::min(parameters.insertion.inserted_this_step, remaining);
-    const ParticleRows rows = parameters.insertion.method == "list" ? list_insertion(parameters, next_id, current_inserting_type) :
-                                                                      volume_insertion(parameters, n, next_id, current_inserting_type);
+    ParticleRows rows;
+    if (parameters.insertion.method == "file")
+      {
+        const auto &files = parameters.insertion.input_files;
+        std::string path = files.at(current_file_id++ % files.size());
+        if (path[0] != '/')
+          path = parameters.prm_directory + "/" + path;
+        rows = file_insertion(parameters, path, remaining, next_id, current_inserting_type);
+      }
+    else if (parameters.insertion.method == "list")
+      rows = list_insertion(parameters, next_id, current_inserting_type);
+    else
+      rows = volume_insertion(parameters, n, next_id, current_inserting_type);
     engine->add_particles(rows); // triggers the contact search (DEMActionManager::particle_insertion_step)
     next_id += uint32_t(rows.size());
     remaining_particles[current_inserting_type] -= long(rows.size());

@@ -28,6 +28,8 @@ namespace lethe_b200
   ParticleRows volume_insertion(const DEMParameters &p, long n_insert, uint32_t first_id, int particle_type);
   // InsertionList::insert (insertion_list.cc): the listed positions / velocities / diameters
   ParticleRows list_insertion(const DEMParameters &p, uint32_t first_id, int particle_type);
+  // InsertionFile::insert (insertion_file.cc:27-130): one `;`-separated table per insertion
+  ParticleRows file_insertion(const DEMParameters &p, const std::string &path, long n_max, uint32_t first_id, int particle_type);
   // GridIn::read_msh for a triangle surface (gmsh 4.1 / 2.2 ASCII): vertices in node order,
   // triangles in element order (SerialSolid::setup_triangulation, serial_solid.cc:163-175)
   void read_msh_triangles(const std::string &path, std::vector<double> &vertices3, std::vector<uint32_t> &triangles3);
@@ -59,6 +61,7 @@ namespace lethe_b200
     std::vector<long> remaining_particles; // per type
     int current_inserting_type = 0;
     uint32_t next_id = 0;
+    size_t current_file_id = 0;
     // contact_list statistics of report_statistics
     double list_min = 1e300, list_max = 0, list_total = 0;
   };

@@ -129,6 +129,7 @@ class Insertion:
     list_velocity: tuple = ()  # per particle (vx, vy, vz)
     list_omega: tuple = ()
     list_diameters: tuple = ()
+    input_files: tuple = ()  # `insertion method = file`: `list of input files`
     inserted_this_step: int = 0
     frequency: int = 1
     box_point_1: tuple = (0.0, 0.0, 0.0)
@@ -407,6 +408,8 @@ def parameters_from_prm(text: str) -> DEMParameters:
 
         ins.list_velocity, ins.list_omega = triple("velocity"), triple("omega")
         ins.list_diameters = tuple(_floats(ii.get("list diameters", "")))
+    if ins.method == "file":
+        ins.input_files = tuple(f.strip() for f in ii.get("list of input files", "particles.input").split(",") if f.strip())
     p.insertion = ins
 
     so = d.get("solid objects", {}).get("solid surfaces", {})

@@ -136,6 +136,27 @@ def list_insertion(p: DEMParameters, first_id: int = 0, particle_type: int = 0):
     return np.arange(first_id, first_id + n, dtype=np.uint32), x, props
 
 
+def file_insertion(p: DEMParameters, path: str, n_max: int, first_id: int = 0, particle_type: int = 0):
+    """InsertionFile::insert (source/dem/insertion_file.cc:27-130): one `;`-separated table
+    `p_x; p_y; p_z; v_x; v_y; v_z; w_x; w_y; w_z; diameters;` per insertion, at most `n_max` rows."""
+    with open(path) as f:
+        lines = [ln for ln in f.read().splitlines() if ln.strip()]
+    header = [h.strip() for h in lines[0].split(";") if h.strip()]
+    rows = [[float(v) for v in ln.split(";") if v.strip()] for ln in lines[1:]]
+    data = {h: np.array([r[k] for r in rows]) for k, h in enumerate(header)}
+    n = min(n_max, len(rows))
+    t = p.particle_types[particle_type]
+    x = np.stack([data["p_x"], data["p_y"], data["p_z"]], axis=1)[:n]
+    d = data["diameters"][:n]
+    props = np.zeros((n, abi.N_PROPERTIES))
+    props[:, 0] = particle_type
+    props[:, 1] = d
+    props[:, 2] = t.density * 4.0 / 3.0 * math.pi * (d * 0.5) ** 3
+    for k, key in enumerate(("v_x", "v_y", "v_z", "w_x", "w_y", "w_z")):
+        props[:, 3 + k] = data[key][:n]
+    return np.arange(first_id, first_id + n, dtype=np.uint32), x, props
+
+
 class DEMSolver:
     """`DEMSolver<3, DEMProperties>` with the hot path behind the C ABI."""
 
@@ -151,6 +172,7 @@ class DEMSolver:
         self._remaining = [t.number for t in parameters.particle_types]
         self._current_type = 0
         self._next_id = 0
+        self._file_id = 0
         self._setup_boundaries()
 
     # DEMSolver::setup_functions_and_pointers / boundary_cell_object.build
@@ -196,7 +218,13 @@ class DEMSolver:
         remaining = self._remaining[self._current_type]
         if remaining == 0:
             return
-        if p.insertion.method == "list":
+        if p.insertion.method == "file":
+            files = p.insertion.input_files
+            path = files[self._file_id % len(files)]
+            self._file_id += 1
+            path = path if os.path.isabs(path) else os.path.join(self.prm_directory, path)
+            ids, x, props = file_insertion(p, path, remaining, self._next_id, self._current_type)
+        elif p.insertion.method == "list":
             ids, x, props = list_insertion(p, self._next_id, self._current_type)
         else:
             n = min(p.insertion.inserted_this_step, remaining)

@@ -26,6 +26,7 @@ CASES = {
     "moving_solid_surface_hmlo": "moving_solid_surface_hmlo.mpirun=1.output",
     "moving_solid_surface_jkr": "moving_solid_surface_jkr.mpirun=1.output",
     "moving_solid_surface_dmt": "moving_solid_surface_dmt.mpirun=1.output",
+    "insert_file_3d": "insert_file_3d.mpirun=1.output",
 }
 
 
@@ -43,6 +44,7 @@ def main():
         print(case, len(rows), "rows")
     # the moving_solid_surface cases name their mesh `../square.msh` relative to the run directory
     shutil.copy(f"{REF}/moving_solid_surface_files/square.msh", os.path.join(os.path.dirname(OUT), "square.msh"))
+    shutil.copy(f"{REF}/insert_file_3d_files/particles.input", os.path.join(os.path.dirname(OUT), "particles.input"))
     with open(f"{OUT}/final_positions.json", "w") as f:
         json.dump(gold, f)
 

@@ -124,3 +124,25 @@ def test_host_sources_solid_surface_prm_against_oracle():
         gold = json.load(f)["NPES_double_edge_contact"]["velocity_magnitude"]
     assert len(got) == len(gold) == 60
     assert all(abs(a - b) <= 1.01e-4 * abs(b) + 1e-12 for a, b in zip(got, gold)), list(zip(got, gold))[:5]
+
+
+@pytest.mark.parametrize("case", ["insert_file_3d", "epsd_rolling_resistance_model", "moving_solid_surface_hmlo", "sliding_in_box"])
+def test_host_sources_application_goldens_against_oracle(case):
+    """More of the reference's application cases through the C++ host mirror (file / list / volume
+    insertion, solid objects, EPSD) linked to the oracle: the printed final table equals the
+    reference's .output to its 4 decimals."""
+    loader.build()
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "lethe-particles-oracle")
+    srcs = [os.path.join(HOST, f) for f in ("dem_parameters.cc", "dem_solver.cc", "lethe_particles_b200.cc")]
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DLETHE_DEM_ABI_PREFIX=oracle_dem_", "-o", exe, *srcs, "-L" + odir,
+                           "-ldem_oracle", "-Wl,-rpath," + odir])
+    r = subprocess.run([exe, os.path.join(GOLDEN, "apps", case + ".prm"), "--quiet"], capture_output=True, text=True, check=True)
+    rows = parse_xyz(r.stdout)
+    with open(os.path.join(GOLDEN, "apps", "final_positions.json")) as f:
+        gold = json.load(f)[case]
+    assert [r_[0] for r_ in rows] == [g[0] for g in gold]
+    err = np.abs(np.array([r_[3:6] for r_ in rows]) - np.array([g[3:6] for g in gold])).max()
+    assert err <= 1.01e-4, (case, err)  # both sides print 4 decimals
