@@ -64,6 +64,13 @@ def application_positions(name):
     return rows
 
 
+def contact_on_two_processors():
+    """tests/dem/particle_particle_contact_on_two_processors.mpirun=2.output: y of particle 0 every
+    10th step of a head-on collision across the boundary between the two ranks."""
+    txt = read("tests/dem/particle_particle_contact_on_two_processors.mpirun=2.output")
+    return [float(m) for m in re.findall(r"location of particle 0 is: \S+ (\S+)", txt)]
+
+
 def main():
     g = {}
     g["pp_force_nonlinear"] = floats(read("tests/dem/particle_particle_contact_force_nonlinear.output").split("is:")[1])[:3]
@@ -89,6 +96,7 @@ def main():
     cpo = read("tests/dem/combined_periodic_offsets.output")
     three = cpo.split("dim = 3")[1]
     g["combined_periodic_offsets_3d"] = [floats(l.split("::")[1]) for l in three.splitlines() if "(" in l]
+    g["contact_on_two_processors_y"] = contact_on_two_processors()
     g["find_contact_pairs"] = [
         [int(v) for v in re.findall(r"particle (\d+)", l)] for l in read("tests/dem/find_contact_pairs.output").splitlines() if "pair" in l
     ]

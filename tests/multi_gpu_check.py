@@ -79,6 +79,51 @@ def run_case(name, w, checkpoints, rank, world, local_rank, tol=(1e-9, 1e-6)):
     return bool(flag.item())
 
 
+def two_processor_golden(rank, world, local_rank):
+    """tests/dem/particle_particle_contact_on_two_processors.cc on two GPUs: the two spheres live
+    on different ranks (cut at y = 0, the reference's own 2-rank partition) and collide across the
+    cut. The slab run must equal the single-domain oracle to rounding, and the reference's 2-rank
+    golden to 3e-7 m (see test_contact_on_two_processors_golden)."""
+    import json
+
+    from lethe_b200 import abi
+    from tests.util import GOLDEN, two_processor_contact_case
+
+    p, kw, ids, x, props = two_processor_contact_case()
+    lo, hi = multi.slab_bounds(p.mesh.n[1], world)[rank]
+    eng = abi.load_engine(p.to_config(slab=(1, lo, hi), **kw), local_rank)
+    obj = [abi.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    eng.comm_init(rank, world, obj[0])
+    mask = multi.owner_mask(x, p.mesh, 1, lo, hi)
+    eng.set_particles(ids[mask], x[mask], props[mask])
+    with open(os.path.join(GOLDEN, "unit_goldens.json")) as f:
+        gold = json.load(f)["contact_on_two_processors_y"]
+    o = None
+    if rank == 0:
+        o = loader.oracle_engine(p.to_config(**kw))
+        o.set_particles(ids, x, props)
+    done, worst_o, worst_g = 0, 0.0, 0.0
+    for k, y in enumerate(gold):
+        target = 10 * k + 1
+        eng.step(target - done)
+        rows = gather_rows(eng.get_particles(), world)
+        if rank == 0:
+            o.step(target - done)
+            got = {int(i): xx for r in rows for i, xx in zip(r[0], r[1])}
+            yo = o.get_particles()[1][0, 1]
+            worst_o = max(worst_o, abs(got[0][1] - yo))
+            worst_g = max(worst_g, abs(got[0][1] - y))
+        done = target
+    ok = True
+    if rank == 0:
+        print(f"[two-processor golden] ranks={world} max|y - oracle|={worst_o:.2e} max|y - reference 2-rank golden|={worst_g:.2e}", flush=True)
+        ok = worst_o <= 1e-15 and worst_g <= 3e-7
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    return bool(flag.item())
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -114,6 +159,8 @@ def main():
     v, t = workloads.sheet_mesh(-0.05 * hi[0], 1.05 * hi[0], -0.05 * hi[1], 1.05 * hi[1], lambda x, y: 0.3 * hi[2] + 0.2 * x, 8)
     w.solids = [(v, t, (0.0, 0.0, 10.0), (0.0, 2.0, 0.0), (0.5 * hi[0], 0.5 * hi[1], 0.5 * hi[2]))]
     ok &= run_case("solid", w, (20, 60), rank, world, local_rank, tol=(1e-11, 1e-8))
+    if world == 2:
+        ok &= two_processor_golden(rank, world, local_rank)
     dist.destroy_process_group()
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)

@@ -129,3 +129,19 @@ def solid_surface_case(name):
     R = math.cos(th) * np.eye(3) + math.sin(th) * K + (1 - math.cos(th)) * np.outer(a, a)
     v = v @ R.T
     return c, p, np.array([c["position"]]), np.array([row]), v, np.array(c["triangles"], dtype=np.uint32)
+
+
+def two_processor_contact_case():
+    """tests/dem/particle_particle_contact_on_two_processors.cc: two spheres (m = 1, MOI = 1) collide
+    head-on across y = 0, the boundary between the two ranks' halves of a 4 x 4 mesh; search and
+    `integrate` (no opening half step) every step. 3-D stand-in of the 2-D test: same physics in
+    the z = 0 plane. Returns (parameters, config kwargs, ids, x, props)."""
+    p = unit_test_parameters(young=5e7, restitution=0.9, friction=0.5, rolling_friction=0.1, rolling_viscous=0.5, dt=1e-5, g=(0, 0, 0))
+    p.particle_types[0].poisson = 0.9
+    p.contact_detection_method = "constant"
+    p.contact_detection_frequency = 1
+    p.restart = True  # the test calls integrate() from the first step
+    ids = np.array([0, 1], dtype=np.uint32)
+    x = np.array([[0.0, 0.003, 0.0], [0.0, -0.003, 0.0]])
+    props = np.array([props_row(0, 0.005, 1.0, v=(0, -0.5, 0)), props_row(0, 0.005, 1.0, v=(0, 0.5, 0))], dtype=np.float64)
+    return p, dict(moi_override=1.0), ids, x, props
