@@ -20,7 +20,8 @@
 // of the previous round, cp.async staging of the next round, deeper or shallower sweep
 // pipelines (SWEEP 2 / 8), 3 / 5 / 6 resident blocks per SM, a 256-slot queue, reading
 // neighbours that belong to the warp's own 32 rows from shared memory instead of through L1
-// (+6 %: divergence costs more than the gathers) — the kernel is bound by the issue latency
+// (+6 %: divergence costs more than the gathers), an L2 persisting access-policy window on the
+// position array being gathered (+10 %) — the kernel is bound by the issue latency
 // of dependent FP64 chains at 16 warps/SM. What did pay: prefetch.global.L2 of the round
 // operands as soon as the sweep finds a touching entry (-2 %).
 // Neighbours are read from state generation g, results go to g^1.
