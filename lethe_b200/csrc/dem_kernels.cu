@@ -890,51 +890,67 @@ namespace dem
   void launch_bin(const BinParams &p, cudaStream_t s)
   {
     if (p.n)
-      k_bin<<<blocks_for(p.n, 256), 256, 0, s>>>(p);
-      count_launch();
+      {
+        k_bin<<<blocks_for(p.n, 256), 256, 0, s>>>(p);
+        count_launch();
+      }
   }
   void launch_scatter_perm(const uint32_t *key, const uint32_t *slot, const uint32_t *cell_start, uint32_t *perm, uint32_t n,
                            cudaStream_t s)
   {
     if (n)
-      k_scatter_perm<<<blocks_for(n, 256), 256, 0, s>>>(key, slot, cell_start, perm, n);
-      count_launch();
+      {
+        k_scatter_perm<<<blocks_for(n, 256), 256, 0, s>>>(key, slot, cell_start, perm, n);
+        count_launch();
+      }
   }
   void launch_sort_cells(const uint32_t *cell_start, uint32_t n_buckets, uint32_t *perm, const uint32_t *id, cudaStream_t s)
   {
     if (n_buckets)
-      k_sort_cells<<<blocks_for(n_buckets, 256), 256, 0, s>>>(cell_start, n_buckets, perm, id);
-      count_launch();
+      {
+        k_sort_cells<<<blocks_for(n_buckets, 256), 256, 0, s>>>(cell_start, n_buckets, perm, id);
+        count_launch();
+      }
   }
   void launch_gather(const GatherParams &p, cudaStream_t s)
   {
     if (p.n_new)
-      k_gather<<<blocks_for(p.n_new, 256), 256, 0, s>>>(p);
-      count_launch();
+      {
+        k_gather<<<blocks_for(p.n_new, 256), 256, 0, s>>>(p);
+        count_launch();
+      }
   }
   void launch_count_neighbors(const NeighborParams &p, cudaStream_t s)
   {
     if (p.n_rows)
-      k_count_neighbors<<<blocks_for(p.n_rows, 128), 128, 0, s>>>(p);
-      count_launch();
+      {
+        k_count_neighbors<<<blocks_for(p.n_rows, 128), 128, 0, s>>>(p);
+        count_launch();
+      }
   }
   void launch_fill_neighbors(const NeighborParams &p, cudaStream_t s)
   {
     if (p.n_rows)
-      k_fill_neighbors<<<blocks_for(p.n_rows, 128), 128, 0, s>>>(p);
-      count_launch();
+      {
+        k_fill_neighbors<<<blocks_for(p.n_rows, 128), 128, 0, s>>>(p);
+        count_launch();
+      }
   }
   void launch_count_walls(const WallBuildParams &p, cudaStream_t s)
   {
     if (p.n_rows)
-      k_count_walls<<<blocks_for(p.n_rows, 256), 256, 0, s>>>(p);
-      count_launch();
+      {
+        k_count_walls<<<blocks_for(p.n_rows, 256), 256, 0, s>>>(p);
+        count_launch();
+      }
   }
   void launch_fill_walls(const WallBuildParams &p, cudaStream_t s)
   {
     if (p.n_rows)
-      k_fill_walls<<<blocks_for(p.n_rows, 256), 256, 0, s>>>(p);
-      count_launch();
+      {
+        k_fill_walls<<<blocks_for(p.n_rows, 256), 256, 0, s>>>(p);
+        count_launch();
+      }
   }
   void launch_stats(StateView st, uint32_t n, double moi_override, StatsPartial *partials, uint32_t n_blocks, cudaStream_t s)
   {
@@ -945,29 +961,37 @@ namespace dem
                                uint32_t *id_out, int32_t *cell_reg, double *disp, uint32_t base, cudaStream_t s)
   {
     if (n)
-      k_unpack_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, x3, props9, n, st, id_out, cell_reg, disp, base);
-      count_launch();
+      {
+        k_unpack_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, x3, props9, n, st, id_out, cell_reg, disp, base);
+        count_launch();
+      }
   }
   void launch_update_from_host_rows(const uint32_t *ids, const double *x3, const double *props9, uint32_t n,
                                     const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, cudaStream_t s)
   {
     if (n)
-      k_update_from_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, x3, props9, n, slot_of_id, slot_map_size, st);
-      count_launch();
+      {
+        k_update_from_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, x3, props9, n, slot_of_id, slot_map_size, st);
+        count_launch();
+      }
   }
   void launch_pack_host_rows(const uint32_t *ids, uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st,
                              double *x3, double *props9, cudaStream_t s)
   {
     if (n)
-      k_pack_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, n, slot_of_id, slot_map_size, st, x3, props9);
-      count_launch();
+      {
+        k_pack_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, n, slot_of_id, slot_map_size, st, x3, props9);
+        count_launch();
+      }
   }
   void launch_pack_all_rows(StateView st, const uint32_t *id, uint32_t n, uint32_t *ids_out, double *x3, double *props9,
                             cudaStream_t s)
   {
     if (n)
-      k_pack_all_rows<<<blocks_for(n, 256), 256, 0, s>>>(st, id, n, ids_out, x3, props9);
-      count_launch();
+      {
+        k_pack_all_rows<<<blocks_for(n, 256), 256, 0, s>>>(st, id, n, ids_out, x3, props9);
+        count_launch();
+      }
   }
   namespace
   {
@@ -1225,7 +1249,9 @@ namespace dem
   void launch_fill_u32(uint32_t *p, uint32_t v, size_t n, cudaStream_t s)
   {
     if (n)
-      k_fill_u32<<<unsigned(std::min<size_t>((n + 255) / 256, 148 * 16)), 256, 0, s>>>(p, v, n);
-      count_launch();
+      {
+        k_fill_u32<<<unsigned(std::min<size_t>((n + 255) / 256, 148 * 16)), 256, 0, s>>>(p, v, n);
+        count_launch();
+      }
   }
 } // namespace dem
