@@ -73,3 +73,50 @@ def test_gloo_world2_ownership_and_id_broadcast(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
     assert "GLOO_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_periodic_box_generated_per_slab_equals_global_generation():
+    """bench.py's config-5 workload is built one slab at a time (a 64 M-sphere job never exists on
+    one host): the union of the per-rank pieces must be exactly the single-domain workload and
+    every piece must lie inside its rank's slab."""
+    kw = dict(cells=(12, 6, 6), spacing=1.0, jitter=0.03, vel_sigma=0.5)
+    whole = workloads.periodic_box(**kw)
+    for world in (2, 3, 4):
+        parts = [workloads.periodic_box(slab=(r, world), **kw) for r in range(world)]
+        assert all(p.n_global == whole.n for p in parts)
+        ids = np.concatenate([p.ids for p in parts])
+        order = np.argsort(ids)
+        assert np.array_equal(ids[order], np.sort(whole.ids))
+        ref = np.argsort(whole.ids)
+        assert np.array_equal(np.concatenate([p.x for p in parts])[order], whole.x[ref])
+        assert np.array_equal(np.concatenate([p.props for p in parts])[order], whole.props[ref])
+        bounds = multi.slab_bounds(whole.params.mesh.n[0], world)
+        for r, p in enumerate(parts):
+            assert multi.owner_mask(p.x, p.params.mesh, 0, *bounds[r]).all()
+
+
+def test_gloo_world2_slab_generation_and_forced_search_agreement(tmp_path):
+    """world_size-2 gloo run of the host logic around the per-step agreement: each rank builds its
+    slab, and the logical-or of a rank-local trigger (e.g. an insertion on one rank) reaches both."""
+    script = tmp_path / "w2b.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch, torch.distributed as dist
+        from lethe_b200 import multi, workloads
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        w = workloads.periodic_box(cells=(8, 4, 4), slab=(rank, world))
+        n = torch.tensor([w.n]); dist.all_reduce(n)
+        trigger = torch.tensor([0x80000000 if rank == 1 else 0], dtype=torch.int64)   # host bit of rank 1 only
+        dist.all_reduce(trigger, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert int(n) == w.n_global == 8 * 4 * 4 * 4, (int(n), w.n_global)
+            assert int(trigger) == 0x80000000
+            print("GLOO_OK")
+        dist.destroy_process_group()
+    """))
+    port = _free_port()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
+    assert "GLOO_OK" in out.stdout, out.stdout + out.stderr
