@@ -298,32 +298,57 @@ def main():
             pass
 
     # ---- e2e: per-step plugin call with pinned host rows ----
-    e2e = None
-    if world == 1:
-        ids, x, props = engine.get_particles()
-        n = len(ids)
-        hid = torch.from_numpy(ids.copy()).pin_memory()
-        hx = torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
-        hp = torch.from_numpy(np.ascontiguousarray(props)).pin_memory()
-        for _ in range(3):
-            engine.step_host_ptr(1, n, hid.data_ptr(), hx.data_ptr(), hp.data_ptr())
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            engine.step_host_ptr(1, n, hid.data_ptr(), hx.data_ptr(), hp.data_ptr())
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        sub = 100
-        t0 = time.perf_counter()
-        for _ in range(3):
-            engine.step_host_ptr(sub, n, hid.data_ptr(), hx.data_ptr(), hp.data_ptr())
-        dtb = time.perf_counter() - t0
-        e2e = {
-            "value": n * args.e2e_steps / dt, "unit": "particle-steps/s",
-            "h2d_bytes_per_step": n * (4 + 24 + 72), "d2h_bytes_per_step": n * (24 + 72),
-            "call": "lethe_dem_step_host(n_steps=1): upload id/x/props rows, 1 DEM step, download x/props rows, every step",
-            "batched": {"steps_per_call": sub, "value": n * sub * 3 / dtb, "unit": "particle-steps/s"},
-        }
+    # Every rank keeps host rows of the particles it owns and hands them to lethe_dem_step_host
+    # every step (rows up, one step, rows down). When a step rebuilt the lists, particles may have
+    # changed owner: the rank then re-reads its owned rows (inside the timed region).
+    def owned_rows():
+        ids_, x_, props_ = engine.get_particles()
+        return (torch.from_numpy(ids_.copy()).pin_memory(), torch.from_numpy(np.ascontiguousarray(x_)).pin_memory(),
+                torch.from_numpy(np.ascontiguousarray(props_)).pin_memory())
+
+    def host_step(rows, n_steps, rebuilds_seen):
+        hid, hx, hp = rows
+        engine.step_host_ptr(n_steps, len(hid), hid.data_ptr(), hx.data_ptr(), hp.data_ptr())
+        if world > 1:
+            r = engine.get_stats().n_rebuilds
+            if r != rebuilds_seen:
+                return owned_rows(), r
+        return rows, rebuilds_seen
+
+    rows = owned_rows()
+    seen = engine.get_stats().n_rebuilds
+    for _ in range(3):
+        rows, seen = host_step(rows, 1, seen)
+    barrier()
+    t0 = time.perf_counter()
+    n_moved = 0
+    for _ in range(args.e2e_steps):
+        n_moved += len(rows[0])
+        rows, seen = host_step(rows, 1, seen)
+    barrier()
+    dt = time.perf_counter() - t0
+    sub = 100
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        rows, seen = host_step(rows, sub, seen)
+    barrier()
+    dtb = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt, dtb], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dtb = float(tt[0].item()), float(tt[1].item())
+        nn = torch.tensor([float(n_moved)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        n_moved = int(nn.item())
+    per_step = n_moved / max(1, args.e2e_steps)
+    e2e = {
+        "value": n_moved / dt, "unit": "particle-steps/s",
+        "h2d_bytes_per_step": int(per_step * (4 + 24 + 72)), "d2h_bytes_per_step": int(per_step * (24 + 72)),
+        "call": "lethe_dem_step_host(n_steps=1) on every rank: upload id/x/props rows of the owned particles, 1 DEM step, "
+                "download x/props rows, every step",
+        "batched": {"steps_per_call": sub, "value": n_global * sub * 3 / dtb, "unit": "particle-steps/s"},
+    }
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
