@@ -14,8 +14,9 @@ Workload (config.workload):
           list rebuilds (NCCL).  `--workload periodic_box --n-per-gpu 8000000` runs config 5.
 
 value     whole-job particle-steps/s with state resident in HBM (CUDA events, max over ranks)
-e2e       the same through lethe_dem_step_host: pinned HOST rows uploaded, one step, rows
-          downloaded, every step (the reference-facing per-step plugin call)
+e2e       the same through lethe_dem_step_host on every rank: pinned HOST rows of the owned
+          particles uploaded, one step, rows downloaded, every step (the reference-facing
+          per-step plugin call; PCIe-bound at ~55 GB/s per direction)
 roofline  fused step kernel: algorithmic bytes (160+16+4*C+48*T per particle-step,
           C,T measured) / CUDA-event kernel time, against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample, 1 core
@@ -299,8 +300,8 @@ def main():
 
     # ---- e2e: per-step plugin call with pinned host rows ----
     # Every rank keeps host rows of the particles it owns and hands them to lethe_dem_step_host
-    # every step (rows up, one step, rows down). When a step rebuilt the lists, particles may have
-    # changed owner: the rank then re-reads its owned rows (inside the timed region).
+    # every step (rows up, one step, rows down). When particles changed owner in a rebuild, the
+    # rank re-reads its owned rows (inside the timed region).
     def owned_rows():
         ids_, x_, props_ = engine.get_particles()
         return (torch.from_numpy(ids_.copy()).pin_memory(), torch.from_numpy(np.ascontiguousarray(x_)).pin_memory(),
@@ -310,13 +311,13 @@ def main():
         hid, hx, hp = rows
         engine.step_host_ptr(n_steps, len(hid), hid.data_ptr(), hx.data_ptr(), hp.data_ptr())
         if world > 1:
-            r = engine.get_stats().n_rebuilds
+            r = engine.get_stats().n_migrated  # particles changed owner: re-read the owned rows
             if r != rebuilds_seen:
                 return owned_rows(), r
         return rows, rebuilds_seen
 
     rows = owned_rows()
-    seen = engine.get_stats().n_rebuilds
+    seen = engine.get_stats().n_migrated
     for _ in range(3):
         rows, seen = host_step(rows, 1, seen)
     barrier()

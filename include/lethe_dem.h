@@ -163,6 +163,7 @@ typedef struct lethe_dem_stats {
   double omega_min, omega_max, omega_sum;
   double ke_trans_min, ke_trans_max, ke_trans_sum;
   double ke_rot_min, ke_rot_max, ke_rot_sum;
+  uint64_t n_migrated;          /* multi-GPU: particles this rank has sent to or received from its neighbours so far */
 } lethe_dem_stats;
 
 typedef struct lethe_dem_ctx lethe_dem_ctx;

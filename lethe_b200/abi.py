@@ -122,6 +122,7 @@ class Stats(C.Structure):
         ("ke_rot_min", C.c_double),
         ("ke_rot_max", C.c_double),
         ("ke_rot_sum", C.c_double),
+        ("n_migrated", C.c_uint64),
     ]
 
 

@@ -210,6 +210,7 @@ struct lethe_dem_ctx
   bool contact_search_trigger = true;
   bool clear_history_trigger = false;
   uint64_t n_rebuilds = 0;
+  uint64_t n_migrated = 0; // particles sent to / received from the neighbouring ranks so far
   // contact-detection trigger (StepParams::flag_*): the tag of the step that asked for a new
   // list, 0 = nobody. `h_flag` is mapped pinned memory (device alias `d_flag`) the host polls,
   // `flag_dev[0]` the device copy the next (speculative) launch checks, `flag_dev[1]` the

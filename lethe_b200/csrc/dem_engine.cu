@@ -1521,6 +1521,7 @@ int lethe_dem_get_stats(lethe_dem_ctx *c, lethe_dem_stats *st)
     std::memset(st, 0, sizeof(*st));
     st->n_particles = c->n_owned;
     st->n_rebuilds = c->n_rebuilds;
+    st->n_migrated = c->n_migrated;
     st->n_steps = c->iteration_number;
     st->n_pair_entries = c->lists[c->cur_list].n_entries / 2;
     st->n_wall_entries = c->wlists[c->cur_list].n_entries;

@@ -708,6 +708,7 @@ namespace dem
     }
 
     const uint32_t n_in = n_recv[0] + n_recv[1];
+    c->n_migrated += uint64_t(n_send[0]) + n_send[1] + n_in;
     c->first_immigrant = n0;
     if (n_in)
       {

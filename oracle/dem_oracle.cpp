@@ -2664,6 +2664,7 @@ int oracle_dem_get_forces(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, u
 
 int oracle_dem_get_stats(lethe_dem_ctx *ctx, lethe_dem_stats *st)
 {
+  st->n_migrated = 0; // single domain
   Oracle *o = reinterpret_cast<Oracle *>(ctx);
   std::memset(st, 0, sizeof(*st));
   st->n_particles = o->parts.size();
