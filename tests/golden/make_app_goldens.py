@@ -27,6 +27,11 @@ CASES = {
     "moving_solid_surface_jkr": "moving_solid_surface_jkr.mpirun=1.output",
     "moving_solid_surface_dmt": "moving_solid_surface_dmt.mpirun=1.output",
     "insert_file_3d": "insert_file_3d.mpirun=1.output",
+    "insert_list_3d": "insert_list_3d.output",
+    "insert_z-x-y": "insert_z-x-y.output",
+    "multiperiodic_single_axis_collisions_3d": "multiperiodic_single_axis_collisions_3d.output",
+    "single-time-step-list-insertion": "single-time-step-list-insertion.output",
+    "periodic_boundary_collisions": "periodic_boundary_collisions.mpirun=1.output",  # == the mpirun=2 golden
 }
 
 
