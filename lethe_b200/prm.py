@@ -115,7 +115,8 @@ class SolidSurface:
     rotation_axis: tuple = (1.0, 0.0, 0.0)
     rotation_angle: float = 0.0
     translation: tuple = (0.0, 0.0, 0.0)
-    translational_velocity: tuple = (0.0, 0.0, 0.0)  # constant `Function expression`s only
+    # `Function expression`s of time: floats, or muparser strings evaluated by `solid_velocity_at`
+    translational_velocity: tuple = (0.0, 0.0, 0.0)
     angular_velocity: tuple = (0.0, 0.0, 0.0)
     center_of_rotation: tuple = (0.0, 0.0, 0.0)
 
@@ -275,6 +276,26 @@ class DEMParameters:
         return c
 
 
+def evaluate_function(expr, t: float) -> float:
+    """Value at time t of one component of a deal.II `Function expression` (muparser syntax:
+    `if(c, a, b)`, `^`, the usual functions, variable t; the solid-object velocity functions are
+    evaluated at the centre of rotation, whose coordinates no reference case uses)."""
+    if not isinstance(expr, str):
+        return float(expr)
+    import math
+    import re as _re
+
+    py = _re.sub(r"\bif\s*\(", "_if(", expr).replace("^", "**")
+    env = {name: getattr(math, name) for name in ("sin", "cos", "tan", "exp", "log", "sqrt", "tanh", "atan", "asin", "acos")}
+    env.update({"_if": lambda c, a, b: a if c else b, "pi": math.pi, "t": t, "x": 0.0, "y": 0.0, "z": 0.0, "abs": abs, "min": min, "max": max})
+    return float(eval(py, {"__builtins__": {}}, env))
+
+
+def solid_velocity_at(solid: "SolidSurface", t: float):
+    return (tuple(evaluate_function(c, t) for c in solid.translational_velocity),
+            tuple(evaluate_function(c, t) for c in solid.angular_velocity))
+
+
 _ROLLING_ALIASES = {
     "no_resistance": "none",
     "constant_resistance": "constant",
@@ -423,11 +444,13 @@ def parameters_from_prm(text: str) -> DEMParameters:
             expr = s.get(sub, {}).get("Function expression")
             if expr is None:
                 return default
-            try:
-                return tuple(float(v) for v in expr.split(";"))
-            except ValueError:
-                raise abi.DEMError(f"solid surfaces: `{sub}` must be constant (got {expr!r}); drive time-dependent motion "
-                                   "through Engine.set_solid_motion")
+            out = []
+            for v in expr.split(";"):
+                try:
+                    out.append(float(v))
+                except ValueError:
+                    out.append(v.strip())  # a function of t (muparser syntax), see evaluate_function
+            return tuple(out)
 
         p.solid_surfaces.append(SolidSurface(
             mesh_file=m.get("file name", ""),

@@ -173,6 +173,7 @@ class DEMSolver:
         self._current_type = 0
         self._next_id = 0
         self._file_id = 0
+        self._solid_motion = []
         self._setup_boundaries()
 
     # DEMSolver::setup_functions_and_pointers / boundary_cell_object.build
@@ -197,7 +198,11 @@ class DEMSolver:
             K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
             rot = math.cos(th) * np.eye(3) + math.sin(th) * K + (1 - math.cos(th)) * np.outer(a, a)
             vertices = vertices @ rot.T + np.asarray(so.translation)
-            self.engine.add_solid_surface(vertices, triangles, so.translational_velocity, so.angular_velocity, so.center_of_rotation)
+            from .prm import solid_velocity_at
+
+            tv, av = solid_velocity_at(so, 0.0)
+            self._solid_motion.append((tv, av))
+            self.engine.add_solid_surface(vertices, triangles, tv, av, so.center_of_rotation)
         for bc in p.boundary_conditions:
             if bc.type == "rotational":
                 self.engine.set_boundary_motion(bc.boundary_id, (0, 0, 0), bc.rotational_speed, bc.rotational_vector, bc.point_on_rotational_vector)
@@ -247,6 +252,19 @@ class DEMSolver:
             self.iteration_number += 1
             self.current_time += self.parameters.time_step
             steps += 1
+            # SerialSolid::move_solid_triangulation evaluates the velocity functions at the previous
+            # time (serial_solid.cc:343-352): push new values before the step that uses them
+            t_prev = self.current_time - self.parameters.time_step
+            for k, so in enumerate(self.parameters.solid_surfaces):
+                from .prm import solid_velocity_at
+
+                motion = solid_velocity_at(so, t_prev)
+                if motion != self._solid_motion[k]:
+                    if pending:
+                        self.engine.step(pending)
+                        pending = 0
+                    self.engine.set_solid_motion(k, *motion)
+                    self._solid_motion[k] = motion
             if self._insertion_due():
                 # the insertion belongs to this iteration: flush earlier ones first
                 if pending:

@@ -393,3 +393,29 @@ def test_contact_on_two_processors_golden(oracle_lib):
         assert abs(xx[0, 1] - y) <= (5.1e-9 if k <= 10 else 3e-7), (k, xx[0, 1], y)
     _, xx, pp = e.get_particles()
     assert abs((gold[-1] - gold[-2]) / 10 - pp[0, 4] * 1e-5) <= 1e-9  # same rebound velocity
+
+
+def test_time_dependent_solid_velocity_function(oracle_lib):
+    """`subsection translational velocity / Function expression` with a muparser conditional (as in
+    load_balancing_solid_object.prm): the mirror evaluates it at the previous time of every step
+    (serial_solid.cc:343-352) and pushes changes through lethe_dem_set_solid_motion."""
+    from lethe_b200.prm import SolidSurface, evaluate_function
+
+    assert evaluate_function("if(t>0.5,if(t<0.7,1,0),0)", 0.6) == 1.0
+    assert evaluate_function("if(t>0.5,if(t<0.7,1,0),0)", 0.8) == 0.0
+    assert evaluate_function("2*t^2", 3.0) == 18.0
+    d = os.path.join(GOLDEN, "solid_surfaces")
+    params = load_prm(os.path.join(d, "particle_solid_surface_NPES_double_edge_contact.prm"))
+    params.time_step, params.time_end = 1e-5, 1e-3
+    params.solid_surfaces[0].translational_velocity = (0.0, 0.0, "if(t>0.0005,2,0)")
+    solver = DEMSolver(params, engine_factory=loader.oracle_engine, prm_directory=d)
+    v0 = None
+    solver.solve(max_steps=0)
+    v0 = solver.engine.get_solid_vertices(0).copy()
+    solver.solve()
+    v1 = solver.engine.get_solid_vertices(0)
+    # steps n = 1..100 use t_prev = (n - 1) dt; t_prev > 0.0005 for n = 52..100 (binary rounding of
+    # 51 * 1e-5 decides the edge): 49 or 50 moving steps of 2e-5 each
+    dz = v1[:, 2] - v0[:, 2]
+    assert np.allclose(dz, dz[0]) and np.allclose(v1[:, :2], v0[:, :2])
+    assert round(dz[0] / 2e-5) in (49, 50), dz[0]
