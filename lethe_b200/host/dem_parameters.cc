@@ -217,8 +217,18 @@ namespace lethe_b200
         // constant `Function expression = a ; b ; c` only (time-dependent motion: lethe_dem_set_solid_motion)
         auto constant_function = [&](const char *sub, Vec3 &out) {
           const PrmSection &f = s.sub(sub);
-          if (f.has("Function expression"))
-            out = to_vec3(f.get_list("Function expression", ';'), sub);
+          if (!f.has("Function expression"))
+            return;
+          try
+            {
+              out = to_vec3(f.get_list("Function expression", ';'), sub);
+            }
+          catch (const std::exception &)
+            {
+              throw std::runtime_error(std::string("solid surfaces: `") + sub + "` = `" + f.get("Function expression", "") +
+                                       "` depends on time; this host evaluates constant expressions only (drive the motion "
+                                       "with lethe_dem_set_solid_motion, as lethe_b200/solver.py does)");
+            }
         };
         constant_function("translational velocity", sd.translational_velocity);
         constant_function("angular velocity", sd.angular_velocity);
