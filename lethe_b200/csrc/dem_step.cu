@@ -39,7 +39,10 @@ namespace dem
 {
   namespace
   {
-    constexpr int STEP_WARPS = 4; // warps per block
+#ifndef DEM_STEP_WARPS
+#define DEM_STEP_WARPS 4
+#endif
+    constexpr int STEP_WARPS = DEM_STEP_WARPS; // warps per block
 #ifndef DEM_QUEUE
 #define DEM_QUEUE 512
 #endif
