@@ -142,6 +142,8 @@ namespace lethe_b200
         t.surface_energy = s.get_double("surface energy particles", 0);
         t.hamaker_constant = s.get_double("hamaker constant particles", 4e-19);
         t.prn_seed = s.get_int("distribution prn seed", 1);
+        t.min_cutoff = s.get_double("minimum diameter cutoff", -1);
+        t.max_cutoff = s.get_double("maximum diameter cutoff", -1);
         p.particle_types.push_back(t);
       }
     p.young_wall = lp.get_double("young modulus wall", 1e6);
@@ -282,12 +284,41 @@ namespace lethe_b200
     return p;
   }
 
+  // NormalDistribution / LogNormalDistribution constructors (distributions.cc:23-165,231-290),
+  // number-based weighting
+  double ParticleType::max_diameter() const
+  {
+    if (size_distribution_type == "uniform")
+      return average_diameter;
+    if (max_cutoff >= 0)
+      return max_cutoff;
+    if (size_distribution_type == "lognormal")
+      {
+        const double sigma_ln = std::sqrt(std::log(1. + (standard_deviation / average_diameter) * (standard_deviation / average_diameter)));
+        return std::exp((std::log(average_diameter) - 0.5 * sigma_ln * sigma_ln) + 2.5 * sigma_ln);
+      }
+    return average_diameter + 2.5 * standard_deviation;
+  }
+  double ParticleType::min_diameter() const
+  {
+    if (size_distribution_type == "uniform")
+      return average_diameter;
+    if (min_cutoff >= 0)
+      return min_cutoff;
+    if (size_distribution_type == "lognormal")
+      {
+        const double sigma_ln = std::sqrt(std::log(1. + (standard_deviation / average_diameter) * (standard_deviation / average_diameter)));
+        return std::exp((std::log(average_diameter) - 0.5 * sigma_ln * sigma_ln) - 2.5 * sigma_ln);
+      }
+    return average_diameter - 2.5 * standard_deviation;
+  }
+
   double DEMParameters::maximum_particle_diameter() const
   {
-    // setup_distribution_type: normal / lognormal PSDs are truncated at +-2.5 sigma
+    // setup_distributions: the largest find_max_diameter() over the particle types
     double d = 0;
     for (const auto &t : particle_types)
-      d = std::max(d, t.size_distribution_type == "uniform" ? t.average_diameter : t.average_diameter + 2.5 * t.standard_deviation);
+      d = std::max(d, t.max_diameter());
     return d;
   }
 

@@ -35,6 +35,10 @@ namespace lethe_b200
     double surface_energy = 0.0;
     double hamaker_constant = 4e-19;
     long prn_seed = 1;
+    double min_cutoff = -1, max_cutoff = -1; // `minimum / maximum diameter cutoff` (< 0: +-2.5 sigma)
+    // find_min_diameter / find_max_diameter of the type's Distribution (distributions.cc)
+    double max_diameter() const;
+    double min_diameter() const;
   };
 
   // Uniform hex grid equivalent of the deal.II triangulation (`subsection mesh`)

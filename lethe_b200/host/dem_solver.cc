@@ -50,12 +50,44 @@ namespace lethe_b200
     return faces;
   }
 
-  ParticleRows volume_insertion(const DEMParameters &p, long n_insert, uint32_t first_id, int particle_type)
+  SizeDistribution::SizeDistribution(const ParticleType &t, unsigned rank)
+    : type(t)
+    , gen(unsigned(t.prn_seed) + rank)
+    , normal(t.average_diameter, t.standard_deviation > 0 ? t.standard_deviation : 1.0)
+  {
+    if (t.size_distribution_type == "lognormal")
+      {
+        const double r = t.standard_deviation / t.average_diameter;
+        const double sigma_ln = std::sqrt(std::log(1. + r * r));
+        lognormal = std::lognormal_distribution<>(std::log(t.average_diameter) - 0.5 * sigma_ln * sigma_ln, sigma_ln);
+      }
+    else if (t.size_distribution_type != "uniform" && t.size_distribution_type != "normal")
+      throw std::runtime_error("size distribution type `" + t.size_distribution_type + "` is not mirrored (uniform, normal, lognormal are)");
+  }
+
+  std::vector<double> SizeDistribution::sample(long n)
+  {
+    std::vector<double> out;
+    out.reserve(size_t(std::max(0l, n)));
+    if (type.size_distribution_type == "uniform")
+      {
+        out.assign(size_t(std::max(0l, n)), type.average_diameter);
+        return out;
+      }
+    const double lo = type.min_diameter(), hi = type.max_diameter();
+    while (long(out.size()) < n)
+      {
+        const double d = type.size_distribution_type == "normal" ? normal(gen) : lognormal(gen);
+        if (d > lo && d < hi)
+          out.push_back(d);
+      }
+    return out;
+  }
+
+  ParticleRows volume_insertion(const DEMParameters &p, long n_insert, uint32_t first_id, int particle_type, SizeDistribution &sizes)
   {
     const InsertionInfo &ins = p.insertion;
     const ParticleType &t = p.particle_types.at(particle_type);
-    if (t.size_distribution_type != "uniform")
-      throw std::runtime_error("volume insertion on the host supports the uniform size distribution only");
     const double d_max = p.maximum_particle_diameter();
     long n_dir[3] = {0, 0, 0};
     for (int axis : ins.direction_sequence)
@@ -74,9 +106,10 @@ namespace lethe_b200
     rows.id.resize(n_insert);
     rows.x.resize(3 * n_insert);
     rows.props.assign(size_t(LETHE_DEM_N_PROPERTIES) * n_insert, 0.0);
-    const double d = std::fabs(t.average_diameter), half = d * 0.5;
+    const std::vector<double> diameters = sizes.sample(n_insert); // insertion.cc:78-90
     for (long k = 0; k < n_insert; ++k)
       {
+        const double d = std::fabs(diameters[k]), half = d * 0.5;
         const double r1 = rnd[k], r2 = rnd[n_sites - k - 1];
         const long i0 = k % n_dir[a0], i1 = (k % (n_dir[a0] * n_dir[a1])) / n_dir[a0], i2 = k / (n_dir[a0] * n_dir[a1]);
         rows.x[3 * k + a0] = ins.box_point_1[a0] + ((i0 + 0.5) * ins.distance_threshold - r1) * d_max;
@@ -103,7 +136,10 @@ namespace lethe_b200
     const lethe_dem_config config = parameters.to_config();
     engine = std::make_unique<DEMEngine>(config, device);
     for (const auto &t : parameters.particle_types)
-      remaining_particles.push_back(t.number_of_particles);
+      {
+        remaining_particles.push_back(t.number_of_particles);
+        size_distributions.emplace_back(t, 0u);
+      }
     setup_boundaries();
   }
 
@@ -337,7 +373,7 @@ namespace lethe_b200
     else if (parameters.insertion.method == "list")
       rows = list_insertion(parameters, next_id, current_inserting_type);
     else
-      rows = volume_insertion(parameters, n, next_id, current_inserting_type);
+      rows = volume_insertion(parameters, n, next_id, current_inserting_type, size_distributions.at(current_inserting_type));
     engine->add_particles(rows); // triggers the contact search (DEMActionManager::particle_insertion_step)
     next_id += uint32_t(rows.size());
     remaining_particles[current_inserting_type] -= long(rows.size());

@@ -10,6 +10,7 @@
 
 #include <iosfwd>
 #include <memory>
+#include <random>
 
 #include "dem_engine.h"
 #include "dem_parameters.h"
@@ -25,7 +26,21 @@ namespace lethe_b200
   // InsertionVolume::insert + assign_particle_properties on one rank, uniform diameters
   // (insertion_volume.cc:43-206, insertion.cc:60-121); jitter from glibc rand() exactly as
   // create_random_number_container does (include/core/utilities.h:1061-1073).
-  ParticleRows volume_insertion(const DEMParameters &p, long n_insert, uint32_t first_id, int particle_type);
+  // Distribution::particle_size_sampling (distributions.cc): uniform, normal, lognormal with the
+  // reference's generator (std::mt19937(seed + rank), std::normal_distribution / lognormal_distribution)
+  class SizeDistribution
+  {
+  public:
+    SizeDistribution(const ParticleType &t, unsigned rank);
+    std::vector<double> sample(long n);
+
+  private:
+    ParticleType type;
+    std::mt19937 gen;
+    std::normal_distribution<> normal;
+    std::lognormal_distribution<> lognormal;
+  };
+  ParticleRows volume_insertion(const DEMParameters &p, long n_insert, uint32_t first_id, int particle_type, SizeDistribution &sizes);
   // InsertionList::insert (insertion_list.cc): the listed positions / velocities / diameters
   ParticleRows list_insertion(const DEMParameters &p, uint32_t first_id, int particle_type);
   // InsertionFile::insert (insertion_file.cc:27-130): one `;`-separated table per insertion
@@ -62,6 +77,7 @@ namespace lethe_b200
     int current_inserting_type = 0;
     uint32_t next_id = 0;
     size_t current_file_id = 0;
+    std::vector<SizeDistribution> size_distributions; // one per particle type (setup_distributions)
     // contact_list statistics of report_statistics
     double list_min = 1e300, list_max = 0, list_total = 0;
   };

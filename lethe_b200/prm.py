@@ -69,7 +69,9 @@ class ParticleType:
     rolling_viscous_damping: float = 0.1
     surface_energy: float = 0.0
     hamaker: float = 4e-19
-    seed: int = 1
+    seed: int = 1           # `distribution prn seed`
+    min_cutoff: float = -1.0  # `minimum / maximum diameter cutoff` (< 0: average -+ 2.5 sigma)
+    max_cutoff: float = -1.0
 
 
 @dataclass
@@ -188,13 +190,9 @@ class DEMParameters:
     def d_max(self) -> float:
         # setup_distributions: maximum_particle_diameter (dem.cc:149-159);
         # normal/lognormal PSDs are truncated at +-2.5 sigma in the reference
-        d = 0.0
-        for t in self.particle_types:
-            if t.size_distribution_type == "uniform":
-                d = max(d, t.diameter)
-            else:
-                d = max(d, t.diameter + 2.5 * t.standard_deviation)
-        return d
+        from .distributions import make_distribution
+
+        return max(make_distribution(t).max_diameter() for t in self.particle_types)
 
     @property
     def periodic(self):
@@ -387,6 +385,8 @@ def parameters_from_prm(text: str) -> DEMParameters:
         t.surface_energy = float(s.get("surface energy particles", "0"))
         t.hamaker = float(s.get("hamaker constant particles", "4e-19"))
         t.seed = int(s.get("distribution prn seed", "1"))
+        t.min_cutoff = float(s.get("minimum diameter cutoff", "-1"))
+        t.max_cutoff = float(s.get("maximum diameter cutoff", "-1"))
         p.particle_types.append(t)
     p.young_wall = float(lp.get("young modulus wall", "1000000"))
     p.poisson_wall = float(lp.get("poisson ratio wall", "0.3"))

@@ -81,15 +81,18 @@ def _glibc_rand_container(n: int, maximum_range: float, seed: int):
     return out
 
 
-def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particle_type: int = 0):
+def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particle_type: int = 0, distribution=None):
     """InsertionVolume::insert / find_insertion_location
     (source/dem/insertion_volume.cc:43-206) + assign_particle_properties
-    (source/dem/insertion.cc:60-121) on one rank, uniform size distribution."""
+    (source/dem/insertion.cc:60-121) on one rank. `distribution` is the particle type's size
+    distribution object (its generator state carries over from one insertion to the next)."""
     ins = p.insertion
     d_max = p.d_max
     t = p.particle_types[particle_type]
-    if t.size_distribution_type != "uniform":
-        raise abi.DEMError("volume_insertion replay supports the uniform size distribution only")
+    if distribution is None:
+        from .distributions import make_distribution
+
+        distribution = make_distribution(t)
     n_dir = [0, 0, 0]
     for axis in ins.direction_sequence:
         n_dir[axis] = int((ins.box_point_2[axis] - ins.box_point_1[axis]) / (ins.distance_threshold * d_max))
@@ -107,7 +110,7 @@ def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particl
         x[k, a1] = ins.box_point_1[a1] + ((i1 + 0.5) * ins.distance_threshold - r2) * d_max
         x[k, a2] = ins.box_point_1[a2] + ((i2 + 0.5) * ins.distance_threshold - r1) * d_max
     props = np.zeros((n_insert, abi.N_PROPERTIES))
-    d = abs(t.diameter)
+    d = np.abs(distribution.sample(n_insert))  # particle_size_sampling (insertion.cc:78-90)
     h = d * 0.5
     props[:, 0] = particle_type
     props[:, 1] = d
@@ -174,6 +177,9 @@ class DEMSolver:
         self._next_id = 0
         self._file_id = 0
         self._solid_motion = []
+        from .distributions import make_distribution
+
+        self._distributions = [make_distribution(t) for t in parameters.particle_types]  # setup_distributions, rank 0
         self._setup_boundaries()
 
     # DEMSolver::setup_functions_and_pointers / boundary_cell_object.build
@@ -233,7 +239,7 @@ class DEMSolver:
             ids, x, props = list_insertion(p, self._next_id, self._current_type)
         else:
             n = min(p.insertion.inserted_this_step, remaining)
-            ids, x, props = volume_insertion(p, n, self._next_id, self._current_type)
+            ids, x, props = volume_insertion(p, n, self._next_id, self._current_type, self._distributions[self._current_type])
         self.engine.add_particles(ids, x, props)
         self._next_id += len(ids)
         self._remaining[self._current_type] -= len(ids)

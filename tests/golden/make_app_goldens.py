@@ -32,6 +32,8 @@ CASES = {
     "multiperiodic_single_axis_collisions_3d": "multiperiodic_single_axis_collisions_3d.output",
     "single-time-step-list-insertion": "single-time-step-list-insertion.output",
     "periodic_boundary_collisions": "periodic_boundary_collisions.mpirun=1.output",  # == the mpirun=2 golden
+    "distribution_normal": "distribution_normal.output",
+    "distribution_lognormal": "distribution_lognormal.output",
 }
 
 

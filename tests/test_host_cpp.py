@@ -126,7 +126,8 @@ def test_host_sources_solid_surface_prm_against_oracle():
     assert all(abs(a - b) <= 1.01e-4 * abs(b) + 1e-12 for a, b in zip(got, gold)), list(zip(got, gold))[:5]
 
 
-@pytest.mark.parametrize("case", ["insert_file_3d", "epsd_rolling_resistance_model", "moving_solid_surface_hmlo", "sliding_in_box"])
+@pytest.mark.parametrize("case", ["insert_file_3d", "epsd_rolling_resistance_model", "moving_solid_surface_hmlo", "sliding_in_box",
+                                  "distribution_normal", "distribution_lognormal"])
 def test_host_sources_application_goldens_against_oracle(case):
     """More of the reference's application cases through the C++ host mirror (file / list / volume
     insertion, solid objects, EPSD) linked to the oracle: the printed final table equals the
@@ -146,3 +147,5 @@ def test_host_sources_application_goldens_against_oracle(case):
     assert [r_[0] for r_ in rows] == [g[0] for g in gold]
     err = np.abs(np.array([r_[3:6] for r_ in rows]) - np.array([g[3:6] for g in gold])).max()
     assert err <= 1.01e-4, (case, err)  # both sides print 4 decimals
+    derr = np.abs(np.array([r_[2] for r_ in rows]) - np.array([g[2] for g in gold])).max()
+    assert derr <= 1.01e-5, (case, derr)  # diameters: 5 decimals

@@ -304,7 +304,8 @@ APP_CASES = ["rolling_on_plane", "velocity_verlet_free_fall", "multiperiodic_col
              "pp_jkr_equilibrium", "pp_dmt_equilibrium", "pw_jkr_equilibrium", "pw_dmt_equilibrium", "epsd_rolling_resistance_model",
              "sliding_in_box", "periodic_boundary_box", "moving_solid_surface_hmlo", "moving_solid_surface_jkr",
              "moving_solid_surface_dmt", "insert_file_3d", "insert_list_3d", "insert_z-x-y",
-             "multiperiodic_single_axis_collisions_3d", "single-time-step-list-insertion", "periodic_boundary_collisions"]
+             "multiperiodic_single_axis_collisions_3d", "single-time-step-list-insertion", "periodic_boundary_collisions",
+             "distribution_normal", "distribution_lognormal"]
 
 
 def run_application_case(case, engine_factory):
