@@ -28,6 +28,23 @@ def product_binary():
     return os.path.join(HOST, "lethe-particles-b200")
 
 
+def oracle_host_binary():
+    """The host sources compiled against the CPU oracle's identically-shaped ABI (test-only binary
+    under tests/_build); rebuilt only when a source is newer."""
+    loader.build()
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "lethe-particles-oracle")
+    srcs = [os.path.join(HOST, f) for f in ("dem_parameters.cc", "dem_solver.cc", "lethe_particles_b200.cc")]
+    odir = os.path.join(ROOT, "oracle")
+    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")] + [os.path.join(odir, "libdem_oracle.so"),
+                                                                                            os.path.join(ROOT, "include", "lethe_dem.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DLETHE_DEM_ABI_PREFIX=oracle_dem_", "-o", exe, *srcs, "-L" + odir,
+                               "-ldem_oracle", "-Wl,-rpath," + odir])
+    return exe
+
+
 def parse_xyz(text):
     rows = []
     for line in text.splitlines():
@@ -73,14 +90,7 @@ def test_product_binary_fails_loudly_without_gpu_or_runs():
 
 
 def test_host_sources_against_oracle_reproduce_reference_golden(tmp_path):
-    loader.build()
-    build = os.path.join(ROOT, "tests", "_build")
-    os.makedirs(build, exist_ok=True)
-    exe = os.path.join(build, "lethe-particles-oracle")
-    srcs = [os.path.join(HOST, f) for f in ("dem_parameters.cc", "dem_solver.cc", "lethe_particles_b200.cc")]
-    odir = os.path.join(ROOT, "oracle")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DLETHE_DEM_ABI_PREFIX=oracle_dem_", "-o", exe, *srcs, "-L" + odir,
-                           "-ldem_oracle", "-Wl,-rpath," + odir])
+    exe = oracle_host_binary()
     r = subprocess.run([exe, PRM, "--quiet"], capture_output=True, text=True, check=True)
     check_against_golden(parse_xyz(r.stdout))
 
@@ -109,14 +119,7 @@ def test_host_sources_solid_surface_prm_against_oracle():
     reference's .output to its 5 printed digits at all 60 log lines."""
     import re
 
-    loader.build()
-    build = os.path.join(ROOT, "tests", "_build")
-    os.makedirs(build, exist_ok=True)
-    exe = os.path.join(build, "lethe-particles-oracle")
-    srcs = [os.path.join(HOST, f) for f in ("dem_parameters.cc", "dem_solver.cc", "lethe_particles_b200.cc")]
-    odir = os.path.join(ROOT, "oracle")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DLETHE_DEM_ABI_PREFIX=oracle_dem_", "-o", exe, *srcs, "-L" + odir,
-                           "-ldem_oracle", "-Wl,-rpath," + odir])
+    exe = oracle_host_binary()
     prm = os.path.join(GOLDEN, "solid_surfaces", "particle_solid_surface_NPES_double_edge_contact.prm")
     r = subprocess.run([exe, prm], capture_output=True, text=True, check=True)
     got = [float(m) for m in re.findall(r"Velocity magnitude\s*\|\s*\S+\s*\|\s*(\S+)", r.stdout)]
@@ -132,14 +135,7 @@ def test_host_sources_application_goldens_against_oracle(case):
     """More of the reference's application cases through the C++ host mirror (file / list / volume
     insertion, solid objects, EPSD) linked to the oracle: the printed final table equals the
     reference's .output to its 4 decimals."""
-    loader.build()
-    build = os.path.join(ROOT, "tests", "_build")
-    os.makedirs(build, exist_ok=True)
-    exe = os.path.join(build, "lethe-particles-oracle")
-    srcs = [os.path.join(HOST, f) for f in ("dem_parameters.cc", "dem_solver.cc", "lethe_particles_b200.cc")]
-    odir = os.path.join(ROOT, "oracle")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DLETHE_DEM_ABI_PREFIX=oracle_dem_", "-o", exe, *srcs, "-L" + odir,
-                           "-ldem_oracle", "-Wl,-rpath," + odir])
+    exe = oracle_host_binary()
     r = subprocess.run([exe, os.path.join(GOLDEN, "apps", case + ".prm"), "--quiet"], capture_output=True, text=True, check=True)
     rows = parse_xyz(r.stdout)
     with open(os.path.join(GOLDEN, "apps", "final_positions.json")) as f:
