@@ -2522,6 +2522,45 @@ int oracle_dem_get_solid_contacts(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *
   return 0;
 }
 
+// Test hook: the cell-neighbour lists in active-cell numbering. which = 0: find_cell_neighbors
+// <dim, false> (each pair of neighbouring cells listed once, find_cell_neighbors.cc:10-104);
+// which = 1: find_full_cell_neighbors (find_cell_neighbors.cc:293-333, the solid-surface search).
+// out = rows of `stride` ints: [cell, neighbours..., -1 padding].
+int oracle_dem_cell_neighbors(lethe_dem_ctx *ctx, int which, int stride, int32_t *out)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  for (int r = 0; r < o->n_cells; ++r)
+    {
+      std::vector<int> row;
+      if (which == 0)
+        {
+          for (int c : o->cells_local_neighbor_list[r])
+            row.push_back(o->rank_of_cell[c]);
+        }
+      else
+        {
+          // the cell, then the cells of its 8 vertices in vertex order, each vertex's cells in
+          // active-cell order, first occurrence only
+          const int cell = o->cell_of_rank[r];
+          const int ci = cell % o->nx, cj = (cell / o->nx) % o->ny, ck = cell / (o->nx * o->ny);
+          row.push_back(r);
+          std::vector<int> vcells;
+          for (int vertex = 0; vertex < 8; ++vertex)
+            {
+              cells_at_vertex(*o, ci + (vertex & 1), cj + ((vertex >> 1) & 1), ck + ((vertex >> 2) & 1), vcells);
+              for (int nb : vcells)
+                if (std::find(row.begin(), row.end(), o->rank_of_cell[nb]) == row.end())
+                  row.push_back(o->rank_of_cell[nb]);
+            }
+        }
+      if (int(row.size()) > stride)
+        return fail(o, "stride too small");
+      for (int k = 0; k < stride; ++k)
+        out[size_t(r) * stride + k] = k < int(row.size()) ? row[k] : -1;
+    }
+  return 0;
+}
+
 int oracle_dem_step(lethe_dem_ctx *ctx, uint64_t n_steps)
 {
   Oracle *o = reinterpret_cast<Oracle *>(ctx);

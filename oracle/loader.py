@@ -70,3 +70,18 @@ def set_option(engine, name, value):
     fn.restype = ctypes.c_int
     rc = fn(engine._ctx, name.encode(), ctypes.c_int(int(value)))
     assert rc == 0, name
+
+
+def cell_neighbors(engine, which, stride=32):
+    """Cell-neighbour lists of the oracle in active-cell numbering (test hook, see dem_oracle.cpp)."""
+    import ctypes as C
+
+    import numpy as np
+
+    n_cells = int(np.prod(list(engine.config.grid_n)))
+    out = np.full((n_cells, stride), -1, dtype=np.int32)
+    fn = library().oracle_dem_cell_neighbors
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    fn.restype = C.c_int
+    assert fn(engine._ctx, which, stride, out.ctypes.data) == 0
+    return [[int(v) for v in row if v >= 0] for row in out]

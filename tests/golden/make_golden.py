@@ -97,6 +97,12 @@ def main():
     three = cpo.split("dim = 3")[1]
     g["combined_periodic_offsets_3d"] = [floats(l.split("::")[1]) for l in three.splitlines() if "(" in l]
     g["contact_on_two_processors_y"] = contact_on_two_processors()
+    # find_cell_neighbors<3, false> on hyper_cube(-1, 1) refined twice: "2.k" = active cell k of level 2
+    fcn = read("tests/dem/find_cell_neighbors.output").split("reciprocal = 1")[0]
+    g["find_cell_neighbors"] = [[int(v.split(".")[1]) for v in re.findall(r"2\.\d+", l.split("are:")[1])]
+                                for l in fcn.splitlines() if "neighbors of cell" in l]
+    g["find_full_cell_neighbors"] = [[int(v) for v in l.split("are:")[1].split()]
+                                     for l in read("tests/dem/find_full_cell_neighbors.output").splitlines() if "neighbors of cell" in l]
     g["find_contact_pairs"] = [
         [int(v) for v in re.findall(r"particle (\d+)", l)] for l in read("tests/dem/find_contact_pairs.output").splitlines() if "pair" in l
     ]

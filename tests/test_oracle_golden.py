@@ -420,3 +420,13 @@ def test_time_dependent_solid_velocity_function(oracle_lib):
     dz = v1[:, 2] - v0[:, 2]
     assert np.allclose(dz, dz[0]) and np.allclose(v1[:, :2], v0[:, :2])
     assert round(dz[0] / 2e-5) in (49, 50), dz[0]
+
+
+def test_cell_neighbor_lists_match_reference_goldens(oracle_lib):
+    """tests/dem/find_cell_neighbors.output (reciprocal = 0) and find_full_cell_neighbors.output on
+    hyper_cube(-1, 1) refined twice: the oracle's active-cell numbering and the ORDER of every
+    neighbour list (which fixes the candidate and force-summation order of the search) equal the
+    reference's for all 64 cells."""
+    e = loader.oracle_engine(unit_test_parameters().to_config())
+    assert loader.cell_neighbors(e, 0) == golden()["find_cell_neighbors"]
+    assert loader.cell_neighbors(e, 1) == golden()["find_full_cell_neighbors"]
