@@ -207,10 +207,14 @@ namespace lethe_b200
       {
         const PrmSection &s = so.sub("solid object " + std::to_string(i));
         const PrmSection &m = s.sub("mesh");
-        if (m.get("type", "gmsh") != "gmsh")
-          throw std::runtime_error("solid surfaces: only `mesh type = gmsh` files are read");
+        if (m.get("type", "dealii") == "dealii" && m.get("simplex", "false") != "true")
+          throw std::runtime_error("solid surfaces: a `type = dealii` mesh needs `simplex = true` (the contact search is on triangles)");
         SolidSurface sd;
         sd.mesh_file = m.get("file name", "");
+        sd.mesh_type = m.get("type", "dealii");
+        sd.grid_type = m.get("grid type", "hyper_cube");
+        sd.grid_arguments = m.get("grid arguments", "-1 : 1 : false");
+        sd.initial_refinement = m.get_int("initial refinement", 0);
         if (m.has("initial rotation axis"))
           sd.rotation_axis = to_vec3(m.get_list("initial rotation axis"), "initial rotation axis");
         sd.rotation_angle = m.get_double("initial rotation angle", 0);

@@ -166,8 +166,14 @@ namespace lethe_b200
       {
         std::vector<double> v;
         std::vector<uint32_t> t;
-        const std::string path = (!so.mesh_file.empty() && so.mesh_file[0] == '/') ? so.mesh_file : parameters.prm_directory + "/" + so.mesh_file;
-        read_msh_triangles(path, v, t);
+        if (so.mesh_type == "dealii")
+          dealii_simplex_surface(so.grid_type, so.grid_arguments, so.initial_refinement, v, t);
+        else
+          {
+            const std::string path =
+              (!so.mesh_file.empty() && so.mesh_file[0] == '/') ? so.mesh_file : parameters.prm_directory + "/" + so.mesh_file;
+            read_msh_triangles(path, v, t);
+          }
         Vec3 a = so.rotation_axis;
         const double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
         for (auto &c : a)
@@ -250,6 +256,68 @@ namespace lethe_b200
         rows.props.insert(rows.props.end(), props, props + 9);
       }
     return rows;
+  }
+
+  // deal.II is an external dependency of the reference: restated are GridGenerator::hyper_cube /
+  // hyper_rectangle<2,3> and the 2-D table of convert_hypercube_to_simplex_mesh (corners 0-3 in
+  // lexicographic order, edge midpoints 4: x-low, 5: x-high, 6: y-low, 7: y-high, centre 8).
+  void dealii_simplex_surface(const std::string &grid_type, const std::string &grid_arguments, long initial_refinement,
+                              std::vector<double> &vertices3, std::vector<uint32_t> &triangles3)
+  {
+    const auto args = PrmSection::split(grid_arguments, ':');
+    double p1[2], p2[2];
+    if (grid_type == "hyper_cube")
+      {
+        p1[0] = p1[1] = std::stod(args.at(0));
+        p2[0] = p2[1] = std::stod(args.at(1));
+      }
+    else if (grid_type == "hyper_rectangle")
+      {
+        const auto a = PrmSection::split_doubles(args.at(0), ','), b = PrmSection::split_doubles(args.at(1), ',');
+        p1[0] = a.at(0), p1[1] = a.at(1), p2[0] = b.at(0), p2[1] = b.at(1);
+      }
+    else
+      throw std::runtime_error("solid surfaces: dealii grid type `" + grid_type + "` is not generated here (hyper_cube, hyper_rectangle)");
+    const long n = 1L << initial_refinement;
+    const double hx = (p2[0] - p1[0]) / double(n), hy = (p2[1] - p1[1]) / double(n);
+    static const int table[8][3] = {{0, 6, 4}, {8, 4, 6}, {8, 6, 5}, {1, 5, 6}, {2, 4, 7}, {8, 7, 4}, {8, 5, 7}, {3, 7, 5}};
+    std::map<std::pair<long, long>, uint32_t> index; // half-cell lattice coordinates -> vertex
+    auto vertex = [&](long i2, long j2) {
+      auto it = index.find({i2, j2});
+      if (it != index.end())
+        return it->second;
+      const uint32_t v = uint32_t(vertices3.size() / 3);
+      index[{i2, j2}] = v;
+      vertices3.push_back(p1[0] + 0.5 * double(i2) * hx);
+      vertices3.push_back(p1[1] + 0.5 * double(j2) * hy);
+      vertices3.push_back(0.0);
+      return v;
+    };
+    std::vector<std::pair<long, long>> cells; // z-order of the refined quadrilaterals
+    for (long k = 0; k < n * n; ++k)
+      {
+        long i = 0, j = 0;
+        for (long b = 0; b < initial_refinement; ++b)
+          {
+            i |= ((k >> (2 * b)) & 1) << b;
+            j |= ((k >> (2 * b + 1)) & 1) << b;
+          }
+        cells.push_back({i, j});
+      }
+    for (const auto &c : cells) // the quadrilateral mesh's own vertices come first
+      for (long dj = 0; dj <= 2; dj += 2)
+        for (long di = 0; di <= 2; di += 2)
+          vertex(2 * c.first + di, 2 * c.second + dj);
+    for (const auto &c : cells)
+      {
+        const long i = 2 * c.first, j = 2 * c.second;
+        const uint32_t local[9] = {vertex(i, j),         vertex(i + 2, j),     vertex(i, j + 2),
+                                   vertex(i + 2, j + 2), vertex(i, j + 1),     vertex(i + 2, j + 1),
+                                   vertex(i + 1, j),     vertex(i + 1, j + 2), vertex(i + 1, j + 1)};
+        for (const auto &t : table)
+          for (int k = 0; k < 3; ++k)
+            triangles3.push_back(local[t[k]]);
+      }
   }
 
   void read_msh_triangles(const std::string &path, std::vector<double> &vertices3, std::vector<uint32_t> &triangles3)

@@ -48,6 +48,10 @@ namespace lethe_b200
   // GridIn::read_msh for a triangle surface (gmsh 4.1 / 2.2 ASCII): vertices in node order,
   // triangles in element order (SerialSolid::setup_triangulation, serial_solid.cc:163-175)
   void read_msh_triangles(const std::string &path, std::vector<double> &vertices3, std::vector<uint32_t> &triangles3);
+  // `type = dealii`, `simplex = true` solid surfaces (serial_solid.cc:176-196): hyper_cube /
+  // hyper_rectangle in the z = 0 plane, refined, every quadrilateral split into 8 triangles
+  void dealii_simplex_surface(const std::string &grid_type, const std::string &grid_arguments, long initial_refinement,
+                              std::vector<double> &vertices3, std::vector<uint32_t> &triangles3);
 
   class DEMSolverB200
   {

@@ -132,7 +132,7 @@ def list_insertion(p: DEMParameters, first_id: int = 0, particle_type: int = 0):
     props = np.zeros((n, abi.N_PROPERTIES))
     props[:, 0] = particle_type
     props[:, 1] = d
-    props[:, 2] = t.density * 4.0 / 3.0 * math.pi * (d * 0.5) ** 3
+    props[:, 2] = t.density * 4.0 / 3.0 * math.pi * ((d * 0.5) * (d * 0.5) * (d * 0.5))
     if n:
         props[:, 3:6] = np.asarray(ins.list_velocity)
         props[:, 6:9] = np.asarray(ins.list_omega)
@@ -154,7 +154,7 @@ def file_insertion(p: DEMParameters, path: str, n_max: int, first_id: int = 0, p
     props = np.zeros((n, abi.N_PROPERTIES))
     props[:, 0] = particle_type
     props[:, 1] = d
-    props[:, 2] = t.density * 4.0 / 3.0 * math.pi * (d * 0.5) ** 3
+    props[:, 2] = t.density * 4.0 / 3.0 * math.pi * ((d * 0.5) * (d * 0.5) * (d * 0.5))
     for k, key in enumerate(("v_x", "v_y", "v_z", "w_x", "w_y", "w_z")):
         props[:, 3 + k] = data[key][:n]
     return np.arange(first_id, first_id + n, dtype=np.uint32), x, props
@@ -194,10 +194,13 @@ class DEMSolver:
         # DEMSolver::setup_solid_objects (dem.cc:164-191) + SerialSolid::setup_triangulation
         # (serial_solid.cc:163-216: read, rotate, translate)
         for so in p.solid_surfaces:
-            from .mesh_io import read_msh_triangles
+            from .mesh_io import dealii_simplex_surface, read_msh_triangles
 
-            path = so.mesh_file if os.path.isabs(so.mesh_file) else os.path.join(self.prm_directory, so.mesh_file)
-            vertices, triangles = read_msh_triangles(path)
+            if so.mesh_type == "dealii":
+                vertices, triangles = dealii_simplex_surface(so.grid_type, so.grid_arguments, so.initial_refinement)
+            else:
+                path = so.mesh_file if os.path.isabs(so.mesh_file) else os.path.join(self.prm_directory, so.mesh_file)
+                vertices, triangles = read_msh_triangles(path)
             a = np.asarray(so.rotation_axis, dtype=np.float64)
             a = a / np.linalg.norm(a)
             th = so.rotation_angle

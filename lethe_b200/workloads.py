@@ -37,7 +37,7 @@ def make_props(n, d, density, rng, vel_sigma=0.0, types=None):
     d = np.broadcast_to(np.asarray(d, dtype=np.float64), (n,))
     props[:, 0] = 0 if types is None else types
     props[:, 1] = d
-    props[:, 2] = density * 4.0 / 3.0 * math.pi * (d * 0.5) ** 3
+    props[:, 2] = density * 4.0 / 3.0 * math.pi * ((d * 0.5) * (d * 0.5) * (d * 0.5))
     if vel_sigma > 0:
         props[:, 3:6] = rng.normal(0.0, vel_sigma, (n, 3))
     return props

@@ -569,19 +569,81 @@ namespace
       }
   }
 
-  // DEMSolver::sort_particles_into_subdomains_and_cells (dem.cc:982-1016)
+  // The cell a particle registered in `old_cell` belongs to after moving: it stays while it is inside
+  // the old cell up to ParticleHandler's tolerance_inside_cell (1e-12 in unit-cell coordinates).
+  inline int cell_after_move(const Oracle &o, const V3 &x, int old_cell)
+  {
+    if (old_cell >= 0)
+      {
+        const int idx[3] = {old_cell % o.nx, (old_cell / o.nx) % o.ny, old_cell / (o.nx * o.ny)};
+        bool inside = true;
+        for (int d = 0; d < 3; ++d)
+          {
+            const double u = (x[d] - (o.cfg.grid_lo[d] + idx[d] * o.cfg.cell_size[d])) / o.cfg.cell_size[d];
+            inside = inside && u >= -1e-12 && u <= 1. + 1e-12;
+          }
+        if (inside)
+          return old_cell;
+      }
+    return cell_of_point(o, x);
+  }
+
+  // DEMSolver::sort_particles_into_subdomains_and_cells (dem.cc:982-1016) ->
+  // Particles::ParticleHandler::sort_particles_into_subdomains_and_cells of deal.II (external
+  // dependency, >= 9.4 storage: one vector of particles per cell). The order of the particles
+  // inside a cell fixes the order of the broad-search candidates, through it the insertion order of
+  // the contact containers and so the floating-point summation order of the forces; chaotic cases
+  // (solid_surface.output: 78 spheres, dozens of collisions each) only reproduce with the same order:
+  //  1. cells in active-cell order, particles in cell order: those no longer inside go to a list;
+  //  2. in list order each one is appended to the END of its new cell and its old slot invalidated;
+  //  3. remove_particles walks the list BACKWARDS; each invalid slot is overwritten by the cell's
+  //     LAST entry (swap-and-pop), so arrivals fill the holes of departures from the back.
+  // Newly inserted particles were appended to their cells at insertion time, in insertion order.
   void sort_particles_into_subdomains_and_cells(Oracle &o)
   {
     std::vector<std::vector<int>> new_cells(o.n_cells);
     std::vector<char> lost(o.parts.size(), 0);
-    // visit in the current iteration order (cell by cell)
-    for (size_t s = 0; s < o.parts.size(); ++s)
+    size_t registered = 0;
+    for (int c = 0; c < o.n_cells; ++c)
       {
-        const int c = cell_of_point(o, o.parts[s].x);
-        if (c < 0)
-          lost[s] = 1;
+        registered += o.cell_parts[c].size();
+        new_cells[c] = o.cell_parts[c];
+      }
+    for (size_t s = registered; s < o.parts.size(); ++s)
+      {
+        if (o.parts[s].cell < 0)
+          lost[s] = 1; // inserted outside of the triangulation: no cell is found for it
         else
-          new_cells[c].push_back(int(s));
+          new_cells[o.parts[s].cell].push_back(int(s));
+      }
+    struct Out
+    {
+      int cell, index, destination;
+    };
+    std::vector<Out> out_of_cell;
+    for (int r = 0; r < o.n_cells; ++r)
+      {
+        const int c = o.cell_of_rank[r];
+        for (size_t k = 0; k < new_cells[c].size(); ++k)
+          {
+            const int destination = cell_after_move(o, o.parts[new_cells[c][k]].x, c);
+            if (destination != c)
+              out_of_cell.push_back({c, int(k), destination});
+          }
+      }
+    for (const Out &m : out_of_cell)
+      {
+        const int s = new_cells[m.cell][m.index];
+        if (m.destination >= 0)
+          new_cells[m.destination].push_back(s);
+        else
+          lost[s] = 1;
+      }
+    for (auto m = out_of_cell.rbegin(); m != out_of_cell.rend(); ++m)
+      {
+        std::vector<int> &v = new_cells[m->cell];
+        v[m->index] = v.back();
+        v.pop_back();
       }
     std::vector<Particle> np;
     np.reserve(o.parts.size());
@@ -2350,6 +2412,7 @@ int oracle_dem_set_particles(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id,
 {
   Oracle *o = reinterpret_cast<Oracle *>(ctx);
   o->parts.clear();
+  o->cell_parts.assign(o->n_cells, std::vector<int>());
   o->force.clear();
   o->torque.clear();
   o->displacement.clear();

@@ -34,6 +34,9 @@ CASES = {
     "periodic_boundary_collisions": "periodic_boundary_collisions.mpirun=1.output",  # == the mpirun=2 golden
     "distribution_normal": "distribution_normal.output",
     "distribution_lognormal": "distribution_lognormal.output",
+    "solid_surface": "solid_surface.output",
+    "deprecated_parameters": "deprecated_parameters.output",
+    "insert_list_3d_default_velocities": "insert_list_3d_default_velocities.output",
 }
 
 

@@ -305,7 +305,8 @@ APP_CASES = ["rolling_on_plane", "velocity_verlet_free_fall", "multiperiodic_col
              "sliding_in_box", "periodic_boundary_box", "moving_solid_surface_hmlo", "moving_solid_surface_jkr",
              "moving_solid_surface_dmt", "insert_file_3d", "insert_list_3d", "insert_z-x-y",
              "multiperiodic_single_axis_collisions_3d", "single-time-step-list-insertion", "periodic_boundary_collisions",
-             "distribution_normal", "distribution_lognormal"]
+             "distribution_normal", "distribution_lognormal", "solid_surface", "deprecated_parameters",
+             "insert_list_3d_default_velocities"]
 
 
 def run_application_case(case, engine_factory):
