@@ -172,6 +172,9 @@ namespace lethe_b200
     ins.distance_threshold = ii.get_double("insertion distance threshold", 1);
     ins.maximum_offset = ii.get_double("insertion maximum offset", 1);
     ins.prn_seed = ii.get_int("insertion prn seed", 1);
+    if (ii.sub("insertion acceptance function").has("Function expression"))
+      throw std::runtime_error("`insertion acceptance function` needs a function parser; this host has none (the Python mirror "
+                               "lethe_b200/solver.py evaluates it)");
     if (ii.has("insertion direction sequence"))
       {
         const auto seq = ii.get_list("insertion direction sequence");

@@ -97,18 +97,32 @@ def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particl
     for axis in ins.direction_sequence:
         n_dir[axis] = int((ins.box_point_2[axis] - ins.box_point_1[axis]) / (ins.distance_threshold * d_max))
     n_sites = n_dir[0] * n_dir[1] * n_dir[2]
-    n_insert = min(n_insert, n_sites)
-    rnd = _glibc_rand_container(n_sites, ins.maximum_offset, ins.seed)
     a0, a1, a2 = ins.direction_sequence
+
+    def location(site, r1, r2):
+        i0 = site % n_dir[a0]
+        i1 = (site % (n_dir[a0] * n_dir[a1])) // n_dir[a0]
+        i2 = site // (n_dir[a0] * n_dir[a1])
+        out = [0.0, 0.0, 0.0]
+        out[a0] = ins.box_point_1[a0] + ((i0 + 0.5) * ins.distance_threshold - r1) * d_max
+        out[a1] = ins.box_point_1[a1] + ((i1 + 0.5) * ins.distance_threshold - r2) * d_max
+        out[a2] = ins.box_point_1[a2] + ((i2 + 0.5) * ins.distance_threshold - r1) * d_max
+        return out
+
+    # set_filtered_index (insertion_volume.cc:207-351): the sites whose un-jittered location the
+    # acceptance function accepts; the random offsets are drawn for the accepted sites only
+    if ins.acceptance_function:
+        from .prm import evaluate_function
+
+        sites = [k for k in range(n_sites) if evaluate_function(ins.acceptance_function, 0.0, location(k, 0.0, 0.0)) > 0.0]
+    else:
+        sites = range(n_sites)
+    n_valid = len(sites)
+    n_insert = min(n_insert, n_valid)
+    rnd = _glibc_rand_container(n_valid, ins.maximum_offset, ins.seed)
     x = np.empty((n_insert, 3))
     for k in range(n_insert):
-        r1, r2 = rnd[k], rnd[n_sites - k - 1]
-        i0 = k % n_dir[a0]
-        i1 = (k % (n_dir[a0] * n_dir[a1])) // n_dir[a0]
-        i2 = k // (n_dir[a0] * n_dir[a1])
-        x[k, a0] = ins.box_point_1[a0] + ((i0 + 0.5) * ins.distance_threshold - r1) * d_max
-        x[k, a1] = ins.box_point_1[a1] + ((i1 + 0.5) * ins.distance_threshold - r2) * d_max
-        x[k, a2] = ins.box_point_1[a2] + ((i2 + 0.5) * ins.distance_threshold - r1) * d_max
+        x[k] = location(sites[k], rnd[k], rnd[n_valid - k - 1])
     props = np.zeros((n_insert, abi.N_PROPERTIES))
     d = np.abs(distribution.sample(n_insert))  # particle_size_sampling (insertion.cc:78-90)
     h = d * 0.5

@@ -37,6 +37,7 @@ CASES = {
     "solid_surface": "solid_surface.output",
     "deprecated_parameters": "deprecated_parameters.output",
     "insert_list_3d_default_velocities": "insert_list_3d_default_velocities.output",
+    "insertion_acceptance_function": "insertion_acceptance_function.output",
 }
 
 
