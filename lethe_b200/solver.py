@@ -135,6 +135,71 @@ def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particl
     return ids, x, props
 
 
+def active_cell_order(mesh):
+    """Lexicographic cell (i, j, k) triples of the uniform grid in deal.II's active-cell order:
+    lexicographic for an unrefined subdivided grid, the z-order curve after refine_global."""
+    nx, ny, nz = mesh.n
+    cells = [(i, j, k) for k in range(nz) for j in range(ny) for i in range(nx)]
+    if mesh.cell_order != "morton":
+        return cells
+
+    def key(c):
+        out = 0
+        for b in range(max(nx, ny, nz).bit_length()):
+            out |= ((c[0] >> b) & 1) << (3 * b) | ((c[1] >> b) & 1) << (3 * b + 1) | ((c[2] >> b) & 1) << (3 * b + 2)
+        return out
+
+    return sorted(cells, key=key)
+
+
+class PlaneInsertion:
+    """InsertionPlane (source/dem/insertion_plane.cc): at every insertion iteration one particle
+    in each cell cut by the plane that holds no particle, at the cell centre plus rand() * maximum
+    offset / RAND_MAX per axis — glibc's rand() stream, never seeded by this method."""
+
+    def __init__(self, p: DEMParameters):
+        mesh, ins = p.mesh, p.insertion
+        h = mesh.cell_size
+        point, normal = np.asarray(ins.plane_point), np.asarray(ins.plane_normal)
+        self.cells = []  # find_inplane_cells (:43-88), in std::set order = active-cell order
+        for c in active_cell_order(mesh):
+            lo = np.array([mesh.lo[d] + c[d] * h[d] for d in range(3)])
+            ref = None
+            for v in range(8):  # deal.II vertex order: x fastest
+                vertex = lo + np.array([(v & 1) * h[0], ((v >> 1) & 1) * h[1], ((v >> 2) & 1) * h[2]])
+                dist = float(np.dot(vertex - point, normal))
+                if ref is None:
+                    ref = dist
+                elif ref * dist <= 0:
+                    self.cells.append(c)
+                    break
+        self.centers = {c: tuple(mesh.lo[d] + (c[d] + 0.5) * h[d] for d in range(3)) for c in self.cells}
+        self.maximum_range_for_randomness = ins.maximum_offset / float(2147483647)
+        _glibc_rand_container(0, 0.0, 0)  # loads libc
+        _libc.srand(1)  # the state of a process that never called srand
+
+    def insert(self, p, occupied_cells, remaining, first_id, particle_type, distribution):
+        """-> ids, x, props of this iteration's particles. `occupied_cells`: (i, j, k) of the cells
+        particles are registered in (as of the last sort)."""
+        empty = [c for c in self.cells if c not in occupied_cells]
+        n_insert = min(len(empty), remaining)
+        empty = empty[len(empty) - n_insert:]  # surplus cells are dropped from the front (:216-222)
+        x = np.empty((n_insert, 3))
+        for k, c in enumerate(empty):
+            for d in range(3):
+                x[k, d] = self.centers[c][d] + float(_libc.rand()) * self.maximum_range_for_randomness
+        t = p.particle_types[particle_type]
+        props = np.zeros((n_insert, abi.N_PROPERTIES))
+        dp = np.abs(distribution.sample(n_insert))
+        half = dp * 0.5
+        props[:, 0] = particle_type
+        props[:, 1] = dp
+        props[:, 2] = t.density * 4.0 / 3.0 * math.pi * (half * half * half)
+        props[:, 3:6] = p.insertion.initial_velocity
+        props[:, 6:9] = p.insertion.initial_omega
+        return np.arange(first_id, first_id + n_insert, dtype=np.uint32), x, props
+
+
 def list_insertion(p: DEMParameters, first_id: int = 0, particle_type: int = 0):
     """InsertionList::insert (source/dem/insertion_list.cc): the listed positions, velocities and
     diameters, all at the first insertion step."""
@@ -194,6 +259,10 @@ class DEMSolver:
         from .distributions import make_distribution
 
         self._distributions = [make_distribution(t) for t in parameters.particle_types]  # setup_distributions, rank 0
+        # plane insertion asks which cells hold particles, i.e. where the last sort registered them:
+        # the positions that sort saw are kept (one engine call per iteration while it is active)
+        self._plane = PlaneInsertion(parameters) if parameters.insertion.method == "plane" else None
+        self._registered_cells = set()
         self._setup_boundaries()
 
     # DEMSolver::setup_functions_and_pointers / boundary_cell_object.build
@@ -254,6 +323,9 @@ class DEMSolver:
             ids, x, props = file_insertion(p, path, remaining, self._next_id, self._current_type)
         elif p.insertion.method == "list":
             ids, x, props = list_insertion(p, self._next_id, self._current_type)
+        elif p.insertion.method == "plane":
+            ids, x, props = self._plane.insert(p, self._registered_cells, remaining, self._next_id, self._current_type,
+                                               self._distributions[self._current_type])
         else:
             n = min(p.insertion.inserted_this_step, remaining)
             ids, x, props = volume_insertion(p, n, self._next_id, self._current_type, self._distributions[self._current_type])
@@ -299,6 +371,15 @@ class DEMSolver:
                 # iteration, whether or not particles are left to insert (dem.cc:494-500)
                 self.engine.force_contact_search()
             pending += 1
+            if self._plane is not None:
+                _, seen, _ = self.engine.get_particles()  # what a sort in this iteration registers
+                searches = self.engine.get_stats().n_rebuilds
+                self.engine.step(pending)
+                pending = 0
+                if self.engine.get_stats().n_rebuilds != searches:
+                    mesh = p_mesh = self.parameters.mesh
+                    h = mesh.cell_size
+                    self._registered_cells = {tuple(int(math.floor((row[d] - p_mesh.lo[d]) / h[d])) for d in range(3)) for row in seen}
         if pending:
             self.engine.step(pending)
         self.engine.synchronize_velocities()

@@ -38,6 +38,7 @@ CASES = {
     "deprecated_parameters": "deprecated_parameters.output",
     "insert_list_3d_default_velocities": "insert_list_3d_default_velocities.output",
     "insertion_acceptance_function": "insertion_acceptance_function.output",
+    "insert_plane_3d": "insert_plane_3d.output",  # == the mpirun=2 golden
 }
 
 

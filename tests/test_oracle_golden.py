@@ -306,7 +306,7 @@ APP_CASES = ["rolling_on_plane", "velocity_verlet_free_fall", "multiperiodic_col
              "moving_solid_surface_dmt", "insert_file_3d", "insert_list_3d", "insert_z-x-y",
              "multiperiodic_single_axis_collisions_3d", "single-time-step-list-insertion", "periodic_boundary_collisions",
              "distribution_normal", "distribution_lognormal", "solid_surface", "deprecated_parameters",
-             "insert_list_3d_default_velocities", "insertion_acceptance_function"]
+             "insert_list_3d_default_velocities", "insertion_acceptance_function", "insert_plane_3d"]
 
 
 def run_application_case(case, engine_factory):
