@@ -39,6 +39,7 @@ CASES = {
     "insert_list_3d_default_velocities": "insert_list_3d_default_velocities.output",
     "insertion_acceptance_function": "insertion_acceptance_function.output",
     "insert_plane_3d": "insert_plane_3d.output",  # == the mpirun=2 golden
+    "initial_value_insertion": "initial_value_insertion.output",
 }
 
 
