@@ -97,6 +97,17 @@ def main():
     three = cpo.split("dim = 3")[1]
     g["combined_periodic_offsets_3d"] = [floats(l.split("::")[1]) for l in three.splitlines() if "(" in l]
     g["contact_on_two_processors_y"] = contact_on_two_processors()
+    # two_particles_multiple_contacts_parallel (2 ranks, both spheres on rank 1): force_y on particle 0 every 10th step
+    g["two_particles_multiple_contacts"] = [[int(m.group(1)), float(m.group(2))] for m in re.finditer(
+        r"at step (\d+) is: (\S+)", read("tests/dem/two_particles_multiple_contacts_parallel.mpirun=2.output"))]
+    for k in (1, 2):  # insertion_volume_{1,2}: the 10 inserted positions
+        g[f"insertion_volume_{k}"] = [[float(v) for v in l.split("at:")[1].split()]
+                                      for l in read(f"tests/dem/insertion_volume_{k}.output").splitlines() if "inserted at" in l]
+    # boundary_cells_and_faces: (active cell, deal.II face number) of the 96 boundary faces, in face-number order
+    g["boundary_cells_and_faces"] = [[int(m.group(1)), int(m.group(2))] for m in re.finditer(
+        r"Cell 2\.(\d+) is on system boundaries \(boundary(\d+)\)", read("tests/dem/boundary_cells_and_faces.output"))]
+    g["insertion_plane"] = [[float(v) for v in l.split("at:")[1].split()]
+                            for l in read("tests/dem/insertion_plane.output").splitlines() if "inserted at" in l]
     # find_cell_neighbors<3, false> on hyper_cube(-1, 1) refined twice: "2.k" = active cell k of level 2
     fcn = read("tests/dem/find_cell_neighbors.output").split("reciprocal = 1")[0]
     g["find_cell_neighbors"] = [[int(v.split(".")[1]) for v in re.findall(r"2\.\d+", l.split("are:")[1])]

@@ -482,7 +482,8 @@ def test_moving_solid_surface_parity_stepwise():
                                   "pw_jkr_equilibrium", "pw_dmt_equilibrium", "epsd_rolling_resistance_model", "sliding_in_box",
                                   "periodic_boundary_box", "moving_solid_surface_hmlo", "moving_solid_surface_jkr",
                                   "moving_solid_surface_dmt", "insert_z-x-y", "periodic_boundary_collisions",
-                                  "multiperiodic_single_axis_collisions_3d", "insert_file_3d", "deprecated_parameters"])
+                                  "multiperiodic_single_axis_collisions_3d", "insert_file_3d", "deprecated_parameters", "initial_value_insertion",
+                                  "insertion_acceptance_function"])
 def test_application_goldens_on_gpu(case):
     """The reference's application tests (unmodified .prm files) through the CUDA engine: final
     positions to the 4 printed decimals of the reference's .output."""

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from lethe_b200 import abi
-from lethe_b200.prm import load_prm
+from lethe_b200.prm import Mesh, load_prm
 from lethe_b200.solver import DEMSolver, box_wall_faces
 from oracle import loader
 from tests.util import GOLDEN, assert_sig6, golden, props_row, unit_test_parameters
@@ -306,7 +306,8 @@ APP_CASES = ["rolling_on_plane", "velocity_verlet_free_fall", "multiperiodic_col
              "moving_solid_surface_dmt", "insert_file_3d", "insert_list_3d", "insert_z-x-y",
              "multiperiodic_single_axis_collisions_3d", "single-time-step-list-insertion", "periodic_boundary_collisions",
              "distribution_normal", "distribution_lognormal", "solid_surface", "deprecated_parameters",
-             "insert_list_3d_default_velocities", "insertion_acceptance_function", "insert_plane_3d"]
+             "insert_list_3d_default_velocities", "insertion_acceptance_function", "insert_plane_3d",
+             "initial_value_insertion"]
 
 
 def run_application_case(case, engine_factory):
@@ -431,3 +432,115 @@ def test_cell_neighbor_lists_match_reference_goldens(oracle_lib):
     e = loader.oracle_engine(unit_test_parameters().to_config())
     assert loader.cell_neighbors(e, 0) == golden()["find_cell_neighbors"]
     assert loader.cell_neighbors(e, 1) == golden()["find_full_cell_neighbors"]
+
+
+def test_particle_wall_contact_pairs_and_fine_search_goldens(oracle_lib):
+    """tests/dem/particle_wall_contact_pairs.cc (golden: only particle 2, at x = 0.8, is in a boundary
+    cell) and particle_wall_fine_search.cc (golden: particle 0 at x = -0.998 holds one wall contact whose
+    stored normal — from the wall to the particle — is 1 0 0). deal.II's face number (77) is not
+    reproducible without its face enumeration and is not compared."""
+    p = unit_test_parameters()
+    faces = box_wall_faces(p.mesh)
+    e = loader.oracle_engine(p.to_config())
+    e.set_walls(faces)
+    e.set_particles([0, 1, 2], [[-0.4, 0, 0], [0.4, 0, 0], [0.8, 0, 0]], [props_row(0, 0.2, 1.0)] * 3)
+    e.step(1)
+    particle, face, _ = e.get_wall_contacts()
+    assert list(particle) == [2]
+
+    e = loader.oracle_engine(p.to_config())
+    e.set_walls(faces)
+    e.set_particles([0], [[-0.998, 0, 0]], [props_row(0, 0.005, 1.0)])
+    e.step(1)
+    particle, face, _ = e.get_wall_contacts()
+    assert list(particle) == [0] and len(face) == 1
+    hit = [f for f in faces if f.global_face_id == face[0]]
+    assert len(hit) == 1 and tuple(hit[0].normal) == (1.0, 0.0, 0.0)
+
+
+def test_two_particles_multiple_contacts_golden(oracle_lib):
+    """tests/dem/two_particles_multiple_contacts_parallel.cc (its only golden is the 2-rank run, both
+    spheres on one rank): a sphere falls at 0.4 m/s onto one at rest, E = 5e7, nu = 0.9, e = 0.9,
+    m = MOI = 1, plain integrate() from the first step; the y force on particle 0 at every 10th of
+    1000 steps to the 6 printed digits (100 samples through the whole contact)."""
+    p = unit_test_parameters(restitution=0.9)
+    p.particle_types[0].poisson = 0.9
+    p.restart = True
+    p.contact_detection_method, p.contact_detection_frequency = "constant", 1
+    e = loader.oracle_engine(p.to_config(store_forces=True, moi_override=1.0))
+    e.set_particles([0, 1], [[0, 0.007, 0], [0, 0.001, 0]], [props_row(0, 0.005, 1, (0, -0.4, 0)), props_row(0, 0.005, 1)])
+    series = dict(golden()["two_particles_multiple_contacts"])
+    assert len(series) == 100 and max(series.values()) > 100
+    for it in range(1000):
+        e.step(1)
+        if it in series:
+            _, f, _ = e.get_forces()
+            assert_sig6(f[0, 1], series[it], f"it={it}")
+
+
+@pytest.mark.parametrize("case,offset", [(1, 0.75), (2, 0.0)])
+def test_insertion_volume_goldens(case, offset):
+    """tests/dem/insertion_volume_{1,2}.cc: 10 spheres of 5 mm in the box (-0.05, 0.05)^3, distance
+    threshold 2, maximum offset 0.75 / 0, seed 19: the inserted positions (lattice site order, the
+    two glibc rand() offsets per sphere and their pairing r[k], r[n - k - 1]) to 6 digits."""
+    from lethe_b200.solver import volume_insertion
+
+    p = unit_test_parameters()
+    p.particle_types[0].number = 10
+    ins = p.insertion
+    ins.box_point_1, ins.box_point_2 = (-0.05, -0.05, -0.05), (0.05, 0.05, 0.05)
+    ins.direction_sequence, ins.inserted_this_step = (0, 1, 2), 10
+    ins.distance_threshold, ins.maximum_offset, ins.seed = 2.0, offset, 19
+    _, x, _ = volume_insertion(p, 10)
+    gold = golden()[f"insertion_volume_{case}"]
+    assert len(gold) == 10
+    for row, g_row in zip(x, gold):
+        for a, b in zip(row, g_row):
+            assert_sig6(a, b, f"insertion_volume_{case}")
+
+
+def test_insertion_plane_golden():
+    """tests/dem/insertion_plane.cc: hyper_cube(-2, 2) refined twice, plane y = 1.75 with normal y,
+    maximum offset 0.2: one sphere in each of the 16 cells the plane cuts, in active-cell order, at
+    the cell centre plus three successive glibc rand() offsets — positions to 6 digits."""
+    from lethe_b200.solver import PlaneInsertion
+
+    p = unit_test_parameters(d=0.2)
+    p.mesh = Mesh((-2.0,) * 3, (2.0,) * 3, (4, 4, 4), True, "morton")
+    p.particle_types[0].number = 16
+    p.insertion.method = "plane"
+    p.insertion.plane_point, p.insertion.plane_normal, p.insertion.maximum_offset = (0.0, 1.75, 0.0), (0.0, 1.0, 0.0), 0.2
+    plane = PlaneInsertion(p)
+    from lethe_b200.distributions import make_distribution
+
+    ids, x, props = plane.insert(p, set(), 16, 0, 0, make_distribution(p.particle_types[0]))
+    gold = golden()["insertion_plane"]
+    assert len(gold) == len(ids) == 16
+    for row, g_row in zip(x, gold):
+        for a, b in zip(row, g_row):
+            assert_sig6(a, b, "insertion_plane")
+
+
+def test_boundary_cells_and_faces_golden():
+    """tests/dem/boundary_cells_and_faces.cc on hyper_cube(-1, 1) refined twice: the 96 (boundary
+    cell, boundary face) rows. deal.II's face numbers (42..137) come from its refinement history and
+    are not restated; what is compared is which cells carry how many boundary faces, and that the
+    golden's 6 runs of 16 rows are exactly the six sides of box_wall_faces (y-, z-, x-, x+, y+, z+
+    in deal.II's numbering)."""
+    from collections import Counter
+
+    from lethe_b200.solver import active_cell_order
+
+    p = unit_test_parameters()
+    rank = {c: r for r, c in enumerate(active_cell_order(p.mesh))}
+    nx, ny, _ = p.mesh.n
+    mine = {}
+    for f in box_wall_faces(p.mesh):
+        c = (f.cell % nx, (f.cell // nx) % ny, f.cell // (nx * ny))
+        mine.setdefault(tuple(f.normal), []).append(rank[c])
+    gold = golden()["boundary_cells_and_faces"]
+    assert len(gold) == 96 and sorted(n for _, n in gold) == list(range(42, 138))
+    assert Counter(c for c, _ in gold) == Counter(c for cells in mine.values() for c in cells)
+    sides = [(0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (1.0, 0.0, 0.0), (-1.0, 0.0, 0.0), (0.0, -1.0, 0.0), (0.0, 0.0, -1.0)]
+    for k, normal in enumerate(sides):  # inward normals
+        assert sorted(c for c, _ in gold[16 * k:16 * k + 16]) == sorted(mine[normal]), normal
