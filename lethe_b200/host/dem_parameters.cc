@@ -65,6 +65,21 @@ namespace lethe_b200
     }
   } // namespace
 
+  void SolidSurface::velocities_at(double t, Vec3 &translational, Vec3 &angular) const
+  {
+    FunctionExpression::Variables v;
+    v.t = t;
+    translational = translational_velocity;
+    angular = angular_velocity;
+    for (int c = 0; c < 3; ++c)
+      {
+        if (!translational_velocity_function[c].empty())
+          translational[c] = translational_velocity_function[c](v);
+        if (!angular_velocity_function[c].empty())
+          angular[c] = angular_velocity_function[c](v);
+      }
+  }
+
   double Mesh::minimal_cell_diameter() const
   {
     const Vec3 h = cell_size();
@@ -173,8 +188,11 @@ namespace lethe_b200
     ins.maximum_offset = ii.get_double("insertion maximum offset", 1);
     ins.prn_seed = ii.get_int("insertion prn seed", 1);
     if (ii.sub("insertion acceptance function").has("Function expression"))
-      throw std::runtime_error("`insertion acceptance function` needs a function parser; this host has none (the Python mirror "
-                               "lethe_b200/solver.py evaluates it)");
+      ins.acceptance_function = FunctionExpression(ii.sub("insertion acceptance function").get("Function expression", ""));
+    if (ii.has("insertion plane point"))
+      ins.plane_point = to_vec3(ii.get_list("insertion plane point"), "insertion plane point");
+    if (ii.has("insertion plane normal vector"))
+      ins.plane_normal = to_vec3(ii.get_list("insertion plane normal vector"), "insertion plane normal vector");
     if (ii.has("insertion direction sequence"))
       {
         const auto seq = ii.get_list("insertion direction sequence");
@@ -223,24 +241,22 @@ namespace lethe_b200
         sd.rotation_angle = m.get_double("initial rotation angle", 0);
         if (m.has("initial translation"))
           sd.translation = to_vec3(m.get_list("initial translation"), "initial translation");
-        // constant `Function expression = a ; b ; c` only (time-dependent motion: lethe_dem_set_solid_motion)
-        auto constant_function = [&](const char *sub, Vec3 &out) {
+        // `Function expression = a ; b ; c`: three expressions of t (muparser syntax)
+        auto velocity_function = [&](const char *sub, std::array<FunctionExpression, 3> &fn, Vec3 &at_start) {
           const PrmSection &f = s.sub(sub);
           if (!f.has("Function expression"))
             return;
-          try
+          const auto parts = PrmSection::split(f.get("Function expression", ""), ';');
+          if (parts.size() != 3)
+            throw std::runtime_error(std::string("expected 3 `;`-separated expressions for `") + sub + "`");
+          for (int c = 0; c < 3; ++c)
             {
-              out = to_vec3(f.get_list("Function expression", ';'), sub);
-            }
-          catch (const std::exception &)
-            {
-              throw std::runtime_error(std::string("solid surfaces: `") + sub + "` = `" + f.get("Function expression", "") +
-                                       "` depends on time; this host evaluates constant expressions only (drive the motion "
-                                       "with lethe_dem_set_solid_motion, as lethe_b200/solver.py does)");
+              fn[c] = FunctionExpression(PrmSection::trim(parts[c]));
+              at_start[c] = fn[c](FunctionExpression::Variables());
             }
         };
-        constant_function("translational velocity", sd.translational_velocity);
-        constant_function("angular velocity", sd.angular_velocity);
+        velocity_function("translational velocity", sd.translational_velocity_function, sd.translational_velocity);
+        velocity_function("angular velocity", sd.angular_velocity_function, sd.angular_velocity);
         if (s.has("center of rotation"))
           sd.center_of_rotation = to_vec3(s.get_list("center of rotation"), "center of rotation");
         p.solid_surfaces.push_back(sd);

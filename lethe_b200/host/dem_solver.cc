@@ -92,7 +92,31 @@ namespace lethe_b200
     long n_dir[3] = {0, 0, 0};
     for (int axis : ins.direction_sequence)
       n_dir[axis] = long((ins.box_point_2[axis] - ins.box_point_1[axis]) / (ins.distance_threshold * d_max));
-    const long n_sites = n_dir[0] * n_dir[1] * n_dir[2];
+    const long n_lattice = n_dir[0] * n_dir[1] * n_dir[2];
+    const int a0 = ins.direction_sequence[0], a1 = ins.direction_sequence[1], a2 = ins.direction_sequence[2];
+    auto location = [&](long site, double r1, double r2, double *out) {
+      const long i0 = site % n_dir[a0], i1 = (site % (n_dir[a0] * n_dir[a1])) / n_dir[a0], i2 = site / (n_dir[a0] * n_dir[a1]);
+      out[a0] = ins.box_point_1[a0] + ((i0 + 0.5) * ins.distance_threshold - r1) * d_max;
+      out[a1] = ins.box_point_1[a1] + ((i1 + 0.5) * ins.distance_threshold - r2) * d_max;
+      out[a2] = ins.box_point_1[a2] + ((i2 + 0.5) * ins.distance_threshold - r1) * d_max;
+    };
+    // set_filtered_index (insertion_volume.cc:207-351): the sites whose un-jittered location the
+    // acceptance function accepts; the random offsets are drawn for the accepted sites only
+    std::vector<long> sites;
+    for (long k = 0; k < n_lattice; ++k)
+      {
+        if (!ins.acceptance_function.empty())
+          {
+            double x[3];
+            location(k, 0., 0., x);
+            FunctionExpression::Variables v;
+            v.x = x[0], v.y = x[1], v.z = x[2];
+            if (!(ins.acceptance_function(v) > 0.))
+              continue;
+          }
+        sites.push_back(k);
+      }
+    const long n_sites = long(sites.size());
     n_insert = std::min(n_insert, n_sites);
     // one srand(seed * (i + 1)) + rand() per site
     std::vector<double> rnd(n_sites);
@@ -101,7 +125,6 @@ namespace lethe_b200
         srand(unsigned(ins.prn_seed * (i + 1)));
         rnd[i] = (double(rand()) / double(RAND_MAX)) * ins.maximum_offset;
       }
-    const int a0 = ins.direction_sequence[0], a1 = ins.direction_sequence[1], a2 = ins.direction_sequence[2];
     ParticleRows rows;
     rows.id.resize(n_insert);
     rows.x.resize(3 * n_insert);
@@ -110,11 +133,7 @@ namespace lethe_b200
     for (long k = 0; k < n_insert; ++k)
       {
         const double d = std::fabs(diameters[k]), half = d * 0.5;
-        const double r1 = rnd[k], r2 = rnd[n_sites - k - 1];
-        const long i0 = k % n_dir[a0], i1 = (k % (n_dir[a0] * n_dir[a1])) / n_dir[a0], i2 = k / (n_dir[a0] * n_dir[a1]);
-        rows.x[3 * k + a0] = ins.box_point_1[a0] + ((i0 + 0.5) * ins.distance_threshold - r1) * d_max;
-        rows.x[3 * k + a1] = ins.box_point_1[a1] + ((i1 + 0.5) * ins.distance_threshold - r2) * d_max;
-        rows.x[3 * k + a2] = ins.box_point_1[a2] + ((i2 + 0.5) * ins.distance_threshold - r1) * d_max;
+        location(sites[k], rnd[k], rnd[n_sites - k - 1], &rows.x[3 * k]);
         double *pr = &rows.props[size_t(LETHE_DEM_N_PROPERTIES) * k];
         pr[0] = particle_type;
         pr[1] = d;
@@ -123,6 +142,89 @@ namespace lethe_b200
           {
             pr[3 + c] = ins.initial_velocity[c];
             pr[6 + c] = ins.initial_omega[c];
+          }
+        rows.id[k] = first_id + uint32_t(k);
+      }
+    return rows;
+  }
+
+  std::vector<std::array<int, 3>> active_cell_order(const Mesh &mesh)
+  {
+    std::vector<std::array<int, 3>> cells;
+    for (int k = 0; k < mesh.n[2]; ++k)
+      for (int j = 0; j < mesh.n[1]; ++j)
+        for (int i = 0; i < mesh.n[0]; ++i)
+          cells.push_back({{i, j, k}});
+    if (mesh.cell_order != LETHE_CELL_ORDER_MORTON)
+      return cells;
+    auto key = [](const std::array<int, 3> &c) {
+      uint64_t out = 0;
+      for (int b = 0; b < 21; ++b)
+        out |= (uint64_t((c[0] >> b) & 1) << (3 * b)) | (uint64_t((c[1] >> b) & 1) << (3 * b + 1)) | (uint64_t((c[2] >> b) & 1) << (3 * b + 2));
+      return out;
+    };
+    std::sort(cells.begin(), cells.end(), [&](const std::array<int, 3> &a, const std::array<int, 3> &b) { return key(a) < key(b); });
+    return cells;
+  }
+
+  PlaneInsertion::PlaneInsertion(const DEMParameters &p)
+  {
+    const Mesh &mesh = p.mesh;
+    const Vec3 h = mesh.cell_size();
+    const Vec3 &point = p.insertion.plane_point, &normal = p.insertion.plane_normal;
+    // find_inplane_cells (insertion_plane.cc:43-88): a sign change of the vertex distances
+    for (const auto &c : active_cell_order(mesh))
+      {
+        double reference = 0;
+        for (int v = 0; v < 8; ++v) // deal.II vertex order: x fastest
+          {
+            double distance = 0;
+            for (int d = 0; d < 3; ++d)
+              distance += ((mesh.lo[d] + (c[d] + ((v >> d) & 1)) * h[d]) - point[d]) * normal[d];
+            if (v == 0)
+              reference = distance;
+            else if (reference * distance <= 0)
+              {
+                cells.push_back(c);
+                break;
+              }
+          }
+      }
+    maximum_range_for_randomness = p.insertion.maximum_offset / double(RAND_MAX);
+    srand(1); // the method never seeds: the stream of a process that has not called srand
+  }
+
+  ParticleRows PlaneInsertion::insert(const DEMParameters &p, const std::vector<char> &occupied, long remaining, uint32_t first_id,
+                                      int particle_type, SizeDistribution &sizes)
+  {
+    const Mesh &mesh = p.mesh;
+    const Vec3 h = mesh.cell_size();
+    std::vector<std::array<int, 3>> empty;
+    for (const auto &c : cells)
+      if (!occupied.at(size_t(c[0] + mesh.n[0] * (c[1] + mesh.n[1] * c[2]))))
+        empty.push_back(c);
+    const long n_insert = std::min<long>(long(empty.size()), remaining);
+    empty.erase(empty.begin(), empty.begin() + (long(empty.size()) - n_insert)); // surplus cells go from the front (:216-222)
+    const ParticleType &t = p.particle_types.at(particle_type);
+    ParticleRows rows;
+    rows.id.resize(n_insert);
+    rows.x.resize(3 * n_insert);
+    rows.props.assign(size_t(LETHE_DEM_N_PROPERTIES) * n_insert, 0.0);
+    for (long k = 0; k < n_insert; ++k)
+      for (int d = 0; d < 3; ++d)
+        rows.x[3 * k + d] = (mesh.lo[d] + (empty[k][d] + 0.5) * h[d]) + double(rand()) * maximum_range_for_randomness;
+    const std::vector<double> diameters = sizes.sample(n_insert);
+    for (long k = 0; k < n_insert; ++k)
+      {
+        const double d = std::fabs(diameters[k]), half = d * 0.5;
+        double *pr = &rows.props[size_t(LETHE_DEM_N_PROPERTIES) * k];
+        pr[0] = particle_type;
+        pr[1] = d;
+        pr[2] = t.density * 4.0 / 3.0 * M_PI * (half * half * half);
+        for (int c = 0; c < 3; ++c)
+          {
+            pr[3 + c] = p.insertion.initial_velocity[c];
+            pr[6 + c] = p.insertion.initial_omega[c];
           }
         rows.id[k] = first_id + uint32_t(k);
       }
@@ -139,6 +241,11 @@ namespace lethe_b200
       {
         remaining_particles.push_back(t.number_of_particles);
         size_distributions.emplace_back(t, 0u);
+      }
+    if (parameters.insertion.method == "plane")
+      {
+        plane_insertion = std::make_unique<PlaneInsertion>(parameters);
+        occupied_cells.assign(size_t(parameters.mesh.n[0]) * parameters.mesh.n[1] * parameters.mesh.n[2], 0);
       }
     setup_boundaries();
   }
@@ -191,6 +298,7 @@ namespace lethe_b200
               v[3 * k + r] = (R[r][0] * x[0] + R[r][1] * x[1] + R[r][2] * x[2]) + so.translation[r];
           }
         engine->add_solid_surface(v, t, so.translational_velocity.data(), so.angular_velocity.data(), so.center_of_rotation.data());
+        solid_motion.push_back({so.translational_velocity, so.angular_velocity});
       }
     const double zero[3] = {0, 0, 0};
     for (const auto &bc : parameters.boundary_conditions)
@@ -440,6 +548,11 @@ namespace lethe_b200
       }
     else if (parameters.insertion.method == "list")
       rows = list_insertion(parameters, next_id, current_inserting_type);
+    else if (parameters.insertion.method == "plane")
+      rows = plane_insertion->insert(parameters, occupied_cells, remaining, next_id, current_inserting_type,
+                                     size_distributions.at(current_inserting_type));
+    else if (parameters.insertion.method != "volume")
+      throw std::runtime_error("insertion method `" + parameters.insertion.method + "` is not mirrored by this host");
     else
       rows = volume_insertion(parameters, n, next_id, current_inserting_type, size_distributions.at(current_inserting_type));
     engine->add_particles(rows); // triggers the contact search (DEMActionManager::particle_insertion_step)
@@ -506,6 +619,19 @@ namespace lethe_b200
             print_progression();
             report_statistics();
           }
+        // SerialSolid::move_solid_triangulation evaluates the velocity functions at the previous
+        // time (serial_solid.cc:343-352): hand new values over before the step that uses them
+        for (size_t k = 0; k < parameters.solid_surfaces.size(); ++k)
+          {
+            Vec3 tv, av;
+            parameters.solid_surfaces[k].velocities_at(current_time - parameters.time_step, tv, av);
+            if (tv != solid_motion[k].first || av != solid_motion[k].second)
+              {
+                flush();
+                engine->set_solid_motion(int(k), tv.data(), av.data());
+                solid_motion[k] = {tv, av};
+              }
+          }
         bool any_left = false;
         for (long r : remaining_particles)
           any_left = any_left || r > 0;
@@ -519,6 +645,31 @@ namespace lethe_b200
             engine->force_contact_search(false);
           }
         ++pending;
+        if (plane_insertion)
+          {
+            // what a sort in this iteration registers: the positions it sees
+            const ParticleRows seen = engine->get_particles();
+            const uint64_t searches = engine->stats().n_rebuilds;
+            flush();
+            if (engine->stats().n_rebuilds != searches)
+              {
+                const Mesh &mesh = parameters.mesh;
+                const Vec3 h = mesh.cell_size();
+                occupied_cells.assign(size_t(mesh.n[0]) * mesh.n[1] * mesh.n[2], 0);
+                for (size_t q = 0; q < seen.size(); ++q)
+                  {
+                    long c[3];
+                    bool inside = true;
+                    for (int d = 0; d < 3; ++d)
+                      {
+                        c[d] = long(std::floor((seen.x[3 * q + d] - mesh.lo[d]) / h[d]));
+                        inside = inside && c[d] >= 0 && c[d] < mesh.n[d];
+                      }
+                    if (inside)
+                      occupied_cells[size_t(c[0] + mesh.n[0] * (c[1] + mesh.n[1] * c[2]))] = 1;
+                  }
+              }
+          }
       }
     flush();
     // closing half kick of the velocity-Verlet scheme (dem.cc:1249-1259)

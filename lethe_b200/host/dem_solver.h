@@ -41,6 +41,23 @@ namespace lethe_b200
     std::lognormal_distribution<> lognormal;
   };
   ParticleRows volume_insertion(const DEMParameters &p, long n_insert, uint32_t first_id, int particle_type, SizeDistribution &sizes);
+  // (i, j, k) of the uniform grid's cells in deal.II's active-cell order: lexicographic for an
+  // unrefined subdivided grid, the z-order curve after refine_global
+  std::vector<std::array<int, 3>> active_cell_order(const Mesh &mesh);
+  // InsertionPlane (insertion_plane.cc): one particle in every cell the plane cuts that holds no
+  // particle, at the cell centre plus rand() * maximum offset / RAND_MAX per axis
+  class PlaneInsertion
+  {
+  public:
+    explicit PlaneInsertion(const DEMParameters &p);
+    // `occupied`: linear index (i + nx (j + ny k)) -> whether particles are registered in the cell
+    ParticleRows insert(const DEMParameters &p, const std::vector<char> &occupied, long remaining, uint32_t first_id, int particle_type,
+                        SizeDistribution &sizes);
+
+  private:
+    std::vector<std::array<int, 3>> cells; // find_inplane_cells, in active-cell order
+    double maximum_range_for_randomness = 0;
+  };
   // InsertionList::insert (insertion_list.cc): the listed positions / velocities / diameters
   ParticleRows list_insertion(const DEMParameters &p, uint32_t first_id, int particle_type);
   // InsertionFile::insert (insertion_file.cc:27-130): one `;`-separated table per insertion
@@ -82,6 +99,10 @@ namespace lethe_b200
     uint32_t next_id = 0;
     size_t current_file_id = 0;
     std::vector<SizeDistribution> size_distributions; // one per particle type (setup_distributions)
+    // plane insertion asks which cells hold particles, i.e. where the last sort registered them
+    std::unique_ptr<PlaneInsertion> plane_insertion;
+    std::vector<char> occupied_cells;
+    std::vector<std::pair<Vec3, Vec3>> solid_motion; // last velocities handed to the engine
     // contact_list statistics of report_statistics
     double list_min = 1e300, list_max = 0, list_total = 0;
   };

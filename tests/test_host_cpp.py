@@ -131,7 +131,8 @@ def test_host_sources_solid_surface_prm_against_oracle():
 
 @pytest.mark.parametrize("case", ["insert_file_3d", "epsd_rolling_resistance_model", "moving_solid_surface_hmlo", "sliding_in_box",
                                   "distribution_normal", "distribution_lognormal", "solid_surface", "deprecated_parameters",
-                                  "insert_list_3d_default_velocities"])
+                                  "insert_list_3d_default_velocities", "insertion_acceptance_function", "insert_plane_3d",
+                                  "initial_value_insertion"])
 def test_host_sources_application_goldens_against_oracle(case):
     """More of the reference's application cases through the C++ host mirror (file / list / volume
     insertion, solid objects, EPSD) linked to the oracle: the printed final table equals the
@@ -146,3 +147,34 @@ def test_host_sources_application_goldens_against_oracle(case):
     assert err <= 1.01e-4, (case, err)  # both sides print 4 decimals
     derr = np.abs(np.array([r_[2] for r_ in rows]) - np.array([g[2] for g in gold])).max()
     assert derr <= 1.01e-5, (case, derr)  # diameters: 5 decimals
+
+
+def test_host_sources_time_dependent_solid_velocity(tmp_path):
+    """A solid-object velocity that depends on time (muparser conditional and power, as in
+    load_balancing_solid_object.prm) through the C++ host's own expression evaluator
+    (function_expression.h): same final table as the Python mirror on the same engine."""
+    import shutil
+
+    from lethe_b200.prm import load_prm
+    from lethe_b200.solver import DEMSolver
+
+    src = os.path.join(GOLDEN, "apps", "moving_solid_surface_hmlo.prm")
+    case_dir = tmp_path / "apps"
+    case_dir.mkdir()
+    shutil.copy(os.path.join(GOLDEN, "square.msh"), tmp_path / "square.msh")
+    with open(src) as f:
+        text = f.read().replace("set Function expression = -0.1 ; 0 ; 0", "set Function expression = if(t < 0.2, -0.1, -0.4 * t^2) ; 0 ; 0.01*sin(2*pi*t)")
+    assert "sin(2*pi*t)" in text
+    text = text.replace("set time end         = 1", "set time end         = 0.5")
+    prm = case_dir / "moving.prm"
+    prm.write_text(text)
+    r = subprocess.run([oracle_host_binary(), str(prm), "--quiet"], capture_output=True, text=True, check=True)
+    rows = parse_xyz(r.stdout)
+    solver = DEMSolver(load_prm(str(prm)), engine_factory=loader.oracle_engine, prm_directory=str(case_dir))
+    ids, x, props = solver.solve()
+    assert [r_[0] for r_ in rows] == list(ids) and len(ids) > 0
+    assert np.abs(np.array([r_[3:6] for r_ in rows]) - x).max() <= 0.51e-4
+    # and the motion did something: not the constant-velocity golden
+    with open(os.path.join(GOLDEN, "apps", "final_positions.json")) as f:
+        gold = np.array([g[3:6] for g in json.load(f)["moving_solid_surface_hmlo"]])
+    assert np.abs(x - gold).max() > 1e-3
