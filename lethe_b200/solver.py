@@ -81,11 +81,14 @@ def _glibc_rand_container(n: int, maximum_range: float, seed: int):
     return out
 
 
-def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particle_type: int = 0, distribution=None):
+def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particle_type: int = 0, distribution=None, n_ranks: int = 1):
     """InsertionVolume::insert / find_insertion_location
     (source/dem/insertion_volume.cc:43-206) + assign_particle_properties
     (source/dem/insertion.cc:60-121) on one rank. `distribution` is the particle type's size
-    distribution object (its generator state carries over from one insertion to the next)."""
+    distribution object (its generator state carries over from one insertion to the next).
+    `n_ranks` > 1 restates how the reference run on that many MPI processes pairs sites with random
+    offsets (each process takes a contiguous share of the lattice and indexes its OWN random vector,
+    insertion_volume.cc:256-283): only needed to reproduce its multi-rank goldens."""
     ins = p.insertion
     d_max = p.d_max
     t = p.particle_types[particle_type]
@@ -119,10 +122,19 @@ def volume_insertion(p: DEMParameters, n_insert: int, first_id: int = 0, particl
         sites = range(n_sites)
     n_valid = len(sites)
     n_insert = min(n_insert, n_valid)
-    rnd = _glibc_rand_container(n_valid, ins.maximum_offset, ins.seed)
     x = np.empty((n_insert, 3))
-    for k in range(n_insert):
-        x[k] = location(sites[k], rnd[k], rnd[n_valid - k - 1])
+    share = n_sites // n_ranks
+    k = 0
+    for rank in range(n_ranks):
+        first = n_sites - (n_sites - (n_ranks - 1) * share) if rank == n_ranks - 1 else rank * share
+        last = n_sites if rank == n_ranks - 1 else (rank + 1) * share
+        mine = [site for site in sites if first <= site < last]
+        rnd = _glibc_rand_container(len(mine), ins.maximum_offset, ins.seed)
+        for counter, site in enumerate(mine):
+            if k >= n_insert:
+                break
+            x[k] = location(site, rnd[counter], rnd[len(mine) - counter - 1])
+            k += 1
     props = np.zeros((n_insert, abi.N_PROPERTIES))
     d = np.abs(distribution.sample(n_insert))  # particle_size_sampling (insertion.cc:78-90)
     h = d * 0.5
@@ -243,9 +255,10 @@ class DEMSolver:
     """`DEMSolver<3, DEMProperties>` with the hot path behind the C ABI."""
 
     def __init__(self, parameters: DEMParameters, engine_factory=None, device: int = 0, store_forces=False, moi_override=0.0,
-                 prm_directory="."):
+                 prm_directory=".", reference_insertion_ranks=1):
         self.parameters = parameters
         self.prm_directory = prm_directory  # mesh file names of the .prm are relative to it
+        self.reference_insertion_ranks = reference_insertion_ranks  # see volume_insertion(n_ranks=)
         self.config = parameters.to_config(store_forces=store_forces, moi_override=moi_override)
         factory = engine_factory or (lambda cfg: abi.load_engine(cfg, device))
         self.engine = factory(self.config)
@@ -328,7 +341,8 @@ class DEMSolver:
                                                self._distributions[self._current_type])
         else:
             n = min(p.insertion.inserted_this_step, remaining)
-            ids, x, props = volume_insertion(p, n, self._next_id, self._current_type, self._distributions[self._current_type])
+            ids, x, props = volume_insertion(p, n, self._next_id, self._current_type, self._distributions[self._current_type],
+                                             n_ranks=self.reference_insertion_ranks)
         self.engine.add_particles(ids, x, props)
         self._next_id += len(ids)
         self._remaining[self._current_type] -= len(ids)

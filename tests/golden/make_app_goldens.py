@@ -40,6 +40,8 @@ CASES = {
     "insertion_acceptance_function": "insertion_acceptance_function.output",
     "insert_plane_3d": "insert_plane_3d.output",  # == the mpirun=2 golden
     "initial_value_insertion": "initial_value_insertion.output",
+    # a 2-rank golden: the run needs DEMSolver(reference_insertion_ranks=2) for the same site / offset pairing
+    "periodic_boundary_load_balancing": "periodic_boundary_load_balancing.mpirun=2.output",
 }
 
 
