@@ -34,6 +34,7 @@ int LETHE_DEM_FN(add_solid_surface)(lethe_dem_ctx *, uint32_t, const double *, u
                                     const double *, int32_t *);
 int LETHE_DEM_FN(set_solid_motion)(lethe_dem_ctx *, int32_t, const double *, const double *);
 int LETHE_DEM_FN(step)(lethe_dem_ctx *, uint64_t);
+int LETHE_DEM_FN(step_host)(lethe_dem_ctx *, uint64_t, uint64_t, const uint32_t *, double *, double *);
 int LETHE_DEM_FN(synchronize_velocities)(lethe_dem_ctx *);
 int LETHE_DEM_FN(force_contact_search)(lethe_dem_ctx *, int);
 int LETHE_DEM_FN(get_stats)(lethe_dem_ctx *, lethe_dem_stats *);
@@ -111,6 +112,11 @@ namespace lethe_b200
     }
     void set_solid_motion(int solid, const double tv[3], const double av[3]) { check(LETHE_DEM_FN(set_solid_motion)(ctx, solid, tv, av)); }
     void step(uint64_t n_steps) { check(LETHE_DEM_FN(step)(ctx, n_steps)); }
+    // overwrite the state of the listed particles, then n_steps steps (rows come back updated)
+    void step_host(uint64_t n_steps, ParticleRows &r)
+    {
+      check(LETHE_DEM_FN(step_host)(ctx, n_steps, r.size(), r.id.data(), r.x.data(), r.props.data()));
+    }
     void synchronize_velocities() { check(LETHE_DEM_FN(synchronize_velocities)(ctx)); }
     void force_contact_search(bool clear_tangential_displacement)
     {

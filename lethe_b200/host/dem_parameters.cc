@@ -189,6 +189,13 @@ namespace lethe_b200
     ins.prn_seed = ii.get_int("insertion prn seed", 1);
     if (ii.sub("insertion acceptance function").has("Function expression"))
       ins.acceptance_function = FunctionExpression(ii.sub("insertion acceptance function").get("Function expression", ""));
+    ins.remove_particles = ii.get_bool("remove particles", false);
+    if (ii.has("removal box points coordinates"))
+      {
+        const auto pts = PrmSection::split(ii.get("removal box points coordinates", ""), ':');
+        ins.removal_box_point_1 = to_vec3(PrmSection::split_doubles(pts.at(0), ','), "removal box points coordinates");
+        ins.removal_box_point_2 = to_vec3(PrmSection::split_doubles(pts.at(1), ','), "removal box points coordinates");
+      }
     if (ii.has("insertion plane point"))
       ins.plane_point = to_vec3(ii.get_list("insertion plane point"), "insertion plane point");
     if (ii.has("insertion plane normal vector"))

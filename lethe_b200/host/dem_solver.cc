@@ -243,8 +243,9 @@ namespace lethe_b200
         size_distributions.emplace_back(t, 0u);
       }
     if (parameters.insertion.method == "plane")
+      plane_insertion = std::make_unique<PlaneInsertion>(parameters);
+    if (plane_insertion || parameters.insertion.remove_particles)
       {
-        plane_insertion = std::make_unique<PlaneInsertion>(parameters);
         occupied_cells.assign(size_t(parameters.mesh.n[0]) * parameters.mesh.n[1] * parameters.mesh.n[2], 0);
       }
     setup_boundaries();
@@ -536,6 +537,8 @@ namespace lethe_b200
     const long remaining = remaining_particles[current_inserting_type];
     if (remaining == 0)
       return;
+    if (parameters.insertion.remove_particles)
+      remove_particles_in_box();
     const long n = std::min(parameters.insertion.inserted_this_step, remaining);
     ParticleRows rows;
     if (parameters.insertion.method == "file")
@@ -558,6 +561,71 @@ namespace lethe_b200
     engine->add_particles(rows); // triggers the contact search (DEMActionManager::particle_insertion_step)
     next_id += uint32_t(rows.size());
     remaining_particles[current_inserting_type] -= long(rows.size());
+  }
+
+  long DEMSolverB200::cell_of(const double *x) const
+  {
+    const Mesh &mesh = parameters.mesh;
+    const Vec3 h = mesh.cell_size();
+    long c[3];
+    for (int d = 0; d < 3; ++d)
+      {
+        c[d] = long(std::floor((x[d] - mesh.lo[d]) / h[d]));
+        if (c[d] < 0 || c[d] >= mesh.n[d])
+          return -1;
+      }
+    return c[0] + mesh.n[0] * (c[1] + mesh.n[1] * c[2]);
+  }
+
+  // Every particle REGISTERED in a cell whose 8 vertices are in the box goes, and of the cells with
+  // some vertices in the box those particles whose position is in the box. The C ABI needs no
+  // removal call: the particle is moved out of the triangulation — how the reference itself loses
+  // particles — and the sort of this iteration drops it. New particles then take the lowest free
+  // ids again (ParticleHandler::get_next_free_particle_index).
+  void DEMSolverB200::remove_particles_in_box()
+  {
+    const Mesh &mesh = parameters.mesh;
+    const Vec3 h = mesh.cell_size();
+    const Vec3 &lo = parameters.insertion.removal_box_point_1, &hi = parameters.insertion.removal_box_point_2;
+    const ParticleRows all = engine->get_particles();
+    ParticleRows gone;
+    uint32_t next_free = 0;
+    for (size_t q = 0; q < all.size(); ++q)
+      {
+        long cell = all.id[q] < registered_cell.size() ? registered_cell[all.id[q]] : -1;
+        if (cell < 0)
+          cell = cell_of(&all.x[3 * q]);
+        const long c[3] = {cell % mesh.n[0], (cell / mesh.n[0]) % mesh.n[1], cell / (long(mesh.n[0]) * mesh.n[1])};
+        int vertices_inside = 0;
+        for (int v = 0; v < 8 && cell >= 0; ++v)
+          {
+            bool inside = true;
+            for (int d = 0; d < 3; ++d)
+              {
+                const double coordinate = mesh.lo[d] + (c[d] + ((v >> d) & 1)) * h[d];
+                inside = inside && lo[d] <= coordinate && coordinate <= hi[d];
+              }
+            vertices_inside += inside;
+          }
+        bool position_inside = true;
+        for (int d = 0; d < 3; ++d)
+          position_inside = position_inside && lo[d] <= all.x[3 * q + d] && all.x[3 * q + d] <= hi[d];
+        if (vertices_inside == 8 || (vertices_inside > 0 && position_inside))
+          {
+            gone.id.push_back(all.id[q]);
+            for (int d = 0; d < 3; ++d)
+              gone.x.push_back(mesh.hi[d] + 10.0 * (mesh.hi[d] - mesh.lo[d]));
+            gone.props.insert(gone.props.end(), all.props.begin() + long(LETHE_DEM_N_PROPERTIES * q),
+                              all.props.begin() + long(LETHE_DEM_N_PROPERTIES * (q + 1)));
+          }
+        else
+          next_free = std::max(next_free, all.id[q] + 1);
+      }
+    if (gone.size())
+      {
+        engine->step_host(0, gone);
+        next_id = next_free;
+      }
   }
 
   bool DEMSolverB200::is_at_end() const
@@ -645,7 +713,7 @@ namespace lethe_b200
             engine->force_contact_search(false);
           }
         ++pending;
-        if (plane_insertion)
+        if (plane_insertion || parameters.insertion.remove_particles)
           {
             // what a sort in this iteration registers: the positions it sees
             const ParticleRows seen = engine->get_particles();
@@ -654,19 +722,16 @@ namespace lethe_b200
             if (engine->stats().n_rebuilds != searches)
               {
                 const Mesh &mesh = parameters.mesh;
-                const Vec3 h = mesh.cell_size();
                 occupied_cells.assign(size_t(mesh.n[0]) * mesh.n[1] * mesh.n[2], 0);
+                registered_cell.assign(registered_cell.size(), -1);
                 for (size_t q = 0; q < seen.size(); ++q)
                   {
-                    long c[3];
-                    bool inside = true;
-                    for (int d = 0; d < 3; ++d)
-                      {
-                        c[d] = long(std::floor((seen.x[3 * q + d] - mesh.lo[d]) / h[d]));
-                        inside = inside && c[d] >= 0 && c[d] < mesh.n[d];
-                      }
-                    if (inside)
-                      occupied_cells[size_t(c[0] + mesh.n[0] * (c[1] + mesh.n[1] * c[2]))] = 1;
+                    const long cell = cell_of(&seen.x[3 * q]);
+                    if (seen.id[q] >= registered_cell.size())
+                      registered_cell.resize(size_t(seen.id[q]) + 1, -1);
+                    registered_cell[seen.id[q]] = cell;
+                    if (cell >= 0)
+                      occupied_cells[size_t(cell)] = 1;
                   }
               }
           }

@@ -84,6 +84,8 @@ namespace lethe_b200
     void setup_boundaries();     // setup_functions_and_pointers + boundary_cell_object.build
     bool insertion_due() const;  // insert_particles (dem.cc:484-506)
     void insert_particles();
+    void remove_particles_in_box(); // Insertion::remove_particles_in_box (insertion.cc:132-260)
+    long cell_of(const double *x) const; // linear index of the cell around a point, -1 outside
     bool is_at_end() const;      // SimulationControlTransient::is_at_end
     bool is_verbose_iteration() const { return (iteration_number % parameters.log_frequency) == 0; }
     void print_progression();    // SimulationControlTransientDEM::print_progression
@@ -102,6 +104,7 @@ namespace lethe_b200
     // plane insertion asks which cells hold particles, i.e. where the last sort registered them
     std::unique_ptr<PlaneInsertion> plane_insertion;
     std::vector<char> occupied_cells;
+    std::vector<long> registered_cell; // particle id -> linear cell index of the last sort (-1: none)
     std::vector<std::pair<Vec3, Vec3>> solid_motion; // last velocities handed to the engine
     // contact_list statistics of report_statistics
     double list_min = 1e300, list_max = 0, list_total = 0;

@@ -275,7 +275,9 @@ class DEMSolver:
         # plane insertion asks which cells hold particles, i.e. where the last sort registered them:
         # the positions that sort saw are kept (one engine call per iteration while it is active)
         self._plane = PlaneInsertion(parameters) if parameters.insertion.method == "plane" else None
+        self._track_registration = self._plane is not None or parameters.insertion.remove_particles
         self._registered_cells = set()
+        self._registered = {}  # particle id -> (i, j, k) of the cell the last sort registered it in
         self._setup_boundaries()
 
     # DEMSolver::setup_functions_and_pointers / boundary_cell_object.build
@@ -328,6 +330,8 @@ class DEMSolver:
         remaining = self._remaining[self._current_type]
         if remaining == 0:
             return
+        if p.insertion.remove_particles:
+            self._remove_particles_in_box()
         if p.insertion.method == "file":
             files = p.insertion.input_files
             path = files[self._file_id % len(files)]
@@ -346,6 +350,35 @@ class DEMSolver:
         self.engine.add_particles(ids, x, props)
         self._next_id += len(ids)
         self._remaining[self._current_type] -= len(ids)
+
+    def _cell_of(self, row):
+        mesh = self.parameters.mesh
+        h = mesh.cell_size
+        return tuple(int(math.floor((row[d] - mesh.lo[d]) / h[d])) for d in range(3))
+
+    def _remove_particles_in_box(self):
+        """Insertion::find_cells_in_removing_box + remove_particles_in_box (insertion.cc:132-260):
+        every particle REGISTERED in a cell whose 8 vertices are in the box goes, and of the cells
+        with some vertices in the box those particles whose position is in the box. The C ABI has
+        no removal call and needs none: the particle is moved out of the triangulation, which is
+        how the reference itself loses particles, and the sort of this iteration drops it. New
+        particles then take the lowest free ids again (get_next_free_particle_index)."""
+        p, mesh = self.parameters, self.parameters.mesh
+        lo, hi = np.asarray(p.insertion.removal_box_point_1), np.asarray(p.insertion.removal_box_point_2)
+        h = mesh.cell_size
+        ids, x, props = self.engine.get_particles()
+        gone = []
+        for k, pid in enumerate(ids):
+            c = self._registered.get(int(pid), self._cell_of(x[k]))
+            inside = [all(lo[d] <= mesh.lo[d] + (c[d] + ((v >> d) & 1)) * h[d] <= hi[d] for d in range(3)) for v in range(8)]
+            if all(inside) or (any(inside) and bool(np.all((lo <= x[k]) & (x[k] <= hi)))):
+                gone.append(k)
+        if gone:
+            far = np.ascontiguousarray(x[gone])
+            far[:] = np.asarray(mesh.hi) + 10.0 * (np.asarray(mesh.hi) - np.asarray(mesh.lo))
+            self.engine.step_host(0, np.ascontiguousarray(ids[gone]), far, np.ascontiguousarray(props[gone]))
+            kept = np.delete(ids, gone)
+            self._next_id = int(kept.max()) + 1 if len(kept) else 0
 
     def _is_at_end(self) -> bool:
         # SimulationControlTransient::is_at_end (simulation_control.cc:371-378)
@@ -385,15 +418,14 @@ class DEMSolver:
                 # iteration, whether or not particles are left to insert (dem.cc:494-500)
                 self.engine.force_contact_search()
             pending += 1
-            if self._plane is not None:
-                _, seen, _ = self.engine.get_particles()  # what a sort in this iteration registers
+            if self._track_registration:
+                seen_ids, seen, _ = self.engine.get_particles()  # what a sort in this iteration registers
                 searches = self.engine.get_stats().n_rebuilds
                 self.engine.step(pending)
                 pending = 0
                 if self.engine.get_stats().n_rebuilds != searches:
-                    mesh = p_mesh = self.parameters.mesh
-                    h = mesh.cell_size
-                    self._registered_cells = {tuple(int(math.floor((row[d] - p_mesh.lo[d]) / h[d])) for d in range(3)) for row in seen}
+                    self._registered = {int(pid): self._cell_of(row) for pid, row in zip(seen_ids, seen)}
+                    self._registered_cells = set(self._registered.values())
         if pending:
             self.engine.step(pending)
         self.engine.synchronize_velocities()

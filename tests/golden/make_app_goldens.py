@@ -40,6 +40,7 @@ CASES = {
     "insertion_acceptance_function": "insertion_acceptance_function.output",
     "insert_plane_3d": "insert_plane_3d.output",  # == the mpirun=2 golden
     "initial_value_insertion": "initial_value_insertion.output",
+    "insert_and_remove_with_files": "insert_and_remove_with_files.with_dealii.geq.9.6.mpirun=1.output",
     # a 2-rank golden: the run needs DEMSolver(reference_insertion_ranks=2) for the same site / offset pairing
     "periodic_boundary_load_balancing": "periodic_boundary_load_balancing.mpirun=2.output",
 }
@@ -60,6 +61,8 @@ def main():
     # the moving_solid_surface cases name their mesh `../square.msh` relative to the run directory
     shutil.copy(f"{REF}/moving_solid_surface_files/square.msh", os.path.join(os.path.dirname(OUT), "square.msh"))
     shutil.copy(f"{REF}/insert_file_3d_files/particles.input", os.path.join(os.path.dirname(OUT), "particles.input"))
+    for k in (0, 1):
+        shutil.copy(f"{REF}/insert_and_remove_with_files_files/particles_0{k}.input", os.path.join(os.path.dirname(OUT), f"particles_0{k}.input"))
     with open(f"{OUT}/final_positions.json", "w") as f:
         json.dump(gold, f)
 

@@ -483,7 +483,8 @@ def test_moving_solid_surface_parity_stepwise():
                                   "periodic_boundary_box", "moving_solid_surface_hmlo", "moving_solid_surface_jkr",
                                   "moving_solid_surface_dmt", "insert_z-x-y", "periodic_boundary_collisions",
                                   "multiperiodic_single_axis_collisions_3d", "insert_file_3d", "deprecated_parameters", "initial_value_insertion",
-                                  "insertion_acceptance_function", "periodic_boundary_load_balancing", "insert_plane_3d"])
+                                  "insertion_acceptance_function", "periodic_boundary_load_balancing", "insert_plane_3d",
+                                  "insert_and_remove_with_files"])
 def test_application_goldens_on_gpu(case):
     """The reference's application tests (unmodified .prm files) through the CUDA engine: final
     positions to the 4 printed decimals of the reference's .output."""

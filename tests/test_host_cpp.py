@@ -132,7 +132,7 @@ def test_host_sources_solid_surface_prm_against_oracle():
 @pytest.mark.parametrize("case", ["insert_file_3d", "epsd_rolling_resistance_model", "moving_solid_surface_hmlo", "sliding_in_box",
                                   "distribution_normal", "distribution_lognormal", "solid_surface", "deprecated_parameters",
                                   "insert_list_3d_default_velocities", "insertion_acceptance_function", "insert_plane_3d",
-                                  "initial_value_insertion"])
+                                  "initial_value_insertion", "insert_and_remove_with_files"])
 def test_host_sources_application_goldens_against_oracle(case):
     """More of the reference's application cases through the C++ host mirror (file / list / volume
     insertion, solid objects, EPSD) linked to the oracle: the printed final table equals the

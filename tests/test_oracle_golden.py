@@ -307,7 +307,8 @@ APP_CASES = ["rolling_on_plane", "velocity_verlet_free_fall", "multiperiodic_col
              "multiperiodic_single_axis_collisions_3d", "single-time-step-list-insertion", "periodic_boundary_collisions",
              "distribution_normal", "distribution_lognormal", "solid_surface", "deprecated_parameters",
              "insert_list_3d_default_velocities", "insertion_acceptance_function", "insert_plane_3d",
-             "initial_value_insertion", "periodic_boundary_load_balancing"]
+             "initial_value_insertion", "periodic_boundary_load_balancing",
+             "insert_and_remove_with_files"]
 # goldens the reference produced on 2 MPI ranks with a volume insertion: each rank pairs its share of
 # the lattice with its own random vector, which the mirror restates on request
 REFERENCE_INSERTION_RANKS = {"periodic_boundary_load_balancing": 2}
