@@ -14,9 +14,9 @@ Workload (config.workload):
           list rebuilds (NCCL).  `--workload periodic_box --n-per-gpu 8000000` runs config 5.
 
 value     whole-job particle-steps/s with state resident in HBM (CUDA events, max over ranks)
-e2e       the same through lethe_dem_step_host on every rank: pinned HOST rows of the owned
-          particles uploaded, one step, rows downloaded, every step (the reference-facing
-          per-step plugin call; PCIe-bound at ~55 GB/s per direction)
+e2e       the same through lethe_dem_step_host_state on every rank: pinned HOST rows (x, v, omega)
+          of the owned particles uploaded, one step, rows downloaded, every step (the
+          reference-facing per-step plugin call; PCIe-bound at ~55 GB/s per direction)
 roofline  fused step kernel: algorithmic bytes (160+16+4*C+48*T per particle-step,
           C,T measured) / CUDA-event kernel time, against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample, 1 core
@@ -299,17 +299,22 @@ def main():
             pass
 
     # ---- e2e: per-step plugin call with pinned host rows ----
-    # Every rank keeps host rows of the particles it owns and hands them to lethe_dem_step_host
-    # every step (rows up, one step, rows down). When particles changed owner in a rebuild, the
-    # rank re-reads its owned rows (inside the timed region).
+    # Every rank keeps host rows of the particles it owns — what a step changes: x, v, omega, 72 B
+    # per particle — and hands them to lethe_dem_step_host_state every step (rows up, one step, rows
+    # down). The row -> id table goes up with the first call and again whenever particles changed
+    # owner in a rebuild (the rank then re-reads its owned rows, inside the timed region).
     def owned_rows():
         ids_, x_, props_ = engine.get_particles()
-        return (torch.from_numpy(ids_.copy()).pin_memory(), torch.from_numpy(np.ascontiguousarray(x_)).pin_memory(),
-                torch.from_numpy(np.ascontiguousarray(props_)).pin_memory())
+        state = np.ascontiguousarray(np.concatenate([x_, props_[:, 3:9]], axis=1))
+        return [torch.from_numpy(ids_.copy()).pin_memory(), torch.from_numpy(state).pin_memory(), True]
+
+    id_uploads = [0]
 
     def host_step(rows, n_steps, rebuilds_seen):
-        hid, hx, hp = rows
-        engine.step_host_ptr(n_steps, len(hid), hid.data_ptr(), hx.data_ptr(), hp.data_ptr())
+        hid, hstate, fresh = rows
+        engine.step_host_state_ptr(n_steps, len(hid), hid.data_ptr() if fresh else 0, hstate.data_ptr())
+        id_uploads[0] += len(hid) if fresh else 0
+        rows[2] = False
         if world > 1:
             r = engine.get_stats().n_migrated  # particles changed owner: re-read the owned rows
             if r != rebuilds_seen:
@@ -323,11 +328,13 @@ def main():
     barrier()
     t0 = time.perf_counter()
     n_moved = 0
+    id_uploads[0] = 0
     for _ in range(args.e2e_steps):
         n_moved += len(rows[0])
         rows, seen = host_step(rows, 1, seen)
     barrier()
     dt = time.perf_counter() - t0
+    n_id_rows = id_uploads[0]
     sub = 100
     barrier()
     t0 = time.perf_counter()
@@ -339,15 +346,15 @@ def main():
         tt = torch.tensor([dt, dtb], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt, dtb = float(tt[0].item()), float(tt[1].item())
-        nn = torch.tensor([float(n_moved)], device="cuda", dtype=torch.float64)
+        nn = torch.tensor([float(n_moved), float(n_id_rows)], device="cuda", dtype=torch.float64)
         dist.all_reduce(nn, op=dist.ReduceOp.SUM)
-        n_moved = int(nn.item())
+        n_moved, n_id_rows = int(nn[0].item()), int(nn[1].item())
     per_step = n_moved / max(1, args.e2e_steps)
     e2e = {
         "value": n_moved / dt, "unit": "particle-steps/s",
-        "h2d_bytes_per_step": int(per_step * (4 + 24 + 72)), "d2h_bytes_per_step": int(per_step * (24 + 72)),
-        "call": "lethe_dem_step_host(n_steps=1) on every rank: upload id/x/props rows of the owned particles, 1 DEM step, "
-                "download x/props rows, every step",
+        "h2d_bytes_per_step": int(per_step * 72 + 4 * n_id_rows / max(1, args.e2e_steps)), "d2h_bytes_per_step": int(per_step * 72),
+        "call": "lethe_dem_step_host_state(n_steps=1) on every rank: upload the x/v/omega rows of the owned particles (72 B each; "
+                "the id table only when ownership changed), 1 DEM step, download the rows, every step",
         "batched": {"steps_per_call": sub, "value": n_global * sub * 3 / dtb, "unit": "particle-steps/s"},
     }
 

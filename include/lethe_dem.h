@@ -228,6 +228,13 @@ int lethe_dem_force_contact_search(lethe_dem_ctx *ctx, int clear_tangential_disp
  * the updated rows into the same buffers. Contact history stays resident. */
 int lethe_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
                         const uint32_t *id, double *x3, double *props9);
+/* The same call moving only what a step changes: state9 = [n][9] rows of
+ * x, y, z, v_x, v_y, v_z, omega_x, omega_y, omega_z (what Integrator::integrate writes,
+ * velocity_verlet_integrator.cc:214-290); type, diameter and mass keep the values given at
+ * insertion. id = the particle of every row; NULL = the table of the previous call (same n),
+ * which is then not uploaded again. 72 bytes per particle each way instead of 100 / 96. */
+int lethe_dem_step_host_state(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
+                              const uint32_t *id, double *state9);
 
 /* --- debug taps / statistics --- */
 /* Unordered pairs (i_id < j_id) of the contact list with the tangential

@@ -147,6 +147,7 @@ ABI_SYMBOLS = [
     "synchronize_velocities",
     "force_contact_search",
     "step_host",
+    "step_host_state",
     "get_pairs",
     "get_wall_contacts",
     "get_forces",
@@ -320,6 +321,17 @@ class Engine:
         assert ids.dtype == np.uint32 and x.dtype == np.float64 and props.dtype == np.float64
         assert x.flags.c_contiguous and props.flags.c_contiguous
         self._call("step_host", C.c_uint64(n_steps), C.c_uint64(len(ids)), _ptr(ids, _p_u32), _ptr(x, _p_f64), _ptr(props, _p_f64))
+
+    def step_host_state(self, n_steps, ids, state9):
+        """lethe_dem_step_host_state: rows of (x, v, omega) up, n_steps, rows down in place;
+        ids=None reuses the id table of the previous call."""
+        assert state9.dtype == np.float64 and state9.flags.c_contiguous and state9.shape[1] == 9
+        id_arg = None if ids is None else _ptr(np.ascontiguousarray(ids, dtype=np.uint32), _p_u32)
+        self._call("step_host_state", C.c_uint64(n_steps), C.c_uint64(len(state9)), id_arg, _ptr(state9, _p_f64))
+
+    def step_host_state_ptr(self, n_steps, n, id_ptr, state_ptr):
+        """Same on raw host addresses (pinned buffers); id_ptr = 0 reuses the previous id table."""
+        self._call("step_host_state", C.c_uint64(n_steps), C.c_uint64(n), C.c_void_p(id_ptr or None), C.c_void_p(state_ptr))
 
     def step_host_ptr(self, n_steps, n, id_ptr, x_ptr, props_ptr):
         """Same as step_host on raw host addresses (pinned buffers)."""

@@ -229,6 +229,10 @@ struct lethe_dem_ctx
 
   // staging for host rows
   DevBuf<uint32_t> stage_ids;
+  // lethe_dem_step_host_state: the row -> particle id table of the caller's host rows, kept between
+  // calls so that an unchanged table is not uploaded again
+  DevBuf<uint32_t> host_row_ids;
+  uint64_t host_row_ids_n = 0;
   DevBuf<double> stage_x, stage_p;
   DevBuf<StatsPartial> stats_partials;
 

@@ -1345,6 +1345,35 @@ int lethe_dem_force_contact_search(lethe_dem_ctx *c, int clear_tangential_displa
   return 0;
 }
 
+int lethe_dem_step_host_state(lethe_dem_ctx *c, uint64_t n_steps, uint64_t n, const uint32_t *id, double *state9)
+{
+  return guarded(c, [&] {
+    cudaStream_t s = c->stream;
+    if (n)
+      {
+        if (id)
+          {
+            c->host_row_ids.ensure(n);
+            CU_TRY(cudaMemcpyAsync(c->host_row_ids.p, id, n * 4, cudaMemcpyHostToDevice, s));
+            c->host_row_ids_n = n;
+          }
+        else if (c->host_row_ids_n != n)
+          throw std::runtime_error("step_host_state: id == NULL reuses the id table of the previous call, which had a different row count");
+        c->stage_p.ensure(9 * n);
+        CU_TRY(cudaMemcpyAsync(c->stage_p.p, state9, 9 * n * 8, cudaMemcpyHostToDevice, s));
+        launch_update_state_rows(c->host_row_ids.p, c->stage_p.p, uint32_t(n), c->slot_of_id.p, c->slot_map_size, c->st[c->cur].view(), s);
+      }
+    for (uint64_t k = 0; k < n_steps; ++k)
+      one_step(c);
+    if (n)
+      {
+        launch_pack_state_rows(c->host_row_ids.p, uint32_t(n), c->slot_of_id.p, c->slot_map_size, c->st[c->cur].view(), c->stage_p.p, s);
+        CU_TRY(cudaMemcpyAsync(state9, c->stage_p.p, 9 * n * 8, cudaMemcpyDeviceToHost, s));
+      }
+    CU_TRY(cudaStreamSynchronize(s));
+  });
+}
+
 int lethe_dem_step_host(lethe_dem_ctx *c, uint64_t n_steps, uint64_t n, const uint32_t *id, double *x3, double *props9)
 {
   return guarded(c, [&] {

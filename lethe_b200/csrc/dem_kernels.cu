@@ -623,6 +623,45 @@ namespace dem
       st.omg[q] = make_double4(p[6], p[7], p[8], p[0]);
     }
 
+    // step_host_state: the 9 doubles that a step changes (x, v, omega); diameter, mass and type
+    // in the .w lanes stay what add_particles / set_particles made them
+    __global__ void __launch_bounds__(256) k_update_state_rows(const uint32_t *ids, const double *state9, uint32_t n,
+                                                               const uint32_t *slot_of_id, uint32_t map_size, StateView st)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t pid = ids[k];
+      if (pid >= map_size)
+        return;
+      const uint32_t q = slot_of_id[pid];
+      if (q == 0xffffffffu)
+        return;
+      const double *p = state9 + 9 * size_t(k);
+      st.pos[q] = make_double4(p[0], p[1], p[2], st.pos[q].w);
+      st.vel[q] = make_double4(p[3], p[4], p[5], st.vel[q].w);
+      st.omg[q] = make_double4(p[6], p[7], p[8], st.omg[q].w);
+    }
+
+    __global__ void __launch_bounds__(256) k_pack_state_rows(const uint32_t *ids, uint32_t n, const uint32_t *slot_of_id,
+                                                             uint32_t map_size, StateView st, double *state9)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t pid = ids[k];
+      if (pid >= map_size)
+        return;
+      const uint32_t q = slot_of_id[pid];
+      if (q == 0xffffffffu)
+        return;
+      const double4 x = st.pos[q], v = st.vel[q], w = st.omg[q];
+      double *p = state9 + 9 * size_t(k);
+      p[0] = x.x, p[1] = x.y, p[2] = x.z;
+      p[3] = v.x, p[4] = v.y, p[5] = v.z;
+      p[6] = w.x, p[7] = w.y, p[8] = w.z;
+    }
+
     __device__ __forceinline__ void write_row(double4 x, double4 v, double4 w, double *x3, double *props9, size_t k)
     {
       x3[3 * k] = x.x;
@@ -981,6 +1020,24 @@ namespace dem
     if (n)
       {
         k_pack_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, n, slot_of_id, slot_map_size, st, x3, props9);
+        count_launch();
+      }
+  }
+  void launch_update_state_rows(const uint32_t *ids, const double *state9, uint32_t n, const uint32_t *slot_of_id,
+                                uint32_t slot_map_size, StateView st, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_update_state_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, state9, n, slot_of_id, slot_map_size, st);
+        count_launch();
+      }
+  }
+  void launch_pack_state_rows(const uint32_t *ids, uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st,
+                              double *state9, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_pack_state_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, n, slot_of_id, slot_map_size, st, state9);
         count_launch();
       }
   }

@@ -372,6 +372,10 @@ namespace dem
                                uint32_t *id_out, int32_t *cell_reg, double *disp, uint32_t base, cudaStream_t s);
   void launch_update_from_host_rows(const uint32_t *ids, const double *x3, const double *props9, uint32_t n,
                                     const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, cudaStream_t s);
+  void launch_update_state_rows(const uint32_t *ids, const double *state9, uint32_t n, const uint32_t *slot_of_id,
+                                uint32_t slot_map_size, StateView st, cudaStream_t s);
+  void launch_pack_state_rows(const uint32_t *ids, uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st,
+                              double *state9, cudaStream_t s);
   void launch_pack_host_rows(const uint32_t *ids, uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st,
                              double *x3, double *props9, cudaStream_t s);
   void launch_pack_all_rows(StateView st, const uint32_t *id, uint32_t n, uint32_t *ids_out, double *x3, double *props9,

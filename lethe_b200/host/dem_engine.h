@@ -35,6 +35,7 @@ int LETHE_DEM_FN(add_solid_surface)(lethe_dem_ctx *, uint32_t, const double *, u
 int LETHE_DEM_FN(set_solid_motion)(lethe_dem_ctx *, int32_t, const double *, const double *);
 int LETHE_DEM_FN(step)(lethe_dem_ctx *, uint64_t);
 int LETHE_DEM_FN(step_host)(lethe_dem_ctx *, uint64_t, uint64_t, const uint32_t *, double *, double *);
+int LETHE_DEM_FN(step_host_state)(lethe_dem_ctx *, uint64_t, uint64_t, const uint32_t *, double *);
 int LETHE_DEM_FN(synchronize_velocities)(lethe_dem_ctx *);
 int LETHE_DEM_FN(force_contact_search)(lethe_dem_ctx *, int);
 int LETHE_DEM_FN(get_stats)(lethe_dem_ctx *, lethe_dem_stats *);
@@ -121,6 +122,11 @@ namespace lethe_b200
     void force_contact_search(bool clear_tangential_displacement)
     {
       check(LETHE_DEM_FN(force_contact_search)(ctx, clear_tangential_displacement ? 1 : 0));
+    }
+    // rows of (x, v, omega) only; ids == nullptr reuses the id table of the previous call
+    void step_host_state(uint64_t n_steps, uint64_t n, const uint32_t *ids, double *state9)
+    {
+      check(LETHE_DEM_FN(step_host_state)(ctx, n_steps, n, ids, state9));
     }
     lethe_dem_stats stats()
     {

@@ -226,6 +226,7 @@ namespace
     // particles
     std::vector<Particle> parts;               // iteration (= local index) order
     std::vector<std::vector<int>> cell_parts;  // per lexicographic cell: local indices in order
+    std::vector<uint32_t> host_row_ids;        // step_host_state: id table of the previous call
     std::vector<int> slot_of_id;               // particle_container
     std::vector<V3> force, torque;
     std::vector<double> displacement, MOI;
@@ -2672,6 +2673,34 @@ int oracle_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n, const
       for (int d = 0; d < 3; ++d)
         x3[3 * i + d] = o->parts[s].x[d];
       std::memcpy(props9 + 9 * i, o->parts[s].p, 9 * sizeof(double));
+    }
+  return 0;
+}
+
+int oracle_dem_step_host_state(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n, const uint32_t *id, double *state9)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  if (id)
+    o->host_row_ids.assign(id, id + n);
+  else if (o->host_row_ids.size() != n)
+    return fail(o, "step_host_state: id == NULL reuses the id table of the previous call, which had a different row count");
+  for (uint64_t i = 0; i < n; ++i)
+    {
+      const int s = slot(*o, o->host_row_ids[i]);
+      if (s < 0)
+        continue;
+      o->parts[s].x = mk(state9[9 * i], state9[9 * i + 1], state9[9 * i + 2]);
+      std::memcpy(o->parts[s].p + P_VX, state9 + 9 * i + 3, 6 * sizeof(double));
+    }
+  oracle_dem_step(ctx, n_steps);
+  for (uint64_t i = 0; i < n; ++i)
+    {
+      const int s = slot(*o, o->host_row_ids[i]);
+      if (s < 0)
+        continue;
+      for (int d = 0; d < 3; ++d)
+        state9[9 * i + d] = o->parts[s].x[d];
+      std::memcpy(state9 + 9 * i + 3, o->parts[s].p + P_VX, 6 * sizeof(double));
     }
   return 0;
 }

@@ -329,6 +329,33 @@ def test_step_host_roundtrip_matches_resident():
     assert np.array_equal(xa, hx[order]) and np.array_equal(pa, hp[order])
 
 
+def test_step_host_state_roundtrip_matches_resident():
+    """lethe_dem_step_host_state (x, v, omega rows only; the id table uploaded once and then reused)
+    gives bit for bit what resident stepping gives, in a shuffled row order, and a wrong row count
+    with id = NULL is refused."""
+    d = 0.005
+    ids, x, props, extent = random_packing(8, d=d, spacing=0.99, seed=2)
+    params = packing_parameters(extent, d=d)
+    a, _ = setup_pair(params, ids, x, props)
+    b, _ = setup_pair(params, ids, x, props)
+    a.step(20)
+    perm = np.random.default_rng(5).permutation(len(ids))
+    rows = np.ascontiguousarray(np.concatenate([x, props[:, 3:9]], axis=1)[perm])
+    b.step_host_state(1, ids[perm], rows)
+    b.get_particles()  # other calls in between must not disturb the cached id table
+    for _ in range(19):
+        b.step_host_state(1, None, rows)
+    ia, xa, pa = a.get_particles()
+    back = np.empty_like(rows)
+    back[perm] = rows
+    order = np.argsort(ids)
+    assert np.array_equal(xa, back[order, :3]) and np.array_equal(pa[:, 3:9], back[order, 3:9])
+    ib, xb, pb = b.get_particles()
+    assert np.array_equal(pb[:, :3], pa[:, :3])  # type, diameter, mass untouched
+    with pytest.raises(abi.DEMError):
+        b.step_host_state(1, None, rows[:-1].copy())
+
+
 def test_properties_at_scale():
     """Size-independent properties on a 64^3 packing (262k spheres): run-to-run bitwise
     determinism, exact action-reaction (sum of pair forces == 0 up to summation rounding)

@@ -549,3 +549,26 @@ def test_boundary_cells_and_faces_golden():
     sides = [(0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (1.0, 0.0, 0.0), (-1.0, 0.0, 0.0), (0.0, -1.0, 0.0), (0.0, 0.0, -1.0)]
     for k, normal in enumerate(sides):  # inward normals
         assert sorted(c for c, _ in gold[16 * k:16 * k + 16]) == sorted(mine[normal]), normal
+
+
+def test_step_host_state_equals_step_host(oracle_lib):
+    """The oracle's side of lethe_dem_step_host_state: rows of (x, v, omega) with a cached id table
+    advance exactly like lethe_dem_step_host rows."""
+    from tests.util import packing_parameters, random_packing
+
+    ids, x, props, extent = random_packing(5, d=0.005, spacing=0.99, seed=3)
+    params = packing_parameters(extent, d=0.005)
+    engines = []
+    for _ in range(2):
+        e = loader.oracle_engine(params.to_config())
+        e.set_walls(box_wall_faces(params.mesh))
+        e.set_particles(ids, x, props)
+        engines.append(e)
+    hx, hp = x.copy(), props.copy()
+    rows = np.ascontiguousarray(np.concatenate([x, props[:, 3:9]], axis=1))
+    for k in range(10):
+        engines[0].step_host(1, ids, hx, hp)
+        engines[1].step_host_state(1, ids if k == 0 else None, rows)
+    assert np.array_equal(rows[:, :3], hx) and np.array_equal(rows[:, 3:], hp[:, 3:9])
+    with pytest.raises(abi.DEMError):
+        engines[1].step_host_state(1, None, rows[:-1].copy())
