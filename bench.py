@@ -104,6 +104,19 @@ def make_workload(args, rank, world):
     return workloads.drum(n_target=args.n_per_gpu * world, spacing=1.005, jitter=0.002)
 
 
+_RESULT_FD = None
+
+
+def emit_result(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    text = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, text)
+    else:
+        os.write(_RESULT_FD, text)
+
+
 def run_reference(args):
     """CPU arm: the oracle on every host core, each core an independent sub-domain of the
     workload (what MPI ranks would own, minus the halo cost)."""
@@ -145,7 +158,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_result(line)
 
 
 def cpu_baseline_sample(args):
@@ -192,6 +205,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries ONE JSON line (rank 0). Libraries write there too (NCCL's version banner when the
+    # environment sets NCCL_DEBUG, torch.distributed notices): file descriptor 1 is pointed at stderr
+    # for the whole run and the line goes to the saved descriptor at the end.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
     if args.impl == "reference":
         if rank == 0:
             run_reference(args)
@@ -205,8 +226,6 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the DEM engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of the one-JSON-line stdout
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -375,7 +394,7 @@ def main():
             },
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit_result(line)
     if world > 1:
         dist.destroy_process_group()
 
