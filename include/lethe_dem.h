@@ -222,6 +222,18 @@ int lethe_dem_get_solid_contacts(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n
 int lethe_dem_step(lethe_dem_ctx *ctx, uint64_t n_steps);
 int lethe_dem_synchronize_velocities(lethe_dem_ctx *ctx);
 int lethe_dem_force_contact_search(lethe_dem_ctx *ctx, int clear_tangential_displacement);
+/* The second consumer of the path, the CFD-DEM coupling (fem-dem/cfd_dem_coupling.cc:1380-1540):
+ * - lethe_dem_set_external_loads = add_fluid_particle_interaction_force / _torque (:881-925):
+ *   force3 / torque3 ([n][3], torque3 may be NULL) of the listed particles are added to the
+ *   contact forces of every following step and of lethe_dem_synchronize_velocities, after the
+ *   contact forces and before the integration, until set again; n = 0 clears all loads. In a
+ *   slab-decomposed job every rank sets the loads of the particles it owns.
+ * - lethe_dem_restart_integration: the next step is an opening step of the scheme again
+ *   (integrate_start). CFD-DEM synchronises the velocities at the end of every CFD time step
+ *   (lethe_dem_synchronize_velocities) and opens the next one this way (:1420-1431). */
+int lethe_dem_set_external_loads(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id,
+                                 const double *force3, const double *torque3);
+int lethe_dem_restart_integration(lethe_dem_ctx *ctx);
 /* Reference-facing per-step call with HOST buffers (what a patched DEMSolver
  * that keeps ParticleHandler on the host would call every iteration): uploads
  * x/props for the n particles (same ids as resident), runs n_steps, downloads

@@ -148,6 +148,8 @@ ABI_SYMBOLS = [
     "force_contact_search",
     "step_host",
     "step_host_state",
+    "set_external_loads",
+    "restart_integration",
     "get_pairs",
     "get_wall_contacts",
     "get_forces",
@@ -321,6 +323,16 @@ class Engine:
         assert ids.dtype == np.uint32 and x.dtype == np.float64 and props.dtype == np.float64
         assert x.flags.c_contiguous and props.flags.c_contiguous
         self._call("step_host", C.c_uint64(n_steps), C.c_uint64(len(ids)), _ptr(ids, _p_u32), _ptr(x, _p_f64), _ptr(props, _p_f64))
+
+    def set_external_loads(self, ids, force, torque=None):
+        """lethe_dem_set_external_loads (CFD-DEM fluid-particle interaction); ids=[] clears all."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        f = np.ascontiguousarray(force, dtype=np.float64).reshape(len(ids), 3) if len(ids) else np.zeros((0, 3))
+        t = None if torque is None else np.ascontiguousarray(torque, dtype=np.float64).reshape(len(ids), 3)
+        self._call("set_external_loads", C.c_uint64(len(ids)), _ptr(ids, _p_u32), _ptr(f, _p_f64), None if t is None else _ptr(t, _p_f64))
+
+    def restart_integration(self):
+        self._call("restart_integration")
 
     def step_host_state(self, n_steps, ids, state9):
         """lethe_dem_step_host_state: rows of (x, v, omega) up, n_steps, rows down in place;

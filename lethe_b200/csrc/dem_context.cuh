@@ -231,6 +231,12 @@ struct lethe_dem_ctx
   DevBuf<uint32_t> stage_ids;
   // lethe_dem_step_host_state: the row -> particle id table of the caller's host rows, kept between
   // calls so that an unchanged table is not uploaded again
+  // lethe_dem_set_external_loads: force / torque per particle ID (CFD-DEM fluid-particle interaction),
+  // and the per-row sums handed to the step kernel (solid surfaces + external)
+  DevBuf<double> ext_force, ext_torque, addend_force, addend_torque;
+  uint32_t ext_size = 0;
+  bool ext_enabled = false;
+  bool open_next_step = false; // lethe_dem_restart_integration
   DevBuf<uint32_t> host_row_ids;
   uint64_t host_row_ids_n = 0;
   DevBuf<double> stage_x, stage_p;

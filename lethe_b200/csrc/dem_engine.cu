@@ -667,6 +667,17 @@ namespace
         P.solid_force = c->solid_force.p;
         P.solid_torque = c->solid_torque.p;
       }
+    if (c->ext_enabled && c->n_owned)
+      {
+        // add_fluid_particle_interaction_force / _torque (cfd_dem_coupling.cc:881-925): after the
+        // contact forces (solid surfaces included), before the integration
+        c->addend_force.ensure(3 * size_t(c->n_owned));
+        c->addend_torque.ensure(3 * size_t(c->n_owned));
+        launch_compose_external_loads(P.id, c->n_owned, c->ext_force.p, c->ext_torque.p, c->ext_size, P.solid_force, P.solid_torque,
+                                      c->addend_force.p, c->addend_torque.p, s);
+        P.solid_force = c->addend_force.p;
+        P.solid_torque = c->addend_torque.p;
+      }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (c->timers_enabled)
       {
@@ -816,7 +827,8 @@ namespace
   {
     c->iteration_number++;
     c->current_time += c->cfg.dt;
-    const int phase = (c->iteration_number <= 1 && !c->cfg.restart) ? PHASE_START : PHASE_REGULAR;
+    const int phase = ((c->iteration_number <= 1 && !c->cfg.restart) || c->open_next_step) ? PHASE_START : PHASE_REGULAR;
+    c->open_next_step = false;
     if (c->multi.fused() && c->pipeline)
       step_fused_multi(c, phase);
     else if (!step_speculatively(c, phase))
@@ -1332,8 +1344,63 @@ int lethe_dem_synchronize_velocities(lethe_dem_ctx *c)
   return guarded(c, [&] {
     contact_detection_and_search(c);
     launch_step_kernel(c, PHASE_END);
+    if (!c->multi.enabled() && c->cfg.detection == LETHE_DETECTION_DYNAMIC)
+      {
+        // a caller that goes on stepping after the synchronisation (CFD-DEM does, every CFD time
+        // step): the next iteration's displacement check sees the synchronised velocities
+        launch_accumulate_displacement(c->st[c->cur].view().vel, c->disp.p, c->n_owned, c->cfg.dt,
+                                       c->cfg.smallest_contact_search_criterion, c->flag_dev.p, c->d_flag,
+                                       step_tag(c->iteration_number), c->stream);
+        CU_TRY(cudaEventRecord(c->step_done[c->iteration_number & 1], c->stream));
+      }
     c->contact_search_trigger = false;
     c->clear_history_trigger = false;
+  });
+}
+
+int lethe_dem_restart_integration(lethe_dem_ctx *c)
+{
+  c->open_next_step = true;
+  return 0;
+}
+
+int lethe_dem_set_external_loads(lethe_dem_ctx *c, uint64_t n, const uint32_t *id, const double *force3, const double *torque3)
+{
+  return guarded(c, [&] {
+    cudaStream_t s = c->stream;
+    if (n == 0)
+      {
+        c->ext_enabled = false; // all loads cleared
+        if (c->ext_size)
+          {
+            CU_TRY(cudaMemsetAsync(c->ext_force.p, 0, 3 * size_t(c->ext_size) * 8, s));
+            CU_TRY(cudaMemsetAsync(c->ext_torque.p, 0, 3 * size_t(c->ext_size) * 8, s));
+          }
+        return;
+      }
+    uint32_t max_id = 0;
+    for (uint64_t k = 0; k < n; ++k)
+      max_id = std::max(max_id, id[k]);
+    if (size_t(max_id) + 1 > c->ext_size)
+      {
+        const size_t old = c->ext_size, want = std::max<size_t>(size_t(max_id) + 1, c->slot_map_size);
+        c->ext_force.ensure(3 * want, 3 * old, s, 1.0);
+        c->ext_torque.ensure(3 * want, 3 * old, s, 1.0);
+        CU_TRY(cudaMemsetAsync(c->ext_force.p + 3 * old, 0, 3 * (want - old) * 8, s));
+        CU_TRY(cudaMemsetAsync(c->ext_torque.p + 3 * old, 0, 3 * (want - old) * 8, s));
+        c->ext_size = uint32_t(want);
+      }
+    c->stage_ids.ensure(n);
+    c->stage_x.ensure(3 * n);
+    c->stage_p.ensure(9 * n);
+    CU_TRY(cudaMemcpyAsync(c->stage_ids.p, id, n * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(c->stage_x.p, force3, 3 * n * 8, cudaMemcpyHostToDevice, s));
+    if (torque3)
+      CU_TRY(cudaMemcpyAsync(c->stage_p.p, torque3, 3 * n * 8, cudaMemcpyHostToDevice, s));
+    launch_scatter_external_loads(c->stage_ids.p, c->stage_x.p, torque3 ? c->stage_p.p : nullptr, uint32_t(n), c->ext_force.p,
+                                  c->ext_torque.p, c->ext_size, s);
+    CU_TRY(cudaStreamSynchronize(s)); // the caller's buffers are free again
+    c->ext_enabled = true;
   });
 }
 

@@ -623,6 +623,67 @@ namespace dem
       st.omg[q] = make_double4(p[6], p[7], p[8], p[0]);
     }
 
+    // After the closing half kick the velocities have changed: the displacement the NEXT
+    // iteration's contact-detection check adds (find_contact_detection_step.cc:26-50, dt |v| with
+    // the velocity it finds) is accumulated here, as the step kernel does at the end of a step.
+    __global__ void __launch_bounds__(256) k_accumulate_displacement(const double4 *vel, double *disp, uint32_t n, double dt,
+                                                                     double criterion, uint32_t *flag_local, uint32_t *flag_host,
+                                                                     uint32_t tag)
+    {
+      const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= n)
+        return;
+      const double4 v = vel[i];
+      const double dsp = disp[i] + dt * sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+      disp[i] = dsp;
+      if (dsp > criterion && *reinterpret_cast<volatile uint32_t *>(flag_local) != tag)
+        {
+          *reinterpret_cast<volatile uint32_t *>(flag_local) = tag;
+          if (flag_host)
+            *reinterpret_cast<volatile uint32_t *>(flag_host) = tag;
+        }
+    }
+
+    // External (fluid-particle interaction) loads live per particle ID; the step kernel adds one
+    // per-ROW force / torque pair to the contact sums: gather the rows' loads, on top of the
+    // solid-surface sums of this step when there are any.
+    __global__ void __launch_bounds__(256) k_compose_external_loads(const uint32_t *id, uint32_t n, const double *ext_force,
+                                                                    const double *ext_torque, uint32_t ext_size,
+                                                                    const double *solid_force, const double *solid_torque,
+                                                                    double *force, double *torque)
+    {
+      const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= n)
+        return;
+      const uint32_t pid = id[i];
+      const bool have = pid < ext_size;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        {
+          const double f = have ? ext_force[3 * size_t(pid) + d] : 0.0;
+          const double t = have ? ext_torque[3 * size_t(pid) + d] : 0.0;
+          force[3 * size_t(i) + d] = solid_force ? solid_force[3 * size_t(i) + d] + f : f;
+          torque[3 * size_t(i) + d] = solid_torque ? solid_torque[3 * size_t(i) + d] + t : t;
+        }
+    }
+
+    __global__ void __launch_bounds__(256) k_scatter_external_loads(const uint32_t *ids, const double *force3, const double *torque3,
+                                                                    uint32_t n, double *ext_force, double *ext_torque, uint32_t ext_size)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t pid = ids[k];
+      if (pid >= ext_size)
+        return;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        {
+          ext_force[3 * size_t(pid) + d] = force3[3 * size_t(k) + d];
+          ext_torque[3 * size_t(pid) + d] = torque3 ? torque3[3 * size_t(k) + d] : 0.0;
+        }
+    }
+
     // step_host_state: the 9 doubles that a step changes (x, v, omega); diameter, mass and type
     // in the .w lanes stay what add_particles / set_particles made them
     __global__ void __launch_bounds__(256) k_update_state_rows(const uint32_t *ids, const double *state9, uint32_t n,
@@ -1020,6 +1081,35 @@ namespace dem
     if (n)
       {
         k_pack_host_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, n, slot_of_id, slot_map_size, st, x3, props9);
+        count_launch();
+      }
+  }
+  void launch_accumulate_displacement(const double4 *vel, double *disp, uint32_t n, double dt, double criterion, uint32_t *flag_local,
+                                      uint32_t *flag_host, uint32_t tag, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_accumulate_displacement<<<blocks_for(n, 256), 256, 0, s>>>(vel, disp, n, dt, criterion, flag_local, flag_host, tag);
+        count_launch();
+      }
+  }
+  void launch_compose_external_loads(const uint32_t *id, uint32_t n, const double *ext_force, const double *ext_torque,
+                                     uint32_t ext_size, const double *solid_force, const double *solid_torque, double *force,
+                                     double *torque, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_compose_external_loads<<<blocks_for(n, 256), 256, 0, s>>>(id, n, ext_force, ext_torque, ext_size, solid_force, solid_torque,
+                                                                    force, torque);
+        count_launch();
+      }
+  }
+  void launch_scatter_external_loads(const uint32_t *ids, const double *force3, const double *torque3, uint32_t n, double *ext_force,
+                                     double *ext_torque, uint32_t ext_size, cudaStream_t s)
+  {
+    if (n)
+      {
+        k_scatter_external_loads<<<blocks_for(n, 256), 256, 0, s>>>(ids, force3, torque3, n, ext_force, ext_torque, ext_size);
         count_launch();
       }
   }

@@ -372,6 +372,13 @@ namespace dem
                                uint32_t *id_out, int32_t *cell_reg, double *disp, uint32_t base, cudaStream_t s);
   void launch_update_from_host_rows(const uint32_t *ids, const double *x3, const double *props9, uint32_t n,
                                     const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, cudaStream_t s);
+  void launch_accumulate_displacement(const double4 *vel, double *disp, uint32_t n, double dt, double criterion, uint32_t *flag_local,
+                                      uint32_t *flag_host, uint32_t tag, cudaStream_t s);
+  void launch_compose_external_loads(const uint32_t *id, uint32_t n, const double *ext_force, const double *ext_torque,
+                                     uint32_t ext_size, const double *solid_force, const double *solid_torque, double *force,
+                                     double *torque, cudaStream_t s);
+  void launch_scatter_external_loads(const uint32_t *ids, const double *force3, const double *torque3, uint32_t n, double *ext_force,
+                                     double *ext_torque, uint32_t ext_size, cudaStream_t s);
   void launch_update_state_rows(const uint32_t *ids, const double *state9, uint32_t n, const uint32_t *slot_of_id,
                                 uint32_t slot_map_size, StateView st, cudaStream_t s);
   void launch_pack_state_rows(const uint32_t *ids, uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st,

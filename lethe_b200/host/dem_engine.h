@@ -36,6 +36,8 @@ int LETHE_DEM_FN(set_solid_motion)(lethe_dem_ctx *, int32_t, const double *, con
 int LETHE_DEM_FN(step)(lethe_dem_ctx *, uint64_t);
 int LETHE_DEM_FN(step_host)(lethe_dem_ctx *, uint64_t, uint64_t, const uint32_t *, double *, double *);
 int LETHE_DEM_FN(step_host_state)(lethe_dem_ctx *, uint64_t, uint64_t, const uint32_t *, double *);
+int LETHE_DEM_FN(set_external_loads)(lethe_dem_ctx *, uint64_t, const uint32_t *, const double *, const double *);
+int LETHE_DEM_FN(restart_integration)(lethe_dem_ctx *);
 int LETHE_DEM_FN(synchronize_velocities)(lethe_dem_ctx *);
 int LETHE_DEM_FN(force_contact_search)(lethe_dem_ctx *, int);
 int LETHE_DEM_FN(get_stats)(lethe_dem_ctx *, lethe_dem_stats *);
@@ -128,6 +130,12 @@ namespace lethe_b200
     {
       check(LETHE_DEM_FN(step_host_state)(ctx, n_steps, n, ids, state9));
     }
+    // CFD-DEM: fluid-particle interaction loads per particle id (torque3 may be nullptr; n = 0 clears)
+    void set_external_loads(uint64_t n, const uint32_t *ids, const double *force3, const double *torque3)
+    {
+      check(LETHE_DEM_FN(set_external_loads)(ctx, n, ids, force3, torque3));
+    }
+    void restart_integration() { check(LETHE_DEM_FN(restart_integration)(ctx)); }
     lethe_dem_stats stats()
     {
       lethe_dem_stats s;

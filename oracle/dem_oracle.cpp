@@ -227,6 +227,9 @@ namespace
     std::vector<Particle> parts;               // iteration (= local index) order
     std::vector<std::vector<int>> cell_parts;  // per lexicographic cell: local indices in order
     std::vector<uint32_t> host_row_ids;        // step_host_state: id table of the previous call
+    std::vector<V3> ext_force, ext_torque;     // set_external_loads: per particle id
+    bool ext_enabled = false;
+    bool open_next_step = false;               // restart_integration
     std::vector<int> slot_of_id;               // particle_container
     std::vector<V3> force, torque;
     std::vector<double> displacement, MOI;
@@ -2294,6 +2297,17 @@ namespace
       calculate_particle_wall_contact(o, o.fwall_in_contact, dt);
     if (!o.solids.empty())
       calculate_particle_solid_object_contact(o, dt);
+    // CFDDEMSolver::add_fluid_particle_interaction_force / _torque (cfd_dem_coupling.cc:881-925)
+    if (o.ext_enabled)
+      for (size_t s = 0; s < o.parts.size(); ++s)
+        {
+          const uint32_t id = o.parts[s].id;
+          if (id < o.ext_force.size())
+            {
+              o.force[s] = o.force[s] + o.ext_force[id];
+              o.torque[s] = o.torque[s] + o.ext_torque[id];
+            }
+        }
     if (o.cfg.store_forces)
       {
         o.last_force = o.force;
@@ -2316,10 +2330,11 @@ namespace
     execute_contact_detection_and_search(o);
     move_solid_objects(o); // dem.cc:1141-1142
     compute_contact_forces(o);
-    if (o.iteration_number <= 1 && !o.cfg.restart)
+    if ((o.iteration_number <= 1 && !o.cfg.restart) || o.open_next_step)
       integrate_start(o);
     else
       integrate(o);
+    o.open_next_step = false;
     reset_triggers(o);
   }
 
@@ -2674,6 +2689,36 @@ int oracle_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n, const
         x3[3 * i + d] = o->parts[s].x[d];
       std::memcpy(props9 + 9 * i, o->parts[s].p, 9 * sizeof(double));
     }
+  return 0;
+}
+
+int oracle_dem_restart_integration(lethe_dem_ctx *ctx)
+{
+  reinterpret_cast<Oracle *>(ctx)->open_next_step = true;
+  return 0;
+}
+
+int oracle_dem_set_external_loads(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *force3, const double *torque3)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  if (n == 0)
+    {
+      o->ext_enabled = false;
+      o->ext_force.clear();
+      o->ext_torque.clear();
+      return 0;
+    }
+  for (uint64_t k = 0; k < n; ++k)
+    {
+      if (o->ext_force.size() <= id[k])
+        {
+          o->ext_force.resize(size_t(id[k]) + 1, mk(0, 0, 0));
+          o->ext_torque.resize(size_t(id[k]) + 1, mk(0, 0, 0));
+        }
+      o->ext_force[id[k]] = mk(force3[3 * k], force3[3 * k + 1], force3[3 * k + 2]);
+      o->ext_torque[id[k]] = torque3 ? mk(torque3[3 * k], torque3[3 * k + 1], torque3[3 * k + 2]) : mk(0, 0, 0);
+    }
+  o->ext_enabled = true;
   return 0;
 }
 

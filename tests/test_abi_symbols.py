@@ -21,7 +21,7 @@ def declared_functions():
 def test_header_declares_the_documented_entry_points():
     names = declared_functions()
     for must in ("lethe_dem_create", "lethe_dem_destroy", "lethe_dem_set_particles", "lethe_dem_add_particles", "lethe_dem_set_walls",
-                 "lethe_dem_set_floating_walls", "lethe_dem_set_boundary_motion", "lethe_dem_step", "lethe_dem_step_host", "lethe_dem_step_host_state",
+                 "lethe_dem_set_floating_walls", "lethe_dem_set_boundary_motion", "lethe_dem_step", "lethe_dem_step_host", "lethe_dem_step_host_state", "lethe_dem_set_external_loads", "lethe_dem_restart_integration",
                  "lethe_dem_synchronize_velocities", "lethe_dem_force_contact_search", "lethe_dem_get_particles", "lethe_dem_get_pairs",
                  "lethe_dem_get_forces", "lethe_dem_get_stats", "lethe_dem_comm_init"):
         assert must in names

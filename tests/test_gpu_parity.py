@@ -226,6 +226,38 @@ def test_packing_parity_stepwise(pp, pw, rolling, poly, n_types):
     assert sg.n_pairs_touching == so.n_pairs_touching
 
 
+def test_cfd_dem_external_loads_parity():
+    """The CFD-DEM caller's use of the path: per-particle fluid loads
+    (lethe_dem_set_external_loads) on a packing with contacts, in lock step with the oracle at the
+    same bar, new loads every "CFD step", each CFD step opened with lethe_dem_restart_integration
+    and closed with lethe_dem_synchronize_velocities; loads of only some of the particles, then
+    cleared."""
+    d = 0.005
+    ids, x, props, extent = random_packing(10, d=d, spacing=0.98, jitter=0.08, poly=0.2, seed=21)
+    params = packing_parameters(extent, d=d)
+    g, o = setup_pair(params, ids, x, props)
+    rng = np.random.default_rng(3)
+    mass = props[:, 2]
+    step = 0
+    for cfd_step in range(4):
+        chosen = ids if cfd_step % 2 == 0 else ids[::3]
+        m = mass if cfd_step % 2 == 0 else mass[::3]
+        force = rng.normal(size=(len(chosen), 3)) * (20.0 * m)[:, None]  # ~2 g
+        torque = rng.normal(size=(len(chosen), 3)) * (m * d)[:, None]
+        for e in (g, o):
+            if cfd_step == 3:
+                e.set_external_loads([], [])
+            else:
+                e.set_external_loads(chosen, force, None if cfd_step == 1 else torque)
+            e.restart_integration()
+        lockstep(g, o, 12, 0)
+        for e in (g, o):
+            e.synchronize_velocities()
+        compare_step(g, o, step, check_pairs=True, pos_rtol=1e-11, force_rtol=1e-9)
+        step += 1
+    assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds
+
+
 def test_explicit_euler_parity_stepwise():
     """`integration method = explicit_euler` (explicit_euler_integrator.cc): same lock-step bar."""
     d = 0.005

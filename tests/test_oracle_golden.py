@@ -572,3 +572,46 @@ def test_step_host_state_equals_step_host(oracle_lib):
     assert np.array_equal(rows[:, :3], hx) and np.array_equal(rows[:, 3:], hp[:, 3:9])
     with pytest.raises(abi.DEMError):
         engines[1].step_host_state(1, None, rows[:-1].copy())
+
+
+def test_cfd_dem_subcycle_external_loads(oracle_lib):
+    """The CFD-DEM caller's pattern (fem-dem/cfd_dem_coupling.cc:1380-1540): constant
+    fluid-particle loads over the DEM sub-iterations of a CFD step, the first sub-iteration an
+    opening step, velocities synchronised at the end of the CFD step. Velocity Verlet is exact for
+    constant loads: after K CFD steps x = a t^2 / 2, v = a t, omega = T t / I — and identical to
+    the uninterrupted run."""
+    p = unit_test_parameters(dt=1e-4, g=(0, 0, 0))
+    mass, d = 2.0, 0.01
+    force, torque = np.array([0.3, -0.2, 0.1]), np.array([1e-6, 2e-6, -3e-6])
+    moi = 0.1 * mass * d * d
+
+    def run(cfd_steps, sub, subcycle):
+        e = loader.oracle_engine(p.to_config())
+        e.set_walls(box_wall_faces(p.mesh))
+        e.set_particles([7], [[0.0, 0.0, 0.0]], [props_row(0, d, mass)])
+        e.set_external_loads([7], [force], [torque])
+        for _ in range(cfd_steps):
+            if subcycle:
+                e.restart_integration()
+            e.step(sub)
+            if subcycle:
+                e.synchronize_velocities()
+        if not subcycle:
+            e.synchronize_velocities()
+        return e.get_particles()
+
+    t = 5 * 20 * 1e-4
+    for subcycle in (True, False):
+        _, x, props = run(5, 20, subcycle)
+        assert np.allclose(x[0], 0.5 * force / mass * t * t, rtol=1e-12, atol=0)
+        assert np.allclose(props[0, 3:6], force / mass * t, rtol=1e-12, atol=0)
+        assert np.allclose(props[0, 6:9], torque / moi * t, rtol=1e-12, atol=0)
+    # cleared loads: the particle coasts
+    e = loader.oracle_engine(p.to_config())
+    e.set_walls(box_wall_faces(p.mesh))
+    e.set_particles([7], [[0.0, 0.0, 0.0]], [props_row(0, d, mass)])
+    e.set_external_loads([7], [force])
+    e.set_external_loads([], [])
+    e.step(10)
+    _, x, _ = e.get_particles()
+    assert np.array_equal(x[0], np.zeros(3))
