@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from dataclasses import dataclass
 
 import numpy as np
 
