@@ -248,10 +248,11 @@ def test_packing_in_box_application(oracle_lib):
     gold = np.array([r[3:6] for r in rows])
     assert [r[0] for r in rows] == list(ids)
     err = np.abs(x - gold).max(axis=1)
-    # 4 printed decimals; trajectories are chaotic, so require the bulk to agree to the
-    # printed digit and every particle to within a fraction of a diameter
-    assert np.mean(err <= 1.01e-4) > 0.9, (np.mean(err <= 1.01e-4), err.max())
-    assert err.max() < 0.2 * 0.005, err.max()
+    # 4 printed decimals. The bed is still settling at t_end (speeds up to 0.3 m/s) and mildly
+    # sensitive: a 1e-15 perturbation of the inserted positions moves 11 rows past the printed
+    # digit. The oracle has 195 rows on the digit and 5 off by at most 2e-5 (open item).
+    assert np.mean(err <= 0.5e-4 + 1e-9) >= 0.97, (np.mean(err <= 0.5e-4 + 1e-9), err.max())
+    assert err.max() < 1e-4, err.max()
 
 
 @pytest.mark.parametrize("case", ["edge_vertex_contact", "CPES_double_edge_contact", "NPES_double_edge_contact",
