@@ -178,3 +178,25 @@ def test_host_sources_time_dependent_solid_velocity(tmp_path):
     with open(os.path.join(GOLDEN, "apps", "final_positions.json")) as f:
         gold = np.array([g[3:6] for g in json.load(f)["moving_solid_surface_hmlo"]])
     assert np.abs(x - gold).max() > 1e-3
+
+
+def test_function_expression_evaluator_matches_python_mirror(tmp_path):
+    """lethe_b200/host/function_expression.h against the Python mirror's evaluator on the
+    expression forms the reference's DEM parameter files use (and a few more): same values,
+    constancy detected, malformed input refused."""
+    from lethe_b200.prm import evaluate_function
+
+    exe = str(tmp_path / "eval_expression")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "eval_expression.cc")])
+    point, t = (0.01, 0.07, -0.02), 0.6
+    cases = ["if( (x*x + z * z) < (0.025^2), if(y > 0.05, 1., -1), -1.)", "if(t>0.5,if(t<0.7,1,0),0)", "-0.4 * t^2", "0.01*sin(2*pi*t)",
+             "2^-1 + 3*(x - y)/z", "-x^2", "exp(-t)*cos(pi*t) + sqrt(abs(z))", "min(x, y) + max(y, z)", "1e-3 + 2.5E2*t", "3", "tanh(t) - log(1 + t)"]
+    out = subprocess.run([exe, *(repr(v) for v in point), repr(t), *cases], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert len(out) == len(cases)
+    for expr, line in zip(cases, out):
+        value, constant = line.split()
+        expected = evaluate_function(expr, t, point)
+        assert abs(float(value) - expected) <= 1e-15 * max(1.0, abs(expected)), (expr, value, expected)
+        assert int(constant) == (0 if any(c in expr.replace("exp", "").replace("max", "").replace("tanh", "") for c in "xyzt") else 1), expr
+    bad = subprocess.run([exe, "0", "0", "0", "0", "2 +", "foo(1)", "if(1, 2)", "1 2"], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert len(bad) == 4 and all(line.startswith("error:") for line in bad), bad
