@@ -1,27 +1,36 @@
 #!/usr/bin/env python
 """bench.py — particle-steps/s of the DEM time-step hot path on N B200s (one rank per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
 
-A "step" is one DEM time step (contact-detection check [+ list rebuild when triggered],
-particle-particle + particle-wall forces, velocity-Verlet) of the whole system.
+A bench "step" is `--dem-steps` (default 100) consecutive DEM time steps of the whole system — the
+contact-detection check of every step, the contact-list rebuilds the displacement criterion
+triggers (several per bench step: they are INSIDE the timed region, with the particle migration
+and ghost exchange they imply at N > 1), particle-particle + particle-wall forces, velocity-Verlet.
+The reference arm uses the same unit. particle-steps/s counts DEM steps.
 
 Workload (config.workload):
-  N = 1   BASELINE.json configs[1]: 3D rotating drum, 1M spheres, Hertz-Mindlin limit-overlap
-          + constant rolling resistance, faceted rotating cylinder wall.
-  N > 1   the same drum made N times longer (1M spheres per GPU, weak scaling), slab-decomposed
-          along the drum axis with a ghost-halo exchange every step and particle migration at
-          list rebuilds (NCCL).  `--workload periodic_box --n-per-gpu 8000000` runs config 5.
+  periodic (default)  BASELINE.json configs[4], the configuration the north-star target is quoted
+          on: a FIXED 64 M-sphere 3-periodic box at every N (strong scaling), slab-decomposed along
+          x at N > 1. Disordered packing: the committed 64 000-sphere unit cell
+          (lethe_b200/data/periodic_cell_64000.npz, grown and relaxed by the DEM engine itself,
+          solid fraction 0.64, 2.8 touching pairs and 5.8 list entries per sphere) tiled
+          10 x 10 x 10, every sphere with its own Maxwellian velocity (sigma 0.1 m/s); material of
+          applications_tests/lethe-particles/multiperiodic_collisions_3d.prm (elastic, g = 0).
+  drum    configs[1]: 3D rotating drum, 1 M spheres per GPU (weak scaling), HM limit-overlap +
+          constant rolling resistance, faceted rotating cylinder wall, disordered bed.
+  hopper | box_packing | cohesive_jkr | cohesive_dmt | periodic_lattice: the other configs' workloads.
 
-value     whole-job particle-steps/s with state resident in HBM (CUDA events, max over ranks)
+value     whole-job particle-steps/s with state resident in HBM (CUDA events on the engine's
+          stream, max over ranks), rebuilds included
 e2e       the same through lethe_dem_step_host_state on every rank: pinned HOST rows (x, v, omega)
-          of the owned particles uploaded, one step, rows downloaded, every step (the
-          reference-facing per-step plugin call; PCIe-bound at ~55 GB/s per direction)
+          of the owned particles uploaded, ONE DEM step, rows downloaded, every DEM step (the
+          reference-facing per-step plugin call; PCIe-bound)
 roofline  fused step kernel: algorithmic bytes (160+16+4*C+48*T per particle-step,
-          C,T measured) / CUDA-event kernel time, against MEASURED_PEAKS.json hbm_gbs
+          C,T measured in this run) / CUDA-event kernel time, against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample, 1 core
---impl reference  the oracle on all host cores (independent sub-domains, no halo cost) — the
-          reference itself (deal.II + MPI) cannot be built in this image.
+--impl reference  the oracle on all host cores (independent sub-domains of the same workload, no
+          halo cost) — the reference itself (deal.II + MPI) cannot be built in this image.
 """
 import argparse
 import json
@@ -37,6 +46,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "particle-steps/sec"
+CELL_D = 0.002  # sphere diameter of the periodic workload (m)
 
 
 def measured_peak():
@@ -84,10 +94,22 @@ def algorithmic_bytes(c_half, t_half, epsd=False):
     return 160.0 + 16.0 + 4.0 * c_half + 48.0 * t_half * (2.0 if epsd else 1.0)
 
 
+def periodic_reps(n_particles, n_cell):
+    """Tiles per direction of the unit cell for ~n_particles spheres (x gets the remainder)."""
+    r = max(1, round((n_particles / n_cell) ** (1.0 / 3.0)))
+    rx = max(1, round(n_particles / (n_cell * r * r)))
+    return (rx, r, r)
+
+
 def make_workload(args, rank, world):
     from lethe_b200 import workloads
 
-    if args.workload == "periodic_box":
+    if args.workload == "periodic":
+        xc, Lc, _ = workloads.load_periodic_cell()
+        reps = periodic_reps(args.particles, len(xc))
+        return workloads.periodic_packing(xc * CELL_D, Lc * CELL_D, reps, d=CELL_D, vel_sigma=args.vel_sigma,
+                                          slab=(rank, world) if world > 1 else None)
+    if args.workload == "periodic_lattice":
         # cubic cells per direction for ~n_per_gpu*world particles: 4 per FCC cell
         per = args.n_per_gpu
         side = max(4, round((per / 4.0) ** (1.0 / 3.0)))
@@ -101,7 +123,22 @@ def make_workload(args, rank, world):
     if args.workload == "box_packing":
         side = max(4, round((args.n_per_gpu / 1.41) ** (1.0 / 3.0)))
         return workloads.box_packing(side, spacing=1.005, jitter=0.002)
-    return workloads.drum(n_target=args.n_per_gpu * world, spacing=1.005, jitter=0.002)
+    return workloads.drum(n_target=args.n_per_gpu * world, bed="disordered")
+
+
+def make_cpu_workload(args, n_target, seed):
+    """The same workload at a size the CPU oracle steps in seconds."""
+    from lethe_b200 import workloads
+
+    if args.workload == "drum":
+        return workloads.drum(n_target=n_target, seed=seed, bed="disordered")
+    xc, Lc, _ = workloads.load_periodic_cell()
+    reps = periodic_reps(n_target, len(xc))
+    if n_target < len(xc):
+        # a sub-box of the cell is not periodic: small samples (tests) use a small lattice box instead
+        side = max(4, round((n_target / 4.0) ** (1.0 / 3.0)))
+        return workloads.periodic_box(cells=(side, side, side), spacing=1.005, jitter=0.002, seed=seed)
+    return workloads.periodic_packing(xc * CELL_D, Lc * CELL_D, reps, d=CELL_D, vel_sigma=args.vel_sigma, seed=seed)
 
 
 _RESULT_FD = None
@@ -120,7 +157,6 @@ def emit_result(line):
 def run_reference(args):
     """CPU arm: the oracle on every host core, each core an independent sub-domain of the
     workload (what MPI ranks would own, minus the halo cost)."""
-    from lethe_b200 import workloads
     from oracle import loader
 
     loader.build()
@@ -128,7 +164,7 @@ def run_reference(args):
     per_core = args.cpu_particles
     ws = []
     for c in range(cores):
-        w = workloads.drum(n_target=per_core, seed=19 + c, spacing=1.005, jitter=0.002)
+        w = make_cpu_workload(args, per_core, 19 + c)
         e = loader.oracle_engine(w.params.to_config())
         w.install(e)
         ws.append((w, e))
@@ -139,8 +175,9 @@ def run_reference(args):
         [t.start() for t in ts]
         [t.join() for t in ts]
 
-    sub = args.cpu_substeps
+    sub = args.dem_steps
     run_all(args.cpu_settle)
+    r0 = sum(e.get_stats().n_rebuilds for _, e in ws)
     for _ in range(args.warmup):
         run_all(sub)
     t0 = time.perf_counter()
@@ -148,13 +185,14 @@ def run_reference(args):
         run_all(sub)
     dt = time.perf_counter() - t0
     value = n_total * sub * args.steps / dt
-    sample = f"{cores} independent drum slices x {per_core} spheres (one oracle thread each), {sub} DEM steps per bench step, after {args.cpu_settle} settling steps"
+    sample = (f"{cores} independent sub-domains x {ws[0][0].n} spheres of the same workload (one oracle thread each), {sub} DEM steps per "
+              f"bench step, after {args.cpu_settle} settling steps; {sum(e.get_stats().n_rebuilds for _, e in ws) - r0} list rebuilds in all")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D rotating drum slices, HM limit-overlap + constant rolling (CPU oracle = port of the reference algorithm; "
-                               "the deal.II/MPI reference cannot be built here)", "particles": n_total},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak" if args.workload != "periodic" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": ws[0][0].description + " (CPU oracle = port of the reference algorithm; the deal.II/MPI reference cannot "
+                               "be built here)", "particles": n_total, "dem_steps_per_step": sub},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -162,11 +200,10 @@ def run_reference(args):
 
 
 def cpu_baseline_sample(args):
-    from lethe_b200 import workloads
     from oracle import loader
 
     loader.build()
-    w = workloads.drum(n_target=args.cpu_particles, spacing=1.005, jitter=0.002)
+    w = make_cpu_workload(args, args.cpu_particles, 19)
     e = loader.oracle_engine(w.params.to_config())
     w.install(e)
     e.step(args.cpu_settle)
@@ -175,29 +212,33 @@ def cpu_baseline_sample(args):
     e.step(n_steps)
     dt = time.perf_counter() - t0
     return {"value": w.n * n_steps / dt, "unit": "particle-steps/s", "cores": 1, "kind": "port",
-            "sample": f"drum slice of {w.n} spheres (same material / models / dt), {n_steps} steps after {args.cpu_settle} settling steps, single thread, g++ -O2 no FMA"}
+            "sample": f"{w.n} spheres of the same workload (same material / models / dt), {n_steps} steps after {args.cpu_settle} settling steps, single thread, g++ -O2 no FMA"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="drum", choices=["drum", "periodic_box", "box_packing", "hopper", "cohesive_jkr", "cohesive_dmt"])
-    ap.add_argument("--n-per-gpu", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="periodic",
+                    choices=["periodic", "drum", "periodic_lattice", "box_packing", "hopper", "cohesive_jkr", "cohesive_dmt"])
+    ap.add_argument("--particles", type=int, default=64_000_000, help="periodic: total spheres of the FIXED box (strong scaling)")
+    ap.add_argument("--n-per-gpu", type=int, default=1_000_000, help="other workloads: spheres per GPU (weak scaling)")
+    ap.add_argument("--dem-steps", type=int, default=100, help="DEM time steps per bench step")
+    ap.add_argument("--vel-sigma", type=float, default=0.1)
     ap.add_argument("--settle", type=int, default=-1, help="untimed settling steps before warm-up (-1: per workload)")
-    ap.add_argument("--e2e-steps", type=int, default=30)
-    ap.add_argument("--cpu-particles", type=int, default=40_000)
+    ap.add_argument("--e2e-steps", type=int, default=-1, help="DEM steps of the e2e leg (-1: by size)")
+    ap.add_argument("--cpu-particles", type=int, default=64_000)
     ap.add_argument("--cpu-steps", type=int, default=300)
-    ap.add_argument("--cpu-settle", type=int, default=-1, help="settling steps of the CPU sample (-1: same as --settle)")
-    ap.add_argument("--cpu-substeps", type=int, default=100)
+    ap.add_argument("--cpu-settle", type=int, default=-1, help="settling steps of the CPU sample (-1: per workload)")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.settle < 0:
-        # enough for the bed to come to rest on its supports (loose lattices fall first)
-        args.settle = {"drum": 3000, "hopper": 20000, "box_packing": 20000, "periodic_box": 500}.get(args.workload, 3000)
+        # enough for the bed to come to rest on its supports (loose lattices fall first); the periodic
+        # packing only needs its kinetic energy to spread over the contacts
+        args.settle = {"drum": 3000, "hopper": 20000, "box_packing": 20000, "periodic": 200, "periodic_lattice": 500}.get(args.workload, 3000)
     if args.cpu_settle < 0:
         args.cpu_settle = args.settle
 
@@ -229,12 +270,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    t_setup = time.perf_counter()
     w = make_workload(args, rank, world)
     cfg_params = w.params
     if world > 1:
         from lethe_b200 import multi
 
-        # a workload generated per slab (periodic_box) is cut into equal-width slabs; otherwise the
+        # a workload generated per slab (periodic) is cut into equal-width slabs; otherwise the
         # cut planes balance the particle histogram
         engine, n_local = multi.create_slab_engine(w, rank, world, local_rank, dist, balanced=not hasattr(w, "n_global"))
     else:
@@ -242,6 +284,9 @@ def main():
         w.install(engine)
         n_local = w.n
     n_global = getattr(w, "n_global", w.n)
+    # the host copies of the initial state are not needed any more (6 GB at 64 M)
+    w.ids = w.x = w.props = None
+    S = max(1, args.dem_steps)
 
     def barrier():
         if world > 1:
@@ -256,10 +301,12 @@ def main():
     for _ in range(2):
         engine.force_contact_search()
         engine.step(1)
-    engine.step(max(3, args.warmup))
+    for _ in range(max(3, args.warmup)):
+        engine.step(S)
     barrier()
+    setup_s = time.perf_counter() - t_setup
 
-    # ---- timed region: K steps, device-resident ----
+    # ---- timed region: K bench steps of S DEM steps, device-resident, rebuilds included ----
     engine.enable_timers(True)
     engine.get_timers(reset=True)
     launches0 = engine.kernel_launches()
@@ -270,7 +317,8 @@ def main():
     # CUDA events on the stream the engine launches on (torch.cuda.Event would only see
     # torch's current stream)
     engine.event_record(0)
-    engine.step(args.steps)
+    for _ in range(args.steps):
+        engine.step(S)
     engine.event_record(1)
     elapsed = engine.event_elapsed_ms() * 1e-3
     barrier()
@@ -278,11 +326,16 @@ def main():
     timers = engine.get_timers(reset=True)  # CUDA events on the engine's stream
     launches = engine.kernel_launches() - launches0
     st1 = engine.get_stats()
+    migrated = float(st1.n_migrated - st0.n_migrated)
     if world > 1:
         tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed = float(tt.item())
-    value = n_global * args.steps / elapsed
+        mm = torch.tensor([migrated], device="cuda", dtype=torch.float64)
+        dist.all_reduce(mm, op=dist.ReduceOp.SUM)
+        migrated = float(mm.item()) / 2  # every migration is counted by the sender and by the receiver
+    n_dem = args.steps * S
+    value = n_global * n_dem / elapsed
 
     # ---- C-bar, T-bar for the roofline (one extra step with the touching counter on) ----
     engine.enable_timers(False, count_touching=True)
@@ -300,46 +353,55 @@ def main():
     k_launch = max(1, timers["step_kernel_launches"])
     k_ms = timers["step_kernel_ms"] / k_launch
     achieved = bytes_per_pstep * n_local / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    rebuilds = int(st1.n_rebuilds - st0.n_rebuilds)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
         "kernel": "k_step (fused pp+pw forces, history, velocity-Verlet)", "kernel_ms": k_ms, "peak_source": peak_src,
-        "algorithmic_bytes_per_particle_step": bytes_per_pstep, "C_half": c_half, "T_half": t_half,
+        "algorithmic_bytes_per_particle_step": bytes_per_pstep, "algorithmic_bytes_per_launch": bytes_per_pstep * n_local,
+        "C_half": c_half, "T_half": t_half,
         "kernel_share_of_step": timers["step_kernel_ms"] / (1e3 * elapsed),
         "rebuild_ms_total": timers["rebuild_ms"], "rebuilds": timers["rebuild_launches"],
+        "rebuild_ms_each": timers["rebuild_ms"] / max(1, timers["rebuild_launches"]),
+        "rebuild_share_of_step": timers["rebuild_ms"] / (1e3 * elapsed),
     }
     traffic_file = os.path.join(ROOT, "profiles", "k_step_traffic.json")
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as f:
-                tj = json.load(f)
-            roofline["traffic"] = tj.get("dram_bytes_per_launch")
-            roofline["traffic_source"] = tj.get("source")
+                tj = json.load(f).get(args.workload)
+            if tj:
+                # ncu's figure is per launch on ITS particle count: scaled to this run's rows per launch
+                roofline["traffic"] = tj["dram_bytes_per_particle_step"] * n_local
+                roofline["traffic_source"] = tj.get("source")
+                roofline["traffic_over_algorithmic"] = tj["dram_bytes_per_particle_step"] / bytes_per_pstep
         except Exception:
             pass
 
     # ---- e2e: per-step plugin call with pinned host rows ----
     # Every rank keeps host rows of the particles it owns — what a step changes: x, v, omega, 72 B
-    # per particle — and hands them to lethe_dem_step_host_state every step (rows up, one step, rows
-    # down). The row -> id table goes up with the first call and again whenever particles changed
+    # per particle — and hands them to lethe_dem_step_host_state every DEM step (rows up, one step,
+    # rows down). The row -> id table goes up with the first call and again whenever particles changed
     # owner in a rebuild (the rank then re-reads its owned rows, inside the timed region).
     def owned_rows():
         ids_, x_, props_ = engine.get_particles()
         state = np.ascontiguousarray(np.concatenate([x_, props_[:, 3:9]], axis=1))
+        del x_, props_
         return [torch.from_numpy(ids_.copy()).pin_memory(), torch.from_numpy(state).pin_memory(), True]
 
     id_uploads = [0]
 
-    def host_step(rows, n_steps, rebuilds_seen):
+    def host_step(rows, n_steps, migrated_seen):
         hid, hstate, fresh = rows
         engine.step_host_state_ptr(n_steps, len(hid), hid.data_ptr() if fresh else 0, hstate.data_ptr())
         id_uploads[0] += len(hid) if fresh else 0
         rows[2] = False
         if world > 1:
             r = engine.get_stats().n_migrated  # particles changed owner: re-read the owned rows
-            if r != rebuilds_seen:
+            if r != migrated_seen:
                 return owned_rows(), r
-        return rows, rebuilds_seen
+        return rows, migrated_seen
 
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else (30 if n_local <= 4_000_000 else 6)
     rows = owned_rows()
     seen = engine.get_stats().n_migrated
     for _ in range(3):
@@ -348,17 +410,15 @@ def main():
     t0 = time.perf_counter()
     n_moved = 0
     id_uploads[0] = 0
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         n_moved += len(rows[0])
         rows, seen = host_step(rows, 1, seen)
     barrier()
     dt = time.perf_counter() - t0
     n_id_rows = id_uploads[0]
-    sub = 100
     barrier()
     t0 = time.perf_counter()
-    for _ in range(3):
-        rows, seen = host_step(rows, sub, seen)
+    rows, seen = host_step(rows, S, seen)
     barrier()
     dtb = time.perf_counter() - t0
     if world > 1:
@@ -368,29 +428,35 @@ def main():
         nn = torch.tensor([float(n_moved), float(n_id_rows)], device="cuda", dtype=torch.float64)
         dist.all_reduce(nn, op=dist.ReduceOp.SUM)
         n_moved, n_id_rows = int(nn[0].item()), int(nn[1].item())
-    per_step = n_moved / max(1, args.e2e_steps)
+    per_step = n_moved / max(1, e2e_steps)
+    h2d = int(per_step * 72 + 4 * n_id_rows / max(1, e2e_steps))
     e2e = {
         "value": n_moved / dt, "unit": "particle-steps/s",
-        "h2d_bytes_per_step": int(per_step * 72 + 4 * n_id_rows / max(1, args.e2e_steps)), "d2h_bytes_per_step": int(per_step * 72),
+        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(per_step * 72), "dem_steps": e2e_steps,
+        "pcie_gbs_per_direction_if_copy_bound": (h2d + per_step * 72) / world / (dt / max(1, e2e_steps)) / 1e9,
         "call": "lethe_dem_step_host_state(n_steps=1) on every rank: upload the x/v/omega rows of the owned particles (72 B each; "
-                "the id table only when ownership changed), 1 DEM step, download the rows, every step",
-        "batched": {"steps_per_call": sub, "value": n_global * sub * 3 / dtb, "unit": "particle-steps/s"},
+                "the id table only when ownership changed), 1 DEM step, download the rows, every DEM step",
+        "batched": {"steps_per_call": S, "value": n_global * S / dtb, "unit": "particle-steps/s"},
     }
+    del rows
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(args)
 
     if rank == 0:
+        strong = args.workload == "periodic"
         line = {
             "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": w.description, "particles": int(n_global), "particles_per_gpu": int(n_global // world),
                 "parallelism": f"slab{world}" if world > 1 else "single",
+                "dem_steps_per_step": S, "ms_per_dem_step": 1e3 * elapsed / n_dem,
                 "settle_steps": args.settle, "l2": "inputs larger than L2 (state+lists >> 126 MB)",
-                "rebuilds_in_timed_region": int(st1.n_rebuilds - st0.n_rebuilds),
+                "rebuilds_in_timed_region": rebuilds, "dem_steps_per_rebuild": n_dem / max(1, rebuilds),
+                "particles_migrated_in_timed_region": int(migrated), "setup_s": setup_s,
             },
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
         }

@@ -434,7 +434,8 @@ namespace
     const size_t n_buckets = size_t(n_cells) + 3;
     exclusive_scan_u32(c->cell_count.p, c->cell_start.p, n_buckets + 1, c->scan_tmp.p, s);
     launch_scatter_perm(c->key.p, c->slot.p, c->cell_start.p, c->perm.p, n, s);
-    launch_sort_cells(c->cell_start.p, uint32_t(n_buckets), c->perm.p, src.id.p, s);
+    // real cells only: the order inside the bucket of dropped particles (rank n_cells) is never used
+    launch_sort_cells(c->cell_start.p, uint32_t(n_cells), c->perm.p, src.id.p, s);
     const uint32_t n_new = read_u32(c, c->cell_start.p + n_cells); // particles still inside the domain
 
     dst.ensure(std::max<size_t>(n_new, 1), 0, s);
@@ -663,6 +664,8 @@ namespace
         sp.flag_check = P.flag_check;
         sp.flag_tag = P.flag_tag;
         sp.spec_check = P.spec_check;
+        sp.flag_local = P.flag_local;
+        sp.flag_host = P.flag_host;
         launch_solid_contacts(sp, c->mt, s);
         P.solid_force = c->solid_force.p;
         P.solid_torque = c->solid_torque.p;
@@ -864,6 +867,14 @@ namespace
     const size_t total = base + n;
     if (total >= 0x7fffffffull)
       throw std::runtime_error("too many particles for 31-bit indices");
+    for (uint64_t k = 0; k < n; ++k)
+      {
+        const double *p = props9 + 9 * k;
+        if (!(p[0] >= 0.0) || !(p[0] < double(c->cfg.n_types)) || p[0] != std::floor(p[0]))
+          throw std::runtime_error("particle type outside [0, number of particle types)");
+        if (!(p[1] > 0.0) || !(p[2] > 0.0))
+          throw std::runtime_error("particle diameter and mass must be positive");
+      }
     c->st[c->cur].ensure(total, base, s);
     c->st[c->cur ^ 1].ensure(total, 0, s);
     c->disp.ensure(total, base, s);
@@ -885,6 +896,9 @@ namespace
         launch_fill_u32(c->slot_of_id.p + old, 0xffffffffu, size_t(max_id) + 1 - old, s);
         c->slot_map_size = uint32_t(size_t(max_id) + 1);
       }
+    // the new rows are addressable by id at once (lethe_dem_step_host* resolve their rows through
+    // this map before the next rebuild renumbers the slots)
+    launch_register_ids(c->st[c->cur].id.p, uint32_t(base), uint32_t(n), c->slot_of_id.p, c->slot_map_size, s);
     CU_TRY(cudaStreamSynchronize(s));
     c->n_owned = uint32_t(total);
     c->n_ghost = 0;
@@ -964,6 +978,15 @@ int lethe_dem_create(const lethe_dem_config *config, int device, lethe_dem_ctx *
       return bad("a periodic direction needs at least 3 grid cells");
   if (double(config->grid_n[0]) * config->grid_n[1] * config->grid_n[2] > 2.0e9)
     return bad("grid too large");
+  // report_cell_size_to_particle_diameter_ratio (include/dem/utilities.h:33-60, called from
+  // dem.cc:1093-1096): the reference refuses a mesh whose smallest cell edge is below the largest
+  // particle diameter. Its candidate set is "particles of vertex-sharing cells" whatever the
+  // neighbourhood threshold, and the 27-cell stencil here reproduces exactly that set, so the
+  // reference's own bound is the one enforced (a single layer of cells has no neighbour layer).
+  for (int d = 0; d < 3; ++d)
+    if (config->grid_n[d] > 1 && config->d_max > 0 && config->cell_size[d] < config->d_max * (1.0 - 1e-12))
+      return bad("Minimum cell size is smaller than the maximum particle diameter. Consider coarsening the mesh to achieve a "
+                 "ratio larger than 1");
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev == 0)
@@ -1202,6 +1225,9 @@ int lethe_dem_set_boundary_motion(lethe_dem_ctx *c, uint32_t boundary_id, const 
         c->motions_host.push_back(m);
       }
     c->walls_dirty = true;
+    // the motion table is uploaded with the wall table at a rebuild: ask for one so that the
+    // change applies from the next step on (as set_walls / set_floating_walls do)
+    c->contact_search_trigger = true;
   });
 }
 

@@ -628,8 +628,12 @@ namespace dem
     uint32_t hc[4] = {0, 0, 0, 0};
     CU_TRY(cudaMemcpyAsync(hc, m->counters.p, 16, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
-    if (hc[0] > cap || hc[1] > cap)
-      throw std::runtime_error("migration buffer overflow: more than 1/8 of the slab left in one rebuild");
+    // every rank learns about an overflow on any rank BEFORE the exchanges start, so that all of
+    // them fail together instead of one throwing and the others waiting in NCCL for ever
+    if (c->multi.agree(c, hc[0] > cap || hc[1] > cap))
+      throw std::runtime_error(hc[0] > cap || hc[1] > cap
+                                 ? "migration buffer overflow: more than 1/8 of the slab left in one rebuild"
+                                 : "migration buffer overflow on another rank");
     if (hc[2])
       fprintf(stderr, "[lethe_dem] rank %d: %u particles jumped over a whole slab and were dropped\n", m->rank, hc[2]);
     uint32_t n_send[2] = {m->peer[0] >= 0 ? hc[0] : 0, m->peer[1] >= 0 ? hc[1] : 0};

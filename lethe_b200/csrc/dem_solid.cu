@@ -381,7 +381,13 @@ namespace dem
                           ++n_rec;
                         }
                       else
-                        *P.overflow = 1u;
+                        {
+                          *P.overflow = 1u;
+                          if (P.flag_local)
+                            *reinterpret_cast<volatile uint32_t *>(P.flag_local) = P.flag_tag;
+                          if (P.flag_host)
+                            *reinterpret_cast<volatile uint32_t *>(P.flag_host) = P.flag_tag;
+                        }
                     }
                 }
               // clear_contact_info: dropping the flag is the clear

@@ -103,6 +103,9 @@ namespace dem
     const uint32_t *flag_check;
     uint32_t flag_tag;
     int spec_check;
+    // an overflow also raises the contact-search trigger of this step (StepParams::flag_*), so that
+    // the host reaches the rebuild — where the overflow is turned into an error — at the next step
+    uint32_t *flag_local, *flag_host;
   };
   void launch_solid_contacts(const SolidContactParams &p, const MaterialTables &mt, cudaStream_t s);
 

@@ -373,6 +373,11 @@ namespace dem
                         touching = false;
                       else
                         touching = (0.5 * dsum - sqrt(d2)) > mt.pp_force_threshold;
+#ifdef DEM_EXPERIMENT_HALF
+                      // timing experiment only (wrong physics): the cost of evaluating each pair once
+                      if ((c[u] & COL_INDEX_MASK) < warp_base + ow[u])
+                        touching = false;
+#endif
                       // contact_info.tangential_displacement.clear() (…force.h:2057-2063): dropping
                       // the flag is the clear; the 24 B are not touched.
                       if (!touching && (c[u] & COL_HIST_BIT))

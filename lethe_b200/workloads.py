@@ -13,6 +13,7 @@ CPU oracle.  Host set-up only (the reference does this in insertion / mesh code)
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -152,15 +153,48 @@ def sheet_mesh(x0, x1, y0, y1, z_of_xy, n):
     return vertices, np.asarray(tris, dtype=np.uint32)
 
 
-def drum(n_target=1_000_000, d=0.003, radius=0.12, fill=0.45, seed=19, spacing=1.0, jitter=0.02):
+CELL_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "periodic_cell_64000.npz")
+
+
+def load_periodic_cell(path=CELL_FILE):
+    """The committed disordered 3-periodic unit cell (tools/make_periodic_cell.py): positions in
+    units of the sphere diameter and the cell edge L/d, solid fraction 0.64."""
+    z = np.load(path)
+    return np.ascontiguousarray(z["x_over_d"]), np.asarray(z["L_over_d"], dtype=np.float64), float(z["phi"])
+
+
+def disordered_points(lo, hi, d, phi=0.60, cell=None):
+    """Sphere centres of a disordered packing of solid fraction `phi` filling the box [lo, hi):
+    the periodic unit cell, dilated from its own solid fraction to `phi` (which opens a gap between
+    neighbours), repeated periodically and cut to the box."""
+    xc, Lc, phi_c = cell if cell is not None else load_periodic_cell()
+    scale = d * (phi_c / phi) ** (1.0 / 3.0)
+    L = Lc * scale
+    t0 = [int(math.floor(lo[k] / L[k])) for k in range(3)]
+    t1 = [int(math.ceil(hi[k] / L[k])) for k in range(3)]
+    out = []
+    for i in range(t0[0], t1[0]):
+        for j in range(t0[1], t1[1]):
+            for k in range(t0[2], t1[2]):
+                pts = xc * scale + np.array([i * L[0], j * L[1], k * L[2]])
+                keep = np.all((pts >= np.asarray(lo)) & (pts < np.asarray(hi)), axis=1)
+                out.append(pts[keep])
+    return np.concatenate(out) if out else np.zeros((0, 3))
+
+
+def drum(n_target=1_000_000, d=0.003, radius=0.12, fill=0.45, seed=19, spacing=1.0, jitter=0.02, bed="lattice"):
     """Config 2 (examples/dem/3d-rotating-drum/rotating-drum.prm scaled to n_target):
     rho 2500, Y 1e7, nu 0.2, e 0.97, mu 0.85, rolling = constant mu_r 0.05, dt 1e-5,
-    omega_wall = 1.2147 rad/s about x; a jittered FCC bed fills the lower part of the drum."""
+    omega_wall = 1.2147 rad/s about x. bed="disordered": the lower part of the drum is filled
+    with a random packing (the periodic unit cell dilated to solid fraction 0.60 and cut to the
+    bed; it settles onto the wall in the first steps); bed="lattice": a jittered FCC bed."""
     rng = np.random.default_rng(seed)
     a = d * spacing
     # bed: points of the lattice inside the circle (with clearance) and below the fill level
     area = fill * math.pi * radius**2
     per_volume = math.sqrt(2.0) / a**3
+    if bed == "disordered":
+        per_volume = 0.60 * 6.0 / (math.pi * d**3)
     length = n_target / (per_volume * area) * 1.02
     h = 1.5 * d
     ny = nz = int(math.ceil(2 * radius / h)) + 2
@@ -172,12 +206,16 @@ def drum(n_target=1_000_000, d=0.003, radius=0.12, fill=0.45, seed=19, spacing=1
     zs = np.linspace(-radius, radius, 4001)
     seg = np.array([radius**2 * math.acos(-z / radius) + z * math.sqrt(max(radius**2 - z * z, 0.0)) for z in zs])
     z_top = float(zs[np.searchsorted(seg, area)])
-    pts = fcc_points((0.5 * d, -radius, -radius), (length - 0.5 * d, radius, z_top), a)
+    if bed == "disordered":
+        pts = disordered_points((0.5 * d, -radius, -radius), (length - 0.5 * d, radius, z_top), d)
+    else:
+        pts = fcc_points((0.5 * d, -radius, -radius), (length - 0.5 * d, radius, z_top), a)
     r = np.hypot(pts[:, 1], pts[:, 2])
     pts = pts[(r < radius - 0.55 * d) & (pts[:, 2] < z_top) & (pts[:, 0] > 0.55 * d) & (pts[:, 0] < length - 0.55 * d)]
     if len(pts) > n_target:
         pts = pts[np.argsort(pts[:, 0], kind="stable")[:n_target]]
-    pts = pts + rng.uniform(-jitter, jitter, pts.shape) * d
+    if bed != "disordered":
+        pts = pts + rng.uniform(-jitter, jitter, pts.shape) * d
     n = len(pts)
     p = DEMParameters()
     p.time_step = 1e-5
@@ -195,7 +233,8 @@ def drum(n_target=1_000_000, d=0.003, radius=0.12, fill=0.45, seed=19, spacing=1
     motions = [(4, (0.0, 0.0, 0.0), 1.2147, (1.0, 0.0, 0.0), (0.0, 0.0, 0.0))]
     ids = rng.permutation(n).astype(np.uint32)
     props = make_props(n, d, 2500, rng)
-    desc = f"3D rotating drum, {n} spheres d={d * 1e3:g} mm, R={radius} L={length:.3f} m, HM limit-overlap + constant rolling, faceted cylinder wall"
+    desc = (f"3D rotating drum, {n} spheres d={d * 1e3:g} mm, R={radius} L={length:.3f} m, HM limit-overlap + constant rolling, "
+            f"faceted cylinder wall, {'disordered (random-packing) bed' if bed == 'disordered' else 'jittered FCC bed'}")
     return Workload("drum", p, ids, pts, props, faces, motions, desc)
 
 
@@ -286,6 +325,119 @@ def periodic_box(n_cells_side=32, d=0.005, seed=19, spacing=1.0, jitter=0.03, ve
     if n:
         props[:, 3:6] = np.concatenate(vs)
     w = Workload("periodic_box", p, ids, pts, props, [], (), f"3-periodic box, {n_global} spheres, HM limit-overlap, Maxwellian v")
+    w.n_global = n_global
+    return w
+
+
+def _periodic_params(L, d, young=1e6, restitution=1.0, friction=0.3, density=1000.0, dt=1e-5, search_factor=0.9):
+    """3-periodic cube of side L (mesh cells just above the neighbourhood radius 1.3 d), g = 0, HM limit-overlap."""
+    ng = tuple(max(3, int(math.floor(L[k] / (1.3 * d * (1.0 + 1e-9))))) for k in range(3))
+    p = DEMParameters()
+    p.time_step = dt
+    p.pp_model, p.pw_model, p.rolling_model = "hertz_mindlin_limit_overlap", "nonlinear", "none"
+    p.g = (0.0, 0.0, 0.0)
+    p.dynamic_contact_search_factor = search_factor
+    p.neighborhood_threshold = 1.3
+    p.particle_types = [ParticleType(diameter=d, density=density, young=young, poisson=0.3, restitution=restitution, friction=friction)]
+    p.mesh = Mesh((0.0, 0.0, 0.0), tuple(L), ng, True, "lexicographic")
+    p.boundary_conditions = [BoundaryCondition(type="periodic", periodic_id_0=2 * ax, periodic_id_1=2 * ax + 1, periodic_direction=ax) for ax in range(3)]
+    return p
+
+
+def grow_periodic_cell(make_engine, n_side=100, d=0.002, phi=0.64, seed=19, d0_frac=0.5, eps=0.004, steps_per_stage=40,
+                       relax_steps=1500, vel_sigma=0.05, log=None):
+    """A DISORDERED 3-periodic packing of n_side^3 monodisperse spheres at solid fraction `phi`.
+
+    There is no gravity to settle a periodic box with, so the packing is made the way random
+    packings are made in the literature (Lubachevsky-Stillinger style growth): the spheres start
+    as a dilute gas (diameter d0_frac*d on a simple-cubic lattice with +-0.2 d random offsets and
+    thermal velocities) and are grown geometrically, `eps` per stage, while the engine itself
+    integrates their collisions with a dissipative, frictionless material (restitution 0.5, mu 0);
+    `relax_steps` steps at the final size let the last overlaps relax. Only the public per-step
+    plugin call is used (lethe_dem_step_host: rows with the new diameter up, steps, rows down).
+    make_engine(config) -> engine (abi.load_engine on a GPU; the oracle in CPU tests of small cells).
+    Returns (x[n,3] wrapped into the cell, L[3])."""
+    rng = np.random.default_rng(seed)
+    a = d * (math.pi / (6.0 * phi)) ** (1.0 / 3.0)
+    L = [n_side * a] * 3
+    p = _periodic_params(L, d, restitution=0.5, friction=0.0)
+    eng = make_engine(p.to_config())
+    i, j, k = np.meshgrid(np.arange(n_side), np.arange(n_side), np.arange(n_side), indexing="ij")
+    x = (np.stack([i.ravel(), j.ravel(), k.ravel()], axis=1) + 0.5) * a
+    x = x + rng.uniform(-0.2, 0.2, x.shape) * d
+    n = len(x)
+    dc = d0_frac * d
+    props = make_props(n, d, 1000, rng, vel_sigma=vel_sigma)  # the mass of the final sphere throughout
+    props[:, 1] = dc
+    ids = np.arange(n, dtype=np.uint32)
+    x = np.ascontiguousarray(x)
+    eng.set_particles(ids, x, props)
+    stage = 0
+    while dc < d:
+        dc = min(d, dc * (1.0 + eps))
+        props[:, 1] = dc
+        eng.step_host(steps_per_stage, ids, x, props)
+        stage += 1
+        if log and stage % 20 == 0:
+            st = eng.get_stats()
+            log(f"grow stage {stage}: d/d_final {dc / d:.4f} pairs/particle {st.n_pair_entries / n:.2f} v_max {st.v_max:.3g} rebuilds {st.n_rebuilds}")
+    if relax_steps:
+        eng.step_host(relax_steps, ids, x, props)
+    if log:
+        st = eng.get_stats()
+        log(f"grown: {n} spheres phi {phi} pairs/particle {st.n_pair_entries / n:.2f} v_max {st.v_max:.3g} rebuilds {st.n_rebuilds}")
+    eng.close()
+    Lc = np.asarray(L)
+    return np.mod(x, Lc), L
+
+
+def periodic_packing(cell_x, L_cell, reps=(1, 1, 1), d=0.002, seed=19, vel_sigma=0.1, slab=None, restitution=1.0, friction=0.3):
+    """Config 5: the disordered cell of grow_periodic_cell tiled reps[0] x reps[1] x reps[2] times
+    (a periodic tiling of a periodic packing is a packing of the larger box), every sphere with
+    its own Maxwellian velocity (sigma `vel_sigma` m/s per component, seeded per tile) so that the
+    copies diverge at once. Material after multiperiodic_collisions_3d.prm (Y 1e6, nu 0.3, elastic,
+    g = 0) with friction 0.3 so that the tangential history is live. `slab=(rank, world)` keeps the
+    particles of one rank's equal-width slab along x (the ownership rule of multi.owner_mask)."""
+    nc = len(cell_x)
+    L = [L_cell[k] * reps[k] for k in range(3)]
+    p = _periodic_params(L, d, restitution=restitution, friction=friction)
+    mesh = p.mesh
+    lo = hi = None
+    if slab is not None:
+        from .multi import slab_bounds
+
+        lo, hi = slab_bounds(mesh.n[0], slab[1])[slab[0]]
+    xs, vs, idl = [], [], []
+    for ti in range(reps[0]):
+        if slab is not None:
+            # tiles that cannot reach the slab are skipped without being generated
+            hx = mesh.cell_size[0]
+            if (ti + 1) * L_cell[0] < lo * hx - 1e-9 or ti * L_cell[0] > hi * hx + 1e-9:
+                continue
+        for tj in range(reps[1]):
+            for tk in range(reps[2]):
+                tile = (ti * reps[1] + tj) * reps[2] + tk
+                rng = np.random.default_rng([seed, tile])
+                pts = cell_x + np.array([ti * L_cell[0], tj * L_cell[1], tk * L_cell[2]])
+                vel = rng.normal(0.0, vel_sigma, pts.shape)
+                gid = np.arange(nc, dtype=np.int64) + tile * nc
+                if slab is not None:
+                    cx = np.floor((pts[:, 0] - mesh.lo[0]) / mesh.cell_size[0]).astype(np.int64)
+                    keep = (cx >= lo) & (cx < hi)
+                    pts, vel, gid = pts[keep], vel[keep], gid[keep]
+                xs.append(pts)
+                vs.append(vel)
+                idl.append(gid)
+    pts = np.ascontiguousarray(np.concatenate(xs)) if xs else np.zeros((0, 3))
+    n = len(pts)
+    n_global = nc * reps[0] * reps[1] * reps[2]
+    props = make_props(n, d, 1000, np.random.default_rng(seed))
+    if n:
+        props[:, 3:6] = np.concatenate(vs)
+    ids = np.concatenate(idl).astype(np.uint32) if idl else np.zeros(0, np.uint32)
+    desc = (f"3-periodic box, {n_global} spheres d={d * 1e3:g} mm, disordered packing (grown cell of {nc} tiled "
+            f"{reps[0]}x{reps[1]}x{reps[2]}), HM limit-overlap, Maxwellian v sigma={vel_sigma:g} m/s, g=0")
+    w = Workload("periodic_packing", p, ids, pts, props, [], (), desc)
     w.n_global = n_global
     return w
 
