@@ -15,6 +15,7 @@
 #include <cstdint>
 
 #include "../../include/lethe_dem.h"
+#include "dem_math.cuh"
 
 namespace dem
 {
@@ -139,7 +140,7 @@ namespace dem
     const double P = -sqr(c2) / 12. - c0;
     const double Q = -cub(c2) / 108. + c0 * c2 / 3. - sqr(c1) * 0.125;
     double root1 = clamp_root1 ? fmax(0., (0.25 * sqr(Q)) + (cub(P) / 27.)) : 0.25 * sqr(Q) + cub(P) / 27.;
-    const double U = cbrt(-0.5 * Q + sqrt(root1));
+    const double U = glibc_cbrt(-0.5 * Q + sqrt(root1)); // std::cbrt of the reference's host (dem_math.cuh)
     const double s = -c2 * (5. / 6.) + U - P / (3. * U);
     const double w = sqrt(fmax(1e-16, c2 + 2. * s));
     const double lambda = 0.5 * c1 / w;
@@ -224,7 +225,7 @@ namespace dem
     else if constexpr (MODEL == LETHE_PP_LINEAR)
       {
         const double kn =
-          1.0667 * sqrt(effective_radius) * Y * pow((0.9375 * effective_mass * 1.0 * 1.0 / (sqrt(effective_radius) * Y)), 0.2);
+          1.0667 * sqrt(effective_radius) * Y * pow_0_2_cr((0.9375 * effective_mass * 1.0 * 1.0 / (sqrt(effective_radius) * Y)));
         const double kt = kn * 0.4;
         const double etan = -2 * beta * sqrt(effective_mass * kn);
         const double etat = etan * 0.6324555320336759;
@@ -434,7 +435,7 @@ namespace dem
       {
         const double R = p.d * 0.5;
         const double rp_sqrt = sqrt(R);
-        const double kn = 1.0667 * rp_sqrt * Y * pow((0.9375 * p.m * 1.0 * 1.0 / (rp_sqrt * Y)), 0.2);
+        const double kn = 1.0667 * rp_sqrt * Y * pow_0_2_cr((0.9375 * p.m * 1.0 * 1.0 / (rp_sqrt * Y)));
         const double etan = 2 * beta * sqrt(p.m * kn);
         const double kt = -kn * 0.4;
         const double etat = etan * 0.6324555320336759;

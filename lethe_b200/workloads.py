@@ -391,12 +391,13 @@ def grow_periodic_cell(make_engine, n_side=100, d=0.002, phi=0.64, seed=19, d0_f
     return np.mod(x, Lc), L
 
 
-def periodic_packing(cell_x, L_cell, reps=(1, 1, 1), d=0.002, seed=19, vel_sigma=0.1, slab=None, restitution=1.0, friction=0.3):
+def periodic_packing(cell_x, L_cell, reps=(1, 1, 1), d=0.002, seed=19, vel_sigma=0.1, slab=None, restitution=1.0, friction=0.0):
     """Config 5: the disordered cell of grow_periodic_cell tiled reps[0] x reps[1] x reps[2] times
     (a periodic tiling of a periodic packing is a packing of the larger box), every sphere with
     its own Maxwellian velocity (sigma `vel_sigma` m/s per component, seeded per tile) so that the
-    copies diverge at once. Material after multiperiodic_collisions_3d.prm (Y 1e6, nu 0.3, elastic,
-    g = 0) with friction 0.3 so that the tangential history is live. `slab=(rank, world)` keeps the
+    copies diverge at once. Material of multiperiodic_collisions_3d.prm (Y 1e6, nu 0.3, restitution
+    1, friction 0, g = 0): the thermal motion does not decay, so the list-rebuild rate is steady
+    (with friction the bed is cold, and rebuild-free, after a few hundred steps). `slab=(rank, world)` keeps the
     particles of one rank's equal-width slab along x (the ownership rule of multi.owner_mask)."""
     nc = len(cell_x)
     L = [L_cell[k] * reps[k] for k in range(3)]
