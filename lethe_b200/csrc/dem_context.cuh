@@ -165,6 +165,8 @@ struct lethe_dem_ctx
   DevBuf<int32_t> cell_rank, cell_of_rank;
   DevBuf<uint32_t> cell_count, cell_start;
   DevBuf<uint32_t> key, slot, perm, old_of_new, counts, scan_tmp;
+  DevBuf<uint32_t> nb_cand;    // candidate cache of the neighbour counting pass (NB_CACHE x n_owned)
+  DevBuf<uint8_t> nb_cand_img; //   image codes beside it (periodic grids)
 
   // walls
   std::vector<lethe_wall_face> faces_host; // sorted by cell

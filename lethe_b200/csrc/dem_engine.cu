@@ -501,6 +501,11 @@ namespace
     np.use_img = use_img;
     HistPayload pay{c->n_pay ? c->pay.p : nullptr, c->pay_start.p, c->n_pay, c->slot_map_size, stn.id.p};
     np.pay = pay;
+    c->nb_cand.ensure(std::max<size_t>(size_t(NB_CACHE) * n_new, 1));
+    if (use_img)
+      c->nb_cand_img.ensure(std::max<size_t>(size_t(NB_CACHE) * n_new, 1));
+    np.cand = c->nb_cand.p;
+    np.cand_img = use_img ? c->nb_cand_img.p : nullptr;
     launch_count_neighbors(np, s);
     exclusive_scan_u32(c->counts.p, newl.row_start.p, size_t(n_new) + 1, c->scan_tmp.p, s);
     const uint32_t n_entries = n_new ? read_u32(c, newl.row_start.p + n_new) : 0;

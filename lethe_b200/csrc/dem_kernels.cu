@@ -222,6 +222,10 @@ namespace dem
     };
 
     // Visits every (neighbour r, image code) of particle q that belongs in the contact list.
+    // The 27 stencil cells are resolved first, in three batches of independent loads (curve rank,
+    // [start, end) of the owned run and of the ghost runs), so that the per-cell chain of dependent
+    // loads rank -> start -> position is paid once instead of 27 times; the walk itself keeps the
+    // stencil order (z, y, x ascending), which is the order of the list row.
     template <class F> __device__ __forceinline__ void for_each_neighbor(const NeighborParams &P, uint32_t q, F &&f)
     {
       const GridDesc &g = P.grid;
@@ -230,103 +234,124 @@ namespace dem
       const int lin = P.cell_reg[q];
       const int ci = lin % g.n[0], cj = (lin / g.n[0]) % g.n[1], ck = lin / (g.n[0] * g.n[1]);
       const uint32_t old_q = P.old_of_new ? P.old_of_new[q] : 0xffffffffu;
-      for (int dz = -1; dz <= 1; ++dz)
+      // s = image shift (in units of L) that brings the neighbour cell next to mine:
+      // my cell on the low face, neighbour wrapped to the high face -> s = -1.
+      int n1[3][3]; // wrapped cell coordinate per axis and offset, -1: outside a non-periodic face
+      int sh[3][3]; // image shift per axis and offset
+      const int cc[3] = {ci, cj, ck};
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int o = 0; o < 3; ++o)
+          {
+            int v = cc[a] + o - 1, sft = 0;
+            if (v < 0 || v >= g.n[a])
+              {
+                if (!g.periodic[a])
+                  v = -1;
+                else
+                  {
+                    sft = v < 0 ? -1 : 1;
+                    v -= sft * g.n[a];
+                  }
+              }
+            n1[a][o] = v;
+            sh[a][o] = sft;
+          }
+      uint32_t rank[27];
+#pragma unroll
+      for (int k = 0; k < 27; ++k)
         {
-          // s = image shift (in units of L) that brings the neighbour cell next to mine:
-          // my cell on the low face, neighbour wrapped to the high face -> s = -1.
-          int nk = ck + dz, sz = 0;
-          if (nk < 0 || nk >= g.n[2])
+          const int ni = n1[0][k % 3], nj = n1[1][(k / 3) % 3], nk = n1[2][k / 9];
+          rank[k] = (ni < 0 || nj < 0 || nk < 0) ? 0xffffffffu : uint32_t(P.cell_rank[ni + g.n[0] * (nj + g.n[1] * nk)]);
+        }
+      uint32_t cs[27], ce[27];
+#pragma unroll
+      for (int k = 0; k < 27; ++k)
+        {
+          cs[k] = rank[k] != 0xffffffffu ? P.cell_start[rank[k]] : 0u;
+          ce[k] = rank[k] != 0xffffffffu ? P.cell_start[rank[k] + 1] : 0u;
+        }
+      const bool ghosts = P.ghost_start[0] || P.ghost_start[1];
+#pragma unroll
+      for (int k = 0; k < 27; ++k)
+        {
+          if (rank[k] == 0xffffffffu)
+            continue;
+          const int sx = sh[0][k % 3], sy = sh[1][(k / 3) % 3], sz = sh[2][k / 9];
+          const uint32_t img = (sx | sy | sz) ? uint32_t(1 + (sx + 1) + 3 * (sy + 1) + 9 * (sz + 1)) : 0u;
+          // owned particles of the cell, then the ghost copies of either neighbour rank
+          for (int range = 0; range < (ghosts ? 3 : 1); ++range)
             {
-              if (!g.periodic[2])
-                continue;
-              sz = nk < 0 ? -1 : 1;
-              nk -= sz * g.n[2];
-            }
-          for (int dy = -1; dy <= 1; ++dy)
-            {
-              int nj = cj + dy, sy = 0;
-              if (nj < 0 || nj >= g.n[1])
+              uint32_t s, e;
+              if (range == 0)
                 {
-                  if (!g.periodic[1])
-                    continue;
-                  sy = nj < 0 ? -1 : 1;
-                  nj -= sy * g.n[1];
+                  s = cs[k];
+                  e = ce[k];
                 }
-              for (int dx = -1; dx <= 1; ++dx)
+              else
                 {
-                  int ni = ci + dx, sx = 0;
-                  if (ni < 0 || ni >= g.n[0])
+                  if (!P.ghost_start[range - 1])
+                    continue;
+                  s = P.ghost_start[range - 1][rank[k]];
+                  e = P.ghost_end[range - 1][rank[k]];
+                }
+              for (uint32_t r = s; r < e; ++r)
+                {
+                  if (r == q)
+                    continue;
+                  const double4 pr = P.st.pos[r];
+                  const vec3 xr = v3(pr.x, pr.y, pr.z);
+                  double d2;
+                  if (img)
                     {
-                      if (!g.periodic[0])
-                        continue;
-                      sx = ni < 0 ? -1 : 1;
-                      ni -= sx * g.n[0];
-                    }
-                  const uint32_t img = (sx | sy | sz) ? uint32_t(1 + (sx + 1) + 3 * (sy + 1) + 9 * (sz + 1)) : 0u;
-                  const int nlin = ni + g.n[0] * (nj + g.n[1] * nk);
-                  const uint32_t rank = uint32_t(P.cell_rank[nlin]);
-                  // owned particles of the cell, then the ghost copies of either neighbour rank
-                  for (int range = 0; range < 3; ++range)
-                    {
-                      uint32_t s, e;
-                      if (range == 0)
-                        {
-                          s = P.cell_start[rank];
-                          e = P.cell_start[rank + 1];
-                        }
+                      const vec3 shift = v3(sx * g.L[0], sy * g.L[1], sz * g.L[2]);
+                      const int first = sx != 0 ? sx : (sy != 0 ? sy : sz);
+                      // canonical orientation (see decode_image in dem_step.cu)
+                      if (first < 0)
+                        d2 = dist2(xq, xr + shift);
                       else
-                        {
-                          if (!P.ghost_start[range - 1])
-                            continue;
-                          s = P.ghost_start[range - 1][rank];
-                          e = P.ghost_end[range - 1][rank];
-                        }
-                  for (uint32_t r = s; r < e; ++r)
-                        {
-                          if (r == q)
-                            continue;
-                          const double4 pr = P.st.pos[r];
-                          const vec3 xr = v3(pr.x, pr.y, pr.z);
-                          double d2;
-                          if (img)
-                            {
-                              const vec3 shift = v3(sx * g.L[0], sy * g.L[1], sz * g.L[2]);
-                              const int first = sx != 0 ? sx : (sy != 0 ? sy : sz);
-                              // canonical orientation (see decode_image in dem_step.cu)
-                              if (first < 0)
-                                d2 = dist2(xq, xr + shift);
-                              else
-                                d2 = dist2(xr, xq + (-shift));
-                            }
-                          else
-                            d2 = dist2(xq, xr);
-                          bool in = d2 < P.thr2;
-                          if (!in && d2 == P.thr2 && old_q != 0xffffffffu && old_q < P.n_old_rows)
-                            {
-                              // pairs sitting exactly on the threshold are neither inserted (<) nor
-                              // erased (>): they survive iff they were already listed.
-                              const uint32_t old_r = P.old_of_new[r];
-                              for (uint32_t eo = P.old_list.row_start[old_q]; eo < P.old_list.row_start[old_q + 1]; ++eo)
-                                if ((P.old_list.col[eo] & COL_INDEX_MASK) == old_r &&
-                                    ((P.use_img ? P.old_list.img[eo] != 0 : false) == (img != 0)))
-                                  in = true;
-                            }
-                          if (in)
-                            f(r, img);
-                        }
+                        d2 = dist2(xr, xq + (-shift));
                     }
+                  else
+                    d2 = dist2(xq, xr);
+                  bool in = d2 < P.thr2;
+                  if (!in && d2 == P.thr2 && old_q != 0xffffffffu && old_q < P.n_old_rows)
+                    {
+                      // pairs sitting exactly on the threshold are neither inserted (<) nor
+                      // erased (>): they survive iff they were already listed.
+                      const uint32_t old_r = P.old_of_new[r];
+                      for (uint32_t eo = P.old_list.row_start[old_q]; eo < P.old_list.row_start[old_q + 1]; ++eo)
+                        if ((P.old_list.col[eo] & COL_INDEX_MASK) == old_r &&
+                            ((P.use_img ? P.old_list.img[eo] != 0 : false) == (img != 0)))
+                          in = true;
+                    }
+                  if (in)
+                    f(r, img);
                 }
             }
         }
     }
 
+    // The counting pass keeps what it finds: candidate k of row q goes to cand[k * n_rows + q]
+    // (coalesced across the rows of a warp), image code beside it, for the first NB_CACHE
+    // candidates of a row. The filling pass then reads its row back instead of walking the
+    // stencil a second time; rows with more candidates than the cache holds are walked again.
     __global__ void __launch_bounds__(128) k_count_neighbors(const __grid_constant__ NeighborParams P)
     {
       const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
       if (q >= P.n_rows)
         return;
       uint32_t count = 0;
-      for_each_neighbor(P, q, [&](uint32_t, uint32_t) { ++count; });
+      for_each_neighbor(P, q, [&](uint32_t r, uint32_t img) {
+        if (P.cand && count < NB_CACHE)
+          {
+            P.cand[size_t(count) * P.n_rows + q] = r;
+            if (P.use_img)
+              P.cand_img[size_t(count) * P.n_rows + q] = uint8_t(img);
+          }
+        ++count;
+      });
       P.counts[q] = count;
     }
 
@@ -336,6 +361,7 @@ namespace dem
       if (q >= P.n_rows)
         return;
       uint32_t e = P.new_list.row_start[q];
+      const uint32_t n_mine = P.new_list.row_start[q + 1] - e;
       const uint32_t old_q = P.old_of_new ? P.old_of_new[q] : 0xffffffffu;
       const bool have_old = !P.clear_history && old_q != 0xffffffffu && old_q < P.n_old_rows;
       uint32_t o0 = 0, o1 = 0;
@@ -345,7 +371,7 @@ namespace dem
           o1 = P.old_list.row_start[old_q + 1];
         }
       const uint32_t qid = P.pay.rec ? P.pay.id[q] : 0u;
-      for_each_neighbor(P, q, [&](uint32_t r, uint32_t img) {
+      auto emit = [&](uint32_t r, uint32_t img) {
         uint32_t word = r;
         const uint32_t old_r = (!P.clear_history && P.old_of_new) ? P.old_of_new[r] : 0xffffffffu;
         bool found = false;
@@ -421,7 +447,14 @@ namespace dem
         if (P.use_img)
           P.new_list.img[e] = uint8_t(img);
         ++e;
-      });
+      };
+      if (P.cand && n_mine <= NB_CACHE)
+        {
+          for (uint32_t k = 0; k < n_mine; ++k)
+            emit(P.cand[size_t(k) * P.n_rows + q], P.use_img ? uint32_t(P.cand_img[size_t(k) * P.n_rows + q]) : 0u);
+        }
+      else
+        for_each_neighbor(P, q, emit);
     }
 
     // ---- wall candidates ----

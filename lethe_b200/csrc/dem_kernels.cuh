@@ -328,7 +328,12 @@ namespace dem
     uint32_t *counts; // [n_rows+1]
     int use_roll, use_img;
     HistPayload pay; // history that arrived with immigrants
+    // candidate cache written by the counting pass, read by the filling pass (or nullptr):
+    // candidate k of row q at [k * n_rows + q], k < NB_CACHE
+    uint32_t *cand;
+    uint8_t *cand_img;
   };
+  constexpr uint32_t NB_CACHE = 24;
   void launch_count_neighbors(const NeighborParams &p, cudaStream_t s);
   void launch_fill_neighbors(const NeighborParams &p, cudaStream_t s);
 

@@ -343,7 +343,9 @@ def test_packing_in_box_application_on_gpu():
     gold = np.array([r[3:6] for r in rows])
     assert [r[0] for r in rows] == list(ids)
     err = np.abs(x - gold).max(axis=1)
-    assert np.mean(err <= 1.01e-4) > 0.9 and err.max() < 0.2 * 0.005, (np.mean(err <= 1.01e-4), err.max())
+    # the same bar as the oracle's own run of this golden (tests/test_oracle_golden.py): >= 97 % of the
+    # rows on the printed digit; the residue is the open item documented in DESIGN.md §5
+    assert np.mean(err <= 1.01e-4) >= 0.97 and err.max() < 0.2 * 0.005, (np.mean(err <= 1.01e-4), err.max())
 
 
 def test_step_host_roundtrip_matches_resident():
@@ -468,6 +470,41 @@ def test_baseline_config_workloads_parity(name):
     lockstep(g, o, 40, 10, force_rtol=FORCE_RTOL, extra=walls_equal)
     assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 2
     assert g.get_stats().n_particles == o.get_stats().n_particles
+
+
+@pytest.mark.parametrize("name", ["box_packing", "drum", "hopper", "cohesive_jkr", "cohesive_dmt", "periodic"])
+def test_baseline_configs_at_100k_lockstep(name):
+    """lock-step parity at 1e-12 on ~100 k particles of every BASELINE config, from
+    t = 0 — config 1 (box packing) for 100 steps, a 100 k slice of the others for 25. The periodic
+    case is the disordered cell bench.py tiles for config 5."""
+    from lethe_b200 import workloads
+
+    steps = 25
+    if name == "box_packing":
+        w, steps = workloads.box_packing(n_side=43, spacing=1.0, jitter=0.02), 100
+    elif name == "drum":
+        w = workloads.drum(n_target=100_000, radius=0.05, spacing=1.0, jitter=0.02)
+    elif name == "hopper":
+        w = workloads.hopper(n_target=100_000, gate_open_time=0.0001)
+    elif name == "periodic":
+        xc, Lc, _ = workloads.load_periodic_cell()
+        n1 = len(xc)
+        reps = max(1, round((100_000 / n1) ** (1 / 3)))
+        w = workloads.periodic_packing(xc * 0.002, Lc * 0.002, (reps, reps, reps), d=0.002, vel_sigma=0.1, friction=0.3)
+    else:
+        w = workloads.cohesive_box(43, model="hertz_JKR" if name == "cohesive_jkr" else "DMT")
+    assert 60_000 <= w.n <= 1_200_000, w.n
+    w.props[:, 6:9] = np.random.default_rng(8).normal(0.0, 5.0, (w.n, 3))
+    w.params.dynamic_contact_search_factor = 0.1
+    cfg = w.params.to_config(store_forces=True)
+    g, o = abi.load_engine(cfg), loader.oracle_engine(cfg)
+    w.install(g)
+    w.install(o)
+    if name == "cohesive_dmt":
+        loader.set_option(o, "dmt_stale_scratch", 0)  # see DESIGN.md "known reference defect"
+    lockstep(g, o, steps, 0, force_rtol=FORCE_RTOL)
+    assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 1
+    assert g.get_stats().n_pair_entries == o.get_stats().n_pair_entries
 
 
 @pytest.mark.parametrize("case", ["edge_vertex_contact", "CPES_double_edge_contact", "NPES_double_edge_contact",
