@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--cpu-settle", type=int, default=-1, help="settling steps of the CPU sample (-1: per workload)")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="f64", choices=["f64", "mixed"],
+                    help="f64: the reference's arithmetic (the headline); mixed: FP32 contact model between FP64 geometry and integration")
     args = ap.parse_args()
     if args.settle < 0:
         # enough for the bed to come to rest on its supports (loose lattices fall first); the periodic
@@ -278,9 +280,9 @@ def main():
 
         # a workload generated per slab (periodic) is cut into equal-width slabs; otherwise the
         # cut planes balance the particle histogram
-        engine, n_local = multi.create_slab_engine(w, rank, world, local_rank, dist, balanced=not hasattr(w, "n_global"))
+        engine, n_local = multi.create_slab_engine(w, rank, world, local_rank, dist, balanced=not hasattr(w, "n_global"), precision=args.precision)
     else:
-        engine = abi.load_engine(cfg_params.to_config(), local_rank)
+        engine = abi.load_engine(cfg_params.to_config(precision=args.precision), local_rank)
         w.install(engine)
         n_local = w.n
     n_global = getattr(w, "n_global", w.n)
@@ -449,7 +451,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f64" if args.precision == "f64" else "f64 state and accumulation, f32 contact model", "data": "synthetic",
             "config": {
                 "workload": w.description, "particles": int(n_global), "particles_per_gpu": int(n_global // world),
                 "parallelism": f"slab{world}" if world > 1 else "single",

@@ -136,8 +136,32 @@ typedef struct lethe_dem_config {
   int32_t slab_axis;
   int32_t slab_lo;
   int32_t slab_hi;
-  int32_t pad1;
+  /* `subsection adaptive sparse contacts` (parameters_lagrangian.cc; AdaptiveSparseContacts::
+   * set_parameters, adaptive_sparse_contacts.h:176-192): != 0 enables the per-cell mobility status
+   * (identify_mobility_status, adaptive_sparse_contacts.cc:132-356) at every contact search, the
+   * status-aware broad searches (particle_particle_broad_search.cc:134-316,
+   * particle_wall_broad_search.cc:212-336) and integration (velocity_verlet_integrator.cc:117-210,
+   * 292-436). `advect particles` (CFD-DEM) is not supported. */
+  int32_t sparse_contacts;
+  double asc_granular_temperature_threshold; /* `granular temperature threshold` */
+  double asc_solid_fraction_threshold;       /* `solid fraction threshold` */
+  /* Arithmetic of the particle-particle contact model (enum lethe_precision). The reference is
+   * FP64 throughout; LETHE_PRECISION_MIXED is this library's documented-bound fast mode:
+   * positions, overlaps, relative velocities, force accumulation and integration stay FP64, the
+   * contact model between them runs in FP32. Particle-wall and solid-surface contacts stay FP64. */
+  int32_t precision;
+  int32_t pad2;
 } lethe_dem_config;
+
+enum lethe_precision { LETHE_PRECISION_F64 = 0, LETHE_PRECISION_MIXED = 1 };
+
+/* AdaptiveSparseContacts::mobility_status of a cell (adaptive_sparse_contacts.h:154-162) */
+enum lethe_mobility_status {
+  LETHE_MOBILITY_INACTIVE = 0,
+  LETHE_MOBILITY_STATIC_ACTIVE = 1,
+  LETHE_MOBILITY_MOBILE = 4,
+  LETHE_MOBILITY_EMPTY_NODE = 5 /* nodes only */
+};
 
 /* One row of boundary_cells_info_struct (include/dem/boundary_cells_info_struct.h:20-38):
  * a boundary face of grid cell `cell` (lexicographic index ix + nx*(iy + ny*iz)),
@@ -260,6 +284,11 @@ int lethe_dem_get_wall_contacts(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_
 int lethe_dem_get_forces(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id,
                          double *force3, double *torque3);
 int lethe_dem_get_stats(lethe_dem_ctx *ctx, lethe_dem_stats *stats);
+/* Mobility status of every grid cell (lexicographic index ix + nx*(iy + ny*iz)) as of the last
+ * contact search: AdaptiveSparseContacts::get_mobility_status_vector
+ * (adaptive_sparse_contacts.h:317-326), what the reference's `mobility_status` test prints
+ * (dem.cc:771-783). All LETHE_MOBILITY_MOBILE when sparse contacts are disabled. */
+int lethe_dem_get_mobility_status(lethe_dem_ctx *ctx, uint64_t n_cells, int32_t *status);
 /* Device time (ms, CUDA events on the engine's stream) spent in the fused step
  * kernel and in list rebuilds since the last call with reset != 0. */
 int lethe_dem_get_timers(lethe_dem_ctx *ctx, int reset, double *step_kernel_ms,

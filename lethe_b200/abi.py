@@ -82,7 +82,11 @@ class Config(C.Structure):
         ("slab_axis", C.c_int32),
         ("slab_lo", C.c_int32),
         ("slab_hi", C.c_int32),
-        ("pad1", C.c_int32),
+        ("sparse_contacts", C.c_int32),
+        ("asc_granular_temperature_threshold", C.c_double),
+        ("asc_solid_fraction_threshold", C.c_double),
+        ("precision", C.c_int32),
+        ("pad2", C.c_int32),
     ]
 
 
@@ -153,6 +157,7 @@ ABI_SYMBOLS = [
     "get_wall_contacts",
     "get_forces",
     "get_stats",
+    "get_mobility_status",
     "get_timers",
     "enable_timers",
     "kernel_launches",
@@ -391,6 +396,13 @@ class Engine:
         ms = C.c_double()
         self._call("event_elapsed", C.byref(ms))
         return ms.value
+
+    def get_mobility_status(self):
+        """Per-cell mobility status (lexicographic cell index) as of the last contact search."""
+        n = int(self.config.grid_n[0]) * int(self.config.grid_n[1]) * int(self.config.grid_n[2])
+        out = np.empty(n, np.int32)
+        self._call("get_mobility_status", C.c_uint64(n), _ptr(out, C.POINTER(C.c_int32)))
+        return out
 
     def kernel_launches(self) -> int:
         n = C.c_uint64()

@@ -165,6 +165,12 @@ struct lethe_dem_ctx
   DevBuf<int32_t> cell_rank, cell_of_rank;
   DevBuf<uint32_t> cell_count, cell_start;
   DevBuf<uint32_t> key, slot, perm, old_of_new, counts, scan_tmp;
+  // adaptive sparse contacts (dem_kernels.cuh AscParams)
+  bool asc_enabled = false;
+  bool asc_reset = false;    // mobility_status_reset_trigger (dem_action_manager.h:128-134,61-75)
+  bool asc_in_force = false; // the lists of the current generation were built with the mobility status
+  DevBuf<uint8_t> asc_cell_status, asc_row_mobile;
+  DevBuf<int> asc_node_status;
   DevBuf<uint32_t> nb_cand;    // candidate cache of the neighbour counting pass (NB_CACHE x n_owned)
   DevBuf<uint8_t> nb_cand_img; //   image codes beside it (periodic grids)
 

@@ -379,6 +379,7 @@ namespace
     bp.old_list = olds.view();
     bp.old_of_new = c->old_of_new.p;
     bp.n_old_rows = olds.n_rows;
+    bp.mobility = c->asc_in_force ? c->asc_cell_status.p : nullptr;
     bp.clear_history = c->clear_history_trigger ? 1 : 0;
     bp.new_list = news.view();
     bp.counts = c->counts.p;
@@ -462,6 +463,43 @@ namespace
     c->st[c->cur ^ 1].ensure(std::max<size_t>(n_new, 1), 0, s);
   }
 
+  // AdaptiveSparseContacts::identify_mobility_status at every contact search (dem.cc:639-644)
+  void identify_mobility_status(Ctx *c)
+  {
+    c->asc_in_force = false;
+    if (!c->asc_enabled)
+      return;
+    cudaStream_t s = c->stream;
+    const size_t n_cells = size_t(c->grid.n_cells);
+    c->asc_cell_status.ensure(n_cells);
+    if (c->asc_reset)
+      {
+        // first iteration: every cell mobile, the regular searches and integration
+        CU_TRY(cudaMemsetAsync(c->asc_cell_status.p, LETHE_MOBILITY_MOBILE, n_cells, s));
+        return;
+      }
+    const size_t n_nodes = size_t(c->grid.n[0] + 1) * (c->grid.n[1] + 1) * (c->grid.n[2] + 1);
+    c->asc_node_status.ensure(n_nodes);
+    c->asc_row_mobile.ensure(std::max<size_t>(c->n_owned, 1));
+    CU_TRY(cudaMemsetAsync(c->asc_node_status.p, 0, n_nodes * sizeof(int), s));
+    StateBufs &stn = c->st[c->cur];
+    AscParams ap;
+    ap.st = stn.view();
+    ap.cell_start = c->cell_start.p;
+    ap.cell_rank = c->cell_rank.p;
+    ap.cell_reg = stn.cell_reg.p;
+    ap.grid = c->grid;
+    ap.granular_temperature_threshold = c->cfg.asc_granular_temperature_threshold;
+    ap.solid_fraction_threshold = c->cfg.asc_solid_fraction_threshold;
+    ap.cell_status = c->asc_cell_status.p;
+    ap.node_status = c->asc_node_status.p;
+    ap.row_mobile = c->asc_row_mobile.p;
+    ap.n_rows = c->n_owned;
+    for (int pass = 0; pass < 5; ++pass)
+      launch_asc_pass(ap, pass, s);
+    c->asc_in_force = true;
+  }
+
   // Phase 2: contact lists (particle-particle with history carry-over, particle-wall).
   void rebuild_lists(Ctx *c)
   {
@@ -504,6 +542,7 @@ namespace
     c->nb_cand.ensure(std::max<size_t>(size_t(NB_CACHE) * n_new, 1));
     if (use_img)
       c->nb_cand_img.ensure(std::max<size_t>(size_t(NB_CACHE) * n_new, 1));
+    np.mobility = c->asc_in_force ? c->asc_cell_status.p : nullptr;
     np.cand = c->nb_cand.p;
     np.cand_img = use_img ? c->nb_cand_img.p : nullptr;
     launch_count_neighbors(np, s);
@@ -541,6 +580,7 @@ namespace
     wp.counts = c->counts.p;
     wp.use_roll = use_roll;
     wp.pay = pay;
+    wp.mobility = c->asc_in_force ? c->asc_cell_status.p : nullptr;
     launch_count_walls(wp, s);
     exclusive_scan_u32(c->counts.p, neww.row_start.p, size_t(n_new) + 1, c->scan_tmp.p, s);
     const uint32_t n_wall = n_new ? read_u32(c, neww.row_start.p + n_new) : 0;
@@ -572,6 +612,7 @@ namespace
       }
     upload_walls(c);
     rebuild_sort(c);
+    identify_mobility_status(c);
     rebuild_lists(c);
     if (c->timers_enabled)
       {
@@ -605,6 +646,8 @@ namespace
         c->multi.fill_halo(c, c->cur ^ 1, P.halo);
         P.flag_check = c->multi.agreed_flag_dev(c); // the job-wide agreement, never this step's own tag
       }
+    // the first iteration after a reset integrates everything (check_mobility_status_reset)
+    P.row_mobile = (c->asc_in_force && !c->asc_reset) ? c->asc_row_mobile.p : nullptr;
     if (c->cfg.store_forces || c->count_touching)
       {
         c->touching.ensure(1);
@@ -624,6 +667,7 @@ namespace
     P.n_owned = c->n_owned;
     P.phase = phase;
     P.integrator = c->cfg.integrator;
+    P.mixed_precision = c->cfg.precision == LETHE_PRECISION_MIXED ? 1 : 0;
     P.pw_model = c->cfg.pw_model;
     P.rolling_model = c->cfg.rolling_model;
     P.periodic_any = c->grid.periodic[0] || c->grid.periodic[1] || c->grid.periodic[2];
@@ -844,7 +888,10 @@ namespace
         contact_detection_and_search(c);
         launch_step_kernel(c, phase);
       }
-    c->contact_search_trigger = false;
+    // reset_triggers (dem_action_manager.h:61-75): the iteration after a mobility-status reset
+    // searches again, with the statuses identified from the velocities of the full step
+    c->contact_search_trigger = c->asc_reset;
+    c->asc_reset = false;
     c->clear_history_trigger = false;
   }
 
@@ -976,6 +1023,10 @@ int lethe_dem_create(const lethe_dem_config *config, int device, lethe_dem_ctx *
   if (config->pp_model < 0 || config->pp_model > LETHE_PP_DMT || config->pw_model < 0 || config->pw_model > LETHE_PW_DMT ||
       config->rolling_model < 0 || config->rolling_model > LETHE_ROLLING_EPSD)
     return bad("invalid contact model selector");
+  if (config->sparse_contacts && config->integrator == LETHE_INTEGRATOR_EXPLICIT_EULER)
+    return bad("Adaptive sparse contacts are not supported with explicit Euler integrator, use Velocity Verlet integrator."); // explicit_euler_integrator.cc:157-159
+  if (config->precision != LETHE_PRECISION_F64 && config->precision != LETHE_PRECISION_MIXED)
+    return bad("unknown precision (LETHE_PRECISION_F64 or LETHE_PRECISION_MIXED)");
   if (!(config->dt > 0))
     return bad("dt must be positive");
   for (int d = 0; d < 3; ++d)
@@ -1023,6 +1074,8 @@ int lethe_dem_create(const lethe_dem_config *config, int device, lethe_dem_ctx *
       g.slab_lo = config->slab_lo;
       g.slab_hi = config->slab_hi;
       build_material_tables(*config, c->mt);
+      c->asc_enabled = config->sparse_contacts != 0;
+      c->asc_reset = c->asc_enabled; // set_sparse_contacts_enabled (dem_action_manager.h:128-134)
       c->thr2 = std::pow(config->neighborhood_threshold * config->d_max, 2); // dem.cc:156-159
       std::vector<int32_t> rank, inv;
       build_cell_curve(g, rank, inv);
@@ -1384,7 +1437,8 @@ int lethe_dem_synchronize_velocities(lethe_dem_ctx *c)
                                        step_tag(c->iteration_number), c->stream);
         CU_TRY(cudaEventRecord(c->step_done[c->iteration_number & 1], c->stream));
       }
-    c->contact_search_trigger = false;
+    c->contact_search_trigger = c->asc_reset;
+    c->asc_reset = false;
     c->clear_history_trigger = false;
   });
 }
@@ -1753,6 +1807,25 @@ int lethe_dem_get_timers(lethe_dem_ctx *c, int reset, double *step_kernel_ms, ui
         c->step_ms = c->rebuild_ms = 0;
         c->step_launches = c->rebuild_launches = 0;
       }
+  });
+}
+
+int lethe_dem_get_mobility_status(lethe_dem_ctx *c, uint64_t n_cells, int32_t *status)
+{
+  return guarded(c, [&] {
+    if (n_cells != uint64_t(c->grid.n_cells))
+      throw std::runtime_error("get_mobility_status: n_cells does not match the grid");
+    if (!c->asc_enabled || c->asc_cell_status.cap < n_cells)
+      {
+        for (uint64_t k = 0; k < n_cells; ++k)
+          status[k] = LETHE_MOBILITY_MOBILE;
+        return;
+      }
+    std::vector<uint8_t> h(n_cells);
+    CU_TRY(cudaMemcpyAsync(h.data(), c->asc_cell_status.p, n_cells, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    for (uint64_t k = 0; k < n_cells; ++k)
+      status[k] = h[k];
   });
 }
 

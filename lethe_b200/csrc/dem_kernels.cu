@@ -234,6 +234,10 @@ namespace dem
       const int lin = P.cell_reg[q];
       const int ci = lin % g.n[0], cj = (lin / g.n[0]) % g.n[1], ck = lin / (g.n[0] * g.n[1]);
       const uint32_t old_q = P.old_of_new ? P.old_of_new[q] : 0xffffffffu;
+      // adaptive sparse contacts: particles of inactive cells are in no list; a pair needs a mobile cell
+      const uint32_t my_status = P.mobility ? P.mobility[lin] : uint32_t(LETHE_MOBILITY_MOBILE);
+      if (my_status == LETHE_MOBILITY_INACTIVE)
+        return;
       // s = image shift (in units of L) that brings the neighbour cell next to mine:
       // my cell on the low face, neighbour wrapped to the high face -> s = -1.
       int n1[3][3]; // wrapped cell coordinate per axis and offset, -1: outside a non-periodic face
@@ -263,7 +267,11 @@ namespace dem
       for (int k = 0; k < 27; ++k)
         {
           const int ni = n1[0][k % 3], nj = n1[1][(k / 3) % 3], nk = n1[2][k / 9];
-          rank[k] = (ni < 0 || nj < 0 || nk < 0) ? 0xffffffffu : uint32_t(P.cell_rank[ni + g.n[0] * (nj + g.n[1] * nk)]);
+          const bool outside = ni < 0 || nj < 0 || nk < 0;
+          const int nlin = outside ? 0 : ni + g.n[0] * (nj + g.n[1] * nk);
+          rank[k] = outside ? 0xffffffffu : uint32_t(P.cell_rank[nlin]);
+          if (!outside && my_status != LETHE_MOBILITY_MOBILE && P.mobility[nlin] != LETHE_MOBILITY_MOBILE)
+            rank[k] = 0xffffffffu;
         }
       uint32_t cs[27], ce[27];
 #pragma unroll
@@ -461,6 +469,9 @@ namespace dem
     template <class F> __device__ __forceinline__ void for_each_wall(const WallBuildParams &P, uint32_t q, F &&f)
     {
       const int lin = P.cell_reg[q];
+      // particle_wall_broad_search.cc:239-246,310-317: mobile cells only
+      if (P.mobility && P.mobility[lin] != LETHE_MOBILITY_MOBILE)
+        return;
       if (P.faces.n_faces)
         for (uint32_t k = P.faces.cell_face_start[lin]; k < P.faces.cell_face_start[lin + 1]; ++k)
           f(k);
@@ -960,6 +971,123 @@ namespace dem
       P.old_of_new[q] = old;
     }
 
+    // ---- adaptive sparse contacts ----
+    __device__ __forceinline__ int asc_node(const GridDesc &g, int i, int j, int k)
+    {
+      // periodic directions share the nodes of their two faces (periodic_node_ids)
+      if (g.periodic[0] && i == g.n[0])
+        i = 0;
+      if (g.periodic[1] && j == g.n[1])
+        j = 0;
+      if (g.periodic[2] && k == g.n[2])
+        k = 0;
+      return i + (g.n[0] + 1) * (j + (g.n[1] + 1) * k);
+    }
+    __device__ __forceinline__ bool asc_any_node(const AscParams &P, int lin, int value)
+    {
+      const GridDesc &g = P.grid;
+      const int ci = lin % g.n[0], cj = (lin / g.n[0]) % g.n[1], ck = lin / (g.n[0] * g.n[1]);
+      bool any = false;
+      for (int v = 0; v < 8; ++v)
+        any |= P.node_status[asc_node(g, ci + (v & 1), cj + ((v >> 1) & 1), ck + (v >> 2))] == value;
+      return any;
+    }
+    // assign_mobility_status (adaptive_sparse_contacts.h:389-412): the prevailing (larger) status stays at a node
+    __device__ __forceinline__ void asc_raise_nodes(const AscParams &P, int lin, int value)
+    {
+      const GridDesc &g = P.grid;
+      const int ci = lin % g.n[0], cj = (lin / g.n[0]) % g.n[1], ck = lin / (g.n[0] * g.n[1]);
+      for (int v = 0; v < 8; ++v)
+        atomicMax(P.node_status + asc_node(g, ci + (v & 1), cj + ((v >> 1) & 1), ck + (v >> 2)), value);
+    }
+
+    constexpr uint8_t ASC_UNASSIGNED = 0xffu;
+
+    // One thread per cell; the four passes are separate launches because each reads the node
+    // values the previous one wrote. Within a pass the node value tested is never one the pass writes.
+    template <int PASS> __global__ void __launch_bounds__(128) k_asc_cells(const __grid_constant__ AscParams P)
+    {
+      const int lin = blockIdx.x * blockDim.x + threadIdx.x;
+      if (lin >= P.grid.n_cells)
+        return;
+      const uint32_t rank = uint32_t(P.cell_rank[lin]);
+      const uint32_t p0 = P.cell_start[rank], p1 = P.cell_start[rank + 1];
+      if constexpr (PASS == 0)
+        {
+          // 1. empty cells: cell inactive, nodes empty
+          if (p1 == p0)
+            {
+              P.cell_status[lin] = LETHE_MOBILITY_INACTIVE;
+              asc_raise_nodes(P, lin, LETHE_MOBILITY_EMPTY_NODE);
+            }
+          else
+            P.cell_status[lin] = ASC_UNASSIGNED;
+          return;
+        }
+      if (P.cell_status[lin] != ASC_UNASSIGNED)
+        return;
+      if constexpr (PASS == 1)
+        {
+          // 2. mobile by criteria: granular temperature, solid fraction (calculate_granular_temperature_
+          // and_solid_fraction, adaptive_sparse_contacts.cc:35-130), next to an empty cell
+          const unsigned int n = p1 - p0;
+          double solid_volume = 0.0;
+          double va[3] = {0, 0, 0};
+          for (uint32_t r = p0; r < p1; ++r)
+            {
+              const double4 x = P.st.pos[r], v = P.st.vel[r];
+              va[0] += v.x;
+              va[1] += v.y;
+              va[2] += v.z;
+              solid_volume += M_PI * (x.w * x.w * x.w) / (2.0 * 3);
+            }
+          const double inv = 1.0 / n;
+          for (int d = 0; d < 3; ++d)
+            va[d] *= inv;
+          const double solid_fraction = solid_volume / (P.grid.h[0] * P.grid.h[1] * P.grid.h[2]);
+          double fl[3] = {0, 0, 0};
+          for (uint32_t r = p0; r < p1; ++r)
+            {
+              const double4 v = P.st.vel[r];
+              const double f0 = v.x - va[0], f1 = v.y - va[1], f2 = v.z - va[2];
+              fl[0] += f0 * f0;
+              fl[1] += f1 * f1;
+              fl[2] += f2 * f2;
+            }
+          double granular_temperature = 0.0;
+          for (int d = 0; d < 3; ++d)
+            {
+              fl[d] /= n;
+              granular_temperature += fl[d] / 3;
+            }
+          if (granular_temperature > P.granular_temperature_threshold || solid_fraction < P.solid_fraction_threshold ||
+              asc_any_node(P, lin, LETHE_MOBILITY_EMPTY_NODE))
+            {
+              P.cell_status[lin] = LETHE_MOBILITY_MOBILE;
+              asc_raise_nodes(P, lin, LETHE_MOBILITY_MOBILE);
+            }
+        }
+      else if constexpr (PASS == 2)
+        {
+          // 3. the additional mobile layer: a node made mobile by pass 1; its other nodes become active
+          if (asc_any_node(P, lin, LETHE_MOBILITY_MOBILE))
+            {
+              P.cell_status[lin] = LETHE_MOBILITY_MOBILE;
+              asc_raise_nodes(P, lin, LETHE_MOBILITY_STATIC_ACTIVE);
+            }
+        }
+      else
+        // 4. the active layer; the rest is inactive
+        P.cell_status[lin] = asc_any_node(P, lin, LETHE_MOBILITY_STATIC_ACTIVE) ? LETHE_MOBILITY_STATIC_ACTIVE : LETHE_MOBILITY_INACTIVE;
+    }
+
+    __global__ void __launch_bounds__(256) k_asc_rows(const __grid_constant__ AscParams P)
+    {
+      const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q < P.n_rows)
+        P.row_mobile[q] = P.cell_status[P.cell_reg[q]] == LETHE_MOBILITY_MOBILE ? 1 : 0;
+    }
+
     __global__ void __launch_bounds__(256) k_register_ids(const uint32_t *id, uint32_t base, uint32_t n, uint32_t *slot_of_id,
                                                           uint32_t map_size)
     {
@@ -1418,6 +1546,22 @@ namespace dem
         count_launch();
       }
   }
+  void launch_asc_pass(const AscParams &p, int pass, cudaStream_t s)
+  {
+    const unsigned cells = unsigned((p.grid.n_cells + 127) / 128);
+    if (pass == 0)
+      k_asc_cells<0><<<cells, 128, 0, s>>>(p);
+    else if (pass == 1)
+      k_asc_cells<1><<<cells, 128, 0, s>>>(p);
+    else if (pass == 2)
+      k_asc_cells<2><<<cells, 128, 0, s>>>(p);
+    else if (pass == 3)
+      k_asc_cells<3><<<cells, 128, 0, s>>>(p);
+    else if (p.n_rows)
+      k_asc_rows<<<(p.n_rows + 255) / 256, 256, 0, s>>>(p);
+    count_launch(1);
+  }
+
   void launch_register_ids(const uint32_t *id, uint32_t base, uint32_t n, uint32_t *slot_of_id, uint32_t map_size, cudaStream_t s)
   {
     if (n)

@@ -140,6 +140,7 @@ namespace dem
     int spec_check;
     HaloPush halo;
     unsigned long long *touching_counter; // debug (store_forces)
+    const uint8_t *row_mobile;            // adaptive sparse contacts: per row, 0 = not integrated; nullptr = all mobile
     double *force_out, *torque_out;       // debug taps [N][3] or nullptr
     const double *solid_force, *solid_torque; // [N][3] solid-surface contacts of this step (dem_solid.cuh) or nullptr
     FaceTable faces;
@@ -148,6 +149,7 @@ namespace dem
     uint32_t n_owned; // particles integrated by this rank
     int phase;
     int integrator; // lethe_integrator
+    int mixed_precision; // pair model in float (lethe_precision)
     int pw_model;
     int rolling_model;
     int periodic_any;
@@ -332,6 +334,10 @@ namespace dem
     // candidate k of row q at [k * n_rows + q], k < NB_CACHE
     uint32_t *cand;
     uint8_t *cand_img;
+    // adaptive sparse contacts: per-cell mobility status (lexicographic cell index) or nullptr.
+    // A pair is listed iff at least one of its two cells is mobile
+    // (particle_particle_broad_search.cc:134-316).
+    const uint8_t *mobility;
   };
   constexpr uint32_t NB_CACHE = 24;
   void launch_count_neighbors(const NeighborParams &p, cudaStream_t s);
@@ -355,6 +361,7 @@ namespace dem
     uint32_t *counts;
     int use_roll;
     HistPayload pay;
+    const uint8_t *mobility; // adaptive sparse contacts: only particles of mobile cells get wall candidates, or nullptr
   };
   void launch_count_walls(const WallBuildParams &p, cudaStream_t s);
   void launch_fill_walls(const WallBuildParams &p, cudaStream_t s);
@@ -396,4 +403,21 @@ namespace dem
   // process-wide count of kernel launches issued by this library
   void count_launch(unsigned n = 1);
   unsigned long long launch_count();
+  // ---- adaptive sparse contacts (AdaptiveSparseContacts::identify_mobility_status,
+  // adaptive_sparse_contacts.cc:132-356, on the uniform grid: nodes = grid vertices) ----
+  struct AscParams
+  {
+    StateView st;               // cell-sorted owned particles
+    const uint32_t *cell_start; // by curve rank
+    const int32_t *cell_rank;   // lexicographic cell -> curve rank
+    const int32_t *cell_reg;    // per particle: lexicographic cell
+    GridDesc grid;
+    double granular_temperature_threshold, solid_fraction_threshold;
+    uint8_t *cell_status; // [n_cells] lethe_mobility_status, 0xff = not assigned yet
+    int *node_status;     // [(nx+1)(ny+1)(nz+1)]
+    uint8_t *row_mobile;  // [n_rows] 1 = the particle's cell is mobile
+    uint32_t n_rows;
+  };
+  // pass 0: empty cells, 1: mobile by criteria, 2: mobile by neighbour, 3: active / inactive, 4: per-particle flag
+  void launch_asc_pass(const AscParams &p, int pass, cudaStream_t s);
 } // namespace dem

@@ -220,7 +220,9 @@ namespace dem
       if (q >= P.n_rows)
         return;
       const int c = P.cell_reg[q];
-      P.counts[q] = c >= 0 ? P.cell_tri_start[c + 1] - P.cell_tri_start[c] : 0u;
+      // adaptive sparse contacts: particles of mobile cells only (particle_wall_broad_search.cc:391-398)
+      const bool listed = c >= 0 && (!P.mobility || P.mobility[c] == LETHE_MOBILITY_MOBILE);
+      P.counts[q] = listed ? P.cell_tri_start[c + 1] - P.cell_tri_start[c] : 0u;
     }
     __global__ void __launch_bounds__(256) k_fill_solid_rows(const __grid_constant__ SolidBuildParams P)
     {

@@ -85,6 +85,7 @@ namespace dem
     uint32_t *counts; // [n_rows + 1]; after the fill: 1 where the row is not empty
     int use_roll;
     HistPayload pay; // history that arrived with particles that immigrated in this rebuild
+    const uint8_t *mobility; // adaptive sparse contacts: per-cell status or nullptr
   };
   void launch_count_solid_rows(const SolidBuildParams &p, cudaStream_t s);
   void launch_fill_solid_rows(const SolidBuildParams &p, cudaStream_t s);

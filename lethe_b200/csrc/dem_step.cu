@@ -59,6 +59,10 @@ namespace dem
 #endif
     constexpr int SWEEP = DEM_SWEEP;      // 32-entry blocks of the list swept per phase-A iteration (loads in flight)
     constexpr int STEP_MIN_BLOCKS = DEM_MIN_BLOCKS; // resident blocks per SM the register allocation is held to
+#ifndef DEM_MIN_BLOCKS_MIXED
+#define DEM_MIN_BLOCKS_MIXED 4
+#endif
+    constexpr int STEP_MIN_BLOCKS_MIXED = DEM_MIN_BLOCKS_MIXED; // the same for the mixed-precision instantiations
 
     __device__ __forceinline__ ParticleView make_view(double4 p, double4 v, double4 w)
     {
@@ -134,8 +138,8 @@ namespace dem
       uint32_t halo[4];                  // HaloPush bits / prefix of this 32-row block, per direction
     };
 
-    template <int MODEL, int ROLLING, bool PERIODIC>
-    __global__ void __launch_bounds__(32 * STEP_WARPS, STEP_MIN_BLOCKS) k_step(const __grid_constant__ StepParams P, const __grid_constant__ MaterialTables mt)
+    template <int MODEL, int ROLLING, bool PERIODIC, bool MIXED>
+    __global__ void __launch_bounds__(32 * STEP_WARPS, MIXED ? STEP_MIN_BLOCKS_MIXED : STEP_MIN_BLOCKS) k_step(const __grid_constant__ StepParams P, const __grid_constant__ MaterialTables mt)
     {
       __shared__ WarpScratch scratch[STEP_WARPS];
       const uint32_t lane = threadIdx.x & 31u;
@@ -219,39 +223,91 @@ namespace dem
                     rs = v3(rp[0], rp[1], rp[2]);
                   }
               }
-            PairResult r;
-            r.normal_force = r.tangential_force = r.torque_one = r.torque_two = r.rolling = v3(0, 0, 0);
             const double2 self = S.self[owner];
-            const SelfPair sp{self.x, self.y};
-            vec3 n, vt;
-            double vn;
             vec3 fc, tc; // what the row particle receives: F -= fc, T += tc
-            if (PERIODIC && i_am_two)
+            if constexpr (!MIXED)
               {
-                // evaluate the pair in its canonical orientation (one = neighbour) so that both
-                // owners of the pair run bit-identical arithmetic; my copy of the history is the
-                // negative of the canonical one.
-                ParticleView one = other, two = me;
-                one.x = x1;
-                h = -h;
-                rs = -rs;
-                pp_update_contact_information(h, vt, vn, n, one, two, x2, distance, dt);
-                pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, two, r, sp);
-                // apply_force_and_torque_on_local_particles, particle two (…force.h:565-569)
-                fc = -(r.normal_force + r.tangential_force);
-                tc = -r.torque_two - r.rolling;
-                h = -h;
-                rs = -rs;
+                PairResult r;
+                r.normal_force = r.tangential_force = r.torque_one = r.torque_two = r.rolling = v3(0, 0, 0);
+                const SelfPair sp{self.x, self.y};
+                vec3 n, vt;
+                double vn;
+                if (PERIODIC && i_am_two)
+                  {
+                    // evaluate the pair in its canonical orientation (one = neighbour) so that both
+                    // owners of the pair run bit-identical arithmetic; my copy of the history is the
+                    // negative of the canonical one.
+                    ParticleView one = other, two = me;
+                    one.x = x1;
+                    h = -h;
+                    rs = -rs;
+                    pp_update_contact_information<double>(h, vt, vn, n, one, two, x2, distance, dt);
+                    pp_calculate_contact<MODEL, ROLLING, double>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, two, r, sp);
+                    // apply_force_and_torque_on_local_particles, particle two (…force.h:565-569)
+                    fc = -(r.normal_force + r.tangential_force);
+                    tc = -r.torque_two - r.rolling;
+                    h = -h;
+                    rs = -rs;
+                  }
+                else
+                  {
+                    ParticleView one = me;
+                    one.x = x1;
+                    pp_update_contact_information<double>(h, vt, vn, n, one, other, x2, distance, dt);
+                    pp_calculate_contact<MODEL, ROLLING, double>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, other, r, sp);
+                    // particle one (…force.h:561-567)
+                    fc = r.normal_force + r.tangential_force;
+                    tc = -r.torque_one + r.rolling;
+                  }
               }
             else
               {
-                ParticleView one = me;
-                one.x = x1;
-                pp_update_contact_information(h, vt, vn, n, one, other, x2, distance, dt);
-                pp_calculate_contact<MODEL, ROLLING>(mt, h, rs, vt, vn, n, normal_overlap, dt, one, other, r, sp);
-                // particle one (…force.h:561-567)
-                fc = r.normal_force + r.tangential_force;
-                tc = -r.torque_one + r.rolling;
+                // Mixed precision (config.precision = LETHE_PRECISION_MIXED): what cancels is done in
+                // double — the centre distance and the overlap above, the contact vector and the
+                // relative translational velocity below — and handed to the model as floats; the
+                // model itself (stiffnesses, damping, Coulomb limit, rolling resistance, history
+                // update) runs in float; the force and torque go back to double for the segment
+                // reduction and the integration. Both owners of a pair still run the same
+                // arithmetic on the same operands (canonical orientation), so action = reaction
+                // holds to the last bit here too.
+                PairResult_t<float> r;
+                r.normal_force = r.tangential_force = r.torque_one = r.torque_two = r.rolling = v3t<float>(0, 0, 0);
+                const SelfPair_t<float> sp{float(self.x), float(self.y)};
+                const bool flip = PERIODIC && i_am_two;
+                const ParticleView &a = flip ? other : me; // particle one of the canonical orientation
+                const ParticleView &b = flip ? me : other;
+                ParticleView_t<float> one, two;
+                one.x = v3t<float>(0, 0, 0);
+                one.d = float(a.d);
+                one.m = float(a.m);
+                one.v = to_float(a.v - b.v);
+                one.w = to_float(a.w);
+                one.type = a.type;
+                two.x = to_float(x2 - x1);
+                two.d = float(b.d);
+                two.m = float(b.m);
+                two.v = v3t<float>(0, 0, 0);
+                two.w = to_float(b.w);
+                two.type = b.type;
+                vec3f hf = to_float(flip ? -h : h), rf = to_float(flip ? -rs : rs);
+                vec3f n, vt;
+                float vn;
+                pp_update_contact_information<float>(hf, vt, vn, n, one, two, two.x, float(distance), float(dt));
+                pp_calculate_contact<MODEL, ROLLING, float>(mt, hf, rf, vt, vn, n, float(normal_overlap), float(dt), one, two, r, sp);
+                if (flip)
+                  {
+                    fc = to_double(-(r.normal_force + r.tangential_force));
+                    tc = to_double(-r.torque_two - r.rolling);
+                    h = to_double(-hf);
+                    rs = to_double(-rf);
+                  }
+                else
+                  {
+                    fc = to_double(r.normal_force + r.tangential_force);
+                    tc = to_double(-r.torque_one + r.rolling);
+                    h = to_double(hf);
+                    rs = to_double(rf);
+                  }
               }
             hp[0] = h.x;
             hp[1] = h.y;
@@ -592,6 +648,14 @@ namespace dem
               x.z = x.z + v.z * dt;
             }
         }
+      // adaptive sparse contacts (velocity_verlet_integrator.cc:117-210,292-436): only the particles of
+      // mobile cells are integrated; the others keep their state, their force and torque are dropped
+      if (P.row_mobile && !P.row_mobile[i])
+        {
+          v = me.v;
+          x = me.x;
+          om = me.w;
+        }
       const double4 new_pos = make_double4(x.x, x.y, x.z, pi.w), new_vel = make_double4(v.x, v.y, v.z, vi.w),
                     new_omg = make_double4(om.x, om.y, om.z, wi.w);
       P.out.pos[i] = new_pos;
@@ -632,10 +696,17 @@ namespace dem
         return;
       constexpr uint32_t per_block = 32 * STEP_WARPS;
       const dim3 block(per_block), grid((p.n_owned + per_block - 1) / per_block);
-      if (p.periodic_any)
-        k_step<MODEL, ROLLING, true><<<grid, block, 0, stream>>>(p, mt);
+      if (p.mixed_precision)
+        {
+          if (p.periodic_any)
+            k_step<MODEL, ROLLING, true, true><<<grid, block, 0, stream>>>(p, mt);
+          else
+            k_step<MODEL, ROLLING, false, true><<<grid, block, 0, stream>>>(p, mt);
+        }
+      else if (p.periodic_any)
+        k_step<MODEL, ROLLING, true, false><<<grid, block, 0, stream>>>(p, mt);
       else
-        k_step<MODEL, ROLLING, false><<<grid, block, 0, stream>>>(p, mt);
+        k_step<MODEL, ROLLING, false, false><<<grid, block, 0, stream>>>(p, mt);
       count_launch();
     }
 

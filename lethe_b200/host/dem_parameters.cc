@@ -129,6 +129,13 @@ namespace lethe_b200
     p.dmt_cut_off_threshold = mp.get_double("dmt cut-off threshold", 0.1);
     p.f_coefficient = mp.get_double("f coefficient", 0.0);
     p.solver_type = mp.get("solver type", "dem");
+    // `subsection adaptive sparse contacts` (parameters_lagrangian.cc:1059-1116)
+    const PrmSection &asc = mp.sub("adaptive sparse contacts");
+    p.sparse_contacts = asc.get("enable adaptive sparse contacts", "false") == "true";
+    p.asc_granular_temperature_threshold = asc.get_double("granular temperature threshold", 1e-4);
+    p.asc_solid_fraction_threshold = asc.get_double("solid fraction threshold", 0.4);
+    if (asc.get("enable particle advection", "false") == "true")
+      throw std::runtime_error("adaptive sparse contacts: particle advection (CFD-DEM) is out of scope");
 
     const PrmSection &lp = d.sub("lagrangian physical properties");
     if (lp.has("g"))
@@ -445,6 +452,9 @@ namespace lethe_b200
         c.periodic[d] = per[d];
       }
     c.slab_axis = -1;
+    c.sparse_contacts = sparse_contacts ? 1 : 0;
+    c.asc_granular_temperature_threshold = asc_granular_temperature_threshold;
+    c.asc_solid_fraction_threshold = asc_solid_fraction_threshold;
     return c;
   }
 } // namespace lethe_b200

@@ -41,7 +41,8 @@ def owner_mask(x: np.ndarray, mesh, axis: int, lo: int, hi: int):
     return (c >= lo) & (c < hi)
 
 
-def create_slab_engine(workload, rank: int, world: int, device: int, dist=None, axis: int = 0, store_forces=False, balanced=True):
+def create_slab_engine(workload, rank: int, world: int, device: int, dist=None, axis: int = 0, store_forces=False, balanced=True,
+                       precision="f64"):
     """Engine of rank `rank` holding its slab of `workload`; returns (engine, n_local)."""
     p = workload.params
     mesh = p.mesh
@@ -52,7 +53,7 @@ def create_slab_engine(workload, rank: int, world: int, device: int, dist=None, 
     else:
         bounds = slab_bounds(mesh.n[axis], world)
     lo, hi = bounds[rank]
-    cfg = p.to_config(store_forces=store_forces, slab=(axis, lo, hi))
+    cfg = p.to_config(store_forces=store_forces, slab=(axis, lo, hi), precision=precision)
     engine = abi.load_engine(cfg, device)
     if dist is not None:
         obj = [abi.nccl_unique_id() if rank == 0 else None]

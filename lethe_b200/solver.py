@@ -386,14 +386,23 @@ class DEMSolver:
         margin = max(1e-6 * p.time_step, 1e-12 * p.time_end)
         return self.current_time >= (p.time_end - margin)
 
-    def solve(self, max_steps=None):
-        """The `while (simulation_control->integrate())` loop + closing half step."""
+    def solve(self, max_steps=None, log_callback=None):
+        """The `while (simulation_control->integrate())` loop + closing half step.
+        `log_callback(iteration_number)` runs where report_statistics does, at the top of every
+        iteration that logs (`log frequency`, dem.cc:1116-1118)."""
         pending = 0
         steps = 0
         while not self._is_at_end() and (max_steps is None or steps < max_steps):
             self.iteration_number += 1
             self.current_time += self.parameters.time_step
             steps += 1
+            if log_callback is not None and self.iteration_number % max(1, self.parameters.log_frequency) == 0:
+                # report_statistics comes first in the iteration (dem.cc:1116-1118): the state the
+                # previous iterations left
+                if pending:
+                    self.engine.step(pending)
+                    pending = 0
+                log_callback(self.iteration_number)
             # SerialSolid::move_solid_triangulation evaluates the velocity functions at the previous
             # time (serial_solid.cc:343-352): push new values before the step that uses them
             t_prev = self.current_time - self.parameters.time_step

@@ -270,6 +270,15 @@ namespace
     uint64_t n_touching_last;
     // reference defect switch, see pp_execute_contact_calculation
     bool dmt_stale_scratch = true;
+
+    // adaptive sparse contacts (AdaptiveSparseContacts, adaptive_sparse_contacts.h)
+    bool sparse_contacts_enabled = false;
+    bool mobility_status_reset_trigger = false; // dem_action_manager.h:128-134
+    std::vector<int> cell_mobility_status;      // per lexicographic cell
+    std::vector<int> mobility_at_nodes;         // (nx+1)(ny+1)(nz+1) grid vertices
+    // the status-aware searches / integration are in force (dem_action_manager.h:391-395)
+    bool asc_active() const { return sparse_contacts_enabled && !mobility_status_reset_trigger; }
+    bool cell_is_mobile(int cell) const { return !asc_active() || cell_mobility_status[cell] == LETHE_MOBILITY_MOBILE; }
   };
 
   // ---------------------------------------------------------------- grid ----
@@ -702,19 +711,173 @@ namespace
       row.c.push_back(o.parts[cellp[k]].id);
   }
 
-  // find_particle_particle_contact_pairs (particle_particle_broad_search.cc:9-132), local part
+  // ------------------------------------------------ adaptive sparse contacts ----
+  // Grid vertex (node of the FE_Q(1) background DoF handler) index; periodic directions share
+  // the nodes of their two faces (periodic_node_ids, adaptive_sparse_contacts.h:279-295: nodes
+  // that are identity-constrained to each other exchange their status on every assignment).
+  inline int node_index(const Oracle &o, int i, int j, int k)
+  {
+    if (o.cfg.periodic[0] && i == o.nx)
+      i = 0;
+    if (o.cfg.periodic[1] && j == o.ny)
+      j = 0;
+    if (o.cfg.periodic[2] && k == o.nz)
+      k = 0;
+    return i + (o.nx + 1) * (j + (o.ny + 1) * k);
+  }
+  inline void cell_nodes(const Oracle &o, int cell, int out[8])
+  {
+    const int ci = cell % o.nx, cj = (cell / o.nx) % o.ny, ck = cell / (o.nx * o.ny);
+    for (int v = 0; v < 8; ++v)
+      out[v] = node_index(o, ci + (v & 1), cj + ((v >> 1) & 1), ck + (v >> 2));
+  }
+
+  // AdaptiveSparseContacts::calculate_granular_temperature_and_solid_fraction
+  // (adaptive_sparse_contacts.cc:35-130) for one non-empty cell
+  void granular_temperature_and_solid_fraction(const Oracle &o, int cell, double &granular_temperature, double &solid_fraction)
+  {
+    const std::vector<int> &in_cell = o.cell_parts[cell];
+    const unsigned int n_particles_in_cell = static_cast<unsigned int>(in_cell.size());
+    double solid_volume = 0.0;
+    // cell->measure() of an axis-aligned hexahedron
+    const double cell_volume = o.cfg.cell_size[0] * o.cfg.cell_size[1] * o.cfg.cell_size[2];
+    V3 velocity_cell_average = mk(0, 0, 0);
+    V3 cell_velocity_fluctuation_squared_average = mk(0, 0, 0);
+    for (int s : in_cell)
+      {
+        const double *p = o.parts[s].p;
+        const double dp = p[P_DP];
+        for (int d = 0; d < 3; ++d)
+          velocity_cell_average[d] += p[P_VX + d];
+        solid_volume += M_PI * (dp * dp * dp) / (2.0 * 3);
+      }
+    {
+      // Tensor /= scalar
+      const double inv = 1.0 / n_particles_in_cell;
+      for (int d = 0; d < 3; ++d)
+        velocity_cell_average[d] *= inv;
+    }
+    solid_fraction = solid_volume / cell_volume;
+    for (int s : in_cell)
+      {
+        const double *p = o.parts[s].p;
+        for (int d = 0; d < 3; ++d)
+          {
+            const double f = p[P_VX + d] - velocity_cell_average[d];
+            cell_velocity_fluctuation_squared_average[d] += f * f;
+          }
+      }
+    granular_temperature = 0.0;
+    for (int d = 0; d < 3; ++d)
+      {
+        cell_velocity_fluctuation_squared_average[d] /= n_particles_in_cell;
+        granular_temperature += cell_velocity_fluctuation_squared_average[d] / 3;
+      }
+  }
+
+  // AdaptiveSparseContacts::identify_mobility_status (adaptive_sparse_contacts.cc:132-356);
+  // `advect particles` (CFD-DEM) is not restated: inactive / static_active only.
+  void identify_mobility_status(Oracle &o)
+  {
+    if (!o.sparse_contacts_enabled)
+      return;
+    o.cell_mobility_status.assign(o.n_cells, -1);
+    if (o.mobility_status_reset_trigger)
+      {
+        o.cell_mobility_status.assign(o.n_cells, LETHE_MOBILITY_MOBILE);
+        return;
+      }
+    o.mobility_at_nodes.assign(size_t(o.nx + 1) * (o.ny + 1) * (o.nz + 1), 0);
+    int nodes[8];
+    auto assign = [&](int cell, int cell_status, int node_status) {
+      o.cell_mobility_status[cell] = cell_status;
+      for (int v = 0; v < 8; ++v)
+        o.mobility_at_nodes[nodes[v]] = std::max(node_status, o.mobility_at_nodes[nodes[v]]);
+    };
+    // 1. empty cells: cell inactive, nodes empty
+    for (int cell = 0; cell < o.n_cells; ++cell)
+      if (o.cell_parts[cell].empty())
+        {
+          cell_nodes(o, cell, nodes);
+          assign(cell, LETHE_MOBILITY_INACTIVE, LETHE_MOBILITY_EMPTY_NODE);
+        }
+    // 2. mobile by criteria: granular temperature, solid fraction, next to an empty cell
+    for (int cell = 0; cell < o.n_cells; ++cell)
+      {
+        if (o.cell_mobility_status[cell] != -1)
+          continue;
+        cell_nodes(o, cell, nodes);
+        bool has_empty_node = false;
+        for (int v = 0; v < 8; ++v)
+          if (o.mobility_at_nodes[nodes[v]] == LETHE_MOBILITY_EMPTY_NODE)
+            {
+              has_empty_node = true;
+              break;
+            }
+        double granular_temperature, solid_fraction;
+        granular_temperature_and_solid_fraction(o, cell, granular_temperature, solid_fraction);
+        if (granular_temperature > o.cfg.asc_granular_temperature_threshold || solid_fraction < o.cfg.asc_solid_fraction_threshold ||
+            has_empty_node)
+          assign(cell, LETHE_MOBILITY_MOBILE, LETHE_MOBILITY_MOBILE);
+      }
+    // 3. mobile by neighbour (a node flagged mobile by step 2): the additional mobile layer;
+    //    its other nodes become active. Step 3 never creates a mobile node (max with active).
+    for (int cell = 0; cell < o.n_cells; ++cell)
+      {
+        if (o.cell_mobility_status[cell] != -1)
+          continue;
+        cell_nodes(o, cell, nodes);
+        bool has_mobile_node = false;
+        for (int v = 0; v < 8; ++v)
+          if (o.mobility_at_nodes[nodes[v]] == LETHE_MOBILITY_MOBILE)
+            {
+              has_mobile_node = true;
+              break;
+            }
+        if (has_mobile_node)
+          assign(cell, LETHE_MOBILITY_MOBILE, LETHE_MOBILITY_STATIC_ACTIVE);
+      }
+    // 4. the layer of active cells (a node flagged active); the rest is inactive
+    for (int cell = 0; cell < o.n_cells; ++cell)
+      {
+        if (o.cell_mobility_status[cell] != -1)
+          continue;
+        cell_nodes(o, cell, nodes);
+        bool has_active_nodes = false;
+        for (int v = 0; v < 8; ++v)
+          if (o.mobility_at_nodes[nodes[v]] == LETHE_MOBILITY_STATIC_ACTIVE)
+            {
+              has_active_nodes = true;
+              break;
+            }
+        o.cell_mobility_status[cell] = has_active_nodes ? LETHE_MOBILITY_STATIC_ACTIVE : LETHE_MOBILITY_INACTIVE;
+      }
+  }
+
+  // find_particle_particle_contact_pairs (particle_particle_broad_search.cc:9-132; with adaptive
+  // sparse contacts :134-316), local part
   void find_particle_particle_contact_pairs(Oracle &o)
   {
     o.local_candidates.clear();
+    const bool asc = o.asc_active();
     for (const auto &list : o.cells_local_neighbor_list)
       {
         const std::vector<int> &main = o.cell_parts[list[0]];
+        const int main_status = asc ? o.cell_mobility_status[list[0]] : LETHE_MOBILITY_MOBILE;
+        // inactive main cell: nothing; empty cells are inactive
+        if (main_status == LETHE_MOBILITY_INACTIVE)
+          continue;
         if (main.empty())
           continue;
-        for (size_t a = 0; a < main.size(); ++a)
-          store_candidates(o, o.local_candidates, o.parts[main[a]].id, main, a + 1);
+        // pairs inside the main cell only if it is mobile
+        if (main_status == LETHE_MOBILITY_MOBILE)
+          for (size_t a = 0; a < main.size(); ++a)
+            store_candidates(o, o.local_candidates, o.parts[main[a]].id, main, a + 1);
         for (size_t nb = 1; nb < list.size(); ++nb)
           {
+            // an active main cell only pairs with mobile neighbours
+            if (asc && main_status == LETHE_MOBILITY_STATIC_ACTIVE && o.cell_mobility_status[list[nb]] != LETHE_MOBILITY_MOBILE)
+              continue;
             const std::vector<int> &other = o.cell_parts[list[nb]];
             for (size_t a = 0; a < main.size(); ++a)
               store_candidates(o, o.local_candidates, o.parts[main[a]].id, other, 0);
@@ -725,13 +888,19 @@ namespace
   void find_particle_particle_periodic_contact_pairs(Oracle &o)
   {
     o.periodic_candidates.clear();
+    const bool asc = o.asc_active();
     for (const auto &list : o.cells_local_periodic_neighbor_list)
       {
         const std::vector<int> &main = o.cell_parts[list[0]];
+        const int main_status = asc ? o.cell_mobility_status[list[0]] : LETHE_MOBILITY_MOBILE;
+        if (main_status == LETHE_MOBILITY_INACTIVE)
+          continue;
         if (main.empty())
           continue;
         for (size_t nb = 1; nb < list.size(); ++nb)
           {
+            if (asc && main_status == LETHE_MOBILITY_STATIC_ACTIVE && o.cell_mobility_status[list[nb]] != LETHE_MOBILITY_MOBILE)
+              continue;
             const std::vector<int> &other = o.cell_parts[list[nb]];
             for (size_t a = 0; a < main.size(); ++a)
               store_candidates(o, o.periodic_candidates, o.parts[main[a]].id, other, 0);
@@ -749,6 +918,8 @@ namespace
       {
         const lethe_wall_face &face = o.faces[f];
         if (face.cell < 0 || face.cell >= o.n_cells)
+          continue;
+        if (!o.cell_is_mobile(face.cell)) // particle_wall_broad_search.cc:239-246
           continue;
         for (int s : o.cell_parts[face.cell])
           {
@@ -775,6 +946,8 @@ namespace
         for (int cell : o.fw_cells[w])
           for (int s : o.cell_parts[cell])
             {
+              if (!o.cell_is_mobile(cell)) // particle_wall_broad_search.cc:310-317
+                continue;
               WCandRow &row = o.fwall_candidates.get_or_create(o.parts[s].id);
               bool exists = false;
               for (auto &c : row.c)
@@ -1874,8 +2047,12 @@ namespace
           {
             full_cell_neighbors(o, bt.first, cell_list);
             for (int c : cell_list)
-              for (int s : o.cell_parts[c])
-                sd.candidates[bt.second].insert(o.parts[s].id);
+              {
+                if (!o.cell_is_mobile(c)) // particle_wall_broad_search.cc:391-398
+                  continue;
+                for (int s : o.cell_parts[c])
+                  sd.candidates[bt.second].insert(o.parts[s].id);
+              }
           }
       }
   }
@@ -2164,9 +2341,16 @@ namespace
     const double dt = o.cfg.dt;
     const V3 g = mk(o.cfg.g[0], o.cfg.g[1], o.cfg.g[2]);
     const V3 half_dt_g = 0.5 * g * dt;
+    const bool asc = o.asc_active(); // velocity_verlet_integrator.cc:117-210
     for (size_t s = 0; s < o.parts.size(); ++s)
       {
         double *p = o.parts[s].p;
+        if (asc && o.cell_mobility_status[o.parts[s].cell] != LETHE_MOBILITY_MOBILE)
+          {
+            o.force[s] = mk(0, 0, 0);
+            o.torque[s] = mk(0, 0, 0);
+            continue;
+          }
         const double half_dt_mass_inverse = 0.5 * dt / p[P_MASS];
         const double half_dt_MOI_inverse = 0.5 * dt / o.MOI[s];
         for (int d = 0; d < 3; ++d)
@@ -2184,9 +2368,18 @@ namespace
     const double dt = o.cfg.dt;
     const V3 g = mk(o.cfg.g[0], o.cfg.g[1], o.cfg.g[2]);
     const V3 dt_g = g * dt;
+    // with adaptive sparse contacts (velocity_verlet_integrator.cc:292-436) only the particles of
+    // mobile cells move; the others keep position and velocity, their force and torque are dropped
+    const bool asc = o.asc_active();
     for (size_t s = 0; s < o.parts.size(); ++s)
       {
         double *p = o.parts[s].p;
+        if (asc && o.cell_mobility_status[o.parts[s].cell] != LETHE_MOBILITY_MOBILE)
+          {
+            o.force[s] = mk(0, 0, 0);
+            o.torque[s] = mk(0, 0, 0);
+            continue;
+          }
         const double dt_mass_inverse = dt / p[P_MASS];
         const double dt_MOI_inverse = dt / o.MOI[s];
         for (int d = 0; d < 3; ++d)
@@ -2241,6 +2434,7 @@ namespace
       return;
     execute_particles_displacement(o);
     sort_particles_into_subdomains_and_cells(o);
+    identify_mobility_status(o); // dem.cc:639-644
 
     find_particle_particle_contact_pairs(o);
     if (o.periodic_enabled)
@@ -2317,7 +2511,11 @@ namespace
 
   void reset_triggers(Oracle &o)
   {
-    o.contact_search_trigger = false;
+    // dem_action_manager.h:61-75: the iteration after a mobility-status reset searches again, with
+    // the statuses identified from the velocities the full step produced
+    o.contact_search_trigger = o.mobility_status_reset_trigger;
+    o.mobility_status_reset_trigger = false;
+
     o.clear_tangential_displacement_trigger = false;
     o.solid_object_search_trigger = false;
   }
@@ -2374,6 +2572,12 @@ int oracle_dem_create(const lethe_dem_config *config, int /*device*/, lethe_dem_
       g_create_error = "unknown integrator";
       return -1;
     }
+  if (config->sparse_contacts && config->integrator == LETHE_INTEGRATOR_EXPLICIT_EULER)
+    {
+      // explicit_euler_integrator.cc:157-159
+      g_create_error = "Adaptive sparse contacts are not supported with explicit Euler integrator, use Velocity Verlet integrator.";
+      return -1;
+    }
   Oracle *o = new Oracle();
   o->cfg = *config;
   o->nx = config->grid_n[0];
@@ -2388,6 +2592,8 @@ int oracle_dem_create(const lethe_dem_config *config, int /*device*/, lethe_dem_
   o->clear_tangential_displacement_trigger = false;
   o->contact_build_number = 0;
   o->n_touching_last = 0;
+  o->sparse_contacts_enabled = config->sparse_contacts != 0;
+  o->mobility_status_reset_trigger = o->sparse_contacts_enabled; // set_sparse_contacts_enabled()
   build_cell_order(*o);
   find_cell_neighbors(*o);
   find_cell_periodic_neighbors(*o);
@@ -2877,6 +3083,16 @@ int oracle_dem_get_stats(lethe_dem_ctx *ctx, lethe_dem_stats *st)
     }
   if (o->parts.empty())
     st->v_min = st->omega_min = st->ke_trans_min = st->ke_rot_min = 0;
+  return 0;
+}
+
+int oracle_dem_get_mobility_status(lethe_dem_ctx *ctx, uint64_t n_cells, int32_t *status)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  if (n_cells != uint64_t(o->n_cells))
+    return fail(o, "get_mobility_status: n_cells does not match the grid");
+  for (int c = 0; c < o->n_cells; ++c)
+    status[c] = (o->sparse_contacts_enabled && !o->cell_mobility_status.empty()) ? o->cell_mobility_status[c] : LETHE_MOBILITY_MOBILE;
   return 0;
 }
 

