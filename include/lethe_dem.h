@@ -315,6 +315,26 @@ int lethe_dem_kernel_launches(lethe_dem_ctx *ctx, uint64_t *n_launches);
  *   LETHE_DEM_HALO=nccl      per-step ghost refresh over ncclSend/ncclRecv instead of peer stores
  *   LETHE_DEM_AGREE=nccl     per-step agreement over ncclAllReduce instead of peer memory
  *   LETHE_DEM_NO_PIPELINE=1  synchronous flag check before every step (no speculative launch) */
+/* `subsection load balancing` (parameters_lagrangian.cc:960-1040,1118-1170; LagrangianLoadBalancing,
+ * load_balancing.cc:17-58; DEMSolver::load_balance, dem.cc:383-457) for the slab decomposition: at a
+ * load-balance iteration every internal cut plane moves towards the position that balances the
+ * particles-per-layer histogram (by less than the narrowest slab per event), the particles that change
+ * owner migrate with their contact history, and the contact search runs. frequency = `load balance
+ * step` (once), `frequency` (frequent) or `dynamic check frequency` (dynamic); threshold = `threshold`.
+ * dynamic_with_sparse_contacts needs adaptive sparse contacts, which run on one GPU only. */
+enum lethe_load_balance_method {
+  LETHE_LOAD_BALANCE_NONE = 0,
+  LETHE_LOAD_BALANCE_ONCE = 1,
+  LETHE_LOAD_BALANCE_FREQUENT = 2,
+  LETHE_LOAD_BALANCE_DYNAMIC = 3
+};
+int lethe_dem_set_load_balancing(lethe_dem_ctx *ctx, int method, double threshold, int frequency);
+/* Cell layers [lo, hi) along the slab axis this context owns now, and how many repartitions it has seen. */
+int lethe_dem_get_slab(lethe_dem_ctx *ctx, int32_t *lo, int32_t *hi, uint64_t *n_repartitions);
+/* The cut-plane rule on its own (host arithmetic, no device): cuts / new_cuts have world + 1 entries,
+ * cuts[0] = 0, cuts[world] = n_layers. */
+int lethe_dem_balanced_cuts(int32_t n_layers, const uint64_t *histogram, int32_t world, const int32_t *cuts,
+                            int32_t max_shift, int32_t min_width, int32_t *new_cuts);
 #define LETHE_DEM_NCCL_ID_BYTES 128
 int lethe_dem_nccl_unique_id(uint8_t id[LETHE_DEM_NCCL_ID_BYTES]);
 int lethe_dem_comm_init(lethe_dem_ctx *ctx, int rank, int world_size,

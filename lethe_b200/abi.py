@@ -163,9 +163,14 @@ ABI_SYMBOLS = [
     "kernel_launches",
     "event_record",
     "event_elapsed",
+    "set_load_balancing",
+    "get_slab",
+    "balanced_cuts",
     "nccl_unique_id",
     "comm_init",
 ]
+
+LOAD_BALANCE_METHODS = {"none": 0, "once": 1, "frequent": 2, "dynamic": 3}
 
 _p_u32 = C.POINTER(C.c_uint32)
 _p_f64 = C.POINTER(C.c_double)
@@ -415,6 +420,15 @@ class Engine:
         self._call("get_timers", C.c_int(int(reset)), C.byref(a), C.byref(na), C.byref(b), C.byref(nb))
         return {"step_kernel_ms": a.value, "step_kernel_launches": na.value, "rebuild_ms": b.value, "rebuild_launches": nb.value}
 
+    def set_load_balancing(self, method="dynamic", threshold=0.5, frequency=100):
+        self._call("set_load_balancing", C.c_int(LOAD_BALANCE_METHODS[method]), C.c_double(threshold), C.c_int(frequency))
+
+    def get_slab(self):
+        """(lo, hi, n_repartitions): the cell layers along the slab axis this context owns now."""
+        lo, hi, n = C.c_int32(), C.c_int32(), C.c_uint64()
+        self._call("get_slab", C.byref(lo), C.byref(hi), C.byref(n))
+        return lo.value, hi.value, n.value
+
     def comm_init(self, rank, world_size, nccl_id: bytes):
         buf = (C.c_uint8 * NCCL_ID_BYTES).from_buffer_copy(nccl_id)
         self._call("comm_init", C.c_int(rank), C.c_int(world_size), buf)
@@ -445,3 +459,18 @@ def nccl_unique_id() -> bytes:
     if rc != 0:
         raise DEMError("lethe_dem_nccl_unique_id failed")
     return bytes(buf)
+
+
+def balanced_cuts(histogram, cuts, max_shift, min_width=2):
+    """lethe_dem_balanced_cuts: the cut planes a load-balance step moves a slab decomposition to
+    (host arithmetic inside the CUDA library; no device needed)."""
+    lib = load_library()
+    hist = np.ascontiguousarray(histogram, dtype=np.uint64)
+    cur = np.ascontiguousarray(cuts, dtype=np.int32)
+    out = np.empty_like(cur)
+    rc = lib.lethe_dem_balanced_cuts(C.c_int32(len(hist)), hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int32(len(cur) - 1),
+                                     cur.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(max_shift), C.c_int32(min_width),
+                                     out.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise DEMError("lethe_dem_balanced_cuts: invalid arguments")
+    return out

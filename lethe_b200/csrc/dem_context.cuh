@@ -165,6 +165,12 @@ struct lethe_dem_ctx
   DevBuf<int32_t> cell_rank, cell_of_rank;
   DevBuf<uint32_t> cell_count, cell_start;
   DevBuf<uint32_t> key, slot, perm, old_of_new, counts, scan_tmp;
+  // load balancing of a slab decomposition (lethe_dem_set_load_balancing; LagrangianLoadBalancing, load_balancing.cc)
+  int lb_method = 0; // lethe_load_balance_method
+  double lb_threshold = 0.5;
+  int lb_frequency = 100000;
+  bool lb_recut_pending = false;
+  uint64_t n_recuts = 0;
   // adaptive sparse contacts (dem_kernels.cuh AscParams)
   bool asc_enabled = false;
   bool asc_reset = false;    // mobility_status_reset_trigger (dem_action_manager.h:128-134,61-75)

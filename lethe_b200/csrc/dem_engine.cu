@@ -881,6 +881,12 @@ namespace
     c->current_time += c->cfg.dt;
     const int phase = ((c->iteration_number <= 1 && !c->cfg.restart) || c->open_next_step) ? PHASE_START : PHASE_REGULAR;
     c->open_next_step = false;
+    // DEMSolver::load_balance (dem.cc:383-457): a load-balance iteration repartitions and searches
+    if (c->multi.enabled() && c->multi.load_balance_due(c))
+      {
+        c->lb_recut_pending = true;
+        c->contact_search_trigger = true;
+      }
     if (c->multi.fused() && c->pipeline)
       step_fused_multi(c, phase);
     else if (!step_speculatively(c, phase))
@@ -1827,6 +1833,36 @@ int lethe_dem_get_mobility_status(lethe_dem_ctx *c, uint64_t n_cells, int32_t *s
     for (uint64_t k = 0; k < n_cells; ++k)
       status[k] = h[k];
   });
+}
+
+int lethe_dem_set_load_balancing(lethe_dem_ctx *c, int method, double threshold, int frequency)
+{
+  return guarded(c, [&] {
+    if (method < LETHE_LOAD_BALANCE_NONE || method > LETHE_LOAD_BALANCE_DYNAMIC)
+      throw std::runtime_error("unknown load balance method (none|once|frequent|dynamic)");
+    c->lb_method = method;
+    c->lb_threshold = threshold;
+    c->lb_frequency = frequency;
+  });
+}
+
+int lethe_dem_get_slab(lethe_dem_ctx *c, int32_t *lo, int32_t *hi, uint64_t *n_repartitions)
+{
+  return guarded(c, [&] {
+    const bool slab = c->grid.slab_axis >= 0;
+    *lo = slab ? c->grid.slab_lo : 0;
+    *hi = slab ? c->grid.slab_hi : c->grid.n[0];
+    *n_repartitions = c->n_recuts;
+  });
+}
+
+int lethe_dem_balanced_cuts(int32_t n_layers, const uint64_t *histogram, int32_t world, const int32_t *cuts, int32_t max_shift,
+                            int32_t min_width, int32_t *new_cuts)
+{
+  if (n_layers < 1 || world < 1 || !histogram || !cuts || !new_cuts || n_layers < world * min_width)
+    return -1;
+  balanced_cuts(n_layers, histogram, world, cuts, max_shift, min_width, new_cuts);
+  return 0;
 }
 
 int lethe_dem_nccl_unique_id(uint8_t id[LETHE_DEM_NCCL_ID_BYTES]) { return dem::MultiGpu::unique_id(id); }

@@ -16,6 +16,7 @@
 // non-periodic vs periodic). That is what k_count/k_fill_neighbors build directly.
 #include <algorithm>
 #include <atomic>
+#include <vector>
 
 #include "dem_kernels.cuh"
 
@@ -849,10 +850,17 @@ namespace dem
       if (ca >= g.slab_lo && ca < g.slab_hi)
         return;
       const int na = g.n[a];
+      // layers below the slab's first / above its last one (periodic: the short way round)
+      int below = g.slab_lo - ca, above = ca - (g.slab_hi - 1);
+      if (g.periodic[a])
+        {
+          below = ((below % na) + na) % na;
+          above = ((above % na) + na) % na;
+        }
       int dir;
-      if (ca == g.slab_lo - 1 || (g.periodic[a] && ca == (g.slab_lo - 1 + na) % na))
+      if (below > 0 && below <= P.max_hop && (above <= 0 || below <= above))
         dir = 0;
-      else if (ca == g.slab_hi || (g.periodic[a] && ca == g.slab_hi % na))
+      else if (above > 0 && above <= P.max_hop)
         dir = 1;
       else
         {
@@ -887,6 +895,19 @@ namespace dem
       id_out[q] = ids[k];
       cell_reg[q] = -1;
       disp[q] = 0.0;
+    }
+
+    __global__ void __launch_bounds__(256) k_layer_histogram(const double4 *pos, GridDesc g, uint32_t n, uint32_t *hist)
+    {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      if (p >= n)
+        return;
+      const double4 x = pos[p];
+      const int a = g.slab_axis;
+      const double xa = a == 0 ? x.x : (a == 1 ? x.y : x.z);
+      int layer = int(floor((xa - g.lo[a]) / g.h[a]));
+      layer = min(max(layer, 0), g.n[a] - 1);
+      atomicAdd(hist + layer, 1u);
     }
 
     __global__ void __launch_bounds__(256) k_flag_layer(const int32_t *cell_reg, GridDesc g, int layer_cell, uint32_t n, uint32_t *flags)
@@ -1415,6 +1436,37 @@ namespace dem
         count_launch();
       }
   }
+  void launch_layer_histogram(const double4 *pos, GridDesc grid, uint32_t n, uint32_t *hist, cudaStream_t s)
+  {
+    if (!n)
+      return;
+    k_layer_histogram<<<(n + 255) / 256, 256, 0, s>>>(pos, grid, n, hist);
+    count_launch(1);
+  }
+
+  void balanced_cuts(int n_layers, const uint64_t *hist, int world, const int32_t *cuts, int max_shift, int min_width, int32_t *new_cuts)
+  {
+    std::vector<uint64_t> cum(size_t(n_layers) + 1, 0);
+    for (int l = 0; l < n_layers; ++l)
+      cum[l + 1] = cum[l] + hist[l];
+    const uint64_t total = cum[n_layers];
+    new_cuts[0] = 0;
+    new_cuts[world] = n_layers;
+    for (int r = 1; r < world; ++r)
+      {
+        // first layer boundary at which the particles below reach r / world of the total
+        const double target = double(total) * r / world;
+        int e = int(std::lower_bound(cum.begin(), cum.end(), target, [](uint64_t c, double t) { return double(c) < t; }) - cum.begin());
+        // pick the nearer of the two boundaries around the target
+        if (e > 0 && e <= n_layers && (target - double(cum[e - 1])) < (double(cum[std::min(e, n_layers)]) - target))
+          --e;
+        e = std::max(cuts[r] - max_shift, std::min(e, cuts[r] + max_shift));
+        e = std::max(e, new_cuts[r - 1] + min_width);
+        e = std::min(e, n_layers - min_width * (world - r));
+        new_cuts[r] = e;
+      }
+  }
+
   void launch_classify(const ClassifyParams &p, cudaStream_t s)
   {
     if (p.n)

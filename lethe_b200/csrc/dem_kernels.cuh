@@ -263,8 +263,16 @@ namespace dem
     uint32_t *send_slot[2];
     uint32_t *send_count; // [2] + [2] = far movers (error)
     uint32_t send_cap;
+    int max_hop; // cell layers a particle may lie outside the slab and still go to the adjacent rank (1; more right after a re-cut)
   };
   void launch_classify(const ClassifyParams &p, cudaStream_t s);
+  // particles per cell layer along the slab axis (load balancing): hist[layer] += 1 for every owned particle
+  void launch_layer_histogram(const double4 *pos, GridDesc grid, uint32_t n, uint32_t *hist, cudaStream_t s);
+  // New cut planes of a slab decomposition: cuts[0] = 0 < cuts[1] < ... < cuts[world] = n_layers. Every
+  // internal cut moves towards the position that balances the particle histogram, by at most
+  // max_shift layers, keeping every slab at least min_width layers wide. Pure host function (the
+  // role of p4est's weighted repartition, load_balancing.cc:9-40, for slabs).
+  void balanced_cuts(int n_layers, const uint64_t *hist, int world, const int32_t *cuts, int max_shift, int min_width, int32_t *new_cuts);
   void launch_append_records(const MigrateRecord *rec, const uint32_t *ids, uint32_t n, StateView st, uint32_t *id_out,
                              int32_t *cell_reg, double *disp, uint32_t base, cudaStream_t s);
   // flag owned particles (sorted) lying in the slab's boundary cell layer `layer` along the axis

@@ -247,6 +247,33 @@ namespace dem
     return m->flag_host[0] != 0;
   }
 
+  bool MultiGpu::load_balance_due(lethe_dem_ctx *c)
+  {
+    MultiGpuImpl *m = impl;
+    if (c->lb_method == LETHE_LOAD_BALANCE_NONE || m->world < 2)
+      return false;
+    const uint64_t it = c->iteration_number;
+    const uint64_t freq = uint64_t(std::max(1, c->lb_frequency));
+    if (c->lb_method == LETHE_LOAD_BALANCE_ONCE)
+      return it == freq; // `step` of the once method
+    if (c->lb_method == LETHE_LOAD_BALANCE_FREQUENT)
+      return (it % freq) == 0;
+    if ((it % freq) != 0)
+      return false;
+    // dynamic: (max - min) particles per rank > threshold * (local particles / ranks). The reference
+    // evaluates this with each rank's own count on the right-hand side (load_balancing.cc:44-55);
+    // here any rank that finds it true makes all of them repartition.
+    cudaStream_t s = c->stream;
+    uint32_t h[2] = {c->n_owned, ~c->n_owned};
+    CU_TRY(cudaMemcpyAsync(m->xcount.p, h, 8, cudaMemcpyHostToDevice, s));
+    NCCL_TRY(g_nccl.AllReduce(m->xcount.p, m->xcount.p, 2, ncclUint32, ncclMax, m->comm, s));
+    CU_TRY(cudaMemcpyAsync(h, m->xcount.p, 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    const uint32_t n_max = h[0], n_min = ~h[1];
+    const bool local = double(n_max - n_min) > c->lb_threshold * double(c->n_owned / uint32_t(m->world));
+    return agree(c, local);
+  }
+
   bool MultiGpu::any_rank_flag(lethe_dem_ctx *c)
   {
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -599,6 +626,46 @@ namespace dem
         }
     }
 
+    // ---- 0b. load balancing: move the cut planes towards the balanced histogram ----
+    // (the slab counterpart of triangulation.repartition() with particle weights, dem.cc:383-457).
+    // A cut moves by less than the narrowest slab, so that every particle that changes owner goes to
+    // an adjacent rank through the migration below; the contact history travels with it (the
+    // reference clears every history at a load-balance step, dem_action_manager.h:223-233).
+    int max_hop = 1;
+    if (c->lb_recut_pending)
+      {
+        c->lb_recut_pending = false;
+        const int a = c->grid.slab_axis, na = c->grid.n[a];
+        DevBuf<uint32_t> hist_dev;
+        hist_dev.ensure(size_t(na) + size_t(m->world) + 1);
+        CU_TRY(cudaMemsetAsync(hist_dev.p, 0, (size_t(na) + size_t(m->world) + 1) * 4, s));
+        launch_layer_histogram(c->st[c->cur].pos.p, c->grid, c->n_owned, hist_dev.p, s);
+        // every rank also publishes its lower cut in the slot behind the histogram
+        const uint32_t lo = uint32_t(c->grid.slab_lo);
+        CU_TRY(cudaMemcpyAsync(hist_dev.p + na + m->rank, &lo, 4, cudaMemcpyHostToDevice, s));
+        NCCL_TRY(g_nccl.AllReduce(hist_dev.p, hist_dev.p, size_t(na) + size_t(m->world), ncclUint32, ncclSum, m->comm, s));
+        std::vector<uint32_t> h(size_t(na) + size_t(m->world));
+        CU_TRY(cudaMemcpyAsync(h.data(), hist_dev.p, h.size() * 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        std::vector<uint64_t> hist(h.begin(), h.begin() + na);
+        std::vector<int32_t> cuts(size_t(m->world) + 1), new_cuts(size_t(m->world) + 1);
+        int narrowest = na;
+        for (int r = 0; r < m->world; ++r)
+          cuts[r] = int32_t(h[size_t(na) + r]);
+        cuts[m->world] = na;
+        for (int r = 0; r < m->world; ++r)
+          narrowest = std::min(narrowest, cuts[r + 1] - cuts[r]);
+        const int max_shift = std::max(0, narrowest - 2);
+        balanced_cuts(na, hist.data(), m->world, cuts.data(), max_shift, 2, new_cuts.data());
+        if (new_cuts[m->rank] != c->grid.slab_lo || new_cuts[m->rank + 1] != c->grid.slab_hi)
+          {
+            c->grid.slab_lo = new_cuts[m->rank];
+            c->grid.slab_hi = new_cuts[m->rank + 1];
+          }
+        max_hop = max_shift + 1;
+        ++c->n_recuts;
+      }
+
     // ---- 1. migration of the particles that left the slab ----
     const uint32_t n0 = c->n_owned;
     const uint32_t cap = std::max<uint32_t>(1024u, n0 / 8 + 1024u);
@@ -626,6 +693,7 @@ namespace dem
       }
     cp.send_count = m->counters.p;
     cp.send_cap = cap;
+    cp.max_hop = max_hop;
     launch_classify(cp, s);
     uint32_t hc[4] = {0, 0, 0, 0};
     CU_TRY(cudaMemcpyAsync(hc, m->counters.p, 16, cudaMemcpyDeviceToHost, s));

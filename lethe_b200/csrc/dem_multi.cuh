@@ -24,6 +24,9 @@ namespace dem
     bool any_rank_flag(lethe_dem_ctx *c);
     // logical_or over ranks of a host-side decision
     bool agree(lethe_dem_ctx *c, bool local);
+    // LagrangianLoadBalancing::check_load_balance_{once,frequent,dynamic} (load_balancing.cc:17-58) at the
+    // top of an iteration: true = this iteration repartitions (collective; same answer on every rank)
+    bool load_balance_due(lethe_dem_ctx *c);
 
     // ---- fused halo (peer-memory) mode ----
     // true once every rank has mapped its neighbours' state arrays (CUDA IPC over NVLink): the

@@ -33,6 +33,8 @@
 //   VelocityVerletIntegrator::integrate{,_start,_end} (velocity_verlet_integrator.cc:14-115,214-290)
 //   displacement accumulation of find_particle_contact_detection_step
 //     (find_contact_detection_step.cc:29-47) for the NEXT step's check.
+#include <cstdlib>
+
 #include "dem_kernels.cuh"
 
 namespace dem
@@ -696,17 +698,18 @@ namespace dem
         return;
       constexpr uint32_t per_block = 32 * STEP_WARPS;
       const dim3 block(per_block), grid((p.n_owned + per_block - 1) / per_block);
+      auto launch = [&](auto kernel) { kernel<<<grid, block, 0, stream>>>(p, mt); };
       if (p.mixed_precision)
         {
           if (p.periodic_any)
-            k_step<MODEL, ROLLING, true, true><<<grid, block, 0, stream>>>(p, mt);
+            launch(k_step<MODEL, ROLLING, true, true>);
           else
-            k_step<MODEL, ROLLING, false, true><<<grid, block, 0, stream>>>(p, mt);
+            launch(k_step<MODEL, ROLLING, false, true>);
         }
       else if (p.periodic_any)
-        k_step<MODEL, ROLLING, true, false><<<grid, block, 0, stream>>>(p, mt);
+        launch(k_step<MODEL, ROLLING, true, false>);
       else
-        k_step<MODEL, ROLLING, false, false><<<grid, block, 0, stream>>>(p, mt);
+        launch(k_step<MODEL, ROLLING, false, false>);
       count_launch();
     }
 

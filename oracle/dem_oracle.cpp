@@ -3096,6 +3096,16 @@ int oracle_dem_get_mobility_status(lethe_dem_ctx *ctx, uint64_t n_cells, int32_t
   return 0;
 }
 
+// a single domain has nothing to balance: the calls exist so that drivers run unchanged
+int oracle_dem_set_load_balancing(lethe_dem_ctx *, int, double, int) { return 0; }
+int oracle_dem_get_slab(lethe_dem_ctx *ctx, int32_t *lo, int32_t *hi, uint64_t *n_repartitions)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  *lo = 0;
+  *hi = o->nx;
+  *n_repartitions = 0;
+  return 0;
+}
 int oracle_dem_enable_timers(lethe_dem_ctx *, int) { return 0; }
 int oracle_dem_event_record(lethe_dem_ctx *, int) { return 0; }
 int oracle_dem_event_elapsed(lethe_dem_ctx *, double *ms) { *ms = 0; return 0; }

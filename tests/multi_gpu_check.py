@@ -21,11 +21,14 @@ def gather_rows(arrs, world):
     return objs
 
 
-def run_case(name, w, checkpoints, rank, world, local_rank, tol=(1e-9, 1e-6)):
+def run_case(name, w, checkpoints, rank, world, local_rank, tol=(1e-9, 1e-6), load_balance=None):
     """Slab-decomposed run vs the single-domain oracle (and, for reference, vs a single-GPU
     engine on rank 0) at several horizons: a decomposition bug shows up at the first
     checkpoint, chaotic growth of summation-order noise only at the late ones."""
     eng, n_local = multi.create_slab_engine(w, rank, world, local_rank, dist, store_forces=True, balanced=False)
+    if load_balance:
+        eng.set_load_balancing(*load_balance)
+    slab0 = eng.get_slab()
     o = single = None
     if rank == 0:
         o = loader.oracle_engine(w.params.to_config(store_forces=True))
@@ -72,8 +75,21 @@ def run_case(name, w, checkpoints, rank, world, local_rank, tol=(1e-9, 1e-6)):
                   f"pairs={len(pairs)} same_pairs={same_pairs} slab-vs-oracle dx={ex:.2e} dF={ef:.2e} dT={et:.2e} | "
                   f"1gpu-vs-oracle dx={sx_err:.2e} dF={sf_err:.2e}", flush=True)
             if k == 0:  # the bar: short horizon (trajectories are chaotic, BASELINE north_star)
-                ok &= same_pairs and ex < tol[0] and ef < tol[1] and et < tol[1] and all(r == o.get_stats().n_rebuilds for r in rebuilds)
+                # a load-balance iteration searches on top of the displacement-triggered ones (dem.cc:383-457)
+                same_rebuilds = load_balance is not None or all(r == o.get_stats().n_rebuilds for r in rebuilds)
+                ok &= same_pairs and ex < tol[0] and ef < tol[1] and et < tol[1] and same_rebuilds
         done = steps
+    if load_balance:
+        # the cuts must have moved towards the particles and evened out the load
+        slabs = gather_rows((slab0, eng.get_slab(), eng.n_particles()), world)
+        if rank == 0:
+            counts = [r[2] for r in slabs]
+            moved = any(r[0][:2] != r[1][:2] for r in slabs)
+            events = [r[1][2] for r in slabs]
+            print(f"[{name}] load balancing: slabs {[r[0][:2] for r in slabs]} -> {[r[1][:2] for r in slabs]}, particles per rank {counts}, "
+                  f"repartitions {events}", flush=True)
+            ok &= moved and min(events) >= 1 and max(counts) <= 1.5 * sum(counts) / world
+            ok &= all(slabs[r][1][1] == slabs[r + 1][1][0] for r in range(world - 1)) and slabs[0][1][0] == 0
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     return bool(flag.item())
@@ -159,6 +175,16 @@ def main():
     v, t = workloads.sheet_mesh(-0.05 * hi[0], 1.05 * hi[0], -0.05 * hi[1], 1.05 * hi[1], lambda x, y: 0.3 * hi[2] + 0.2 * x, 8)
     w.solids = [(v, t, (0.0, 0.0, 10.0), (0.0, 2.0, 0.0), (0.5 * hi[0], 0.5 * hi[1], 0.5 * hi[2]))]
     ok &= run_case("solid", w, (20, 60), rank, world, local_rank, tol=(1e-11, 1e-8))
+    # load balancing: a bed heaped against the low-x wall, equal-width slabs (the upper ranks start
+    # empty), `dynamic` method checking every 5 iterations: the cut planes follow the particles while
+    # the heap collapses, pairs and forces stay those of the single-domain oracle
+    w = workloads.box_packing(n_side=max(24, 8 * world), nz=8, spacing=1.02, jitter=0.05)
+    keep = w.x[:, 0] < 0.3 * w.params.mesh.hi[0]
+    w.ids, w.x, w.props = w.ids[keep], w.x[keep], w.props[keep]
+    w.props[:, 6:9] = np.random.default_rng(9).normal(0.0, 5.0, (w.n, 3))
+    w.params.rolling_model = "constant"
+    w.params.dynamic_contact_search_factor = 0.1
+    ok &= run_case("load-balance", w, (20, 80), rank, world, local_rank, tol=(1e-11, 1e-8), load_balance=("dynamic", 0.2, 5))
     if world == 2:
         ok &= two_processor_golden(rank, world, local_rank)
     dist.destroy_process_group()

@@ -120,3 +120,33 @@ def test_gloo_world2_slab_generation_and_forced_search_agreement(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
     assert "GLOO_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_load_balance_cut_rule():
+    """lethe_dem_balanced_cuts (host arithmetic of the load-balance step, exported by the CUDA library;
+    no device): the cuts move towards the balanced histogram, never by more than max_shift, every slab
+    keeps min_width layers, and repeated events converge to the balanced partition."""
+    from lethe_b200 import abi
+
+    rng = np.random.default_rng(4)
+    n_layers, world = 64, 4
+    # a bed that fills the first third of the axis: equal-width slabs leave ranks 2 and 3 empty
+    hist = np.zeros(n_layers, np.uint64)
+    hist[:22] = rng.integers(900, 1100, 22)
+    cuts = np.array([0, 16, 32, 48, 64], np.int32)
+    shifts = []
+    for _ in range(12):
+        widths = np.diff(cuts)
+        max_shift = int(widths.min()) - 2
+        new = abi.balanced_cuts(hist, cuts, max_shift)
+        assert new[0] == 0 and new[-1] == n_layers
+        assert np.all(np.diff(new) >= 2)
+        assert np.all(np.abs(new - cuts) <= max(max_shift, 0))
+        shifts.append(int(np.abs(new - cuts).sum()))
+        cuts = new
+    counts = [int(hist[cuts[r]:cuts[r + 1]].sum()) for r in range(world)]
+    assert max(counts) - min(counts) <= 2 * int(hist.max()), (cuts, counts)  # within one layer of particles per cut
+    assert shifts[-1] == 0  # a fixed point
+    # an already balanced partition stays where it is
+    flat = np.full(n_layers, 100, np.uint64)
+    assert np.array_equal(abi.balanced_cuts(flat, np.array([0, 16, 32, 48, 64], np.int32), 8), [0, 16, 32, 48, 64])
