@@ -272,6 +272,13 @@ int lethe_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
 int lethe_dem_step_host_state(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
                               const uint32_t *id, double *state9);
 
+/* Restart (read_checkpoint.cc:14-130: simulation_control->read(prefix) restores the iteration number
+ * and the time; DEMActionManager::restart_simulation, dem_action_manager.h:185-200, triggers the
+ * contact search and clears every tangential history): a context created with config.restart = 1
+ * and given the checkpointed particles resumes at this iteration / time with regular
+ * integrate() steps. The contact history is not part of a reference checkpoint and starts at zero. */
+int lethe_dem_set_time(lethe_dem_ctx *ctx, uint64_t iteration_number, double current_time);
+
 /* --- debug taps / statistics --- */
 /* Unordered pairs (i_id < j_id) of the contact list with the tangential
  * displacement oriented i -> j. */

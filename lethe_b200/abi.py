@@ -153,6 +153,7 @@ ABI_SYMBOLS = [
     "step_host_state",
     "set_external_loads",
     "restart_integration",
+    "set_time",
     "get_pairs",
     "get_wall_contacts",
     "get_forces",
@@ -401,6 +402,9 @@ class Engine:
         ms = C.c_double()
         self._call("event_elapsed", C.byref(ms))
         return ms.value
+
+    def set_time(self, iteration_number: int, current_time: float):
+        self._call("set_time", C.c_uint64(iteration_number), C.c_double(current_time))
 
     def get_mobility_status(self):
         """Per-cell mobility status (lexicographic cell index) as of the last contact search."""

@@ -1449,6 +1449,16 @@ int lethe_dem_synchronize_velocities(lethe_dem_ctx *c)
   });
 }
 
+int lethe_dem_set_time(lethe_dem_ctx *c, uint64_t iteration_number, double current_time)
+{
+  return guarded(c, [&] {
+    c->iteration_number = iteration_number;
+    c->current_time = current_time;
+    c->contact_search_trigger = true; // restart_simulation(): search, with every history cleared
+    c->clear_history_trigger = true;
+  });
+}
+
 int lethe_dem_restart_integration(lethe_dem_ctx *c)
 {
   c->open_next_step = true;

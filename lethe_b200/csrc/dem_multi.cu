@@ -20,8 +20,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "dem_context.cuh"
 
@@ -608,7 +610,22 @@ namespace dem
         CU_TRY(cudaEventCreate(&ev1));
         CU_TRY(cudaEventRecord(ev0, s));
       }
+    // LETHE_DEM_TRACE=1: wall-clock of every phase of this exchange (stream synchronised at each mark)
+    static const bool trace = std::getenv("LETHE_DEM_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    std::string trace_line;
+    auto mark = [&](const char *what) {
+      if (!trace)
+        return;
+      cudaStreamSynchronize(s);
+      const auto now = std::chrono::steady_clock::now();
+      char buf[64];
+      snprintf(buf, sizeof buf, " %s %.2f", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      trace_line += buf;
+      t_last = now;
+    };
     engine_upload_walls(c);
+    mark("walls");
 
     // ---- 0. the id -> slot maps must cover every id of the job (ghosts, immigrants) ----
     {
@@ -626,6 +643,7 @@ namespace dem
         }
     }
 
+    mark("idmap");
     // ---- 0b. load balancing: move the cut planes towards the balanced histogram ----
     // (the slab counterpart of triangulation.repartition() with particle weights, dem.cc:383-457).
     // A cut moves by less than the narrowest slab, so that every particle that changes owner goes to
@@ -729,6 +747,7 @@ namespace dem
     });
     NCCL_TRY(g_nccl.GroupEnd());
 
+    mark("migrate");
     // ---- 1b. the contact history of the emigrants travels with them ----
     {
       const bool use_roll = c->cfg.rolling_model == LETHE_ROLLING_EPSD;
@@ -801,10 +820,12 @@ namespace dem
         c->n_owned = uint32_t(total);
       }
 
+    mark("history");
     // ---- 2. local sort (drops the particles sent away) ----
     engine_rebuild_sort(c);
     c->first_immigrant = 0xffffffffu;
 
+    mark("sort");
     // ---- 3. ghost exchange: my boundary cell layers -> neighbours ----
     const uint32_t n = c->n_owned;
     StateBufs &sn = c->st[c->cur];
@@ -859,6 +880,7 @@ namespace dem
       exchange_halo_info(c, m, g_recv); // after the last (re)allocation of the state arrays in this rebuild
     refresh_ghosts(c); // positions / velocities of the new ghost set
 
+    mark("ghosts");
     // ---- 4. ghost cell tables + history source ----
     const size_t n_cells = size_t(c->grid.n_cells);
     StateBufs &sg = c->st[c->cur];
@@ -891,10 +913,15 @@ namespace dem
     if (c->n_ghost)
       launch_register_ids(sg.id.p, n, c->n_ghost, c->slot_of_id.p, c->slot_map_size, s);
 
+    mark("tables");
     // ---- 5. lists ----
     engine_rebuild_lists(c);
     c->n_pay = 0;
     engine_mirror_ids(c);
+    mark("lists");
+    if (trace)
+      fprintf(stderr, "[lethe_dem trace] rank %d it %llu rebuild n_owned %u n_ghost %u fused %d mailbox %d ms:%s\n", m->rank,
+              (unsigned long long)c->iteration_number, c->n_owned, c->n_ghost, int(m->fused_ready), int(m->mailbox_ready), trace_line.c_str());
     if (c->timers_enabled)
       {
         CU_TRY(cudaEventRecord(ev1, s));

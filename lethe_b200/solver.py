@@ -440,6 +440,41 @@ class DEMSolver:
         self.engine.synchronize_velocities()
         return self.engine.get_particles()
 
+    # ---- checkpoint / restart (write_checkpoint.cc:30-88, read_checkpoint.cc:14-130) ----
+    def write_checkpoint(self, prefix: str):
+        """What the reference checkpoints for a DEM run: the simulation control (time, iteration; same
+        text layout as its `<prefix>.simulationcontrol`), the particles (id, location, 9 properties) and
+        the insertion counters. deal.II serialises the particles inside the p4est triangulation file;
+        here they go to `<prefix>.particles_b200.npz`. Contact history is not checkpointed (neither does
+        the reference: a restart clears it, dem_action_manager.h:185-200)."""
+        ids, x, props = self.engine.get_particles()
+        dt = self.parameters.time_step
+        with open(prefix + ".simulationcontrol", "w") as f:
+            f.write("Simulation control\n")
+            for k in range(4):
+                f.write(f"dt_{k} {dt!r}\n")
+            f.write("CFL  0\n")
+            f.write(f"Time {self.current_time!r}\n")
+            f.write(f"Iter {self.iteration_number}\n")
+        np.savez(prefix + ".particles_b200.npz", id=ids, x=x, props=props, remaining=np.asarray(self._remaining, np.int64),
+                 next_id=np.int64(self._next_id), current_type=np.int64(self._current_type))
+
+    def read_checkpoint(self, prefix: str):
+        """Resume from write_checkpoint: needs `subsection restart / set restart = true` (the engine then
+        continues with regular integrate() steps, dem.cc:1162-1171)."""
+        if not self.parameters.restart:
+            raise abi.DEMError("read_checkpoint needs `set restart = true`")
+        with open(prefix + ".simulationcontrol") as f:
+            fields = dict(line.split() for line in f.read().splitlines()[1:] if line.strip())
+        data = np.load(prefix + ".particles_b200.npz")
+        self.current_time = float(fields["Time"])
+        self.iteration_number = int(fields["Iter"])
+        self._remaining = [int(v) for v in data["remaining"]]
+        self._next_id = int(data["next_id"])
+        self._current_type = int(data["current_type"])
+        self.engine.set_particles(data["id"], data["x"], data["props"])
+        self.engine.set_time(self.iteration_number, self.current_time)
+
     def test_output(self) -> str:
         """finish_simulation with `subsection test / enable = true` (dem.cc:760-770)."""
         ids, x, props = self.engine.get_particles()

@@ -2898,6 +2898,18 @@ int oracle_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n, const
   return 0;
 }
 
+// simulation_control->read(prefix) + DEMActionManager::restart_simulation (read_checkpoint.cc:47,
+// dem_action_manager.h:185-200)
+int oracle_dem_set_time(lethe_dem_ctx *ctx, uint64_t iteration_number, double current_time)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  o->iteration_number = iteration_number;
+  o->current_time = current_time;
+  o->contact_search_trigger = true;
+  o->clear_tangential_displacement_trigger = true;
+  return 0;
+}
+
 int oracle_dem_restart_integration(lethe_dem_ctx *ctx)
 {
   reinterpret_cast<Oracle *>(ctx)->open_next_step = true;

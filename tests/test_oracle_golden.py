@@ -685,3 +685,42 @@ def test_load_balancing_mobility_status_golden_first_block(oracle_lib):
     for got_v, gold_v in zip((vmin, vmax, vavg, wmin, wmax, wavg), block["Velocity magnitude"][:3] + block["Angular velocity magnitude"][:3]):
         assert abs(got_v - gold_v) <= 5.1e-5 * abs(gold_v) + 1e-300, (got_v, gold_v)
     assert np.array_equal(got.reshape(16, 3)[:4], want.reshape(16, 3)[:4])
+
+
+def _checkpoint_restart_run(engine_factory, tmp_path, tag):
+    """packing_in_box for 300 steps, checkpoint, 200 more steps (A); a second solver restarts from
+    the checkpoint files with `set restart = true` and runs the same 200 steps (B). Returns both
+    final states and the state at the checkpoint."""
+    import copy
+
+    p = load_prm(os.path.join(GOLDEN, "packing_in_box.prm"))
+    p.time_end = 500 * p.time_step
+    a = DEMSolver(p, engine_factory=engine_factory)
+    a.solve(max_steps=300)  # ends with the closing half kick, like a run whose time_end is here
+    prefix = str(tmp_path / f"restart_{tag}")
+    a.write_checkpoint(prefix)
+    ids_c, x_c, props_c = a.engine.get_particles()
+    pr = copy.deepcopy(p)
+    pr.restart = True
+    b = DEMSolver(pr, engine_factory=engine_factory)
+    b.read_checkpoint(prefix)
+    assert b.iteration_number == 300 and abs(b.current_time - 300 * p.time_step) < 1e-15
+    ids_b0, x_b0, props_b0 = b.engine.get_particles()
+    assert np.array_equal(ids_b0, ids_c) and np.array_equal(x_b0, x_c) and np.array_equal(props_b0, props_c)
+    out_b = b.solve()
+    assert b.iteration_number == 500
+    return (ids_c, x_c, props_c), out_b, b
+
+
+def test_checkpoint_restart_round_trip(oracle_lib, tmp_path):
+    """write_checkpoint.cc / read_checkpoint.cc semantics on the oracle: the files carry the
+    simulation control and the particles; the restarted run resumes at the checkpointed iteration with
+    regular integrate() steps (dem.cc:1162-1171), a forced contact search and empty contact
+    histories (dem_action_manager.h:185-200); the state right after reading is bit-identical to the
+    state written."""
+    (ids_c, x_c, props_c), (ids, x, props), solver = _checkpoint_restart_run(loader.oracle_engine, tmp_path, "oracle")
+    assert np.array_equal(ids, ids_c)
+    assert np.isfinite(x).all() and np.abs(x - x_c).max() > 0  # it moved on
+    with open(str(tmp_path / "restart_oracle.simulationcontrol")) as f:
+        text = f.read()
+    assert text.startswith("Simulation control\n") and "Iter 300" in text  # the reference's text layout
