@@ -215,6 +215,34 @@ def cpu_baseline_sample(args):
             "sample": f"{w.n} spheres of the same workload (same material / models / dt), {n_steps} steps after {args.cpu_settle} settling steps, single thread, g++ -O2 no FMA"}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Host side of the e2e path: run this rank on the CPU cores next to its GPU (NVML's CPU affinity of the
+    device) so that the pinned host rows it allocates afterwards are first-touched on that NUMA node and
+    the per-step copies do not cross the socket interconnect (8 ranks x 2 directions otherwise share it).
+    Returns a short description for the e2e record; never fails the run."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        index = local_rank
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            entries = [v.strip() for v in visible.split(",") if v.strip()]
+            if local_rank < len(entries) and entries[local_rank].isdigit():
+                index = int(entries[local_rank])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"rank bound to the {len(cpus)} cores NVML lists next to GPU {index}"
+        return "NVML lists no cores for this GPU: not bound"
+    except Exception as exc:  # noqa: BLE001
+        return f"not bound ({type(exc).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,6 +297,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the DEM engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -436,6 +465,7 @@ def main():
         "value": n_moved / dt, "unit": "particle-steps/s",
         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(per_step * 72), "dem_steps": e2e_steps,
         "pcie_gbs_per_direction_if_copy_bound": (h2d + per_step * 72) / world / (dt / max(1, e2e_steps)) / 1e9,
+        "host_placement": numa,
         "call": "lethe_dem_step_host_state(n_steps=1) on every rank: upload the x/v/omega rows of the owned particles (72 B each; "
                 "the id table only when ownership changed), 1 DEM step, download the rows, every DEM step",
         "batched": {"steps_per_call": S, "value": n_global * S / dtb, "unit": "particle-steps/s"},
