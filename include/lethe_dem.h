@@ -272,6 +272,20 @@ int lethe_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
 int lethe_dem_step_host_state(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
                               const uint32_t *id, double *state9);
 
+/* The CFD-DEM particle record (DEM::CFDDEMProperties::PropertiesIndex, include/core/dem_properties.h:92-142:
+ * 23 doubles per particle — the 9 DEM properties, then fem_force_two_way_coupling[3], fem_force_one_way_
+ * coupling[3], fem_drag[3], fem_torque[3], volumetric_contribution, momentum_transfer_coefficient).
+ * - lethe_dem_set_particles_cfd: lethe_dem_set_particles with rows of 23; the fluid loads of every particle
+ *   become its external loads exactly as add_fluid_particle_interaction_force / _torque add them
+ *   (cfd_dem_coupling.cc:881-925): force = (two_way + one_way) + drag per component, torque = fem_torque.
+ * - lethe_dem_update_loads_cfd: the loads alone, from rows of 23 (what changes at every CFD time step).
+ * - lethe_dem_get_particles_cfd: rows sorted by id; properties 0-8 are written, 9-22 are left as the caller
+ *   holds them (they belong to the fluid solver). */
+#define LETHE_DEM_N_CFD_PROPERTIES 23
+int lethe_dem_set_particles_cfd(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *x3, const double *props23);
+int lethe_dem_update_loads_cfd(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *props23);
+int lethe_dem_get_particles_cfd(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *x3, double *props23);
+
 /* Restart (read_checkpoint.cc:14-130: simulation_control->read(prefix) restores the iteration number
  * and the time; DEMActionManager::restart_simulation, dem_action_manager.h:185-200, triggers the
  * contact search and clears every tangential history): a context created with config.restart = 1

@@ -154,6 +154,9 @@ ABI_SYMBOLS = [
     "set_external_loads",
     "restart_integration",
     "set_time",
+    "set_particles_cfd",
+    "update_loads_cfd",
+    "get_particles_cfd",
     "get_pairs",
     "get_wall_contacts",
     "get_forces",
@@ -171,6 +174,7 @@ ABI_SYMBOLS = [
     "comm_init",
 ]
 
+N_CFD_PROPERTIES = 23
 LOAD_BALANCE_METHODS = {"none": 0, "once": 1, "frequent": 2, "dynamic": 3}
 
 _p_u32 = C.POINTER(C.c_uint32)
@@ -402,6 +406,25 @@ class Engine:
         ms = C.c_double()
         self._call("event_elapsed", C.byref(ms))
         return ms.value
+
+    # -- CFD-DEM rows of 23 properties (DEM::CFDDEMProperties) --
+    def set_particles_cfd(self, ids, x, props23):
+        ids, x, props23 = _u32(ids), _f64(x).reshape(-1, 3), _f64(props23).reshape(-1, N_CFD_PROPERTIES)
+        self._call("set_particles_cfd", C.c_uint64(len(ids)), _ptr(ids, _p_u32), _ptr(x, _p_f64), _ptr(props23, _p_f64))
+
+    def update_loads_cfd(self, ids, props23):
+        ids, props23 = _u32(ids), _f64(props23).reshape(-1, N_CFD_PROPERTIES)
+        self._call("update_loads_cfd", C.c_uint64(len(ids)), _ptr(ids, _p_u32), _ptr(props23, _p_f64))
+
+    def get_particles_cfd(self, props23):
+        """Rows sorted by id; columns 0-8 of `props23` (one row per particle, in id order) are overwritten."""
+        n = self.n_particles()
+        ids = np.empty(n, np.uint32)
+        x = np.empty((n, 3), np.float64)
+        props23 = np.ascontiguousarray(props23, dtype=np.float64).reshape(n, N_CFD_PROPERTIES).copy()
+        out = C.c_uint64()
+        self._call("get_particles_cfd", C.c_uint64(n), C.byref(out), _ptr(ids, _p_u32), _ptr(x, _p_f64), _ptr(props23, _p_f64))
+        return ids, x, props23
 
     def set_time(self, iteration_number: int, current_time: float):
         self._call("set_time", C.c_uint64(iteration_number), C.c_double(current_time))

@@ -1005,6 +1005,30 @@ namespace dem
 } // namespace dem
 
 // =================================================================== C ABI ===
+// ---- CFD-DEM rows of 23 properties (dem_properties.h:92-142) on top of the 9-property calls ----
+namespace
+{
+  void split_cfd_rows(uint64_t n, const double *props23, std::vector<double> *props9, std::vector<double> &force3, std::vector<double> &torque3)
+  {
+    if (props9)
+      props9->resize(9 * n);
+    force3.resize(3 * n);
+    torque3.resize(3 * n);
+    for (uint64_t k = 0; k < n; ++k)
+      {
+        const double *p = props23 + 23 * k;
+        if (props9)
+          std::memcpy(props9->data() + 9 * k, p, 72);
+        for (int d = 0; d < 3; ++d)
+          {
+            // add_fluid_particle_interaction_force (cfd_dem_coupling.cc:891-902): two_way + one_way + drag
+            force3[3 * k + d] = (p[9 + d] + p[12 + d]) + p[15 + d];
+            torque3[3 * k + d] = p[18 + d];
+          }
+      }
+  }
+} // namespace
+
 extern "C" {
 
 const char *lethe_dem_create_error(void) { return g_create_error.c_str(); }
@@ -1447,6 +1471,33 @@ int lethe_dem_synchronize_velocities(lethe_dem_ctx *c)
     c->asc_reset = false;
     c->clear_history_trigger = false;
   });
+}
+
+
+extern "C" int lethe_dem_set_particles_cfd(lethe_dem_ctx *c, uint64_t n, const uint32_t *id, const double *x3, const double *props23)
+{
+  std::vector<double> p9, f3, t3;
+  split_cfd_rows(n, props23, &p9, f3, t3);
+  const int rc = lethe_dem_set_particles(c, n, id, x3, p9.data());
+  return rc ? rc : lethe_dem_set_external_loads(c, n, id, f3.data(), t3.data());
+}
+
+extern "C" int lethe_dem_update_loads_cfd(lethe_dem_ctx *c, uint64_t n, const uint32_t *id, const double *props23)
+{
+  std::vector<double> f3, t3;
+  split_cfd_rows(n, props23, nullptr, f3, t3);
+  return lethe_dem_set_external_loads(c, n, id, f3.data(), t3.data());
+}
+
+extern "C" int lethe_dem_get_particles_cfd(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *x3, double *props23)
+{
+  std::vector<double> p9(9 * n_max);
+  const int rc = lethe_dem_get_particles(c, n_max, n_out, id, x3, p9.data());
+  if (rc)
+    return rc;
+  for (uint64_t k = 0; k < *n_out; ++k)
+    std::memcpy(props23 + 23 * k, p9.data() + 9 * k, 72);
+  return 0;
 }
 
 int lethe_dem_set_time(lethe_dem_ctx *c, uint64_t iteration_number, double current_time)

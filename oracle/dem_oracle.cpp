@@ -2898,6 +2898,54 @@ int oracle_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n, const
   return 0;
 }
 
+// CFD-DEM rows of 23 properties (dem_properties.h:92-142); the loads as add_fluid_particle_interaction_force /
+// _torque add them (cfd_dem_coupling.cc:881-925)
+int oracle_dem_set_particles(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *x3, const double *props9);
+int oracle_dem_set_external_loads(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *force3, const double *torque3);
+int oracle_dem_get_particles(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *x3, double *props9);
+static void split_cfd_rows(uint64_t n, const double *props23, std::vector<double> *props9, std::vector<double> &force3,
+                           std::vector<double> &torque3)
+{
+  if (props9)
+    props9->resize(9 * n);
+  force3.resize(3 * n);
+  torque3.resize(3 * n);
+  for (uint64_t k = 0; k < n; ++k)
+    {
+      const double *p = props23 + 23 * k;
+      if (props9)
+        std::memcpy(props9->data() + 9 * k, p, 72);
+      for (int d = 0; d < 3; ++d)
+        {
+          force3[3 * k + d] = (p[9 + d] + p[12 + d]) + p[15 + d];
+          torque3[3 * k + d] = p[18 + d];
+        }
+    }
+}
+int oracle_dem_set_particles_cfd(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *x3, const double *props23)
+{
+  std::vector<double> p9, f3, t3;
+  split_cfd_rows(n, props23, &p9, f3, t3);
+  const int rc = oracle_dem_set_particles(ctx, n, id, x3, p9.data());
+  return rc ? rc : oracle_dem_set_external_loads(ctx, n, id, f3.data(), t3.data());
+}
+int oracle_dem_update_loads_cfd(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *props23)
+{
+  std::vector<double> f3, t3;
+  split_cfd_rows(n, props23, nullptr, f3, t3);
+  return oracle_dem_set_external_loads(ctx, n, id, f3.data(), t3.data());
+}
+int oracle_dem_get_particles_cfd(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *x3, double *props23)
+{
+  std::vector<double> p9(9 * n_max);
+  const int rc = oracle_dem_get_particles(ctx, n_max, n_out, id, x3, p9.data());
+  if (rc)
+    return rc;
+  for (uint64_t k = 0; k < *n_out; ++k)
+    std::memcpy(props23 + 23 * k, p9.data() + 9 * k, 72);
+  return 0;
+}
+
 // simulation_control->read(prefix) + DEMActionManager::restart_simulation (read_checkpoint.cc:47,
 // dem_action_manager.h:185-200)
 int oracle_dem_set_time(lethe_dem_ctx *ctx, uint64_t iteration_number, double current_time)

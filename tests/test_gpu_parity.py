@@ -258,6 +258,39 @@ def test_cfd_dem_external_loads_parity():
     assert g.get_stats().n_rebuilds == o.get_stats().n_rebuilds
 
 
+def test_cfd_property_rows_parity():
+    """The CFD-DEM record of 23 properties (lethe_dem_set_particles_cfd / update_loads_cfd /
+    get_particles_cfd) on the CUDA engine against the oracle: two CFD time steps of 15 DEM
+    sub-iterations each with new fluid loads, in lock step at the 1e-12 bar; columns 9-22 untouched."""
+    from tests.test_oracle_golden import cfd_rows
+
+    d = 0.005
+    ids, x, props, extent = random_packing(10, d=d, spacing=0.98, jitter=0.08, poly=0.2, seed=21)
+    params = packing_parameters(extent, d=d)
+    g, o = both(params)
+    rng = np.random.default_rng(13)
+    rows = cfd_rows(props, rng, 20.0 * props[:, 2], props[:, 2] * d)
+    for e in (g, o):
+        e.set_walls(box_wall_faces(params.mesh, params.outlet_boundaries, params.periodic))
+        e.set_particles_cfd(ids, x, rows)
+    for cfd_step in range(2):
+        if cfd_step:
+            rows = cfd_rows(props, rng, 10.0 * props[:, 2], props[:, 2] * d)
+            for e in (g, o):
+                e.update_loads_cfd(ids, rows)
+        for e in (g, o):
+            e.restart_integration()
+        lockstep(g, o, 15, 0)
+        for e in (g, o):
+            e.synchronize_velocities()
+    order = np.argsort(ids)
+    ig, xg, rg = g.get_particles_cfd(rows[order])
+    io, xo, ro = o.get_particles_cfd(rows[order])
+    assert np.array_equal(ig, io) and np.array_equal(rg[:, 9:], rows[order][:, 9:])
+    assert np.abs(xg - xo).max() <= 1e-11 * np.abs(xo).max()
+    assert np.abs(rg[:, 3:9] - ro[:, 3:9]).max() <= 1e-9 * np.abs(ro[:, 3:9]).max()
+
+
 def test_explicit_euler_parity_stepwise():
     """`integration method = explicit_euler` (explicit_euler_integrator.cc): same lock-step bar."""
     d = 0.005

@@ -13,7 +13,7 @@ from lethe_b200 import abi
 from lethe_b200.prm import Mesh, load_prm
 from lethe_b200.solver import DEMSolver, box_wall_faces
 from oracle import loader
-from tests.util import GOLDEN, assert_sig6, golden, props_row, unit_test_parameters
+from tests.util import GOLDEN, assert_sig6, golden, packing_parameters, props_row, random_packing, unit_test_parameters
 
 
 def test_abi_struct_sizes(oracle_lib):
@@ -724,3 +724,51 @@ def test_checkpoint_restart_round_trip(oracle_lib, tmp_path):
     with open(str(tmp_path / "restart_oracle.simulationcontrol")) as f:
         text = f.read()
     assert text.startswith("Simulation control\n") and "Iter 300" in text  # the reference's text layout
+
+
+def cfd_rows(props9, rng, scale_f, scale_t):
+    """Rows of DEM::CFDDEMProperties (23 doubles): the 9 DEM properties + random fluid loads."""
+    n = len(props9)
+    rows = np.zeros((n, 23))
+    rows[:, :9] = props9
+    rows[:, 9:18] = rng.normal(size=(n, 9)) * scale_f[:, None]  # two-way, one-way, drag
+    rows[:, 18:21] = rng.normal(size=(n, 3)) * scale_t[:, None]  # fem_torque
+    rows[:, 21] = rng.uniform(0, 1, n)  # volumetric contribution: the fluid solver's, carried untouched
+    rows[:, 22] = rng.uniform(0, 1, n)  # momentum transfer coefficient
+    return rows
+
+
+def test_cfd_property_rows(oracle_lib):
+    """The 23-property particle record of the CFD-DEM solver (dem_properties.h:92-142) through
+    lethe_dem_set_particles_cfd / update_loads_cfd / get_particles_cfd: identical, bit for bit, to
+    feeding the 9 DEM properties and the summed loads separately — the sum taken in the reference's
+    order (two_way + one_way) + drag (cfd_dem_coupling.cc:891-902) — and columns 9-22 come back untouched."""
+    d = 0.005
+    ids, x, props, extent = random_packing(6, d=d, spacing=0.98, jitter=0.08, poly=0.2, seed=5)
+    params = packing_parameters(extent, d=d)
+    rng = np.random.default_rng(11)
+    rows = cfd_rows(props, rng, 20.0 * props[:, 2], props[:, 2] * d)
+    a, b = loader.oracle_engine(params.to_config()), loader.oracle_engine(params.to_config())
+    for e in (a, b):
+        e.set_walls(box_wall_faces(params.mesh))
+    a.set_particles_cfd(ids, x, rows)
+    b.set_particles(ids, x, props)
+    b.set_external_loads(ids, (rows[:, 9:12] + rows[:, 12:15]) + rows[:, 15:18], rows[:, 18:21])
+    for e in (a, b):
+        e.restart_integration()
+        e.step(25)
+        e.synchronize_velocities()
+    order = np.argsort(ids)
+    ia, xa, ra = a.get_particles_cfd(rows[order])
+    ib, xb, pb = b.get_particles()
+    assert np.array_equal(ia, ib) and np.array_equal(xa, xb) and np.array_equal(ra[:, :9], pb)
+    assert np.array_equal(ra[:, 9:], rows[order][:, 9:])
+    assert np.abs(xa - x[order]).max() > 0
+    # new loads for the next CFD step
+    rows2 = cfd_rows(props, rng, 10.0 * props[:, 2], props[:, 2] * d)
+    a.update_loads_cfd(ids, rows2)
+    b.set_external_loads(ids, (rows2[:, 9:12] + rows2[:, 12:15]) + rows2[:, 15:18], rows2[:, 18:21])
+    for e in (a, b):
+        e.restart_integration()
+        e.step(10)
+    assert np.array_equal(a.get_particles()[1], b.get_particles()[1])
