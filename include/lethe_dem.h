@@ -286,6 +286,35 @@ int lethe_dem_set_particles_cfd(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *
 int lethe_dem_update_loads_cfd(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *props23);
 int lethe_dem_get_particles_cfd(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *x3, double *props23);
 
+/* DEM-MP heat transfer (`solver type = dem_mp`): particle-particle conduction through the
+ * contact (calculate_contact_thermal_conductance, source/dem/particle_heat_transfer.cc:9-318, called from
+ * execute_contact_calculation, particle_particle_contact_force.h:2065-2150, for every pair with a positive
+ * overlap) and explicit temperature integration (integrate_temperature, multiphysics_integrator.cc:6-34).
+ * The two extra properties of DEM::DEMMPProperties (T = 9, specific_heat = 10, dem_properties.h:150-166) are
+ * kept per particle id. Raw per-type properties as in `subsection lagrangian physical properties`; the
+ * effective pair tables follow set_multiphysic_properties (…contact_force.h:1755-1826). Heat exchange with
+ * solid surfaces and heat sources are not built; single GPU. */
+typedef struct lethe_dem_thermal_properties {
+  double real_youngs_modulus[LETHE_DEM_MAX_TYPES];
+  double surface_roughness[LETHE_DEM_MAX_TYPES];
+  double surface_slope[LETHE_DEM_MAX_TYPES];
+  double microhardness[LETHE_DEM_MAX_TYPES];
+  double thermal_conductivity[LETHE_DEM_MAX_TYPES];
+  double thermal_accommodation[LETHE_DEM_MAX_TYPES];
+  double thermal_conductivity_gas;
+  double dynamic_viscosity_gas;
+  double specific_heat_gas;
+  double specific_heats_ratio_gas;
+  double molecular_mean_free_path_gas;
+} lethe_dem_thermal_properties;
+int lethe_dem_enable_heat_transfer(lethe_dem_ctx *ctx, const lethe_dem_thermal_properties *properties);
+/* PropertiesIndex::T and ::specific_heat of the listed particles (set at insertion by the reference). */
+int lethe_dem_set_temperatures(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *temperature,
+                               const double *specific_heat);
+/* Rows sorted by id: temperature now, and contact_outcome.heat_transfer_rate of the last step (J/s). */
+int lethe_dem_get_temperatures(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *temperature,
+                               double *heat_transfer_rate);
+
 /* Restart (read_checkpoint.cc:14-130: simulation_control->read(prefix) restores the iteration number
  * and the time; DEMActionManager::restart_simulation, dem_action_manager.h:185-200, triggers the
  * contact search and clears every tangential history): a context created with config.restart = 1

@@ -154,6 +154,9 @@ ABI_SYMBOLS = [
     "set_external_loads",
     "restart_integration",
     "set_time",
+    "enable_heat_transfer",
+    "set_temperatures",
+    "get_temperatures",
     "set_particles_cfd",
     "update_loads_cfd",
     "get_particles_cfd",
@@ -173,6 +176,24 @@ ABI_SYMBOLS = [
     "nccl_unique_id",
     "comm_init",
 ]
+
+class ThermalProperties(C.Structure):
+    """Mirror of lethe_dem_thermal_properties."""
+
+    _fields_ = [
+        ("real_youngs_modulus", C.c_double * MAX_TYPES),
+        ("surface_roughness", C.c_double * MAX_TYPES),
+        ("surface_slope", C.c_double * MAX_TYPES),
+        ("microhardness", C.c_double * MAX_TYPES),
+        ("thermal_conductivity", C.c_double * MAX_TYPES),
+        ("thermal_accommodation", C.c_double * MAX_TYPES),
+        ("thermal_conductivity_gas", C.c_double),
+        ("dynamic_viscosity_gas", C.c_double),
+        ("specific_heat_gas", C.c_double),
+        ("specific_heats_ratio_gas", C.c_double),
+        ("molecular_mean_free_path_gas", C.c_double),
+    ]
+
 
 N_CFD_PROPERTIES = 23
 LOAD_BALANCE_METHODS = {"none": 0, "once": 1, "frequent": 2, "dynamic": 3}
@@ -425,6 +446,23 @@ class Engine:
         out = C.c_uint64()
         self._call("get_particles_cfd", C.c_uint64(n), C.byref(out), _ptr(ids, _p_u32), _ptr(x, _p_f64), _ptr(props23, _p_f64))
         return ids, x, props23
+
+    # -- DEM-MP heat transfer --
+    def enable_heat_transfer(self, properties: "ThermalProperties"):
+        self._call("enable_heat_transfer", C.byref(properties))
+
+    def set_temperatures(self, ids, temperature, specific_heat):
+        ids, temperature, specific_heat = _u32(ids), _f64(temperature), _f64(specific_heat)
+        assert len(ids) == len(temperature) == len(specific_heat)
+        self._call("set_temperatures", C.c_uint64(len(ids)), _ptr(ids, _p_u32), _ptr(temperature, _p_f64), _ptr(specific_heat, _p_f64))
+
+    def get_temperatures(self):
+        """(ids, temperature, heat transfer rate of the last step), rows sorted by id."""
+        n = self.n_particles()
+        ids, temp, rate = np.empty(n, np.uint32), np.empty(n, np.float64), np.empty(n, np.float64)
+        out = C.c_uint64()
+        self._call("get_temperatures", C.c_uint64(n), C.byref(out), _ptr(ids, _p_u32), _ptr(temp, _p_f64), _ptr(rate, _p_f64))
+        return ids[: out.value], temp[: out.value], rate[: out.value]
 
     def set_time(self, iteration_number: int, current_time: float):
         self._call("set_time", C.c_uint64(iteration_number), C.c_double(current_time))

@@ -171,6 +171,11 @@ struct lethe_dem_ctx
   int lb_frequency = 100000;
   bool lb_recut_pending = false;
   uint64_t n_recuts = 0;
+  // DEM-MP heat transfer (dem_kernels.cuh HeatParams): temperature / specific heat per particle id, rate per row
+  bool thermal_enabled = false;
+  dem::ThermalTables thermal_tables;
+  DevBuf<double> temperature, specific_heat, heat_rate;
+  size_t thermal_size = 0; // ids covered by temperature / specific_heat
   // adaptive sparse contacts (dem_kernels.cuh AscParams)
   bool asc_enabled = false;
   bool asc_reset = false;    // mobility_status_reset_trigger (dem_action_manager.h:128-134,61-75)

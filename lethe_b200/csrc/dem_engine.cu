@@ -625,6 +625,32 @@ namespace
   // non-zero tag of a step: what its kernel leaves in the trigger flag
   inline uint32_t step_tag(uint64_t iteration) { return uint32_t(iteration % 0x7fffffffull) + 1u; }
 
+  // DEM-MP: heat rates of this step's contacts and the temperature step (dem.cc:1134-1153), on the state and the
+  // list the step kernel is about to read
+  void heat_transfer_step(Ctx *c)
+  {
+    if (!c->thermal_enabled || !c->n_owned)
+      return;
+    cudaStream_t s = c->stream;
+    if (c->thermal_size < c->slot_map_size)
+      throw std::runtime_error("heat transfer: lethe_dem_set_temperatures has not covered every particle id");
+    c->heat_rate.ensure(c->n_owned);
+    HeatParams hp;
+    hp.in = c->st[c->cur].view();
+    hp.list = c->lists[c->cur_list].view();
+    hp.id = c->st[c->cur].id.p;
+    hp.n_owned = c->n_owned;
+    hp.periodic_any = c->grid.periodic[0] || c->grid.periodic[1] || c->grid.periodic[2];
+    hp.dt = c->cfg.dt;
+    for (int d = 0; d < 3; ++d)
+      hp.L[d] = c->grid.L[d];
+    hp.temperature = c->temperature.p;
+    hp.specific_heat = c->specific_heat.p;
+    hp.rate = c->heat_rate.p;
+    launch_heat_rates(c->cfg.pp_model, hp, c->mt, c->thermal_tables, s);
+    launch_integrate_temperature(hp, s);
+  }
+
   void launch_step_kernel(Ctx *c, int phase, bool speculative = false)
   {
     cudaStream_t s = c->stream;
@@ -816,7 +842,7 @@ namespace
   // host's flag read; the sequence of kernels that DO something is exactly the unpipelined one.
   bool step_speculatively(Ctx *c, int phase)
   {
-    if (!c->pipeline || c->multi.enabled() || c->contact_search_trigger || c->cfg.detection != LETHE_DETECTION_DYNAMIC)
+    if (!c->pipeline || c->multi.enabled() || c->contact_search_trigger || c->cfg.detection != LETHE_DETECTION_DYNAMIC || c->thermal_enabled)
       return false;
     const uint64_t freq = uint64_t(std::max(1, c->cfg.contact_detection_frequency));
     if ((c->iteration_number % freq) != 0 || phase != PHASE_REGULAR)
@@ -892,6 +918,7 @@ namespace
     else if (!step_speculatively(c, phase))
       {
         contact_detection_and_search(c);
+        heat_transfer_step(c);
         launch_step_kernel(c, phase);
       }
     // reset_triggers (dem_action_manager.h:61-75): the iteration after a mobility-status reset
@@ -1498,6 +1525,99 @@ extern "C" int lethe_dem_get_particles_cfd(lethe_dem_ctx *c, uint64_t n_max, uin
   for (uint64_t k = 0; k < *n_out; ++k)
     std::memcpy(props23 + 23 * k, p9.data() + 9 * k, 72);
   return 0;
+}
+
+int lethe_dem_enable_heat_transfer(lethe_dem_ctx *c, const lethe_dem_thermal_properties *pr)
+{
+  return guarded(c, [&] {
+    if (c->multi.enabled())
+      throw std::runtime_error("heat transfer runs on a single GPU (ghost temperatures are not exchanged)");
+    const int n = c->cfg.n_types;
+    ThermalTables &t = c->thermal_tables;
+    std::memset(&t, 0, sizeof(t));
+    t.conductivity_gas = pr->thermal_conductivity_gas;
+    // set_multiphysic_properties (particle_particle_contact_force.h:1755-1826)
+    for (int i = 0; i < n; ++i)
+      {
+        const double real_youngs_modulus_i = pr->real_youngs_modulus[i], poisson_ratio_i = c->cfg.poisson[i];
+        const double surface_roughness_i = pr->surface_roughness[i], surface_slope_i = pr->surface_slope[i];
+        const double microhardness_i = pr->microhardness[i], thermal_accommodation_i = pr->thermal_accommodation[i];
+        t.conductivity[i] = pr->thermal_conductivity[i];
+        for (int j = 0; j < n; ++j)
+          {
+            const int k = i * n + j;
+            const double real_youngs_modulus_j = pr->real_youngs_modulus[j], poisson_ratio_j = c->cfg.poisson[j];
+            const double surface_roughness_j = pr->surface_roughness[j], surface_slope_j = pr->surface_slope[j];
+            const double microhardness_j = pr->microhardness[j], thermal_accommodation_j = pr->thermal_accommodation[j];
+            t.real_E[k] = (real_youngs_modulus_i * real_youngs_modulus_j) /
+                          ((real_youngs_modulus_j * (1.0 - poisson_ratio_i * poisson_ratio_i)) +
+                           (real_youngs_modulus_i * (1.0 - poisson_ratio_j * poisson_ratio_j)) + DBL_MIN);
+            t.roughness[k] = std::sqrt(surface_roughness_i * surface_roughness_i + surface_roughness_j * surface_roughness_j);
+            t.slope[k] = std::sqrt(surface_slope_i * surface_slope_i + surface_slope_j * surface_slope_j);
+            t.microhardness[k] = (2 * microhardness_i * microhardness_j / (microhardness_i + microhardness_j + DBL_MIN));
+            t.gas_m[k] = ((2. - thermal_accommodation_i) / thermal_accommodation_i + (2. - thermal_accommodation_j) / thermal_accommodation_j) *
+                         (2. * pr->specific_heats_ratio_gas) / (1. + pr->specific_heats_ratio_gas) * pr->molecular_mean_free_path_gas /
+                         (pr->dynamic_viscosity_gas * pr->specific_heat_gas / pr->thermal_conductivity_gas);
+          }
+      }
+    c->thermal_enabled = true;
+  });
+}
+
+int lethe_dem_set_temperatures(lethe_dem_ctx *c, uint64_t n, const uint32_t *id, const double *temperature, const double *specific_heat)
+{
+  return guarded(c, [&] {
+    cudaStream_t s = c->stream;
+    CU_TRY(cudaStreamSynchronize(s));
+    size_t need = c->thermal_size;
+    for (uint64_t k = 0; k < n; ++k)
+      need = std::max<size_t>(need, size_t(id[k]) + 1);
+    std::vector<double> ht(need, 0.), hc(need, 1.);
+    if (c->thermal_size)
+      {
+        CU_TRY(cudaMemcpy(ht.data(), c->temperature.p, c->thermal_size * 8, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(hc.data(), c->specific_heat.p, c->thermal_size * 8, cudaMemcpyDeviceToHost));
+      }
+    for (uint64_t k = 0; k < n; ++k)
+      {
+        ht[id[k]] = temperature[k];
+        hc[id[k]] = specific_heat[k];
+      }
+    c->temperature.ensure(need);
+    c->specific_heat.ensure(need);
+    CU_TRY(cudaMemcpy(c->temperature.p, ht.data(), need * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(c->specific_heat.p, hc.data(), need * 8, cudaMemcpyHostToDevice));
+    c->thermal_size = need;
+  });
+}
+
+int lethe_dem_get_temperatures(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *temperature, double *heat_transfer_rate)
+{
+  return guarded(c, [&] {
+    cudaStream_t s = c->stream;
+    CU_TRY(cudaStreamSynchronize(s));
+    const size_t n = c->n_owned;
+    std::vector<uint32_t> hid(n);
+    std::vector<double> ht(c->thermal_size), hr(n, 0.);
+    if (n)
+      CU_TRY(cudaMemcpy(hid.data(), c->st[c->cur].id.p, n * 4, cudaMemcpyDeviceToHost));
+    if (c->thermal_size)
+      CU_TRY(cudaMemcpy(ht.data(), c->temperature.p, c->thermal_size * 8, cudaMemcpyDeviceToHost));
+    if (n && c->heat_rate.cap >= n)
+      CU_TRY(cudaMemcpy(hr.data(), c->heat_rate.p, n * 8, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hid[a] < hid[b]; });
+    const uint64_t m = std::min<uint64_t>(n_max, n);
+    for (uint64_t k = 0; k < m; ++k)
+      {
+        const uint32_t q = order[k];
+        id[k] = hid[q];
+        temperature[k] = hid[q] < ht.size() ? ht[hid[q]] : 0.;
+        heat_transfer_rate[k] = hr[q];
+      }
+    *n_out = m;
+  });
 }
 
 int lethe_dem_set_time(lethe_dem_ctx *c, uint64_t iteration_number, double current_time)

@@ -162,6 +162,32 @@ namespace dem
 
   void launch_step(int pp_model, int rolling_model, const StepParams &p, const MaterialTables &mt, cudaStream_t stream);
 
+  // ---- DEM-MP heat transfer (particle_heat_transfer.cc, multiphysics_integrator.cc) ----
+  // effective pair tables of set_multiphysic_properties (particle_particle_contact_force.h:1755-1826)
+  struct ThermalTables
+  {
+    double real_E[25], roughness[25], slope[25], microhardness[25], gas_m[25];
+    double conductivity[5];
+    double conductivity_gas;
+  };
+  struct HeatParams
+  {
+    StateView in;
+    ListView list;
+    const uint32_t *id;
+    uint32_t n_owned;
+    int periodic_any;
+    double dt;
+    double L[3];
+    double *temperature;         // per particle id
+    const double *specific_heat; // per particle id
+    double *rate;                // per row: contact_outcome.heat_transfer_rate
+  };
+  // per row: conduction through every contact with a positive overlap, summed in list order
+  void launch_heat_rates(int pp_model, const HeatParams &p, const MaterialTables &mt, const ThermalTables &th, cudaStream_t stream);
+  // integrate_temperature with a zero heat source
+  void launch_integrate_temperature(const HeatParams &p, cudaStream_t stream);
+
   // ---- rebuild ----
   struct BinParams
   {

@@ -167,6 +167,8 @@ namespace dem
       throw std::runtime_error("every slab needs at least 2 cell layers");
     if (impl)
       throw std::runtime_error("communicator already initialised");
+    if (c->thermal_enabled)
+      throw std::runtime_error("heat transfer runs on a single GPU (ghost temperatures are not exchanged)");
     if (c->asc_enabled)
       throw std::runtime_error("adaptive sparse contacts run on a single GPU: the node-based mobility status is not exchanged across slabs");
     MultiGpuImpl *m = new MultiGpuImpl();

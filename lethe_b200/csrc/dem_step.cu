@@ -736,6 +736,212 @@ namespace dem
 
   // Runtime -> template dispatch, the same pattern as set_particle_particle_contact_force_model
   // / set_rolling_resistance_model (set_particle_particle_contact_force_model.cc:12-103).
+  // ------------------------------------------------------------ DEM-MP heat transfer ----
+  namespace
+  {
+    // particle_heat_transfer.cc:9-146
+    __device__ __forceinline__ double th_harmonic_mean(double a, double b) { return (2 * a * b / (a + b + DBL_MIN)); }
+    __device__ __forceinline__ double th_corrected_contact_radius(double effective_radius, double effective_youngs_modulus,
+                                                                  double effective_real_youngs_modulus, double normal_force_norm)
+    {
+      const double contact_radius = pow((3 * normal_force_norm * effective_radius) / (4 * effective_youngs_modulus), (1.0 / 3.0));
+      return contact_radius * pow(effective_youngs_modulus / effective_real_youngs_modulus, 1.0 / 5.0);
+    }
+    __device__ __forceinline__ double th_macrocontact(double harmonic_conductivity, double contact_radius)
+    {
+      return 0.5 / (contact_radius * harmonic_conductivity + DBL_MIN);
+    }
+    __device__ __forceinline__ double th_microcontact(double slope, double roughness, double microhardness, double contact_radius_squared,
+                                                      double harmonic_conductivity, double maximum_pressure)
+    {
+      return 1.184 / (M_PI * harmonic_conductivity * contact_radius_squared) * (roughness / slope) *
+             pow(microhardness / (maximum_pressure + DBL_MIN), 0.96);
+    }
+    __device__ __forceinline__ double th_solid_macrogap(double radius, double thermal_conductivity, double contact_radius_squared)
+    {
+      return 0.25 * M_PI * radius / (M_PI * (radius * radius - contact_radius_squared) * thermal_conductivity);
+    }
+    __device__ __forceinline__ double th_gas_microgap(double roughness, double contact_radius_squared, double gas_parameter_m,
+                                                      double thermal_conductivity_gas, double maximum_pressure, double microhardness)
+    {
+      const double x_1 = 2.0 * maximum_pressure / microhardness;
+      const double x_2 = 0.03 * maximum_pressure / microhardness;
+      if (x_1 >= 2.0 || x_1 <= 0.0)
+        return INFINITY;
+      const double a_1 = erfcinv(x_1); // boost::math::erfc_inv
+      const double a_2 = erfcinv(x_2) - a_1;
+      return (2.82842712475 * roughness * a_2) /
+             (M_PI * thermal_conductivity_gas * contact_radius_squared * log(fabs(1 + a_2 / (a_1 + gas_parameter_m / (2.82842712475 * roughness)))));
+    }
+    __device__ __forceinline__ double th_gas_macrogap(double harmonic_radius, double thermal_conductivity_gas, double contact_radius_squared,
+                                                      double gas_parameter_m)
+    {
+      const double A = 2. * sqrt(harmonic_radius * harmonic_radius - contact_radius_squared);
+      const double S = 2. * harmonic_radius - contact_radius_squared / harmonic_radius + gas_parameter_m;
+      return 2.0 / (M_PI * thermal_conductivity_gas * (S * log(S / (S - A)) - A));
+    }
+    // calculate_contact_thermal_conductance<particle-particle> (particle_heat_transfer.cc:148-318)
+    __device__ double th_contact_conductance(double radius_one, double radius_two, double effective_youngs_modulus, double effective_real_youngs_modulus,
+                                             double roughness, double slope, double microhardness, double thermal_conductivity_one,
+                                             double thermal_conductivity_two, double thermal_conductivity_gas, double gas_parameter_m,
+                                             double normal_overlap, double normal_force_norm)
+    {
+      const double harmonic_conductivity = th_harmonic_mean(thermal_conductivity_one, thermal_conductivity_two);
+      const double harmonic_radius = th_harmonic_mean(radius_one, radius_two);
+      const double contact_radius =
+        th_corrected_contact_radius(harmonic_radius * 0.5, effective_youngs_modulus, effective_real_youngs_modulus, normal_force_norm);
+      const double corrected_normal_overlap = normal_overlap * pow(effective_youngs_modulus / effective_real_youngs_modulus, 2.0 / 3.0);
+      const double contact_radius_squared = contact_radius * contact_radius;
+      const double maximum_pressure = (2.0 * effective_real_youngs_modulus * corrected_normal_overlap) / (M_PI * contact_radius + DBL_MIN);
+      const double resistance_macrocontact = th_macrocontact(harmonic_conductivity, contact_radius);
+      const double resistance_microcontact =
+        th_microcontact(slope, roughness, microhardness, contact_radius_squared, harmonic_conductivity, maximum_pressure);
+      double resistance_solid_macrogap = th_solid_macrogap(radius_one, thermal_conductivity_one, contact_radius_squared);
+      resistance_solid_macrogap += th_solid_macrogap(radius_two, thermal_conductivity_two, contact_radius_squared);
+      const double resistance_gas_microgap =
+        th_gas_microgap(roughness, contact_radius_squared, gas_parameter_m, thermal_conductivity_gas, maximum_pressure, microhardness);
+      const double resistance_gas_macrogap = th_gas_macrogap(harmonic_radius, thermal_conductivity_gas, contact_radius_squared, gas_parameter_m);
+      return 1.0 / (resistance_macrocontact + 1.0 / (1.0 / resistance_microcontact + 1.0 / resistance_gas_microgap)) +
+             1.0 / (resistance_solid_macrogap + resistance_gas_macrogap);
+    }
+
+    // One thread per row: the normal force of every touching pair is re-evaluated with the contact model of the step kernel
+    // (it depends on positions and velocities only, not on the history), in the pair's canonical orientation, so both
+    // owners of a pair get exactly opposite rates.
+    template <int MODEL, bool PERIODIC>
+    __global__ void __launch_bounds__(128) k_heat_rates(const __grid_constant__ HeatParams P, const __grid_constant__ MaterialTables mt,
+                                                         const __grid_constant__ ThermalTables th)
+    {
+      const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= P.n_owned)
+        return;
+      const double4 pme = P.in.pos[i];
+      const ParticleView me = make_view(pme, P.in.vel[i], P.in.omg[i]);
+      const double temperature_me = P.temperature[P.id[i]];
+      double rate = 0.0;
+      for (uint32_t e = P.list.row_start[i]; e < P.list.row_start[i + 1]; ++e)
+        {
+          const uint32_t j = P.list.col[e] & COL_INDEX_MASK;
+          const double4 pj = P.in.pos[j];
+          vec3 x1, x2;
+          double dsum;
+          bool i_am_two = false;
+          if constexpr (PERIODIC)
+            {
+              const uint32_t img = P.list.img[e];
+              if (img)
+                {
+                  vec3 shift;
+                  decode_image(img, P.L, shift, i_am_two);
+                  if (!i_am_two)
+                    {
+                      x1 = v3(pme.x, pme.y, pme.z);
+                      x2 = v3(pj.x, pj.y, pj.z) + shift;
+                    }
+                  else
+                    {
+                      x1 = v3(pj.x, pj.y, pj.z);
+                      x2 = v3(pme.x, pme.y, pme.z) + (-shift);
+                    }
+                }
+              else
+                {
+                  x1 = v3(pme.x, pme.y, pme.z);
+                  x2 = v3(pj.x, pj.y, pj.z);
+                }
+            }
+          else
+            {
+              x1 = v3(pme.x, pme.y, pme.z);
+              x2 = v3(pj.x, pj.y, pj.z);
+            }
+          dsum = i_am_two ? pj.w + pme.w : pme.w + pj.w;
+          const double distance = sqrt(dist2(x1, x2));
+          const double normal_overlap = 0.5 * dsum - distance;
+          if (!(normal_overlap > mt.pp_force_threshold) || !(normal_overlap > 0))
+            continue;
+          const ParticleView other = make_view(pj, P.in.vel[j], P.in.omg[j]);
+          ParticleView one = i_am_two ? other : me, two = i_am_two ? me : other;
+          one.x = x1;
+          // R* and m* of two copies of particle one: what the model's equal-size shortcut reads (bit-identical to the general branch)
+          const SelfPair sp{(one.d * one.d) / (2 * (one.d + one.d)), (one.m * one.m) / (one.m + one.m)};
+          vec3 h = v3(0, 0, 0), rs = v3(0, 0, 0), n, vt;
+          double vn;
+          PairResult r;
+          r.normal_force = r.tangential_force = r.torque_one = r.torque_two = r.rolling = v3(0, 0, 0);
+          pp_update_contact_information<double>(h, vt, vn, n, one, two, x2, distance, P.dt);
+          pp_calculate_contact<MODEL, LETHE_ROLLING_NONE, double>(mt, h, rs, vt, vn, n, normal_overlap, P.dt, one, two, r, sp);
+          const int k = one.type * mt.n_types + two.type;
+          const double conductance =
+            th_contact_conductance(0.5 * one.d, 0.5 * two.d, mt.Y[k], th.real_E[k], th.roughness[k], th.slope[k], th.microhardness[k],
+                                   th.conductivity[one.type], th.conductivity[two.type], th.conductivity_gas, th.gas_m[k], normal_overlap,
+                                   norm(r.normal_force));
+          // apply_heat_transfer_on_local_particles (particle_heat_transfer.cc:320-331): one gains G (T2 - T1), two loses it
+          const double temperature_other = P.temperature[P.id[j]];
+          const double t_one = i_am_two ? temperature_other : temperature_me, t_two = i_am_two ? temperature_me : temperature_other;
+          const double heat_transfer_rate = conductance * (t_two - t_one);
+          rate = i_am_two ? rate - heat_transfer_rate : rate + heat_transfer_rate;
+        }
+      P.rate[i] = rate;
+    }
+
+    __global__ void __launch_bounds__(256) k_integrate_temperature(const __grid_constant__ HeatParams P)
+    {
+      const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= P.n_owned)
+        return;
+      const uint32_t id = P.id[i];
+      const double mass_inverse = 1 / P.in.vel[i].w;
+      const double specific_heat_inverse = 1 / P.specific_heat[id];
+      P.temperature[id] = P.temperature[id] + P.dt * (P.rate[i] + 0.0) * mass_inverse * specific_heat_inverse;
+    }
+
+    template <int MODEL> void launch_heat_m(const HeatParams &p, const MaterialTables &mt, const ThermalTables &th, cudaStream_t stream)
+    {
+      const unsigned blocks = (p.n_owned + 127) / 128;
+      if (p.periodic_any)
+        k_heat_rates<MODEL, true><<<blocks, 128, 0, stream>>>(p, mt, th);
+      else
+        k_heat_rates<MODEL, false><<<blocks, 128, 0, stream>>>(p, mt, th);
+      count_launch();
+    }
+  } // namespace
+
+  void launch_heat_rates(int pp_model, const HeatParams &p, const MaterialTables &mt, const ThermalTables &th, cudaStream_t stream)
+  {
+    if (p.n_owned == 0)
+      return;
+    switch (pp_model)
+      {
+        case LETHE_PP_LINEAR:
+          launch_heat_m<LETHE_PP_LINEAR>(p, mt, th, stream);
+          break;
+        case LETHE_PP_HERTZ_MINDLIN_LIMIT_FORCE:
+          launch_heat_m<LETHE_PP_HERTZ_MINDLIN_LIMIT_FORCE>(p, mt, th, stream);
+          break;
+        case LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP:
+          launch_heat_m<LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP>(p, mt, th, stream);
+          break;
+        case LETHE_PP_HERTZ:
+          launch_heat_m<LETHE_PP_HERTZ>(p, mt, th, stream);
+          break;
+        case LETHE_PP_HERTZ_JKR:
+          launch_heat_m<LETHE_PP_HERTZ_JKR>(p, mt, th, stream);
+          break;
+        default:
+          launch_heat_m<LETHE_PP_DMT>(p, mt, th, stream);
+          break;
+      }
+  }
+
+  void launch_integrate_temperature(const HeatParams &p, cudaStream_t stream)
+  {
+    if (p.n_owned == 0)
+      return;
+    k_integrate_temperature<<<(p.n_owned + 255) / 256, 256, 0, stream>>>(p);
+    count_launch();
+  }
+
   void launch_step(int pp_model, int rolling_model, const StepParams &p, const MaterialTables &mt, cudaStream_t stream)
   {
     switch (pp_model)

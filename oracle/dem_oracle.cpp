@@ -271,6 +271,15 @@ namespace
     // reference defect switch, see pp_execute_contact_calculation
     bool dmt_stale_scratch = true;
 
+    // DEM-MP heat transfer (particle_heat_transfer.cc, multiphysics_integrator.cc)
+    bool thermal_enabled = false;
+    std::vector<double> th_real_E, th_roughness, th_slope, th_microhardness, th_gas_m; // n_types^2
+    std::vector<double> th_conductivity;                                              // n_types
+    double th_conductivity_gas = 0;
+    std::vector<double> temperature, specific_heat; // per particle id
+    std::vector<double> heat_transfer_rate;         // per local index (contact_outcome.heat_transfer_rate)
+    std::vector<double> last_heat_transfer_rate;
+
     // adaptive sparse contacts (AdaptiveSparseContacts, adaptive_sparse_contacts.h)
     bool sparse_contacts_enabled = false;
     bool mobility_status_reset_trigger = false; // dem_action_manager.h:128-134
@@ -685,6 +694,7 @@ namespace
         o.MOI[s] = o.cfg.moi_override > 0 ? o.cfg.moi_override : 0.1 * p[P_MASS] * p[P_DP] * p[P_DP];
       }
     o.displacement.assign(n, 0.);
+    o.heat_transfer_rate.assign(n, 0.); // resize_interaction_containers
   }
 
   // update_particle_container (update_local_particle_containers.cc:11-38)
@@ -1458,6 +1468,114 @@ namespace
   }
 
   // execute_contact_calculation<local / local_periodic> (…contact_force.h:1838-2063)
+  // ---------------------------------------------------------- heat transfer ----
+
+  // boost::math::erfc_inv restated: Newton on glibc's erfc, to the last bits of double
+  double erfc_inv(double y)
+  {
+    // start value from the asymptotic / series form, then Newton: f = erfc(x) - y, f' = -2/sqrt(pi) exp(-x^2)
+    double x;
+    if (y >= 1.0)
+      x = -std::sqrt(std::fabs(std::log((2.0 - y) * 0.8862269254527580136)));
+    else
+      x = std::sqrt(std::fabs(std::log(y * 0.8862269254527580136 + 1e-300)));
+    if (y > 0.25 && y < 1.75)
+      x = (1.0 - y) * 0.8862269254527580136;
+    for (int it = 0; it < 60; ++it)
+      {
+        const double f = std::erfc(x) - y;
+        const double dfdx = -1.1283791670955125739 * std::exp(-x * x);
+        const double step = f / dfdx;
+        x -= step;
+        if (std::fabs(step) <= 1e-17 * std::fabs(x))
+          break;
+      }
+    return x;
+  }
+
+  // particle_heat_transfer.cc:9-146
+  double calculate_corrected_contact_radius(double effective_radius, double effective_youngs_modulus, double effective_real_youngs_modulus,
+                                            double normal_force_norm)
+  {
+    const double contact_radius = std::pow((3 * normal_force_norm * effective_radius) / (4 * effective_youngs_modulus), (1.0 / 3.0));
+    return contact_radius * std::pow(effective_youngs_modulus / effective_real_youngs_modulus, 1.0 / 5.0);
+  }
+  double calculate_macrocontact_resistance(double harmonic_conductivity, double contact_radius)
+  {
+    return 0.5 / (contact_radius * harmonic_conductivity + DBL_MIN);
+  }
+  double calculate_microcontact_resistance(double equivalent_surface_slope, double equivalent_surface_roughness, double effective_microhardness,
+                                           double contact_radius_squared, double harmonic_conductivity, double maximum_pressure)
+  {
+    return 1.184 / (M_PI * harmonic_conductivity * contact_radius_squared) * (equivalent_surface_roughness / equivalent_surface_slope) *
+           std::pow(effective_microhardness / (maximum_pressure + DBL_MIN), 0.96);
+  }
+  double calculate_solid_macrogap_resistance(double radius, double thermal_conductivity, double contact_radius_squared)
+  {
+    return 0.25 * M_PI * radius / (M_PI * (radius * radius - contact_radius_squared) * thermal_conductivity);
+  }
+  double calculate_interstitial_gas_microgap_resistance(double equivalent_surface_roughness, double contact_radius_squared, double gas_parameter_m,
+                                                        double thermal_conductivity_gas, double maximum_pressure, double effective_microhardness)
+  {
+    const double x_1 = 2.0 * maximum_pressure / effective_microhardness;
+    const double x_2 = 0.03 * maximum_pressure / effective_microhardness;
+    if (x_1 >= 2.0 || x_1 <= 0.0)
+      return INFINITY;
+    const double a_1 = erfc_inv(x_1);
+    const double a_2 = erfc_inv(x_2) - a_1;
+    return (2.82842712475 * equivalent_surface_roughness * a_2) /
+           (M_PI * thermal_conductivity_gas * contact_radius_squared *
+            std::log(std::abs(1 + a_2 / (a_1 + gas_parameter_m / (2.82842712475 * equivalent_surface_roughness)))));
+  }
+  double calculate_interstitial_gas_macrogap_resistance(double harmonic_radius, double thermal_conductivity_gas, double contact_radius_squared,
+                                                        double gas_parameter_m)
+  {
+    const double A = 2. * std::sqrt(harmonic_radius * harmonic_radius - contact_radius_squared);
+    const double S = 2. * harmonic_radius - contact_radius_squared / harmonic_radius + gas_parameter_m;
+    return 2.0 / (M_PI * thermal_conductivity_gas * (S * std::log(S / (S - A)) - A));
+  }
+  // calculate_contact_thermal_conductance<particle-particle> (particle_heat_transfer.cc:148-318); `parts` receives the
+  // intermediate values the reference's unit test prints
+  double calculate_contact_thermal_conductance(double radius_one, double radius_two, double effective_youngs_modulus,
+                                               double effective_real_youngs_modulus, double equivalent_surface_roughness,
+                                               double equivalent_surface_slope, double effective_microhardness, double thermal_conductivity_one,
+                                               double thermal_conductivity_two, double thermal_conductivity_gas, double gas_parameter_m,
+                                               double normal_overlap, double normal_force_norm, double *parts = nullptr)
+  {
+    const double harmonic_conductivity = harmonic_mean(thermal_conductivity_one, thermal_conductivity_two);
+    const double harmonic_radius = harmonic_mean(radius_one, radius_two);
+    const double contact_radius =
+      calculate_corrected_contact_radius(harmonic_radius * 0.5, effective_youngs_modulus, effective_real_youngs_modulus, normal_force_norm);
+    const double corrected_normal_overlap = normal_overlap * std::pow(effective_youngs_modulus / effective_real_youngs_modulus, 2.0 / 3.0);
+    const double contact_radius_squared = contact_radius * contact_radius;
+    const double maximum_pressure = (2.0 * effective_real_youngs_modulus * corrected_normal_overlap) / (M_PI * contact_radius + DBL_MIN);
+    const double resistance_macrocontact = calculate_macrocontact_resistance(harmonic_conductivity, contact_radius);
+    const double resistance_microcontact = calculate_microcontact_resistance(equivalent_surface_slope, equivalent_surface_roughness,
+                                                                             effective_microhardness, contact_radius_squared,
+                                                                             harmonic_conductivity, maximum_pressure);
+    double resistance_solid_macrogap = calculate_solid_macrogap_resistance(radius_one, thermal_conductivity_one, contact_radius_squared);
+    resistance_solid_macrogap += calculate_solid_macrogap_resistance(radius_two, thermal_conductivity_two, contact_radius_squared);
+    const double resistance_gas_microgap = calculate_interstitial_gas_microgap_resistance(
+      equivalent_surface_roughness, contact_radius_squared, gas_parameter_m, thermal_conductivity_gas, maximum_pressure, effective_microhardness);
+    const double resistance_gas_macrogap =
+      calculate_interstitial_gas_macrogap_resistance(harmonic_radius, thermal_conductivity_gas, contact_radius_squared, gas_parameter_m);
+    const double thermal_conductance =
+      1.0 / (resistance_macrocontact + 1.0 / (1.0 / resistance_microcontact + 1.0 / resistance_gas_microgap)) +
+      1.0 / (resistance_solid_macrogap + resistance_gas_macrogap);
+    if (parts)
+      {
+        parts[0] = contact_radius;
+        parts[1] = resistance_macrocontact;
+        parts[2] = resistance_microcontact;
+        parts[3] = resistance_solid_macrogap;
+        parts[4] = resistance_gas_microgap;
+        parts[5] = resistance_gas_macrogap;
+        parts[6] = 1.0 / thermal_conductance;
+        parts[7] = thermal_conductance;
+      }
+    return thermal_conductance;
+  }
+
   void pp_execute_contact_calculation(Oracle &o, PPRow &row, bool periodic, double dt)
   {
     if (row.second.empty())
@@ -1499,6 +1617,20 @@ namespace
           {
             info.tangential_displacement = mk(0, 0, 0);
             info.rolling_resistance_spring_torque = mk(0, 0, 0);
+          }
+        // DEM-MP (…contact_force.h:2065-2150): conduction through every contact with a positive overlap
+        if (o.thermal_enabled && normal_overlap > 0)
+          {
+            const int t1 = int(p1[P_TYPE]), t2 = int(p2[P_TYPE]);
+            const int k = t1 * o.n_types + t2;
+            const uint32_t id1 = o.parts[s1].id, id2 = o.parts[s2].id;
+            const double thermal_conductance = calculate_contact_thermal_conductance(
+              0.5 * p1[P_DP], 0.5 * p2[P_DP], o.eY[k], o.th_real_E[k], o.th_roughness[k], o.th_slope[k], o.th_microhardness[k],
+              o.th_conductivity[t1], o.th_conductivity[t2], o.th_conductivity_gas, o.th_gas_m[k], normal_overlap, norm(out.normal_force));
+            // apply_heat_transfer_on_local_particles (particle_heat_transfer.cc:320-331)
+            const double heat_transfer_rate = thermal_conductance * (o.temperature[id2] - o.temperature[id1]);
+            o.heat_transfer_rate[s1] += heat_transfer_rate;
+            o.heat_transfer_rate[s2] -= heat_transfer_rate;
           }
       }
   }
@@ -2509,6 +2641,26 @@ namespace
       }
   }
 
+  // integrate_temperature (multiphysics_integrator.cc:6-34) with a zero heat source (dem.cc:1148-1152)
+  void integrate_temperature(Oracle &o)
+  {
+    if (!o.thermal_enabled)
+      return;
+    o.heat_transfer_rate.resize(o.parts.size(), 0.);
+    o.last_heat_transfer_rate = o.heat_transfer_rate;
+    const double dt = o.cfg.dt;
+    for (size_t s = 0; s < o.parts.size(); ++s)
+      {
+        const uint32_t id = o.parts[s].id;
+        double &particle_heat_transfer_rate = o.heat_transfer_rate[s];
+        const double particle_heat_source = 0.;
+        const double mass_inverse = 1 / o.parts[s].p[P_MASS];
+        const double specific_heat_inverse = 1 / o.specific_heat[id];
+        o.temperature[id] += dt * (particle_heat_transfer_rate + particle_heat_source) * mass_inverse * specific_heat_inverse;
+        particle_heat_transfer_rate = 0;
+      }
+  }
+
   void reset_triggers(Oracle &o)
   {
     // dem_action_manager.h:61-75: the iteration after a mobility-status reset searches again, with
@@ -2528,6 +2680,7 @@ namespace
     execute_contact_detection_and_search(o);
     move_solid_objects(o); // dem.cc:1141-1142
     compute_contact_forces(o);
+    integrate_temperature(o); // dem.cc:1144-1153
     if ((o.iteration_number <= 1 && !o.cfg.restart) || o.open_next_step)
       integrate_start(o);
     else
@@ -2895,6 +3048,88 @@ int oracle_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n, const
         x3[3 * i + d] = o->parts[s].x[d];
       std::memcpy(props9 + 9 * i, o->parts[s].p, 9 * sizeof(double));
     }
+  return 0;
+}
+
+// set_multiphysic_properties (particle_particle_contact_force.h:1755-1826)
+int oracle_dem_enable_heat_transfer(lethe_dem_ctx *ctx, const lethe_dem_thermal_properties *pr)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  const int n = o->n_types;
+  o->th_real_E.assign(n * n, 0.);
+  o->th_roughness.assign(n * n, 0.);
+  o->th_slope.assign(n * n, 0.);
+  o->th_microhardness.assign(n * n, 0.);
+  o->th_gas_m.assign(n * n, 0.);
+  o->th_conductivity.assign(n, 0.);
+  o->th_conductivity_gas = pr->thermal_conductivity_gas;
+  for (int i = 0; i < n; ++i)
+    {
+      const double real_youngs_modulus_i = pr->real_youngs_modulus[i], poisson_ratio_i = o->cfg.poisson[i];
+      const double surface_roughness_i = pr->surface_roughness[i], surface_slope_i = pr->surface_slope[i];
+      const double microhardness_i = pr->microhardness[i], thermal_accommodation_i = pr->thermal_accommodation[i];
+      o->th_conductivity[i] = pr->thermal_conductivity[i];
+      for (int j = 0; j < n; ++j)
+        {
+          const int k = i * n + j;
+          const double real_youngs_modulus_j = pr->real_youngs_modulus[j], poisson_ratio_j = o->cfg.poisson[j];
+          const double surface_roughness_j = pr->surface_roughness[j], surface_slope_j = pr->surface_slope[j];
+          const double microhardness_j = pr->microhardness[j], thermal_accommodation_j = pr->thermal_accommodation[j];
+          o->th_real_E[k] = (real_youngs_modulus_i * real_youngs_modulus_j) /
+                            ((real_youngs_modulus_j * (1.0 - poisson_ratio_i * poisson_ratio_i)) +
+                             (real_youngs_modulus_i * (1.0 - poisson_ratio_j * poisson_ratio_j)) + DBL_MIN);
+          o->th_roughness[k] = std::sqrt(surface_roughness_i * surface_roughness_i + surface_roughness_j * surface_roughness_j);
+          o->th_slope[k] = std::sqrt(surface_slope_i * surface_slope_i + surface_slope_j * surface_slope_j);
+          o->th_microhardness[k] = harmonic_mean(microhardness_i, microhardness_j);
+          o->th_gas_m[k] = ((2. - thermal_accommodation_i) / thermal_accommodation_i + (2. - thermal_accommodation_j) / thermal_accommodation_j) *
+                           (2. * pr->specific_heats_ratio_gas) / (1. + pr->specific_heats_ratio_gas) * pr->molecular_mean_free_path_gas /
+                           (pr->dynamic_viscosity_gas * pr->specific_heat_gas / pr->thermal_conductivity_gas);
+        }
+    }
+  o->thermal_enabled = true;
+  return 0;
+}
+
+int oracle_dem_set_temperatures(lethe_dem_ctx *ctx, uint64_t n, const uint32_t *id, const double *temperature, const double *specific_heat)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  for (uint64_t k = 0; k < n; ++k)
+    {
+      if (id[k] >= o->temperature.size())
+        {
+          o->temperature.resize(size_t(id[k]) + 1, 0.);
+          o->specific_heat.resize(size_t(id[k]) + 1, 1.);
+        }
+      o->temperature[id[k]] = temperature[k];
+      o->specific_heat[id[k]] = specific_heat[k];
+    }
+  return 0;
+}
+
+int oracle_dem_get_temperatures(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *temperature,
+                                double *heat_transfer_rate)
+{
+  Oracle *o = reinterpret_cast<Oracle *>(ctx);
+  std::vector<std::pair<uint32_t, size_t>> order;
+  for (size_t s = 0; s < o->parts.size(); ++s)
+    order.emplace_back(o->parts[s].id, s);
+  std::sort(order.begin(), order.end());
+  const uint64_t m = std::min<uint64_t>(n_max, order.size());
+  for (uint64_t k = 0; k < m; ++k)
+    {
+      id[k] = order[k].first;
+      temperature[k] = order[k].first < o->temperature.size() ? o->temperature[order[k].first] : 0.;
+      heat_transfer_rate[k] = order[k].second < o->last_heat_transfer_rate.size() ? o->last_heat_transfer_rate[order[k].second] : 0.;
+    }
+  *n_out = m;
+  return 0;
+}
+
+// the intermediate values tests/dem/particle_particle_thermal_resistances.cc prints (test hook)
+int oracle_dem_thermal_resistances(const double *in13, double *out8)
+{
+  calculate_contact_thermal_conductance(in13[0], in13[1], in13[2], in13[3], in13[4], in13[5], in13[6], in13[7], in13[8], in13[9], in13[10],
+                                        in13[11], in13[12], out8);
   return 0;
 }
 

@@ -291,6 +291,61 @@ def test_cfd_property_rows_parity():
     assert np.abs(rg[:, 3:9] - ro[:, 3:9]).max() <= 1e-9 * np.abs(ro[:, 3:9]).max()
 
 
+def test_heat_transfer_golden_on_gpu():
+    """DEM-MP: tests/dem/particle_particle_heat_transfer.output (-1.56046 J/s) through the CUDA engine."""
+    from tests.test_oracle_golden import heat_transfer_unit_case
+
+    e = heat_transfer_unit_case(abi.load_engine)
+    o = heat_transfer_unit_case(loader.oracle_engine)
+    ids, temp, rate = e.get_temperatures()
+    _, temp_o, rate_o = o.get_temperatures()
+    assert_sig6(rate[0], -1.56046)
+    assert rate[1] == -rate[0]
+    assert np.abs(rate - rate_o).max() <= 1e-12 * np.abs(rate_o).max()
+    assert np.abs(temp - temp_o).max() <= 1e-13 * np.abs(temp_o).max()
+
+
+@pytest.mark.parametrize("pp,periodic", [("hertz_mindlin_limit_overlap", (0, 0, 0)), ("hertz_JKR", (1, 0, 0)), ("linear", (0, 0, 0))])
+def test_heat_transfer_parity_stepwise(pp, periodic):
+    """DEM-MP conduction on a polydisperse two-type packing with a temperature gradient, in lock step with
+    the oracle: heat transfer rates within 1e-11 of the largest rate every step (CUDA's pow / log / erfcinv
+    against glibc's and a Newton erfc^-1, a few ulp each), temperatures within 1e-13 relative, the
+    mechanical state at the usual 1e-12, and the total heat exchanged is zero to rounding."""
+    from tests.test_oracle_golden import thermal_properties
+
+    d = 0.005
+    ids, x, props, extent = random_packing(10, d=d, spacing=0.98, jitter=0.08, poly=0.2, n_types=2, seed=17)
+    cohesive = pp == "hertz_JKR"
+    params = packing_parameters(extent, d=d, pp_model=pp, rolling="constant", n_types=2, periodic=periodic,
+                                surface_energy=0.05 if cohesive else 0.0, young=1e6)
+    g, o = setup_pair(params, ids, x, props)
+    rng = np.random.default_rng(23)
+    temperature = 300.0 + 200.0 * x[:, 2] / extent[2] + rng.normal(0, 5.0, len(ids))
+    specific_heat = np.where(props[:, 0] == 0, 840.0, 500.0)
+    th = thermal_properties(real_young=65e9)
+    for e in (g, o):
+        e.enable_heat_transfer(th)
+        e.set_temperatures(ids, temperature, specific_heat)
+    worst = 0.0
+    for step in range(25):
+        i_o, x_o, p_o = o.get_particles()
+        g.step_host(0, i_o, np.ascontiguousarray(x_o), np.ascontiguousarray(p_o))
+        g.step(1)
+        o.step(1)
+        compare_step(g, o, step)
+        ig, tg, rg = g.get_temperatures()
+        io, to, ro = o.get_temperatures()
+        assert np.array_equal(ig, io)
+        scale = np.abs(ro).max()
+        assert scale > 0
+        worst = max(worst, np.abs(rg - ro).max() / scale)
+        assert np.abs(rg - ro).max() <= 1e-11 * scale, (step, np.abs(rg - ro).max() / scale)
+        assert np.abs(tg - to).max() <= 1e-13 * np.abs(to).max(), step
+        assert abs(rg.sum()) <= 1e-9 * np.abs(rg).sum()
+    print(f"heat transfer {pp}: max |dQ| / max |Q| = {worst:.2e}")
+    assert np.abs(tg - temperature[np.argsort(ids)]).max() > 0
+
+
 def test_explicit_euler_parity_stepwise():
     """`integration method = explicit_euler` (explicit_euler_integrator.cc): same lock-step bar."""
     d = 0.005

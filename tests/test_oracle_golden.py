@@ -772,3 +772,91 @@ def test_cfd_property_rows(oracle_lib):
         e.restart_integration()
         e.step(10)
     assert np.array_equal(a.get_particles()[1], b.get_particles()[1])
+
+
+def thermal_properties(real_young=65e9, conductivity=1.0):
+    """lpp of tests/dem/particle_particle_heat_transfer.cc:62-72 (glass beads in air)."""
+    from lethe_b200 import abi
+
+    th = abi.ThermalProperties()
+    for t in range(abi.MAX_TYPES):
+        th.real_youngs_modulus[t] = real_young
+        th.surface_roughness[t] = 25e-9
+        th.surface_slope[t] = 0.078
+        th.microhardness[t] = 9e9
+        th.thermal_conductivity[t] = conductivity * (1 + 0.5 * t)
+        th.thermal_accommodation[t] = 0.7
+    th.thermal_conductivity_gas = 0.027
+    th.dynamic_viscosity_gas = 1.85e-5
+    th.specific_heat_gas = 1006
+    th.specific_heats_ratio_gas = 1
+    th.molecular_mean_free_path_gas = 68e-9
+    return th
+
+
+def heat_transfer_unit_case(engine_factory):
+    """tests/dem/particle_particle_heat_transfer.cc: two 1 cm glass spheres, 10 um overlap, 600 K and 100 K."""
+    p = unit_test_parameters(dt=0.1, g=(0, 0, 0))
+    t = p.particle_types[0]
+    t.young, t.poisson, t.restitution, t.friction, t.rolling_friction, t.rolling_viscous_damping = 65e9, 0.22, 0.8, 1.0, 0.02, 0.0
+    t.diameter = 0.01
+    p.rolling_model = "constant"
+    e = engine_factory(p.to_config(store_forces=True, moi_override=1.0))
+    e.enable_heat_transfer(thermal_properties())
+    e.set_particles([0, 1], [[0, 0, 0], [0.00999, 0, 0]], [props_row(0, 0.01, 1), props_row(0, 0.01, 1)])
+    e.set_temperatures([0, 1], [600, 100], [840, 840])
+    e.step(1)
+    return e
+
+
+def test_particle_particle_heat_transfer_golden(oracle_lib):
+    """DEM-MP: tests/dem/particle_particle_heat_transfer.output (-1.56046 J/s on particle one) through the
+    oracle's contact loop, and the temperature step that follows (integrate_temperature)."""
+    e = heat_transfer_unit_case(loader.oracle_engine)
+    ids, temp, rate = e.get_temperatures()
+    assert_sig6(rate[0], -1.56046)
+    assert rate[1] == -rate[0]
+    assert temp[0] == 600 + 0.1 * rate[0] * (1 / 1.0) * (1 / 840.0)
+    assert temp[1] == 100 + 0.1 * rate[1] * (1 / 1.0) * (1 / 840.0)
+
+
+def test_thermal_resistances_golden(oracle_lib):
+    """tests/dem/particle_particle_thermal_resistances.output: contact radius and the five resistances of
+    calculate_contact_thermal_conductance for two 1 cm spheres with 100 um overlap, E = 5 MPa simulated /
+    65 GPa real. The normal force comes from the contact model, as in the reference test."""
+    import ctypes
+
+    p = unit_test_parameters(dt=0.001, g=(0, 0, 0))
+    t = p.particle_types[0]
+    t.young, t.poisson, t.restitution, t.friction, t.rolling_friction, t.diameter = 5e6, 0.22, 0.8, 1.0, 0.02, 0.01
+    p.rolling_model = "constant"
+    e = loader.oracle_engine(p.to_config(store_forces=True, moi_override=1.0))
+    e.set_particles([0, 1], [[0, 0, 0], [0.0099, 0, 0]], [props_row(0, 0.01, 1), props_row(0, 0.01, 1)])
+    e.step(1)
+    _, f, _ = e.get_forces()
+    normal_force_norm = float(np.sqrt((f[0] ** 2).sum()))
+    nu = 0.22
+    e_eff, e_real = 5e6 / (2.0 * (1.0 - nu * nu)), 65e9 / (2.0 * (1.0 - nu * nu))
+    prandtl = 1.85e-5 * 1006 / 0.027
+    m = 2.0 * (2.0 - 0.7) / 0.7 * (2.0 * 1) / (1.0 + 1) * 68e-9 / prandtl
+    overlap = (0.005 + 0.005) - 0.0099
+    vin = (ctypes.c_double * 13)(0.005, 0.005, e_eff, e_real, 25e-9, 0.078, 9e9, 1.0, 1.0, 0.027, m, overlap, normal_force_norm)
+    out = (ctypes.c_double * 8)()
+    oracle_lib.oracle_dem_thermal_resistances(vin, out)
+    gold = [7.51931e-05, 6649.55, 2992.28, 100.023, 1089.98, 255.915, 339.705, 0.00294373]
+    for got, want in zip(out, gold):
+        assert_sig6(got, want)
+
+
+def test_temperature_integration_order(oracle_lib):
+    """tests/dem/integration_temperature.cc: dT/dt = -T / (m c_p) integrated explicitly is first order
+    (golden: 1.00001). Driven through the engine with a partner that is too far to touch, the rate set
+    by hand is not available, so the scheme is checked on its closed form: T_n = T_0 (1 - dt/(m c_p))^n."""
+    for dt, n in ((0.01, 100), (0.005, 200)):
+        T = 300.0
+        for _ in range(n):
+            T += dt * (-T + 0.0) * (1 / 1.0) * (1 / 840.0)
+        assert abs(T - 300.0 * (1 - dt / 840.0) ** n) < 1e-10
+    e1 = 300.0 * (1 - 0.01 / 840.0) ** 100 - 300.0 * math.exp(-1.0 / 840.0)
+    e2 = 300.0 * (1 - 0.005 / 840.0) ** 200 - 300.0 * math.exp(-1.0 / 840.0)
+    assert abs(math.log(e1 / e2) / math.log(2.0) - 1.0) < 1e-3
