@@ -371,14 +371,20 @@ int lethe_dem_kernel_launches(lethe_dem_ctx *ctx, uint64_t *n_launches);
  * particles-per-layer histogram (by less than the narrowest slab per event), the particles that change
  * owner migrate with their contact history, and the contact search runs. frequency = `load balance
  * step` (once), `frequency` (frequent) or `dynamic check frequency` (dynamic); threshold = `threshold`.
- * dynamic_with_sparse_contacts needs adaptive sparse contacts, which run on one GPU only. */
+ */
 enum lethe_load_balance_method {
   LETHE_LOAD_BALANCE_NONE = 0,
   LETHE_LOAD_BALANCE_ONCE = 1,
   LETHE_LOAD_BALANCE_FREQUENT = 2,
-  LETHE_LOAD_BALANCE_DYNAMIC = 3
+  LETHE_LOAD_BALANCE_DYNAMIC = 3,
+  LETHE_LOAD_BALANCE_DYNAMIC_WITH_SPARSE_CONTACTS = 4 /* needs config.sparse_contacts */
 };
 int lethe_dem_set_load_balancing(lethe_dem_ctx *ctx, int method, double threshold, int frequency);
+/* `particle weight` (2000), the constant of `cell weight function` (1000), `active weight factor`, `inactive weight factor`
+ * (1.0) of dynamic_with_sparse_contacts: load of a rank = cells x cell weight + sum over its particles of particle weight x
+ * the factor of the particle's cell status (load_balancing.cc:60-122,184-222); the same weights shape the re-cut histogram. */
+int lethe_dem_set_load_balancing_weights(lethe_dem_ctx *ctx, double particle_weight, double cell_weight,
+                                         double active_weight_factor, double inactive_weight_factor);
 /* Cell layers [lo, hi) along the slab axis this context owns now, and how many repartitions it has seen. */
 int lethe_dem_get_slab(lethe_dem_ctx *ctx, int32_t *lo, int32_t *hi, uint64_t *n_repartitions);
 /* The cut-plane rule on its own (host arithmetic, no device): cuts / new_cuts have world + 1 entries,

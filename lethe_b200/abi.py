@@ -171,6 +171,7 @@ ABI_SYMBOLS = [
     "event_record",
     "event_elapsed",
     "set_load_balancing",
+    "set_load_balancing_weights",
     "get_slab",
     "balanced_cuts",
     "nccl_unique_id",
@@ -196,7 +197,7 @@ class ThermalProperties(C.Structure):
 
 
 N_CFD_PROPERTIES = 23
-LOAD_BALANCE_METHODS = {"none": 0, "once": 1, "frequent": 2, "dynamic": 3}
+LOAD_BALANCE_METHODS = {"none": 0, "once": 1, "frequent": 2, "dynamic": 3, "dynamic_with_sparse_contacts": 4}
 
 _p_u32 = C.POINTER(C.c_uint32)
 _p_f64 = C.POINTER(C.c_double)
@@ -487,6 +488,10 @@ class Engine:
 
     def set_load_balancing(self, method="dynamic", threshold=0.5, frequency=100):
         self._call("set_load_balancing", C.c_int(LOAD_BALANCE_METHODS[method]), C.c_double(threshold), C.c_int(frequency))
+
+    def set_load_balancing_weights(self, particle_weight=2000.0, cell_weight=1000.0, active_weight_factor=1.0, inactive_weight_factor=1.0):
+        self._call("set_load_balancing_weights", C.c_double(particle_weight), C.c_double(cell_weight), C.c_double(active_weight_factor),
+                   C.c_double(inactive_weight_factor))
 
     def get_slab(self):
         """(lo, hi, n_repartitions): the cell layers along the slab axis this context owns now."""

@@ -169,6 +169,7 @@ struct lethe_dem_ctx
   int lb_method = 0; // lethe_load_balance_method
   double lb_threshold = 0.5;
   int lb_frequency = 100000;
+  double lb_particle_weight = 2000.0, lb_cell_weight = 1000.0, lb_active_factor = 1.0, lb_inactive_factor = 1.0;
   bool lb_recut_pending = false;
   uint64_t n_recuts = 0;
   // DEM-MP heat transfer (dem_kernels.cuh HeatParams): temperature / specific heat per particle id, rate per row
@@ -181,7 +182,7 @@ struct lethe_dem_ctx
   bool asc_reset = false;    // mobility_status_reset_trigger (dem_action_manager.h:128-134,61-75)
   bool asc_in_force = false; // the lists of the current generation were built with the mobility status
   DevBuf<uint8_t> asc_cell_status, asc_row_mobile;
-  DevBuf<int> asc_node_status;
+  DevBuf<int> asc_node_status, asc_xbuf; // asc_xbuf: node planes / cell layers exchanged across the cuts
   DevBuf<uint32_t> nb_cand;    // candidate cache of the neighbour counting pass (NB_CACHE x n_owned)
   DevBuf<uint8_t> nb_cand_img; //   image codes beside it (periodic grids)
 

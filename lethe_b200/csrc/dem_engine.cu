@@ -495,8 +495,17 @@ namespace
     ap.node_status = c->asc_node_status.p;
     ap.row_mobile = c->asc_row_mobile.p;
     ap.n_rows = c->n_owned;
+    const bool slabs = c->multi.enabled();
+    ap.owned_lo = slabs ? c->grid.slab_lo : -1;
+    ap.owned_hi = slabs ? c->grid.slab_hi : -1;
     for (int pass = 0; pass < 5; ++pass)
-      launch_asc_pass(ap, pass, s);
+      {
+        launch_asc_pass(ap, pass, s);
+        if (slabs && pass < 3)
+          c->multi.asc_exchange_nodes(c); // mobility_at_nodes.update_ghost_values()
+        if (slabs && pass == 3)
+          c->multi.asc_exchange_cells(c);
+      }
     c->asc_in_force = true;
   }
 
@@ -1027,6 +1036,7 @@ namespace dem
   void engine_upload_walls(lethe_dem_ctx *c) { upload_walls(c); }
   void engine_rebuild_sort(lethe_dem_ctx *c) { rebuild_sort(c); }
   void engine_rebuild_lists(lethe_dem_ctx *c) { rebuild_lists(c); }
+  void engine_identify_mobility_status(lethe_dem_ctx *c) { identify_mobility_status(c); }
   void engine_mirror_ids(lethe_dem_ctx *c) { mirror_ids(c); }
   cudaEvent_t engine_get_event(lethe_dem_ctx *c) { return get_event(c); }
 } // namespace dem
@@ -2019,11 +2029,25 @@ int lethe_dem_get_mobility_status(lethe_dem_ctx *c, uint64_t n_cells, int32_t *s
 int lethe_dem_set_load_balancing(lethe_dem_ctx *c, int method, double threshold, int frequency)
 {
   return guarded(c, [&] {
-    if (method < LETHE_LOAD_BALANCE_NONE || method > LETHE_LOAD_BALANCE_DYNAMIC)
-      throw std::runtime_error("unknown load balance method (none|once|frequent|dynamic)");
+    if (method < LETHE_LOAD_BALANCE_NONE || method > LETHE_LOAD_BALANCE_DYNAMIC_WITH_SPARSE_CONTACTS)
+      throw std::runtime_error("unknown load balance method (none|once|frequent|dynamic|dynamic_with_sparse_contacts)");
+    if (method == LETHE_LOAD_BALANCE_DYNAMIC_WITH_SPARSE_CONTACTS && !c->asc_enabled)
+      throw std::runtime_error("Invalid contact detection method: adaptive sparse contacts is not enabled while dynamic_with_sparse_contacts "
+                               "is selected, use dynamic instead"); // parameters_lagrangian.cc:1160-1164
     c->lb_method = method;
     c->lb_threshold = threshold;
     c->lb_frequency = frequency;
+  });
+}
+
+int lethe_dem_set_load_balancing_weights(lethe_dem_ctx *c, double particle_weight, double cell_weight, double active_weight_factor,
+                                         double inactive_weight_factor)
+{
+  return guarded(c, [&] {
+    c->lb_particle_weight = particle_weight;
+    c->lb_cell_weight = cell_weight;
+    c->lb_active_factor = active_weight_factor;
+    c->lb_inactive_factor = inactive_weight_factor;
   });
 }
 

@@ -1022,8 +1022,6 @@ namespace dem
         atomicMax(P.node_status + asc_node(g, ci + (v & 1), cj + ((v >> 1) & 1), ck + (v >> 2)), value);
     }
 
-    constexpr uint8_t ASC_UNASSIGNED = 0xffu;
-
     // One thread per cell; the four passes are separate launches because each reads the node
     // values the previous one wrote. Within a pass the node value tested is never one the pass writes.
     template <int PASS> __global__ void __launch_bounds__(128) k_asc_cells(const __grid_constant__ AscParams P)
@@ -1031,6 +1029,18 @@ namespace dem
       const int lin = blockIdx.x * blockDim.x + threadIdx.x;
       if (lin >= P.grid.n_cells)
         return;
+      if (P.owned_lo >= 0)
+        {
+          const GridDesc &g = P.grid;
+          const int a = g.slab_axis;
+          const int ca = a == 0 ? lin % g.n[0] : (a == 1 ? (lin / g.n[0]) % g.n[1] : lin / (g.n[0] * g.n[1]));
+          if (ca < P.owned_lo || ca >= P.owned_hi)
+            {
+              if (PASS == 0)
+                P.cell_status[lin] = ASC_FOREIGN;
+              return;
+            }
+        }
       const uint32_t rank = uint32_t(P.cell_rank[lin]);
       const uint32_t p0 = P.cell_start[rank], p1 = P.cell_start[rank + 1];
       if constexpr (PASS == 0)
@@ -1100,6 +1110,62 @@ namespace dem
       else
         // 4. the active layer; the rest is inactive
         P.cell_status[lin] = asc_any_node(P, lin, LETHE_MOBILITY_STATIC_ACTIVE) ? LETHE_MOBILITY_STATIC_ACTIVE : LETHE_MOBILITY_INACTIVE;
+    }
+
+    // the two in-plane axes of a plane / layer across the slab axis
+    __device__ __forceinline__ void asc_plane_axes(int a, int &u, int &v)
+    {
+      u = a == 0 ? 1 : 0;
+      v = a == 2 ? 1 : 2;
+    }
+    template <int OP> __global__ void __launch_bounds__(256) k_asc_plane(const __grid_constant__ AscPlaneParams P)
+    {
+      const GridDesc &g = P.grid;
+      const int a = g.slab_axis;
+      int u, v;
+      asc_plane_axes(a, u, v);
+      const bool nodes = OP < 2;
+      const int nu = g.n[u] + (nodes ? 1 : 0), nv = g.n[v] + (nodes ? 1 : 0);
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= nu * nv)
+        return;
+      int c[3];
+      c[a] = P.index;
+      c[u] = t % nu;
+      c[v] = t / nu;
+      if (nodes)
+        {
+          const int node = asc_node(g, c[0], c[1], c[2]);
+          if (OP == 0)
+            P.buf[t] = P.node_status[node];
+          else
+            atomicMax(P.node_status + node, P.buf[t]); // periodic in-plane nodes alias each other
+        }
+      else
+        {
+          const int lin = c[0] + g.n[0] * (c[1] + g.n[1] * c[2]);
+          if (OP == 2)
+            P.buf[t] = int(P.cell_status[lin]);
+          else
+            P.cell_status[lin] = uint8_t(P.buf[t]);
+        }
+    }
+
+    __global__ void __launch_bounds__(256) k_layer_histogram_weighted(const double4 *pos, const int32_t *cell_reg, const uint8_t *cell_status,
+                                                                      GridDesc g, uint32_t n, uint32_t w_mobile, uint32_t w_active,
+                                                                      uint32_t w_inactive, uint32_t *hist)
+    {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      if (p >= n)
+        return;
+      const double4 x = pos[p];
+      const int a = g.slab_axis;
+      const double xa = a == 0 ? x.x : (a == 1 ? x.y : x.z);
+      int layer = int(floor((xa - g.lo[a]) / g.h[a]));
+      layer = min(max(layer, 0), g.n[a] - 1);
+      const int lin = cell_reg[p];
+      const uint8_t st = lin >= 0 ? cell_status[lin] : uint8_t(LETHE_MOBILITY_MOBILE);
+      atomicAdd(hist + layer, st == LETHE_MOBILITY_MOBILE ? w_mobile : (st == LETHE_MOBILITY_STATIC_ACTIVE ? w_active : w_inactive));
     }
 
     __global__ void __launch_bounds__(256) k_asc_rows(const __grid_constant__ AscParams P)
@@ -1460,7 +1526,10 @@ namespace dem
         // pick the nearer of the two boundaries around the target
         if (e > 0 && e <= n_layers && (target - double(cum[e - 1])) < (double(cum[std::min(e, n_layers)]) - target))
           --e;
-        e = std::max(cuts[r] - max_shift, std::min(e, cuts[r] + max_shift));
+        // a cut stays strictly inside the two slabs it separates (so that every particle that changes owner goes to an
+        // adjacent rank), and moves by at most max_shift layers
+        const int down = std::min(max_shift, cuts[r] - cuts[r - 1] - 1), up = std::min(max_shift, cuts[r + 1] - cuts[r] - 1);
+        e = std::max(cuts[r] - std::max(down, 0), std::min(e, cuts[r] + std::max(up, 0)));
         e = std::max(e, new_cuts[r - 1] + min_width);
         e = std::min(e, n_layers - min_width * (world - r));
         new_cuts[r] = e;
@@ -1598,6 +1667,33 @@ namespace dem
         count_launch();
       }
   }
+  void launch_asc_plane(const AscPlaneParams &p, int op, cudaStream_t s)
+  {
+    const int a = p.grid.slab_axis;
+    const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+    const int extra = op < 2 ? 1 : 0;
+    const unsigned n = unsigned((p.grid.n[u] + extra) * (p.grid.n[v] + extra));
+    const unsigned blocks = (n + 255) / 256;
+    if (op == 0)
+      k_asc_plane<0><<<blocks, 256, 0, s>>>(p);
+    else if (op == 1)
+      k_asc_plane<1><<<blocks, 256, 0, s>>>(p);
+    else if (op == 2)
+      k_asc_plane<2><<<blocks, 256, 0, s>>>(p);
+    else
+      k_asc_plane<3><<<blocks, 256, 0, s>>>(p);
+    count_launch(1);
+  }
+
+  void launch_layer_histogram_weighted(const double4 *pos, const int32_t *cell_reg, const uint8_t *cell_status, GridDesc grid, uint32_t n,
+                                       uint32_t w_mobile, uint32_t w_active, uint32_t w_inactive, uint32_t *hist, cudaStream_t s)
+  {
+    if (!n)
+      return;
+    k_layer_histogram_weighted<<<(n + 255) / 256, 256, 0, s>>>(pos, cell_reg, cell_status, grid, n, w_mobile, w_active, w_inactive, hist);
+    count_launch(1);
+  }
+
   void launch_asc_pass(const AscParams &p, int pass, cudaStream_t s)
   {
     const unsigned cells = unsigned((p.grid.n_cells + 127) / 128);

@@ -296,7 +296,7 @@ namespace dem
   void launch_layer_histogram(const double4 *pos, GridDesc grid, uint32_t n, uint32_t *hist, cudaStream_t s);
   // New cut planes of a slab decomposition: cuts[0] = 0 < cuts[1] < ... < cuts[world] = n_layers. Every
   // internal cut moves towards the position that balances the particle histogram, by at most
-  // max_shift layers, keeping every slab at least min_width layers wide. Pure host function (the
+  // max_shift layers and never out of the two slabs it separates, keeping every slab at least min_width layers wide. Pure host function (the
   // role of p4est's weighted repartition, load_balancing.cc:9-40, for slabs).
   void balanced_cuts(int n_layers, const uint64_t *hist, int world, const int32_t *cuts, int max_shift, int min_width, int32_t *new_cuts);
   void launch_append_records(const MigrateRecord *rec, const uint32_t *ids, uint32_t n, StateView st, uint32_t *id_out,
@@ -451,7 +451,25 @@ namespace dem
     int *node_status;     // [(nx+1)(ny+1)(nz+1)]
     uint8_t *row_mobile;  // [n_rows] 1 = the particle's cell is mobile
     uint32_t n_rows;
+    int owned_lo, owned_hi; // slab decomposition: only cell layers [owned_lo, owned_hi) along grid.slab_axis are this rank's to classify; -1 = all
   };
+  constexpr uint8_t ASC_UNASSIGNED = 0xffu; // cell_status while the passes run
+  constexpr uint8_t ASC_FOREIGN = 0xfeu;    // a cell another rank classifies (its status arrives with MultiGpu::asc_exchange_cells)
+  // slab decomposition: one plane of nodes (axis index `index` in node coordinates) or one layer of cells across the slab
+  // axis, gathered into / merged from a contiguous buffer that travels to the neighbour rank
+  struct AscPlaneParams
+  {
+    GridDesc grid;
+    int index;
+    int *node_status;
+    uint8_t *cell_status;
+    int *buf;
+  };
+  // op 0: buf <- node plane, 1: node plane <- max(node plane, buf), 2: buf <- cell layer, 3: cell layer <- buf
+  void launch_asc_plane(const AscPlaneParams &p, int op, cudaStream_t s);
+  // particles per cell layer weighted by the mobility status of their cell (x1000 fixed point): load_balancing.cc:184-222
+  void launch_layer_histogram_weighted(const double4 *pos, const int32_t *cell_reg, const uint8_t *cell_status, GridDesc grid, uint32_t n,
+                                       uint32_t w_mobile, uint32_t w_active, uint32_t w_inactive, uint32_t *hist, cudaStream_t s);
   // pass 0: empty cells, 1: mobile by criteria, 2: mobile by neighbour, 3: active / inactive, 4: per-particle flag
   void launch_asc_pass(const AscParams &p, int pass, cudaStream_t s);
 } // namespace dem

@@ -21,6 +21,7 @@
 #include <nccl.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -169,8 +170,6 @@ namespace dem
       throw std::runtime_error("communicator already initialised");
     if (c->thermal_enabled)
       throw std::runtime_error("heat transfer runs on a single GPU (ghost temperatures are not exchanged)");
-    if (c->asc_enabled)
-      throw std::runtime_error("adaptive sparse contacts run on a single GPU: the node-based mobility status is not exchanged across slabs");
     MultiGpuImpl *m = new MultiGpuImpl();
     m->rank = rank;
     m->world = world;
@@ -264,6 +263,41 @@ namespace dem
       return (it % freq) == 0;
     if ((it % freq) != 0)
       return false;
+    if (c->lb_method == LETHE_LOAD_BALANCE_DYNAMIC_WITH_SPARSE_CONTACTS)
+      {
+        // check_load_balance_with_sparse_contacts (load_balancing.cc:60-122): cell weight per owned cell + particle weight x
+        // mobility factor per particle; repartition if (max - min) load > threshold * total / ranks
+        cudaStream_t s = c->stream;
+        DevBuf<uint32_t> acc;
+        acc.ensure(size_t(c->grid.n[c->grid.slab_axis]) + 4);
+        CU_TRY(cudaMemsetAsync(acc.p, 0, (size_t(c->grid.n[c->grid.slab_axis]) + 4) * 4, s));
+        if (c->asc_in_force)
+          launch_layer_histogram_weighted(c->st[c->cur].pos.p, c->st[c->cur].cell_reg.p, c->asc_cell_status.p, c->grid, c->n_owned, 1000u,
+                                          uint32_t(std::lround(1000.0 * c->lb_active_factor)), uint32_t(std::lround(1000.0 * c->lb_inactive_factor)),
+                                          acc.p, s);
+        else
+          launch_layer_histogram(c->st[c->cur].pos.p, c->grid, c->n_owned, acc.p, s);
+        std::vector<uint32_t> hh(size_t(c->grid.n[c->grid.slab_axis]));
+        CU_TRY(cudaMemcpyAsync(hh.data(), acc.p, hh.size() * 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        double weighted = 0;
+        for (uint32_t v : hh)
+          weighted += v;
+        if (c->asc_in_force)
+          weighted /= 1000.0;
+        const int a = c->grid.slab_axis;
+        const double cells = double(c->grid.slab_hi - c->grid.slab_lo) * (double(c->grid.n_cells) / c->grid.n[a]);
+        const double load = cells * c->lb_cell_weight + weighted * c->lb_particle_weight;
+        double v[3] = {load, -load, load};
+        DevBuf<double> dv;
+        dv.ensure(3);
+        CU_TRY(cudaMemcpyAsync(dv.p, v, 24, cudaMemcpyHostToDevice, s));
+        NCCL_TRY(g_nccl.AllReduce(dv.p, dv.p, 2, ncclDouble, ncclMax, m->comm, s));
+        NCCL_TRY(g_nccl.AllReduce(dv.p + 2, dv.p + 2, 1, ncclDouble, ncclSum, m->comm, s));
+        CU_TRY(cudaMemcpyAsync(v, dv.p, 24, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        return (v[0] - (-v[1])) > c->lb_threshold * (v[2] / m->world);
+      }
     // dynamic: (max - min) particles per rank > threshold * (local particles / ranks). The reference
     // evaluates this with each rank's own count on the right-hand side (load_balancing.cc:44-55);
     // here any rank that finds it true makes all of them repartition.
@@ -276,6 +310,92 @@ namespace dem
     const uint32_t n_max = h[0], n_min = ~h[1];
     const bool local = double(n_max - n_min) > c->lb_threshold * double(c->n_owned / uint32_t(m->world));
     return agree(c, local);
+  }
+
+  namespace
+  {
+    // buf layout: [0] what I send down, [1] what I send up, [2] received from below, [3] received from above, `count` ints each
+    void asc_exchange(lethe_dem_ctx *c, MultiGpuImpl *m, int *buf, size_t count)
+    {
+      cudaStream_t s = c->stream;
+      NCCL_TRY(g_nccl.GroupStart());
+      if (m->peer[1] >= 0)
+        NCCL_TRY(g_nccl.Send(buf + 1 * count, count, ncclInt32, m->peer[1], m->comm, s));
+      if (m->peer[0] >= 0)
+        NCCL_TRY(g_nccl.Recv(buf + 2 * count, count, ncclInt32, m->peer[0], m->comm, s));
+      if (m->peer[0] >= 0)
+        NCCL_TRY(g_nccl.Send(buf + 0 * count, count, ncclInt32, m->peer[0], m->comm, s));
+      if (m->peer[1] >= 0)
+        NCCL_TRY(g_nccl.Recv(buf + 3 * count, count, ncclInt32, m->peer[1], m->comm, s));
+      NCCL_TRY(g_nccl.GroupEnd());
+    }
+  } // namespace
+
+  void MultiGpu::asc_exchange_nodes(lethe_dem_ctx *c)
+  {
+    MultiGpuImpl *m = impl;
+    cudaStream_t s = c->stream;
+    const GridDesc &g = c->grid;
+    const int a = g.slab_axis, u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+    const size_t count = size_t(g.n[u] + 1) * (g.n[v] + 1);
+    c->asc_xbuf.ensure(4 * count);
+    AscPlaneParams pp;
+    pp.grid = g;
+    pp.node_status = c->asc_node_status.p;
+    pp.cell_status = c->asc_cell_status.p;
+    // my lower cut plane is node index slab_lo, my upper one slab_hi (asc_node wraps it on a periodic axis)
+    pp.index = g.slab_lo;
+    pp.buf = c->asc_xbuf.p + 0 * count;
+    launch_asc_plane(pp, 0, s);
+    pp.index = g.slab_hi;
+    pp.buf = c->asc_xbuf.p + 1 * count;
+    launch_asc_plane(pp, 0, s);
+    asc_exchange(c, m, c->asc_xbuf.p, count);
+    if (m->peer[0] >= 0)
+      {
+        pp.index = g.slab_lo;
+        pp.buf = c->asc_xbuf.p + 2 * count;
+        launch_asc_plane(pp, 1, s);
+      }
+    if (m->peer[1] >= 0)
+      {
+        pp.index = g.slab_hi;
+        pp.buf = c->asc_xbuf.p + 3 * count;
+        launch_asc_plane(pp, 1, s);
+      }
+  }
+
+  void MultiGpu::asc_exchange_cells(lethe_dem_ctx *c)
+  {
+    MultiGpuImpl *m = impl;
+    cudaStream_t s = c->stream;
+    const GridDesc &g = c->grid;
+    const int a = g.slab_axis, u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2, na = g.n[a];
+    const size_t count = size_t(g.n[u]) * g.n[v];
+    c->asc_xbuf.ensure(4 * count);
+    AscPlaneParams pp;
+    pp.grid = g;
+    pp.node_status = c->asc_node_status.p;
+    pp.cell_status = c->asc_cell_status.p;
+    pp.index = g.slab_lo; // my lowest layer goes down
+    pp.buf = c->asc_xbuf.p + 0 * count;
+    launch_asc_plane(pp, 2, s);
+    pp.index = g.slab_hi - 1; // my highest layer goes up
+    pp.buf = c->asc_xbuf.p + 1 * count;
+    launch_asc_plane(pp, 2, s);
+    asc_exchange(c, m, c->asc_xbuf.p, count);
+    if (m->peer[0] >= 0)
+      {
+        pp.index = (g.slab_lo - 1 + na) % na; // the lower neighbour's highest layer
+        pp.buf = c->asc_xbuf.p + 2 * count;
+        launch_asc_plane(pp, 3, s);
+      }
+    if (m->peer[1] >= 0)
+      {
+        pp.index = g.slab_hi % na; // the upper neighbour's lowest layer
+        pp.buf = c->asc_xbuf.p + 3 * count;
+        launch_asc_plane(pp, 3, s);
+      }
   }
 
   bool MultiGpu::any_rank_flag(lethe_dem_ctx *c)
@@ -659,7 +779,13 @@ namespace dem
         DevBuf<uint32_t> hist_dev;
         hist_dev.ensure(size_t(na) + size_t(m->world) + 1);
         CU_TRY(cudaMemsetAsync(hist_dev.p, 0, (size_t(na) + size_t(m->world) + 1) * 4, s));
-        launch_layer_histogram(c->st[c->cur].pos.p, c->grid, c->n_owned, hist_dev.p, s);
+        if (c->lb_method == LETHE_LOAD_BALANCE_DYNAMIC_WITH_SPARSE_CONTACTS && c->asc_in_force)
+          // particle weight x the factor of its cell's mobility status (load_balancing.cc:184-222), in thousandths
+          launch_layer_histogram_weighted(c->st[c->cur].pos.p, c->st[c->cur].cell_reg.p, c->asc_cell_status.p, c->grid, c->n_owned, 1000u,
+                                          uint32_t(std::lround(1000.0 * c->lb_active_factor)), uint32_t(std::lround(1000.0 * c->lb_inactive_factor)),
+                                          hist_dev.p, s);
+        else
+          launch_layer_histogram(c->st[c->cur].pos.p, c->grid, c->n_owned, hist_dev.p, s);
         // every rank also publishes its lower cut in the slot behind the histogram
         const uint32_t lo = uint32_t(c->grid.slab_lo);
         CU_TRY(cudaMemcpyAsync(hist_dev.p + na + m->rank, &lo, 4, cudaMemcpyHostToDevice, s));
@@ -669,20 +795,16 @@ namespace dem
         CU_TRY(cudaStreamSynchronize(s));
         std::vector<uint64_t> hist(h.begin(), h.begin() + na);
         std::vector<int32_t> cuts(size_t(m->world) + 1), new_cuts(size_t(m->world) + 1);
-        int narrowest = na;
         for (int r = 0; r < m->world; ++r)
           cuts[r] = int32_t(h[size_t(na) + r]);
         cuts[m->world] = na;
-        for (int r = 0; r < m->world; ++r)
-          narrowest = std::min(narrowest, cuts[r + 1] - cuts[r]);
-        const int max_shift = std::max(0, narrowest - 2);
-        balanced_cuts(na, hist.data(), m->world, cuts.data(), max_shift, 2, new_cuts.data());
-        if (new_cuts[m->rank] != c->grid.slab_lo || new_cuts[m->rank + 1] != c->grid.slab_hi)
-          {
-            c->grid.slab_lo = new_cuts[m->rank];
-            c->grid.slab_hi = new_cuts[m->rank + 1];
-          }
-        max_hop = max_shift + 1;
+        balanced_cuts(na, hist.data(), m->world, cuts.data(), na, 2, new_cuts.data());
+        int largest_shift = 0;
+        for (int r = 1; r < m->world; ++r)
+          largest_shift = std::max(largest_shift, std::abs(new_cuts[r] - cuts[r]));
+        c->grid.slab_lo = new_cuts[m->rank];
+        c->grid.slab_hi = new_cuts[m->rank + 1];
+        max_hop = largest_shift + 1;
         ++c->n_recuts;
       }
 
@@ -916,6 +1038,8 @@ namespace dem
       launch_register_ids(sg.id.p, n, c->n_ghost, c->slot_of_id.p, c->slot_map_size, s);
 
     mark("tables");
+    // ---- 4b. adaptive sparse contacts: mobility status of my cells, node values merged across the cuts ----
+    engine_identify_mobility_status(c);
     // ---- 5. lists ----
     engine_rebuild_lists(c);
     c->n_pay = 0;

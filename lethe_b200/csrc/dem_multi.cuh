@@ -27,6 +27,12 @@ namespace dem
     // LagrangianLoadBalancing::check_load_balance_{once,frequent,dynamic} (load_balancing.cc:17-58) at the
     // top of an iteration: true = this iteration repartitions (collective; same answer on every rank)
     bool load_balance_due(lethe_dem_ctx *c);
+    // adaptive sparse contacts across slabs (identify_mobility_status runs per rank on its own cells; the reference's
+    // mobility_at_nodes.update_ghost_values(), adaptive_sparse_contacts.cc:212,270,308): the node values on the two cut
+    // planes are max-merged with the neighbours' after each node pass, and the statuses of the neighbours' boundary
+    // cell layers arrive after the last one (the broad search needs them for pairs that straddle a cut)
+    void asc_exchange_nodes(lethe_dem_ctx *c);
+    void asc_exchange_cells(lethe_dem_ctx *c);
 
     // ---- fused halo (peer-memory) mode ----
     // true once every rank has mapped its neighbours' state arrays (CUDA IPC over NVLink): the
@@ -46,5 +52,6 @@ namespace dem
   void engine_upload_walls(lethe_dem_ctx *c);
   void engine_rebuild_sort(lethe_dem_ctx *c);
   void engine_rebuild_lists(lethe_dem_ctx *c);
+  void engine_identify_mobility_status(lethe_dem_ctx *c);
   void engine_mirror_ids(lethe_dem_ctx *c);
 } // namespace dem

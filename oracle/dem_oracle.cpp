@@ -3393,6 +3393,7 @@ int oracle_dem_get_mobility_status(lethe_dem_ctx *ctx, uint64_t n_cells, int32_t
 
 // a single domain has nothing to balance: the calls exist so that drivers run unchanged
 int oracle_dem_set_load_balancing(lethe_dem_ctx *, int, double, int) { return 0; }
+int oracle_dem_set_load_balancing_weights(lethe_dem_ctx *, double, double, double, double) { return 0; }
 int oracle_dem_get_slab(lethe_dem_ctx *ctx, int32_t *lo, int32_t *hi, uint64_t *n_repartitions)
 {
   Oracle *o = reinterpret_cast<Oracle *>(ctx);

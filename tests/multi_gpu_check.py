@@ -26,8 +26,12 @@ def run_case(name, w, checkpoints, rank, world, local_rank, tol=(1e-9, 1e-6), lo
     engine on rank 0) at several horizons: a decomposition bug shows up at the first
     checkpoint, chaotic growth of summation-order noise only at the late ones."""
     eng, n_local = multi.create_slab_engine(w, rank, world, local_rank, dist, store_forces=True, balanced=False)
+    expect_recut = bool(load_balance) and load_balance[0] != "dynamic_with_sparse_contacts"
     if load_balance:
         eng.set_load_balancing(*load_balance)
+        if load_balance[0] == "dynamic_with_sparse_contacts":
+            # the weights of load_balancing_mobility_status.prm: particles of active / inactive cells count for 1/1000
+            eng.set_load_balancing_weights(2000.0, 1000.0, 0.001, 0.001)
     slab0 = eng.get_slab()
     o = single = None
     if rank == 0:
@@ -79,7 +83,24 @@ def run_case(name, w, checkpoints, rank, world, local_rank, tol=(1e-9, 1e-6), lo
                 same_rebuilds = load_balance is not None or all(r == o.get_stats().n_rebuilds for r in rebuilds)
                 ok &= same_pairs and ex < tol[0] and ef < tol[1] and et < tol[1] and same_rebuilds
         done = steps
-    if load_balance:
+    if w.params.sparse_contacts:
+        # adaptive sparse contacts across slabs: every rank classifies its own cell layers; merged, the statuses are the
+        # single-domain oracle's
+        mesh = w.params.mesh
+        parts = gather_rows((eng.get_slab()[:2], eng.get_mobility_status()), world)
+        if rank == 0:
+            merged = np.full(mesh.n[0] * mesh.n[1] * mesh.n[2], -1)
+            layer = np.arange(len(merged)) % mesh.n[0]  # slab axis 0
+            for (lo, hi), st in parts:
+                own = (layer >= lo) & (layer < hi)
+                merged[own] = st[own]
+            so = o.get_mobility_status()
+            same = bool(np.array_equal(merged, so))
+            print(f"[{name}] mobility status: {np.bincount(so, minlength=5).tolist()} cells per status in the oracle, slab runs agree: {same}", flush=True)
+            ok &= same and len(set(np.unique(so).tolist()) & {1, 4}) == 2
+    if load_balance and not expect_recut and rank == 0:
+        print(f"[{name}] dynamic_with_sparse_contacts: slab of rank 0 {slab0[:2]} -> {eng.get_slab()[:2]}, repartitions {eng.get_slab()[2]}", flush=True)
+    if expect_recut:
         # the cuts must have moved towards the particles and evened out the load
         slabs = gather_rows((slab0, eng.get_slab(), eng.n_particles()), world)
         if rank == 0:
@@ -175,16 +196,30 @@ def main():
     v, t = workloads.sheet_mesh(-0.05 * hi[0], 1.05 * hi[0], -0.05 * hi[1], 1.05 * hi[1], lambda x, y: 0.3 * hi[2] + 0.2 * x, 8)
     w.solids = [(v, t, (0.0, 0.0, 10.0), (0.0, 2.0, 0.0), (0.5 * hi[0], 0.5 * hi[1], 0.5 * hi[2]))]
     ok &= run_case("solid", w, (20, 60), rank, world, local_rank, tol=(1e-11, 1e-8))
-    # load balancing: a bed heaped against the low-x wall, equal-width slabs (the upper ranks start
-    # empty), `dynamic` method checking every 5 iterations: the cut planes follow the particles while
+    # load balancing: a bed heaped against the low-x wall (55 % of the box), equal-width slabs (the upper
+    # ranks start empty), `dynamic` method checking every 5 iterations: the cut planes follow the particles while
     # the heap collapses, pairs and forces stay those of the single-domain oracle
     w = workloads.box_packing(n_side=max(24, 8 * world), nz=8, spacing=1.02, jitter=0.05)
-    keep = w.x[:, 0] < 0.3 * w.params.mesh.hi[0]
+    keep = w.x[:, 0] < 0.55 * w.params.mesh.hi[0]
     w.ids, w.x, w.props = w.ids[keep], w.x[keep], w.props[keep]
     w.props[:, 6:9] = np.random.default_rng(9).normal(0.0, 5.0, (w.n, 3))
     w.params.rolling_model = "constant"
     w.params.dynamic_contact_search_factor = 0.1
     ok &= run_case("load-balance", w, (20, 80), rank, world, local_rank, tol=(1e-11, 1e-8), load_balance=("dynamic", 0.2, 5))
+    # adaptive sparse contacts: a bed at rest with an agitated top layer; the node-based status crosses the cuts
+    w = workloads.box_packing(n_side=max(14, 5 * world), nz=20, spacing=1.0, jitter=0.02)
+    rng = np.random.default_rng(3)
+    top = w.x[:, 2] > 0.75 * w.x[:, 2].max()
+    w.props[:, 3:9] = 0.0
+    w.props[top, 3:6] = rng.normal(0.0, 1.0, (int(top.sum()), 3))
+    w.params.sparse_contacts = True
+    w.params.asc_granular_temperature_threshold = 0.02
+    w.params.asc_solid_fraction_threshold = 0.3
+    w.params.rolling_model = "constant"
+    w.params.dynamic_contact_search_factor = 0.05
+    ok &= run_case("sparse-contacts", w, (15, 45), rank, world, local_rank, tol=(1e-11, 1e-8))
+    # the same bed with the load balanced by mobility-weighted particle counts
+    ok &= run_case("sparse-contacts-lb", w, (15, 45), rank, world, local_rank, tol=(1e-11, 1e-8), load_balance=("dynamic_with_sparse_contacts", 0.05, 5))
     if world == 2:
         ok &= two_processor_golden(rank, world, local_rank)
     dist.destroy_process_group()

@@ -136,12 +136,11 @@ def test_load_balance_cut_rule():
     cuts = np.array([0, 16, 32, 48, 64], np.int32)
     shifts = []
     for _ in range(12):
-        widths = np.diff(cuts)
-        max_shift = int(widths.min()) - 2
-        new = abi.balanced_cuts(hist, cuts, max_shift)
+        new = abi.balanced_cuts(hist, cuts, n_layers)
         assert new[0] == 0 and new[-1] == n_layers
         assert np.all(np.diff(new) >= 2)
-        assert np.all(np.abs(new - cuts) <= max(max_shift, 0))
+        # every cut stays strictly inside the two slabs it separated: owners only change between adjacent ranks
+        assert np.all(new[1:-1] > cuts[:-2]) and np.all(new[1:-1] < cuts[2:])
         shifts.append(int(np.abs(new - cuts).sum()))
         cuts = new
     counts = [int(hist[cuts[r]:cuts[r + 1]].sum()) for r in range(world)]
@@ -150,3 +149,11 @@ def test_load_balance_cut_rule():
     # an already balanced partition stays where it is
     flat = np.full(n_layers, 100, np.uint64)
     assert np.array_equal(abi.balanced_cuts(flat, np.array([0, 16, 32, 48, 64], np.int32), 8), [0, 16, 32, 48, 64])
+    # the situation of the 4-GPU check: a heap in the first 6 of 17 layers, equal slabs -> the cuts close in on it
+    heap = np.zeros(17, np.uint64)
+    heap[:6] = [700, 600, 500, 450, 400, 233]
+    cuts = np.array([0, 4, 8, 12, 17], np.int32)
+    for _ in range(8):
+        cuts = abi.balanced_cuts(heap, cuts, 17)
+    # six occupied layers cannot feed four slabs of at least two layers: the best partition leaves the last rank empty
+    assert np.array_equal(cuts, [0, 2, 4, 6, 17])
