@@ -86,7 +86,8 @@ namespace dem
   struct ListBufs
   {
     DevBuf<uint32_t> row_start, col;
-    DevBuf<double> hist, roll;
+    DevBuf<double4> hist; // one 32-byte row per entry
+    DevBuf<double> roll;
     DevBuf<uint8_t> img, rowl;
     uint32_t n_rows = 0;
     uint64_t n_entries = 0;

@@ -558,7 +558,7 @@ namespace
     exclusive_scan_u32(c->counts.p, newl.row_start.p, size_t(n_new) + 1, c->scan_tmp.p, s);
     const uint32_t n_entries = n_new ? read_u32(c, newl.row_start.p + n_new) : 0;
     newl.col.ensure(std::max<size_t>(n_entries, 1));
-    newl.hist.ensure(std::max<size_t>(3 * size_t(n_entries), 1));
+    newl.hist.ensure(std::max<size_t>(size_t(n_entries), 1));
     newl.rowl.ensure(std::max<size_t>(n_entries, 1));
     if (use_roll)
       newl.roll.ensure(std::max<size_t>(3 * size_t(n_entries), 1));
@@ -1759,7 +1759,7 @@ int lethe_dem_get_pairs(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint3
     const size_t n = l.n_rows, E = l.n_entries;
     const size_t n_all = size_t(c->n_owned) + c->n_ghost;
     std::vector<uint32_t> rs(n + 1, 0), col(E), ids(n_all);
-    std::vector<double> hist(3 * E);
+    std::vector<double> hist(4 * E); // 32-byte rows
     if (n)
       {
         CU_TRY(cudaMemcpy(rs.data(), l.row_start.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
@@ -1768,7 +1768,7 @@ int lethe_dem_get_pairs(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint3
     if (E)
       {
         CU_TRY(cudaMemcpy(col.data(), l.col.p, E * 4, cudaMemcpyDeviceToHost));
-        CU_TRY(cudaMemcpy(hist.data(), l.hist.p, 3 * E * 8, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(hist.data(), l.hist.p, 4 * E * 8, cudaMemcpyDeviceToHost));
       }
     struct P
     {
@@ -1792,7 +1792,7 @@ int lethe_dem_get_pairs(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint3
               p.i = std::min(a, b);
               p.j = std::max(a, b);
               for (int d = 0; d < 3; ++d)
-                p.t[d] = has ? sgn * hist[3 * size_t(e) + d] : 0.0;
+                p.t[d] = has ? sgn * hist[4 * size_t(e) + d] : 0.0;
               pairs.push_back(p);
             }
         }

@@ -402,8 +402,7 @@ namespace dem
               if (oc & COL_HIST_BIT)
                 {
                   word |= COL_HIST_BIT;
-                  for (int d = 0; d < 3; ++d)
-                    P.new_list.hist[3 * size_t(e) + d] = P.old_list.hist[3 * size_t(eo) + d];
+                  P.new_list.hist[e] = P.old_list.hist[eo];
                   if (P.use_roll)
                     for (int d = 0; d < 3; ++d)
                       P.new_list.roll[3 * size_t(e) + d] = P.old_list.roll[3 * size_t(eo) + d];
@@ -425,8 +424,10 @@ namespace dem
               if (oc & COL_HIST_BIT)
                 {
                   word |= COL_HIST_BIT;
-                  for (int d = 0; d < 3; ++d)
-                    P.new_list.hist[3 * size_t(e) + d] = -P.old_list.hist[3 * size_t(eo) + d];
+                  {
+                    const double4 ho = P.old_list.hist[eo];
+                    P.new_list.hist[e] = make_double4(-ho.x, -ho.y, -ho.z, 0.0);
+                  }
                   if (P.use_roll)
                     for (int d = 0; d < 3; ++d)
                       P.new_list.roll[3 * size_t(e) + d] = -P.old_list.roll[3 * size_t(eo) + d];
@@ -443,8 +444,7 @@ namespace dem
                 if (rec.rid != rid || (rec.flags & (HIST_REC_WALL | HIST_REC_SOLID)) || ((rec.flags & HIST_REC_PERIODIC) != 0) != (img != 0))
                   continue;
                 word |= COL_HIST_BIT;
-                for (int d = 0; d < 3; ++d)
-                  P.new_list.hist[3 * size_t(e) + d] = rec.h[d];
+                P.new_list.hist[e] = make_double4(rec.h[0], rec.h[1], rec.h[2], 0.0);
                 if (P.use_roll)
                   for (int d = 0; d < 3; ++d)
                     P.new_list.roll[3 * size_t(e) + d] = rec.roll[d];
@@ -1412,11 +1412,12 @@ namespace dem
                 r.rid = P.id[c & COL_INDEX_MASK];
                 r.flags = (P.use_img && P.list.img[e]) ? HIST_REC_PERIODIC : 0u;
                 r.pad = 0;
+                const double4 hh = P.list.hist[e];
+                r.h[0] = hh.x;
+                r.h[1] = hh.y;
+                r.h[2] = hh.z;
                 for (int d = 0; d < 3; ++d)
-                  {
-                    r.h[d] = P.list.hist[3 * size_t(e) + d];
-                    r.roll[d] = P.use_roll ? P.list.roll[3 * size_t(e) + d] : 0.0;
-                  }
+                  r.roll[d] = P.use_roll ? P.list.roll[3 * size_t(e) + d] : 0.0;
                 P.out[base + n] = r;
               }
             ++n;

@@ -12,7 +12,7 @@
 //
 //   row_start[p], col[e]          CSR contact list, FULL (each unordered pair appears in the
 //                                 row of both particles); col bit 31 = "history is non-zero"
-//   hist[e][3], roll[e][3]        tangential displacement / EPSD spring torque of entry e in the
+//   hist[e] (double4), roll[e][3] tangential displacement / EPSD spring torque of entry e in the
 //                                 orientation row-particle -> col-particle. Both rows keep their own
 //                                 copy; the arithmetic is exactly antisymmetric so the copies stay
 //                                 bit-wise negatives of each other.
@@ -86,7 +86,7 @@ namespace dem
   {
     uint32_t *row_start;
     uint32_t *col;
-    double *hist; // [E][3]
+    double4 *hist; // [E] one 32-byte row per entry: (x, y, z, unused) — a single 256-bit access, one DRAM sector
     double *roll; // [E][3] (EPSD only, else nullptr)
     uint8_t *img; // periodic only, else nullptr
     uint8_t *rowl; // [E] row of the entry modulo 32 (= lane of the step kernel's warp that owns it)

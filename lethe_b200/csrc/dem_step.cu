@@ -78,6 +78,54 @@ namespace dem
       return r;
     }
 
+
+    // 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256). A double4 row is one 32-byte
+    // sector; CUDA 12's double4 is only 16-byte aligned for the compiler, which therefore emits two
+    // 128-bit requests per row — twice the L1 wavefronts for a gather that lands one line per lane.
+    // All rows here are 32-byte aligned (cudaMalloc base + 32 * index).
+#ifndef DEM_LD256
+#define DEM_LD256 1
+#endif
+    __device__ __forceinline__ double4 ld_row(const double4 *p)
+    {
+#if DEM_LD256
+      double4 r;
+      asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+      return r;
+#else
+      return *p;
+#endif
+    }
+    // the same for a row this thread may have written earlier in the launch (history): ordered with its stores
+    __device__ __forceinline__ double4 ld_row_rw(const double4 *p)
+    {
+#if DEM_LD256
+      double4 r;
+      asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+      return r;
+#else
+      return *p;
+#endif
+    }
+#ifndef DEM_STAGE
+#define DEM_STAGE 0 // 1: the operands of a round are gathered by cp.async into shared memory (no registers held across the latency)
+#endif
+    // 32-byte row -> two conflict-free 16-byte halves in shared memory, asynchronously
+    __device__ __forceinline__ void cp_async_row(double2 *lo, double2 *hi, const void *g)
+    {
+      const uint32_t a = uint32_t(__cvta_generic_to_shared(lo)), b = uint32_t(__cvta_generic_to_shared(hi));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(b), "l"(reinterpret_cast<const char *>(g) + 16) : "memory");
+    }
+    __device__ __forceinline__ void st_row(double4 *p, const double4 &r)
+    {
+#if DEM_LD256
+      asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.x), "d"(r.y), "d"(r.z), "d"(r.w) : "memory");
+#else
+      *p = r;
+#endif
+    }
+
     // img = 1 + (sx+1) + 3*(sy+1) + 9*(sz+1) for a neighbour seen through the periodic
     // image shifted by (sx*Lx, sy*Ly, sz*Lz); 0 = no image.
     __device__ __forceinline__ void decode_image(uint32_t img, const double *L, vec3 &shift, bool &i_am_two)
@@ -94,13 +142,12 @@ namespace dem
 
     // Canonical positions of particle one / two of the pair (row particle, neighbour).
     template <bool PERIODIC>
-    __device__ __forceinline__ void pair_positions(const StepParams &P, uint32_t e, const double4 &pme, const double4 &pj, vec3 &x1,
+    __device__ __forceinline__ void pair_positions(const StepParams &P, uint32_t img, const double4 &pme, const double4 &pj, vec3 &x1,
                                                    vec3 &x2, double &dsum, bool &i_am_two)
     {
       i_am_two = false;
       if constexpr (PERIODIC)
         {
-          const uint32_t img = P.list.img[e];
           if (img)
             {
               vec3 shift;
@@ -138,14 +185,17 @@ namespace dem
       double disp[32];                   // per owner: accumulated displacement, loaded with the state
       uint32_t w0[32], w1[32];           // per owner: its range of the wall list
       uint32_t halo[4];                  // HaloPush bits / prefix of this 32-row block, per direction
+#if DEM_STAGE
+      double2 stg[4][2][32];             // round operands (neighbour pos / vel / omg, history row) landed by cp.async, lane-private
+#endif
     };
 
     template <int MODEL, int ROLLING, bool PERIODIC, bool MIXED>
     __global__ void __launch_bounds__(32 * STEP_WARPS, MIXED ? STEP_MIN_BLOCKS_MIXED : STEP_MIN_BLOCKS) k_step(const __grid_constant__ StepParams P, const __grid_constant__ MaterialTables mt)
     {
-      __shared__ WarpScratch scratch[STEP_WARPS];
+      extern __shared__ __align__(16) unsigned char scratch_raw[]; // STEP_WARPS x WarpScratch (may exceed the 48 KB static limit)
       const uint32_t lane = threadIdx.x & 31u;
-      WarpScratch &S = scratch[threadIdx.x >> 5];
+      WarpScratch &S = reinterpret_cast<WarpScratch *>(scratch_raw)[threadIdx.x >> 5];
       const uint32_t warp_base = (blockIdx.x * STEP_WARPS + (threadIdx.x >> 5)) * 32u;
       if (warp_base >= P.n_owned)
         return; // whole warp
@@ -166,9 +216,9 @@ namespace dem
       uint32_t own_w0 = 0, own_w1 = 0;
       if (valid)
         {
-          own_pos = P.in.pos[i];
-          own_vel = P.in.vel[i];
-          own_omg = P.in.omg[i];
+          own_pos = ld_row(P.in.pos + i);
+          own_vel = ld_row(P.in.vel + i);
+          own_omg = ld_row(P.in.omg + i);
           own_disp = P.disp[i];
           own_w0 = P.walls.row_start[i];
           own_w1 = P.walls.row_start[i + 1];
@@ -205,26 +255,54 @@ namespace dem
             const uint32_t c = S.q_c[slot];
             const uint32_t j = c & COL_INDEX_MASK;
             const double4 pme = S.pos[owner];
-            const double4 pj = P.in.pos[j];
-            const ParticleView me = make_view(pme, S.vel[owner], S.omg[owner]);
-            const ParticleView other = make_view(pj, P.in.vel[j], P.in.omg[j]);
-            vec3 x1, x2;
-            double dsum;
-            bool i_am_two;
-            pair_positions<PERIODIC>(P, e, pme, pj, x1, x2, dsum, i_am_two);
-            const double distance = sqrt(dist2(x1, x2));
-            const double normal_overlap = 0.5 * dsum - distance;
+            // every operand of the pair is requested here, before the first use of any of them
+            double4 *hp = P.list.hist + size_t(e);
+#if DEM_STAGE
+            cp_async_row(&S.stg[0][0][lane], &S.stg[0][1][lane], P.in.pos + j);
+            cp_async_row(&S.stg[1][0][lane], &S.stg[1][1][lane], P.in.vel + j);
+            cp_async_row(&S.stg[2][0][lane], &S.stg[2][1][lane], P.in.omg + j);
+            if (c & COL_HIST_BIT)
+              cp_async_row(&S.stg[3][0][lane], &S.stg[3][1][lane], hp);
+            uint32_t img = 0;
+            if constexpr (PERIODIC)
+              img = P.list.img[e];
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+            const double2 pj0 = S.stg[0][0][lane], pj1 = S.stg[0][1][lane], vj0 = S.stg[1][0][lane], vj1 = S.stg[1][1][lane],
+                          wj0 = S.stg[2][0][lane], wj1 = S.stg[2][1][lane];
+            const double4 pj = make_double4(pj0.x, pj0.y, pj1.x, pj1.y), vj = make_double4(vj0.x, vj0.y, vj1.x, vj1.y),
+                          wj = make_double4(wj0.x, wj0.y, wj1.x, wj1.y);
+#else
+            const double4 pj = ld_row(P.in.pos + j);
+            const double4 vj = ld_row(P.in.vel + j);
+            const double4 wj = ld_row(P.in.omg + j);
+            uint32_t img = 0;
+            if constexpr (PERIODIC)
+              img = P.list.img[e];
+#endif
             vec3 h = v3(0, 0, 0), rs = v3(0, 0, 0);
-            double *hp = P.list.hist + 3 * size_t(e);
             if (c & COL_HIST_BIT)
               {
-                h = v3(hp[0], hp[1], hp[2]);
+#if DEM_STAGE
+                const double2 h0 = S.stg[3][0][lane], h1 = S.stg[3][1][lane];
+                const double4 h4 = make_double4(h0.x, h0.y, h1.x, h1.y);
+#else
+                const double4 h4 = ld_row_rw(hp);
+#endif
+                h = v3(h4.x, h4.y, h4.z);
                 if constexpr (ROLLING == LETHE_ROLLING_EPSD)
                   {
                     const double *rp = P.list.roll + 3 * size_t(e);
                     rs = v3(rp[0], rp[1], rp[2]);
                   }
               }
+            const ParticleView me = make_view(pme, S.vel[owner], S.omg[owner]);
+            const ParticleView other = make_view(pj, vj, wj);
+            vec3 x1, x2;
+            double dsum;
+            bool i_am_two;
+            pair_positions<PERIODIC>(P, img, pme, pj, x1, x2, dsum, i_am_two);
+            const double distance = sqrt(dist2(x1, x2));
+            const double normal_overlap = 0.5 * dsum - distance;
             const double2 self = S.self[owner];
             vec3 fc, tc; // what the row particle receives: F -= fc, T += tc
             if constexpr (!MIXED)
@@ -311,9 +389,7 @@ namespace dem
                     rs = to_double(rf);
                   }
               }
-            hp[0] = h.x;
-            hp[1] = h.y;
-            hp[2] = h.z;
+            st_row(hp, make_double4(h.x, h.y, h.z, 0.0));
             if constexpr (ROLLING == LETHE_ROLLING_EPSD)
               {
                 double *rp = P.list.roll + 3 * size_t(e);
@@ -380,6 +456,7 @@ namespace dem
       while (eb < E1)
         {
           // ---------------- phase A ----------------
+          // rowl and (periodic) img travel with col, one sweep iteration ahead: ow_nx = rowl | img << 8
           uint32_t c_nx[SWEEP], ow_nx[SWEEP];
 #pragma unroll
           for (int u = 0; u < SWEEP; ++u)
@@ -387,6 +464,8 @@ namespace dem
               const uint32_t e = eb + 32u * u + lane;
               c_nx[u] = e < E1 ? P.list.col[e] : 0u;
               ow_nx[u] = e < E1 ? P.list.rowl[e] : 0u;
+              if constexpr (PERIODIC)
+                ow_nx[u] |= e < E1 ? uint32_t(P.list.img[e]) << 8 : 0u;
             }
           while (eb < E1 && q_n + 32u * SWEEP <= QUEUE)
             {
@@ -399,7 +478,7 @@ namespace dem
                   ow[u] = ow_nx[u];
                   const uint32_t e = eb + 32u * u + lane;
                   if (e < E1)
-                    pj[u] = P.in.pos[c[u] & COL_INDEX_MASK];
+                    pj[u] = ld_row(P.in.pos + (c[u] & COL_INDEX_MASK));
                 }
 #pragma unroll
               for (int u = 0; u < SWEEP; ++u)
@@ -407,6 +486,8 @@ namespace dem
                   const uint32_t e = eb + 32u * (SWEEP + u) + lane;
                   c_nx[u] = e < E1 ? P.list.col[e] : 0u;
                   ow_nx[u] = e < E1 ? P.list.rowl[e] : 0u;
+                  if constexpr (PERIODIC)
+                    ow_nx[u] |= e < E1 ? uint32_t(P.list.img[e]) << 8 : 0u;
                 }
 #pragma unroll
               for (int u = 0; u < SWEEP; ++u)
@@ -415,11 +496,11 @@ namespace dem
                   bool touching = false;
                   if (e < E1)
                     {
-                      const double4 pme = S.pos[ow[u]];
+                      const double4 pme = S.pos[ow[u] & 31u];
                       vec3 x1, x2;
                       double dsum;
                       bool i_am_two;
-                      pair_positions<PERIODIC>(P, e, pme, pj[u], x1, x2, dsum, i_am_two);
+                      pair_positions<PERIODIC>(P, ow[u] >> 8, pme, pj[u], x1, x2, dsum, i_am_two);
                       const double d2 = dist2(x1, x2);
                       // in contact  <=>  0.5*dsum - sqrt(d2) > threshold (…force.h:1868-1876). Decide
                       // without the square root when d2 is clearly on one side of (0.5*dsum - thr)^2.
@@ -433,7 +514,7 @@ namespace dem
                         touching = (0.5 * dsum - sqrt(d2)) > mt.pp_force_threshold;
 #ifdef DEM_EXPERIMENT_HALF
                       // timing experiment only (wrong physics): the cost of evaluating each pair once
-                      if ((c[u] & COL_INDEX_MASK) < warp_base + ow[u])
+                      if ((c[u] & COL_INDEX_MASK) < warp_base + (ow[u] & 31u))
                         touching = false;
 #endif
                       // contact_info.tangential_displacement.clear() (…force.h:2057-2063): dropping
@@ -449,7 +530,7 @@ namespace dem
                         // the pair will be evaluated a few hundred cycles from now: start moving its
                         // operands (neighbour velocity / angular velocity, history row) towards the SM
                         const uint32_t jj = c[u] & COL_INDEX_MASK;
-                        const double *hq = P.list.hist + 3 * size_t(e);
+                        const double4 *hq = P.list.hist + size_t(e);
 #if DEM_PREFETCH == 1
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(P.in.vel + jj));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(P.in.omg + jj));
@@ -466,7 +547,7 @@ namespace dem
                       const uint32_t slot = q_n + __popc(m & ((1u << lane) - 1u));
                       S.q_e[slot] = e;
                       S.q_c[slot] = c[u];
-                      S.q_owner[slot] = uint8_t(ow[u]);
+                      S.q_owner[slot] = uint8_t(ow[u] & 31u);
                     }
                   q_n += __popc(m);
                 }
@@ -660,9 +741,9 @@ namespace dem
         }
       const double4 new_pos = make_double4(x.x, x.y, x.z, pi.w), new_vel = make_double4(v.x, v.y, v.z, vi.w),
                     new_omg = make_double4(om.x, om.y, om.z, wi.w);
-      P.out.pos[i] = new_pos;
-      P.out.vel[i] = new_vel;
-      P.out.omg[i] = new_omg;
+      st_row(P.out.pos + i, new_pos);
+      st_row(P.out.vel + i, new_vel);
+      st_row(P.out.omg + i, new_omg);
       // fused halo push: boundary-layer rows also go to the neighbour GPU's ghost slots
 #pragma unroll
       for (int d = 0; d < 2; ++d)
@@ -671,9 +752,9 @@ namespace dem
           if ((bits >> lane) & 1u)
             {
               const uint32_t k = P.halo.base[d] + S.halo[2 + d] + __popc(bits & ((1u << lane) - 1u));
-              P.halo.pos[d][k] = new_pos;
-              P.halo.vel[d][k] = new_vel;
-              P.halo.omg[d][k] = new_omg;
+              st_row(P.halo.pos[d] + k, new_pos);
+              st_row(P.halo.vel[d] + k, new_vel);
+              st_row(P.halo.omg[d] + k, new_omg);
             }
         }
 
@@ -698,7 +779,19 @@ namespace dem
         return;
       constexpr uint32_t per_block = 32 * STEP_WARPS;
       const dim3 block(per_block), grid((p.n_owned + per_block - 1) / per_block);
-      auto launch = [&](auto kernel) { kernel<<<grid, block, 0, stream>>>(p, mt); };
+      constexpr size_t smem = sizeof(WarpScratch) * STEP_WARPS;
+      auto launch = [&](auto kernel) {
+        static bool configured[64] = {}; // per instantiation (the lambda's operator() is a template) and device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63])
+          {
+            // a failure here surfaces as a launch error, which the engine checks after every step launch
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            configured[dev & 63] = true;
+          }
+        kernel<<<grid, block, smem, stream>>>(p, mt);
+      };
       if (p.mixed_precision)
         {
           if (p.periodic_any)
@@ -944,6 +1037,13 @@ namespace dem
 
   void launch_step(int pp_model, int rolling_model, const StepParams &p, const MaterialTables &mt, cudaStream_t stream)
   {
+#ifdef DEM_BENCH_VARIANT
+    // timing builds (tools/build_variant.sh): only the model of the bench workloads is instantiated
+    if (pp_model != LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP)
+      abort();
+    launch_m<LETHE_PP_HERTZ_MINDLIN_LIMIT_OVERLAP>(rolling_model, p, mt, stream);
+    return;
+#else
     switch (pp_model)
       {
         case LETHE_PP_LINEAR:
@@ -965,5 +1065,6 @@ namespace dem
           launch_m<LETHE_PP_DMT>(rolling_model, p, mt, stream);
           break;
       }
+#endif
   }
 } // namespace dem
