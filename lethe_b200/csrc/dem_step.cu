@@ -101,12 +101,24 @@ namespace dem
     {
 #if DEM_LD256
       double4 r;
+#if DEM_STREAM
+      asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+#else
       asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+#endif
       return r;
 #else
       return *p;
 #endif
     }
+#ifndef DEM_STREAM
+#define DEM_STREAM 0 // 1: evict-first loads / stores for the list streams (col, rowl, img, history rows)
+#endif
+#if DEM_STREAM
+#define DEM_LDS(p) __ldcs(p)
+#else
+#define DEM_LDS(p) (*(p))
+#endif
 #ifndef DEM_STAGE
 #define DEM_STAGE 0 // 1: the operands of a round are gathered by cp.async into shared memory (no registers held across the latency)
 #endif
@@ -116,6 +128,17 @@ namespace dem
       const uint32_t a = uint32_t(__cvta_generic_to_shared(lo)), b = uint32_t(__cvta_generic_to_shared(hi));
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory");
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(b), "l"(reinterpret_cast<const char *>(g) + 16) : "memory");
+    }
+    // history rows are touched once per step: streaming (evict-first) accesses keep them from displacing the gathered state
+    __device__ __forceinline__ void st_row_stream(double4 *p, const double4 &r)
+    {
+#if DEM_STREAM && DEM_LD256
+      asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.x), "d"(r.y), "d"(r.z), "d"(r.w) : "memory");
+#elif DEM_LD256
+      asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.x), "d"(r.y), "d"(r.z), "d"(r.w) : "memory");
+#else
+      *p = r;
+#endif
     }
     __device__ __forceinline__ void st_row(double4 *p, const double4 &r)
     {
@@ -389,7 +412,7 @@ namespace dem
                     rs = to_double(rf);
                   }
               }
-            st_row(hp, make_double4(h.x, h.y, h.z, 0.0));
+            st_row_stream(hp, make_double4(h.x, h.y, h.z, 0.0));
             if constexpr (ROLLING == LETHE_ROLLING_EPSD)
               {
                 double *rp = P.list.roll + 3 * size_t(e);
@@ -462,10 +485,10 @@ namespace dem
           for (int u = 0; u < SWEEP; ++u)
             {
               const uint32_t e = eb + 32u * u + lane;
-              c_nx[u] = e < E1 ? P.list.col[e] : 0u;
-              ow_nx[u] = e < E1 ? P.list.rowl[e] : 0u;
+              c_nx[u] = e < E1 ? DEM_LDS(P.list.col + e) : 0u;
+              ow_nx[u] = e < E1 ? DEM_LDS(P.list.rowl + e) : 0u;
               if constexpr (PERIODIC)
-                ow_nx[u] |= e < E1 ? uint32_t(P.list.img[e]) << 8 : 0u;
+                ow_nx[u] |= e < E1 ? uint32_t(DEM_LDS(P.list.img + e)) << 8 : 0u;
             }
           while (eb < E1 && q_n + 32u * SWEEP <= QUEUE)
             {
@@ -484,10 +507,10 @@ namespace dem
               for (int u = 0; u < SWEEP; ++u)
                 {
                   const uint32_t e = eb + 32u * (SWEEP + u) + lane;
-                  c_nx[u] = e < E1 ? P.list.col[e] : 0u;
-                  ow_nx[u] = e < E1 ? P.list.rowl[e] : 0u;
+                  c_nx[u] = e < E1 ? DEM_LDS(P.list.col + e) : 0u;
+                  ow_nx[u] = e < E1 ? DEM_LDS(P.list.rowl + e) : 0u;
                   if constexpr (PERIODIC)
-                    ow_nx[u] |= e < E1 ? uint32_t(P.list.img[e]) << 8 : 0u;
+                    ow_nx[u] |= e < E1 ? uint32_t(DEM_LDS(P.list.img + e)) << 8 : 0u;
                 }
 #pragma unroll
               for (int u = 0; u < SWEEP; ++u)
