@@ -414,10 +414,15 @@ def main():
     # rows down). The row -> id table goes up with the first call and again whenever particles changed
     # owner in a rebuild (the rank then re-reads its owned rows, inside the timed region).
     def owned_rows():
-        ids_, x_, props_ = engine.get_particles()
-        state = np.ascontiguousarray(np.concatenate([x_, props_[:, 3:9]], axis=1))
+        # the host keeps its rows in the order the engine names for the transfer (by cell layer, cell-sorted inside a layer:
+        # the kind of order a cell-by-cell walk of ParticleHandler gives), not by particle id
+        ids_, x_, props_ = engine.get_particles()  # sorted by id
+        order = np.searchsorted(ids_, engine.get_transfer_order())
+        state = np.empty((len(ids_), 9))
+        state[:, :3] = x_[order]
+        state[:, 3:] = props_[order, 3:9]
         del x_, props_
-        return [torch.from_numpy(ids_.copy()).pin_memory(), torch.from_numpy(state).pin_memory(), True]
+        return [torch.from_numpy(ids_[order]).pin_memory(), torch.from_numpy(state).pin_memory(), True]
 
     id_uploads = [0]
 
@@ -447,6 +452,7 @@ def main():
     barrier()
     dt = time.perf_counter() - t0
     n_id_rows = id_uploads[0]
+    streamed = engine.host_pipeline_stats()
     barrier()
     t0 = time.perf_counter()
     rows, seen = host_step(rows, S, seen)
@@ -469,6 +475,8 @@ def main():
         "call": "lethe_dem_step_host_state(n_steps=1) on every rank: upload the x/v/omega rows of the owned particles (72 B each; "
                 "the id table only when ownership changed), 1 DEM step, download the rows, every DEM step",
         "batched": {"steps_per_call": S, "value": n_global * S / dtb, "unit": "particle-steps/s"},
+        # rank 0's calls that ran as upload / partial step launches / download pipelined over the rows
+        "streamed_calls": streamed[0], "stream_plans": streamed[1],
     }
     del rows
 

@@ -268,9 +268,26 @@ int lethe_dem_step_host(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
  * x, y, z, v_x, v_y, v_z, omega_x, omega_y, omega_z (what Integrator::integrate writes,
  * velocity_verlet_integrator.cc:214-290); type, diameter and mass keep the values given at
  * insertion. id = the particle of every row; NULL = the table of the previous call (same n),
- * which is then not uploaded again. 72 bytes per particle each way instead of 100 / 96. */
+ * which is then not uploaded again. 72 bytes per particle each way instead of 100 / 96.
+ * With n_steps = 1 on one GPU the call is STREAMED when nothing but the plain step runs in it: the rows go up in the
+ * caller's order in a few contiguous stages, the step kernel is launched on the blocks of
+ * particles whose own rows and listed neighbours have arrived, and rows go back down as soon as their blocks are
+ * stepped, so the download runs under the upload (PCIe is full duplex). Results are bit-identical to the plain
+ * call. LETHE_DEM_HOST_PIPELINE=0 switches it off, LETHE_DEM_HOST_STAGES (8) and LETHE_DEM_HOST_PIPELINE_MIN_ROWS
+ * (262144) tune it. Page-locked host rows are needed for the copies to overlap. LETHE_DEM_HOST_ZEROCOPY=1 lets the
+ * device write page-locked rows itself, block by block as the step finishes them (slower than the copy engines on the
+ * PCIe Gen5 boxes measured; off by default). */
 int lethe_dem_step_host_state(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
                               const uint32_t *id, double *state9);
+/* The ids of the owned particles in the row order that lets the streamed call overlap its copies best: by cell layer
+ * along the axis with the most layers, cell-sorted inside a layer (the kind of order a cell-by-cell walk of
+ * ParticleHandler gives). With rows in this order a block of particles is complete one or two layers after its own rows
+ * have arrived, so upload and download run side by side almost from the first stage. Any other order is still correct.
+ * A host re-reads it when it re-reads its rows (after insertion, or when particles changed owner). */
+int lethe_dem_get_transfer_order(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id);
+/* How often lethe_dem_step_host_state took the streamed form, how many times its plan was made (once per list
+ * rebuild or new id table) and how many of the streamed calls wrote the host rows directly from the device. */
+int lethe_dem_host_pipeline_stats(lethe_dem_ctx *ctx, uint64_t *n_streamed_calls, uint64_t *n_plans, uint64_t *n_direct_calls);
 
 /* The CFD-DEM particle record (DEM::CFDDEMProperties::PropertiesIndex, include/core/dem_properties.h:92-142:
  * 23 doubles per particle — the 9 DEM properties, then fem_force_two_way_coupling[3], fem_force_one_way_

@@ -151,6 +151,8 @@ ABI_SYMBOLS = [
     "force_contact_search",
     "step_host",
     "step_host_state",
+    "host_pipeline_stats",
+    "get_transfer_order",
     "set_external_loads",
     "restart_integration",
     "set_time",
@@ -376,6 +378,20 @@ class Engine:
         assert state9.dtype == np.float64 and state9.flags.c_contiguous and state9.shape[1] == 9
         id_arg = None if ids is None else _ptr(np.ascontiguousarray(ids, dtype=np.uint32), _p_u32)
         self._call("step_host_state", C.c_uint64(n_steps), C.c_uint64(len(state9)), id_arg, _ptr(state9, _p_f64))
+
+    def get_transfer_order(self):
+        """Ids of the owned particles in the row order that overlaps the copies of step_host_state best."""
+        n = self.n_particles()
+        ids = np.empty(n, np.uint32)
+        out = C.c_uint64()
+        self._call("get_transfer_order", C.c_uint64(n), C.byref(out), _ptr(ids, _p_u32))
+        return ids[: out.value]
+
+    def host_pipeline_stats(self):
+        """(calls of step_host_state that took the streamed form, plans made, streamed calls that wrote the host rows directly)."""
+        a, b, d = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._call("host_pipeline_stats", C.byref(a), C.byref(b), C.byref(d))
+        return a.value, b.value, d.value
 
     def step_host_state_ptr(self, n_steps, n, id_ptr, state_ptr):
         """Same on raw host addresses (pinned buffers); id_ptr = 0 reuses the previous id table."""

@@ -260,6 +260,23 @@ struct lethe_dem_ctx
   bool open_next_step = false; // lethe_dem_restart_integration
   DevBuf<uint32_t> host_row_ids;
   uint64_t host_row_ids_n = 0;
+  uint64_t host_row_ids_version = 0; // bumped whenever the caller hands over a new row -> id table
+  // streamed host step: the plan that orders upload, partial step launches and download over space
+  struct HostPipe
+  {
+    bool valid = false;
+    uint64_t rebuild_gen = ~0ull, ids_version = ~0ull;
+    uint32_t n_rows = 0, n_owned = 0, seg_rows = 0, n_seg = 0, n_stages = 0, n_blocks = 0;
+    DevBuf<uint32_t> seg_up, seg_down, block_ready, up_list, down_list, block_list, row_of_slot;
+    DevBuf<uint8_t> up_stage_of_slot;
+    std::vector<uint32_t> up_off, down_off, block_off; // per stage: offsets into up_list / down_list / block_list
+    // per stage: runs of consecutive host rows (first row, row count) moved by one copy each
+    std::vector<std::vector<std::pair<uint64_t, uint64_t>>> up_runs, down_runs;
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_down;
+    cudaEvent_t ev_begin = nullptr;
+    uint64_t n_calls = 0, n_plans = 0, n_zero_copy_calls = 0;
+  } host_pipe;
   DevBuf<double> stage_x, stage_p;
   DevBuf<StatsPartial> stats_partials;
 

@@ -660,10 +660,10 @@ namespace
     launch_integrate_temperature(hp, s);
   }
 
-  void launch_step_kernel(Ctx *c, int phase, bool speculative = false)
+  // the operands of one step kernel launch that do not depend on solids / external loads
+  void fill_step_params(Ctx *c, int phase, bool speculative, StepParams &P)
   {
     cudaStream_t s = c->stream;
-    StepParams P;
     std::memset(&P, 0, sizeof(P));
     P.in = c->st[c->cur].view();
     P.out = c->st[c->cur ^ 1].view();
@@ -714,6 +714,13 @@ namespace
       }
     P.criterion = c->cfg.smallest_contact_search_criterion;
     P.moi_override = c->cfg.moi_override;
+  }
+
+  void launch_step_kernel(Ctx *c, int phase, bool speculative = false)
+  {
+    cudaStream_t s = c->stream;
+    StepParams P;
+    fill_step_params(c, phase, speculative, P);
     if (c->n_solids)
       {
         // dem.cc:1141-1147: move the solids (not in the closing half step, dem.cc:726-728), then
@@ -1000,6 +1007,234 @@ namespace
     c->contact_search_trigger = true;
   }
 
+
+  // ------------------------------------------------------------ streamed host step ----
+  // lethe_dem_step_host_state moves 72 B per particle up and 72 B down around a step that takes a tenth of either copy.
+  // PCIe is full duplex, but "upload everything, step, download everything" uses one direction at a time. The streamed
+  // form takes the step apart: the host rows go up in the caller's order in a few contiguous stages, the
+  // step kernel is launched on the 128-row blocks whose own rows and listed neighbours have all arrived
+  // (StepParams::block_list), and a segment goes back down as soon as every block it has rows in has been stepped — so the
+  // download of the first slabs runs under the upload of the later ones. The kernels that touch a particle, their
+  // operands and their order per particle are those of the plain call: results are bit-identical
+  // (test_streamed_host_step_is_bitwise_identical). The plan depends on the list and on the row -> id table only, so it
+  // is made once per rebuild (HostPlanParams, dem_kernels.cuh). Calls that cannot be taken apart (a new list is due,
+  // solids, external loads, sparse contacts, heat transfer, several ranks, more than one step) run the plain form.
+  int env_int(const char *name, int fallback)
+  {
+    const char *e = std::getenv(name);
+    return e && *e ? std::atoi(e) : fallback;
+  }
+
+  bool host_pipe_eligible(Ctx *c, uint64_t n_steps, uint64_t n)
+  {
+    const int wanted = env_int("LETHE_DEM_HOST_PIPELINE", 1); // read per call: tests switch it between calls
+    const int min_rows = env_int("LETHE_DEM_HOST_PIPELINE_MIN_ROWS", 262144);
+    if (!wanted || n_steps != 1 || n < uint64_t(std::max(1, min_rows)) || n >= 0xffffffffull)
+      return false;
+    if (c->multi.enabled() || c->thermal_enabled || c->n_solids || c->ext_enabled || c->asc_enabled || c->timers_enabled ||
+        c->cfg.store_forces || c->count_touching)
+      return false;
+    if (c->contact_search_trigger || c->clear_history_trigger || c->open_next_step || c->lists[c->cur_list].n_rows != c->n_owned ||
+        c->n_owned == 0)
+      return false;
+    const uint64_t it = c->iteration_number + 1;
+    if (it <= 1 && !c->cfg.restart)
+      return false; // the opening half step
+    const uint64_t freq = uint64_t(std::max(1, c->cfg.contact_detection_frequency));
+    if ((it % freq) == 0)
+      {
+        if (c->cfg.detection == LETHE_DETECTION_CONSTANT)
+          return false;
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (*c->h_flag)
+          return false; // the previous step asked for a new list: the plain call rebuilds
+      }
+    return true;
+  }
+
+  void host_pipe_plan(Ctx *c, uint64_t n)
+  {
+    auto &hp = c->host_pipe;
+    cudaStream_t s = c->stream;
+    hp.valid = false;
+    hp.rebuild_gen = c->n_rebuilds;
+    hp.ids_version = c->host_row_ids_version;
+    hp.n_rows = uint32_t(n);
+    hp.n_owned = c->n_owned;
+    ++hp.n_plans;
+    hp.seg_rows = uint32_t(std::max(256, env_int("LETHE_DEM_HOST_SEG_ROWS", 4096)));
+    while ((n + hp.seg_rows - 1) / hp.seg_rows > uint64_t(std::max(64, env_int("LETHE_DEM_HOST_MAX_SEGS", 4096))))
+      hp.seg_rows *= 2;
+    hp.n_seg = uint32_t((n + hp.seg_rows - 1) / hp.seg_rows);
+    // stages: enough that the tail (the download of what only the last upload makes ready) is short, few enough that a
+    // stage's copies and launches stay large against their fixed cost
+    // (measured, B200 / PCIe Gen5: a stage costs about 0.1 ms of launch chain — scatter, partial step launch of less
+    // than a few waves, pack — so it should carry some 0.4 ms of copy: 262144 rows; 1 M rows: 4 stages, 8 M rows and more: 32)
+    const int auto_stages = int(std::min<uint64_t>(32, std::max<uint64_t>(2, (n + 131072) / 262144)));
+    const int K = std::min(std::min(env_int("LETHE_DEM_HOST_STAGES", auto_stages), 120), int(hp.n_seg));
+    if (K < 2)
+      return;
+    if (!hp.s_up)
+      {
+        CU_TRY(cudaStreamCreateWithFlags(&hp.s_up, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&hp.s_down, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&hp.ev_begin, cudaEventDisableTiming));
+      }
+    while (hp.ev_up.size() < size_t(K))
+      {
+        cudaEvent_t a, b;
+        CU_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        hp.ev_up.push_back(a);
+        hp.ev_down.push_back(b);
+      }
+    hp.n_stages = uint32_t(K);
+    hp.n_blocks = (c->n_owned + STEP_BLOCK_ROWS - 1) / STEP_BLOCK_ROWS;
+    const size_t n_slots = size_t(c->n_owned) + c->n_ghost;
+    hp.seg_up.ensure(hp.n_seg);
+    hp.seg_down.ensure(hp.n_seg);
+    hp.block_ready.ensure(hp.n_blocks);
+    hp.up_stage_of_slot.ensure(n_slots);
+    hp.up_list.ensure(hp.n_seg);
+    hp.down_list.ensure(hp.n_seg);
+    hp.block_list.ensure(hp.n_blocks);
+    hp.row_of_slot.ensure(std::max<size_t>(c->n_owned, 1));
+    CU_TRY(cudaMemsetAsync(hp.row_of_slot.p, 0xff, size_t(c->n_owned) * 4, s));
+    CU_TRY(cudaMemsetAsync(hp.seg_down.p, 0, size_t(hp.n_seg) * 4, s));
+    CU_TRY(cudaMemsetAsync(hp.block_ready.p, 0, size_t(hp.n_blocks) * 4, s));
+    CU_TRY(cudaMemsetAsync(hp.up_stage_of_slot.p, 0, n_slots, s));
+    HostPlanParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.row_ids = c->host_row_ids.p;
+    P.n_rows = hp.n_rows;
+    P.seg_rows = hp.seg_rows;
+    P.slot_of_id = c->slot_of_id.p;
+    P.map_size = c->slot_map_size;
+    P.list = c->lists[c->cur_list].view();
+    P.n_owned = c->n_owned;
+    P.seg_up = hp.seg_up.p;
+    P.seg_down = hp.seg_down.p;
+    P.up_stage_of_slot = hp.up_stage_of_slot.p;
+    P.row_of_slot = hp.row_of_slot.p;
+    P.block_ready = hp.block_ready.p;
+    launch_host_plan(P, 0, s);
+    // upload stages: the caller's row order cut into K contiguous pieces, one copy each. (Ordering the segments
+    // breadth-first over their contact adjacency instead was measured and is worse: on a 3-D packing the waves are
+    // shells of hundreds of segments, so the readiness lag grows and the uploads fall apart into small copies.)
+    std::vector<uint32_t> seg_up(hp.n_seg), seg_down(hp.n_seg), ready(hp.n_blocks);
+    for (uint32_t g = 0; g < hp.n_seg; ++g)
+      seg_up[g] = uint32_t(uint64_t(g) * uint64_t(K) / hp.n_seg);
+    CU_TRY(cudaMemcpyAsync(hp.seg_up.p, seg_up.data(), size_t(hp.n_seg) * 4, cudaMemcpyHostToDevice, s));
+    for (int pass = 1; pass < 4; ++pass)
+      launch_host_plan(P, pass, s);
+    CU_TRY(cudaMemcpyAsync(seg_down.data(), hp.seg_down.p, size_t(hp.n_seg) * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(ready.data(), hp.block_ready.p, size_t(hp.n_blocks) * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    // a segment none of whose rows names a particle of this context still travels both ways (its rows come back unchanged)
+    for (uint32_t g = 0; g < hp.n_seg; ++g)
+      seg_down[g] = std::min(std::max(seg_down[g], seg_up[g]), uint32_t(K - 1));
+    // stable counting sorts by stage; consecutive segments of one stage move with one copy
+    auto order = [&](const std::vector<uint32_t> &stage, std::vector<uint32_t> &off, std::vector<uint32_t> &list) {
+      off.assign(size_t(K) + 1, 0);
+      for (uint32_t v : stage)
+        ++off[std::min(v, uint32_t(K - 1)) + 1];
+      for (int k = 0; k < K; ++k)
+        off[k + 1] += off[k];
+      list.resize(stage.size());
+      std::vector<uint32_t> at(off.begin(), off.end() - 1);
+      for (uint32_t g = 0; g < stage.size(); ++g)
+        list[at[std::min(stage[g], uint32_t(K - 1))]++] = g;
+    };
+    auto runs_of = [&](const std::vector<uint32_t> &off, const std::vector<uint32_t> &list,
+                       std::vector<std::vector<std::pair<uint64_t, uint64_t>>> &runs) {
+      runs.assign(size_t(K), {});
+      for (int k = 0; k < K; ++k)
+        for (uint32_t a = off[k]; a < off[k + 1];)
+          {
+            uint32_t b = a + 1;
+            while (b < off[k + 1] && list[b] == list[b - 1] + 1)
+              ++b;
+            const uint64_t first = uint64_t(list[a]) * hp.seg_rows;
+            const uint64_t end = std::min<uint64_t>(n, uint64_t(list[b - 1] + 1) * hp.seg_rows);
+            runs[k].emplace_back(first, end - first);
+            a = b;
+          }
+    };
+    std::vector<uint32_t> up_list, down_list, block_list;
+    order(seg_up, hp.up_off, up_list);
+    order(seg_down, hp.down_off, down_list);
+    order(ready, hp.block_off, block_list);
+    runs_of(hp.up_off, up_list, hp.up_runs);
+    runs_of(hp.down_off, down_list, hp.down_runs);
+    CU_TRY(cudaMemcpyAsync(hp.up_list.p, up_list.data(), size_t(hp.n_seg) * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(hp.down_list.p, down_list.data(), size_t(hp.n_seg) * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(hp.block_list.p, block_list.data(), size_t(hp.n_blocks) * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s)); // the host vectors go out of scope
+    hp.valid = true;
+  }
+
+  void step_host_state_streamed(Ctx *c, uint64_t n, double *state9)
+  {
+    auto &hp = c->host_pipe;
+    cudaStream_t s = c->stream;
+    const int K = int(hp.n_stages);
+    c->stage_p.ensure(9 * n);
+    c->iteration_number++;
+    c->current_time += c->cfg.dt;
+    StepParams P;
+    fill_step_params(c, PHASE_REGULAR, false, P);
+    const StateView out = c->st[c->cur ^ 1].view();
+    // page-locked host rows are addressable from the device: the stepped blocks' rows are then written straight into them
+    // by the pack kernel of each stage (no staging, no per-segment wait for the last block of a segment)
+    double *state9_dev = nullptr;
+    if (env_int("LETHE_DEM_HOST_ZEROCOPY", 0)) // measured on B200 / PCIe Gen5: device stores into host memory reach about half the copy engines' rate
+      {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, state9) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+          state9_dev = static_cast<double *>(attr.devicePointer);
+        else
+          cudaGetLastError();
+      }
+    CU_TRY(cudaEventRecord(hp.ev_begin, s));
+    CU_TRY(cudaStreamWaitEvent(hp.s_up, hp.ev_begin, 0));
+    CU_TRY(cudaStreamWaitEvent(hp.s_down, hp.ev_begin, 0));
+    for (int k = 0; k < K; ++k)
+      {
+        for (const auto &r : hp.up_runs[k])
+          CU_TRY(cudaMemcpyAsync(c->stage_p.p + 9 * r.first, state9 + 9 * r.first, 72 * r.second, cudaMemcpyHostToDevice, hp.s_up));
+        CU_TRY(cudaEventRecord(hp.ev_up[k], hp.s_up));
+        CU_TRY(cudaStreamWaitEvent(s, hp.ev_up[k], 0));
+        launch_update_state_rows_segs(hp.up_list.p + hp.up_off[k], hp.up_off[k + 1] - hp.up_off[k], hp.seg_rows, c->host_row_ids.p,
+                                      c->stage_p.p, uint32_t(n), c->slot_of_id.p, c->slot_map_size, P.in, s);
+        P.block_list = hp.block_list.p + hp.block_off[k];
+        P.n_blocks_listed = hp.block_off[k + 1] - hp.block_off[k];
+        if (P.n_blocks_listed)
+          launch_step(c->cfg.pp_model, c->cfg.rolling_model, P, c->mt, s);
+        if (state9_dev)
+          {
+            launch_pack_state_rows_blocks(P.block_list, P.n_blocks_listed, hp.row_of_slot.p, c->n_owned, out, state9_dev, s);
+            continue;
+          }
+        launch_pack_state_rows_segs(hp.down_list.p + hp.down_off[k], hp.down_off[k + 1] - hp.down_off[k], hp.seg_rows, c->host_row_ids.p,
+                                    uint32_t(n), c->slot_of_id.p, c->slot_map_size, out, c->stage_p.p, s);
+        CU_TRY(cudaEventRecord(hp.ev_down[k], s));
+        CU_TRY(cudaStreamWaitEvent(hp.s_down, hp.ev_down[k], 0));
+        for (const auto &r : hp.down_runs[k])
+          CU_TRY(cudaMemcpyAsync(state9 + 9 * r.first, c->stage_p.p + 9 * r.first, 72 * r.second, cudaMemcpyDeviceToHost, hp.s_down));
+      }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(c->step_done[c->iteration_number & 1], s));
+    c->cur ^= 1;
+    // reset_triggers (one_step)
+    c->contact_search_trigger = false;
+    c->clear_history_trigger = false;
+    ++hp.n_calls;
+    if (state9_dev)
+      ++hp.n_zero_copy_calls;
+    CU_TRY(cudaStreamSynchronize(s));
+    CU_TRY(cudaStreamSynchronize(hp.s_down));
+  }
+
   struct HostRows
   {
     std::vector<uint32_t> id;
@@ -1223,6 +1458,16 @@ void lethe_dem_destroy(lethe_dem_ctx *c)
     cudaFreeHost(const_cast<uint32_t *>(c->h_flag));
   if (c->h_remap)
     cudaFreeHost(const_cast<uint32_t *>(c->h_remap));
+  for (auto ev : c->host_pipe.ev_up)
+    cudaEventDestroy(ev);
+  for (auto ev : c->host_pipe.ev_down)
+    cudaEventDestroy(ev);
+  if (c->host_pipe.ev_begin)
+    cudaEventDestroy(c->host_pipe.ev_begin);
+  if (c->host_pipe.s_up)
+    cudaStreamDestroy(c->host_pipe.s_up);
+  if (c->host_pipe.s_down)
+    cudaStreamDestroy(c->host_pipe.s_down);
   if (c->stream)
     cudaStreamDestroy(c->stream);
   delete c;
@@ -1705,9 +1950,21 @@ int lethe_dem_step_host_state(lethe_dem_ctx *c, uint64_t n_steps, uint64_t n, co
             c->host_row_ids.ensure(n);
             CU_TRY(cudaMemcpyAsync(c->host_row_ids.p, id, n * 4, cudaMemcpyHostToDevice, s));
             c->host_row_ids_n = n;
+            ++c->host_row_ids_version;
           }
         else if (c->host_row_ids_n != n)
           throw std::runtime_error("step_host_state: id == NULL reuses the id table of the previous call, which had a different row count");
+        if (host_pipe_eligible(c, n_steps, n))
+          {
+            auto &hp = c->host_pipe;
+            if (!(hp.rebuild_gen == c->n_rebuilds && hp.ids_version == c->host_row_ids_version && hp.n_rows == n && hp.n_owned == c->n_owned))
+              host_pipe_plan(c, n);
+            if (hp.valid)
+              {
+                step_host_state_streamed(c, n, state9);
+                return;
+              }
+          }
         c->stage_p.ensure(9 * n);
         CU_TRY(cudaMemcpyAsync(c->stage_p.p, state9, 9 * n * 8, cudaMemcpyHostToDevice, s));
         launch_update_state_rows(c->host_row_ids.p, c->stage_p.p, uint32_t(n), c->slot_of_id.p, c->slot_map_size, c->st[c->cur].view(), s);
@@ -1721,6 +1978,53 @@ int lethe_dem_step_host_state(lethe_dem_ctx *c, uint64_t n_steps, uint64_t n, co
       }
     CU_TRY(cudaStreamSynchronize(s));
   });
+}
+
+int lethe_dem_get_transfer_order(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *id)
+{
+  return guarded(c, [&] {
+    const size_t n = c->n_owned;
+    *n_out = n;
+    if (n_max < n || n == 0)
+      return;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> ids(n);
+    std::vector<int32_t> cell(n);
+    CU_TRY(cudaMemcpy(ids.data(), c->st[c->cur].id.p, n * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(cell.data(), c->st[c->cur].cell_reg.p, n * 4, cudaMemcpyDeviceToHost));
+    const GridDesc &g = c->grid;
+    int axis = 0, best = 0;
+    for (int d = 0; d < 3; ++d)
+      {
+        const int layers = (d == g.slab_axis && g.slab_lo >= 0) ? g.slab_hi - g.slab_lo : g.n[d];
+        if (layers > best)
+          best = layers, axis = d;
+      }
+    auto layer_of = [&](int32_t cl) -> uint32_t {
+      if (cl < 0)
+        return 0u; // not registered in a cell yet (inserted since the last sort): first
+      return 1u + uint32_t(axis == 0 ? cl % g.n[0] : (axis == 1 ? (cl / g.n[0]) % g.n[1] : cl / (g.n[0] * g.n[1])));
+    };
+    // stable counting sort of the slots by layer: inside a layer the engine's cell-sorted order is kept
+    std::vector<uint64_t> start(size_t(g.n[axis]) + 2, 0);
+    for (size_t q = 0; q < n; ++q)
+      ++start[layer_of(cell[q]) + 1];
+    for (size_t l = 1; l < start.size(); ++l)
+      start[l] += start[l - 1];
+    for (size_t q = 0; q < n; ++q)
+      id[start[layer_of(cell[q])]++] = ids[q];
+  });
+}
+
+int lethe_dem_host_pipeline_stats(lethe_dem_ctx *c, uint64_t *n_streamed_calls, uint64_t *n_plans, uint64_t *n_direct_calls)
+{
+  if (n_direct_calls)
+    *n_direct_calls = c->host_pipe.n_zero_copy_calls;
+  if (n_streamed_calls)
+    *n_streamed_calls = c->host_pipe.n_calls;
+  if (n_plans)
+    *n_plans = c->host_pipe.n_plans;
+  return 0;
 }
 
 int lethe_dem_step_host(lethe_dem_ctx *c, uint64_t n_steps, uint64_t n, const uint32_t *id, double *x3, double *props9)

@@ -768,6 +768,117 @@ namespace dem
       p[6] = w.x, p[7] = w.y, p[8] = w.z;
     }
 
+
+    // ---- streamed host step (HostPlanParams, dem_kernels.cuh) ----
+    __device__ __forceinline__ uint32_t plan_slot_of_row(const HostPlanParams &P, uint32_t r)
+    {
+      const uint32_t pid = P.row_ids[r];
+      if (pid >= P.map_size)
+        return 0xffffffffu;
+      const uint32_t q = P.slot_of_id[pid];
+      return q < P.n_owned ? q : 0xffffffffu;
+    }
+    template <int PASS> __global__ void __launch_bounds__(256) k_host_plan(const __grid_constant__ HostPlanParams P)
+    {
+      const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+      if constexpr (PASS == 2)
+        {
+          // one thread per list row: the latest upload stage among the row's particle and its listed neighbours
+          if (t >= P.n_owned)
+            return;
+          uint32_t m = P.up_stage_of_slot[t];
+          for (uint32_t e = P.list.row_start[t]; e < P.list.row_start[t + 1]; ++e)
+            m = max(m, uint32_t(P.up_stage_of_slot[P.list.col[e] & COL_INDEX_MASK]));
+          m = __reduce_max_sync(__activemask(), m); // a warp = 32 consecutive rows of one 128-row block
+          if ((threadIdx.x & 31u) == 0 && m)
+            atomicMax(P.block_ready + t / STEP_BLOCK_ROWS, m);
+        }
+      else
+        {
+          if (t >= P.n_rows)
+            return;
+          const uint32_t q = plan_slot_of_row(P, t);
+          if (q == 0xffffffffu)
+            return;
+          const uint32_t seg = t / P.seg_rows;
+          if constexpr (PASS == 0)
+            P.row_of_slot[q] = t;
+          else if constexpr (PASS == 1)
+            P.up_stage_of_slot[q] = uint8_t(P.seg_up[seg]);
+          else
+            atomicMax(P.seg_down + seg, P.block_ready[q / STEP_BLOCK_ROWS]);
+        }
+    }
+
+    __global__ void __launch_bounds__(256) k_update_state_rows_segs(const uint32_t *seg_list, uint32_t seg_rows, const uint32_t *ids,
+                                                                    const double *state9, uint32_t n, const uint32_t *slot_of_id,
+                                                                    uint32_t map_size, StateView st)
+    {
+      const uint32_t k = seg_list[blockIdx.y] * seg_rows + blockIdx.x * blockDim.x + threadIdx.x;
+      if (blockIdx.x * blockDim.x + threadIdx.x >= seg_rows || k >= n)
+        return;
+      const uint32_t pid = ids[k];
+      if (pid >= map_size)
+        return;
+      const uint32_t q = slot_of_id[pid];
+      if (q == 0xffffffffu)
+        return;
+      const double *p = state9 + 9 * size_t(k);
+      st.pos[q] = make_double4(p[0], p[1], p[2], st.pos[q].w);
+      st.vel[q] = make_double4(p[3], p[4], p[5], st.vel[q].w);
+      st.omg[q] = make_double4(p[6], p[7], p[8], st.omg[q].w);
+    }
+
+    __global__ void __launch_bounds__(256) k_pack_state_rows_segs(const uint32_t *seg_list, uint32_t seg_rows, const uint32_t *ids, uint32_t n,
+                                                                  const uint32_t *slot_of_id, uint32_t map_size, StateView st, double *state9)
+    {
+      const uint32_t k = seg_list[blockIdx.y] * seg_rows + blockIdx.x * blockDim.x + threadIdx.x;
+      if (blockIdx.x * blockDim.x + threadIdx.x >= seg_rows || k >= n)
+        return;
+      const uint32_t pid = ids[k];
+      if (pid >= map_size)
+        return;
+      const uint32_t q = slot_of_id[pid];
+      if (q == 0xffffffffu)
+        return;
+      const double4 x = st.pos[q], v = st.vel[q], w = st.omg[q];
+      double *p = state9 + 9 * size_t(k);
+      p[0] = x.x, p[1] = x.y, p[2] = x.z;
+      p[3] = v.x, p[4] = v.y, p[5] = v.z;
+      p[6] = w.x, p[7] = w.y, p[8] = w.z;
+    }
+
+    // one thread block = one 128-slot block of the step kernel, one warp = 32 consecutive slots; the 32 x 9 doubles are
+    // transposed through shared memory so that consecutive lanes store consecutive words of the host rows
+    __global__ void __launch_bounds__(128) k_pack_state_rows_blocks(const uint32_t *block_list, const uint32_t *row_of_slot, uint32_t n_owned,
+                                                                    StateView st, double *state9)
+    {
+      __shared__ double buf[4][32 * 9];
+      __shared__ uint32_t rows[4][32];
+      const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+      const uint32_t q = block_list[blockIdx.x] * STEP_BLOCK_ROWS + threadIdx.x;
+      uint32_t r = 0xffffffffu;
+      if (q < n_owned)
+        {
+          r = row_of_slot[q];
+          const double4 x = st.pos[q], v = st.vel[q], w = st.omg[q];
+          double *b = buf[warp] + 9 * lane;
+          b[0] = x.x, b[1] = x.y, b[2] = x.z;
+          b[3] = v.x, b[4] = v.y, b[5] = v.z;
+          b[6] = w.x, b[7] = w.y, b[8] = w.z;
+        }
+      rows[warp][lane] = r;
+      __syncwarp();
+#pragma unroll
+      for (uint32_t k = 0; k < 9; ++k)
+        {
+          const uint32_t t = 32 * k + lane, rl = t / 9, comp = t - 9 * rl;
+          const uint32_t rr = rows[warp][rl];
+          if (rr != 0xffffffffu)
+            state9[9 * size_t(rr) + comp] = buf[warp][t];
+        }
+    }
+
     __device__ __forceinline__ void write_row(double4 x, double4 v, double4 w, double *x3, double *props9, size_t k)
     {
       x3[3 * k] = x.x;
@@ -1376,6 +1487,59 @@ namespace dem
     if (n)
       {
         k_pack_state_rows<<<blocks_for(n, 256), 256, 0, s>>>(ids, n, slot_of_id, slot_map_size, st, state9);
+        count_launch();
+      }
+  }
+  void launch_host_plan(const HostPlanParams &p, int pass, cudaStream_t s)
+  {
+    const uint32_t n = pass == 2 ? p.n_owned : p.n_rows;
+    if (!n)
+      return;
+    const unsigned blocks = blocks_for(n, 256);
+    switch (pass)
+      {
+        case 0:
+          k_host_plan<0><<<blocks, 256, 0, s>>>(p);
+          break;
+        case 1:
+          k_host_plan<1><<<blocks, 256, 0, s>>>(p);
+          break;
+        case 2:
+          k_host_plan<2><<<blocks, 256, 0, s>>>(p);
+          break;
+        default:
+          k_host_plan<3><<<blocks, 256, 0, s>>>(p);
+          break;
+      }
+    count_launch();
+  }
+  void launch_update_state_rows_segs(const uint32_t *seg_list, uint32_t n_segs, uint32_t seg_rows, const uint32_t *ids, const double *state9,
+                                     uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, cudaStream_t s)
+  {
+    // blockIdx.y = segment: at most 65535 of them per launch (the planner keeps the segment count far below that)
+    if (n_segs)
+      {
+        k_update_state_rows_segs<<<dim3(blocks_for(seg_rows, 256), n_segs), 256, 0, s>>>(seg_list, seg_rows, ids, state9, n, slot_of_id,
+                                                                                        slot_map_size, st);
+        count_launch();
+      }
+  }
+  void launch_pack_state_rows_segs(const uint32_t *seg_list, uint32_t n_segs, uint32_t seg_rows, const uint32_t *ids, uint32_t n,
+                                   const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, double *state9, cudaStream_t s)
+  {
+    if (n_segs)
+      {
+        k_pack_state_rows_segs<<<dim3(blocks_for(seg_rows, 256), n_segs), 256, 0, s>>>(seg_list, seg_rows, ids, n, slot_of_id, slot_map_size,
+                                                                                      st, state9);
+        count_launch();
+      }
+  }
+  void launch_pack_state_rows_blocks(const uint32_t *block_list, uint32_t n_blocks, const uint32_t *row_of_slot, uint32_t n_owned,
+                                     StateView st, double *state9, cudaStream_t s)
+  {
+    if (n_blocks)
+      {
+        k_pack_state_rows_blocks<<<n_blocks, 128, 0, s>>>(block_list, row_of_slot, n_owned, st, state9);
         count_launch();
       }
   }

@@ -147,6 +147,10 @@ namespace dem
     const BoundaryMotionDev *motions;
     const FloatingWallsDev *floating;
     uint32_t n_owned; // particles integrated by this rank
+    // partial launch (streamed host step): only the 128-row blocks block_list[0 .. n_blocks_listed) are
+    // stepped by this launch; nullptr = every block
+    const uint32_t *block_list;
+    uint32_t n_blocks_listed;
     int phase;
     int integrator; // lethe_integrator
     int mixed_precision; // pair model in float (lethe_precision)
@@ -161,6 +165,41 @@ namespace dem
   };
 
   void launch_step(int pp_model, int rolling_model, const StepParams &p, const MaterialTables &mt, cudaStream_t stream);
+  constexpr uint32_t STEP_BLOCK_ROWS = 128; // rows (particles) one thread block of the step kernel owns
+
+  // ---- streamed host step: lethe_dem_step_host_state pipelined over space ----
+  // The caller's host rows are cut into segments of seg_rows consecutive rows and go up in the caller's order, in n_stages
+  // contiguous copies (segment g in stage seg_up[g] = g * n_stages / n_seg). A 128-row block of the step kernel is
+  // ready in the latest upload stage of its own rows and of every particle its list rows name; a segment can go back to
+  // the host after the latest ready stage of the blocks its rows belong to. Any host order that is coherent in space
+  // (the engine's own cell-sorted order, the reference's cell-by-cell ParticleHandler order, slabs) makes most blocks
+  // ready with their own rows; an incoherent order degenerates to "everything is ready in the last stage", the plain call.
+  struct HostPlanParams
+  {
+    const uint32_t *row_ids; // [n_rows] particle id of every host row
+    uint32_t n_rows, seg_rows;
+    const uint32_t *slot_of_id;
+    uint32_t map_size;
+    ListView list;
+    uint32_t n_owned;
+    const uint32_t *seg_up;    // [n_seg] upload stage (host-made)
+    uint32_t *seg_down;        // [n_seg] download stage, zeroed
+    uint8_t *up_stage_of_slot; // [n_owned + ghosts], zeroed: particles without a host row are always there
+    uint32_t *row_of_slot;     // [n_owned] host row of every particle slot, initialised to 0xffffffff (none)
+    uint32_t *block_ready;     // [n_blocks], zeroed
+  };
+  // pass 0: row_of_slot, 1: up_stage_of_slot, 2: block_ready, 3: seg_down
+  void launch_host_plan(const HostPlanParams &p, int pass, cudaStream_t s);
+  // the rows of the segments seg_list[0 .. n_segs): host rows -> particle slots and back
+  void launch_update_state_rows_segs(const uint32_t *seg_list, uint32_t n_segs, uint32_t seg_rows, const uint32_t *ids, const double *state9,
+                                     uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, cudaStream_t s);
+  void launch_pack_state_rows_segs(const uint32_t *seg_list, uint32_t n_segs, uint32_t seg_rows, const uint32_t *ids, uint32_t n,
+                                   const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, double *state9, cudaStream_t s);
+  // the rows of the 128-slot blocks block_list[0 .. n_blocks) written straight into the caller's page-locked host rows
+  // (state9 = device alias of the host buffer): rows of consecutive slots that are consecutive on the host leave as
+  // full 128-byte lines
+  void launch_pack_state_rows_blocks(const uint32_t *block_list, uint32_t n_blocks, const uint32_t *row_of_slot, uint32_t n_owned,
+                                     StateView st, double *state9, cudaStream_t s);
 
   // ---- DEM-MP heat transfer (particle_heat_transfer.cc, multiphysics_integrator.cc) ----
   // effective pair tables of set_multiphysic_properties (particle_particle_contact_force.h:1755-1826)

@@ -219,7 +219,8 @@ namespace dem
       extern __shared__ __align__(16) unsigned char scratch_raw[]; // STEP_WARPS x WarpScratch (may exceed the 48 KB static limit)
       const uint32_t lane = threadIdx.x & 31u;
       WarpScratch &S = reinterpret_cast<WarpScratch *>(scratch_raw)[threadIdx.x >> 5];
-      const uint32_t warp_base = (blockIdx.x * STEP_WARPS + (threadIdx.x >> 5)) * 32u;
+      const uint32_t block = P.block_list ? P.block_list[blockIdx.x] : blockIdx.x; // partial launch: the listed blocks only
+      const uint32_t warp_base = (block * STEP_WARPS + (threadIdx.x >> 5)) * 32u;
       if (warp_base >= P.n_owned)
         return; // whole warp
       // speculative launch: the flag of the steps before this one, read with everything else
@@ -801,7 +802,10 @@ namespace dem
       if (p.n_owned == 0)
         return;
       constexpr uint32_t per_block = 32 * STEP_WARPS;
-      const dim3 block(per_block), grid((p.n_owned + per_block - 1) / per_block);
+      static_assert(per_block == STEP_BLOCK_ROWS, "the streamed host step plans in blocks of STEP_BLOCK_ROWS rows");
+      if (p.block_list && p.n_blocks_listed == 0)
+        return;
+      const dim3 block(per_block), grid(p.block_list ? p.n_blocks_listed : (p.n_owned + per_block - 1) / per_block);
       constexpr size_t smem = sizeof(WarpScratch) * STEP_WARPS;
       auto launch = [&](auto kernel) {
         static bool configured[64] = {}; // per instantiation (the lambda's operator() is a template) and device

@@ -478,6 +478,54 @@ def test_step_host_state_roundtrip_matches_resident():
         b.step_host_state(1, None, rows[:-1].copy())
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_streamed_host_step_is_bitwise_identical(periodic, pinned, monkeypatch):
+    """lethe_dem_step_host_state taken apart over space (rows up slab by slab, partial step launches on the blocks whose
+    neighbours have arrived, rows down as their blocks finish) returns bit for bit the rows of the plain call — over
+    list rebuilds, with host rows in the engine's own order and in a shuffled order (where the plan degenerates to one
+    stage), with walls and across periodic seams; pageable host rows (download through the staging buffer, segment by
+    segment) and page-locked ones (written by the device block by block)."""
+    import torch
+
+    d = 0.005
+    ids, x, props, extent = random_packing(28, d=d, spacing=0.99, jitter=0.06, seed=3)
+    props[:, 3:6] += np.random.default_rng(7).normal(0, 0.2, (len(ids), 3))
+    if periodic:
+        params = packing_parameters(extent, d=d, g=(0, 0, 0), periodic=(1, 1, 1), cell=extent[0] / 14)
+    else:
+        params = packing_parameters(extent, d=d)
+    for shuffled in (False, True, "transfer order"):
+        engines = []
+        for streamed in (False, True):
+            monkeypatch.setenv("LETHE_DEM_HOST_PIPELINE", "1" if streamed else "0")
+            monkeypatch.setenv("LETHE_DEM_HOST_PIPELINE_MIN_ROWS", "1")
+            monkeypatch.setenv("LETHE_DEM_HOST_STAGES", "5")
+            monkeypatch.setenv("LETHE_DEM_HOST_SEG_ROWS", "1024")
+            monkeypatch.setenv("LETHE_DEM_HOST_ZEROCOPY", "1" if pinned else "0")
+            e = abi.load_engine(params.to_config())
+            e.set_particles(ids, x, props)
+            e.step(3)
+            i0, x0, p0 = e.get_particles()  # sorted by id (ids are a random permutation of the lattice sites)
+            if shuffled == "transfer order":
+                order = np.searchsorted(i0, e.get_transfer_order())  # get_particles sorts by id
+                assert sorted(order.tolist()) == list(range(len(i0)))
+            else:
+                order = np.random.default_rng(11).permutation(len(i0)) if shuffled else np.arange(len(i0))
+            rows = np.ascontiguousarray(np.concatenate([x0, p0[:, 3:9]], axis=1)[order])
+            if pinned:
+                keep = torch.from_numpy(rows).pin_memory()
+                rows = keep.numpy()
+            e.step_host_state(1, i0[order], rows)
+            for _ in range(400):
+                e.step_host_state(1, None, rows)
+            engines.append((i0[order], rows.copy(), e.get_stats().n_rebuilds, e.host_pipeline_stats()))
+        (ia, ra, rebuilds_a, pa), (ib, rb, rebuilds_b, pb) = engines
+        assert pa == (0, 0, 0) and pb[0] > 300 and pb[1] >= 2 and pb[2] == (pb[0] if pinned else 0), (pa, pb)
+        assert rebuilds_a == rebuilds_b and rebuilds_a >= 3
+        assert np.array_equal(ia, ib) and np.array_equal(ra, rb)
+
+
 def test_properties_at_scale():
     """Size-independent properties on a 64^3 packing (262k spheres): run-to-run bitwise
     determinism, exact action-reaction (sum of pair forces == 0 up to summation rounding)
