@@ -416,13 +416,11 @@ def main():
     def owned_rows():
         # the host keeps its rows in the order the engine names for the transfer (by cell layer, cell-sorted inside a layer:
         # the kind of order a cell-by-cell walk of ParticleHandler gives), not by particle id
-        ids_, x_, props_ = engine.get_particles()  # sorted by id
-        order = np.searchsorted(ids_, engine.get_transfer_order())
-        state = np.empty((len(ids_), 9))
-        state[:, :3] = x_[order]
-        state[:, 3:] = props_[order, 3:9]
-        del x_, props_
-        return [torch.from_numpy(ids_[order]).pin_memory(), torch.from_numpy(state).pin_memory(), True]
+        n_rows = engine.n_particles()
+        hid = torch.empty(n_rows, dtype=torch.int32).pin_memory()
+        hstate = torch.empty((n_rows, 9), dtype=torch.float64).pin_memory()
+        engine.get_state_rows(hid.numpy().view(np.uint32), hstate.numpy())
+        return [hid, hstate, True]
 
     id_uploads = [0]
 

@@ -285,6 +285,10 @@ int lethe_dem_step_host_state(lethe_dem_ctx *ctx, uint64_t n_steps, uint64_t n,
  * have arrived, so upload and download run side by side almost from the first stage. Any other order is still correct.
  * A host re-reads it when it re-reads its rows (after insertion, or when particles changed owner). */
 int lethe_dem_get_transfer_order(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id);
+/* The same order together with the rows themselves: id[k] and state9[k] = (x, v, omega) of the owned particles, ready to be
+ * handed back to lethe_dem_step_host_state. What a host calls to (re)read the rows it keeps — at the start and whenever
+ * lethe_dem_stats.n_migrated shows that particles changed owner. */
+int lethe_dem_get_state_rows(lethe_dem_ctx *ctx, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *state9);
 /* How often lethe_dem_step_host_state took the streamed form, how many times its plan was made (once per list
  * rebuild or new id table) and how many of the streamed calls wrote the host rows directly from the device. */
 int lethe_dem_host_pipeline_stats(lethe_dem_ctx *ctx, uint64_t *n_streamed_calls, uint64_t *n_plans, uint64_t *n_direct_calls);

@@ -153,6 +153,7 @@ ABI_SYMBOLS = [
     "step_host_state",
     "host_pipeline_stats",
     "get_transfer_order",
+    "get_state_rows",
     "set_external_loads",
     "restart_integration",
     "set_time",
@@ -386,6 +387,16 @@ class Engine:
         out = C.c_uint64()
         self._call("get_transfer_order", C.c_uint64(n), C.byref(out), _ptr(ids, _p_u32))
         return ids[: out.value]
+
+    def get_state_rows(self, ids_out=None, state_out=None):
+        """Ids and (x, v, omega) rows of the owned particles in transfer order (optionally into caller-owned arrays)."""
+        n = self.n_particles()
+        ids = np.empty(n, np.uint32) if ids_out is None else ids_out
+        state = np.empty((n, 9), np.float64) if state_out is None else state_out
+        assert len(ids) >= n and len(state) >= n and ids.dtype == np.uint32 and state.dtype == np.float64
+        out = C.c_uint64()
+        self._call("get_state_rows", C.c_uint64(n), C.byref(out), _ptr(ids, _p_u32), _ptr(state, _p_f64))
+        return ids[: out.value], state[: out.value]
 
     def host_pipeline_stats(self):
         """(calls of step_host_state that took the streamed form, plans made, streamed calls that wrote the host rows directly)."""

@@ -1031,8 +1031,13 @@ namespace
     const int min_rows = env_int("LETHE_DEM_HOST_PIPELINE_MIN_ROWS", 262144);
     if (!wanted || n_steps != 1 || n < uint64_t(std::max(1, min_rows)) || n >= 0xffffffffull)
       return false;
-    if (c->multi.enabled() || c->thermal_enabled || c->n_solids || c->ext_enabled || c->asc_enabled || c->timers_enabled ||
-        c->cfg.store_forces || c->count_touching)
+    if (c->thermal_enabled || c->n_solids || c->ext_enabled || c->asc_enabled || c->timers_enabled || c->cfg.store_forces ||
+        c->count_touching)
+      return false;
+    // several ranks: only the fused-halo form of the step (peer stores + mailbox agreement) can be taken apart, and a
+    // load-balance iteration is a collective decision of its own
+    const bool multi = c->multi.enabled();
+    if (multi && !(c->multi.fused() && c->pipeline && c->lb_method == 0))
       return false;
     if (c->contact_search_trigger || c->clear_history_trigger || c->open_next_step || c->lists[c->cur_list].n_rows != c->n_owned ||
         c->n_owned == 0)
@@ -1045,6 +1050,8 @@ namespace
       {
         if (c->cfg.detection == LETHE_DETECTION_CONSTANT)
           return false;
+        if (multi)
+          return true; // the ranks agree on the flag inside the call (step_host_state_streamed)
         CU_TRY(cudaStreamSynchronize(c->stream));
         if (*c->h_flag)
           return false; // the previous step asked for a new list: the plain call rebuilds
@@ -1181,6 +1188,28 @@ namespace
     c->stage_p.ensure(9 * n);
     c->iteration_number++;
     c->current_time += c->cfg.dt;
+    if (c->multi.enabled())
+      {
+        // the one collective of a step (step_fused_multi): does any rank need a new list? It is also the barrier behind
+        // which the neighbours' halo stores of the previous step are visible.
+        const uint64_t freq = uint64_t(std::max(1, c->cfg.contact_detection_frequency));
+        const bool consult = c->cfg.detection == LETHE_DETECTION_DYNAMIC && (c->iteration_number % freq) == 0;
+        c->multi.post_agree(c, 0u, consult);
+        if (c->multi.wait_agree(c) != 0u)
+          {
+            // plain form of this call: rows up, new list with migration, step, rows down
+            CU_TRY(cudaMemcpyAsync(c->stage_p.p, state9, 9 * n * 8, cudaMemcpyHostToDevice, s));
+            launch_update_state_rows(c->host_row_ids.p, c->stage_p.p, uint32_t(n), c->slot_of_id.p, c->slot_map_size, c->st[c->cur].view(), s);
+            c->multi.rebuild_with_exchange(c);
+            launch_step_kernel(c, PHASE_REGULAR, false);
+            c->contact_search_trigger = false;
+            c->clear_history_trigger = false;
+            launch_pack_state_rows(c->host_row_ids.p, uint32_t(n), c->slot_of_id.p, c->slot_map_size, c->st[c->cur].view(), c->stage_p.p, s);
+            CU_TRY(cudaMemcpyAsync(state9, c->stage_p.p, 9 * n * 8, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));
+            return;
+          }
+      }
     StepParams P;
     fill_step_params(c, PHASE_REGULAR, false, P);
     const StateView out = c->st[c->cur ^ 1].view();
@@ -1980,18 +2009,12 @@ int lethe_dem_step_host_state(lethe_dem_ctx *c, uint64_t n_steps, uint64_t n, co
   });
 }
 
-int lethe_dem_get_transfer_order(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *id)
+namespace
 {
-  return guarded(c, [&] {
-    const size_t n = c->n_owned;
-    *n_out = n;
-    if (n_max < n || n == 0)
-      return;
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    std::vector<uint32_t> ids(n);
-    std::vector<int32_t> cell(n);
-    CU_TRY(cudaMemcpy(ids.data(), c->st[c->cur].id.p, n * 4, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(cell.data(), c->st[c->cur].cell_reg.p, n * 4, cudaMemcpyDeviceToHost));
+  // perm[k] = slot of row k of the transfer order (by cell layer along the axis with the most layers of this rank's part
+  // of the grid, cell-sorted inside a layer), left in c->host_pipe.row_of_slot's sibling buffer `perm`
+  void transfer_order(Ctx *c, DevBuf<uint32_t> &perm)
+  {
     const GridDesc &g = c->grid;
     int axis = 0, best = 0;
     for (int d = 0; d < 3; ++d)
@@ -2000,19 +2023,42 @@ int lethe_dem_get_transfer_order(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_o
         if (layers > best)
           best = layers, axis = d;
       }
-    auto layer_of = [&](int32_t cl) -> uint32_t {
-      if (cl < 0)
-        return 0u; // not registered in a cell yet (inserted since the last sort): first
-      return 1u + uint32_t(axis == 0 ? cl % g.n[0] : (axis == 1 ? (cl / g.n[0]) % g.n[1] : cl / (g.n[0] * g.n[1])));
-    };
-    // stable counting sort of the slots by layer: inside a layer the engine's cell-sorted order is kept
-    std::vector<uint64_t> start(size_t(g.n[axis]) + 2, 0);
-    for (size_t q = 0; q < n; ++q)
-      ++start[layer_of(cell[q]) + 1];
-    for (size_t l = 1; l < start.size(); ++l)
-      start[l] += start[l - 1];
-    for (size_t q = 0; q < n; ++q)
-      id[start[layer_of(cell[q])]++] = ids[q];
+    perm.ensure(std::max<size_t>(c->n_owned, 1));
+    transfer_order_perm(c->st[c->cur].cell_reg.p, g, axis, c->n_owned, perm.p, c->stream);
+  }
+} // namespace
+
+int lethe_dem_get_transfer_order(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *id)
+{
+  return guarded(c, [&] {
+    const size_t n = c->n_owned;
+    *n_out = n;
+    if (n_max < n || n == 0)
+      return;
+    DevBuf<uint32_t> perm;
+    transfer_order(c, perm);
+    c->stage_ids.ensure(n);
+    launch_pack_state_rows_perm(perm.p, uint32_t(n), c->st[c->cur].view(), c->st[c->cur].id.p, c->stage_ids.p, nullptr, c->stream);
+    CU_TRY(cudaMemcpyAsync(id, c->stage_ids.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int lethe_dem_get_state_rows(lethe_dem_ctx *c, uint64_t n_max, uint64_t *n_out, uint32_t *id, double *state9)
+{
+  return guarded(c, [&] {
+    const size_t n = c->n_owned;
+    *n_out = n;
+    if (n_max < n || n == 0)
+      return;
+    DevBuf<uint32_t> perm;
+    transfer_order(c, perm);
+    c->stage_ids.ensure(n);
+    c->stage_p.ensure(9 * n);
+    launch_pack_state_rows_perm(perm.p, uint32_t(n), c->st[c->cur].view(), c->st[c->cur].id.p, c->stage_ids.p, c->stage_p.p, c->stream);
+    CU_TRY(cudaMemcpyAsync(id, c->stage_ids.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(state9, c->stage_p.p, 9 * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
   });
 }
 

@@ -18,6 +18,8 @@
 #include <atomic>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh> // host-side plumbing only (transfer_order_perm); no step or rebuild kernel uses it
+
 #include "dem_kernels.cuh"
 
 namespace dem
@@ -879,6 +881,38 @@ namespace dem
         }
     }
 
+    __global__ void __launch_bounds__(256) k_layer_keys(const int32_t *cell_reg, GridDesc g, int axis, uint32_t n, uint16_t *keys, uint32_t *vals)
+    {
+      const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+      if (q >= n)
+        return;
+      const int cell = cell_reg[q];
+      int layer = 0;
+      if (cell >= 0)
+        layer = 1 + (axis == 0 ? cell % g.n[0] : (axis == 1 ? (cell / g.n[0]) % g.n[1] : cell / (g.n[0] * g.n[1])));
+      keys[q] = uint16_t(min(layer, 65535));
+      vals[q] = q;
+    }
+
+    __global__ void __launch_bounds__(256) k_pack_state_rows_perm(const uint32_t *perm, uint32_t n, StateView st, const uint32_t *id,
+                                                                  uint32_t *ids_out, double *state9)
+    {
+      const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= n)
+        return;
+      const uint32_t q = perm[k];
+      const double4 x = st.pos[q], v = st.vel[q], w = st.omg[q];
+      if (ids_out)
+        ids_out[k] = id[q];
+      if (state9)
+        {
+          double *p = state9 + 9 * size_t(k);
+          p[0] = x.x, p[1] = x.y, p[2] = x.z;
+          p[3] = v.x, p[4] = v.y, p[5] = v.z;
+          p[6] = w.x, p[7] = w.y, p[8] = w.z;
+        }
+    }
+
     __device__ __forceinline__ void write_row(double4 x, double4 v, double4 w, double *x3, double *props9, size_t k)
     {
       x3[3 * k] = x.x;
@@ -1531,6 +1565,42 @@ namespace dem
       {
         k_pack_state_rows_segs<<<dim3(blocks_for(seg_rows, 256), n_segs), 256, 0, s>>>(seg_list, seg_rows, ids, n, slot_of_id, slot_map_size,
                                                                                       st, state9);
+        count_launch();
+      }
+  }
+  void transfer_order_perm(const int32_t *cell_reg, GridDesc grid, int axis, uint32_t n, uint32_t *perm, cudaStream_t s)
+  {
+    if (!n)
+      return;
+    uint16_t *keys = nullptr, *keys_out = nullptr;
+    uint32_t *vals = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    auto check = [](cudaError_t e) {
+      if (e != cudaSuccess)
+        throw std::runtime_error(std::string("transfer_order_perm: ") + cudaGetErrorString(e));
+    };
+    check(cudaMalloc(&keys, size_t(n) * 2));
+    check(cudaMalloc(&keys_out, size_t(n) * 2));
+    check(cudaMalloc(&vals, size_t(n) * 4));
+    k_layer_keys<<<blocks_for(n, 256), 256, 0, s>>>(cell_reg, grid, axis, n, keys, vals);
+    count_launch();
+    // LSD radix sort: stable, so the cell-sorted slot order survives inside a layer
+    check(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, perm, int(n), 0, 16, s));
+    check(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+    check(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, perm, int(n), 0, 16, s));
+    check(cudaStreamSynchronize(s));
+    cudaFree(tmp);
+    cudaFree(vals);
+    cudaFree(keys_out);
+    cudaFree(keys);
+  }
+  void launch_pack_state_rows_perm(const uint32_t *perm, uint32_t n, StateView st, const uint32_t *id, uint32_t *ids_out, double *state9,
+                                   cudaStream_t s)
+  {
+    if (n)
+      {
+        k_pack_state_rows_perm<<<blocks_for(n, 256), 256, 0, s>>>(perm, n, st, id, ids_out, state9);
         count_launch();
       }
   }

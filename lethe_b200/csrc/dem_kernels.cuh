@@ -195,6 +195,12 @@ namespace dem
                                      uint32_t n, const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, cudaStream_t s);
   void launch_pack_state_rows_segs(const uint32_t *seg_list, uint32_t n_segs, uint32_t seg_rows, const uint32_t *ids, uint32_t n,
                                    const uint32_t *slot_of_id, uint32_t slot_map_size, StateView st, double *state9, cudaStream_t s);
+  // Transfer order of the owned slots (lethe_dem_get_transfer_order): stable sort by cell layer along `axis` (slots not
+  // registered in a cell first), the engine's cell-sorted order kept inside a layer. perm[k] = slot of row k.
+  void transfer_order_perm(const int32_t *cell_reg, GridDesc grid, int axis, uint32_t n, uint32_t *perm, cudaStream_t s);
+  // ids and (x, v, omega) rows of the slots perm[0 .. n), in that order
+  void launch_pack_state_rows_perm(const uint32_t *perm, uint32_t n, StateView st, const uint32_t *id, uint32_t *ids_out, double *state9,
+                                   cudaStream_t s);
   // the rows of the 128-slot blocks block_list[0 .. n_blocks) written straight into the caller's page-locked host rows
   // (state9 = device alias of the host buffer): rows of consecutive slots that are consecutive on the host leave as
   // full 128-byte lines

@@ -161,6 +161,50 @@ def two_processor_golden(rank, world, local_rank):
     return bool(flag.item())
 
 
+def host_streamed_case(rank, world, local_rank):
+    """lethe_dem_step_host_state on every rank of a slab-decomposed periodic box, one DEM step per call with the rank's
+    host rows in the engine's transfer order: the streamed form (upload stages, partial step launches with the fused halo
+    push, download under the upload; a call in which the ranks agree on a new list runs plain) returns bit for bit the
+    rows of the plain form, through list rebuilds and migration."""
+    w = workloads.periodic_box(cells=(max(16, 6 * world), 10, 10), spacing=1.0, jitter=0.03, vel_sigma=0.5)
+    w.params.dynamic_contact_search_factor = 0.4
+    w.props[:, 3] += 8.0  # the whole packing drifts along the slab axis: particles change owner at the rebuilds
+    finals = []
+    for streamed in (False, True):
+        os.environ["LETHE_DEM_HOST_PIPELINE"] = "1" if streamed else "0"
+        os.environ["LETHE_DEM_HOST_PIPELINE_MIN_ROWS"] = "1"
+        os.environ["LETHE_DEM_HOST_STAGES"] = "3"
+        os.environ["LETHE_DEM_HOST_SEG_ROWS"] = "256"
+        eng, _ = multi.create_slab_engine(w, rank, world, local_rank, dist, balanced=False)
+        eng.step(2)
+
+        def rows_now():
+            ids, rows = eng.get_state_rows()
+            return ids, rows, True
+
+        ids, rows, fresh = rows_now()
+        seen = eng.get_stats().n_migrated
+        for _ in range(150):
+            eng.step_host_state(1, ids if fresh else None, rows)
+            fresh = False
+            now = eng.get_stats().n_migrated
+            if now != seen:  # particles changed owner: the rank re-reads the rows it owns
+                ids, rows, fresh = rows_now()
+                seen = now
+        st = eng.get_stats()
+        finals.append((eng.get_particles(), st.n_rebuilds, st.n_migrated, eng.host_pipeline_stats()))
+        eng.close()
+    for k in ("LETHE_DEM_HOST_PIPELINE", "LETHE_DEM_HOST_PIPELINE_MIN_ROWS", "LETHE_DEM_HOST_STAGES", "LETHE_DEM_HOST_SEG_ROWS"):
+        os.environ.pop(k, None)
+    (pa, ra, ma, sa), (pb, rb, mb, sb) = finals
+    same = all(np.array_equal(u, v) for u, v in zip(pa, pb)) and ra == rb and ma == mb
+    ok = same and sa[0] == 0 and sb[0] > 50 and ra >= 3 and ma > 0
+    print(f"[host-streamed] rank {rank}: rows identical {same}, rebuilds {ra}/{rb}, migrated {ma}/{mb}, streamed calls {sb[0]} of 150, plans {sb[1]}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -220,6 +264,7 @@ def main():
     ok &= run_case("sparse-contacts", w, (15, 45), rank, world, local_rank, tol=(1e-11, 1e-8))
     # the same bed with the load balanced by mobility-weighted particle counts
     ok &= run_case("sparse-contacts-lb", w, (15, 45), rank, world, local_rank, tol=(1e-11, 1e-8), load_balance=("dynamic_with_sparse_contacts", 0.05, 5))
+    ok &= host_streamed_case(rank, world, local_rank)
     if world == 2:
         ok &= two_processor_golden(rank, world, local_rank)
     dist.destroy_process_group()

@@ -508,8 +508,11 @@ def test_streamed_host_step_is_bitwise_identical(periodic, pinned, monkeypatch):
             e.step(3)
             i0, x0, p0 = e.get_particles()  # sorted by id (ids are a random permutation of the lattice sites)
             if shuffled == "transfer order":
-                order = np.searchsorted(i0, e.get_transfer_order())  # get_particles sorts by id
+                ids_t, rows_t = e.get_state_rows()
+                assert np.array_equal(ids_t, e.get_transfer_order())
+                order = np.searchsorted(i0, ids_t)  # get_particles sorts by id
                 assert sorted(order.tolist()) == list(range(len(i0)))
+                assert np.array_equal(rows_t, np.concatenate([x0, p0[:, 3:9]], axis=1)[order])
             else:
                 order = np.random.default_rng(11).permutation(len(i0)) if shuffled else np.arange(len(i0))
             rows = np.ascontiguousarray(np.concatenate([x0, p0[:, 3:9]], axis=1)[order])
