@@ -25,7 +25,9 @@ value     whole-job particle-steps/s with state resident in HBM (CUDA events on 
           stream, max over ranks), rebuilds included
 e2e       the same through lethe_dem_step_host_state on every rank: pinned HOST rows (x, v, omega)
           of the owned particles uploaded, ONE DEM step, rows downloaded, every DEM step (the
-          reference-facing per-step plugin call; PCIe-bound)
+          reference-facing per-step plugin call; PCIe-bound). The host keeps its rows in the
+          engine's transfer order (lethe_dem_get_state_rows, re-read when particles change owner), so
+          the call streams: upload, partial step launches and download overlap
 roofline  fused step kernel: algorithmic bytes (160+16+4*C+48*T per particle-step,
           C,T measured in this run) / CUDA-event kernel time, against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample, 1 core
@@ -411,8 +413,9 @@ def main():
     # ---- e2e: per-step plugin call with pinned host rows ----
     # Every rank keeps host rows of the particles it owns — what a step changes: x, v, omega, 72 B
     # per particle — and hands them to lethe_dem_step_host_state every DEM step (rows up, one step,
-    # rows down). The row -> id table goes up with the first call and again whenever particles changed
-    # owner in a rebuild (the rank then re-reads its owned rows, inside the timed region).
+    # rows down; 2 x 72 B per particle cross PCIe inside the timed region, every step). The row -> id
+    # table goes up with the first call and again whenever particles changed owner in a rebuild (the
+    # rank then re-reads its owned rows with lethe_dem_get_state_rows, inside the timed region).
     def owned_rows():
         # the host keeps its rows in the order the engine names for the transfer (by cell layer, cell-sorted inside a layer:
         # the kind of order a cell-by-cell walk of ParticleHandler gives), not by particle id
@@ -471,7 +474,8 @@ def main():
         "pcie_gbs_per_direction_if_copy_bound": (h2d + per_step * 72) / world / (dt / max(1, e2e_steps)) / 1e9,
         "host_placement": numa,
         "call": "lethe_dem_step_host_state(n_steps=1) on every rank: upload the x/v/omega rows of the owned particles (72 B each; "
-                "the id table only when ownership changed), 1 DEM step, download the rows, every DEM step",
+                "the id table only when ownership changed), 1 DEM step, download the rows, every DEM step; page-locked rows in the "
+                "engine's transfer order, streamed (upload / partial step launches / download overlapped) when streamed_calls > 0",
         "batched": {"steps_per_call": S, "value": n_global * S / dtb, "unit": "particle-steps/s"},
         # rank 0's calls that ran as upload / partial step launches / download pipelined over the rows
         "streamed_calls": streamed[0], "stream_plans": streamed[1],
