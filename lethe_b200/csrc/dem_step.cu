@@ -596,7 +596,11 @@ namespace dem
       const ParticleView me = make_view(pi, vi, wi);
 
       // ---------------- particle-wall contacts ----------------
+#ifdef DEM_EXPERIMENT_NOWALLS
+      const uint32_t w0 = 0, w1 = 0; // register-pressure experiment only (wrong physics)
+#else
       const uint32_t w0 = S.w0[lane], w1 = S.w1[lane];
+#endif
       for (uint32_t w = w0; w < w1; ++w)
         {
           const uint32_t we = P.walls.entry[w];
