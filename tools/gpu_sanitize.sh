@@ -25,6 +25,29 @@ for pp, rolling, periodic, asc in [("hertz_mindlin_limit_overlap", "constant", (
     e.synchronize_velocities()
     _, xx, _ = e.get_particles()
     print(pp, rolling, periodic, asc, "ok", e.get_stats().n_rebuilds, float(np.abs(xx).max()))
+# the streamed host step (upload stages, partial step launches through block lists, segment download) and the
+# device-side transfer order, with pageable rows and with page-locked rows written by the device
+import os
+import torch
+os.environ.update(LETHE_DEM_HOST_PIPELINE_MIN_ROWS="1", LETHE_DEM_HOST_STAGES="3", LETHE_DEM_HOST_SEG_ROWS="256")
+for periodic, zero_copy in [((0, 0, 0), False), ((1, 1, 1), True)]:
+    os.environ["LETHE_DEM_HOST_ZEROCOPY"] = "1" if zero_copy else "0"
+    ids, x, props, extent = random_packing(14, d=d, spacing=0.99, jitter=0.06, seed=3)
+    props[:, 3:6] += np.random.default_rng(7).normal(0, 0.2, (len(ids), 3))
+    p = packing_parameters(extent, d=d, g=(0, 0, 0) if periodic[0] else (0, 0, -9.81), periodic=periodic, cell=extent[0] / 7)
+    e = abi.load_engine(p.to_config())
+    if not periodic[0]:
+        e.set_walls(box_wall_faces(p.mesh, p.outlet_boundaries, p.periodic))
+    e.set_particles(ids, x, props)
+    e.step(3)
+    rid, rows = e.get_state_rows()
+    if zero_copy:
+        keep = torch.from_numpy(rows).pin_memory()
+        rows = keep.numpy()
+    e.step_host_state(1, rid, rows)
+    for _ in range(60):
+        e.step_host_state(1, None, rows)
+    print("streamed host step", periodic, zero_copy, "ok", e.get_stats().n_rebuilds, e.host_pipeline_stats(), float(np.abs(rows).max()))
 P
 for tool in memcheck racecheck initcheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_case.py > gpurun_out/sanitizer_${tool}_$S.log 2>&1; echo "$tool rc=$?"
