@@ -419,13 +419,18 @@ def main():
     def owned_rows():
         # the host keeps its rows in the order the engine names for the transfer (by cell layer, cell-sorted inside a layer:
         # the kind of order a cell-by-cell walk of ParticleHandler gives), not by particle id
+        # page-locked once, with head-room for the rows that migrate in: a re-read fills the same buffers
         n_rows = engine.n_particles()
-        hid = torch.empty(n_rows, dtype=torch.int32).pin_memory()
-        hstate = torch.empty((n_rows, 9), dtype=torch.float64).pin_memory()
+        if pinned["cap"] < n_rows:
+            pinned["cap"] = int(n_rows * 1.03) + 1024
+            pinned["ids"] = torch.empty(pinned["cap"], dtype=torch.int32).pin_memory()
+            pinned["state"] = torch.empty((pinned["cap"], 9), dtype=torch.float64).pin_memory()
+        hid, hstate = pinned["ids"][:n_rows], pinned["state"][:n_rows]
         engine.get_state_rows(hid.numpy().view(np.uint32), hstate.numpy())
         return [hid, hstate, True]
 
     id_uploads = [0]
+    pinned = {"cap": 0, "ids": None, "state": None}
 
     def host_step(rows, n_steps, migrated_seen):
         hid, hstate, fresh = rows
@@ -438,7 +443,9 @@ def main():
                 return owned_rows(), r
         return rows, migrated_seen
 
-    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else (30 if n_local <= 4_000_000 else 6)
+    # as many DEM steps as one bench step (100): the leg then holds the list rebuilds (and, at N > 1, the migrations with
+    # the re-read of the owned rows) the per-step call meets in steady state, not a lucky window between two of them
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else S
     rows = owned_rows()
     seen = engine.get_stats().n_migrated
     for _ in range(3):
