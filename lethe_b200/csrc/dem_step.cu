@@ -54,7 +54,7 @@ namespace dem
     constexpr int QUEUE = DEM_QUEUE; // touching entries a warp can queue before it has to drain (>= 32 * SWEEP)
     constexpr int RES_SLOTS = 64;  // evaluated pairs buffered per warp before the owners add them up (2 rounds)
 #ifndef DEM_SWEEP
-#define DEM_SWEEP 4
+#define DEM_SWEEP 3 // with 256-bit row accesses three gathers in flight per lane beat four (fewer spills at the 128-register cap): 1 M drum 0.316 / 0.278 / 0.2715 / 0.291 ms for 1 / 2 / 3 / 4
 #endif
 #ifndef DEM_MIN_BLOCKS
 #define DEM_MIN_BLOCKS 4
