@@ -17,8 +17,9 @@
 //     deterministic, the same sequence of additions as a serial walk of the row;
 //   * walls, integrator and the displacement trigger run per owner lane afterwards.
 // Measured dead ends (profiles/): prefetching the round operands at the start
-// of the previous round, cp.async staging of the next round, deeper or shallower sweep
-// pipelines (SWEEP 2 / 8), 3 / 5 / 6 resident blocks per SM, a 256-slot queue, reading
+// of the previous round, cp.async staging of the next or of the current round (DEM_STAGE), a deeper sweep
+// pipeline (SWEEP 8; with 128-bit accesses 4 was the optimum, with 256-bit accesses it is 3), 3 / 5 / 6 resident
+// blocks per SM, a 256-slot queue, evict-first hints on the list streams (DEM_STREAM), reading
 // neighbours that belong to the warp's own 32 rows from shared memory instead of through L1
 // (+6 %: divergence costs more than the gathers), an L2 persisting access-policy window on the
 // position array being gathered (+10 %) — the kernel is bound by the issue latency
